@@ -1,0 +1,155 @@
+"""Golden vectors for GraphDistribution and the MPNN nets, from the UNMODIFIED reference behind oracle/shims.
+Called by oracle/gen_golden.py. TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import numpy as np
+import torch
+
+import ref_loader
+
+
+@contextlib.contextmanager
+def injected_rand(u):
+    orig = torch.rand
+
+    def fake(*size, **k):
+        shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        assert shape == tuple(u.shape), (shape, u.shape)
+        return u.clone()
+
+    torch.rand = fake
+    try:
+        yield
+    finally:
+        torch.rand = orig
+
+
+def dense_source_graph(g, K, extra):
+    """Every node 0..K-1 has >=1 out-edge (ring) plus `extra` random edges, shuffled: the only kind of graph the
+    literal GraphDistribution accepts (sources must be exactly 0..K-1)."""
+    src = torch.cat([torch.arange(K), torch.randint(0, K, (extra,), generator=g)])
+    dst = torch.cat([(torch.arange(K) + 1) % K, torch.randint(0, K, (extra,), generator=g)])
+    perm = torch.randperm(src.numel(), generator=g)
+    return torch.stack([src[perm], dst[perm]])
+
+
+def gen_graph_distribution(out):
+    rl = ref_loader.load("src.reinforcement_learning")
+    cases = {}
+    # known-answer case from SURVEY.md §8c(4): 3-node ring
+    ei = torch.tensor([[0, 0, 1, 1, 2, 2], [1, 2, 2, 0, 0, 1]])
+    logits = torch.tensor([0.0, 1.0, 2.0, 0.0, -1.0, 1.0])
+    cases["ring3"] = (ei, logits, 1.0)
+    g = torch.Generator().manual_seed(11)
+    ei = dense_source_graph(g, 23, 60)
+    cases["rand1d"] = (ei, torch.randn(ei.size(1), generator=g) * 2, 1.0)
+    ei = dense_source_graph(g, 17, 40)
+    cases["rand2d"] = (ei, torch.randn(5, ei.size(1), generator=g) * 3, 0.7)
+    ei = dense_source_graph(g, 9, 0)                      # every group has exactly one edge
+    cases["single"] = (ei, torch.randn(ei.size(1), generator=g), 1.0)
+    blob = {}
+    for name, (ei, logits, temp) in cases.items():
+        lg = logits.clone().requires_grad_(True)
+        d = rl.GraphDistribution(lg, ei, temperature=temp)
+        K = d.nb_nodes
+        stable = torch.equal(d.index, torch.sort(ei[0], stable=True)[1])
+        mode = d.mode.clone()
+        if logits.dim() == 1:
+            u = torch.rand(K, generator=g)
+            with injected_rand(u):
+                action = d.sample()
+        else:
+            # Batched sampling AND batched `mode` are broken in the reference (r_bsum slices the batch axis,
+            # src/reinforcement_learning.py:73; `n = arange(B).repeat(K).view(B,K)` scrambles rows, :51-53).
+            # Declared divergence D7: the batched contract is "row b behaves like the 1-D distribution of logits[b]",
+            # so the golden action/mode rows come from the reference's own 1-D code path, row by row.
+            u = torch.rand(logits.size(0), K, generator=g)
+            rows_a, rows_m = [], []
+            for b in range(logits.size(0)):
+                db = rl.GraphDistribution(logits[b], ei, temperature=temp)
+                assert torch.equal(db.index, d.index)
+                with injected_rand(u[b]):
+                    rows_a.append(db.sample())
+                rows_m.append(db.mode.clone())
+            action, mode = torch.stack(rows_a), torch.stack(rows_m)
+        lp = d.log_prob(action)
+        ent = d.entropy()
+        wl, we = torch.randn(lp.shape, generator=g), torch.randn(ent.shape, generator=g)
+        ((lp * wl).sum() + (ent * we).sum()).backward()
+        bad = action.clone()
+        first = int(torch.nonzero(bad.reshape(-1, bad.size(-1))[0])[0])
+        bad.reshape(-1, bad.size(-1))[0, first] = 0        # drop one selection -> impossible action
+        lp_bad = d.log_prob(bad)
+        blob.update({f"{name}.{k}": v for k, v in dict(
+            edge_index=ei.numpy(), logits=logits.numpy(), temperature=np.float64(temp), proba=d.proba.detach().numpy(),
+            mode=mode.numpy(), u=u.numpy(), sort_index=d.index.numpy(), action=action.numpy(), stable_sort=np.bool_(stable),
+            log_prob=lp.detach().numpy(), entropy=ent.detach().numpy(), w_lp=wl.numpy(), w_ent=we.numpy(),
+            grad_logits=lg.grad.numpy(), bad_action=bad.numpy(), log_prob_bad=lp_bad.detach().numpy()).items()})
+        print(f"graphdist {name}: K={K} E={ei.size(1)} entropy={ent.detach().flatten()[:2].tolist()} stable_sort={stable}")
+    np.savez_compressed(os.path.join(out, "mpnn_graphdist.npz"), **blob)
+
+
+def _small_net_inputs(g, N, E, A, B=None):
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+    lead = () if B is None else (B,)
+    nf = torch.rand(*lead, N, 7, generator=g) * 5
+    nf[..., 6] = torch.arange(N).float()                       # ROAD_INDEX >= 0 everywhere (literal reference runs)
+    nf[..., 1] = torch.randint(0, 9, (*lead, N), generator=g).float()
+    ef = torch.rand(*lead, E, 1, generator=g)
+    ai = torch.randint(0, A + 1, (*lead, N), generator=g)
+    tm = torch.rand(*lead, 1, generator=g) * 10
+    af = torch.rand(A + 1, 9, generator=g) * 3
+    return ei, nf, ef, ai, tm, af
+
+
+def gen_nets(out):
+    mp = ref_loader.load("src.agents.mpnn_agent")
+    g = torch.Generator().manual_seed(21)
+    blob = {}
+    for tag, B in (("u", None), ("b", 3)):
+        N, E, A = 14, 37, 20
+        ei, nf, ef, ai, tm, af = _small_net_inputs(g, N, E, A, B)
+        torch.manual_seed(5)
+        # --- MPNNValueNet (eval mode: dropout off)
+        net = mp.MPNNValueNet(ei, N, "cpu")
+        net.agent_features = af
+        net.eval()
+        v = net(nf, ef, ai, tm)
+        wv = torch.randn(v.shape, generator=g)
+        (v * wv).sum().backward()
+        sd = {k: p.detach().clone() for k, p in net.named_parameters()}
+        gr = {k: p.grad.clone() for k, p in net.named_parameters()}
+        blob.update({f"value.{tag}.{k}": t.numpy() for k, t in dict(
+            edge_index=ei, node_features=nf, edge_features=ef, agent_index=ai, time=tm, agent_features=af,
+            out=v.detach(), w_out=wv).items()})
+        blob.update({f"value.{tag}.param.{k}": t.numpy() for k, t in sd.items()})
+        blob.update({f"value.{tag}.grad.{k}": t.numpy() for k, t in gr.items()})
+        # --- MPNNValueNetSimple
+        net = mp.MPNNValueNetSimple(ei, N, "cpu")
+        v = net(nf, ef, ai, tm)
+        wv = torch.randn(v.shape, generator=g)
+        (v * wv).sum().backward()
+        blob.update({f"simple.{tag}.out": v.detach().numpy(), f"simple.{tag}.w_out": wv.numpy()})
+        blob.update({f"simple.{tag}.param.{k}": p.detach().numpy() for k, p in net.named_parameters()})
+        blob.update({f"simple.{tag}.grad.{k}": p.grad.numpy() for k, p in net.named_parameters()})
+        # --- MPNNPolicyNet (active path = embedding of ROAD_INDEX gathered at edge targets)
+        ff = torch.rand(E, generator=g) + 0.5
+        net = mp.MPNNPolicyNet(ei, N, ff, "cpu")
+        net.agent_features = af
+        lg = net(nf, ef, ai)
+        wl = torch.randn(lg.shape, generator=g)
+        (lg * wl).sum().backward()
+        blob.update({f"policy.{tag}.out": lg.detach().numpy(), f"policy.{tag}.w_out": wl.numpy(),
+                     f"policy.{tag}.emb": net.nodes_embedding.weight.detach().numpy(),
+                     f"policy.{tag}.grad_emb": net.nodes_embedding.weight.grad.numpy(),
+                     f"policy.{tag}.param_names": np.array(sorted(k for k, _ in net.named_parameters()))})
+        print(f"nets {tag}: value={v.detach().flatten().tolist()[:2]} logits[:3]={lg.detach().flatten()[:3].tolist()}")
+    np.savez_compressed(os.path.join(out, "mpnn_nets.npz"), **blob)
+
+
+def main(out):
+    gen_graph_distribution(out)
+    gen_nets(out)

@@ -1,0 +1,133 @@
+"""Pins the CPU oracle (oracle/core_port.py, oracle/mpnn_port.py) against golden vectors that were produced by the
+UNMODIFIED reference (oracle/gen_golden.py) and — when /root/reference is present — against the live reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import core_port
+import mpnn_port
+import ref_loader
+
+CORE_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "core_*.npz")))
+
+
+def replay_core_case(d, step_fn):
+    """Replay a golden trajectory with `step_fn(x, ei, w, t, Nmax, u, cc) -> dict(delta_tt, pop)`; bit-exact asserts."""
+    x = torch.from_numpy(d["x0"]).clone()
+    ei, w = torch.from_numpy(d["edge_index"]), torch.from_numpy(d["edge_attr"])
+    Nmax = int(d["Nmax"])
+    c = core_port.Cols(Nmax)
+    cc = core_port.static_factors(x, c)[1] if bool(d["use_static"]) else None
+    for s in range(len(d["t"])):
+        x[:, c.SEL] = torch.from_numpy(d["sel"][s])
+        out = step_fn(x, ei, w, float(d["t"][s]), Nmax, torch.from_numpy(d["u"][s]), cc)
+        assert torch.equal(x, torch.from_numpy(d["x"][s])), f"x differs after step {s}"
+        assert torch.equal(out["delta_tt"], torch.from_numpy(d["delta_tt"][s]))
+        assert (out["pop"] is not None) == bool(d["has_pop"][s])
+        if out["pop"] is not None:
+            assert torch.equal(out["pop"], torch.from_numpy(d["pop"][s]))
+
+
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_port_matches_reference_goldens(name, golden_dir):
+    assert CORE_CASES, "golden vectors missing"
+    replay_core_case(np.load(os.path.join(golden_dir, name + ".npz")), core_port.core_step)
+
+
+def test_braess_known_answer(golden_dir):
+    """on the reference's braess fixture one core step changes exactly three cells."""
+    d = np.load(os.path.join(golden_dir, "core_braess.npz"))
+    x0, x1 = d["x0"], d["x"][0]
+    changed = np.argwhere(x0 != x1)
+    assert changed.tolist() == [[0, 201], [1, 201], [2, 202]]
+    assert x1[0, 201] == np.float32(3.2704544067382812)
+    assert x1[1, 201] == np.float32(1.0906565189361572)
+    assert x1[2, 202] == np.float32(1.199722170829773)
+    assert not d["has_pop"].any() and (d["delta_tt"][0] == 0).all()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference (authoring container only)")
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_core_port_matches_live_reference(seed):
+    import gen_golden
+    g = torch.Generator().manual_seed(seed)
+    N, Nmax = 150, 12
+    ei, w = cases.random_dual_graph(g, N, 5, sort_by_source=bool(seed % 2))
+    x0, _ = cases.random_road_state(g, N, Nmax, 50.0, ei)
+    g2 = torch.Generator().manual_seed(seed + 1)
+    rec = gen_golden.reference_core_trajectory(x0, ei, w, Nmax, 50.0, 6, g2, use_static=True)
+    x = x0.clone()
+    c = core_port.Cols(Nmax)
+    cc = core_port.static_factors(x, c)[1]
+    for s in range(6):
+        x[:, c.SEL] = rec["sel"][s]
+        out = core_port.core_step(x, ei, w, rec["t"][s], Nmax, rec["u"][s], cc)
+        assert torch.equal(x, rec["x"][s])
+        assert torch.equal(out["delta_tt"], rec["delta_tt"][s])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+GD_CASES = ["ring3", "rand1d", "rand2d", "single"]
+
+
+@pytest.mark.parametrize("name", GD_CASES)
+def test_graph_distribution_port(name, golden_dir):
+    z = np.load(os.path.join(golden_dir, "mpnn_graphdist.npz"))
+    g = lambda k: torch.from_numpy(z[f"{name}.{k}"])
+    lg = g("logits").clone().requires_grad_(True)
+    d = mpnn_port.GraphDistributionPort(lg, g("edge_index"), float(z[f"{name}.temperature"]), sort_index=g("sort_index"))
+    torch.testing.assert_close(d.proba.detach(), g("proba"), rtol=1e-6, atol=1e-7)
+    assert torch.equal(d.mode, g("mode"))
+    if lg.dim() == 1:
+        assert torch.equal(d.sample(g("u")), g("action"))
+    lp, ent = d.log_prob(g("action")), d.entropy()
+    torch.testing.assert_close(lp.detach(), g("log_prob"), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(ent.detach(), g("entropy"), rtol=1e-6, atol=1e-6)
+    ((lp * g("w_lp")).sum() + (ent * g("w_ent")).sum()).backward()
+    torch.testing.assert_close(lg.grad, g("grad_logits"), rtol=1e-5, atol=1e-6)
+    assert torch.equal(d.log_prob(g("bad_action")).detach(), g("log_prob_bad"))
+    # stable order (the contract) gives the same group-wise quantities as the reference's unstable order
+    d2 = mpnn_port.GraphDistributionPort(g("logits"), g("edge_index"), float(z[f"{name}.temperature"]))
+    torch.testing.assert_close(d2.entropy(), g("entropy"), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(d2.log_prob(g("action")), g("log_prob"), rtol=1e-6, atol=1e-6)
+
+
+def test_graph_distribution_known_answer(golden_dir):
+    """SURVEY.md §8c(4)."""
+    z = np.load(os.path.join(golden_dir, "mpnn_graphdist.npz"))
+    assert abs(float(z["ring3.entropy"][0]) - 1.3129) < 1e-4
+    assert z["ring3.mode"].tolist() == [0, 1, 1, 0, 0, 1]
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
+def test_nets_port(tag, golden_dir):
+    z = np.load(os.path.join(golden_dir, "mpnn_nets.npz"))
+    g = lambda k: torch.from_numpy(z[k])
+    ei = g(f"value.{tag}.edge_index")
+    nf, ef, ai, tm, af = (g(f"value.{tag}.{k}") for k in ("node_features", "edge_features", "agent_index", "time", "agent_features"))
+    # MPNNValueNet
+    names = [k[len(f"value.{tag}.param."):] for k in z.files if k.startswith(f"value.{tag}.param.")]
+    p = {k: g(f"value.{tag}.param.{k}").clone().requires_grad_(True) for k in names}
+    v = mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei)
+    torch.testing.assert_close(v.detach(), g(f"value.{tag}.out"), rtol=1e-5, atol=1e-6)
+    (v * g(f"value.{tag}.w_out")).sum().backward()
+    for k in names:
+        torch.testing.assert_close(p[k].grad, g(f"value.{tag}.grad.{k}"), rtol=1e-4, atol=1e-6)
+    # MPNNValueNetSimple
+    names = [k[len(f"simple.{tag}.param."):] for k in z.files if k.startswith(f"simple.{tag}.param.")]
+    p = {k: g(f"simple.{tag}.param.{k}").clone().requires_grad_(True) for k in names}
+    v = mpnn_port.value_simple_forward(p, nf, tm)
+    torch.testing.assert_close(v.detach(), g(f"simple.{tag}.out"), rtol=1e-5, atol=1e-6)
+    (v * g(f"simple.{tag}.w_out")).sum().backward()
+    for k in names:
+        torch.testing.assert_close(p[k].grad, g(f"simple.{tag}.grad.{k}"), rtol=1e-4, atol=1e-6)
+    # MPNNPolicyNet active path
+    emb = g(f"policy.{tag}.emb").clone().requires_grad_(True)
+    lg = mpnn_port.policy_logits(emb, nf, ei)
+    assert torch.equal(lg.detach(), g(f"policy.{tag}.out"))
+    (lg * g(f"policy.{tag}.w_out")).sum().backward()
+    torch.testing.assert_close(emb.grad, g(f"policy.{tag}.grad_emb"), rtol=1e-5, atol=1e-6)
