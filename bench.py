@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path on B200 (contract: see the task brief / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): sim link-steps/s of the per-timestep network step (SimulationCoreModel.forward semantics) on
+the synthetic 1M-link ring-radial network with 2M agents; the MPNN fwd+bwd edges/s figure rides along under "mpnn".
+A "step" = one pass of the core step over the whole network (E uniforms drawn on the device + the three kernels).
+At N>1 every rank steps its own independent replica of the workload (weak scaling, no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "sim link-steps/s", "link-steps/s"
+T0 = 21600.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", default="ring_radial_1m")
+    ap.add_argument("--cpu-steps", type=int, default=8, help="oracle steps timed for cpu_baseline (N=1, rank 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mpnn", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
+
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+
+    def __init__(self, index: int, period=0.1):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _reasons_nvml(self):
+        nv = self._nvml
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            try:
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            except Exception:
+                return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        for k, b in names.items():
+            if bits & b:
+                self.reasons.add(k)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    self.sm.append(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM))
+                    self._reasons_nvml()
+                else:
+                    out = subprocess.run(
+                        ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,"
+                         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                         "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                    f = [v.strip() for v in out.split(",")]
+                    self.sm.append(int(f[0])); self.sm_max = int(f[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:]):
+                        if v == "Active":
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def step_bytes(N, E, Nmax, p):
+    """algorithmic bytes of one core step."""
+    return N * (69 + p * (24 * (Nmax - 1) + 4)) + 20 * E
+
+
+def phase_bytes(N, E, Nmax, p):
+    """The same budget split over the three kernels."""
+    return {
+        "k_offer": N * 36,                                   # head triplet 12 + {MAXN,NUM,FFTT,SEL,RIDX} 20 + cc 4
+        "k_select_append": N * 16 + 16 * E,                  # tail triplet 12 + NUM 4 ; per edge idx 4 + attr 4 + noise 4 + dtt 4
+        "k_respond_shift": N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from tarl_simulator_b200 import _cabi, synthetic
+    from tarl_simulator_b200.core import SimulationCoreModel
+    from tarl_simulator_b200.topology import topology_for
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    g, Nmax, placed = synthetic.make_workload(args.workload, device=dev, t=T0, seed=rank)
+    N, E = int(g.num_roads), g.edge_index_routes.size(1)
+    x = g.x[:N]
+    topo = topology_for(g.edge_index_routes, N)
+    attr = g.edge_attr_routes.reshape(-1).contiguous()
+    cc = g.congestion_constant[:N].contiguous()
+    noise = torch.empty(E, dtype=torch.float32, device=dev)
+    delta_tt = torch.empty(E, dtype=torch.float32, device=dev)
+    pop = torch.empty(N, dtype=torch.uint8, device=dev)
+    flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.tarl_core_workspace_bytes(N), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sptr = C.c_void_p(stream.cuda_stream)
+    state = {"t": T0}
+
+    def launch(mask=7):
+        rc = lib.tarl_core_step_phases(topo.ref(), x.data_ptr(), x.stride(0), Nmax, attr.data_ptr(), cc.data_ptr(),
+                                       noise.data_ptr(), state["t"], delta_tt.data_ptr(), pop.data_ptr(),
+                                       flags.data_ptr(), ws.data_ptr(), ws.numel(), sptr, mask)
+        if rc:
+            raise RuntimeError(lib.tarl_error_string(rc).decode())
+
+    def step():
+        noise.uniform_()            # the E uniforms the reference draws inside aggregate (src/direction_mpnn.py:137)
+        launch(7)
+        state["t"] += 1.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = N * world * args.steps / (ms / 1e3)
+
+    # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
+    names = ["k_offer", "k_select_append", "k_respond_shift"]
+    per = {k: 0.0 for k in names}
+    rng_ms = 0.0
+    pops = 0
+    reps = min(args.steps, 20)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    for _ in range(reps):
+        evs[0].record(stream)
+        noise.uniform_()
+        evs[1].record(stream)
+        for i, m in enumerate((1, 2, 4)):
+            launch(m)
+            evs[i + 2].record(stream)
+        state["t"] += 1.0
+        torch.cuda.synchronize(dev)
+        rng_ms += evs[0].elapsed_time(evs[1])
+        for i, k in enumerate(names):
+            per[k] += evs[i + 1].elapsed_time(evs[i + 2])
+        pops += int(pop.sum().item())
+    p = pops / (reps * N)
+    per = {k: v / reps for k, v in per.items()}
+    rng_ms /= reps
+    err = int(flags[_cabi.FLAG_ERROR].item())
+    if err:
+        raise RuntimeError("core step fault during the benchmark: " + _cabi.decode_error_bits(err))
+    peak, peak_src = peaks()
+    pb = phase_bytes(N, E, Nmax, p)
+    dom = max(per, key=per.get)
+    achieved = pb[dom] / (per[dom] / 1e3) / 1e9
+    step_ms = ms / args.steps
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(pb[dom]), "kernel_ms": round(per[dom], 4),
+                "kernels_ms": {k: round(v, 4) for k, v in per.items()}, "rng_ms": round(rng_ms, 4),
+                "pop_fraction": round(p, 4),
+                "step": {"algorithmic_bytes": int(step_bytes(N, E, Nmax, p)),
+                         "achieved": round(step_bytes(N, E, Nmax, p) / (step_ms / 1e3) / 1e9, 1),
+                         "frac": round(step_bytes(N, E, Nmax, p) / (step_ms / 1e3) / 1e9 / peak, 4)}}
+
+    # ---- end to end through the public drop-in API, host buffers both ways
+    h = synthetic.FeatureHelpers(Nmax)
+    model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"])
+    sel_host = g.x[:N, h.SELECTED_ROAD].cpu().pin_memory()
+    dtt_host = torch.empty(E, dtype=torch.float32).pin_memory()
+    pop_host = torch.empty(N, dtype=torch.bool).pin_memory()
+    e2e_steps = min(args.steps, 30)
+
+    def e2e_step():
+        g.x[:N, h.SELECTED_ROAD].copy_(sel_host, non_blocking=True)      # this step's routing decisions, host -> device
+        model.set_time(state["t"])
+        model(g)
+        dtt_host.copy_(model.direction_mpnn.road_optimality_data["delta_travel_time"], non_blocking=True)
+        pop_host.copy_(model.last_pop, non_blocking=True)
+        state["t"] += 1.0
+
+    for _ in range(3):
+        e2e_step()
+    model.response_mpnn.update_history.resolve()
+    barrier()
+    w0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3)
+    model.response_mpnn.update_history.resolve()
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
+           "h2d_bytes_per_step": int(sel_host.numel() * 4), "d2h_bytes_per_step": int(dtt_host.numel() * 4 + pop_host.numel()),
+           "steps": e2e_steps, "api": "SimulationCoreModel.forward(graph); state resident on device as in the reference "
+           "with --device cuda; per step H2D = SELECTED_ROAD decisions, D2H = delta_travel_time[E] + pop mask[N]"}
+
+    out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 5), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
+                      "replicas_per_gpu": 1, "parallelism": f"replicas x{world}",
+                      "l2": "state (x + summaries + edges) larger than the 126 MB L2" if N * 208 > 130e6 else
+                      "state fits in L2 (small workload)"},
+           "e2e": e2e, "gpu_launches": 3 * args.steps, "library_launches": args.steps,
+           "roofline": roofline, "clocks": clk.summary()}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, sample_steps, warmup=1, workload=None):
+    """The CPU oracle port (op-for-op restatement of the reference's torch code, all host threads) on the same
+    workload. The only place outside tests/smoke where oracle/ is executed — as the thing timed beside the GPU."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import core_port
+    from tarl_simulator_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    name = workload or args.workload
+    g, Nmax, placed = synthetic.make_workload(name, device="cpu", t=T0, seed=0)
+    N = int(g.num_roads)
+    x = g.x[:N].clone()
+    ei, w, cc = g.edge_index_routes, g.edge_attr_routes, g.congestion_constant[:N]
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    t = T0
+    for s in range(warmup + sample_steps):
+        u = torch.rand(ei.size(1), generator=gen).clamp_(min=1e-7)
+        a = time.perf_counter()
+        core_port.core_step(x, ei, w, t, Nmax, u, cc)
+        b = time.perf_counter()
+        if s >= warmup:
+            times.append(b - a)
+        t += 1.0
+    med = statistics.median(times)
+    return {"value": round(N / med, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_steps} core steps of the full {name} workload ({N} links), median; "
+                      f"oracle/core_port.py (op-for-op torch restatement of the reference, {cores} ATen threads)",
+            "ms_per_step": round(med * 1e3, 2), "links": N}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path. The reference is pure Python on wheels
+    that are not installable here, and /root/reference does not exist on the GPU box, so this times the oracle port
+    (kind "port"). Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    name = args.workload
+    budget_s = 150.0
+    est = {"ring_radial_1m": 1.4, "grid100": 0.045}.get(name, 0.05)
+    steps, warm = args.steps, min(args.warmup, 2)
+    if (steps + warm) * est > budget_s:
+        steps = max(3, int(budget_s / est) - warm)
+    t0 = time.perf_counter()
+    cb = cpu_baseline(args, sample_steps=steps, warmup=warm, workload=name)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": name, "links": cb["links"]},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.perf_counter() - t0, 1)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

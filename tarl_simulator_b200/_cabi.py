@@ -1,0 +1,67 @@
+"""ctypes binding of libtarl_b200.so (include/tarl_b200.h). Fails loudly when the library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtarl_b200.so")
+
+OK = 0
+FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
+ERR_QUEUE_RANGE, ERR_NO_WINNER = 1, 2
+ERR_TEXT = {
+    ERR_QUEUE_RANGE: "NUMBER_OF_AGENT of some link left [0, Nmax): the reference's tail write would alias other "
+                     "columns or raise IndexError (src/direction_mpnn.py:175-191)",
+    ERR_NO_WINNER: "a link had positive total probability but no finite Gumbel score (noise == 0 or NaN); the "
+                   "reference raises IndexError at src/direction_mpnn.py:144",
+}
+
+
+class DualCSR(C.Structure):
+    """struct tarl_dual_csr"""
+    _fields_ = [("n_links", C.c_int32), ("n_edges", C.c_int32),
+                ("in_ptr", C.c_void_p), ("in_src", C.c_void_p), ("in_eid", C.c_void_p),
+                ("out_ptr", C.c_void_p), ("out_dst", C.c_void_p), ("out_eid", C.c_void_p)]
+
+
+_P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_t
+_CSR = C.POINTER(DualCSR)
+
+# name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
+SIGNATURES = {
+    "tarl_abi_version": (C.c_int, []),
+    "tarl_error_string": (C.c_char_p, [C.c_int]),
+    "tarl_core_workspace_bytes": (_SZ, [_I32]),
+    "tarl_direction_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
+    "tarl_response_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),
+    "tarl_core_step": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library. Raises RuntimeError if it has not been built (python -m tarl_simulator_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m tarl_simulator_b200.build` (needs nvcc). "
+                "tarl_simulator_b200 has no CPU or PyTorch fallback for its kernels.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != OK:
+        raise RuntimeError(f"{what} failed: {lib().tarl_error_string(rc).decode()} (code {rc})")
+
+
+def decode_error_bits(bits: int) -> str:
+    return "; ".join(text for bit, text in ERR_TEXT.items() if bits & bit) or f"unknown error bits {bits}"

@@ -1,0 +1,68 @@
+"""Static topology preprocessing: int32 CSR of the dual graph in both orientations, original edge ids kept.
+
+Built once per `edge_index_routes` tensor with torch ops on its device (plumbing, not on the timed path) and cached
+by tensor identity + version, so the drop-in `forward(graph)` can be called every step without re-sorting.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+
+from . import _cabi
+
+
+class DualTopology:
+    """CSR-by-target and CSR-by-source of a [2, E] int64 edge index over `n_links` nodes (row 0 = upstream / source,
+    row 1 = downstream / target). Segments keep ascending original edge id (stable sort): the Gumbel arg-max and the
+    reference's scatter_add_ both walk edges in that order."""
+
+    def __init__(self, edge_index: torch.Tensor, n_links: int):
+        assert edge_index.dim() == 2 and edge_index.size(0) == 2
+        E = edge_index.size(1)
+        if n_links >= 2 ** 31 or E >= 2 ** 31:
+            raise ValueError("topology exceeds int32 indexing")
+        dev = edge_index.device
+        src, dst = edge_index[0].long(), edge_index[1].long()
+        if E and (int(src.min()) < 0 or int(dst.min()) < 0 or int(src.max()) >= n_links or int(dst.max()) >= n_links):
+            raise ValueError("edge index out of range for n_links")
+        self.n_links, self.n_edges, self.device = n_links, E, dev
+        i32 = dict(dtype=torch.int32, device=dev)
+        order_in = torch.argsort(dst, stable=True)
+        self.in_eid = order_in.to(torch.int32)
+        self.in_src = src[order_in].to(torch.int32)
+        self.in_ptr = torch.zeros(n_links + 1, **i32)
+        self.in_ptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n_links), 0)
+        order_out = torch.argsort(src, stable=True)
+        self.out_eid = order_out.to(torch.int32)
+        self.out_dst = dst[order_out].to(torch.int32)
+        self.out_ptr = torch.zeros(n_links + 1, **i32)
+        self.out_ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_links), 0)
+        self.src32 = src.to(torch.int32)
+        self.dst32 = dst.to(torch.int32)
+        self.source_sorted = bool(E == 0 or torch.equal(order_out, torch.arange(E, device=dev)))
+        self.struct = _cabi.DualCSR(n_links, E, self.in_ptr.data_ptr(), self.in_src.data_ptr(), self.in_eid.data_ptr(),
+                                    self.out_ptr.data_ptr(), self.out_dst.data_ptr(), self.out_eid.data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+_CACHE: dict = {}
+
+
+def topology_for(edge_index: torch.Tensor, n_links: int) -> DualTopology:
+    """Cached DualTopology for this exact tensor (identity, version counter and shape must all match)."""
+    key = (id(edge_index), n_links)
+    hit = _CACHE.get(key)
+    if hit is not None:
+        ref, version, ptr, shape, topo = hit
+        if ref() is edge_index and version == edge_index._version and ptr == edge_index.data_ptr() and shape == tuple(edge_index.shape):
+            return topo
+    topo = DualTopology(edge_index, n_links)
+    if len(_CACHE) > 64:
+        for k in [k for k, v in _CACHE.items() if v[0]() is None]:
+            del _CACHE[k]
+    _CACHE[key] = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), tuple(edge_index.shape), topo)
+    return topo
