@@ -169,11 +169,17 @@ def run_native(args):
     ws = torch.empty(lib.tarl_core_workspace_bytes(N), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sptr = C.c_void_p(stream.cuda_stream)
-    state = {"t": T0}
+    state = {"t": T0, "i": 0}
+
+    # Agents.choice re-draws SELECTED_ROAD for every link every step (src/agents/base.py:446-494); the draw itself is
+    # not part of the core step, so a bank of pre-drawn decision vectors is cycled through as the step's input.
+    sel_bank = [synthetic.random_out_neighbour(g, 1000 + 17 * rank + i) for i in range(8)]
+    state["i"] = 0
 
     def launch(mask=7):
+        sel = sel_bank[state["i"] % len(sel_bank)]
         rc = lib.tarl_core_step_phases(topo.ref(), x.data_ptr(), x.stride(0), Nmax, attr.data_ptr(), cc.data_ptr(),
-                                       noise.data_ptr(), state["t"], delta_tt.data_ptr(), pop.data_ptr(),
+                                       noise.data_ptr(), sel.data_ptr(), state["t"], delta_tt.data_ptr(), pop.data_ptr(),
                                        flags.data_ptr(), ws.data_ptr(), ws.numel(), sptr, mask)
         if rc:
             raise RuntimeError(lib.tarl_error_string(rc).decode())
@@ -182,6 +188,7 @@ def run_native(args):
         noise.uniform_()            # the E uniforms the reference draws inside aggregate (src/direction_mpnn.py:137)
         launch(7)
         state["t"] += 1.0
+        state["i"] += 1
 
     def barrier():
         if world > 1:
@@ -221,6 +228,7 @@ def run_native(args):
             launch(m)
             evs[i + 2].record(stream)
         state["t"] += 1.0
+        state["i"] += 1
         torch.cuda.synchronize(dev)
         rng_ms += evs[0].elapsed_time(evs[1])
         for i, k in enumerate(names):
@@ -249,18 +257,21 @@ def run_native(args):
     # ---- end to end through the public drop-in API, host buffers both ways
     h = synthetic.FeatureHelpers(Nmax)
     model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"])
-    sel_host = g.x[:N, h.SELECTED_ROAD].cpu().pin_memory()
+    sel_hosts = [b.cpu().pin_memory() for b in sel_bank]
+    sel_dev = torch.empty(N, dtype=torch.float32, device=dev)
+    sel_host = sel_hosts[0]
     dtt_host = torch.empty(E, dtype=torch.float32).pin_memory()
     pop_host = torch.empty(N, dtype=torch.bool).pin_memory()
     e2e_steps = min(args.steps, 30)
 
     def e2e_step():
-        g.x[:N, h.SELECTED_ROAD].copy_(sel_host, non_blocking=True)      # this step's routing decisions, host -> device
+        sel_dev.copy_(sel_hosts[state["i"] % len(sel_hosts)], non_blocking=True)   # this step's routing decisions
         model.set_time(state["t"])
-        model(g)
+        model(g, selected_road=sel_dev)
         dtt_host.copy_(model.direction_mpnn.road_optimality_data["delta_travel_time"], non_blocking=True)
         pop_host.copy_(model.last_pop, non_blocking=True)
         state["t"] += 1.0
+        state["i"] += 1
 
     for _ in range(3):
         e2e_step()

@@ -68,8 +68,11 @@ const char* tarl_error_string(int code);
  *    [2nmax,3nmax) scheduled exit times, then MAXN, NUM, FFTT, LENGTH, MAX_FLOW, SELECTED_ROAD, ROAD_INDEX.
  * edge_attr: edge_attr_routes, [E] in original edge order.   cc: congestion_constant[:N] or NULL (then the formula
  *    of src/simulation_core_model.py:58-67 is evaluated in-kernel).   noise: the E uniforms the reference draws with
- *    torch.rand_like at src/direction_mpnn.py:137, original edge order.   t: the simulation time baked in by
- *    set_time (src/simulation_core_model.py:85-88), as fp32.
+ *    torch.rand_like at src/direction_mpnn.py:137, original edge order.   sel: NULL, or [N] SELECTED_ROAD values for
+ *    this step, written into x[:, SELECTED_ROAD] before anything reads it — the fused form of the caller's
+ *    "apply action / choice, then core" sequence (src/reinforcement_learning.py:231-237,
+ *    src/transportation_simulator.py:316-322).   t: the simulation time baked in by set_time
+ *    (src/simulation_core_model.py:85-88), as fp32.
  * workspace: tarl_core_workspace_bytes(N) bytes of device scratch, 16-byte aligned.
  * ------------------------------------------------------------------------------------------------------------- */
 size_t tarl_core_workspace_bytes(int32_t n_links);
@@ -78,7 +81,8 @@ size_t tarl_core_workspace_bytes(int32_t n_links);
  * eligibility masks, per-downstream-link Gumbel-max pick of one upstream head, tail append on EVERY link.
  * delta_tt: [E] out, road_optimality_data["delta_travel_time"] in original edge order (may be NULL). */
 int tarl_direction_forward(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
-                           const float* edge_attr, const float* cc, const float* noise, float t, float* delta_tt,
+                           const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
+                           float* delta_tt,
                            int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces ResponseMPNN.forward = message + max-aggregate + update (src/response_mpnn.py:27-127): an upstream link
@@ -91,8 +95,8 @@ int tarl_response_forward(const tarl_dual_csr* g, float* x, int64_t x_row_stride
 /* Replaces SimulationCoreModel.forward (src/simulation_core_model.py:41-83): direction then response, sharing the
  * per-link summaries so that x is read once, not gathered four times per edge. */
 int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax, const float* edge_attr,
-                   const float* cc, const float* noise, float t, float* delta_tt, uint8_t* pop, int32_t* flags,
-                   void* workspace, size_t workspace_bytes, void* stream);
+                   const float* cc, const float* noise, const float* sel, float t, float* delta_tt, uint8_t* pop,
+                   int32_t* flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same step with its three kernels individually selectable (profiling and per-kernel timing only; a partial
  * mask leaves x mid-step). Phases must be issued in order on one stream. */
@@ -101,7 +105,8 @@ int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32
 #define TARL_PHASE_RESPOND_SHIFT 4u /* acknowledgement, delta_tt, FIFO shift of popping links       */
 #define TARL_PHASE_ALL 7u
 int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
-                          const float* edge_attr, const float* cc, const float* noise, float t, float* delta_tt,
+                          const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
+                          float* delta_tt,
                           uint8_t* pop, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream,
                           uint32_t phase_mask);
 

@@ -33,10 +33,10 @@ SIGNATURES = {
     "tarl_abi_version": (C.c_int, []),
     "tarl_error_string": (C.c_char_p, [C.c_int]),
     "tarl_core_workspace_bytes": (_SZ, [_I32]),
-    "tarl_direction_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
+    "tarl_direction_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _SZ, _P]),
     "tarl_response_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),
-    "tarl_core_step": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
-    "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
+    "tarl_core_step": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
 }
 
 _lib = None

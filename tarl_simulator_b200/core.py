@@ -141,8 +141,8 @@ class DirectionMPNN(MessagePassing, FeatureHelpers):
         with torch.cuda.device(x.device):
             rc = _cabi.lib().tarl_direction_forward(
                 topo.ref(), x.data_ptr(), x.stride(0) if N > 1 else x.size(1), self.Nmax, attr.data_ptr(),
-                cc.data_ptr() if cc is not None else None, noise.data_ptr(), float(self.time), delta_tt.data_ptr(),
-                flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x.device))
+                cc.data_ptr() if cc is not None else None, noise.data_ptr(), None, float(self.time),
+                delta_tt.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x.device))
         _cabi.check(rc, "tarl_direction_forward")
         self.road_optimality_data = {"delta_travel_time": delta_tt}
         self._flags = flags
@@ -214,6 +214,14 @@ def _edge_inputs(x, E, edge_attr, critical_number, congestion_constant, noise):
     return attr, cc, noise
 
 
+def _sel_ptr(sel, N, dev):
+    if sel is None:
+        return None
+    if sel.dtype != torch.float32 or sel.device != dev or sel.numel() != N or not sel.is_contiguous():
+        raise ValueError("selected_road must be a contiguous fp32 [N] tensor on x's device")
+    return sel.data_ptr()
+
+
 class SimulationCoreModel(nn.Module):
     """One network timestep on the road sub-graph (src/simulation_core_model.py:10-88): DirectionMPNN then
     ResponseMPNN, in place on `graph.x[:graph.num_roads]`. Insertion and withdrawal of agents are not part of it.
@@ -236,7 +244,9 @@ class SimulationCoreModel(nn.Module):
         self.direction_mpnn.set_time(time)
         self.response_mpnn.set_time(time)
 
-    def forward(self, graph, noise: Optional[torch.Tensor] = None):
+    def forward(self, graph, noise: Optional[torch.Tensor] = None, selected_road: Optional[torch.Tensor] = None):
+        """`selected_road` (optional, fp32 [N] on the device): this step's SELECTED_ROAD column, applied inside the
+        first kernel instead of by a separate strided write into graph.x beforehand."""
         N = int(graph.num_roads)
         x_roads = graph.x[:N]                       # a view: every write lands in graph.x (reference :52,:81)
         _require_cuda_rows(x_roads, self.Nmax)
@@ -256,7 +266,8 @@ class SimulationCoreModel(nn.Module):
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_core_step(
                 topo.ref(), x_roads.data_ptr(), x_roads.stride(0) if N > 1 else x_roads.size(1), self.Nmax,
-                attr.data_ptr(), cc.data_ptr() if cc is not None else None, noise.data_ptr(), float(self.time),
+                attr.data_ptr(), cc.data_ptr() if cc is not None else None, noise.data_ptr(),
+                _sel_ptr(selected_road, N, dev), float(self.time),
                 delta_tt.data_ptr(), pop.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
         _cabi.check(rc, "tarl_core_step")
         self.direction_mpnn.road_optimality_data = {"delta_travel_time": delta_tt}

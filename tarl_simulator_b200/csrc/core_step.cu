@@ -49,15 +49,22 @@ inline Workspace carve(void* base, int32_t n) {
 enum : int { kA1 = 1, kA2 = 2, kFree = 4, kBad = 8 };
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_offer(const float* __restrict__ x, int64_t stride, int N, int Nmax,
-                                                    const float* __restrict__ cc, float t, Workspace w,
-                                                    int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(kThreads) k_offer(float* __restrict__ x, int64_t stride, int N, int Nmax,
+                                                    const float* __restrict__ cc, const float* __restrict__ sel_in,
+                                                    float t, Workspace w, int32_t* __restrict__ flags) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    const float* row = x + (int64_t)n * stride;
+    float* row = x + (int64_t)n * stride;
     const int c0 = 3 * Nmax;
     const float head_id = row[0], head_arr = row[Nmax], head_dep = row[2 * Nmax];
-    const float maxn = row[c0], num = row[c0 + 1], fftt = row[c0 + 2], sel = row[c0 + 5], ridx = row[c0 + 6];
+    const float maxn = row[c0], num = row[c0 + 1], fftt = row[c0 + 2], ridx = row[c0 + 6];
+    float sel;
+    if (sel_in != nullptr) {  // this step's routing decision, applied first (src/reinforcement_learning.py:231)
+        sel = sel_in[n];
+        row[c0 + 5] = sel;
+    } else {
+        sel = row[c0 + 5];
+    }
     float ccn;
     if (cc != nullptr) {
         ccn = cc[n];
@@ -246,7 +253,8 @@ size_t tarl_core_workspace_bytes(int32_t n_links) {
 }
 
 int tarl_direction_forward(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
-                           const float* edge_attr, const float* cc, const float* noise, float t, float* delta_tt,
+                           const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
+                           float* delta_tt,
                            int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(g, x, nmax, workspace, workspace_bytes, flags);
     if (rc != TARL_OK) return rc;
@@ -255,7 +263,7 @@ int tarl_direction_forward(const tarl_dual_csr* g, float* x, int64_t x_row_strid
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Workspace w = carve(workspace, g->n_links);
     const int nb = blocks_for(g->n_links);
-    k_offer<<<nb, kThreads, 0, s>>>(x, x_row_stride, g->n_links, nmax, cc, t, w, flags);
+    k_offer<<<nb, kThreads, 0, s>>>(x, x_row_stride, g->n_links, nmax, cc, sel, t, w, flags);
     k_select_append<<<nb, kThreads, 0, s>>>(*g, x, x_row_stride, nmax, edge_attr, noise, t, w, flags);
     if (delta_tt != nullptr && g->n_edges > 0) k_emit_delta_tt<<<nb, kThreads, 0, s>>>(*g, w, delta_tt);
     return launch_status();
@@ -276,7 +284,8 @@ int tarl_response_forward(const tarl_dual_csr* g, float* x, int64_t x_row_stride
 }
 
 int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
-                          const float* edge_attr, const float* cc, const float* noise, float t, float* delta_tt,
+                          const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
+                          float* delta_tt,
                           uint8_t* pop, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream,
                           uint32_t phase_mask) {
     int rc = check_common(g, x, nmax, workspace, workspace_bytes, flags);
@@ -288,7 +297,7 @@ int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride
     Workspace w = carve(workspace, g->n_links);
     const int nb = blocks_for(g->n_links);
     if (phase_mask & TARL_PHASE_OFFER)
-        k_offer<<<nb, kThreads, 0, s>>>(x, x_row_stride, g->n_links, nmax, cc, t, w, flags);
+        k_offer<<<nb, kThreads, 0, s>>>(x, x_row_stride, g->n_links, nmax, cc, sel, t, w, flags);
     if (phase_mask & TARL_PHASE_SELECT_APPEND)
         k_select_append<<<nb, kThreads, 0, s>>>(*g, x, x_row_stride, nmax, edge_attr, noise, t, w, flags);
     if (phase_mask & TARL_PHASE_RESPOND_SHIFT)
@@ -297,9 +306,9 @@ int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride
 }
 
 int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax, const float* edge_attr,
-                   const float* cc, const float* noise, float t, float* delta_tt, uint8_t* pop, int32_t* flags,
-                   void* workspace, size_t workspace_bytes, void* stream) {
-    return tarl_core_step_phases(g, x, x_row_stride, nmax, edge_attr, cc, noise, t, delta_tt, pop, flags, workspace,
+                   const float* cc, const float* noise, const float* sel, float t, float* delta_tt, uint8_t* pop,
+                   int32_t* flags, void* workspace, size_t workspace_bytes, void* stream) {
+    return tarl_core_step_phases(g, x, x_row_stride, nmax, edge_attr, cc, noise, sel, t, delta_tt, pop, flags, workspace,
                                  workspace_bytes, stream, TARL_PHASE_ALL);
 }
 

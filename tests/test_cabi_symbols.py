@@ -50,7 +50,7 @@ def test_workspace_size_is_monotone():
 def test_argument_errors_are_reported_without_a_gpu():
     lib = _cabi.lib()
     csr = _cabi.DualCSR(4, 0, None, None, None, None, None, None)
-    rc = lib.tarl_core_step(ctypes.byref(csr), None, 52, 15, None, None, None, 0.0, None, None, None, None, 0, None)
+    rc = lib.tarl_core_step(ctypes.byref(csr), None, 52, 15, None, None, None, None, 0.0, None, None, None, None, 0, None)
     assert rc == -1          # flags == NULL -> TARL_E_BADARG before any CUDA call
 
 

@@ -91,11 +91,14 @@ def test_core_step_matches_oracle_on_seeded_inputs(seed, N, Nmax, sorted_src):
         sel = cases.random_selection(g, N, ei)
         u = cases.uniforms(g, ei.size(1))
         x[:, c.SEL] = sel
-        graph.x[:, c.SEL] = sel.cuda()
         t = 300.0 + s
         ref = core_port.core_step(x, ei, w, t, Nmax, u, cc)
         model.set_time(t)
-        model(graph, noise=u.cuda())
+        if s % 2:       # decisions handed to the kernel (fused "apply action, then core")
+            model(graph, noise=u.cuda(), selected_road=sel.cuda())
+        else:           # decisions written into graph.x by the caller, as the reference's loop does
+            graph.x[:, c.SEL] = sel.cuda()
+            model(graph, noise=u.cuda())
         assert torch.equal(graph.x.cpu(), x), f"x differs after step {s}"
         assert torch.equal(model.direction_mpnn.road_optimality_data["delta_travel_time"].cpu(), ref["delta_tt"])
         total_pops += 0 if ref["pop"] is None else int(ref["pop"].sum())
