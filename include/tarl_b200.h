@@ -41,6 +41,8 @@ extern "C" {
                                   (src/direction_mpnn.py:175-191) would alias other columns / raise IndexError */
 #define TARL_ERR_NO_WINNER 2   /* a link had positive total probability but no finite Gumbel score (u == 0 or NaN):
                                   the reference raises IndexError at src/direction_mpnn.py:144 */
+#define TARL_ERR_EMBED_RANGE 4 /* an embedding index fell outside nodes_embedding (nn.Embedding raises IndexError,
+                                  src/agents/mpnn_agent.py:216) */
 
 /* Static topology of the dual graph (`edge_index_routes` of the reference, src/transportation_simulator.py:150-171)
  * in both CSR orientations. Original edge ids are kept because the Gumbel arg-max breaks ties towards the lowest
@@ -109,6 +111,59 @@ int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride
                           float* delta_tt,
                           uint8_t* pop, int32_t* flags, void* workspace, size_t workspace_bytes, void* stream,
                           uint32_t phase_mask);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* One CSR orientation of an edge list: row r owns [ptr[r], ptr[r+1]); eid[k] = original edge id of the k-th entry,
+ * ascending inside every row; idx[k] = the other endpoint (may be NULL where unused). */
+typedef struct tarl_csr {
+    int32_t n_rows;
+    int32_t n_edges;
+    const int32_t* ptr;
+    const int32_t* idx;
+    const int32_t* eid;
+} tarl_csr;
+
+/* Replaces MPNNPolicyNet.forward's active path (src/agents/mpnn_agent.py:117-192; update_edges :215-217):
+ * logits[b,e] = nodes_embedding[ idx(b, edge_index[1][e]) ],  idx(b,n) = ROAD_INDEX(b,n) if >= 0 else n  (declared
+ * divergence D2: the literal code raises on ROAD_INDEX = -1 rows). node_features: [B,N,*] fp32 with the given
+ * element strides; node_emb [B,N] and node_idx [B,N] are caller-owned outputs (node_idx is what backward needs). */
+int tarl_policy_embed_forward(const float* emb_weight, int32_t emb_rows, const float* node_features,
+                              int64_t nf_batch_stride, int64_t nf_row_stride, int32_t road_index_col, int32_t batch,
+                              int32_t n_nodes, const int32_t* edge_dst, int32_t n_edges, float* node_emb,
+                              int32_t* node_idx, float* logits, int32_t* flags, void* stream);
+
+/* Gradient of the above w.r.t. nodes_embedding.weight (what embedding_dense_backward computes in the reference):
+ * by_target = CSR of the full edge_index by target node. node_grad: [B,N] scratch. grad_weight [emb_rows] is
+ * overwritten. Fixed summation order (no float atomics when idx is injective and batch-invariant). */
+int tarl_policy_embed_backward(const tarl_csr* by_target, const float* grad_logits, const int32_t* node_idx,
+                               int32_t batch, float* node_grad, float* grad_weight, int32_t emb_rows, void* stream);
+
+/* GraphDistribution (src/reinforcement_learning.py:15-96): categorical over the out-edges of every source node.
+ * groups = CSR of edge_index by RANK of the source id (declared divergence D1). logits [B,E] in original edge order.
+ * Any of proba [B,E], mode [B,E] (one-hot of the per-group arg-max, lowest edge id on ties), entropy [B],
+ * log_prob [B] may be NULL. action: [B,E] one-hot in the dtype named by action_dtype (required for log_prob; a row
+ * without exactly one selected edge per group gets -inf). partials: 3*B*tarl_graphdist_partial_count(K) floats. */
+#define TARL_ACTION_U8 0
+#define TARL_ACTION_I64 1
+#define TARL_ACTION_F32 2
+int32_t tarl_graphdist_partial_count(int32_t n_groups);
+int tarl_graphdist_forward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
+                           const void* action, int32_t action_dtype, float* proba, float* mode, float* entropy,
+                           float* log_prob, float* partials, void* stream);
+
+/* d(sum_b grad_log_prob[b]*log_prob[b] + grad_entropy[b]*entropy[b]) / d logits  -> grad_logits [B,E]. Either
+ * upstream gradient may be NULL. log_prob (forward output, may be NULL) marks -inf rows, which get no gradient. */
+int tarl_graphdist_backward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
+                            const void* action, int32_t action_dtype, const float* grad_log_prob,
+                            const float* grad_entropy, const float* log_prob, float* grad_logits, void* stream);
+
+/* GraphDistribution.sample (:57-80): uniforms [B,K], one per (row, group) in ascending source id; onehot [B,E] int64
+ * out. Inside a group edges are walked in ascending edge id (D3); batched rows are independent (D7). */
+int tarl_graphdist_sample(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
+                          const float* uniforms, int64_t* onehot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,2 @@
+"""Mirror of the reference's src/reinforcement_learning.py."""
+from tarl_simulator_b200.distribution import GraphDistribution  # noqa: F401

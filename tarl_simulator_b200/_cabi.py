@@ -9,12 +9,14 @@ LIB_PATH = os.path.join(_HERE, "libtarl_b200.so")
 
 OK = 0
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
-ERR_QUEUE_RANGE, ERR_NO_WINNER = 1, 2
+ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE = 1, 2, 4
+ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
 ERR_TEXT = {
     ERR_QUEUE_RANGE: "NUMBER_OF_AGENT of some link left [0, Nmax): the reference's tail write would alias other "
                      "columns or raise IndexError (src/direction_mpnn.py:175-191)",
     ERR_NO_WINNER: "a link had positive total probability but no finite Gumbel score (noise == 0 or NaN); the "
                    "reference raises IndexError at src/direction_mpnn.py:144",
+    ERR_EMBED_RANGE: "embedding index out of range (nn.Embedding raises IndexError, src/agents/mpnn_agent.py:216)",
 }
 
 
@@ -25,8 +27,15 @@ class DualCSR(C.Structure):
                 ("out_ptr", C.c_void_p), ("out_dst", C.c_void_p), ("out_eid", C.c_void_p)]
 
 
+class CSR(C.Structure):
+    """struct tarl_csr"""
+    _fields_ = [("n_rows", C.c_int32), ("n_edges", C.c_int32), ("ptr", C.c_void_p), ("idx", C.c_void_p),
+                ("eid", C.c_void_p)]
+
+
 _P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_t
 _CSR = C.POINTER(DualCSR)
+_CSR1 = C.POINTER(CSR)
 
 # name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
 SIGNATURES = {
@@ -37,6 +46,12 @@ SIGNATURES = {
     "tarl_response_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "tarl_core_step": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
     "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
+    "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "tarl_policy_embed_backward": (C.c_int, [_CSR1, _P, _P, _I32, _P, _P, _I32, _P]),
+    "tarl_graphdist_partial_count": (_I32, [_I32]),
+    "tarl_graphdist_forward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "tarl_graphdist_backward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "tarl_graphdist_sample": (C.c_int, [_CSR1, _P, _F, _I32, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,179 @@
+"""GraphDistribution: per-source-node categorical over out-edges, fused on the device.
+
+Drop-in for the reference's src/reinforcement_learning.py:15-96 (`GraphDistribution(logits, edge_index,
+temperature)` with `.sample()`, `.log_prob(action)`, `.entropy()`, `.mode`, `.proba`), computed by the segmented
+kernels of csrc/mpnn.cu behind the C ABI, with autograd through log_prob/entropy. Declared divergences from the
+literal reference code (which raises or scrambles in these cases — SURVEY.md §8c, oracle/mpnn_port.py):
+D1 groups are the ranks of the distinct source ids; D3 edges inside a group are ordered by ascending edge id;
+D7 a batched [B, E] input behaves row-wise like B independent 1-D distributions (sample and mode included);
+the constructor's NaN assert (a host synchronisation, :19) is not performed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.distributions import Distribution
+
+from . import _cabi
+from .topology import group_csr_for
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _action_arg(action: torch.Tensor, B: int, E: int):
+    a = action.reshape(B, E)
+    if a.dtype == torch.bool:
+        a, code = a.contiguous().view(torch.uint8), _cabi.ACTION_U8
+    elif a.dtype == torch.uint8:
+        a, code = a.contiguous(), _cabi.ACTION_U8
+    elif a.dtype == torch.int64:
+        a, code = a.contiguous(), _cabi.ACTION_I64
+    else:
+        a, code = a.to(torch.float32).contiguous(), _cabi.ACTION_F32
+    return a, code
+
+
+class _LogProbEntropy(torch.autograd.Function):
+    """(log_prob [B], entropy [B]) of logits [B,E]; `action` may be None (entropy only)."""
+
+    @staticmethod
+    def forward(ctx, logits, action, groups, temperature):
+        B, E = logits.shape
+        dev = logits.device
+        lib = _cabi.lib()
+        nb = lib.tarl_graphdist_partial_count(groups.n_rows)
+        partials = torch.empty(max(3 * B * nb, 1), dtype=torch.float32, device=dev)
+        ent = torch.empty(B, dtype=torch.float32, device=dev)
+        lp = torch.empty(B, dtype=torch.float32, device=dev) if action is not None else None
+        a, code = _action_arg(action, B, E) if action is not None else (None, 0)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_graphdist_forward(groups.ref(), logits.data_ptr(), temperature, B,
+                                            a.data_ptr() if a is not None else None, code, None, None, ent.data_ptr(),
+                                            lp.data_ptr() if lp is not None else None, partials.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_graphdist_forward")
+        ctx.groups, ctx.temperature, ctx.code = groups, temperature, code
+        ctx.save_for_backward(logits, a, lp)
+        if lp is None:
+            lp = torch.zeros(B, dtype=torch.float32, device=dev)
+            ctx.mark_non_differentiable(lp)
+        return lp, ent
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ent):
+        logits, a, lp = ctx.saved_tensors
+        B, E = logits.shape
+        dev = logits.device
+        grad = torch.empty_like(logits)
+        g_lp = g_lp.contiguous() if (g_lp is not None and a is not None) else None
+        g_ent = g_ent.contiguous() if g_ent is not None else None
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_graphdist_backward(
+                ctx.groups.ref(), logits.data_ptr(), ctx.temperature, B, a.data_ptr() if a is not None else None,
+                ctx.code, g_lp.data_ptr() if g_lp is not None else None,
+                g_ent.data_ptr() if g_ent is not None else None, lp.data_ptr() if lp is not None else None,
+                grad.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_graphdist_backward")
+        return grad, None, None, None
+
+
+class GraphDistribution(Distribution):
+    arg_constraints = {}
+    has_rsample = False
+
+    def __init__(self, logits: torch.Tensor, edge_index: torch.Tensor, temperature: float = 1.0):
+        super().__init__(validate_args=False)
+        if not logits.is_cuda:
+            raise RuntimeError("GraphDistribution computes on CUDA devices only (no CPU fallback)")
+        if logits.size(-1) != edge_index.size(1):
+            raise ValueError("logits' last dimension must equal the number of edges")
+        self.edge_index = edge_index
+        self.temperature = float(temperature)
+        self._lead = logits.shape[:-1]
+        self._E = logits.size(-1)
+        self._logits = logits.to(torch.float32).reshape(-1, self._E).contiguous()
+        self._groups = group_csr_for(edge_index, "source_rank")
+        self.nodes = self._groups.nodes
+        self.nb_nodes = self._groups.n_rows
+        self._cache = {}
+
+    # -- helpers ---------------------------------------------------------------------------------------------
+    def _forward_extras(self, want_proba=False, want_mode=False):
+        B, E = self._logits.shape
+        dev = self._logits.device
+        lg = self._logits.detach()
+        proba = torch.empty(B, E, dtype=torch.float32, device=dev) if want_proba else None
+        mode = torch.empty(B, E, dtype=torch.float32, device=dev) if want_mode else None
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_graphdist_forward(
+                self._groups.ref(), lg.data_ptr(), self.temperature, B, None, 0,
+                proba.data_ptr() if proba is not None else None, mode.data_ptr() if mode is not None else None,
+                None, None, None, _stream(dev))
+        _cabi.check(rc, "tarl_graphdist_forward")
+        if proba is not None:
+            self._cache["proba"] = proba.reshape(*self._lead, E)
+        if mode is not None:
+            self._cache["mode"] = mode.reshape(*self._lead, E)
+
+    @property
+    def proba(self):
+        """softmax(logits / temperature) within each source group (:25); not differentiable here — gradients flow
+        through log_prob() and entropy()."""
+        if "proba" not in self._cache:
+            self._forward_extras(want_proba=True)
+        return self._cache["proba"]
+
+    @property
+    def mode(self):
+        """One-hot [.., E] of the most probable out-edge of every source node (:45-55; lowest edge id on ties)."""
+        if "mode" not in self._cache:
+            self._forward_extras(want_mode=True)
+        return self._cache["mode"]
+
+    @property
+    def deterministic_sample(self):
+        return self.mode
+
+    # -- Distribution API ------------------------------------------------------------------------------------
+    def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None):
+        """One-hot int64 [sample_shape.., .., E]: inverse CDF with one uniform per (row, source group) (:57-80).
+        `uniforms` ([.., K]) injects the noise the reference draws with torch.rand."""
+        sample_shape = torch.Size(sample_shape)
+        B, E = self._logits.shape
+        dev = self._logits.device
+        S = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
+        lg = self._logits.detach()
+        if S > 1:
+            lg = lg.unsqueeze(0).expand(S, B, E).reshape(S * B, E).contiguous()
+        rows = S * B
+        if uniforms is None:
+            u = torch.rand(rows, self.nb_nodes, dtype=torch.float32, device=dev)
+        else:
+            u = uniforms.to(device=dev, dtype=torch.float32).reshape(rows, self.nb_nodes).contiguous()
+        out = torch.empty(rows, E, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), lg.data_ptr(), self.temperature, rows,
+                                                   u.data_ptr(), out.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_graphdist_sample")
+        return out.reshape(*sample_shape, *self._lead, E)
+
+    def _lp_ent(self, action):
+        return _LogProbEntropy.apply(self._logits, action, self._groups, self.temperature)
+
+    def log_prob(self, action: torch.Tensor):
+        """sum_e action_e * log(proba_e + 1e-8); -inf where a row does not select exactly one edge per group (:82-93).
+        Also caches the entropy computed in the same pass for a following entropy() call."""
+        if action.shape[-1] != self._E or action.numel() != self._logits.numel():
+            raise ValueError("action must have the shape of logits")
+        lp, ent = self._lp_ent(action.to(self._logits.device))
+        self._cache["entropy"] = ent
+        return lp.reshape(self._lead)
+
+    def entropy(self):
+        """-sum_e proba_e * log(proba_e + 1e-8), flattened to [B] (:95-96)."""
+        ent = self._cache.pop("entropy", None)
+        if ent is None:
+            _, ent = self._lp_ent(None)
+        return ent.flatten()

@@ -1,0 +1,158 @@
+"""Learned routing nets: MPNNPolicyNet, MPNNValueNet, MPNNValueNetSimple.
+
+Drop-in for the reference's src/agents/mpnn_agent.py: same constructors, parameter names and shapes (state_dict
+compatible), same forward signatures. The gather/scatter parts run in csrc/mpnn.cu (policy embedding fwd/bwd) and
+csrc/value_net.cu (MPNNValueNet message passing fwd/bwd); the dense per-node MLP of MPNNValueNetSimple is a plain
+library GEMM (nn.Linear → cuBLAS), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+from .agents import Agents
+from .feature_helpers import ObservationFeatureHelpers
+from .message_passing import MessagePassing
+from .topology import group_csr_for
+
+_DIJKSTRA_MAX_NODES = 4096      # dense [N,N] distances: impossible (and unused) beyond toy networks
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _PolicyEmbed(torch.autograd.Function):
+    """logits[b,e] = W[idx(b, dst[e])]  with idx(b,n) = ROAD_INDEX(b,n) if >= 0 else n."""
+
+    @staticmethod
+    def forward(ctx, weight, node_features, dst32, by_target, flags):
+        B, N, Fd = node_features.shape
+        E = dst32.numel()
+        dev = weight.device
+        w = weight.detach().reshape(-1).contiguous()
+        node_emb = torch.empty(B, N, dtype=torch.float32, device=dev)
+        node_idx = torch.empty(B, N, dtype=torch.int32, device=dev)
+        logits = torch.empty(B, E, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_policy_embed_forward(
+                w.data_ptr(), w.numel(), node_features.data_ptr(), node_features.stride(0), node_features.stride(1),
+                ObservationFeatureHelpers.ROAD_INDEX, B, N, dst32.data_ptr(), E, node_emb.data_ptr(),
+                node_idx.data_ptr(), logits.data_ptr(), flags.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_policy_embed_forward")
+        ctx.by_target, ctx.rows, ctx.wshape = by_target, w.numel(), weight.shape
+        ctx.save_for_backward(node_idx)
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        (node_idx,) = ctx.saved_tensors
+        B, N = node_idx.shape
+        dev = grad_logits.device
+        g = grad_logits.contiguous()
+        node_grad = torch.empty(B, N, dtype=torch.float32, device=dev)
+        gw = torch.empty(ctx.rows, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_policy_embed_backward(ctx.by_target.ref(), g.data_ptr(), node_idx.data_ptr(), B,
+                                                        node_grad.data_ptr(), gw.data_ptr(), ctx.rows, _stream(dev))
+        _cabi.check(rc, "tarl_policy_embed_backward")
+        return gw.reshape(ctx.wshape), None, None, None, None
+
+
+class MPNNPolicyNet(MessagePassing, Agents):
+    """Per-edge routing logits (src/agents/mpnn_agent.py:16-262). Active path: logits[e] =
+    nodes_embedding(ROAD_INDEX)[edge_index[1][e]] (:215-217); `edge_mlp` (33→64→32→1) and `edge_mlp_test`
+    (32→16→1) exist with the reference's initialisation so that state_dicts are interchangeable, but — as in the
+    reference at this commit — no forward path uses them."""
+
+    h = ObservationFeatureHelpers()
+
+    def __init__(self, edge_index, num_nodes, free_flow_time_travel, device):
+        Agents.__init__(self, device=device)
+        MessagePassing.__init__(self, aggr="mean", flow="target_to_source")
+        self.edge_index = edge_index
+        self.num_nodes = num_nodes
+        self.num_edges = edge_index.size(1)
+        self.dim_node_features = 16
+        self.dim_edge_features = 1
+        self.dist_matrix = None
+        if num_nodes <= _DIJKSTRA_MAX_NODES:
+            self.refresh_dijkstra(edge_index, free_flow_time_travel)
+        self.nodes_embedding = nn.Embedding(num_nodes, 1)
+        self.edge_mlp_test = nn.Sequential(
+            nn.Linear(self.dim_node_features + self.dim_node_features, 16), nn.ReLU(), nn.Linear(16, 1))
+        self.edge_mlp = nn.Sequential(
+            nn.Linear(2 * self.dim_node_features + self.dim_edge_features, 64), nn.ReLU(),
+            nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 1))
+        for seq in (self.edge_mlp, self.edge_mlp_test):
+            for m in seq:
+                if isinstance(m, nn.Linear):
+                    nn.init.uniform_(m.weight, -0.1, 0.1)
+                    nn.init.constant_(m.bias, 0)
+        self.to(device)
+        self._dst32 = None
+        self._flags = None
+
+    def refresh_dijkstra(self, edge_index: torch.Tensor, free_flow_travel: torch.Tensor):
+        """All-pairs shortest travel times (src/agents/mpnn_agent.py:53-82). Host-side, dense [N,N]; its result never
+        reaches the logits in the reference (:188), so it is only computed for toy networks."""
+        assert free_flow_travel.size(0) == edge_index.size(1), "Free flow travel time must match the number of edges."
+        assert edge_index.size(0) == 2, "Edge index must be a 2D tensor with shape [2, num_edges]."
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import dijkstra
+        ei = edge_index.detach().cpu().numpy()
+        w = free_flow_travel.detach().cpu().numpy().astype(np.float64)
+        # parallel edges: the shortest one counts (a MultiGraph-free DiGraph keeps the last; Dijkstra needs the min)
+        m = sp.coo_matrix((w, (ei[0], ei[1])), shape=(self.num_nodes, self.num_nodes)).tocsr()
+        m.sum_duplicates()
+        d = dijkstra(m, directed=True)
+        self.dist_matrix = torch.tensor(d, dtype=torch.float32, device=self.device)
+
+    def forward(self, node_features: torch.Tensor, edge_features: torch.Tensor = None,
+                agent_index: torch.Tensor = None) -> torch.Tensor:
+        if not node_features.is_cuda:
+            raise RuntimeError("MPNNPolicyNet computes on CUDA devices only (no CPU fallback)")
+        batched = node_features.dim() == 3
+        nf = node_features if batched else node_features.unsqueeze(0)
+        nf = nf.to(torch.float32)
+        if nf.stride(2) != 1:
+            nf = nf.contiguous()
+        ei = self.edge_index
+        if self._dst32 is None or self._dst32.device != nf.device or self._dst32.numel() != ei.size(1):
+            self._dst32 = ei[1].to(device=nf.device, dtype=torch.int32).contiguous()
+            self._ei_dev = ei.to(nf.device)
+        by_target = group_csr_for(self._ei_dev, "target", self.num_nodes)
+        self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=nf.device)
+        logits = _PolicyEmbed.apply(self.nodes_embedding.weight, nf, self._dst32, by_target, self._flags)
+        return logits if batched else logits.view(self.num_edges)
+
+    def check_errors(self):
+        if self._flags is not None:
+            bits = int(self._flags[_cabi.FLAG_ERROR])
+            if bits:
+                raise IndexError(_cabi.decode_error_bits(bits))
+
+
+class MPNNValueNetSimple(MessagePassing, Agents):
+    """State value from the per-link occupancies: MLP([NUMBER_OF_AGENT column ‖ time]), (N+1)→64→64→1 with ReLU
+    (src/agents/mpnn_agent.py:407-450) — the value net Runner wires (src/runner.py:68). Dense GEMMs: library calls."""
+
+    def __init__(self, edge_index, num_nodes, device):
+        Agents.__init__(self, device=device)
+        MessagePassing.__init__(self, aggr="mean", flow="target_to_source")
+        self.edge_index = edge_index
+        self.num_nodes = num_nodes
+        self.num_edges = edge_index.size(1)
+        self.dim_nodes_features = 16
+        self.dim_edges_features = 1
+        self.final_mlp = nn.Sequential(nn.Linear(self.num_nodes + 1, 64), nn.ReLU(), nn.Linear(64, 64), nn.ReLU(),
+                                       nn.Linear(64, 1))
+        self.to(device)
+
+    def forward(self, node_features, edge_features, agent_index, time):
+        x = torch.cat((node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time), dim=-1)
+        return self.final_mlp(x)

@@ -66,3 +66,53 @@ def topology_for(edge_index: torch.Tensor, n_links: int) -> DualTopology:
             del _CACHE[k]
     _CACHE[key] = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), tuple(edge_index.shape), topo)
     return topo
+
+
+class GroupCSR:
+    """One CSR orientation of an edge list for the MPNN kernels (struct tarl_csr).
+
+    by="source_rank": rows are the RANKS of the distinct source ids (GraphDistribution groups, declared divergence D1:
+    the reference indexes by raw source id and only works when sources are exactly 0..K-1).
+    by="target": rows are target node ids 0..n_nodes-1 (policy backward)."""
+
+    def __init__(self, edge_index: torch.Tensor, by: str, n_nodes: int | None = None):
+        E = edge_index.size(1)
+        dev = edge_index.device
+        if by == "source_rank":
+            self.nodes, key = torch.unique(edge_index[0], return_inverse=True)
+            rows = int(self.nodes.numel())
+            other = edge_index[1]
+        elif by == "target":
+            key, rows, other = edge_index[1].long(), int(n_nodes), edge_index[0]
+            self.nodes = None
+        else:
+            raise ValueError(by)
+        order = torch.argsort(key, stable=True)
+        self.eid = order.to(torch.int32)
+        self.idx = other[order].to(torch.int32)
+        self.ptr = torch.zeros(rows + 1, dtype=torch.int32, device=dev)
+        if E:
+            self.ptr[1:] = torch.cumsum(torch.bincount(key, minlength=rows), 0)
+        self.n_rows, self.n_edges = rows, E
+        self.struct = _cabi.CSR(rows, E, self.ptr.data_ptr(), self.idx.data_ptr(), self.eid.data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+_GROUP_CACHE: dict = {}
+
+
+def group_csr_for(edge_index: torch.Tensor, by: str, n_nodes: int | None = None) -> GroupCSR:
+    key = (id(edge_index), by, n_nodes)
+    hit = _GROUP_CACHE.get(key)
+    if hit is not None:
+        ref, version, ptr, shape, csr = hit
+        if ref() is edge_index and version == edge_index._version and ptr == edge_index.data_ptr() and shape == tuple(edge_index.shape):
+            return csr
+    csr = GroupCSR(edge_index, by, n_nodes)
+    if len(_GROUP_CACHE) > 64:
+        for k in [k for k, v in _GROUP_CACHE.items() if v[0]() is None]:
+            del _GROUP_CACHE[k]
+    _GROUP_CACHE[key] = (weakref.ref(edge_index), edge_index._version, edge_index.data_ptr(), tuple(edge_index.shape), csr)
+    return csr

@@ -1,0 +1,134 @@
+"""GPU parity of the learned-MPNN path (C ABI: tarl_policy_embed_*, tarl_graphdist_*) against golden vectors from
+the unmodified reference and against the CPU oracle port. Tolerance: 1e-5 relative (fp32), stated per assert;
+integer outputs (mode, sampled actions, -inf rows) exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mpnn_port
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("name", ["ring3", "rand1d", "rand2d", "single"])
+def test_graph_distribution_goldens(name, golden_dir):
+    from tarl_simulator_b200.distribution import GraphDistribution
+    z = np.load(os.path.join(golden_dir, "mpnn_graphdist.npz"))
+    g = lambda k: torch.from_numpy(z[f"{name}.{k}"])
+    lg = g("logits").cuda().requires_grad_(True)
+    ei = g("edge_index").cuda()
+    d = GraphDistribution(lg, ei, temperature=float(z[f"{name}.temperature"]))
+    close(d.proba, g("proba"))
+    assert torch.equal(d.mode.cpu(), g("mode"))
+    lp = d.log_prob(g("action").cuda())
+    ent = d.entropy()
+    assert lp.shape == g("log_prob").shape and ent.shape == g("entropy").shape
+    close(lp, g("log_prob"))
+    close(ent, g("entropy"))
+    ((lp * g("w_lp").cuda()).sum() + (ent * g("w_ent").cuda()).sum()).backward()
+    close(lg.grad, g("grad_logits"), rtol=1e-5, atol=2e-6)
+    assert torch.equal(d.log_prob(g("bad_action").cuda()).cpu(), g("log_prob_bad"))
+    if bool(z[f"{name}.stable_sort"]) and lg.dim() == 1:     # the reference's own (unstable) sort happened to be stable
+        assert torch.equal(d.sample(uniforms=g("u").cuda()).cpu(), g("action"))
+
+
+@pytest.mark.parametrize("seed,B", [(1, None), (2, 4)])
+def test_graph_distribution_vs_oracle_with_sinks(seed, B):
+    """Random graph with sink nodes (sources are NOT 0..K-1: the literal reference raises here, D1)."""
+    from tarl_simulator_b200.distribution import GraphDistribution
+    g = torch.Generator().manual_seed(seed)
+    N, E = 500, 2100
+    src = torch.randint(0, N // 2, (E,), generator=g) * 2          # odd nodes never a source
+    dst = torch.randint(0, N, (E,), generator=g)
+    ei = torch.stack([src, dst])
+    shape = (E,) if B is None else (B, E)
+    logits = torch.randn(*shape, generator=g) * 3
+    ref_l = logits.clone().requires_grad_(True)
+    ref = mpnn_port.GraphDistributionPort(ref_l, ei, 1.3)
+    K = ref.K
+    u = torch.rand(*(() if B is None else (B,)), K, generator=g)
+    if B is None:
+        act = ref.sample(u)
+    else:
+        act = torch.stack([mpnn_port.GraphDistributionPort(logits[b], ei, 1.3).sample(u[b]) for b in range(B)])
+    lg = logits.cuda().requires_grad_(True)
+    d = GraphDistribution(lg, ei.cuda(), temperature=1.3)
+    assert d.nb_nodes == K
+    assert torch.equal(d.sample(uniforms=u.cuda()).cpu(), act)
+    close(d.proba, ref.proba)
+    assert torch.equal(d.mode.cpu(), ref.mode)
+    lp, ent = d.log_prob(act.cuda()), d.entropy()
+    rlp, rent = ref.log_prob(act), ref.entropy()
+    close(lp, rlp); close(ent, rent)
+    wl, we = torch.randn(rlp.shape, generator=g), torch.randn(rent.shape, generator=g)
+    ((rlp * wl).sum() + (rent * we).sum()).backward()
+    ((lp * wl.cuda()).sum() + (ent * we.cuda()).sum()).backward()
+    close(lg.grad, ref_l.grad, rtol=1e-5, atol=2e-6)
+    # entropy alone (no action) and its gradient
+    lg2 = logits.cuda().requires_grad_(True)
+    e2 = GraphDistribution(lg2, ei.cuda(), temperature=1.3).entropy()
+    e2.sum().backward()
+    ref_l.grad = None
+    mpnn_port.GraphDistributionPort(ref_l, ei, 1.3).entropy().sum().backward()
+    close(lg2.grad, ref_l.grad, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
+def test_policy_and_value_simple_goldens(tag, golden_dir):
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNetSimple
+    z = np.load(os.path.join(golden_dir, "mpnn_nets.npz"))
+    g = lambda k: torch.from_numpy(z[k])
+    ei = g(f"value.{tag}.edge_index")
+    nf, ef, ai, tm = (g(f"value.{tag}.{k}").cuda() for k in ("node_features", "edge_features", "agent_index", "time"))
+    N = nf.size(-2)
+    net = MPNNPolicyNet(ei.cuda(), N, torch.ones(ei.size(1)), "cuda")
+    assert sorted(k for k, _ in net.named_parameters()) == list(z[f"policy.{tag}.param_names"])
+    with torch.no_grad():
+        net.nodes_embedding.weight.copy_(g(f"policy.{tag}.emb"))
+    lg = net(nf, ef, ai)
+    assert torch.equal(lg.cpu(), g(f"policy.{tag}.out"))            # a pure gather: exact
+    (lg * g(f"policy.{tag}.w_out").cuda()).sum().backward()
+    close(net.nodes_embedding.weight.grad, g(f"policy.{tag}.grad_emb"))
+    net.check_errors()
+    v = MPNNValueNetSimple(ei.cuda(), N, "cuda")
+    with torch.no_grad():
+        for k, p in v.named_parameters():
+            p.copy_(g(f"simple.{tag}.param.{k}"))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = v(nf, ef, ai, tm)
+    close(out, g(f"simple.{tag}.out"))
+    (out * g(f"simple.{tag}.w_out").cuda()).sum().backward()
+    for k, p in v.named_parameters():
+        close(p.grad, g(f"simple.{tag}.grad.{k}"), rtol=1e-4, atol=1e-6)
+
+
+def test_policy_embed_negative_road_index_and_range_error():
+    """D2: rows with ROAD_INDEX = -1 (SRC/DEST nodes) embed their own node id; an index beyond the table raises."""
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet
+    g = torch.Generator().manual_seed(3)
+    N, E, B = 300, 1500, 3
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+    nf = torch.rand(B, N, 7, generator=g)
+    ridx = torch.arange(N).float()
+    ridx[200:] = -1.0
+    nf[..., 6] = ridx
+    net = MPNNPolicyNet(ei.cuda(), N, torch.ones(E), "cuda")
+    w = net.nodes_embedding.weight.detach().cpu().clone().requires_grad_(True)
+    ref = mpnn_port.policy_logits(w, nf, ei)
+    out = net(nf.cuda(), None, None)
+    assert torch.equal(out.cpu(), ref.detach())
+    wo = torch.randn(B, E, generator=g)
+    (ref * wo).sum().backward()
+    (out * wo.cuda()).sum().backward()
+    close(net.nodes_embedding.weight.grad, w.grad)
+    nf[0, 5, 6] = N + 10
+    net(nf.cuda(), None, None)
+    with pytest.raises(IndexError):
+        net.check_errors()
