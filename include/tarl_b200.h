@@ -113,6 +113,45 @@ int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride
                           uint32_t phase_mask);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Resident link store: the same step on a compact device layout (csrc/engine.cu), for loops that keep the state on
+ * the device between steps (rollouts, benchmarks). tarl_store_import / tarl_store_export convert from / to the
+ * reference's row layout exactly (every cell of x, including what the reference leaves past the queue tails).
+ * All buffers are caller-owned device memory; R replicas of the same network are stepped by one launch.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct tarl_link_store {
+    int32_t n_links;    /* N                                                                             */
+    int32_t n_replicas; /* R >= 1: independent copies of the network state (PPO rollout environments)    */
+    int32_t nmax;       /* Nmax (FIFO slots per link)                                                    */
+    int32_t reserved;
+    void* hot_cur;      /* [R*N] 32-byte records holding the CURRENT state                               */
+    void* hot_next;     /* [R*N] 32-byte records written by the step; the caller swaps the two afterwards */
+    void* sel;          /* [R*N] fp32 SELECTED_ROAD                                                      */
+    void* stat_a;       /* [N] 16-byte {FFTT, congestion_constant, ROAD_INDEX, MAXN}                     */
+    void* stat_b;       /* [N] 16-byte {LENGTH, MAX_FLOW, 0, 0} (export only)                            */
+    void* queue;        /* [R*N*(nmax-1)] 16-byte ring slots {agent id, arrival, exit, pad}              */
+    void* post;         /* [R*N] 16-byte scratch {NUM, tail id, head id, delta_tt} between the two phases */
+} tarl_link_store;
+
+/* x -> store. x element (r, n, c) at x[r*x_replica_stride + n*x_row_stride + c]; cc = congestion_constant[:N] or
+ * NULL (formula). Fills hot_cur, sel, queue and (from replica 0) stat_a / stat_b. */
+int tarl_store_import(const tarl_link_store* store, const float* x, int64_t x_row_stride, int64_t x_replica_stride,
+                      const float* cc, int32_t* flags, void* stream);
+
+/* store (hot_cur) -> x, bit-exact with what the reference's x would hold. t_last_step: the time of the most recent
+ * tarl_store_step (the arrival time the reference wrote past the tails on that step). */
+int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stride, int64_t x_replica_stride,
+                      float t_last_step, void* stream);
+
+/* SimulationCoreModel.forward on the store (src/simulation_core_model.py:41-83): reads hot_cur, writes hot_next.
+ * attr_in: edge_attr_routes permuted into g->in_* order. noise: [R*E] uniforms in original edge order per replica, or
+ * NULL to draw them in-kernel (Philox4x32-10 keyed by seed, counter = (replica*N+link, step_id, in-edge rank/4) — a
+ * documented stream of its own, not torch's). delta_tt: [R*E] or NULL. pop: [R*N]. phase_mask: TARL_PHASE_SELECT_APPEND
+ * | TARL_PHASE_RESPOND_SHIFT (both for a full step). */
+int tarl_store_step(const tarl_dual_csr* g, const tarl_link_store* store, const float* attr_in, const float* noise,
+                    uint64_t seed, uint32_t step_id, float t, float* delta_tt, uint8_t* pop, int32_t* flags,
+                    void* stream, uint32_t phase_mask);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).
  * ------------------------------------------------------------------------------------------------------------- */
 

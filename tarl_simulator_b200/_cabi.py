@@ -33,7 +33,15 @@ class CSR(C.Structure):
                 ("eid", C.c_void_p)]
 
 
+class LinkStore(C.Structure):
+    """struct tarl_link_store"""
+    _fields_ = [("n_links", C.c_int32), ("n_replicas", C.c_int32), ("nmax", C.c_int32), ("reserved", C.c_int32),
+                ("hot_cur", C.c_void_p), ("hot_next", C.c_void_p), ("sel", C.c_void_p), ("stat_a", C.c_void_p),
+                ("stat_b", C.c_void_p), ("queue", C.c_void_p), ("post", C.c_void_p)]
+
+
 _P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_t
+_STORE = C.POINTER(LinkStore)
 _CSR = C.POINTER(DualCSR)
 _CSR1 = C.POINTER(CSR)
 
@@ -46,6 +54,9 @@ SIGNATURES = {
     "tarl_response_forward": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "tarl_core_step": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
     "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
+    "tarl_store_import": (C.c_int, [_STORE, _P, _I64, _I64, _P, _P, _P]),
+    "tarl_store_export": (C.c_int, [_STORE, _P, _I64, _I64, _F, _P]),
+    "tarl_store_step": (C.c_int, [_CSR, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_backward": (C.c_int, [_CSR1, _P, _P, _I32, _P, _P, _I32, _P]),
     "tarl_graphdist_partial_count": (_I32, [_I32]),

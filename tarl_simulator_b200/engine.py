@@ -1,0 +1,141 @@
+"""LinkStore: the resident, compact device representation of the road state (csrc/engine.cu).
+
+It steps R independent replicas of one network with two kernel launches per timestep and converts from/to the
+reference's `graph.x[:num_roads]` row layout exactly (`from_graph` / `export_x`). It is what loops that keep the
+state on the device between steps use (benchmarks, batched PPO rollouts); the per-call drop-in
+`SimulationCoreModel.forward(graph)` works on `graph.x` directly (csrc/core_step.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from .topology import topology_for
+
+PHASE_SELECT_APPEND, PHASE_RESPOND_POP = 2, 4
+
+
+class LinkStore:
+    def __init__(self, edge_index_routes: torch.Tensor, edge_attr_routes: torch.Tensor, n_links: int, Nmax: int,
+                 replicas: int = 1, device=None, seed: int = 0):
+        dev = torch.device(device) if device is not None else edge_index_routes.device
+        if dev.type != "cuda":
+            raise RuntimeError("LinkStore lives on a CUDA device (no CPU fallback)")
+        self.device, self.N, self.R, self.Nmax, self.M = dev, int(n_links), int(replicas), int(Nmax), int(Nmax) - 1
+        self.topo = topology_for(edge_index_routes, self.N)
+        self.E = self.topo.n_edges
+        attr = edge_attr_routes.reshape(-1).to(torch.float32)
+        self.attr_in = attr[self.topo.in_eid.long()].contiguous()        # edge_attr in CSR-by-target order
+        L = self.N * self.R
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.hot = [torch.zeros(max(L, 1), 8, **f32), torch.zeros(max(L, 1), 8, **f32)]
+        self.cur = 0
+        self.sel = torch.zeros(max(L, 1), **f32)
+        self.stat_a = torch.zeros(max(self.N, 1), 4, **f32)
+        self.stat_b = torch.zeros(max(self.N, 1), 4, **f32)
+        self.queue = torch.zeros(max(L * self.M, 1), 4, **f32)
+        self.post = torch.zeros(max(L, 1), 4, **f32)
+        self.pop = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
+        self.flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
+        self.seed, self.step_id = int(seed), 0
+        self.t_last = 0.0
+        self._struct = _cabi.LinkStore()
+        self._fill_struct()
+
+    def _fill_struct(self):
+        s = self._struct
+        s.n_links, s.n_replicas, s.nmax, s.reserved = self.N, self.R, self.Nmax, 0
+        s.hot_cur, s.hot_next = self.hot[self.cur].data_ptr(), self.hot[self.cur ^ 1].data_ptr()
+        s.sel, s.stat_a, s.stat_b = self.sel.data_ptr(), self.stat_a.data_ptr(), self.stat_b.data_ptr()
+        s.queue, s.post = self.queue.data_ptr(), self.post.data_ptr()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_graph(cls, graph, Nmax: int, replicas: int = 1, seed: int = 0) -> "LinkStore":
+        """Build from a reference-layout graph (graph.x on a CUDA device); every replica starts from graph.x."""
+        N = int(graph.num_roads)
+        store = cls(graph.edge_index_routes, graph.edge_attr_routes, N, Nmax, replicas, graph.x.device, seed)
+        cc = graph.congestion_constant[:N] if hasattr(graph, "congestion_constant") and hasattr(graph, "critical_number") else None
+        store.import_x(graph.x[:N], cc, broadcast=True)
+        return store
+
+    def import_x(self, x: torch.Tensor, cc: torch.Tensor | None = None, broadcast: bool = False):
+        """x: [N, F] (broadcast=True: the same rows for every replica) or [R, N, F]; fp32 rows with stride(-1) == 1."""
+        F = 3 * self.Nmax + 7
+        if x.dtype != torch.float32 or x.size(-1) != F or (x.numel() and x.stride(-1) != 1) or x.device != self.device:
+            raise ValueError(f"x must be fp32 [.., N, {F}] with contiguous rows on {self.device}")
+        if x.dim() == 2:
+            if not (broadcast or self.R == 1):
+                raise ValueError("2-D x needs broadcast=True when replicas > 1")
+            row_stride, rep_stride = x.stride(0) if self.N > 1 else F, 0
+        else:
+            if x.size(0) != self.R:
+                raise ValueError("leading dimension of x must equal the number of replicas")
+            row_stride, rep_stride = x.stride(1) if self.N > 1 else F, x.stride(0) if self.R > 1 else 0
+        ccp = None
+        if cc is not None:
+            self._cc = cc.to(torch.float32).contiguous()
+            ccp = self._cc.data_ptr()
+        self._fill_struct()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_import(C.byref(self._struct), x.data_ptr(), row_stride, rep_stride, ccp,
+                                               self.flags.data_ptr(), self._stream())
+        _cabi.check(rc, "tarl_store_import")
+
+    def export_x(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The road rows exactly as the reference would hold them: [R, N, F] (or into `out`, [N,F] allowed if R==1)."""
+        F = 3 * self.Nmax + 7
+        if out is None:
+            out = torch.empty(self.R, self.N, F, dtype=torch.float32, device=self.device)
+        x3 = out if out.dim() == 3 else out.unsqueeze(0)
+        if x3.size(0) != self.R or x3.size(1) != self.N or x3.size(2) != F or x3.dtype != torch.float32 or (x3.numel() and x3.stride(2) != 1):
+            raise ValueError("bad export target")
+        self._fill_struct()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_export(C.byref(self._struct), x3.data_ptr(), x3.stride(1) if self.N > 1 else F,
+                                               x3.stride(0) if self.R > 1 else 0, float(self.t_last), self._stream())
+        _cabi.check(rc, "tarl_store_export")
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------
+    def set_selected_road(self, sel: torch.Tensor):
+        """This step's SELECTED_ROAD values, [N] (all replicas) or [R, N]."""
+        self.sel.view(self.R, self.N).copy_(sel.to(torch.float32).reshape(-1, self.N))
+
+    def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP):
+        """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
+        for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8)."""
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+            if noise.numel() != self.R * self.E:
+                raise ValueError("noise must hold one uniform per replica and dual edge")
+        if delta_tt is not None and (delta_tt.numel() != self.R * self.E or delta_tt.dtype != torch.float32 or not delta_tt.is_contiguous()):
+            raise ValueError("delta_tt must be a contiguous fp32 [R, E] tensor")
+        self._fill_struct()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_step(
+                self.topo.ref(), C.byref(self._struct), self.attr_in.data_ptr(),
+                noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
+                delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
+                self._stream(), phase_mask)
+        _cabi.check(rc, "tarl_store_step")
+        if phase_mask & PHASE_RESPOND_POP:
+            self.cur ^= 1
+            self.step_id += 1
+            self.t_last = float(t)
+        return self.pop[: self.N * self.R].view(self.R, self.N)
+
+    def num_agents(self) -> torch.Tensor:
+        """NUMBER_OF_AGENT per (replica, link), a strided view into the hot records."""
+        return self.hot[self.cur][: self.N * self.R, 4].view(self.R, self.N)
+
+    def check_errors(self):
+        bits = int(self.flags[_cabi.FLAG_ERROR])
+        if bits:
+            raise RuntimeError("link store fault: " + _cabi.decode_error_bits(bits))
