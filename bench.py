@@ -33,13 +33,15 @@ T0 = 21600.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", default="ring_radial_1m")
     ap.add_argument("--cpu-steps", type=int, default=8, help="oracle steps timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpnn", action="store_true")
+    ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
+    ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
     return ap.parse_args()
 
 
@@ -49,7 +51,7 @@ class ClockSampler:
 
     BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
 
-    def __init__(self, index: int, period=0.1):
+    def __init__(self, index: int, period=0.02):
         self.index, self.period = index, period
         self.sm, self.reasons, self.sm_max = [], set(), None
         self._stop = threading.Event()
@@ -143,7 +145,7 @@ def run_native(args):
     import torch.distributed as dist
     from tarl_simulator_b200 import _cabi, synthetic
     from tarl_simulator_b200.core import SimulationCoreModel
-    from tarl_simulator_b200.topology import topology_for
+    from tarl_simulator_b200.engine import PHASE_RESPOND_POP, PHASE_SELECT_APPEND, LinkStore
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -154,52 +156,39 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.lib()
 
-    g, Nmax, placed = synthetic.make_workload(args.workload, device=dev, t=T0, seed=rank)
+    g, Nmax, placed = synthetic.make_workload(args.workload, device=dev, t=T0, seed=rank, order=args.link_order)
     N, E = int(g.num_roads), g.edge_index_routes.size(1)
-    x = g.x[:N]
-    topo = topology_for(g.edge_index_routes, N)
-    attr = g.edge_attr_routes.reshape(-1).contiguous()
-    cc = g.congestion_constant[:N].contiguous()
-    noise = torch.empty(E, dtype=torch.float32, device=dev)
-    delta_tt = torch.empty(E, dtype=torch.float32, device=dev)
-    pop = torch.empty(N, dtype=torch.uint8, device=dev)
-    flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
-    ws = torch.empty(lib.tarl_core_workspace_bytes(N), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    sptr = C.c_void_p(stream.cuda_stream)
-    state = {"t": T0, "i": 0}
-
+    # The resident link store holds the state between steps (same semantics as SimulationCoreModel.forward, exact
+    # import/export: tests/test_link_store_gpu.py). Noise: drawn in-kernel (Philox), as the reference draws inside
+    # aggregate (src/direction_mpnn.py:137). delta_travel_time[E] and the pop mask[N] are produced every step.
+    store = LinkStore.from_graph(g, Nmax, replicas=args.replicas, seed=1234 + rank)
+    R = args.replicas
+    delta_tt = torch.empty(R, E, dtype=torch.float32, device=dev)
     # Agents.choice re-draws SELECTED_ROAD for every link every step (src/agents/base.py:446-494); the draw itself is
     # not part of the core step, so a bank of pre-drawn decision vectors is cycled through as the step's input.
-    sel_bank = [synthetic.random_out_neighbour(g, 1000 + 17 * rank + i) for i in range(8)]
-    state["i"] = 0
+    sel_bank = [synthetic.random_out_neighbour(g, 1000 + 17 * rank + i).repeat(R) for i in range(8)]
+    state = {"t": T0, "i": 0}
 
-    def launch(mask=7):
-        sel = sel_bank[state["i"] % len(sel_bank)]
-        rc = lib.tarl_core_step_phases(topo.ref(), x.data_ptr(), x.stride(0), Nmax, attr.data_ptr(), cc.data_ptr(),
-                                       noise.data_ptr(), sel.data_ptr(), state["t"], delta_tt.data_ptr(), pop.data_ptr(),
-                                       flags.data_ptr(), ws.data_ptr(), ws.numel(), sptr, mask)
-        if rc:
-            raise RuntimeError(lib.tarl_error_string(rc).decode())
-
-    def step():
-        noise.uniform_()            # the E uniforms the reference draws inside aggregate (src/direction_mpnn.py:137)
-        launch(7)
-        state["t"] += 1.0
-        state["i"] += 1
+    def step(mask=PHASE_SELECT_APPEND | PHASE_RESPOND_POP):
+        store.sel = sel_bank[state["i"] % len(sel_bank)]
+        store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=mask)
+        if mask & PHASE_RESPOND_POP:
+            state["t"] += 1.0
+            state["i"] += 1
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, period=0.005) as clk:
         ev0.record(stream)
         for _ in range(args.steps):
             step()
@@ -211,55 +200,48 @@ def run_native(args):
         tms = torch.tensor([ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = N * world * args.steps / (ms / 1e3)
+    value = N * R * world * args.steps / (ms / 1e3)
+    store.check_errors()
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
-    names = ["k_offer", "k_select_append", "k_respond_shift"]
+    names = ["k_store_select_append", "k_store_respond_pop"]
     per = {k: 0.0 for k in names}
-    rng_ms = 0.0
     pops = 0
     reps = min(args.steps, 20)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for _ in range(reps):
         evs[0].record(stream)
-        noise.uniform_()
+        step(PHASE_SELECT_APPEND)
         evs[1].record(stream)
-        for i, m in enumerate((1, 2, 4)):
-            launch(m)
-            evs[i + 2].record(stream)
-        state["t"] += 1.0
-        state["i"] += 1
+        step(PHASE_RESPOND_POP)
+        evs[2].record(stream)
         torch.cuda.synchronize(dev)
-        rng_ms += evs[0].elapsed_time(evs[1])
-        for i, k in enumerate(names):
-            per[k] += evs[i + 1].elapsed_time(evs[i + 2])
-        pops += int(pop.sum().item())
-    p = pops / (reps * N)
+        per[names[0]] += evs[0].elapsed_time(evs[1])
+        per[names[1]] += evs[1].elapsed_time(evs[2])
+        pops += int(store.pop[: N * R].sum().item())
+    p = pops / (reps * N * R)
     per = {k: v / reps for k, v in per.items()}
-    rng_ms /= reps
-    err = int(flags[_cabi.FLAG_ERROR].item())
-    if err:
-        raise RuntimeError("core step fault during the benchmark: " + _cabi.decode_error_bits(err))
+    store.check_errors()
     peak, peak_src = peaks()
-    pb = phase_bytes(N, E, Nmax, p)
+    pb = {"k_store_select_append": R * (N * 52 + 16 * E),
+          "k_store_respond_pop": R * (N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4))}
     dom = max(per, key=per.get)
     achieved = pb[dom] / (per[dom] / 1e3) / 1e9
     step_ms = ms / args.steps
+    sb = R * step_bytes(N, E, Nmax, p)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(pb[dom]), "kernel_ms": round(per[dom], 4),
-                "kernels_ms": {k: round(v, 4) for k, v in per.items()}, "rng_ms": round(rng_ms, 4),
-                "pop_fraction": round(p, 4),
-                "step": {"algorithmic_bytes": int(step_bytes(N, E, Nmax, p)),
-                         "achieved": round(step_bytes(N, E, Nmax, p) / (step_ms / 1e3) / 1e9, 1),
-                         "frac": round(step_bytes(N, E, Nmax, p) / (step_ms / 1e3) / 1e9 / peak, 4)}}
+                "kernels_ms": {k: round(v, 4) for k, v in per.items()}, "pop_fraction": round(p, 4),
+                "step": {"algorithmic_bytes": int(sb), "achieved": round(sb / (step_ms / 1e3) / 1e9, 1),
+                         "frac": round(sb / (step_ms / 1e3) / 1e9 / peak, 4)}}
 
-    # ---- end to end through the public drop-in API, host buffers both ways
+    # ---- end to end through the public drop-in API, host buffers both ways (in-place kernels on graph.x)
     h = synthetic.FeatureHelpers(Nmax)
+    store.export_x(out=g.x[:N].unsqueeze(0)) if R == 1 else g.x[:N].copy_(store.export_x()[0])
     model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"])
-    sel_hosts = [b.cpu().pin_memory() for b in sel_bank]
+    sel_hosts = [b[:N].cpu().pin_memory() for b in sel_bank]
     sel_dev = torch.empty(N, dtype=torch.float32, device=dev)
-    sel_host = sel_hosts[0]
     dtt_host = torch.empty(E, dtype=torch.float32).pin_memory()
     pop_host = torch.empty(N, dtype=torch.bool).pin_memory()
     e2e_steps = min(args.steps, 30)
@@ -290,19 +272,20 @@ def run_native(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_ms = float(tms.item())
     e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
-           "h2d_bytes_per_step": int(sel_host.numel() * 4), "d2h_bytes_per_step": int(dtt_host.numel() * 4 + pop_host.numel()),
-           "steps": e2e_steps, "api": "SimulationCoreModel.forward(graph); state resident on device as in the reference "
-           "with --device cuda; per step H2D = SELECTED_ROAD decisions, D2H = delta_travel_time[E] + pop mask[N]"}
+           "h2d_bytes_per_step": int(sel_dev.numel() * 4), "d2h_bytes_per_step": int(dtt_host.numel() * 4 + pop_host.numel()),
+           "steps": e2e_steps, "api": "SimulationCoreModel.forward(graph, selected_road=...) on graph.x (reference row "
+           "layout, state resident on the device as with the reference's --device cuda); per step H2D = SELECTED_ROAD "
+           "decisions [N] from pinned memory, D2H = delta_travel_time[E] + pop mask[N]; noise drawn on the device"}
 
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": max(args.warmup, 3), "ms_per_step": round(step_ms, 5), "higher_is_better": True,
+           "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
-                      "replicas_per_gpu": 1, "parallelism": f"replicas x{world}",
-                      "l2": "state (x + summaries + edges) larger than the 126 MB L2" if N * 208 > 130e6 else
-                      "state fits in L2 (small workload)"},
-           "e2e": e2e, "gpu_launches": 3 * args.steps, "library_launches": args.steps,
-           "roofline": roofline, "clocks": clk.summary()}
+                      "link_order": args.link_order, "replicas_per_gpu": R, "parallelism": f"independent replicas x{world}",
+                      "state": "resident link store (tarl_store_step), noise drawn in-kernel, delta_tt + pop mask written every step",
+                      "l2": "per-step working set larger than the 126 MB L2" if N * R * 150 > 130e6 else
+                      "per-step working set fits in L2 (small workload)"},
+           "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clk.summary()}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
@@ -323,7 +306,7 @@ def cpu_baseline(args, sample_steps, warmup=1, workload=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     name = workload or args.workload
-    g, Nmax, placed = synthetic.make_workload(name, device="cpu", t=T0, seed=0)
+    g, Nmax, placed = synthetic.make_workload(name, device="cpu", t=T0, seed=0, order=getattr(args, "link_order", "node"))
     N = int(g.num_roads)
     x = g.x[:N].clone()
     ei, w, cc = g.edge_index_routes, g.edge_attr_routes, g.congestion_constant[:N]

@@ -66,6 +66,21 @@ def full_edge_index(frm, to, n_nodes, routes, routes_attr):
     return ei, ea
 
 
+def reorder_links(frm, to, order: str, seed: int = 0):
+    """Link numbering = order of the <link> elements in the network file. "direction": as generated (all links of one
+    compass direction together); "node": grouped by from-node, the way a network written intersection by intersection
+    comes out (neighbouring links get neighbouring ids); "shuffled": a random permutation (worst case for locality)."""
+    if order == "direction":
+        return frm, to
+    if order == "node":
+        perm = torch.argsort(frm, stable=True)
+    elif order == "shuffled":
+        perm = torch.randperm(frm.numel(), generator=torch.Generator().manual_seed(seed)).to(frm.device)
+    else:
+        raise ValueError(order)
+    return frm[perm], to[perm]
+
+
 def build_graph(frm, to, n_nodes, *, with_full_edges=True) -> tuple[Data, int]:
     """Data with the attribute names the reference's code relies on (src/transportation_simulator.py:213-224), minus
     the dense adj_matrix / src_adj."""
@@ -143,9 +158,10 @@ WORKLOADS = {
 }
 
 
-def make_workload(name: str, device="cuda", t: float = 21600.0, seed: int = 0):
+def make_workload(name: str, device="cuda", t: float = 21600.0, seed: int = 0, order: str = "node"):
     kind, args, agents = WORKLOADS[name]
     frm, to, n_nodes = (grid_links if kind == "grid" else ring_radial_links)(*args, device=device)
+    frm, to = reorder_links(frm, to, order)
     g, Nmax = build_graph(frm, to, n_nodes)
     placed = warm_state(g, Nmax, agents, t, seed)
     return g, Nmax, placed
