@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-mpnn", action="store_true")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
+    ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel variant: 0 tiled (default), 1 direct")
     return ap.parse_args()
 
 
@@ -173,7 +174,7 @@ def run_native(args):
 
     def step(mask=PHASE_SELECT_APPEND | PHASE_RESPOND_POP):
         store.sel = sel_bank[state["i"] % len(sel_bank)]
-        store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=mask)
+        store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=mask, variant=args.variant)
         if mask & PHASE_RESPOND_POP:
             state["t"] += 1.0
             state["i"] += 1
@@ -204,7 +205,7 @@ def run_native(args):
     store.check_errors()
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
-    names = ["k_store_select_append", "k_store_respond_pop"]
+    names = ["k_tile_select_append", "k_tile_respond_pop"] if args.variant == 0 else ["k_store_select_append", "k_store_respond_pop"]
     per = {k: 0.0 for k in names}
     pops = 0
     reps = min(args.steps, 20)
@@ -223,8 +224,8 @@ def run_native(args):
     per = {k: v / reps for k, v in per.items()}
     store.check_errors()
     peak, peak_src = peaks()
-    pb = {"k_store_select_append": R * (N * 52 + 16 * E),
-          "k_store_respond_pop": R * (N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4))}
+    pb = {names[0]: R * (N * 52 + 16 * E),
+          names[1]: R * (N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4))}
     dom = max(per, key=per.get)
     achieved = pb[dom] / (per[dom] / 1e3) / 1e9
     step_ms = ms / args.steps
@@ -281,7 +282,7 @@ def run_native(args):
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
-                      "link_order": args.link_order, "replicas_per_gpu": R, "parallelism": f"independent replicas x{world}",
+                      "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": "tiled" if args.variant == 0 else "direct", "parallelism": f"independent replicas x{world}",
                       "state": "resident link store (tarl_store_step), noise drawn in-kernel, delta_tt + pop mask written every step",
                       "l2": "per-step working set larger than the 126 MB L2" if N * R * 150 > 130e6 else
                       "per-step working set fits in L2 (small workload)"},

@@ -56,7 +56,8 @@ typedef struct tarl_dual_csr {
     const int32_t* in_eid;  /* [E]   its original edge id                            */
     const int32_t* out_ptr; /* [N+1] out-edges of upstream link u                    */
     const int32_t* out_dst; /* [E]   downstream link of the k-th out-edge            */
-    const int32_t* out_eid; /* [E]   its original edge id                            */
+    const int32_t* out_eid; /* [E]   its original edge id; NULL = the edge list is already sorted by source,
+                                      i.e. out_eid[k] == k (config_network's order) and need not be read    */
 } tarl_dual_csr;
 
 int tarl_abi_version(void);
@@ -106,6 +107,10 @@ int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32
 #define TARL_PHASE_SELECT_APPEND 2u /* masks + Gumbel arg-max per downstream link, tail append      */
 #define TARL_PHASE_RESPOND_SHIFT 4u /* acknowledgement, delta_tt, FIFO shift of popping links       */
 #define TARL_PHASE_ALL 7u
+/* tarl_store_step only: bits 8..11 of phase_mask pick the kernel variant (results are bit-identical) */
+#define TARL_STEP_VARIANT_SHIFT 8
+#define TARL_STEP_VARIANT_TILED 0u  /* default: one CTA per tile of 256 links, edge-parallel staging in shared memory */
+#define TARL_STEP_VARIANT_DIRECT 1u /* one thread per link walking its own edge segment                            */
 int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
                           const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
                           float* delta_tt,

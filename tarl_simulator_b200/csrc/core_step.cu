@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_delta_tt(tarl_dual_csr g, Wor
     if (u >= g.n_links) return;
     const float v = w.dtt[u];
     const int k1 = g.out_ptr[u + 1];
-    for (int k = g.out_ptr[u]; k < k1; ++k) delta_tt[g.out_eid[k]] = v;
+    for (int k = g.out_ptr[u]; k < k1; ++k) delta_tt[g.out_eid != nullptr ? g.out_eid[k] : k] = v;
 }
 
 // post-append summaries straight from x, for the response-only entry point
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kThreads) k_respond_shift(tarl_dual_csr g, flo
         const float dv = (delta_tt != nullptr) ? w.dtt[u] : 0.0f;
         const int k1 = g.out_ptr[u + 1];
         for (int k = g.out_ptr[u]; k < k1; ++k) {
-            if (delta_tt != nullptr) delta_tt[g.out_eid[k]] = dv;
+            if (delta_tt != nullptr) delta_tt[g.out_eid != nullptr ? g.out_eid[k] : k] = dv;
             const float4 D = w.post[g.out_dst[k]];
             // src/response_mpnn.py:66-83
             accept = accept || (has_up && ((long long)D.x > 0) && ((long long)D.y == head));
@@ -222,7 +222,7 @@ int check_common(const tarl_dual_csr* g, const float* x, int32_t nmax, const voi
                  const int32_t* flags) {
     if (g == nullptr || flags == nullptr || nmax < 2 || g->n_links < 0 || g->n_edges < 0) return TARL_E_BADARG;
     if (g->n_links > 0 && (x == nullptr || g->in_ptr == nullptr || g->out_ptr == nullptr)) return TARL_E_BADARG;
-    if (g->n_edges > 0 && (g->in_src == nullptr || g->in_eid == nullptr || g->out_dst == nullptr || g->out_eid == nullptr))
+    if (g->n_edges > 0 && (g->in_src == nullptr || g->in_eid == nullptr || g->out_dst == nullptr))
         return TARL_E_BADARG;
     if (g->n_links > 0 && (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 15) != 0)) return TARL_E_WORKSPACE;
     if (ws_bytes < tarl_core_workspace_bytes(g->n_links)) return TARL_E_WORKSPACE;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_store_respond_pop(tarl_dual_csr g,
     bool accept = false;
     const int k1 = g.out_ptr[u + 1];
     for (int k = g.out_ptr[u]; k < k1; ++k) {
-        if (delta_tt != nullptr) delta_tt[(int64_t)r * g.n_edges + g.out_eid[k]] = P.w;
+        if (delta_tt != nullptr) delta_tt[(int64_t)r * g.n_edges + (g.out_eid != nullptr ? g.out_eid[k] : k)] = P.w;
         const float4 D = s.post[base + g.out_dst[k]];
         accept = accept || (has_up && ((long long)D.x > 0) && ((long long)D.y == head));
     }
@@ -240,6 +240,284 @@ __global__ void __launch_bounds__(kThreads) k_store_respond_pop(tarl_dual_csr g,
     int nrh = rh + 1; if (nrh >= M) nrh = 0;
     meta = (meta & ~kMetaRingMask) | nrh;
     if (gv && q == 1) meta &= ~kMetaGarbage;                    // the garbage became the head slot
+    h1.w = __int_as_float(meta);
+    s.hot_next[2 * L] = h0;
+    s.hot_next[2 * L + 1] = h1;
+}
+
+
+// ------------------------------------------------------------------------------------------------ tiled variants
+// The kernels above walk each link's edge segment with one thread: in_ptr -> in_src -> hot[u] is a chain of dependent
+// loads that is repeated once per edge, and the step ends up latency-bound (profiles/r01_c: 2.6 TB/s of DRAM traffic at
+// 43 % occupancy). The tiled kernels give one CTA a tile of kTile consecutive links. Because both CSR orientations are
+// sorted by their owner link, the tile's edges form ONE contiguous range: the CTA reads it edge-parallel (coalesced
+// in_src / attr / out_dst streams, four independent upstream gathers in flight per thread), stages the per-edge result
+// in shared memory, and only then runs the per-link scan in ascending edge id out of shared memory. Same arithmetic in
+// the same order as the direct kernels, so the results are bit-identical. Tiles with more than kCap edges (average
+// degree > 8) take the direct path.
+constexpr int kTile = 256;
+constexpr int kCap = 2048;
+
+template <bool kExtNoise>
+__global__ void __launch_bounds__(kTile) k_tile_select_append(
+    tarl_dual_csr g, Store s, const float* __restrict__ attr_in, const float* __restrict__ noise, uint32_t seed_lo,
+    uint32_t seed_hi, uint32_t step_id, float t, int32_t* __restrict__ flags) {
+    __shared__ int s_ptr[kTile + 1];
+    __shared__ float s_room[kTile], s_ridx[kTile];
+    __shared__ uint8_t s_free[kTile];
+    __shared__ uint8_t s_owner[kCap];
+    __shared__ float s_p[kCap], s_id[kCap];
+    __shared__ float s_u[kExtNoise ? kCap : 1];
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.y;
+    const int d = blockIdx.x * kTile + tid;
+    const bool valid = d < s.N;
+    const int base = r * s.N;
+    const int L = base + d;
+
+    s_ptr[tid] = g.in_ptr[min(d, s.N)];
+    if (tid == kTile - 1) s_ptr[kTile] = g.in_ptr[min(d + 1, s.N)];
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, st = h0;
+    if (valid) {
+        h0 = s.hot_cur[2 * L];
+        h1 = s.hot_cur[2 * L + 1];
+        st = s.stat_a[d];
+    }
+    const float num = h1.x, maxn = h1.z, fftt = st.x, ridx_d = st.z;
+    int meta = __float_as_int(h1.w);
+    const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
+    const bool free_d = num < (maxn - 3.0f);
+    const float room_d = maxn - num;
+    s_room[tid] = room_d;
+    s_ridx[tid] = ridx_d;
+    s_free[tid] = free_d ? 1 : 0;
+    __syncthreads();
+
+    const int e0 = s_ptr[0], ne = s_ptr[kTile] - e0;
+    const int kb = s_ptr[tid], ke = s_ptr[tid + 1];
+    float best = -FLT_MAX, best_id = 0.0f, psum = 0.0f;
+    bool have = false;
+
+    if (ne <= kCap) {   // block-uniform
+        for (int k = kb; k < ke; ++k) s_owner[k - e0] = (uint8_t)tid;
+        __syncthreads();
+        for (int i0 = tid; i0 < ne; i0 += 4 * kTile) {
+            int u[4];
+            float a[4], un[4];
+            float4 U0[4], U1[4];
+            float S[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * kTile;
+                u[q] = -1;
+                if (i < ne) {
+                    u[q] = g.in_src[e0 + i];
+                    a[q] = attr_in[e0 + i];
+                    if (kExtNoise) un[q] = noise[(int64_t)r * g.n_edges + g.in_eid[e0 + i]];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (u[q] >= 0) {
+                    const int Lu = base + u[q];
+                    U0[q] = s.hot_cur[2 * Lu];
+                    U1[q] = s.hot_cur[2 * Lu + 1];
+                    S[q] = s.sel[Lu];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (u[q] >= 0) {
+                    const int i = i0 + q * kTile;
+                    const int o = s_owner[i];
+                    const bool a1 = (U0[q].z <= t) && (U1[q].x > 0.0f);
+                    const bool a2 = ((U0[q].z - t) < -10.0f) && ((U1[q].z - 3.0f) <= U1[q].x);
+                    const bool match = (S[q] == s_ridx[o]);
+                    const bool m = (a1 && s_free[o] && match) || (a2 && ((U1[q].z - U1[q].x) <= s_room[o]) && match);
+                    s_p[i] = a[q] * (m ? 1.0f : 0.0f);
+                    s_id[i] = U0[q].x;
+                    if (kExtNoise) s_u[i] = un[q];
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = kb; k < ke; ++k) psum += s_p[k - e0];
+        if (psum > 0.0f) {   // the scores only matter where somebody is eligible (src/direction_mpnn.py:142-144)
+            float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+            for (int k = kb; k < ke; ++k) {
+                const int j = k - kb;
+                float uu;
+                if (kExtNoise) {
+                    uu = s_u[k - e0];
+                } else {
+                    if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
+                    const int jj = j & 3;
+                    uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
+                }
+                const float sc = logf(s_p[k - e0] + 1e-12f) + (-logf(-logf(uu)));
+                if (sc > best) { best = sc; best_id = s_id[k - e0]; have = true; }
+            }
+        }
+    } else if (valid) {
+        float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+        for (int k = kb; k < ke; ++k) {
+            const int j = k - kb;
+            const int Lu = base + g.in_src[k];
+            const float4 u0 = s.hot_cur[2 * Lu], u1 = s.hot_cur[2 * Lu + 1];
+            const float sel_u = s.sel[Lu];
+            const bool a1 = (u0.z <= t) && (u1.x > 0.0f);
+            const bool a2 = ((u0.z - t) < -10.0f) && ((u1.z - 3.0f) <= u1.x);
+            const bool match = (sel_u == ridx_d);
+            const bool m = (a1 && free_d && match) || (a2 && ((u1.z - u1.x) <= room_d) && match);
+            const float p = attr_in[k] * (m ? 1.0f : 0.0f);
+            psum += p;
+            float uu;
+            if (kExtNoise) {
+                uu = noise[(int64_t)r * g.n_edges + g.in_eid[k]];
+            } else {
+                if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
+                const int jj = j & 3;
+                uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
+            }
+            const float sc = logf(p + 1e-12f) + (-logf(-logf(uu)));
+            if (sc > best) { best = sc; best_id = u0.x; have = true; }
+        }
+    }
+    if (!valid) return;
+
+    float chosen = 0.0f;
+    if (psum > 0.0f) {
+        if (!have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
+        else chosen = best_id;
+    }
+    const float dtt = max_propagate_nan((h0.z - h0.y) - fftt, 0.0f);
+    float num_post = num, tail_post = h0.w, head_post = h0.x;
+    if (bad) {
+        atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
+    } else {
+        const int q = (int)num;
+        const float dep_new = t + max_propagate_nan(fftt, st.y / ((maxn + 10.0f) - num));
+        if (q == 0) {
+            h0.x = chosen; h0.y = t; h0.z = dep_new;
+            head_post = chosen;
+            tail_post = chosen;
+            meta &= ~kMetaGarbage;
+            if (chosen != 0.0f) { num_post = num + 1.0f; h0.w = chosen; }
+        } else if (chosen != 0.0f) {
+            s.queue[(size_t)L * s.M + ring_pos(meta & kMetaRingMask, q, s.M)] = make_float4(chosen, t, dep_new, 0.0f);
+            num_post = num + 1.0f;
+            h0.w = chosen;
+            tail_post = chosen;
+            meta &= ~kMetaGarbage;
+        } else {
+            meta |= kMetaGarbage;
+            h1.y = dep_new;
+        }
+        h1.x = num_post;
+    }
+    h1.w = __int_as_float(meta);
+    s.hot_next[2 * L] = h0;
+    s.hot_next[2 * L + 1] = h1;
+    s.post[L] = make_float4(num_post, tail_post, head_post, dtt);
+}
+
+// (long)a == (long)b and (long)a > 0 of src/response_mpnn.py:66-83 on fp32 operands, without 64-bit conversions
+__device__ __forceinline__ bool same_id(float a, float b) { return truncf(a) == truncf(b); }
+__device__ __forceinline__ bool at_least_one(float a) { return a >= 1.0f; }
+
+__global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Store s, float t,
+                                                            float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
+                                                            int32_t* __restrict__ flags) {
+    __shared__ int s_ptr[kTile + 1];
+    __shared__ float s_head[kTile], s_dtt[kTile];
+    __shared__ uint8_t s_has[kTile], s_acc[kTile];
+    __shared__ uint8_t s_owner[kCap];
+
+    const int tid = threadIdx.x;
+    const int r = blockIdx.y;
+    const int u = blockIdx.x * kTile + tid;
+    const bool valid = u < s.N;
+    const int base = r * s.N;
+    const int L = base + u;
+
+    s_ptr[tid] = g.out_ptr[min(u, s.N)];
+    if (tid == kTile - 1) s_ptr[kTile] = g.out_ptr[min(u + 1, s.N)];
+    float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) P = s.post[L];
+    const bool has_up = at_least_one(P.x);
+    s_head[tid] = P.z;
+    s_dtt[tid] = P.w;
+    s_has[tid] = has_up ? 1 : 0;
+    s_acc[tid] = 0;
+    __syncthreads();
+
+    const int e0 = s_ptr[0], ne = s_ptr[kTile] - e0;
+    const int kb = s_ptr[tid], ke = s_ptr[tid + 1];
+    float* dtt_out = (delta_tt != nullptr) ? delta_tt + (int64_t)r * g.n_edges : nullptr;
+    bool accept = false;
+
+    if (ne <= kCap) {
+        for (int k = kb; k < ke; ++k) s_owner[k - e0] = (uint8_t)tid;
+        __syncthreads();
+        for (int i0 = tid; i0 < ne; i0 += 4 * kTile) {
+            int dn[4], eid[4];
+            float4 D[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * kTile;
+                dn[q] = -1;
+                if (i < ne) {
+                    dn[q] = g.out_dst[e0 + i];
+                    eid[q] = (g.out_eid != nullptr) ? g.out_eid[e0 + i] : e0 + i;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (dn[q] >= 0) D[q] = s.post[base + dn[q]];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (dn[q] >= 0) {
+                    const int o = s_owner[i0 + q * kTile];
+                    if (dtt_out != nullptr) dtt_out[eid[q]] = s_dtt[o];
+                    if (s_has[o] && at_least_one(D[q].x) && same_id(D[q].y, s_head[o])) s_acc[o] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        accept = s_acc[tid] != 0;
+    } else if (valid) {
+        for (int k = kb; k < ke; ++k) {
+            if (dtt_out != nullptr) dtt_out[(g.out_eid != nullptr) ? g.out_eid[k] : k] = P.w;
+            const float4 D = s.post[base + g.out_dst[k]];
+            accept = accept || (has_up && at_least_one(D.x) && same_id(D.y, P.z));
+        }
+    }
+    if (valid) pop[L] = accept ? 1 : 0;
+    accept = accept && valid;
+    if (__syncthreads_or(accept) && tid == 0) flags[TARL_FLAG_ANY_POP] = 1;
+    if (!accept) return;
+
+    float4 h0 = s.hot_next[2 * L], h1 = s.hot_next[2 * L + 1];
+    int meta = __float_as_int(h1.w);
+    const int rh = meta & kMetaRingMask;
+    const int M = s.M;
+    const int q = (int)h1.x;
+    const bool gv = meta & kMetaGarbage;
+    const float4 garbage = make_float4(0.0f, t, h1.y, 0.0f);
+    float4* Q = s.queue + (size_t)L * M;
+    const float4 new_head = (gv && q == 1) ? garbage : Q[rh];
+    if (M > 1) {
+        const float4 last = (gv && q == M) ? garbage : Q[ring_pos(rh, M, M)];
+        Q[rh] = last;
+    } else if (gv && q == 1) {
+        Q[rh] = garbage;
+    }
+    h0.x = new_head.x; h0.y = new_head.y; h0.z = new_head.z;
+    h1.x = h1.x - 1.0f;
+    int nrh = rh + 1; if (nrh >= M) nrh = 0;
+    meta = (meta & ~kMetaRingMask) | nrh;
+    if (gv && q == 1) meta &= ~kMetaGarbage;
     h1.w = __int_as_float(meta);
     s.hot_next[2 * L] = h0;
     s.hot_next[2 * L + 1] = h1;
@@ -302,6 +580,25 @@ int tarl_store_step(const tarl_dual_csr* g, const tarl_link_store* store, const 
     if (s.N == 0) return TARL_OK;
     if (pop == nullptr || (g->n_edges > 0 && attr_in == nullptr)) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (g->n_edges > 0 && (g->in_ptr == nullptr || g->in_src == nullptr || g->out_ptr == nullptr || g->out_dst == nullptr))
+        return TARL_E_BADARG;
+    if (noise != nullptr && g->n_edges > 0 && g->in_eid == nullptr) return TARL_E_BADARG;
+    const uint32_t variant = (phase_mask >> TARL_STEP_VARIANT_SHIFT) & 0xfu;
+    const bool tiled = variant != TARL_STEP_VARIANT_DIRECT && (int64_t)s.N * s.R * 2 < INT32_MAX && s.R <= 65535;
+    if (tiled) {
+        const dim3 grid((s.N + kTile - 1) / kTile, s.R);
+        if (phase_mask & TARL_PHASE_SELECT_APPEND) {
+            if (noise != nullptr)
+                k_tile_select_append<true><<<grid, kTile, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed,
+                                                                   (uint32_t)(seed >> 32), step_id, t, flags);
+            else
+                k_tile_select_append<false><<<grid, kTile, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed,
+                                                                    (uint32_t)(seed >> 32), step_id, t, flags);
+        }
+        if (phase_mask & TARL_PHASE_RESPOND_SHIFT)
+            k_tile_respond_pop<<<grid, kTile, 0, cs>>>(*g, s, t, delta_tt, pop, flags);
+        return launch_status();
+    }
     const int nb = blocks_for((int64_t)s.N * s.R);
     if (phase_mask & TARL_PHASE_SELECT_APPEND)
         k_store_select_append<<<nb, kThreads, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed, (uint32_t)(seed >> 32),

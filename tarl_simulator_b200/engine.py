@@ -15,6 +15,8 @@ from . import _cabi
 from .topology import topology_for
 
 PHASE_SELECT_APPEND, PHASE_RESPOND_POP = 2, 4
+VARIANT_TILED, VARIANT_DIRECT = 0, 1        # kernel variants of tarl_store_step (bit-identical results)
+VARIANT_SHIFT = 8
 
 
 class LinkStore:
@@ -108,7 +110,7 @@ class LinkStore:
         self.sel.view(self.R, self.N).copy_(sel.to(torch.float32).reshape(-1, self.N))
 
     def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
-             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP):
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_TILED):
         """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
         for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8)."""
         if noise is not None:
@@ -123,7 +125,7 @@ class LinkStore:
                 self.topo.ref(), C.byref(self._struct), self.attr_in.data_ptr(),
                 noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
                 delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
-                self._stream(), phase_mask)
+                self._stream(), phase_mask | (variant << VARIANT_SHIFT))
         _cabi.check(rc, "tarl_store_step")
         if phase_mask & PHASE_RESPOND_POP:
             self.cur ^= 1

@@ -43,7 +43,8 @@ class DualTopology:
         self.dst32 = dst.to(torch.int32)
         self.source_sorted = bool(E == 0 or torch.equal(order_out, torch.arange(E, device=dev)))
         self.struct = _cabi.DualCSR(n_links, E, self.in_ptr.data_ptr(), self.in_src.data_ptr(), self.in_eid.data_ptr(),
-                                    self.out_ptr.data_ptr(), self.out_dst.data_ptr(), self.out_eid.data_ptr())
+                                    self.out_ptr.data_ptr(), self.out_dst.data_ptr(),
+                                    None if self.source_sorted else self.out_eid.data_ptr())
 
     def ref(self):
         return C.byref(self.struct)

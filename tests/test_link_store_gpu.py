@@ -26,8 +26,12 @@ def make_store(x0, ei, w, Nmax, use_static, replicas=1, seed=0):
     return LinkStore.from_graph(g, Nmax, replicas=replicas, seed=seed), g
 
 
+VARIANTS = [0, 1]     # tiled (default), direct
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name", CORE_CASES)
-def test_store_matches_reference_goldens(name, golden_dir):
+def test_store_matches_reference_goldens(name, golden_dir, variant):
     d = np.load(os.path.join(golden_dir, name + ".npz"))
     Nmax = int(d["Nmax"])
     x0 = torch.from_numpy(d["x0"])
@@ -38,7 +42,7 @@ def test_store_matches_reference_goldens(name, golden_dir):
     dtt = torch.empty(1, E, device="cuda")
     for s in range(len(d["t"])):
         store.set_selected_road(torch.from_numpy(d["sel"][s]).cuda())
-        pop = store.step(float(d["t"][s]), noise=torch.from_numpy(d["u"][s]).cuda(), delta_tt=dtt)
+        pop = store.step(float(d["t"][s]), noise=torch.from_numpy(d["u"][s]).cuda(), delta_tt=dtt, variant=variant)
         assert torch.equal(store.export_x()[0].cpu(), torch.from_numpy(d["x"][s])), f"x differs after step {s}"
         assert torch.equal(dtt[0].cpu(), torch.from_numpy(d["delta_tt"][s]))
         assert torch.equal(pop[0].bool().cpu(), torch.from_numpy(d["pop"][s]))
@@ -46,10 +50,12 @@ def test_store_matches_reference_goldens(name, golden_dir):
     store.check_errors()
 
 
-@pytest.mark.parametrize("seed,N,Nmax,R", [(21, 4000, 15, 1), (22, 1500, 7, 3), (23, 2500, 40, 2)])
-def test_store_replicas_match_oracle(seed, N, Nmax, R):
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("seed,N,Nmax,R,max_out", [(21, 4000, 15, 1, 4), (22, 1500, 7, 3, 4), (23, 2500, 40, 2, 4),
+                                                    (24, 1200, 15, 2, 24)])   # 24: tiles above the staging capacity
+def test_store_replicas_match_oracle(seed, N, Nmax, R, max_out, variant):
     g = torch.Generator().manual_seed(seed)
-    ei, w = cases.random_dual_graph(g, N, 4, sort_by_source=bool(seed % 2))
+    ei, w = cases.random_dual_graph(g, N, max_out, sort_by_source=bool(seed % 2))
     x0, _ = cases.random_road_state(g, N, Nmax, 500.0, ei)
     c = core_port.Cols(Nmax)
     cc = core_port.static_factors(x0, c)[1]
@@ -63,7 +69,7 @@ def test_store_replicas_match_oracle(seed, N, Nmax, R):
         sel = torch.stack([cases.random_selection(g, N, ei) for _ in range(R)])
         u = torch.stack([cases.uniforms(g, E) for _ in range(R)])
         store.set_selected_road(sel.cuda())
-        pop = store.step(t, noise=u.cuda(), delta_tt=dtt)
+        pop = store.step(t, noise=u.cuda(), delta_tt=dtt, variant=variant)
         out = store.export_x().cpu()
         for r in range(R):
             xs[r][:, c.SEL] = sel[r]
