@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--no-mpnn", action="store_true")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
-    ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel variant: 0 tiled (default), 1 direct")
+    ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel variant: 0 pipelined (default), 1 direct, 2 tiled")
     return ap.parse_args()
 
 
@@ -205,7 +205,8 @@ def run_native(args):
     store.check_errors()
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
-    names = ["k_tile_select_append", "k_tile_respond_pop"] if args.variant == 0 else ["k_store_select_append", "k_store_respond_pop"]
+    names = {0: ["k_pipe_select_append", "k_pipe_respond_pop"], 1: ["k_store_select_append", "k_store_respond_pop"],
+             2: ["k_tile_select_append", "k_tile_respond_pop"]}[args.variant]
     per = {k: 0.0 for k in names}
     pops = 0
     reps = min(args.steps, 20)
@@ -282,7 +283,7 @@ def run_native(args):
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
-                      "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": "tiled" if args.variant == 0 else "direct", "parallelism": f"independent replicas x{world}",
+                      "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": {0: "pipelined", 1: "direct", 2: "tiled"}[args.variant], "parallelism": f"independent replicas x{world}",
                       "state": "resident link store (tarl_store_step), noise drawn in-kernel, delta_tt + pop mask written every step",
                       "l2": "per-step working set larger than the 126 MB L2" if N * R * 150 > 130e6 else
                       "per-step working set fits in L2 (small workload)"},

@@ -109,8 +109,9 @@ int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32
 #define TARL_PHASE_ALL 7u
 /* tarl_store_step only: bits 8..11 of phase_mask pick the kernel variant (results are bit-identical) */
 #define TARL_STEP_VARIANT_SHIFT 8
-#define TARL_STEP_VARIANT_TILED 0u  /* default: one CTA per tile of 256 links, edge-parallel staging in shared memory */
-#define TARL_STEP_VARIANT_DIRECT 1u /* one thread per link walking its own edge segment                            */
+#define TARL_STEP_VARIANT_PIPELINED 0u /* default: persistent CTAs, next tile's inputs staged by bulk async copies  */
+#define TARL_STEP_VARIANT_DIRECT 1u    /* one thread per link walking its own edge segment                           */
+#define TARL_STEP_VARIANT_TILED 2u     /* one CTA per tile of 256 links, edge-parallel staging, no prefetch         */
 int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
                           const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
                           float* delta_tt,

@@ -17,52 +17,11 @@
 // past the tail of every link every step is kept as one pending record per link ("garbage at logical slot int(NUM)",
 // it is always overwritten in place by the next step or consumed by an export), and its shift-left that duplicates the
 // last slot becomes a ring-head increment plus one slot copy. Semantics: SURVEY.md Appendix A.
-#include <cuda_runtime.h>
-#include <float.h>
-#include <stdint.h>
+#include "engine_common.cuh"
 
-#include "tarl_b200.h"
+using namespace tarl;
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kMetaRingMask = 0xffff;
-constexpr int kMetaGarbage = 1 << 16;
-
-__device__ __forceinline__ float max_propagate_nan(float a, float b) {
-    return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
-}
-
-// Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields four uniforms in (0,1).
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, float out[4]) {
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    const uint32_t c[4] = {c0, c1, c2, c3};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = ((float)(c[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-}
-
-struct Store {
-    int N, R, Nmax, M;       // M = Nmax-1 ring slots per link
-    const float4* hot_cur;   // [R*N*2]
-    float4* hot_next;        // [R*N*2]
-    float* sel;              // [R*N]
-    const float4* stat_a;    // [N] {FFTT, cc, ROAD_INDEX, MAXN}
-    const float4* stat_b;    // [N] {LENGTH, MAX_FLOW, 0, 0}
-    float4* queue;           // [R*N*M]
-    float4* post;            // [R*N]
-};
-
-__device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logical slot 1..M -> physical 0..M-1
-    int p = rh + logical - 1;
-    return p >= M ? p - M : p;
-}
 
 // ------------------------------------------------------------------------------------------------ import / export
 __global__ void __launch_bounds__(kThreads) k_store_import(Store s, const float* __restrict__ x, int64_t row_stride,
@@ -259,7 +218,7 @@ constexpr int kTile = 256;
 constexpr int kCap = 2048;
 
 template <bool kExtNoise>
-__global__ void __launch_bounds__(kTile) k_tile_select_append(
+__global__ void __launch_bounds__(kTile, 4) k_tile_select_append(
     tarl_dual_csr g, Store s, const float* __restrict__ attr_in, const float* __restrict__ noise, uint32_t seed_lo,
     uint32_t seed_hi, uint32_t step_id, float t, int32_t* __restrict__ flags) {
     __shared__ int s_ptr[kTile + 1];
@@ -268,10 +227,13 @@ __global__ void __launch_bounds__(kTile) k_tile_select_append(
     __shared__ uint8_t s_owner[kCap];
     __shared__ float s_p[kCap], s_id[kCap];
     __shared__ float s_u[kExtNoise ? kCap : 1];
+    __shared__ uint8_t s_list[kTile];
+    __shared__ int s_count;
 
     const int tid = threadIdx.x;
     const int r = blockIdx.y;
     const int d = blockIdx.x * kTile + tid;
+    if (tid == 0) s_count = 0;
     const bool valid = d < s.N;
     const int base = r * s.N;
     const int L = base + d;
@@ -343,22 +305,36 @@ __global__ void __launch_bounds__(kTile) k_tile_select_append(
         }
         __syncthreads();
         for (int k = kb; k < ke; ++k) psum += s_p[k - e0];
-        if (psum > 0.0f) {   // the scores only matter where somebody is eligible (src/direction_mpnn.py:142-144)
+        // The scores only matter where somebody is eligible (src/direction_mpnn.py:142-144): compact those links so
+        // that the three logf per candidate run on dense warps instead of on ~1 lane in 4.
+        if (psum > 0.0f) s_list[atomicAdd(&s_count, 1)] = (uint8_t)tid;
+        __syncthreads();
+        const int n_list = s_count;
+        for (int w = tid; w < n_list; w += kTile) {
+            const int o = s_list[w];
+            const int ob = s_ptr[o], oe = s_ptr[o + 1];
+            const uint32_t Lo = (uint32_t)(L - tid + o);
+            float b = -FLT_MAX, bid = 0.0f;
+            bool hv = false;
             float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-            for (int k = kb; k < ke; ++k) {
-                const int j = k - kb;
+            for (int k = ob; k < oe; ++k) {
+                const int j = k - ob;
                 float uu;
                 if (kExtNoise) {
                     uu = s_u[k - e0];
                 } else {
-                    if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
+                    if ((j & 3) == 0) philox4x32_10(Lo, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
                     const int jj = j & 3;
                     uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
                 }
                 const float sc = logf(s_p[k - e0] + 1e-12f) + (-logf(-logf(uu)));
-                if (sc > best) { best = sc; best_id = s_id[k - e0]; have = true; }
+                if (sc > b) { b = sc; bid = s_id[k - e0]; hv = true; }
             }
+            s_room[o] = bid;             // the downstream-side terms are no longer needed: reuse as the result slots
+            s_free[o] = hv ? 1 : 0;
         }
+        __syncthreads();
+        if (psum > 0.0f) { best_id = s_room[tid]; have = s_free[tid] != 0; }
     } else if (valid) {
         float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
         for (int k = kb; k < ke; ++k) {
@@ -422,9 +398,6 @@ __global__ void __launch_bounds__(kTile) k_tile_select_append(
     s.post[L] = make_float4(num_post, tail_post, head_post, dtt);
 }
 
-// (long)a == (long)b and (long)a > 0 of src/response_mpnn.py:66-83 on fp32 operands, without 64-bit conversions
-__device__ __forceinline__ bool same_id(float a, float b) { return truncf(a) == truncf(b); }
-__device__ __forceinline__ bool at_least_one(float a) { return a >= 1.0f; }
 
 __global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Store s, float t,
                                                             float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
@@ -446,6 +419,9 @@ __global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Sto
     float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) P = s.post[L];
     const bool has_up = at_least_one(P.x);
+    // a link with agents may pop: fetch the second half of its record now, off the critical path of the edge phase
+    float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && has_up) h1 = s.hot_next[2 * L + 1];
     s_head[tid] = P.z;
     s_dtt[tid] = P.w;
     s_has[tid] = has_up ? 1 : 0;
@@ -498,7 +474,7 @@ __global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Sto
     if (__syncthreads_or(accept) && tid == 0) flags[TARL_FLAG_ANY_POP] = 1;
     if (!accept) return;
 
-    float4 h0 = s.hot_next[2 * L], h1 = s.hot_next[2 * L + 1];
+    // h1 was fetched up front; h0 need not be read at all: its tail id is post.y, the rest is replaced by the new head
     int meta = __float_as_int(h1.w);
     const int rh = meta & kMetaRingMask;
     const int M = s.M;
@@ -513,13 +489,12 @@ __global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Sto
     } else if (gv && q == 1) {
         Q[rh] = garbage;
     }
-    h0.x = new_head.x; h0.y = new_head.y; h0.z = new_head.z;
     h1.x = h1.x - 1.0f;
     int nrh = rh + 1; if (nrh >= M) nrh = 0;
     meta = (meta & ~kMetaRingMask) | nrh;
     if (gv && q == 1) meta &= ~kMetaGarbage;
     h1.w = __int_as_float(meta);
-    s.hot_next[2 * L] = h0;
+    s.hot_next[2 * L] = make_float4(new_head.x, new_head.y, new_head.z, P.y);
     s.hot_next[2 * L + 1] = h1;
 }
 
@@ -584,6 +559,8 @@ int tarl_store_step(const tarl_dual_csr* g, const tarl_link_store* store, const 
         return TARL_E_BADARG;
     if (noise != nullptr && g->n_edges > 0 && g->in_eid == nullptr) return TARL_E_BADARG;
     const uint32_t variant = (phase_mask >> TARL_STEP_VARIANT_SHIFT) & 0xfu;
+    if (variant == TARL_STEP_VARIANT_PIPELINED && pipelined_step_supported(*g, s, attr_in))
+        return launch_pipelined_step(*g, s, attr_in, noise, seed, step_id, t, delta_tt, pop, flags, cs, phase_mask);
     const bool tiled = variant != TARL_STEP_VARIANT_DIRECT && (int64_t)s.N * s.R * 2 < INT32_MAX && s.R <= 65535;
     if (tiled) {
         const dim3 grid((s.N + kTile - 1) / kTile, s.R);

@@ -1,0 +1,61 @@
+// engine_common.cuh — shared device helpers of the resident link store kernels (engine.cu, engine_pipe.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "tarl_b200.h"
+
+namespace tarl {
+
+constexpr int kThreads = 256;
+constexpr int kMetaRingMask = 0xffff;
+constexpr int kMetaGarbage = 1 << 16;
+
+__device__ __forceinline__ float max_propagate_nan(float a, float b) {
+    return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields four uniforms in (0,1).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, float out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint32_t c[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = ((float)(c[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+
+struct Store {
+    int N, R, Nmax, M;       // M = Nmax-1 ring slots per link
+    const float4* hot_cur;   // [R*N*2]
+    float4* hot_next;        // [R*N*2]
+    float* sel;              // [R*N]
+    const float4* stat_a;    // [N] {FFTT, cc, ROAD_INDEX, MAXN}
+    const float4* stat_b;    // [N] {LENGTH, MAX_FLOW, 0, 0}
+    float4* queue;           // [R*N*M]
+    float4* post;            // [R*N]
+};
+
+__device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logical slot 1..M -> physical 0..M-1
+    int p = rh + logical - 1;
+    return p >= M ? p - M : p;
+}
+
+
+// (long)a == (long)b and (long)a > 0 of src/response_mpnn.py:66-83 on fp32 operands, without 64-bit conversions
+__device__ __forceinline__ bool same_id(float a, float b) { return truncf(a) == truncf(b); }
+__device__ __forceinline__ bool at_least_one(float a) { return a >= 1.0f; }
+
+// engine_pipe.cu: the pipelined (bulk-copy staged) step kernels; returns a TARL_* code
+bool pipelined_step_supported(const tarl_dual_csr& g, const Store& s, const float* attr_in);
+int launch_pipelined_step(const tarl_dual_csr& g, const Store& s, const float* attr_in, const float* noise, uint64_t seed,
+                          uint32_t step_id, float t, float* delta_tt, uint8_t* pop, int32_t* flags, cudaStream_t stream,
+                          uint32_t phase_mask);
+
+}  // namespace tarl

@@ -15,7 +15,7 @@ from . import _cabi
 from .topology import topology_for
 
 PHASE_SELECT_APPEND, PHASE_RESPOND_POP = 2, 4
-VARIANT_TILED, VARIANT_DIRECT = 0, 1        # kernel variants of tarl_store_step (bit-identical results)
+VARIANT_PIPELINED, VARIANT_DIRECT, VARIANT_TILED = 0, 1, 2    # kernel variants of tarl_store_step (bit-identical)
 VARIANT_SHIFT = 8
 
 
@@ -110,7 +110,7 @@ class LinkStore:
         self.sel.view(self.R, self.N).copy_(sel.to(torch.float32).reshape(-1, self.N))
 
     def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
-             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_TILED):
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_PIPELINED):
         """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
         for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8)."""
         if noise is not None:
