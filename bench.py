@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--no-mpnn", action="store_true")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
-    ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel variant: 0 pipelined (default), 1 direct, 2 tiled")
+    ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel family: 0 ELL (default), 1 CSR")
     return ap.parse_args()
 
 
@@ -205,22 +205,23 @@ def run_native(args):
     store.check_errors()
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
-    names = {0: ["k_pipe_select_append", "k_pipe_respond_pop"], 1: ["k_store_select_append", "k_store_respond_pop"],
-             2: ["k_tile_select_append", "k_tile_respond_pop"]}[args.variant]
+    names = {0: ["k_ell_select_append", "k_ell_respond_pop"], 1: ["k_csr_select_append", "k_csr_respond_pop"]}[args.variant]
     per = {k: 0.0 for k in names}
-    pops = 0
     reps = min(args.steps, 20)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    for _ in range(reps):
-        evs[0].record(stream)
+    pops_dev = torch.zeros((), dtype=torch.int64, device=dev)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3 * reps)]
+    for i in range(reps):          # everything enqueued back to back; one synchronise at the end
+        evs[3 * i].record(stream)
         step(PHASE_SELECT_APPEND)
-        evs[1].record(stream)
+        evs[3 * i + 1].record(stream)
         step(PHASE_RESPOND_POP)
-        evs[2].record(stream)
-        torch.cuda.synchronize(dev)
-        per[names[0]] += evs[0].elapsed_time(evs[1])
-        per[names[1]] += evs[1].elapsed_time(evs[2])
-        pops += int(store.pop[: N * R].sum().item())
+        evs[3 * i + 2].record(stream)
+        pops_dev += store.pop[: N * R].sum()
+    torch.cuda.synchronize(dev)
+    for i in range(reps):
+        per[names[0]] += evs[3 * i].elapsed_time(evs[3 * i + 1])
+        per[names[1]] += evs[3 * i + 1].elapsed_time(evs[3 * i + 2])
+    pops = int(pops_dev.item())
     p = pops / (reps * N * R)
     per = {k: v / reps for k, v in per.items()}
     store.check_errors()
@@ -283,7 +284,7 @@ def run_native(args):
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
-                      "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": {0: "pipelined", 1: "direct", 2: "tiled"}[args.variant], "parallelism": f"independent replicas x{world}",
+                      "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": {0: "ell", 1: "csr"}[args.variant], "parallelism": f"independent replicas x{world}",
                       "state": "resident link store (tarl_store_step), noise drawn in-kernel, delta_tt + pop mask written every step",
                       "l2": "per-step working set larger than the 126 MB L2" if N * R * 150 > 130e6 else
                       "per-step working set fits in L2 (small workload)"},

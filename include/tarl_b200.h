@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 1
+#define TARL_ABI_VERSION 2
 
 /* return codes */
 #define TARL_OK 0
@@ -107,11 +107,6 @@ int tarl_core_step(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32
 #define TARL_PHASE_SELECT_APPEND 2u /* masks + Gumbel arg-max per downstream link, tail append      */
 #define TARL_PHASE_RESPOND_SHIFT 4u /* acknowledgement, delta_tt, FIFO shift of popping links       */
 #define TARL_PHASE_ALL 7u
-/* tarl_store_step only: bits 8..11 of phase_mask pick the kernel variant (results are bit-identical) */
-#define TARL_STEP_VARIANT_SHIFT 8
-#define TARL_STEP_VARIANT_PIPELINED 0u /* default: persistent CTAs, next tile's inputs staged by bulk async copies  */
-#define TARL_STEP_VARIANT_DIRECT 1u    /* one thread per link walking its own edge segment                           */
-#define TARL_STEP_VARIANT_TILED 2u     /* one CTA per tile of 256 links, edge-parallel staging, no prefetch         */
 int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride, int32_t nmax,
                           const float* edge_attr, const float* cc, const float* noise, const float* sel, float t,
                           float* delta_tt,
@@ -129,7 +124,8 @@ typedef struct tarl_link_store {
     int32_t n_replicas; /* R >= 1: independent copies of the network state (PPO rollout environments)    */
     int32_t nmax;       /* Nmax (FIFO slots per link)                                                    */
     int32_t reserved;
-    void* hot_cur;      /* [R*N] 32-byte records holding the CURRENT state                               */
+    void* hot_cur;      /* [R*N] 32-byte records holding the CURRENT state: {head id, head exit, NUM, MAXN |
+                           head arrival, tail id, pending tail-garbage exit time, meta}                   */
     void* hot_next;     /* [R*N] 32-byte records written by the step; the caller swaps the two afterwards */
     void* sel;          /* [R*N] fp32 SELECTED_ROAD                                                      */
     void* stat_a;       /* [N] 16-byte {FFTT, congestion_constant, ROAD_INDEX, MAXN}                     */
@@ -148,14 +144,26 @@ int tarl_store_import(const tarl_link_store* store, const float* x, int64_t x_ro
 int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stride, int64_t x_replica_stride,
                       float t_last_step, void* stream);
 
+/* Optional ELLPACK copy of the first `width` edges of every link, column-major: entry j of link n at [j*pitch + n].
+ * -1 = no such edge. A link with MORE than `width` in-edges (out-edges) carries -2 in column width-1 of in_src
+ * (out_dst) and is served from its CSR segment instead. Edge order inside a link is the CSR's (ascending edge id). */
+typedef struct tarl_dual_ell {
+    int32_t width;          /* 4 or 8                                                        */
+    int32_t pitch;          /* elements between consecutive columns, >= n_links               */
+    const int32_t* in_src;  /* [width*pitch] upstream link of the j-th in-edge                */
+    const float* in_attr;   /* [width*pitch] edge_attr_routes of that edge                    */
+    const int32_t* out_dst; /* [width*pitch] downstream link of the j-th out-edge             */
+} tarl_dual_ell;
+
 /* SimulationCoreModel.forward on the store (src/simulation_core_model.py:41-83): reads hot_cur, writes hot_next.
+ * ell: NULL (every link walks its CSR segment) or the ELLPACK copy above (same results, shorter dependent-load chain).
  * attr_in: edge_attr_routes permuted into g->in_* order. noise: [R*E] uniforms in original edge order per replica, or
- * NULL to draw them in-kernel (Philox4x32-10 keyed by seed, counter = (replica*N+link, step_id, in-edge rank/4) — a
+ * NULL to draw them in-kernel (Philox4x32-10 keyed by seed, counter = (replica*N+link, 0, step_id, in-edge rank/4) — a
  * documented stream of its own, not torch's). delta_tt: [R*E] or NULL. pop: [R*N]. phase_mask: TARL_PHASE_SELECT_APPEND
  * | TARL_PHASE_RESPOND_SHIFT (both for a full step). */
-int tarl_store_step(const tarl_dual_csr* g, const tarl_link_store* store, const float* attr_in, const float* noise,
-                    uint64_t seed, uint32_t step_id, float t, float* delta_tt, uint8_t* pop, int32_t* flags,
-                    void* stream, uint32_t phase_mask);
+int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
+                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).

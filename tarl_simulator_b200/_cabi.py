@@ -27,6 +27,12 @@ class DualCSR(C.Structure):
                 ("out_ptr", C.c_void_p), ("out_dst", C.c_void_p), ("out_eid", C.c_void_p)]
 
 
+class DualELL(C.Structure):
+    """struct tarl_dual_ell"""
+    _fields_ = [("width", C.c_int32), ("pitch", C.c_int32), ("in_src", C.c_void_p), ("in_attr", C.c_void_p),
+                ("out_dst", C.c_void_p)]
+
+
 class CSR(C.Structure):
     """struct tarl_csr"""
     _fields_ = [("n_rows", C.c_int32), ("n_edges", C.c_int32), ("ptr", C.c_void_p), ("idx", C.c_void_p),
@@ -44,6 +50,7 @@ _P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_
 _STORE = C.POINTER(LinkStore)
 _CSR = C.POINTER(DualCSR)
 _CSR1 = C.POINTER(CSR)
+_ELL = C.POINTER(DualELL)
 
 # name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
 SIGNATURES = {
@@ -56,7 +63,7 @@ SIGNATURES = {
     "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
     "tarl_store_import": (C.c_int, [_STORE, _P, _I64, _I64, _P, _P, _P]),
     "tarl_store_export": (C.c_int, [_STORE, _P, _I64, _I64, _F, _P]),
-    "tarl_store_step": (C.c_int, [_CSR, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
+    "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_backward": (C.c_int, [_CSR1, _P, _P, _I32, _P, _P, _I32, _P]),
     "tarl_graphdist_partial_count": (_I32, [_I32]),

@@ -22,7 +22,6 @@ COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-l
 PER_FILE = {
     "core_step.cu": ["-fmad=false"],
     "engine.cu": ["-fmad=false"],
-    "engine_pipe.cu": ["-fmad=false"],
     "agents.cu": ["-fmad=false"],
 }
 

@@ -1,13 +1,13 @@
-// engine.cu — the resident link store: the same per-timestep network step as core_step.cu, on a compact device
-// layout that moves ~1x the algorithmic bytes instead of ~4x (sm_100a). Compiled with -fmad=false.
+// engine.cu — the resident link store: the per-timestep network step of core_step.cu on a compact device layout that
+// moves ~1x the algorithmic bytes instead of ~4x (sm_100a). Compiled with -fmad=false.
 //
 // Why: on the reference's 208-byte AoS rows (Nmax=15) the step has to read every row whole, write 4 partial sectors
 // per link for the mandatory tail write, and shift 3*(Nmax-1) floats per popped link (profiles/r01_a: 796 MB of DRAM
-// traffic per step for 213 MB algorithmic at 1M links). The store keeps, per link,
+// traffic per step for 213 MB algorithmic at 1M links). The store keeps, per (replica, link),
 //
-//   hot   32 B  {head id, head arrival, head exit, tail id | NUM, pending-garbage exit time, MAXN, meta}
-//               read once and rewritten whole every step (full-sector writes, ping-pong buffers: phase A gathers the
-//               PRE-step records of upstream links while owners write POST-step records elsewhere)
+//   hot   32 B  A = {head id, head exit, NUM, MAXN} | B = {head arrival, tail id, pending-garbage exit time, meta}
+//               read once and rewritten whole every step (full-sector writes, ping-pong buffers: the direction phase
+//               gathers the PRE-step A halves of upstream links while owners write POST-step records elsewhere)
 //   sel    4 B  SELECTED_ROAD (the per-step routing input, its own array so that choice/actions write it coalesced)
 //   queue 16 B x (Nmax-1) ring of {id, arrival, exit} for logical FIFO slots 1..Nmax-1 (slot 0 lives in `hot`),
 //               touched only by real admissions (one slot write) and pops (one slot read + one slot copy)
@@ -15,8 +15,17 @@
 //
 // and reproduces the reference's x EXACTLY on export, including its quirks: the tail triplet (0, t, t+tt) it writes
 // past the tail of every link every step is kept as one pending record per link ("garbage at logical slot int(NUM)",
-// it is always overwritten in place by the next step or consumed by an export), and its shift-left that duplicates the
+// always overwritten in place by the next step or consumed by an export), and its shift-left that duplicates the
 // last slot becomes a ring-head increment plus one slot copy. Semantics: SURVEY.md Appendix A.
+//
+// Two kernel families, bit-identical results:
+//   *_csr  one thread per link walking its edge segment of the CSR (in_ptr -> in_src -> record: three dependent loads
+//          per edge; any degree);
+//   *_ell  the same thread reads its first W edges from an ELLPACK copy of the topology (column j of link d at
+//          [j*pitch + d]): all W edge slots load coalesced and INDEPENDENTLY of any pointer array, so the dependent
+//          chain is two levels deep (edge slots -> neighbour records) with 2W gathers in flight per thread. Road
+//          networks have near-uniform small degree, which is exactly the case ELL is made for; links with more than W
+//          edges fall back to their CSR segment.
 #include "engine_common.cuh"
 
 using namespace tarl;
@@ -37,8 +46,8 @@ __global__ void __launch_bounds__(kThreads) k_store_import(Store s, const float*
     const bool bad = !(num >= 0.0f) || !(num <= (float)Nmax);
     if (bad) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
     const int cnt = bad ? 0 : (int)num;
-    hot[2 * L] = make_float4(row[0], row[Nmax], row[2 * Nmax], row[max(cnt - 1, 0)]);
-    hot[2 * L + 1] = make_float4(num, 0.0f, maxn, __int_as_float(0));
+    hot[2 * L] = make_float4(row[0], row[2 * Nmax], num, maxn);
+    hot[2 * L + 1] = make_float4(row[Nmax], row[max(cnt - 1, 0)], 0.0f, __int_as_float(0));
     s.sel[L] = row[c0 + 5];
     for (int k = 1; k <= s.M; ++k)
         s.queue[L * s.M + (k - 1)] = make_float4(row[k], row[Nmax + k], row[2 * Nmax + k], 0.0f);
@@ -58,135 +67,216 @@ __global__ void __launch_bounds__(kThreads) k_store_export(Store s, float* __res
     const int r = (int)(L / s.N), n = (int)(L % s.N);
     float* row = x + r * rep_stride + (int64_t)n * row_stride;
     const int Nmax = s.Nmax, c0 = 3 * Nmax;
-    const float4 h0 = s.hot_cur[2 * L], h1 = s.hot_cur[2 * L + 1];
-    const int meta = __float_as_int(h1.w);
+    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
+    const int meta = __float_as_int(hB.w);
     const int rh = meta & kMetaRingMask;
-    const int gslot = (meta & kMetaGarbage) ? (int)h1.x : -1;
-    row[0] = h0.x; row[Nmax] = h0.y; row[2 * Nmax] = h0.z;
+    const int gslot = (meta & kMetaGarbage) ? (int)hA.z : -1;
+    row[0] = hA.x; row[Nmax] = hB.x; row[2 * Nmax] = hA.y;
     for (int k = 1; k <= s.M; ++k) {
         float4 v = s.queue[L * s.M + ring_pos(rh, k, s.M)];
-        if (k == gslot) v = make_float4(0.0f, t_garbage, h1.y, 0.0f);
+        if (k == gslot) v = make_float4(0.0f, t_garbage, hB.z, 0.0f);
         row[k] = v.x; row[Nmax + k] = v.y; row[2 * Nmax + k] = v.z;
     }
     const float4 a = s.stat_a[n], b = s.stat_b[n];
-    row[c0] = h1.z; row[c0 + 1] = h1.x; row[c0 + 2] = a.x; row[c0 + 3] = b.x; row[c0 + 4] = b.y;
+    row[c0] = hA.w; row[c0 + 1] = hA.z; row[c0 + 2] = a.x; row[c0 + 3] = b.x; row[c0 + 4] = b.y;
     row[c0 + 5] = s.sel[L]; row[c0 + 6] = a.z;
 }
 
 // ------------------------------------------------------------------------------------------------ direction phase
-// One thread per (replica, downstream link d). Reads its own record and the PRE-step records of its upstream links,
-// runs masks + Gumbel arg-max in ascending original edge id (src/direction_mpnn.py:74-99,133-144), then applies the
-// tail write to its own record (:171-195) and publishes the post-append summary.
-__global__ void __launch_bounds__(kThreads) k_store_select_append(
-    tarl_dual_csr g, Store s, const float* __restrict__ attr_in, const float* __restrict__ noise, uint32_t seed_lo,
-    uint32_t seed_hi, uint32_t step_id, float t, int32_t* __restrict__ flags) {
-    const int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= (int64_t)s.N * s.R) return;
-    const int r = (int)(L / s.N), d = (int)(L % s.N);
-    const int64_t base = (int64_t)r * s.N;
-    float4 h0 = s.hot_cur[2 * L], h1 = s.hot_cur[2 * L + 1];
-    const float4 st = s.stat_a[d];
-    const float num = h1.x, maxn = h1.z, fftt = st.x, ridx_d = st.z;
-    int meta = __float_as_int(h1.w);
-    const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
-    const bool free_d = num < (maxn - 3.0f);
-    const float room_d = maxn - num;
+struct Noise {
+    const float* ext;        // [R*E] uniforms in original edge order, or nullptr for the in-kernel Philox stream
+    uint32_t seed_lo, seed_hi, step_id;
+};
 
-    float best = -FLT_MAX, best_id = 0.0f, psum = 0.0f;
-    bool have = false;
+// p_e of src/direction_mpnn.py:81-91 for the edge u -> d. U = A half of the upstream record (pre-step).
+__device__ __forceinline__ float edge_prob(const float4 U, float sel_u, float t, bool free_d, float room_d, float ridx_d,
+                                           float attr) {
+    const bool a1 = (U.y <= t) && (U.z > 0.0f);
+    const bool a2 = ((U.y - t) < -10.0f) && ((U.w - 3.0f) <= U.z);
+    const bool match = (sel_u == ridx_d);
+    const bool m = (a1 && free_d && match) || (a2 && ((U.w - U.z) <= room_d) && match);
+    return attr * (m ? 1.0f : 0.0f);
+}
+
+__device__ __forceinline__ float gumbel_score(float p, float u) {     // src/direction_mpnn.py:137-138
+    return logf(p + 1e-12f) + (-logf(-logf(u)));
+}
+
+struct Pick {
+    float psum, id;
+    bool have;
+};
+
+// The whole in-edge scan of link d out of the CSR, in ascending original edge id: probability sum, then — only where it
+// is positive (src/direction_mpnn.py:142-144) — the Gumbel arg-max with strict '>' (lowest edge id wins ties).
+template <bool kExtNoise>
+__device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Store& s, const float* __restrict__ attr_in,
+                                               const Noise& nz, int r, int d, int L, float t, bool free_d, float room_d,
+                                               float ridx_d) {
+    const int base = L - d;
     const int k0 = g.in_ptr[d], k1 = g.in_ptr[d + 1];
+    Pick out = {0.0f, 0.0f, false};
+    for (int k = k0; k < k1; ++k) {
+        const int Lu = base + g.in_src[k];
+        out.psum += edge_prob(s.hot_cur[2 * Lu], s.sel[Lu], t, free_d, room_d, ridx_d, attr_in[k]);
+    }
+    if (!(out.psum > 0.0f)) return out;
+    float best = -FLT_MAX;
     float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
     for (int k = k0; k < k1; ++k) {
         const int j = k - k0;
-        const int64_t Lu = base + g.in_src[k];
-        const float4 u0 = s.hot_cur[2 * Lu], u1 = s.hot_cur[2 * Lu + 1];
-        const float sel_u = s.sel[Lu];
-        const bool a1 = (u0.z <= t) && (u1.x > 0.0f);
-        const bool a2 = ((u0.z - t) < -10.0f) && ((u1.z - 3.0f) <= u1.x);
-        const bool match = (sel_u == ridx_d);
-        const bool m = (a1 && free_d && match) || (a2 && ((u1.z - u1.x) <= room_d) && match);
-        const float p = attr_in[k] * (m ? 1.0f : 0.0f);
-        psum += p;
+        const int Lu = base + g.in_src[k];
+        const float4 U = s.hot_cur[2 * Lu];
+        const float p = edge_prob(U, s.sel[Lu], t, free_d, room_d, ridx_d, attr_in[k]);
         float uu;
-        if (noise != nullptr) {
-            uu = noise[(int64_t)r * g.n_edges + g.in_eid[k]];
+        if (kExtNoise) {
+            uu = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k]];
         } else {
-            if ((j & 3) == 0) philox4x32_10((uint32_t)L, (uint32_t)(L >> 32), step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
+            if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
             const int jj = j & 3;
             uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
         }
-        const float sc = logf(p + 1e-12f) + (-logf(-logf(uu)));
-        if (sc > best) { best = sc; best_id = u0.x; have = true; }
+        const float sc = gumbel_score(p, uu);
+        if (sc > best) { best = sc; out.id = U.x; out.have = true; }
     }
+    return out;
+}
+
+// Tail append on the link's own record (src/direction_mpnn.py:171-195, on EVERY link) and the post summary.
+__device__ __forceinline__ void append_and_publish(const Store& s, int L, float4 hA, float4 hB, const float4 st,
+                                                   const Pick pk, float t, int32_t* __restrict__ flags) {
+    const float num = hA.z, maxn = hA.w, fftt = st.x;
+    int meta = __float_as_int(hB.w);
+    const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
     float chosen = 0.0f;
-    if (psum > 0.0f) {
-        if (!have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
-        else chosen = best_id;
+    if (pk.psum > 0.0f) {
+        if (!pk.have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
+        else chosen = pk.id;
     }
-    const float dtt = max_propagate_nan((h0.z - h0.y) - fftt, 0.0f);
-    float num_post = num, tail_post = h0.w, head_post = h0.x;
+    const float dtt = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);      // :94-95, pre-step head
+    float num_post = num, tail_post = hB.y, head_post = hA.x;
     if (bad) {
         atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
     } else {
         const int q = (int)num;
         const float dep_new = t + max_propagate_nan(fftt, st.y / ((maxn + 10.0f) - num));
         if (q == 0) {                       // the tail slot IS the head slot
-            h0.x = chosen; h0.y = t; h0.z = dep_new;
+            hA.x = chosen; hB.x = t; hA.y = dep_new;
             head_post = chosen;
             tail_post = chosen;
             meta &= ~kMetaGarbage;
-            if (chosen != 0.0f) { num_post = num + 1.0f; h0.w = chosen; }
+            if (chosen != 0.0f) { num_post = num + 1.0f; hB.y = chosen; }
         } else if (chosen != 0.0f) {        // a real admission: one ring slot write
-            s.queue[L * s.M + ring_pos(meta & kMetaRingMask, q, s.M)] = make_float4(chosen, t, dep_new, 0.0f);
+            s.queue[(size_t)L * s.M + ring_pos(meta & kMetaRingMask, q, s.M)] = make_float4(chosen, t, dep_new, 0.0f);
             num_post = num + 1.0f;
-            h0.w = chosen;
+            hB.y = chosen;
             tail_post = chosen;
             meta &= ~kMetaGarbage;
         } else {                            // the reference writes (0, t, t+tt) past the tail: keep it pending
             meta |= kMetaGarbage;
-            h1.y = dep_new;
+            hB.z = dep_new;
         }
-        h1.x = num_post;
+        hA.z = num_post;
     }
-    h1.w = __int_as_float(meta);
-    s.hot_next[2 * L] = h0;
-    s.hot_next[2 * L + 1] = h1;
+    hB.w = __int_as_float(meta);
+    s.hot_next[2 * (size_t)L] = hA;
+    s.hot_next[2 * (size_t)L + 1] = hB;
     s.post[L] = make_float4(num_post, tail_post, head_post, dtt);
 }
 
-// ------------------------------------------------------------------------------------------------ response phase
-// One thread per (replica, upstream link u): OR over out-edges of "tail(d) == head(u)" on the post-append summaries
-// (src/response_mpnn.py:66-83), delta_travel_time for its out-edges, and the pop itself (:119-122) as a ring-head
-// increment: new head <- logical slot 1, and the slot that becomes logical Nmax-1 <- old logical Nmax-1 (the
-// reference's shift leaves the last slot in place, i.e. duplicates it).
-__global__ void __launch_bounds__(kThreads) k_store_respond_pop(tarl_dual_csr g, Store s, float t,
-                                                                float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
+template <bool kExtNoise>
+__global__ void __launch_bounds__(kThreads) k_csr_select_append(tarl_dual_csr g, Store s,
+                                                                const float* __restrict__ attr_in, Noise nz, float t,
                                                                 int32_t* __restrict__ flags) {
-    const int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= (int64_t)s.N * s.R) return;
-    const int r = (int)(L / s.N), u = (int)(L % s.N);
-    const int64_t base = (int64_t)r * s.N;
-    const float4 P = s.post[L];
-    const bool has_up = (long long)P.x > 0;
-    const long long head = (long long)P.z;
-    bool accept = false;
-    const int k1 = g.out_ptr[u + 1];
-    for (int k = g.out_ptr[u]; k < k1; ++k) {
-        if (delta_tt != nullptr) delta_tt[(int64_t)r * g.n_edges + (g.out_eid != nullptr ? g.out_eid[k] : k)] = P.w;
-        const float4 D = s.post[base + g.out_dst[k]];
-        accept = accept || (has_up && ((long long)D.x > 0) && ((long long)D.y == head));
+    const int d = blockIdx.x * kThreads + threadIdx.x;
+    if (d >= s.N) return;
+    const int r = blockIdx.y;
+    const int L = r * s.N + d;
+    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
+    const float4 st = s.stat_a[d];
+    const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
+    append_and_publish(s, L, hA, hB, st, pk, t, flags);
+}
+
+template <int W, bool kExtNoise>
+__global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g, tarl_dual_ell ell, Store s,
+                                                                const float* __restrict__ attr_in, Noise nz, float t,
+                                                                int32_t* __restrict__ flags) {
+    const int d = blockIdx.x * kThreads + threadIdx.x;
+    if (d >= s.N) return;
+    const int r = blockIdx.y;
+    const int base = r * s.N;
+    const int L = base + d;
+    // level 1: everything addressed by the link id alone
+    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
+    const float4 st = s.stat_a[d];
+    int u[W];
+    float a[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        u[j] = ell.in_src[(size_t)j * ell.pitch + d];
+        a[j] = ell.in_attr[(size_t)j * ell.pitch + d];
     }
-    pop[L] = accept ? 1 : 0;
-    if (!accept) return;
-    flags[TARL_FLAG_ANY_POP] = 1;
-    float4 h0 = s.hot_next[2 * L], h1 = s.hot_next[2 * L + 1];
-    int meta = __float_as_int(h1.w);
+    const bool free_d = hA.z < (hA.w - 3.0f);
+    const float room_d = hA.w - hA.z, ridx_d = st.z;
+    Pick pk = {0.0f, 0.0f, false};
+    if (u[W - 1] == -2) {     // more than W in-edges: this link walks its CSR segment instead
+        pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, free_d, room_d, ridx_d);
+    } else {
+        // level 2: the neighbours' records, all gathers in flight together
+        float4 U[W];
+        float S[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            if (u[j] >= 0) {
+                U[j] = s.hot_cur[2 * (base + u[j])];
+                S[j] = s.sel[base + u[j]];
+            }
+        }
+        float p[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            p[j] = 0.0f;
+            if (u[j] >= 0) {
+                p[j] = edge_prob(U[j], S[j], t, free_d, room_d, ridx_d, a[j]);
+                pk.psum += p[j];
+            }
+        }
+        if (pk.psum > 0.0f) {
+            float best = -FLT_MAX;
+            float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+            const int k0 = kExtNoise ? g.in_ptr[d] : 0;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                if (u[j] >= 0) {
+                    float uu;
+                    if (kExtNoise) {
+                        uu = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k0 + j]];
+                    } else {
+                        if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+                        uu = un[j & 3];
+                    }
+                    const float sc = gumbel_score(p[j], uu);
+                    if (sc > best) { best = sc; pk.id = U[j].x; pk.have = true; }
+                }
+            }
+        }
+    }
+    append_and_publish(s, L, hA, hB, st, pk, t, flags);
+}
+
+// ------------------------------------------------------------------------------------------------ response phase
+// The pop itself (src/response_mpnn.py:119-122) as a ring-head increment: new head <- logical slot 1, and the slot that
+// becomes logical Nmax-1 <- old logical Nmax-1 (the reference's shift leaves the last slot in place, i.e. duplicates it).
+__device__ __forceinline__ void pop_head(const Store& s, int L, float4 hB, float t) {
+    const float4 hA = s.hot_next[2 * (size_t)L];
+    int meta = __float_as_int(hB.w);
     const int rh = meta & kMetaRingMask;
     const int M = s.M;
-    const int q = (int)h1.x;                                    // >= 1 here
+    const int q = (int)hA.z;                                    // >= 1 here
     const bool gv = meta & kMetaGarbage;
-    const float4 garbage = make_float4(0.0f, t, h1.y, 0.0f);    // pending garbage was (re)written this very step
-    float4* Q = s.queue + L * M;
+    const float4 garbage = make_float4(0.0f, t, hB.z, 0.0f);    // pending garbage was (re)written this very step
+    float4* Q = s.queue + (size_t)L * M;
     const float4 new_head = (gv && q == 1) ? garbage : Q[rh];
     if (M > 1) {
         const float4 last = (gv && q == M) ? garbage : Q[ring_pos(rh, M, M)];
@@ -194,315 +284,98 @@ __global__ void __launch_bounds__(kThreads) k_store_respond_pop(tarl_dual_csr g,
     } else if (gv && q == 1) {
         Q[rh] = garbage;                                        // Nmax == 2: slot 1 keeps (a copy of) its value
     }
-    h0.x = new_head.x; h0.y = new_head.y; h0.z = new_head.z;
-    h1.x = h1.x - 1.0f;
     int nrh = rh + 1; if (nrh >= M) nrh = 0;
     meta = (meta & ~kMetaRingMask) | nrh;
     if (gv && q == 1) meta &= ~kMetaGarbage;                    // the garbage became the head slot
-    h1.w = __int_as_float(meta);
-    s.hot_next[2 * L] = h0;
-    s.hot_next[2 * L + 1] = h1;
+    s.hot_next[2 * (size_t)L] = make_float4(new_head.x, new_head.z, hA.z - 1.0f, hA.w);
+    s.hot_next[2 * (size_t)L + 1] = make_float4(new_head.y, hB.y, hB.z, __int_as_float(meta));
 }
 
-
-// ------------------------------------------------------------------------------------------------ tiled variants
-// The kernels above walk each link's edge segment with one thread: in_ptr -> in_src -> hot[u] is a chain of dependent
-// loads that is repeated once per edge, and the step ends up latency-bound (profiles/r01_c: 2.6 TB/s of DRAM traffic at
-// 43 % occupancy). The tiled kernels give one CTA a tile of kTile consecutive links. Because both CSR orientations are
-// sorted by their owner link, the tile's edges form ONE contiguous range: the CTA reads it edge-parallel (coalesced
-// in_src / attr / out_dst streams, four independent upstream gathers in flight per thread), stages the per-edge result
-// in shared memory, and only then runs the per-link scan in ascending edge id out of shared memory. Same arithmetic in
-// the same order as the direct kernels, so the results are bit-identical. Tiles with more than kCap edges (average
-// degree > 8) take the direct path.
-constexpr int kTile = 256;
-constexpr int kCap = 2048;
-
-template <bool kExtNoise>
-__global__ void __launch_bounds__(kTile, 4) k_tile_select_append(
-    tarl_dual_csr g, Store s, const float* __restrict__ attr_in, const float* __restrict__ noise, uint32_t seed_lo,
-    uint32_t seed_hi, uint32_t step_id, float t, int32_t* __restrict__ flags) {
-    __shared__ int s_ptr[kTile + 1];
-    __shared__ float s_room[kTile], s_ridx[kTile];
-    __shared__ uint8_t s_free[kTile];
-    __shared__ uint8_t s_owner[kCap];
-    __shared__ float s_p[kCap], s_id[kCap];
-    __shared__ float s_u[kExtNoise ? kCap : 1];
-    __shared__ uint8_t s_list[kTile];
-    __shared__ int s_count;
-
-    const int tid = threadIdx.x;
-    const int r = blockIdx.y;
-    const int d = blockIdx.x * kTile + tid;
-    if (tid == 0) s_count = 0;
-    const bool valid = d < s.N;
-    const int base = r * s.N;
-    const int L = base + d;
-
-    s_ptr[tid] = g.in_ptr[min(d, s.N)];
-    if (tid == kTile - 1) s_ptr[kTile] = g.in_ptr[min(d + 1, s.N)];
-    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, st = h0;
-    if (valid) {
-        h0 = s.hot_cur[2 * L];
-        h1 = s.hot_cur[2 * L + 1];
-        st = s.stat_a[d];
-    }
-    const float num = h1.x, maxn = h1.z, fftt = st.x, ridx_d = st.z;
-    int meta = __float_as_int(h1.w);
-    const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
-    const bool free_d = num < (maxn - 3.0f);
-    const float room_d = maxn - num;
-    s_room[tid] = room_d;
-    s_ridx[tid] = ridx_d;
-    s_free[tid] = free_d ? 1 : 0;
-    __syncthreads();
-
-    const int e0 = s_ptr[0], ne = s_ptr[kTile] - e0;
-    const int kb = s_ptr[tid], ke = s_ptr[tid + 1];
-    float best = -FLT_MAX, best_id = 0.0f, psum = 0.0f;
-    bool have = false;
-
-    if (ne <= kCap) {   // block-uniform
-        for (int k = kb; k < ke; ++k) s_owner[k - e0] = (uint8_t)tid;
-        __syncthreads();
-        for (int i0 = tid; i0 < ne; i0 += 4 * kTile) {
-            int u[4];
-            float a[4], un[4];
-            float4 U0[4], U1[4];
-            float S[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i0 + q * kTile;
-                u[q] = -1;
-                if (i < ne) {
-                    u[q] = g.in_src[e0 + i];
-                    a[q] = attr_in[e0 + i];
-                    if (kExtNoise) un[q] = noise[(int64_t)r * g.n_edges + g.in_eid[e0 + i]];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (u[q] >= 0) {
-                    const int Lu = base + u[q];
-                    U0[q] = s.hot_cur[2 * Lu];
-                    U1[q] = s.hot_cur[2 * Lu + 1];
-                    S[q] = s.sel[Lu];
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (u[q] >= 0) {
-                    const int i = i0 + q * kTile;
-                    const int o = s_owner[i];
-                    const bool a1 = (U0[q].z <= t) && (U1[q].x > 0.0f);
-                    const bool a2 = ((U0[q].z - t) < -10.0f) && ((U1[q].z - 3.0f) <= U1[q].x);
-                    const bool match = (S[q] == s_ridx[o]);
-                    const bool m = (a1 && s_free[o] && match) || (a2 && ((U1[q].z - U1[q].x) <= s_room[o]) && match);
-                    s_p[i] = a[q] * (m ? 1.0f : 0.0f);
-                    s_id[i] = U0[q].x;
-                    if (kExtNoise) s_u[i] = un[q];
-                }
-            }
-        }
-        __syncthreads();
-        for (int k = kb; k < ke; ++k) psum += s_p[k - e0];
-        // The scores only matter where somebody is eligible (src/direction_mpnn.py:142-144): compact those links so
-        // that the three logf per candidate run on dense warps instead of on ~1 lane in 4.
-        if (psum > 0.0f) s_list[atomicAdd(&s_count, 1)] = (uint8_t)tid;
-        __syncthreads();
-        const int n_list = s_count;
-        for (int w = tid; w < n_list; w += kTile) {
-            const int o = s_list[w];
-            const int ob = s_ptr[o], oe = s_ptr[o + 1];
-            const uint32_t Lo = (uint32_t)(L - tid + o);
-            float b = -FLT_MAX, bid = 0.0f;
-            bool hv = false;
-            float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-            for (int k = ob; k < oe; ++k) {
-                const int j = k - ob;
-                float uu;
-                if (kExtNoise) {
-                    uu = s_u[k - e0];
-                } else {
-                    if ((j & 3) == 0) philox4x32_10(Lo, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
-                    const int jj = j & 3;
-                    uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
-                }
-                const float sc = logf(s_p[k - e0] + 1e-12f) + (-logf(-logf(uu)));
-                if (sc > b) { b = sc; bid = s_id[k - e0]; hv = true; }
-            }
-            s_room[o] = bid;             // the downstream-side terms are no longer needed: reuse as the result slots
-            s_free[o] = hv ? 1 : 0;
-        }
-        __syncthreads();
-        if (psum > 0.0f) { best_id = s_room[tid]; have = s_free[tid] != 0; }
-    } else if (valid) {
-        float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-        for (int k = kb; k < ke; ++k) {
-            const int j = k - kb;
-            const int Lu = base + g.in_src[k];
-            const float4 u0 = s.hot_cur[2 * Lu], u1 = s.hot_cur[2 * Lu + 1];
-            const float sel_u = s.sel[Lu];
-            const bool a1 = (u0.z <= t) && (u1.x > 0.0f);
-            const bool a2 = ((u0.z - t) < -10.0f) && ((u1.z - 3.0f) <= u1.x);
-            const bool match = (sel_u == ridx_d);
-            const bool m = (a1 && free_d && match) || (a2 && ((u1.z - u1.x) <= room_d) && match);
-            const float p = attr_in[k] * (m ? 1.0f : 0.0f);
-            psum += p;
-            float uu;
-            if (kExtNoise) {
-                uu = noise[(int64_t)r * g.n_edges + g.in_eid[k]];
-            } else {
-                if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, step_id, (uint32_t)(j >> 2), seed_lo, seed_hi, un);
-                const int jj = j & 3;
-                uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
-            }
-            const float sc = logf(p + 1e-12f) + (-logf(-logf(uu)));
-            if (sc > best) { best = sc; best_id = u0.x; have = true; }
-        }
-    }
-    if (!valid) return;
-
-    float chosen = 0.0f;
-    if (psum > 0.0f) {
-        if (!have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
-        else chosen = best_id;
-    }
-    const float dtt = max_propagate_nan((h0.z - h0.y) - fftt, 0.0f);
-    float num_post = num, tail_post = h0.w, head_post = h0.x;
-    if (bad) {
-        atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
-    } else {
-        const int q = (int)num;
-        const float dep_new = t + max_propagate_nan(fftt, st.y / ((maxn + 10.0f) - num));
-        if (q == 0) {
-            h0.x = chosen; h0.y = t; h0.z = dep_new;
-            head_post = chosen;
-            tail_post = chosen;
-            meta &= ~kMetaGarbage;
-            if (chosen != 0.0f) { num_post = num + 1.0f; h0.w = chosen; }
-        } else if (chosen != 0.0f) {
-            s.queue[(size_t)L * s.M + ring_pos(meta & kMetaRingMask, q, s.M)] = make_float4(chosen, t, dep_new, 0.0f);
-            num_post = num + 1.0f;
-            h0.w = chosen;
-            tail_post = chosen;
-            meta &= ~kMetaGarbage;
-        } else {
-            meta |= kMetaGarbage;
-            h1.y = dep_new;
-        }
-        h1.x = num_post;
-    }
-    h1.w = __int_as_float(meta);
-    s.hot_next[2 * L] = h0;
-    s.hot_next[2 * L + 1] = h1;
-    s.post[L] = make_float4(num_post, tail_post, head_post, dtt);
+__device__ __forceinline__ bool accepts(const float4 P, const float4 D) {     // src/response_mpnn.py:66-83
+    return at_least_one(P.x) && at_least_one(D.x) && same_id(D.y, P.z);
 }
 
+__device__ __noinline__ bool scan_out_edges_csr(const tarl_dual_csr& g, const Store& s, int base, int u, const float4 P,
+                                                float* __restrict__ dtt_out) {
+    bool accept = false;
+    const int k1 = g.out_ptr[u + 1];
+    for (int k = g.out_ptr[u]; k < k1; ++k) {
+        if (dtt_out != nullptr) dtt_out[g.out_eid != nullptr ? g.out_eid[k] : k] = P.w;
+        accept = accept || accepts(P, s.post[base + g.out_dst[k]]);
+    }
+    return accept;
+}
 
-__global__ void __launch_bounds__(kTile) k_tile_respond_pop(tarl_dual_csr g, Store s, float t,
-                                                            float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
-                                                            int32_t* __restrict__ flags) {
-    __shared__ int s_ptr[kTile + 1];
-    __shared__ float s_head[kTile], s_dtt[kTile];
-    __shared__ uint8_t s_has[kTile], s_acc[kTile];
-    __shared__ uint8_t s_owner[kCap];
-
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, Store s, float t,
+                                                              float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
+                                                              int32_t* __restrict__ flags) {
+    const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
-    const int u = blockIdx.x * kTile + tid;
-    const bool valid = u < s.N;
     const int base = r * s.N;
     const int L = base + u;
-
-    s_ptr[tid] = g.out_ptr[min(u, s.N)];
-    if (tid == kTile - 1) s_ptr[kTile] = g.out_ptr[min(u + 1, s.N)];
-    float4 P = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) P = s.post[L];
-    const bool has_up = at_least_one(P.x);
-    // a link with agents may pop: fetch the second half of its record now, off the critical path of the edge phase
-    float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid && has_up) h1 = s.hot_next[2 * L + 1];
-    s_head[tid] = P.z;
-    s_dtt[tid] = P.w;
-    s_has[tid] = has_up ? 1 : 0;
-    s_acc[tid] = 0;
-    __syncthreads();
-
-    const int e0 = s_ptr[0], ne = s_ptr[kTile] - e0;
-    const int kb = s_ptr[tid], ke = s_ptr[tid + 1];
-    float* dtt_out = (delta_tt != nullptr) ? delta_tt + (int64_t)r * g.n_edges : nullptr;
     bool accept = false;
+    float4 P = make_float4(0.f, 0.f, 0.f, 0.f), hB = P;
+    if (u < s.N) {
+        P = s.post[L];
+        if (at_least_one(P.x)) hB = s.hot_next[2 * (size_t)L + 1];
+        accept = scan_out_edges_csr(g, s, base, u, P, delta_tt != nullptr ? delta_tt + (int64_t)r * g.n_edges : nullptr);
+        pop[L] = accept ? 1 : 0;
+    }
+    if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
+    if (accept) pop_head(s, L, hB, t);
+}
 
-    if (ne <= kCap) {
-        for (int k = kb; k < ke; ++k) s_owner[k - e0] = (uint8_t)tid;
-        __syncthreads();
-        for (int i0 = tid; i0 < ne; i0 += 4 * kTile) {
-            int dn[4], eid[4];
-            float4 D[4];
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
+                                                              float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
+                                                              int32_t* __restrict__ flags) {
+    const int u = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    const int base = r * s.N;
+    const int L = base + u;
+    bool accept = false;
+    float4 P = make_float4(0.f, 0.f, 0.f, 0.f), hB = P;
+    if (u < s.N) {
+        // level 1
+        P = s.post[L];
+        int dn[W];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i0 + q * kTile;
-                dn[q] = -1;
-                if (i < ne) {
-                    dn[q] = g.out_dst[e0 + i];
-                    eid[q] = (g.out_eid != nullptr) ? g.out_eid[e0 + i] : e0 + i;
-                }
-            }
+        for (int j = 0; j < W; ++j) dn[j] = ell.out_dst[(size_t)j * ell.pitch + u];
+        float* dtt_out = delta_tt != nullptr ? delta_tt + (int64_t)r * g.n_edges : nullptr;
+        const int k0 = (dtt_out != nullptr) ? g.out_ptr[u] : 0;
+        // level 2
+        if (at_least_one(P.x)) hB = s.hot_next[2 * (size_t)L + 1];   // a link with agents may pop: fetch early
+        if (dn[W - 1] == -2) {
+            accept = scan_out_edges_csr(g, s, base, u, P, dtt_out);
+        } else {
+            float4 D[W];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (dn[q] >= 0) D[q] = s.post[base + dn[q]];
+            for (int j = 0; j < W; ++j)
+                if (dn[j] >= 0) D[j] = s.post[base + dn[j]];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (dn[q] >= 0) {
-                    const int o = s_owner[i0 + q * kTile];
-                    if (dtt_out != nullptr) dtt_out[eid[q]] = s_dtt[o];
-                    if (s_has[o] && at_least_one(D[q].x) && same_id(D[q].y, s_head[o])) s_acc[o] = 1;
+            for (int j = 0; j < W; ++j) {
+                if (dn[j] >= 0) {
+                    if (dtt_out != nullptr) dtt_out[g.out_eid != nullptr ? g.out_eid[k0 + j] : k0 + j] = P.w;
+                    accept = accept || accepts(P, D[j]);
                 }
             }
         }
-        __syncthreads();
-        accept = s_acc[tid] != 0;
-    } else if (valid) {
-        for (int k = kb; k < ke; ++k) {
-            if (dtt_out != nullptr) dtt_out[(g.out_eid != nullptr) ? g.out_eid[k] : k] = P.w;
-            const float4 D = s.post[base + g.out_dst[k]];
-            accept = accept || (has_up && at_least_one(D.x) && same_id(D.y, P.z));
-        }
+        pop[L] = accept ? 1 : 0;
     }
-    if (valid) pop[L] = accept ? 1 : 0;
-    accept = accept && valid;
-    if (__syncthreads_or(accept) && tid == 0) flags[TARL_FLAG_ANY_POP] = 1;
-    if (!accept) return;
-
-    // h1 was fetched up front; h0 need not be read at all: its tail id is post.y, the rest is replaced by the new head
-    int meta = __float_as_int(h1.w);
-    const int rh = meta & kMetaRingMask;
-    const int M = s.M;
-    const int q = (int)h1.x;
-    const bool gv = meta & kMetaGarbage;
-    const float4 garbage = make_float4(0.0f, t, h1.y, 0.0f);
-    float4* Q = s.queue + (size_t)L * M;
-    const float4 new_head = (gv && q == 1) ? garbage : Q[rh];
-    if (M > 1) {
-        const float4 last = (gv && q == M) ? garbage : Q[ring_pos(rh, M, M)];
-        Q[rh] = last;
-    } else if (gv && q == 1) {
-        Q[rh] = garbage;
-    }
-    h1.x = h1.x - 1.0f;
-    int nrh = rh + 1; if (nrh >= M) nrh = 0;
-    meta = (meta & ~kMetaRingMask) | nrh;
-    if (gv && q == 1) meta &= ~kMetaGarbage;
-    h1.w = __int_as_float(meta);
-    s.hot_next[2 * L] = make_float4(new_head.x, new_head.y, new_head.z, P.y);
-    s.hot_next[2 * L + 1] = h1;
+    if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
+    if (accept) pop_head(s, L, hB, t);
 }
 
 inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
 
+}  // namespace
+
+namespace tarl {
+
 int make_store(const tarl_link_store* p, Store* s) {
     if (p == nullptr || p->n_links < 0 || p->n_replicas < 1 || p->nmax < 2 || p->nmax - 1 > kMetaRingMask) return TARL_E_BADARG;
+    if (p->n_replicas > 65535 || (int64_t)p->n_links * p->n_replicas * 2 >= INT32_MAX) return TARL_E_BADARG;
     if (p->n_links > 0 && (!p->hot_cur || !p->hot_next || !p->sel || !p->stat_a || !p->stat_b || !p->queue || !p->post))
         return TARL_E_BADARG;
     s->N = p->n_links; s->R = p->n_replicas; s->Nmax = p->nmax; s->M = p->nmax - 1;
@@ -516,7 +389,7 @@ int make_store(const tarl_link_store* p, Store* s) {
     return TARL_OK;
 }
 
-}  // namespace
+}  // namespace tarl
 
 extern "C" {
 
@@ -545,43 +418,41 @@ int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stri
     return launch_status();
 }
 
-int tarl_store_step(const tarl_dual_csr* g, const tarl_link_store* store, const float* attr_in, const float* noise,
-                    uint64_t seed, uint32_t step_id, float t, float* delta_tt, uint8_t* pop, int32_t* flags,
-                    void* stream, uint32_t phase_mask) {
+int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
+                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask) {
     Store s;
     int rc = make_store(store, &s);
     if (rc != TARL_OK) return rc;
     if (g == nullptr || flags == nullptr || g->n_links != s.N) return TARL_E_BADARG;
     if (s.N == 0) return TARL_OK;
-    if (pop == nullptr || (g->n_edges > 0 && attr_in == nullptr)) return TARL_E_BADARG;
-    cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    if (g->n_edges > 0 && (g->in_ptr == nullptr || g->in_src == nullptr || g->out_ptr == nullptr || g->out_dst == nullptr))
-        return TARL_E_BADARG;
+    if (pop == nullptr || g->in_ptr == nullptr || g->out_ptr == nullptr) return TARL_E_BADARG;
+    if (g->n_edges > 0 && (attr_in == nullptr || g->in_src == nullptr || g->out_dst == nullptr)) return TARL_E_BADARG;
     if (noise != nullptr && g->n_edges > 0 && g->in_eid == nullptr) return TARL_E_BADARG;
-    const uint32_t variant = (phase_mask >> TARL_STEP_VARIANT_SHIFT) & 0xfu;
-    if (variant == TARL_STEP_VARIANT_PIPELINED && pipelined_step_supported(*g, s, attr_in))
-        return launch_pipelined_step(*g, s, attr_in, noise, seed, step_id, t, delta_tt, pop, flags, cs, phase_mask);
-    const bool tiled = variant != TARL_STEP_VARIANT_DIRECT && (int64_t)s.N * s.R * 2 < INT32_MAX && s.R <= 65535;
-    if (tiled) {
-        const dim3 grid((s.N + kTile - 1) / kTile, s.R);
-        if (phase_mask & TARL_PHASE_SELECT_APPEND) {
-            if (noise != nullptr)
-                k_tile_select_append<true><<<grid, kTile, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed,
-                                                                   (uint32_t)(seed >> 32), step_id, t, flags);
-            else
-                k_tile_select_append<false><<<grid, kTile, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed,
-                                                                    (uint32_t)(seed >> 32), step_id, t, flags);
-        }
-        if (phase_mask & TARL_PHASE_RESPOND_SHIFT)
-            k_tile_respond_pop<<<grid, kTile, 0, cs>>>(*g, s, t, delta_tt, pop, flags);
-        return launch_status();
+    if (ell != nullptr) {
+        if ((ell->width != 4 && ell->width != 8) || ell->pitch < s.N) return TARL_E_BADARG;
+        if (!ell->in_src || !ell->in_attr || !ell->out_dst) return TARL_E_BADARG;
     }
-    const int nb = blocks_for((int64_t)s.N * s.R);
-    if (phase_mask & TARL_PHASE_SELECT_APPEND)
-        k_store_select_append<<<nb, kThreads, 0, cs>>>(*g, s, attr_in, noise, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                       step_id, t, flags);
-    if (phase_mask & TARL_PHASE_RESPOND_SHIFT)
-        k_store_respond_pop<<<nb, kThreads, 0, cs>>>(*g, s, t, delta_tt, pop, flags);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 grid(blocks_for(s.N), s.R);
+    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
+    if (phase_mask & TARL_PHASE_SELECT_APPEND) {
+        if (ell == nullptr) {
+            if (noise) k_csr_select_append<true><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, flags);
+            else k_csr_select_append<false><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, flags);
+        } else if (ell->width == 4) {
+            if (noise) k_ell_select_append<4, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+            else k_ell_select_append<4, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+        } else {
+            if (noise) k_ell_select_append<8, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+            else k_ell_select_append<8, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+        }
+    }
+    if (phase_mask & TARL_PHASE_RESPOND_SHIFT) {
+        if (ell == nullptr) k_csr_respond_pop<<<grid, kThreads, 0, cs>>>(*g, s, t, delta_tt, pop, flags);
+        else if (ell->width == 4) k_ell_respond_pop<4><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, delta_tt, pop, flags);
+        else k_ell_respond_pop<8><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, delta_tt, pop, flags);
+    }
     return launch_status();
 }
 

@@ -1,4 +1,4 @@
-// engine_common.cuh — shared device helpers of the resident link store kernels (engine.cu, engine_pipe.cu).
+// engine_common.cuh — shared device helpers of the resident link store kernels (engine.cu, agents.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -12,6 +12,7 @@ constexpr int kThreads = 256;
 constexpr int kMetaRingMask = 0xffff;
 constexpr int kMetaGarbage = 1 << 16;
 
+// torch.maximum / torch.clamp(min=) propagate NaN; fmaxf does not.
 __device__ __forceinline__ float max_propagate_nan(float a, float b) {
     return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
 }
@@ -31,6 +32,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     for (int i = 0; i < 4; ++i) out[i] = ((float)(c[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
 
+// Device view of struct tarl_link_store. One 32-byte record per (replica, link), two float4 halves:
+//   A = {head id, head exit time, NUM, MAXN}          everything a NEIGHBOUR needs: gathered with one 128-bit load
+//   B = {head arrival time, tail id, pending tail-garbage exit time, meta}   owner only
+// meta = ring head (16 bit) | kMetaGarbage ("the reference's (0, t, t+tt) tail write is pending at slot int(NUM)").
 struct Store {
     int N, R, Nmax, M;       // M = Nmax-1 ring slots per link
     const float4* hot_cur;   // [R*N*2]
@@ -47,15 +52,10 @@ __device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logica
     return p >= M ? p - M : p;
 }
 
-
 // (long)a == (long)b and (long)a > 0 of src/response_mpnn.py:66-83 on fp32 operands, without 64-bit conversions
 __device__ __forceinline__ bool same_id(float a, float b) { return truncf(a) == truncf(b); }
 __device__ __forceinline__ bool at_least_one(float a) { return a >= 1.0f; }
 
-// engine_pipe.cu: the pipelined (bulk-copy staged) step kernels; returns a TARL_* code
-bool pipelined_step_supported(const tarl_dual_csr& g, const Store& s, const float* attr_in);
-int launch_pipelined_step(const tarl_dual_csr& g, const Store& s, const float* attr_in, const float* noise, uint64_t seed,
-                          uint32_t step_id, float t, float* delta_tt, uint8_t* pop, int32_t* flags, cudaStream_t stream,
-                          uint32_t phase_mask);
+int make_store(const tarl_link_store* p, Store* s);
 
 }  // namespace tarl

@@ -15,8 +15,7 @@ from . import _cabi
 from .topology import topology_for
 
 PHASE_SELECT_APPEND, PHASE_RESPOND_POP = 2, 4
-VARIANT_PIPELINED, VARIANT_DIRECT, VARIANT_TILED = 0, 1, 2    # kernel variants of tarl_store_step (bit-identical)
-VARIANT_SHIFT = 8
+VARIANT_ELL, VARIANT_CSR = 0, 1    # kernel families of tarl_store_step (bit-identical results)
 
 
 class LinkStore:
@@ -30,6 +29,7 @@ class LinkStore:
         self.E = self.topo.n_edges
         attr = edge_attr_routes.reshape(-1).to(torch.float32)
         self.attr_in = attr[self.topo.in_eid.long()].contiguous()        # edge_attr in CSR-by-target order
+        self._ell = self.topo.ell(edge_attr_routes)                      # ELLPACK copy of the first W edges per link
         L = self.N * self.R
         f32 = dict(dtype=torch.float32, device=dev)
         self.hot = [torch.zeros(max(L, 1), 8, **f32), torch.zeros(max(L, 1), 8, **f32)]
@@ -110,7 +110,7 @@ class LinkStore:
         self.sel.view(self.R, self.N).copy_(sel.to(torch.float32).reshape(-1, self.N))
 
     def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
-             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_PIPELINED):
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_ELL):
         """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
         for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8)."""
         if noise is not None:
@@ -122,10 +122,11 @@ class LinkStore:
         self._fill_struct()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_store_step(
-                self.topo.ref(), C.byref(self._struct), self.attr_in.data_ptr(),
+                self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
+                self.attr_in.data_ptr(),
                 noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
                 delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
-                self._stream(), phase_mask | (variant << VARIANT_SHIFT))
+                self._stream(), phase_mask)
         _cabi.check(rc, "tarl_store_step")
         if phase_mask & PHASE_RESPOND_POP:
             self.cur ^= 1
@@ -135,7 +136,7 @@ class LinkStore:
 
     def num_agents(self) -> torch.Tensor:
         """NUMBER_OF_AGENT per (replica, link), a strided view into the hot records."""
-        return self.hot[self.cur][: self.N * self.R, 4].view(self.R, self.N)
+        return self.hot[self.cur][: self.N * self.R, 2].view(self.R, self.N)
 
     def check_errors(self):
         bits = int(self.flags[_cabi.FLAG_ERROR])

@@ -49,6 +49,42 @@ class DualTopology:
     def ref(self):
         return C.byref(self.struct)
 
+    def ell(self, edge_attr: torch.Tensor):
+        """ELLPACK copy of the first W edges of every link (struct tarl_dual_ell), W = 4 or 8 by maximum degree.
+        Cached per edge_attr tensor. Column j of link n sits at [j*pitch + n]; links with more than W edges carry -2
+        in the last column and are served from the CSR."""
+        key = (edge_attr.data_ptr(), edge_attr._version)
+        hit = getattr(self, "_ell", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        N, E, dev = self.n_links, self.n_edges, self.device
+        in_deg = (self.in_ptr[1:] - self.in_ptr[:-1]).long()
+        out_deg = (self.out_ptr[1:] - self.out_ptr[:-1]).long()
+        max_deg = int(max(in_deg.max().item() if N else 0, out_deg.max().item() if N else 0))
+        W = 4 if max_deg <= 4 else 8
+        pitch = max((N + 31) // 32 * 32, 32)
+        attr = edge_attr.reshape(-1).to(torch.float32)
+
+        def fill(ptr, deg, values):
+            cols = torch.full((W, pitch), -1, dtype=values.dtype, device=dev)
+            if E:
+                owner = torch.repeat_interleave(torch.arange(N, device=dev), deg)
+                rank = torch.arange(E, device=dev) - ptr[:-1].long()[owner]
+                keep = rank < W
+                cols[rank[keep], owner[keep]] = values[keep]
+            return cols
+
+        in_src = fill(self.in_ptr, in_deg, self.in_src)
+        in_attr = fill(self.in_ptr, in_deg, attr[self.in_eid.long()])
+        out_dst = fill(self.out_ptr, out_deg, self.out_dst)
+        if N:
+            in_src[W - 1, :N][in_deg > W] = -2
+            out_dst[W - 1, :N][out_deg > W] = -2
+        struct = _cabi.DualELL(W, pitch, in_src.data_ptr(), in_attr.data_ptr(), out_dst.data_ptr())
+        pack = (struct, in_src, in_attr, out_dst)
+        self._ell = (key, pack)
+        return pack
+
 
 _CACHE: dict = {}
 

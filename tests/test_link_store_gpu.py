@@ -26,7 +26,7 @@ def make_store(x0, ei, w, Nmax, use_static, replicas=1, seed=0):
     return LinkStore.from_graph(g, Nmax, replicas=replicas, seed=seed), g
 
 
-VARIANTS = [0, 1, 2]     # pipelined (default), direct, tiled
+VARIANTS = [0, 1]     # ELL (default), CSR
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
