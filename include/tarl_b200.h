@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 2
+#define TARL_ABI_VERSION 3
 
 /* return codes */
 #define TARL_OK 0
@@ -43,6 +43,9 @@ extern "C" {
                                   the reference raises IndexError at src/direction_mpnn.py:144 */
 #define TARL_ERR_EMBED_RANGE 4 /* an embedding index fell outside nodes_embedding (nn.Embedding raises IndexError,
                                   src/agents/mpnn_agent.py:216) */
+#define TARL_ERR_INSERT_TARGET 8 /* SELECTED_ROAD of an origin node with agents is not a road id: the reference would
+                                    index a non-road row at src/agents/base.py:259-266 */
+#define TARL_ERR_AGENT_RANGE 16  /* a queued agent id is outside agent_features (IndexError at src/agents/base.py:358) */
 
 /* Static topology of the dual graph (`edge_index_routes` of the reference, src/transportation_simulator.py:150-171)
  * in both CSR orientations. Original edge ids are kept because the Gumbel arg-max breaks ties towards the lowest
@@ -217,6 +220,87 @@ int tarl_graphdist_backward(const tarl_csr* groups, const float* logits, float t
  * out. Inside a group edges are walked in ascending edge id (D3); batched rows are independent (D7). */
 int tarl_graphdist_sample(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
                           const float* uniforms, int64_t* onehot, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Population operations either side of the core step (csrc/agents.cu). Each works on either state layout.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Which road state to operate on: EITHER the reference rows (x != NULL: graph.x, element (r, n, c) at
+ * x[r*x_replica_stride + n*x_row_stride + c], ALL n_nodes rows because SRC nodes carry SELECTED_ROAD too) OR a link
+ * store (store != NULL; then the SELECTED_ROAD of the non-road nodes lives in src_sel [R, n_nodes - n_links]). */
+typedef struct tarl_agent_state {
+    float* x;
+    int64_t x_row_stride;
+    int64_t x_replica_stride;
+    int32_t n_links;    /* N = graph.num_roads (rows layout; taken from the store otherwise)          */
+    int32_t nmax;
+    int32_t n_replicas;
+    int32_t n_nodes;    /* N_tot = graph.x.size(0)                                                    */
+    const float* cc;    /* rows layout: congestion_constant[:N] or NULL (hasattr test, base.py:314)    */
+    const tarl_link_store* store;
+    float* src_sel;
+    float t_garbage;    /* store layout: time of the latest tarl_store_step (see tarl_store_export)    */
+    int32_t reserved;
+} tarl_agent_state;
+
+/* agent_features (src/feature_helpers.py:56-71): fp32 [R, n_rows, 9] row-major, replica r at +r*replica_stride
+ * (ignored when there is one replica). Columns: ORIGIN, DESTINATION, DEPARTURE_TIME, ARRIVAL_TIME, AGE, SEX,
+ * EMPLOYMENT_STATUS, ON_WAY, DONE. Row 0 is the dummy agent. */
+typedef struct tarl_agent_table {
+    float* agent_features;
+    int64_t replica_stride;
+    int32_t n_rows;
+    int32_t reserved;
+} tarl_agent_table;
+
+/* The population indexed by ORIGIN node, built once per population by the host (ORIGIN is static, and identical in
+ * every replica): agents of node o = org_agent[org_ptr[o] .. org_ptr[o+1]) in ascending agent id; origins = the nodes
+ * that own at least one agent. */
+typedef struct tarl_agent_index {
+    int32_t n_nodes;
+    int32_t n_origins;
+    const int32_t* org_ptr;   /* [n_nodes+1] */
+    const int32_t* org_agent; /* [n_rows]    */
+    const int32_t* origins;   /* [n_origins] */
+} tarl_agent_index;
+
+/* Replaces Agents.insert_agent_into_network (src/agents/base.py:244-331): every agent with DEPARTURE_TIME <= t,
+ * ON_WAY == 0 and DONE == 0 targets road x[ORIGIN, SELECTED_ROAD]; per road the first min(count, MAXN-3-NUM) of them
+ * in ascending agent id (declared divergence D3) are appended at the tail with arrival t and exit time
+ * t + max(FFTT, cc/(MAXN+10-NUM_before)); NUM += admitted; ON_WAY = 1.
+ * Scratch (caller-owned int32): head [R*N] initialised to -1 ONCE by the caller (the kernels leave it at -1),
+ * next [R*n_origins], cursor [R*n_origins]. counters: NULL or [R*2] {inserted, withdrawn} running totals. */
+int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
+                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* flags,
+                       void* stream);
+
+/* Replaces Agents.withdraw_agent_from_network (src/agents/base.py:334-403): per link the maximal prefix of queue
+ * slots k < NUM whose exit time <= t and whose agent's DESTINATION node is adjacent to the link — adjacency = CSR of
+ * the FULL edge_index by source node (idx = targets), the sparse form of adj_matrix[ROAD_INDEX, DESTINATION] — is
+ * removed; the three queue segments shift left by that count with zero fill; the agents get DONE = 1, ON_WAY = 0,
+ * ARRIVAL_TIME = t. mask: NULL or [R*N] (the entry of withdraw_history). */
+int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_csr* adjacency,
+                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, void* stream);
+
+/* Replaces Agents.choice (src/agents/base.py:446-494): every node listed in choosers (roads with a downstream road,
+ * SRC nodes with an outgoing road) draws one of its neighbours[node] (ascending road id) uniformly into
+ * SELECTED_ROAD: neighbour number min(floor(u*deg), deg-1). uniforms: [R*n_choosers] or NULL for the in-kernel Philox
+ * stream (seed, step_id) — the reference draws torch.multinomial from the global generator (declared divergence D4). */
+int tarl_agents_choice(const tarl_agent_state* state, const tarl_csr* neighbours, const int32_t* choosers,
+                       int32_t n_choosers, const float* uniforms, uint64_t seed, uint32_t step_id, void* stream);
+
+/* Replaces the action write of SimulatorEnv._step (src/reinforcement_learning.py:223-231):
+ * SELECTED_ROAD[edge_src[e]] = edge_dst[e] for every e of the FULL graph with action[r, e] != 0. */
+int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_src, const int32_t* edge_dst,
+                             int32_t n_edges, const void* action, int32_t action_dtype, void* stream);
+
+/* state() (src/transportation_simulator.py:360-366) and the reward term of SimulatorEnv._step
+ * (src/reinforcement_learning.py:266) from a link store: node_features [R, n_nodes, 7] = {MAXN, NUM, FFTT, LENGTH,
+ * MAX_FLOW, SELECTED_ROAD, ROAD_INDEX}, agent_index [R, n_nodes] int64 = head agent ids, occupancy [R] int32 =
+ * sum of NUM over the links (integer atomics). Any output may be NULL. */
+int tarl_store_observe(const tarl_agent_state* state, float* node_features, int64_t* agent_index, int32_t* occupancy,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libtarl_b200.so")
 
 OK = 0
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
-ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE = 1, 2, 4
+ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
 ERR_TEXT = {
     ERR_QUEUE_RANGE: "NUMBER_OF_AGENT of some link left [0, Nmax): the reference's tail write would alias other "
@@ -17,6 +17,8 @@ ERR_TEXT = {
     ERR_NO_WINNER: "a link had positive total probability but no finite Gumbel score (noise == 0 or NaN); the "
                    "reference raises IndexError at src/direction_mpnn.py:144",
     ERR_EMBED_RANGE: "embedding index out of range (nn.Embedding raises IndexError, src/agents/mpnn_agent.py:216)",
+    ERR_INSERT_TARGET: "SELECTED_ROAD of an origin node with agents is not a road id (src/agents/base.py:259-266)",
+    ERR_AGENT_RANGE: "a queued agent id is outside agent_features (IndexError at src/agents/base.py:358)",
 }
 
 
@@ -46,11 +48,34 @@ class LinkStore(C.Structure):
                 ("stat_b", C.c_void_p), ("queue", C.c_void_p), ("post", C.c_void_p)]
 
 
+class AgentState(C.Structure):
+    """struct tarl_agent_state"""
+    _fields_ = [("x", C.c_void_p), ("x_row_stride", C.c_int64), ("x_replica_stride", C.c_int64),
+                ("n_links", C.c_int32), ("nmax", C.c_int32), ("n_replicas", C.c_int32), ("n_nodes", C.c_int32),
+                ("cc", C.c_void_p), ("store", C.POINTER(LinkStore)), ("src_sel", C.c_void_p),
+                ("t_garbage", C.c_float), ("reserved", C.c_int32)]
+
+
+class AgentTable(C.Structure):
+    """struct tarl_agent_table"""
+    _fields_ = [("agent_features", C.c_void_p), ("replica_stride", C.c_int64), ("n_rows", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class AgentIndex(C.Structure):
+    """struct tarl_agent_index"""
+    _fields_ = [("n_nodes", C.c_int32), ("n_origins", C.c_int32), ("org_ptr", C.c_void_p), ("org_agent", C.c_void_p),
+                ("origins", C.c_void_p)]
+
+
 _P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_t
 _STORE = C.POINTER(LinkStore)
 _CSR = C.POINTER(DualCSR)
 _CSR1 = C.POINTER(CSR)
 _ELL = C.POINTER(DualELL)
+_AST = C.POINTER(AgentState)
+_ATB = C.POINTER(AgentTable)
+_AIX = C.POINTER(AgentIndex)
 
 # name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
 SIGNATURES = {
@@ -70,6 +95,11 @@ SIGNATURES = {
     "tarl_graphdist_forward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "tarl_graphdist_backward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_graphdist_sample": (C.c_int, [_CSR1, _P, _F, _I32, _P, _P, _P]),
+    "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P]),
+    "tarl_agents_withdraw": (C.c_int, [_AST, _ATB, _CSR1, _F, _P, _P, _P, _P]),
+    "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),
+    "tarl_agents_apply_action": (C.c_int, [_AST, _P, _P, _I32, _P, _I32, _P]),
+    "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,0 +1,457 @@
+// agents.cu — the per-step population operations either side of the core step (sm_100a): insertion of departing
+// agents, withdrawal of arrived agents, random route choice, application of an RL action, observation build.
+//
+// Reference semantics: /root/reference/src/agents/base.py:244-331 (insert_agent_into_network), :334-403
+// (withdraw_agent_from_network), :446-494 (choice); /root/reference/src/reinforcement_learning.py:222-231 (action ->
+// SELECTED_ROAD), :256-266 (reward), /root/reference/src/transportation_simulator.py:360-366 (state()).
+// SURVEY.md Appendix B restates them. Compiled with -fmad=false (the exit-time arithmetic must round like ATen's).
+//
+// Every kernel exists for both state layouts through one accessor interface:
+//   RowAcc    the reference's graph.x rows, in place ([R,] N_tot, 3*Nmax+7)            -> drop-in Agents methods
+//   StoreAcc  the resident link store of engine.cu (hot records + ring queues)          -> batched rollouts
+//
+// Insertion without a sort: the reference sorts the ready agents by target road and admits, per road, the first
+// min(count, MAXN-3-NUM) of them (ascending agent id inside a road: declared divergence D3, the reference's argsort is
+// unstable). A ready agent's target road is x[ORIGIN(agent), SELECTED_ROAD], so all agents of one origin node target
+// the same road; with the population indexed ONCE by origin (ascending agent id inside an origin) the per-road work is
+// a k-way merge over the (almost always one) origins that currently select the road:
+//   k_insert_offer  thread per (replica, origin with agents): pushes the origin on its road's list (atomicExch)
+//   k_insert_admit  thread per (replica, road with a list): merges by smallest agent id until the room is used up
+// The merge result does not depend on the order of the list, so the atomics leave no nondeterminism behind.
+#include "engine_common.cuh"
+
+using namespace tarl;
+
+namespace {
+
+constexpr int kDestination = 1, kDepartureTime = 2, kArrivalTime = 3, kOnWay = 7, kDone = 8;  // AgentFeatureHelpers
+
+struct AgentTable {       // agent_features [R?, A+1, 9] fp32
+    float* af;
+    int64_t rep_stride;   // 0 = one table shared by... (only legal when R == 1)
+    int32_t n_rows;
+    __device__ float* row(int r, long long a) const { return af + r * rep_stride + a * 9; }
+};
+
+// ---------------------------------------------------------------------------------------------------------- accessors
+struct RowAcc {
+    float* x;
+    int64_t row_stride, rep_stride;
+    int N, Nmax;
+    const float* cc;      // congestion_constant [>= N] or nullptr (then the congestion term is 0, base.py:318-319)
+    float t_garbage;      // unused
+    __device__ float* row(int r, int n) const { return x + r * rep_stride + (int64_t)n * row_stride; }
+    __device__ float sel_of(int r, int node) const { return row(r, node)[3 * Nmax + 5]; }
+    __device__ void set_sel(int r, int node, float v) const { row(r, node)[3 * Nmax + 5] = v; }
+    __device__ float road_index(int r, int n) const { return row(r, n)[3 * Nmax + 6]; }
+
+    struct Link {
+        float* row;
+        int Nmax;
+        float num, maxn, fftt;
+    };
+    __device__ Link open(int r, int n) const {
+        float* p = row(r, n);
+        return {p, Nmax, p[3 * Nmax + 1], p[3 * Nmax], p[3 * Nmax + 2]};
+    }
+    __device__ static float slot_id(const Link& l, int k) { return l.row[k]; }
+    __device__ static float slot_dep(const Link& l, int k) { return l.row[2 * l.Nmax + k]; }
+    __device__ static void put(Link& l, int k, float id, float arr, float dep) {
+        l.row[k] = id; l.row[l.Nmax + k] = arr; l.row[2 * l.Nmax + k] = dep;
+    }
+    __device__ static void commit_insert(Link& l, int admitted) { l.row[3 * l.Nmax + 1] = l.num + (float)admitted; }
+    // src/agents/base.py:377-396: every segment shifts left by c with zero fill, NUM -= c
+    __device__ static void withdraw(Link& l, int c) {
+        for (int seg = 0; seg < 3; ++seg) {
+            float* q = l.row + seg * l.Nmax;
+            for (int k = 0; k < l.Nmax; ++k) q[k] = (k + c < l.Nmax) ? q[k + c] : 0.0f;
+        }
+        l.row[3 * l.Nmax + 1] = l.num - (float)c;
+    }
+};
+
+struct StoreAcc {
+    Store s;
+    float* hot;           // == s.hot_cur, writable: these operations run between two steps, on the current records
+    float* src_sel;       // [R, n_nodes - N] SELECTED_ROAD of the non-road nodes (SRC nodes use it)
+    int n_nodes;
+    float t_garbage;      // arrival time of a pending tail-garbage record = time of the latest core step
+    int N, Nmax;
+    __device__ float sel_of(int r, int node) const {
+        return node < N ? s.sel[(size_t)r * N + node] : src_sel[(size_t)r * (n_nodes - N) + (node - N)];
+    }
+    __device__ void set_sel(int r, int node, float v) const {
+        if (node < N) s.sel[(size_t)r * N + node] = v;
+        else src_sel[(size_t)r * (n_nodes - N) + (node - N)] = v;
+    }
+    __device__ float road_index(int, int n) const { return s.stat_a[n].z; }
+
+    struct Link {
+        float4* rec;      // the two halves of the hot record
+        float4* ring;
+        float4 A, B;
+        int M, rh;
+        bool gv;
+        float num, maxn, fftt, t_garbage;
+    };
+    __device__ Link open(int r, int n) const {
+        const size_t L = (size_t)r * N + n;
+        float4* rec = reinterpret_cast<float4*>(hot) + 2 * L;
+        Link l;
+        l.rec = rec; l.ring = s.queue + L * s.M; l.A = rec[0]; l.B = rec[1]; l.M = s.M;
+        const int meta = __float_as_int(l.B.w);
+        l.rh = meta & kMetaRingMask; l.gv = (meta & kMetaGarbage) != 0;
+        l.num = l.A.z; l.maxn = l.A.w; l.fftt = s.stat_a[n].x; l.t_garbage = t_garbage;
+        return l;
+    }
+    __device__ static float4 slot(const Link& l, int k) {      // logical FIFO slot k as {id, arrival, exit}
+        if (k == 0) return make_float4(l.A.x, l.B.x, l.A.y, 0.0f);
+        if (l.gv && k == (int)l.num) return make_float4(0.0f, l.t_garbage, l.B.z, 0.0f);
+        return l.ring[ring_pos(l.rh, k, l.M)];
+    }
+    __device__ static float slot_id(const Link& l, int k) { return slot(l, k).x; }
+    __device__ static float slot_dep(const Link& l, int k) { return slot(l, k).z; }
+    __device__ static void put(Link& l, int k, float id, float arr, float dep) {
+        if (k == 0) { l.A.x = id; l.B.x = arr; l.A.y = dep; }
+        else l.ring[ring_pos(l.rh, k, l.M)] = make_float4(id, arr, dep, 0.0f);
+        l.B.y = id;         // the latest append is the tail
+        l.gv = false;       // appends start at slot int(NUM): the pending garbage record is overwritten
+    }
+    __device__ static void store_back(Link& l) {
+        l.B.w = __int_as_float(l.rh | (l.gv ? kMetaGarbage : 0));
+        l.rec[0] = l.A; l.rec[1] = l.B;
+    }
+    __device__ static void commit_insert(Link& l, int admitted) {
+        l.A.z = l.num + (float)admitted;
+        store_back(l);
+    }
+    __device__ static void withdraw(Link& l, int c) {
+        const int g = (int)l.num;                     // slot of the pending garbage record, if any
+        const float4 head = slot(l, c);               // c <= NUM < Nmax, so slot c exists
+        for (int k = 1; k <= c; ++k) l.ring[ring_pos(l.rh, k, l.M)] = make_float4(0.f, 0.f, 0.f, 0.f);   // zero fill
+        int rh = l.rh + c; if (rh >= l.M) rh -= l.M;
+        l.rh = rh;
+        l.A.x = head.x; l.B.x = head.y; l.A.y = head.z;
+        if (l.gv && g == c) l.gv = false;             // the garbage record became the head slot
+        l.A.z = l.num - (float)c;
+        store_back(l);
+    }
+};
+
+__device__ __forceinline__ bool acc_has_cc(const RowAcc& a) { return a.cc != nullptr; }
+__device__ __forceinline__ float acc_cc(const RowAcc& a, int n) { return a.cc[n]; }
+__device__ __forceinline__ bool acc_has_cc(const StoreAcc&) { return true; }
+__device__ __forceinline__ float acc_cc(const StoreAcc& a, int n) { return a.s.stat_a[n].y; }
+
+// ------------------------------------------------------------------------------------------------------------ insert
+__device__ __forceinline__ bool agent_ready(const AgentTable& at, int r, int a, float t) {
+    const float* p = at.row(r, a);
+    return p[kDepartureTime] <= t && p[kOnWay] == 0.0f && p[kDone] == 0.0f;     // base.py:247-251
+}
+
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_index ai, AgentTable at, float t,
+                                                           int32_t* __restrict__ head, int32_t* __restrict__ next,
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ flags) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= ai.n_origins) return;
+    const int r = blockIdx.y;
+    const int o = ai.origins[i];
+    const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
+    const size_t ri = (size_t)r * ai.n_origins + i;
+    cursor[ri] = ai.org_ptr[o];
+    if (road < 0 || road >= acc.N) {          // not a road: harmless unless one of this origin's agents is ready, in
+        bool any = false;                     // which case the reference would index a non-road row (or wrap around)
+        for (int k = ai.org_ptr[o]; k < ai.org_ptr[o + 1] && !any; ++k) any = agent_ready(at, r, ai.org_agent[k], t);
+        if (any) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_INSERT_TARGET);
+        next[ri] = -2;
+        return;
+    }
+    next[ri] = atomicExch(&head[(size_t)r * acc.N + road], i);
+}
+
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_index ai, AgentTable at, float t,
+                                                           int32_t* __restrict__ head, const int32_t* __restrict__ next,
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ counters) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    if (n >= acc.N) return;
+    const int r = blockIdx.y;
+    const size_t L = (size_t)r * acc.N + n;
+    const int h = head[L];
+    if (h < 0) return;
+    head[L] = -1;                                                                // ready for the next call
+    typename Acc::Link l = acc.open(r, n);
+    const long long cap = (long long)((l.maxn - 3.0f) - l.num);                  // base.py:262-267
+    if (cap <= 0) return;
+    if (!(l.num >= 0.0f)) return;
+    const int q0 = (int)l.num;
+    float tc = 0.0f;
+    if (acc_has_cc(acc)) tc = acc_cc(acc, n) / ((l.maxn + 10.0f) - (float)q0);   // :314-319 (start_counts is a long)
+    const float dep = t + max_propagate_nan(l.fftt, tc);                         // :321-325
+    const int32_t* nx = next + (size_t)r * ai.n_origins;
+    int32_t* cur = cursor + (size_t)r * ai.n_origins;
+    int admitted = 0;
+    while (admitted < cap && q0 + admitted < acc.Nmax) {
+        int best_a = INT32_MAX, best_i = -1;
+        for (int i = h; i >= 0; i = nx[i]) {
+            const int end = ai.org_ptr[ai.origins[i] + 1];
+            int k = cur[i];
+            while (k < end && !agent_ready(at, r, ai.org_agent[k], t)) ++k;
+            cur[i] = k;
+            if (k < end && ai.org_agent[k] < best_a) { best_a = ai.org_agent[k]; best_i = i; }
+        }
+        if (best_i < 0) break;
+        Acc::put(l, q0 + admitted, (float)best_a, t, dep);                       // :310-325
+        at.row(r, best_a)[kOnWay] = 1.0f;                                        // :328
+        cur[best_i] += 1;
+        ++admitted;
+    }
+    if (admitted > 0) {
+        Acc::commit_insert(l, admitted);                                         // :327
+        if (counters != nullptr) atomicAdd(&counters[2 * r], admitted);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------- withdraw
+// The maximal PREFIX of a link's queue whose agents are due (exit time <= t) and whose DESTINATION node is adjacent to
+// this link leaves the network (base.py:355-400). adj = CSR of the FULL edge_index by source node: the sparse form of
+// the reference's dense adj_matrix[ROAD_INDEX, DESTINATION] lookup.
+__device__ __forceinline__ bool adjacent(const tarl_csr& adj, long long row, long long dest) {
+    if (row < 0 || row >= adj.n_rows) return false;
+    const int k1 = adj.ptr[row + 1];
+    for (int k = adj.ptr[row]; k < k1; ++k)
+        if (adj.idx[k] == dest) return true;
+    return false;
+}
+
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_withdraw(Acc acc, AgentTable at, tarl_csr adj, float t,
+                                                       uint8_t* __restrict__ mask, int32_t* __restrict__ counters,
+                                                       int32_t* __restrict__ flags) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    if (n >= acc.N) return;
+    const int r = blockIdx.y;
+    typename Acc::Link l = acc.open(r, n);
+    int c = 0;
+    long long ridx = -1;
+    while (c < acc.Nmax && (float)c < l.num) {                                   // active_slots, :363-366
+        if (!(Acc::slot_dep(l, c) <= t)) break;                                  // depart_ok, :362
+        const long long a = (long long)Acc::slot_id(l, c);
+        if (a < 0 || a >= at.n_rows) { atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_AGENT_RANGE); break; }
+        if (c == 0) ridx = (long long)acc.road_index(r, n);
+        if (!adjacent(adj, ridx, (long long)at.row(r, a)[kDestination])) break;  // connectivity, :361
+        ++c;
+    }
+    if (mask != nullptr) mask[(size_t)r * acc.N + n] = c > 0 ? 1 : 0;
+    if (c == 0) return;
+    for (int k = 0; k < c; ++k) {                                                // :398-400
+        float* p = at.row(r, (long long)Acc::slot_id(l, k));
+        p[kDone] = 1.0f; p[kOnWay] = 0.0f; p[kArrivalTime] = t;
+    }
+    Acc::withdraw(l, c);
+    if (counters != nullptr) atomicAdd(&counters[2 * r + 1], c);
+}
+
+// ------------------------------------------------------------------------------------------------------------ choice
+// Every node with out-neighbours (roads -> roads, SRC nodes -> their outgoing roads) draws one of them uniformly
+// (base.py:446-494; the reference samples torch.multinomial over dense 0/1 rows). Here: neighbour number
+// min(floor(u*deg), deg-1) in ascending road id, with u injected per (replica, chooser) or drawn from Philox.
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_choice(Acc acc, tarl_csr nbr, const int32_t* __restrict__ choosers,
+                                                     int n_choosers, const float* __restrict__ uniforms,
+                                                     uint32_t seed_lo, uint32_t seed_hi, uint32_t step_id) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n_choosers) return;
+    const int r = blockIdx.y;
+    const int node = choosers[i];
+    const int k0 = nbr.ptr[node], deg = nbr.ptr[node + 1] - k0;
+    float u;
+    if (uniforms != nullptr) {
+        u = uniforms[(size_t)r * n_choosers + i];
+    } else {
+        float un[4];
+        philox4x32_10((uint32_t)node, (uint32_t)r, step_id, 0x43484f49u, seed_lo, seed_hi, un);
+        u = un[0];
+    }
+    int k = (int)(u * (float)deg);
+    k = min(max(k, 0), deg - 1);
+    acc.set_sel(r, node, (float)nbr.idx[k0 + k]);
+}
+
+// RL action: x[edge_index[0][e], SELECTED_ROAD] = edge_index[1][e] for every selected edge of the FULL graph
+// (reinforcement_learning.py:223-231). action: [R, E_full] one-hot per source group.
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_apply_action(Acc acc, const int32_t* __restrict__ src,
+                                                           const int32_t* __restrict__ dst, int E,
+                                                           const void* __restrict__ action, int action_dtype) {
+    const int e = blockIdx.x * kThreads + threadIdx.x;
+    if (e >= E) return;
+    const int r = blockIdx.y;
+    const size_t i = (size_t)r * E + e;
+    bool on;
+    switch (action_dtype) {
+        case TARL_ACTION_U8: on = static_cast<const uint8_t*>(action)[i] != 0; break;
+        case TARL_ACTION_I64: on = static_cast<const long long*>(action)[i] != 0; break;
+        default: on = static_cast<const float*>(action)[i] != 0.0f; break;
+    }
+    if (on) acc.set_sel(r, src[e], (float)dst[e]);
+}
+
+// ------------------------------------------------------------------------------------------------------- observation
+// state() of the reference on the store (transportation_simulator.py:360-366): node_features[r, n, 0:7] =
+// {MAXN, NUM, FFTT, LENGTH, MAX_FLOW, SELECTED_ROAD, ROAD_INDEX}, agent_index[r, n] = head agent id; non-road nodes
+// are {0,0,0,0,0,sel,-1} / 0. occupancy[r] += sum_n NUM (integer atomics: the reward is -occupancy, :266).
+__global__ void __launch_bounds__(kThreads) k_observe(StoreAcc acc, float* __restrict__ node_features,
+                                                      long long* __restrict__ agent_index,
+                                                      int32_t* __restrict__ occupancy) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    int num_i = 0;
+    if (n < acc.n_nodes) {
+        float f[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -1.0f};
+        long long head = 0;
+        if (n < acc.N) {
+            const float4* rec = reinterpret_cast<const float4*>(acc.hot) + 2 * ((size_t)r * acc.N + n);
+            const float4 A = rec[0];
+            const float4 sa = acc.s.stat_a[n], sb = acc.s.stat_b[n];
+            f[0] = A.w; f[1] = A.z; f[2] = sa.x; f[3] = sb.x; f[4] = sb.y; f[6] = sa.z;
+            head = (long long)A.x;
+            num_i = (int)A.z;
+        }
+        f[5] = acc.sel_of(r, n);
+        const size_t o = (size_t)r * acc.n_nodes + n;
+        if (node_features != nullptr)
+            for (int c = 0; c < 7; ++c) node_features[o * 7 + c] = f[c];
+        if (agent_index != nullptr) agent_index[o] = head;
+    }
+    if (occupancy != nullptr) {
+        for (int off = 16; off > 0; off >>= 1) num_i += __shfl_xor_sync(0xffffffffu, num_i, off);
+        if ((threadIdx.x & 31) == 0 && num_i != 0) atomicAdd(&occupancy[r], num_i);
+    }
+}
+
+inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
+
+int check_state(const tarl_agent_state* st, RowAcc* row, StoreAcc* sto, bool* is_store, int* R) {
+    if (st == nullptr) return TARL_E_BADARG;
+    if ((st->x != nullptr) == (st->store != nullptr)) return TARL_E_BADARG;      // exactly one layout
+    if (st->x != nullptr) {
+        if (st->n_links < 0 || st->nmax < 2 || st->n_replicas < 1 || st->n_replicas > 65535) return TARL_E_BADARG;
+        *row = RowAcc{st->x, st->x_row_stride, st->x_replica_stride, st->n_links, st->nmax, st->cc, 0.0f};
+        *is_store = false;
+        *R = st->n_replicas;
+        return TARL_OK;
+    }
+    Store s;
+    int rc = make_store(st->store, &s);
+    if (rc != TARL_OK) return rc;
+    if (st->n_nodes < s.N || (st->n_nodes > s.N && st->src_sel == nullptr)) return TARL_E_BADARG;
+    *sto = StoreAcc{s, static_cast<float*>(st->store->hot_cur), st->src_sel, st->n_nodes, st->t_garbage, s.N, s.Nmax};
+    *is_store = true;
+    *R = s.R;
+    return TARL_OK;
+}
+
+int check_agents(const tarl_agent_table* t, int R, AgentTable* at) {
+    if (t == nullptr || t->agent_features == nullptr || t->n_rows < 1) return TARL_E_BADARG;
+    if (R > 1 && t->replica_stride < (int64_t)t->n_rows * 9) return TARL_E_BADARG;
+    *at = AgentTable{t->agent_features, R > 1 ? t->replica_stride : 0, t->n_rows};
+    return TARL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
+                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* flags,
+                       void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_agents(agents, R, &at)) != TARL_OK) return rc;
+    if (index == nullptr || flags == nullptr || index->n_origins < 0) return TARL_E_BADARG;
+    const int N = is_store ? sto.N : row.N;
+    if (index->n_origins == 0 || N == 0) return TARL_OK;
+    if (!index->org_ptr || !index->org_agent || !index->origins || !head || !next || !cursor) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 g1(blocks_for(index->n_origins), R), g2(blocks_for(N), R);
+    if (is_store) {
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters);
+    } else {
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters);
+    }
+    return launch_status();
+}
+
+int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_csr* adjacency,
+                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_agents(agents, R, &at)) != TARL_OK) return rc;
+    const int N = is_store ? sto.N : row.N;
+    if (N == 0) return TARL_OK;
+    if (adjacency == nullptr || flags == nullptr || adjacency->n_rows < 0) return TARL_E_BADARG;
+    if (adjacency->n_rows > 0 && (!adjacency->ptr || (adjacency->n_edges > 0 && !adjacency->idx))) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 grid(blocks_for(N), R);
+    if (is_store) k_withdraw<<<grid, kThreads, 0, cs>>>(sto, at, *adjacency, t, mask, counters, flags);
+    else k_withdraw<<<grid, kThreads, 0, cs>>>(row, at, *adjacency, t, mask, counters, flags);
+    return launch_status();
+}
+
+int tarl_agents_choice(const tarl_agent_state* state, const tarl_csr* neighbours, const int32_t* choosers,
+                       int32_t n_choosers, const float* uniforms, uint64_t seed, uint32_t step_id, void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if (n_choosers < 0 || neighbours == nullptr) return TARL_E_BADARG;
+    if (n_choosers == 0) return TARL_OK;
+    if (!choosers || !neighbours->ptr || !neighbours->idx) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 grid(blocks_for(n_choosers), R);
+    if (is_store)
+        k_choice<<<grid, kThreads, 0, cs>>>(sto, *neighbours, choosers, n_choosers, uniforms, (uint32_t)seed,
+                                            (uint32_t)(seed >> 32), step_id);
+    else
+        k_choice<<<grid, kThreads, 0, cs>>>(row, *neighbours, choosers, n_choosers, uniforms, (uint32_t)seed,
+                                            (uint32_t)(seed >> 32), step_id);
+    return launch_status();
+}
+
+int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_src, const int32_t* edge_dst,
+                             int32_t n_edges, const void* action, int32_t action_dtype, void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if (n_edges < 0 || action_dtype < 0 || action_dtype > 2) return TARL_E_BADARG;
+    if (n_edges == 0) return TARL_OK;
+    if (!edge_src || !edge_dst || !action) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 grid(blocks_for(n_edges), R);
+    if (is_store) k_apply_action<<<grid, kThreads, 0, cs>>>(sto, edge_src, edge_dst, n_edges, action, action_dtype);
+    else k_apply_action<<<grid, kThreads, 0, cs>>>(row, edge_src, edge_dst, n_edges, action, action_dtype);
+    return launch_status();
+}
+
+int tarl_store_observe(const tarl_agent_state* state, float* node_features, int64_t* agent_index, int32_t* occupancy,
+                       void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if (!is_store) return TARL_E_BADARG;
+    if (sto.n_nodes == 0) return TARL_OK;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (occupancy != nullptr && cudaMemsetAsync(occupancy, 0, sizeof(int32_t) * (size_t)R, cs) != cudaSuccess)
+        return TARL_E_LAUNCH;
+    const dim3 grid(blocks_for(sto.n_nodes), R);
+    k_observe<<<grid, kThreads, 0, cs>>>(sto, node_features, reinterpret_cast<long long*>(agent_index), occupancy);
+    return launch_status();
+}
+
+}  // extern "C"

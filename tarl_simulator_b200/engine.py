@@ -134,6 +134,14 @@ class LinkStore:
             self.t_last = float(t)
         return self.pop[: self.N * self.R].view(self.R, self.N)
 
+    def clear_queues(self):
+        """TransportationSimulator.reset (src/transportation_simulator.py:353-358) on the store: the three queue
+        segments and NUM become zero on every link; MAXN, the statics and SELECTED_ROAD stay."""
+        hot = self.hot[self.cur]
+        hot[:, 0:3] = 0.0
+        hot[:, 4:8] = 0.0          # head arrival, tail id, pending garbage, meta (ring head 0, no garbage)
+        self.queue.zero_()
+
     def num_agents(self) -> torch.Tensor:
         """NUMBER_OF_AGENT per (replica, link), a strided view into the hot records."""
         return self.hot[self.cur][: self.N * self.R, 2].view(self.R, self.N)

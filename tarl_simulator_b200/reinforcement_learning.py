@@ -1,0 +1,301 @@
+"""RL environments over the simulator.
+
+`SimulatorEnv` is the drop-in for the reference's src/reinforcement_learning.py:102-309 (one environment, state in
+the reference's `graph.x` layout). torchrl / tensordict are not part of this stack: observations and step results
+are plain dicts of tensors with the reference's keys ("node_features", "edge_features", "agent_index", "time",
+"reward", "done", "terminated"), and `reset()` / `step()` / `rollout()` stand where EnvBase's would.
+
+`BatchedSimulatorEnv` is the B200-first form of the same environment for PPO rollouts: R independent replicas of one
+network advance together, state in the resident link store (engine.LinkStore) — per step one launch each for
+action → SELECTED_ROAD, the two core-step kernels, withdraw, the two insert kernels and the observation/reward
+kernel, for all replicas at once, with no host synchronisation.
+
+One `_step` = apply action → core step → withdraw → insert → reward = −Σ NUM → time += timestep
+(src/reinforcement_learning.py:222-276; time advances every step: declared divergence D6, the reference's
+"only if nothing moved" test compares a view with itself).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time as _time
+from types import SimpleNamespace
+
+import torch
+
+from . import _cabi
+from .agents import Agents, PopulationIndex, rows_state, side_tables_for
+from .engine import LinkStore
+from .transportation_simulator import TransportationSimulator
+
+EPISODE_START = 3600 * 6 - 60       # _reset, :203
+EPISODE_END = 7 * 3600              # done test, :273
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _action_code(action: torch.Tensor):
+    if action.dtype == torch.bool:
+        return action.contiguous().view(torch.uint8), _cabi.ACTION_U8
+    if action.dtype == torch.uint8:
+        return action.contiguous(), _cabi.ACTION_U8
+    if action.dtype == torch.int64:
+        return action.contiguous(), _cabi.ACTION_I64
+    return action.to(torch.float32).contiguous(), _cabi.ACTION_F32
+
+
+class SimulatorEnv:
+    def __init__(self, device: str = "cuda", timestep_size: int = 1, start_time: int = 0, scenario: str = "Easy",
+                 torch_compile: bool = False, simulator: TransportationSimulator | None = None):
+        self.device = torch.device(device)
+        if simulator is None:
+            simulator = TransportationSimulator(device=device, torch_compile=torch_compile)
+            simulator.load_network(scenario=scenario)
+        self.simulator = simulator
+        self.simulator.config_parameters(timestep_size=timestep_size, start_time=start_time)
+        g = self.simulator.graph
+        self.num_edge = g.edge_index.size(1)
+        self.num_node = g.x.size(0)
+        self.num_obs = 7
+        self.action_spec = SimpleNamespace(shape=torch.Size([self.num_edge]), dtype=torch.bool)
+        self.reward_spec = SimpleNamespace(shape=torch.Size([1]), dtype=torch.float32, low=-1e6, high=1e6)
+        self.observation_spec = {
+            "node_features": SimpleNamespace(shape=(self.num_node, self.num_obs), dtype=torch.float32),
+            "edge_features": SimpleNamespace(shape=(self.num_edge, 1), dtype=torch.float32),
+            "agent_index": SimpleNamespace(shape=(self.num_node,), dtype=torch.int64),
+            "time": SimpleNamespace(shape=(1,), dtype=torch.float32),
+        }
+        self.batch_size = torch.Size([])
+        self.state = self.simulator.state()
+        self.noise = None              # optional injected core-step uniforms for the next step ([E])
+
+    def set_seed(self, seed):
+        self.rng = torch.Generator(device=self.device)
+        self.rng.manual_seed(seed)
+        return seed
+
+    _set_seed = set_seed
+
+    def _observation(self):
+        x, edge_attr, _, agent_index = self.simulator.state()
+        return {"node_features": x, "edge_features": edge_attr, "agent_index": agent_index,
+                "time": torch.tensor([self.simulator.time], dtype=torch.float32, device=self.device)}
+
+    def _reset(self, tensordict=None):
+        sim = self.simulator
+        sim.reset()
+        sim.inserting_time = sim.choice_time = sim.core_time = sim.withdraw_time = 0
+        sim.leg_histogram_values = []
+        sim.road_optimality_values = []
+        sim.on_way_before = 0
+        sim.done_before = 0
+        sim.model_core.response_mpnn.update_history = []
+        sim.set_time(EPISODE_START)
+        out = self._observation()
+        sim.agent.reset()
+        out["terminated"] = torch.tensor([False])
+        out["done"] = torch.tensor([False])
+        return out
+
+    reset = _reset
+
+    def _step(self, tensordict):
+        sim, h = self.simulator, self.simulator.h
+        g = sim.graph
+        dev = g.x.device
+        action, code = _action_code(tensordict["action"].to(dev).reshape(-1))
+        side = side_tables_for(g)
+        b = _time.time()
+        st = rows_state(g, h.Nmax, with_cc=False)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_agents_apply_action(C.byref(st), side.src32.data_ptr(), side.dst32.data_ptr(),
+                                                      self.num_edge, action.data_ptr(), code, _stream(dev))
+        _cabi.check(rc, "tarl_agents_apply_action")
+        e = _time.time(); sim.choice_time += e - b; b = e
+        sim.graph = sim.model_core(g) if self.noise is None else sim.model_core(g, noise=self.noise)
+        e = _time.time(); sim.core_time += e - b; b = e
+        g.x = sim.agent.withdraw_agent_from_network(g, h)
+        e = _time.time(); sim.withdraw_time += e - b; b = e
+        g.x = sim.agent.insert_agent_into_network(g, h)
+        e = _time.time(); sim.inserting_time += e - b
+        reward = (-torch.sum(g.x[:, h.NUMBER_OF_AGENT])).flatten()                                   # :266-267
+        sim.set_time(sim.time + sim.timestep)                                                        # D6
+        done = torch.tensor(sim.time > EPISODE_END)
+        af = sim.agent.agent_features
+        value_on_way, value_done = torch.sum(af[:, sim.agent.ON_WAY]), torch.sum(af[:, sim.agent.DONE])
+        sim.leg_histogram_values.append([value_on_way - sim.on_way_before + value_done - sim.done_before,
+                                         value_done - sim.done_before, value_on_way, sim.time])
+        sim.on_way_before, sim.done_before = value_on_way, value_done
+        if sim.record_road_optimality:
+            sim.road_optimality_values.append(
+                (sim.time, sim.model_core.direction_mpnn.road_optimality_data["delta_travel_time"].cpu()))
+        out = self._observation()
+        out.update(reward=reward, terminated=done, done=done)
+        return out
+
+    def step(self, tensordict):
+        out = dict(tensordict)
+        out["next"] = self._step(tensordict)
+        return out
+
+    @torch.no_grad()
+    def rollout(self, max_steps, policy=None, break_when_any_done=True):
+        """Reset, then up to `max_steps` steps with `policy(obs) -> dict containing "action"`. Returns the list of
+        transitions (dicts with the observation keys, "action", and "next")."""
+        obs = self._reset()
+        traj = []
+        for _ in range(max_steps):
+            td = dict(obs)
+            td.update(policy(obs) if policy is not None else {"action": self.random_action()})
+            td = self.step(td)
+            traj.append(td)
+            obs = {k: v for k, v in td["next"].items() if k not in ("reward",)}
+            if break_when_any_done and bool(td["next"]["done"]):
+                break
+        return traj
+
+    def random_action(self):
+        """A uniformly random valid action: one out-edge per source node."""
+        from .distribution import GraphDistribution
+        logits = torch.zeros(self.num_edge, device=self.simulator.graph.x.device)
+        return GraphDistribution(logits, self.simulator.graph.edge_index).sample().to(torch.bool)
+
+
+class BatchedSimulatorEnv:
+    """R replicas of one network on one GPU, state in the resident link store. Static inputs (topology, link
+    attributes, the population's origins / destinations / departure times) are shared; per replica: queues,
+    SELECTED_ROAD, the ON_WAY / DONE / ARRIVAL_TIME columns of its own agent_features copy, its noise stream.
+
+    step(action [R, E_full] one-hot) -> dict(reward [R], done [R], occupancy int32 [R]); `observe()` materialises
+    node_features [R, N_tot, 7] / agent_index [R, N_tot] on demand (the policy's active path only needs ROAD_INDEX,
+    the value net only NUM: `num_agents()` is a strided view)."""
+
+    def __init__(self, graph, Nmax: int, agent_features: torch.Tensor, replicas: int, timestep: float = 1,
+                 seed: int = 0):
+        dev = graph.x.device
+        if dev.type != "cuda":
+            raise RuntimeError("BatchedSimulatorEnv lives on a CUDA device (no CPU fallback)")
+        self.graph, self.Nmax, self.R, self.device = graph, int(Nmax), int(replicas), dev
+        self.N, self.n_nodes = int(graph.num_roads), graph.x.size(0)
+        self.E_full = graph.edge_index.size(1)
+        self.timestep = timestep
+        self.store = LinkStore.from_graph(graph, Nmax, replicas=replicas, seed=seed)
+        F = 3 * self.Nmax + 7
+        self.src_sel = graph.x[self.N:, F - 2].to(torch.float32).repeat(self.R, 1).contiguous()
+        self.agent_features = agent_features.to(dev, torch.float32).unsqueeze(0).repeat(self.R, 1, 1).contiguous()
+        self.index = PopulationIndex(self.agent_features, self.n_nodes)
+        self.side = side_tables_for(graph)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self._head = torch.full((max(self.R * self.N, 1),), -1, **i32)
+        self._next = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
+        self._cursor = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
+        self.counters = torch.zeros(self.R, 2, **i32)          # running totals {inserted, withdrawn} per replica
+        self.occupancy = torch.zeros(self.R, **i32)
+        self.withdrawn = torch.zeros(self.R, self.N, dtype=torch.bool, device=dev)
+        self.delta_tt = None                                   # optional [R, E] output of the core step
+        self.time = float(EPISODE_START)
+        self._table = _cabi.AgentTable(self.agent_features.data_ptr(), self.agent_features.stride(0),
+                                       self.agent_features.size(1), 0)
+
+    def _state(self) -> _cabi.AgentState:
+        s = self.store
+        s._fill_struct()
+        st = _cabi.AgentState()
+        st.x, st.x_row_stride, st.x_replica_stride = None, 0, 0
+        st.n_links, st.nmax, st.n_replicas, st.n_nodes = self.N, self.Nmax, self.R, self.n_nodes
+        st.cc = None
+        st.store = C.pointer(s._struct)
+        st.src_sel = self.src_sel.data_ptr()
+        st.t_garbage = float(s.t_last)
+        return st
+
+    def reset(self):
+        """_reset (:186-219): empty queues, ON_WAY = DONE = 0, t = 06:00 − 60 s."""
+        self.store.clear_queues()
+        self.agent_features[..., Agents.ON_WAY] = 0.0
+        self.agent_features[..., Agents.DONE] = 0.0
+        self.counters.zero_()
+        self.time = float(EPISODE_START)
+
+    def set_time(self, t):
+        self.time = float(t)
+
+    def apply_action(self, action: torch.Tensor):
+        a, code = _action_code(action.reshape(self.R, self.E_full))
+        st = self._state()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_agents_apply_action(C.byref(st), self.side.src32.data_ptr(),
+                                                      self.side.dst32.data_ptr(), self.E_full, a.data_ptr(), code,
+                                                      _stream(self.device))
+        _cabi.check(rc, "tarl_agents_apply_action")
+
+    def choice(self, uniforms: torch.Tensor | None = None, seed: int = 0):
+        """Random routing for every replica (Agents.choice on the store)."""
+        st = self._state()
+        up = None
+        if uniforms is not None:
+            uniforms = uniforms.to(self.device, torch.float32).contiguous()
+            up = uniforms.data_ptr()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_agents_choice(C.byref(st), C.byref(self.side.nbr), self.side.choosers.data_ptr(),
+                                                self.side.n_choosers, up, seed, self.store.step_id, _stream(self.device))
+        _cabi.check(rc, "tarl_agents_choice")
+
+    def withdraw(self):
+        st = self._state()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_agents_withdraw(C.byref(st), C.byref(self._table), C.byref(self.side.adj), self.time,
+                                                  self.withdrawn.data_ptr(), self.counters.data_ptr(),
+                                                  self.store.flags.data_ptr(), _stream(self.device))
+        _cabi.check(rc, "tarl_agents_withdraw")
+
+    def insert(self):
+        st = self._state()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(self._table), self.index.ref(), self.time,
+                                                self._head.data_ptr(), self._next.data_ptr(), self._cursor.data_ptr(),
+                                                self.counters.data_ptr(), self.store.flags.data_ptr(),
+                                                _stream(self.device))
+        _cabi.check(rc, "tarl_agents_insert")
+
+    def observe(self, node_features: bool = True, agent_index: bool = True):
+        st = self._state()
+        nf = torch.empty(self.R, self.n_nodes, 7, dtype=torch.float32, device=self.device) if node_features else None
+        ai = torch.empty(self.R, self.n_nodes, dtype=torch.int64, device=self.device) if agent_index else None
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_observe(C.byref(st), nf.data_ptr() if nf is not None else None,
+                                                ai.data_ptr() if ai is not None else None, self.occupancy.data_ptr(),
+                                                _stream(self.device))
+        _cabi.check(rc, "tarl_store_observe")
+        return nf, ai
+
+    def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False):
+        """One _step for every replica. action None = keep the current SELECTED_ROAD values."""
+        if action is not None:
+            self.apply_action(action)
+        self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
+        self.withdraw()
+        self.insert()
+        nf, ai = self.observe(node_features=observe, agent_index=observe)
+        self.time += self.timestep
+        out = {"reward": -self.occupancy.to(torch.float32), "occupancy": self.occupancy,
+               "done": torch.full((self.R,), self.time > EPISODE_END, dtype=torch.bool, device=self.device),
+               "time": self.time}
+        if observe:
+            out["node_features"], out["agent_index"] = nf, ai
+        return out
+
+    def num_agents(self) -> torch.Tensor:
+        return self.store.num_agents()
+
+    def export_x(self) -> torch.Tensor:
+        """The full node table [R, N_tot, F] exactly as the reference would hold it."""
+        F = 3 * self.Nmax + 7
+        x = self.graph.x.unsqueeze(0).repeat(self.R, 1, 1)
+        self.store.export_x(out=x[:, :self.N])
+        x[:, self.N:, F - 2] = self.src_sel
+        return x
+
+    def check_errors(self):
+        self.store.check_errors()

@@ -1,0 +1,293 @@
+"""GPU parity of the simulator loop around the core step, through the C ABI (tarl_agents_insert / _withdraw / _choice /
+_apply_action, tarl_core_step, tarl_store_step, tarl_store_observe): after EVERY step the whole node table x and the
+whole agent_features must equal, bit for bit, what the unmodified reference produced (tests/golden/sim_*.npz) or what
+the CPU oracle port produces on seeded inputs — for the in-place drop-in classes (TransportationSimulator,
+SimulatorEnv) and for the batched link-store environment (BatchedSimulatorEnv)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import agents_port
+import cases
+from core_port import Cols
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CLASSICAL = ["sim_twolink", "sim_chain3", "sim_grid4", "sim_grid3_jam"]
+RL = ["sim_rl_grid3"]
+
+
+def golden(name):
+    return np.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+def product_simulator(d, tmp_path):
+    from tarl_simulator_b200.transportation_simulator import TransportationSimulator
+    (tmp_path / "network.xml").write_text(str(d["xml"]))
+    sim = TransportationSimulator("cuda")
+    sim.config_network(str(tmp_path / "network"))
+    sim.agent.agent_features = torch.from_numpy(d["af0"]).cuda()
+    return sim
+
+
+def as_time(v):
+    v = float(v)
+    return int(v) if v == int(v) else v
+
+
+@pytest.mark.parametrize("name", CLASSICAL)
+def test_transportation_simulator_run_matches_reference(name, tmp_path):
+    d = golden(name)
+    sim = product_simulator(d, tmp_path)
+    assert torch.equal(sim.graph.x.cpu(), torch.from_numpy(d["g_x"]))
+    sim.config_parameters(start_time=as_time(d["t0"]))
+    sim.agent.set_time(sim.time)
+    hist = sim.model_core.response_mpnn.update_history
+    for s in range(len(d["t"])):
+        n_hist = len(hist)
+        sim.run(noise=torch.from_numpy(d["u_core"][s]).cuda(), choice_uniforms=torch.from_numpy(d["u_choice"][s]).cuda())
+        assert torch.equal(sim.graph.x.cpu(), torch.from_numpy(d["x"][s])), f"x differs after step {s}"
+        assert torch.equal(sim.agent.agent_features.cpu(), torch.from_numpy(d["af"][s])), f"agents differ after step {s}"
+        assert torch.equal(sim.agent.withdraw_history[-1][1].cpu(), torch.from_numpy(d["withdrawn"][s]))
+        assert sim.agent.withdraw_history[-1][0] == as_time(d["t"][s])
+        assert torch.equal(sim.road_optimality_values[-1][1], torch.from_numpy(d["delta_tt"][s]))
+        assert (len(hist) > n_hist) == bool(d["has_pop"][s])
+        if d["has_pop"][s]:
+            assert torch.equal(hist[-1][1].cpu(), torch.from_numpy(d["pop"][s]))
+    assert sim.time == as_time(d["t"][-1]) + 1
+    sim.agent.check_errors()
+    sim.model_core.check_errors()
+
+
+@pytest.mark.parametrize("name", RL)
+def test_simulator_env_matches_reference(name, tmp_path):
+    from tarl_simulator_b200.reinforcement_learning import SimulatorEnv
+    d = golden(name)
+    sim = product_simulator(d, tmp_path)
+    env = SimulatorEnv(device="cuda", simulator=sim)
+    obs = env.reset()
+    assert float(obs["time"]) == float(d["t0"]) == 21540.0
+    assert torch.equal(sim.graph.x.cpu(), torch.from_numpy(d["x_reset"]))
+    assert obs["node_features"].shape == (sim.graph.x.size(0), 7) and obs["agent_index"].dtype == torch.int64
+    for s in range(len(d["t"])):
+        env.noise = torch.from_numpy(d["u_core"][s]).cuda()
+        out = env._step({"action": torch.from_numpy(d["action"][s]).cuda()})
+        assert torch.equal(sim.graph.x.cpu(), torch.from_numpy(d["x"][s])), f"x differs after step {s}"
+        assert torch.equal(sim.agent.agent_features.cpu(), torch.from_numpy(d["af"][s])), f"agents differ after step {s}"
+        assert float(out["reward"]) == float(d["reward"][s])
+        assert bool(out["done"]) == bool(d["done"][s])
+        assert float(out["time"]) == float(d["obs_time"][s])
+        assert torch.equal(out["agent_index"].cpu(), torch.from_numpy(d["x"][s][:, 0]).long())
+    sim.agent.check_errors()
+
+
+def batched_env(d, sim, R):
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    return BatchedSimulatorEnv(sim.graph, int(d["Nmax"]), torch.from_numpy(d["af0"]), replicas=R)
+
+
+@pytest.mark.parametrize("name", RL)
+def test_batched_env_matches_reference(name, tmp_path):
+    d = golden(name)
+    sim = product_simulator(d, tmp_path)
+    R = 3
+    env = batched_env(d, sim, R)
+    env.reset()
+    assert torch.equal(env.export_x()[1].cpu(), torch.from_numpy(d["x_reset"]))
+    E = sim.graph.edge_index_routes.size(1)
+    env.delta_tt = torch.empty(R, E, device="cuda")
+    for s in range(len(d["t"])):
+        u = torch.from_numpy(d["u_core"][s]).cuda().repeat(R, 1)
+        a = torch.from_numpy(d["action"][s]).cuda().repeat(R, 1)
+        out = env.step(a, noise=u, observe=True)
+        x = env.export_x().cpu()
+        for r in range(R):
+            assert torch.equal(x[r], torch.from_numpy(d["x"][s])), f"replica {r}: x differs after step {s}"
+            assert torch.equal(env.agent_features[r].cpu(), torch.from_numpy(d["af"][s])), f"replica {r}, step {s}"
+        assert out["reward"].tolist() == [float(d["reward"][s])] * R
+        assert torch.equal(env.withdrawn[0].cpu(), torch.from_numpy(d["withdrawn"][s]))
+        assert torch.equal(env.delta_tt[2].cpu(), torch.from_numpy(d["delta_tt"][s]))
+        assert torch.equal(out["node_features"][0].cpu(), torch.from_numpy(d["x"][s][:, -7:]))
+        assert torch.equal(out["agent_index"][1].cpu(), torch.from_numpy(d["x"][s][:, 0]).long())
+        assert out["time"] == float(d["obs_time"][s])
+    env.check_errors()
+    done = int(d["af"][-1][:, 8].sum())
+    assert env.counters[:, 1].tolist() == [done] * R
+
+
+@pytest.mark.parametrize("name", CLASSICAL)
+def test_batched_store_classical_order_matches_reference(name, tmp_path):
+    """insert -> withdraw -> choice -> core on the link store (the order of TransportationSimulator.run)."""
+    d = golden(name)
+    sim = product_simulator(d, tmp_path)
+    R = 2
+    env = batched_env(d, sim, R)
+    for s in range(len(d["t"])):
+        env.set_time(float(d["t"][s]))
+        env.insert()
+        env.withdraw()
+        env.choice(uniforms=torch.from_numpy(d["u_choice"][s]).cuda().repeat(R, 1))
+        env.store.step(env.time, noise=torch.from_numpy(d["u_core"][s]).cuda().repeat(R, 1))
+        x = env.export_x().cpu()
+        for r in range(R):
+            assert torch.equal(x[r], torch.from_numpy(d["x"][s])), f"replica {r}: x differs after step {s}"
+            assert torch.equal(env.agent_features[r].cpu(), torch.from_numpy(d["af"][s]))
+        assert torch.equal(env.withdrawn[1].cpu(), torch.from_numpy(d["withdrawn"][s]))
+    env.check_errors()
+
+
+def synthetic_case(seed, n, A, spread, length):
+    """n x n grid via the product's graph builder + a random population; dense adjacency for the oracle."""
+    from tarl_simulator_b200.matsim_io import graph_from_links
+    g = torch.Generator().manual_seed(seed)
+    _, _, frm, to = cases.grid_dual_graph(n)
+    L = frm.numel()
+    ln = torch.empty(L).uniform_(*length, generator=g)
+    graph, Nmax = graph_from_links([f"{int(v):04d}" for v in frm], [f"{int(v):04d}" for v in to], ln.tolist(),
+                                   torch.randint(600, 2400, (L,), generator=g).float().tolist(),
+                                   torch.randint(8, 20, (L,), generator=g).float().tolist(),
+                                   torch.randint(1, 3, (L,), generator=g).float().tolist(), dense=True)
+    af = torch.zeros(A + 1, 9)
+    af[0, 2] = 48 * 3600.0
+    o = torch.randint(0, n * n, (A,), generator=g)
+    dd = (o + torch.randint(1, n * n, (A,), generator=g)) % (n * n)
+    af[1:, 0], af[1:, 1] = (L + 2 * o).float(), (L + 2 * dd + 1).float()
+    af[1:, 2] = torch.randint(0, spread, (A,), generator=g).float()
+    return graph, Nmax, af, g
+
+
+@pytest.mark.parametrize("seed,n,A,spread,length,steps", [(31, 10, 4000, 40, (60.0, 140.0), 90),
+                                                          (32, 8, 6000, 10, (20.0, 40.0), 70)])
+def test_inplace_and_store_match_oracle_on_random_grids(seed, n, A, spread, length, steps):
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    from tarl_simulator_b200.transportation_simulator import TransportationSimulator
+    graph, Nmax, af, g = synthetic_case(seed, n, A, spread, length)
+    c = Cols(Nmax)
+    N = int(graph.num_roads)
+    E = graph.edge_index_routes.size(1)
+    ref_graph = {k: getattr(graph, k) for k in ("edge_index", "edge_index_routes", "edge_attr_routes", "adj_matrix",
+                                                "congestion_constant")}
+    ref_graph["num_roads"] = N
+    x_ref, af_ref = graph.x.clone(), af.clone()
+    sim = TransportationSimulator("cuda")
+    sim.graph, sim.Nmax = graph.to("cuda"), Nmax
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    sim.h = FeatureHelpers(Nmax)
+    sim.agent.agent_features = af.cuda()
+    sim.config_parameters(start_time=0)
+    sim.agent.set_time(0)
+    sim.record_road_optimality = False
+    env = BatchedSimulatorEnv(sim.graph, Nmax, af, replicas=2)
+    nodes, _, _ = agents_port.choosers_and_neighbours(graph.edge_index.cpu(), N, x_ref.size(0))
+    moved = 0
+    for s in range(steps):
+        u_core, u_choice = cases.uniforms(g, E), torch.rand(nodes.numel(), generator=g)
+        out = agents_port.run_step(x_ref, af_ref, s, c, ref_graph, u_choice, u_core)
+        moved += 0 if out["pop"] is None else int(out["pop"].sum())
+        sim.run(noise=u_core.cuda(), choice_uniforms=u_choice.cuda())
+        assert torch.equal(sim.graph.x.cpu(), x_ref), f"in-place x differs after step {s}"
+        assert torch.equal(sim.agent.agent_features.cpu(), af_ref), f"in-place agents differ after step {s}"
+        env.set_time(float(s))
+        env.insert(); env.withdraw(); env.choice(uniforms=u_choice.cuda().repeat(2, 1))
+        env.store.step(env.time, noise=u_core.cuda().repeat(2, 1))
+        if s % 10 == 9 or s == steps - 1:
+            assert torch.equal(env.export_x()[1].cpu(), x_ref), f"store x differs after step {s}"
+            assert torch.equal(env.agent_features[0].cpu(), af_ref), f"store agents differ after step {s}"
+    assert moved > 100 and int(af_ref[:, 8].sum()) > 0
+    sim.agent.check_errors(); env.check_errors()
+
+
+def test_reference_agent_tests_on_gpu():
+    """The reference's own tests/agents_test.py (insert_and_withdraw, insert_capacity_limit), on the device."""
+    from tarl_simulator_b200.agents import Agents
+    from tarl_simulator_b200.data import Data
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    h = FeatureHelpers(Nmax=5)
+
+    def graph():
+        x = torch.zeros((2, 3 * h.Nmax + 7))
+        x[0, h.MAX_NUMBER_OF_AGENT] = 5
+        x[0, h.ROAD_INDEX] = 0
+        x[0, h.FREE_FLOW_TIME_TRAVEL] = 10
+        edge_index = torch.tensor([[1, 0], [0, 0]])
+        return Data(x=x.cuda(), edge_index=edge_index.cuda(), edge_index_routes=torch.empty((2, 0), dtype=torch.long).cuda(),
+                    edge_attr_routes=torch.empty((0, 1)).cuda(), num_roads=1)
+
+    agents = Agents("cuda")
+    agents.agent_features = torch.tensor([[1.0, 0.0, 0.0, 0.0, 30.0, 0.0, 1.0, 0.0, 0.0],
+                                          [1.0, 0.0, 0.0, 0.0, 25.0, 1.0, 0.0, 0.0, 0.0]]).cuda()
+    g = graph()
+    agents.time = 0
+    g.x = agents.insert_agent_into_network(g, h)
+    assert g.x[0, h.NUMBER_OF_AGENT] == 2
+    assert torch.all(agents.agent_features[:2, agents.ON_WAY] == 1)
+    g.x = agents.withdraw_agent_from_network(g, h)
+    assert g.x[0, h.NUMBER_OF_AGENT] == 2
+    agents.time = 10
+    g.x = agents.withdraw_agent_from_network(g, h)
+    assert g.x[0, h.NUMBER_OF_AGENT] == 0
+    assert torch.all(agents.agent_features[:2, agents.DONE] == 1)
+    assert len(agents.withdraw_history) == 2 and bool(agents.withdraw_history[1][1][0])
+
+    agent = Agents("cuda")
+    agent.agent_features = torch.tensor([[1.0, 0, 0, 0, 0, 0, 0, 0, 0]] * 4).cuda()
+    g = graph()
+    agent.time = 0
+    g.x = agent.insert_agent_into_network(g, h)
+    assert g.x[0, h.NUMBER_OF_AGENT] == 2
+    assert torch.all(agent.agent_features[:2, agent.ON_WAY] == 1)
+    assert torch.all(agent.agent_features[2:, agent.ON_WAY] == 0)
+
+
+def test_insert_merges_origins_that_select_the_same_road():
+    """Two SRC nodes point at one road: the admitted agents are the smallest ready ids of the union (base.py:275-291
+    with a stable sort), whatever order the origin lists were pushed in."""
+    from tarl_simulator_b200.agents import Agents
+    from tarl_simulator_b200.data import Data
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    h = FeatureHelpers(Nmax=12)
+    c = Cols(12)
+    x = torch.zeros(5, c.F)
+    x[0, c.MAXN], x[0, c.FFTT] = 11, 4.0            # road 0: room 8
+    x[1, c.MAXN], x[1, c.FFTT], x[1, c.RIDX] = 11, 6.0, 1
+    x[2:, c.RIDX] = -1
+    x[2, c.SEL], x[3, c.SEL], x[4, c.SEL] = 0, 0, 1  # nodes 2 and 3 both select road 0
+    g = torch.Generator().manual_seed(3)
+    A = 40
+    af = torch.zeros(A + 1, 9)
+    af[0, 2] = 1e6
+    af[1:, 0] = torch.randint(2, 5, (A,), generator=g).float()
+    af[1:, 2] = torch.randint(0, 3, (A,), generator=g).float()
+    af[1:, 1] = 1.0
+    x_ref, af_ref = x.clone(), af.clone()
+    graph = Data(x=x.cuda(), edge_index=torch.tensor([[2, 3, 4], [0, 0, 1]]).cuda(),
+                 edge_index_routes=torch.empty((2, 0), dtype=torch.long).cuda(), edge_attr_routes=torch.empty((0, 1)).cuda(),
+                 num_roads=2)
+    agents = Agents("cuda")
+    agents.agent_features = af.cuda()
+    for t in range(4):
+        agents_port.insert(x_ref, af_ref, t, c, None)
+        agents.time = t
+        agents.insert_agent_into_network(graph, h)
+        assert torch.equal(graph.x.cpu(), x_ref) and torch.equal(agents.agent_features.cpu(), af_ref)
+        x_ref[:2, c.NUM] = 0
+        graph.x[:2, c.NUM] = 0                      # drain so that later steps admit again
+    assert int(af_ref[:, 7].sum()) >= 24
+    agents.check_errors()
+
+
+def test_cpu_tensors_are_refused():
+    from tarl_simulator_b200.agents import Agents
+    from tarl_simulator_b200.data import Data
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    h = FeatureHelpers(Nmax=5)
+    a = Agents("cpu")
+    a.agent_features = torch.zeros(2, 9)
+    g = Data(x=torch.zeros(2, 22), edge_index=torch.zeros(2, 1, dtype=torch.long), num_roads=1,
+             edge_index_routes=torch.zeros(2, 0, dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        a.insert_agent_into_network(g, h)
