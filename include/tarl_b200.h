@@ -222,6 +222,30 @@ int tarl_graphdist_sample(const tarl_csr* groups, const float* logits, float tem
                           const float* uniforms, int64_t* onehot, void* stream);
 
 
+/* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
+ * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]
+ * + w0); mean over the edges sharing edge_index[0]; v = tanh(a*mean + c). by_source / by_target: CSR of edge_index by
+ * source / target NODE (n_rows = n_nodes), idx = the other endpoint, eid ascending inside a row.
+ * node_features [B,N,>=7] (element strides given), edge_features [B,E], agent_index [B,N] int64, agent_features
+ * [agent_rows, 9]. msg_weight [17] (= message_mlp.1.weight), msg_bias [1], node_weight [1], node_bias [1] are device
+ * pointers. Outputs proj, mean, v: [B,N] each (proj and mean are what backward needs). */
+int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
+                          int64_t nf_row_stride, const float* edge_features, const int64_t* agent_index,
+                          const float* agent_features, int32_t agent_rows, const float* msg_weight,
+                          const float* msg_bias, const float* node_weight, const float* node_bias, int32_t batch,
+                          int32_t n_nodes, float* proj, float* mean, float* v, int32_t* flags, void* stream);
+
+/* Gradient of sum(grad_v * v) w.r.t. the four parameter tensors: grads[0:17] = d msg_weight, [17] = d msg_bias,
+ * [18] = d node_weight, [19] = d node_bias. gm: [B,N] scratch; partials: 20*tarl_value_mp_partial_count(N,B) floats.
+ * Fixed summation order (deterministic). */
+int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch);
+int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                           int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
+                           const float* msg_weight, const float* msg_bias, const float* node_weight, int32_t batch,
+                           int32_t n_nodes, const float* proj, const float* mean, const float* v, const float* grad_v,
+                           float* gm, float* partials, float* grads, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Population operations either side of the core step (csrc/agents.cu). Each works on either state layout.
  * ------------------------------------------------------------------------------------------------------------- */

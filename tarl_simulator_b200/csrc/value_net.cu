@@ -1,0 +1,240 @@
+// value_net.cu — MPNNValueNet's message / mean-aggregate / update, forward and backward (sm_100a, fp32).
+//
+// Reference semantics: /root/reference/src/agents/mpnn_agent.py:267-402 with dropout off (eval mode):
+//   x[b,n]   = [node_features[b,n,0:7] ‖ agent_features[agent_index[b,n], 0:9]]                     (:330-349)
+//   msg[b,e] = tanh(w · [x[b, edge_index[1][e]] ‖ edge_features[b,e]] + w0)   flow target_to_source  (:385-386)
+//   mean[b,n]= mean of msg over the edges whose edge_index[0] == n (0 for nodes without one)         (aggr='mean')
+//   v[b,n]   = tanh(a * mean + c)                                                                    (:402)
+// The 16 node terms of the message do not depend on the edge, so they are projected ONCE per node
+// (proj[b,n] = w[0:16] · x[b,n]) instead of being gathered as [E,16] rows per edge as PyG does: per edge the kernels
+// read one 4-byte projected scalar + the edge feature. Every reduction has a fixed order (segment sums in ascending
+// edge id, per-block partials summed by a second kernel), so results are run-to-run deterministic.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tarl_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kNodeDim = 7, kAgentDim = 9, kIn = 16;
+constexpr int kGrads = 20;   // w[0:17], w0, a, c
+
+inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
+
+struct Inputs {
+    const float* nf; int64_t nf_bs, nf_rs;     // node_features [B,N,>=7]
+    const float* ef;                           // edge_features [B,E]
+    const long long* ai;                       // agent_index [B,N]
+    const float* af; int af_rows;              // agent_features [rows,9]
+    int B, N, E;
+};
+
+__device__ __forceinline__ void load_x(const Inputs& in, int b, int n, float x[kIn], int32_t* flags) {
+    const float* p = in.nf + b * in.nf_bs + n * in.nf_rs;
+#pragma unroll
+    for (int c = 0; c < kNodeDim; ++c) x[c] = p[c];
+    long long a = in.ai[(int64_t)b * in.N + n];
+    if (a < 0) a += in.af_rows;                                   // torch advanced indexing wraps negatives
+    if (a < 0 || a >= in.af_rows) {
+        if (flags != nullptr) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_AGENT_RANGE);
+        a = 0;
+    }
+    const float* q = in.af + a * kAgentDim;
+#pragma unroll
+    for (int c = 0; c < kAgentDim; ++c) x[kNodeDim + c] = q[c];
+}
+
+__global__ void __launch_bounds__(kThreads) k_value_project(Inputs in, const float* __restrict__ w,
+                                                            float* __restrict__ proj, int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)in.B * in.N) return;
+    const int b = (int)(i / in.N), n = (int)(i % in.N);
+    float x[kIn];
+    load_x(in, b, n, x, flags);
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kIn; ++c) acc += w[c] * x[c];
+    proj[i] = acc;
+}
+
+// one thread per (batch row, source node): segment mean of tanh messages in ascending edge id, then the node update
+__global__ void __launch_bounds__(kThreads) k_value_aggregate(tarl_csr by_src, Inputs in, const float* __restrict__ w,
+                                                              const float* __restrict__ w0, const float* __restrict__ a,
+                                                              const float* __restrict__ c, const float* __restrict__ proj,
+                                                              float* __restrict__ mean, float* __restrict__ v) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    if (n >= in.N) return;
+    const int b = blockIdx.y;
+    const float we = w[kIn], bias = w0[0];
+    const float* pj = proj + (int64_t)b * in.N;
+    const float* ef = in.ef + (int64_t)b * in.E;
+    const int k0 = by_src.ptr[n], k1 = by_src.ptr[n + 1];
+    float acc = 0.0f;
+    for (int k = k0; k < k1; ++k) acc += tanhf(pj[by_src.idx[k]] + we * ef[by_src.eid[k]] + bias);
+    const float m = k1 > k0 ? acc / (float)(k1 - k0) : 0.0f;
+    mean[(int64_t)b * in.N + n] = m;
+    v[(int64_t)b * in.N + n] = tanhf(a[0] * m + c[0]);
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// sums `count` per-thread values over the block (fixed tree) and lets thread 0 write them to dst[0..count)
+template <int kCount>
+__device__ __forceinline__ void block_store(float (&vals)[kCount], float* __restrict__ dst) {
+    __shared__ float sm[kThreads / 32][kCount];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kCount; ++j) {
+        const float s = warp_sum(vals[j]);
+        if (lane == 0) sm[wid][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < kCount) {
+        float s = 0.0f;
+        for (int wi = 0; wi < kThreads / 32; ++wi) s += sm[wi][threadIdx.x];
+        dst[threadIdx.x] = s;
+    }
+}
+
+// node update backward: dv = g_v (1 - v^2); partial sums of d a, d c; gm = dv * a / deg handed to the edge pass
+__global__ void __launch_bounds__(kThreads) k_value_node_grad(tarl_csr by_src, int B, int N, const float* __restrict__ a,
+                                                              const float* __restrict__ mean, const float* __restrict__ v,
+                                                              const float* __restrict__ gv, float* __restrict__ gm,
+                                                              float* __restrict__ partials) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    const int b = blockIdx.y;
+    float vals[2] = {0.0f, 0.0f};
+    if (n < N) {
+        const int64_t i = (int64_t)b * N + n;
+        const float vv = v[i];
+        const float dv = gv[i] * (1.0f - vv * vv);
+        vals[0] = dv * mean[i];
+        vals[1] = dv;
+        const int deg = by_src.ptr[n + 1] - by_src.ptr[n];
+        gm[i] = deg > 0 ? dv * a[0] / (float)deg : 0.0f;
+    }
+    block_store<2>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * kGrads + 18);
+}
+
+// message backward, one thread per (batch row, TARGET node): every in-edge's message is recomputed from this node's
+// own projection; the 16 input-weight gradients need the node's x once, not once per edge.
+__global__ void __launch_bounds__(kThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, const float* __restrict__ w,
+                                                              const float* __restrict__ w0, const float* __restrict__ proj,
+                                                              const float* __restrict__ gm, float* __restrict__ partials) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    const int b = blockIdx.y;
+    float vals[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
+    if (n < in.N) {
+        const float we = w[kIn], bias = w0[0];
+        const float pn = proj[(int64_t)b * in.N + n];
+        const float* ef = in.ef + (int64_t)b * in.E;
+        const float* g = gm + (int64_t)b * in.N;
+        float gs = 0.0f, gwe = 0.0f;
+        const int k1 = by_dst.ptr[n + 1];
+        for (int k = by_dst.ptr[n]; k < k1; ++k) {
+            const float f = ef[by_dst.eid[k]];
+            const float m = tanhf(pn + we * f + bias);
+            const float gz = g[by_dst.idx[k]] * (1.0f - m * m);
+            gs += gz;
+            gwe += gz * f;
+        }
+        if (gs != 0.0f) {
+            float x[kIn];
+            load_x(in, b, n, x, nullptr);
+#pragma unroll
+            for (int cI = 0; cI < kIn; ++cI) vals[cI] = gs * x[cI];
+        }
+        vals[16] = gwe;
+        vals[17] = gs;
+    }
+    block_store<18>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * kGrads);
+}
+
+// grads[j] = sum over all blocks of partials[.., j]: one CTA per j, strided accumulation then a fixed tree
+__global__ void __launch_bounds__(kThreads) k_value_finish(const float* __restrict__ partials, int n_parts,
+                                                           float* __restrict__ grads) {
+    __shared__ float sm[kThreads];
+    const int j = blockIdx.x;
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n_parts; i += kThreads) s += partials[(size_t)i * kGrads + j];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grads[j] = sm[0];
+}
+
+int check(const tarl_csr* c, int n_nodes) {
+    if (c == nullptr || c->n_rows != n_nodes || c->n_edges < 0) return TARL_E_BADARG;
+    if (n_nodes > 0 && c->ptr == nullptr) return TARL_E_BADARG;
+    if (c->n_edges > 0 && (c->idx == nullptr || c->eid == nullptr)) return TARL_E_BADARG;
+    return TARL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch) {
+    return (n_nodes > 0 && batch > 0) ? blocks_for(n_nodes) * batch : 0;
+}
+
+int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
+                          int64_t nf_row_stride, const float* edge_features, const int64_t* agent_index,
+                          const float* agent_features, int32_t agent_rows, const float* msg_weight,
+                          const float* msg_bias, const float* node_weight, const float* node_bias, int32_t batch,
+                          int32_t n_nodes, float* proj, float* mean, float* v, int32_t* flags, void* stream) {
+    if (batch < 0 || n_nodes < 0 || agent_rows < 1) return TARL_E_BADARG;
+    int rc = check(by_source, n_nodes);
+    if (rc != TARL_OK) return rc;
+    if (batch == 0 || n_nodes == 0) return TARL_OK;
+    if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !node_bias ||
+        !proj || !mean || !v || !flags || (by_source->n_edges > 0 && !edge_features))
+        return TARL_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features,
+                       reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
+                       by_source->n_edges};
+    k_value_project<<<blocks_for((int64_t)batch * n_nodes), kThreads, 0, s>>>(in, msg_weight, proj, flags);
+    k_value_aggregate<<<dim3(blocks_for(n_nodes), batch), kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias,
+                                                                            node_weight, node_bias, proj, mean, v);
+    return launch_status();
+}
+
+int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                           int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
+                           const float* msg_weight, const float* msg_bias, const float* node_weight, int32_t batch,
+                           int32_t n_nodes, const float* proj, const float* mean, const float* v, const float* grad_v,
+                           float* gm, float* partials, float* grads, void* stream) {
+    if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr) return TARL_E_BADARG;
+    int rc = check(by_source, n_nodes);
+    if (rc == TARL_OK) rc = check(by_target, n_nodes);
+    if (rc != TARL_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (batch == 0 || n_nodes == 0) {
+        return cudaMemsetAsync(grads, 0, sizeof(float) * kGrads, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+    }
+    if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !proj ||
+        !mean || !v || !grad_v || !gm || !partials || (by_source->n_edges > 0 && !edge_features))
+        return TARL_E_BADARG;
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features,
+                       reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
+                       by_source->n_edges};
+    const dim3 grid(blocks_for(n_nodes), batch);
+    k_value_node_grad<<<grid, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, mean, v, grad_v, gm, partials);
+    k_value_edge_grad<<<grid, kThreads, 0, s>>>(*by_target, in, msg_weight, msg_bias, proj, gm, partials);
+    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
+    return launch_status();
+}
+
+}  // extern "C"

@@ -137,6 +137,112 @@ class MPNNPolicyNet(MessagePassing, Agents):
                 raise IndexError(_cabi.decode_error_bits(bits))
 
 
+class _ValueMessagePassing(torch.autograd.Function):
+    """v [B,N] = update(mean-aggregate(message)) of MPNNValueNet; gradients w.r.t. the four parameter tensors."""
+
+    @staticmethod
+    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags):
+        B, N, _ = nf.shape
+        dev = nf.device
+        proj = torch.empty(B, N, dtype=torch.float32, device=dev)
+        mean = torch.empty(B, N, dtype=torch.float32, device=dev)
+        v = torch.empty(B, N, dtype=torch.float32, device=dev)
+        pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_value_mp_forward(
+                by_source.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ai.data_ptr(), af.data_ptr(),
+                af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N, proj.data_ptr(),
+                mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mp_forward")
+        ctx.by_source, ctx.by_target = by_source, by_target
+        ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
+        ctx.save_for_backward(pw, pb, nw, nf, ef, ai, af, proj, mean, v)
+        return v
+
+    @staticmethod
+    def backward(ctx, grad_v):
+        pw, pb, nw, nf, ef, ai, af, proj, mean, v = ctx.saved_tensors
+        B, N, _ = nf.shape
+        dev = nf.device
+        lib = _cabi.lib()
+        gv = grad_v.contiguous()
+        gm = torch.empty(B, N, dtype=torch.float32, device=dev)
+        partials = torch.empty(max(20 * lib.tarl_value_mp_partial_count(N, B), 1), dtype=torch.float32, device=dev)
+        grads = torch.empty(20, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_value_mp_backward(
+                ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
+                ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), B, N,
+                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), gv.data_ptr(), gm.data_ptr(), partials.data_ptr(),
+                grads.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mp_backward")
+        s = ctx.shapes
+        return (grads[:17].reshape(s[0]), grads[17:18].reshape(s[1]), grads[18:19].reshape(s[2]),
+                grads[19:20].reshape(s[3]), None, None, None, None, None, None, None)
+
+
+class MPNNValueNet(MessagePassing, Agents):
+    """State value by one round of message passing over the full graph (src/agents/mpnn_agent.py:267-402):
+    per edge tanh(Linear(17→1)([x_target(16) ‖ edge_attr])), mean over each source node's out-edges,
+    tanh(Linear(1→1)), then Linear(N+1→1) over [v_nodes ‖ time_net(time)]. Parameter names / shapes are the
+    reference's (`message_mlp.1.*`, `node_mlp.0.*`, `final_mlp.0.*`, `time_net.{0,3,6}.*`). The gather / aggregate /
+    update and their backward are csrc/value_net.cu; the two dense heads (time_net, final_mlp) are library GEMVs.
+
+    The reference applies Dropout(0.05) to every [E,17] message input in train mode; an RNG-dependent mask cannot be
+    matched across implementations, so the kernels implement the deterministic (eval / p = 0) path and train mode
+    with p > 0 raises (SURVEY.md §7 "hard parts")."""
+
+    h = ObservationFeatureHelpers()
+
+    def __init__(self, edge_index, num_nodes, device):
+        Agents.__init__(self, device=device)
+        MessagePassing.__init__(self, aggr="mean", flow="target_to_source")
+        self.edge_index = edge_index
+        self.num_nodes = num_nodes
+        self.num_edges = edge_index.size(1)
+        self.dim_nodes_features = 16
+        self.dim_edges_features = 1
+        self.message_mlp = nn.Sequential(nn.Dropout(0.05), nn.Linear(17, 1), nn.Tanh())
+        self.node_mlp = nn.Sequential(nn.Linear(1, 1), nn.Tanh())
+        self.final_mlp = nn.Sequential(nn.Linear(self.num_nodes + 1, 1))
+        self.time_net = nn.Sequential(nn.Linear(1, 32), nn.Dropout(0.05), nn.ReLU(), nn.Linear(32, 32),
+                                      nn.Dropout(0.05), nn.ReLU(), nn.Linear(32, 1))
+        self.to(device)
+        self._ei_dev = None
+        self._flags = None
+
+    def forward(self, node_features, edge_features, agent_index, time):
+        if not node_features.is_cuda:
+            raise RuntimeError("MPNNValueNet computes on CUDA devices only (no CPU fallback)")
+        if self.training and self.message_mlp[0].p > 0:
+            raise NotImplementedError("MPNNValueNet: message dropout is RNG-dependent; call .eval() or set p = 0")
+        batched = node_features.dim() == 3
+        nf = (node_features if batched else node_features.unsqueeze(0)).to(torch.float32)
+        if nf.stride(2) != 1:
+            nf = nf.contiguous()
+        B, N = nf.size(0), nf.size(1)
+        ef = (edge_features if batched else edge_features.unsqueeze(0)).to(torch.float32).reshape(B, -1).contiguous()
+        ai = (agent_index if batched else agent_index.unsqueeze(0)).to(torch.int64).contiguous()
+        af = self.agent_features.to(device=nf.device, dtype=torch.float32).contiguous()
+        if self._ei_dev is None or self._ei_dev.device != nf.device:
+            self._ei_dev = self.edge_index.to(nf.device)
+        by_source = group_csr_for(self._ei_dev, "source", self.num_nodes)
+        by_target = group_csr_for(self._ei_dev, "target", self.num_nodes)
+        self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=nf.device)
+        lin, upd = self.message_mlp[1], self.node_mlp[0]
+        v = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
+                                       by_target, self._flags)
+        if not batched:
+            v = v.view(self.num_nodes)
+        return self.final_mlp(torch.cat((v, self.time_net(time)), dim=-1))
+
+    def check_errors(self):
+        if self._flags is not None:
+            bits = int(self._flags[_cabi.FLAG_ERROR])
+            if bits:
+                raise IndexError(_cabi.decode_error_bits(bits))
+
+
 class MPNNValueNetSimple(MessagePassing, Agents):
     """State value from the per-link occupancies: MLP([NUMBER_OF_AGENT column ‖ time]), (N+1)→64→64→1 with ReLU
     (src/agents/mpnn_agent.py:407-450) — the value net Runner wires (src/runner.py:68). Dense GEMMs: library calls."""

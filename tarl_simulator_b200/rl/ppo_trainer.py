@@ -1,0 +1,298 @@
+"""PPO training loop over SimulatorEnv / BatchedSimulatorEnv.
+
+Drop-in for the reference's src/rl/ppo_trainer.py:12-160 (`ppo_train` keeps its keyword set). torchrl is not part of
+this stack; the pieces the reference takes from torchrl 0.5.0 are restated on plain torch with the same formulas and
+the reference's settings:
+
+  collector   frames_per_batch steps per iteration, environment reset at each iteration, actions sampled
+  GAE         gamma 0.99, lambda 0.95; delta_t = r_t + gamma V(s_{t+1}) (1 - terminated) - V(s_t);
+              A_t = delta_t + gamma lambda (1 - done_t) A_{t+1}; value_target = A + V; then A standardised over the
+              whole batch with std clamped at 1e-4 (average_gae=True)
+  ClipPPOLoss clip 0.2, entropy bonus 0.01, critic coefficient 1.0 with smooth-L1, no advantage normalisation
+  optimiser   Adam(lr 1e-3); per epoch: advantages recomputed, min(sub_batch_size, frames) frames drawn without
+              replacement, one step; gradient norm measured, not clipped
+
+Multi-GPU (one process per GPU, torch.distributed initialised by the launcher): every rank rolls out its own
+replicas with no communication; per optimiser step ONE all-reduce of the flat fp32 gradient bucket (averaged), plus
+a 3-scalar all-reduce for the advantage statistics, so that all ranks apply identical updates.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..distribution import GraphDistribution
+from ..feature_helpers import ObservationFeatureHelpers as OBS
+
+
+class PolicyModule(nn.Module):
+    """Stands where the reference wires TensorDictModule(policy_net) → ProbabilisticActor(GraphDistribution)
+    (src/runner.py:83-95): observation dict → logits → distribution → one-hot action (+ its log-probability)."""
+
+    def __init__(self, policy_net, edge_index, return_log_prob: bool = True):
+        super().__init__()
+        self.net = policy_net
+        self.edge_index = edge_index
+        self.return_log_prob = return_log_prob
+
+    def dist(self, obs) -> GraphDistribution:
+        logits = self.net(obs["node_features"], obs.get("edge_features"), obs.get("agent_index"))
+        return GraphDistribution(logits, self.edge_index)
+
+    def forward(self, obs, mode: bool = False):
+        d = self.dist(obs)
+        action = (d.mode if mode else d.sample()).to(torch.bool)
+        out = {"action": action}
+        if self.return_log_prob:
+            out["sample_log_prob"] = d.log_prob(action).detach()
+        return out
+
+
+class ValueModule(nn.Module):
+    """ValueOperator stand-in (src/runner.py:97-105)."""
+
+    def __init__(self, value_net):
+        super().__init__()
+        self.net = value_net
+
+    def forward(self, obs):
+        return self.net(obs["node_features"], obs.get("edge_features"), obs.get("agent_index"), obs["time"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def gae(value, next_value, reward, done, terminated, gamma=0.99, lmbda=0.95):
+    """torchrl 0.5.0 generalized_advantage_estimate over the leading time dimension. All inputs [T, ...]."""
+    not_term = 1.0 - terminated.to(value.dtype)
+    not_done = 1.0 - done.to(value.dtype)
+    delta = reward + gamma * next_value * not_term - value
+    adv = torch.empty_like(value)
+    running = torch.zeros_like(value[0])
+    for t in range(value.size(0) - 1, -1, -1):
+        running = delta[t] + gamma * lmbda * not_done[t] * running
+        adv[t] = running
+    return adv, adv + value
+
+
+def standardise(adv, group=None):
+    """average_gae=True: (A - mean) / std.clamp_min(1e-4), unbiased std; statistics over every rank's frames."""
+    n = torch.tensor(float(adv.numel()), device=adv.device, dtype=torch.float64)
+    stats = torch.stack([n, adv.double().sum(), (adv.double() ** 2).sum()])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, group=group)
+    n, s, ss = stats[0], stats[1], stats[2]
+    mean = s / n
+    var = (ss - n * mean * mean) / torch.clamp(n - 1, min=1.0)
+    std = torch.sqrt(torch.clamp(var, min=0.0)).clamp_min(1e-4)
+    return ((adv.double() - mean) / std).to(adv.dtype)
+
+
+def clip_ppo_loss(log_prob, sample_log_prob, advantage, entropy, value, value_target, clip_epsilon=0.2,
+                  entropy_coef=0.01, critic_coef=1.0):
+    """torchrl 0.5.0 ClipPPOLoss.forward with the reference's settings."""
+    log_weight = log_prob - sample_log_prob
+    ratio = log_weight.exp()
+    gain1 = ratio * advantage
+    gain2 = ratio.clamp(1.0 - clip_epsilon, 1.0 + clip_epsilon) * advantage
+    out = {
+        "loss_objective": -torch.minimum(gain1, gain2).mean(),
+        "loss_entropy": -entropy_coef * entropy.mean(),
+        "loss_critic": critic_coef * F.smooth_l1_loss(value, value_target, reduction="none").mean(),
+    }
+    with torch.no_grad():
+        out["approx_kl"] = (-log_weight).mean()
+        out["clip_fraction"] = ((ratio - 1.0).abs() > clip_epsilon).float().mean()
+        out["entropy"] = entropy.mean()
+    return out
+
+
+def allreduce_gradients(params, group=None):
+    """One flat fp32 bucket, averaged over ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _EnvAdapter:
+    """Uniform [R]-batched view of SimulatorEnv (R = 1, reference row layout) and BatchedSimulatorEnv (link store)."""
+
+    def __init__(self, env):
+        self.env = env
+        self.batched = hasattr(env, "store")
+        g = env.graph if self.batched else env.simulator.graph
+        self.graph = g
+        self.R = env.R if self.batched else 1
+        self.n_nodes = g.x.size(-2)
+        self.device = g.x.device
+        Nmax = env.Nmax if self.batched else env.simulator.Nmax
+        self.static = g.x[..., 3 * Nmax:].reshape(-1, 7)[: self.n_nodes].clone()      # MAXN .. ROAD_INDEX template
+        self.edge_features = g.edge_attr
+
+    def reset(self):
+        if self.batched:
+            self.env.reset()
+        else:
+            self.env._reset()
+
+    def time(self):
+        return float(self.env.time if self.batched else self.env.simulator.time)
+
+    def dynamic(self):
+        """(NUM [R, N_tot], SELECTED_ROAD [R, N_tot], head agent id [R, N_tot]) of the current state."""
+        if self.batched:
+            nf, ai = self.env.observe(node_features=True, agent_index=True)
+            return nf[..., OBS.NUMBER_OF_AGENT], nf[..., OBS.SELECTED_ROAD], ai
+        x, _, _, ai = self.env.simulator.state()
+        return x[:, OBS.NUMBER_OF_AGENT].unsqueeze(0).clone(), x[:, OBS.SELECTED_ROAD].unsqueeze(0).clone(), ai.unsqueeze(0)
+
+    def step(self, action):
+        """action [R, E_full] bool. Returns (reward [R], done [R])."""
+        if self.batched:
+            out = self.env.step(action)
+            return out["reward"], out["done"]
+        out = self.env._step({"action": action[0]})
+        return out["reward"].reshape(1).to(torch.float32), out["done"].reshape(1).to(self.device)
+
+    def observation(self, num, sel, agent_index, time):
+        """Observation dict with a leading batch dimension from compact dynamic columns. time: [B] tensor."""
+        B = num.size(0)
+        nf = self.static.unsqueeze(0).repeat(B, 1, 1)
+        nf[..., OBS.NUMBER_OF_AGENT] = num
+        nf[..., OBS.SELECTED_ROAD] = sel
+        return {"node_features": nf, "edge_features": self.edge_features.unsqueeze(0).expand(B, -1, -1),
+                "agent_index": agent_index, "time": time.reshape(B, 1).to(torch.float32)}
+
+
+@torch.no_grad()
+def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode: bool = False,
+            break_when_any_done: bool = False):
+    """`frames` steps of every replica after a reset. Returns a dict of [T, R, ...] tensors (compact observations:
+    NUM, SELECTED_ROAD and head ids per node; the static columns are re-attached when a minibatch is formed)."""
+    adapter.reset()
+    keys = ("num", "sel", "agent_index", "time", "action", "sample_log_prob", "reward", "done", "next_num", "next_sel",
+            "next_agent_index", "next_time")
+    buf = {k: [] for k in keys}
+    num, sel, ai = adapter.dynamic()
+    for _ in range(frames):
+        t = torch.full((adapter.R,), adapter.time(), device=adapter.device)
+        obs = adapter.observation(num, sel, ai, t)
+        act = policy_module(obs, mode=mode)
+        reward, done = adapter.step(act["action"])
+        nnum, nsel, nai = adapter.dynamic()
+        nt = torch.full((adapter.R,), adapter.time(), device=adapter.device)
+        for k, v in zip(keys, (num, sel, ai, t, act["action"], act.get("sample_log_prob", torch.zeros_like(t)), reward,
+                               done, nnum, nsel, nai, nt)):
+            buf[k].append(v)
+        num, sel, ai = nnum, nsel, nai
+        if break_when_any_done and bool(done.any()):
+            break
+    return {k: torch.stack(v) for k, v in buf.items()}
+
+
+def _values(adapter, value_module, batch, prefix=""):
+    T, R = batch["num"].shape[:2]
+    flat = lambda k: batch[prefix + k].reshape(T * R, *batch[prefix + k].shape[2:])
+    obs = adapter.observation(flat("num"), flat("sel"), flat("agent_index"), flat("time"))
+    return value_module(obs).reshape(T, R)
+
+
+def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_batch=32, num_epochs=1,
+              sub_batch_size=32, device=None, checkpoint_path=None, log_dir=None, eval_env=None, eval_interval=0,
+              log_interval=1, stochastic_eval=False, lr=1e-3, seed=0, history=None):
+    """See the module docstring. `total_frames` / `frames_per_batch` count environment steps (each step advances
+    every replica of a BatchedSimulatorEnv); `history` (optional list) receives one dict of scalars per iteration."""
+    adapter = _EnvAdapter(env)
+    eval_adapter = _EnvAdapter(eval_env) if eval_env is not None else None
+    params = [p for p in list(policy_module.parameters()) + list(value_module.parameters()) if p.requires_grad]
+    seen, uniq = set(), []
+    for p in params:
+        if id(p) not in seen:
+            seen.add(id(p)); uniq.append(p)
+    params = uniq
+    optim = torch.optim.Adam(params, lr=lr)
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * rank)
+    writer = None
+    log_file = None
+    if log_dir is not None and rank == 0:
+        os.makedirs(log_dir, exist_ok=True)
+        log_file = open(os.path.join(log_dir, "ppo_log.jsonl"), "a")
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            writer = SummaryWriter(log_dir)
+        except Exception:
+            writer = None
+    global_step = 0
+    n_iters = max(total_frames // frames_per_batch, 1)
+    for it in range(n_iters):
+        t0 = time.perf_counter()
+        batch = collect(adapter, policy_module, frames_per_batch)
+        T, R = batch["reward"].shape
+        global_step += frames_per_batch
+        rollout_s = time.perf_counter() - t0
+        for _ in range(num_epochs):
+            with torch.no_grad():
+                value = _values(adapter, value_module, batch)
+                next_value = _values(adapter, value_module, batch, "next_")
+                adv, target = gae(value, next_value, batch["reward"], batch["done"], batch["done"])
+                adv = standardise(adv)
+            n = min(sub_batch_size, T * R)
+            pick = torch.randperm(T * R, generator=gen)[:n].to(adapter.device)
+            flat = lambda x: x.reshape(T * R, *x.shape[2:])[pick]
+            obs = adapter.observation(flat(batch["num"]), flat(batch["sel"]), flat(batch["agent_index"]), flat(batch["time"]))
+            d = policy_module.dist(obs)
+            log_prob = d.log_prob(flat(batch["action"]))
+            entropy = d.entropy()
+            v = value_module(obs).reshape(n)
+            losses = clip_ppo_loss(log_prob, flat(batch["sample_log_prob"]), flat(adv), entropy, v, flat(target))
+            loss = losses["loss_objective"] + losses["loss_critic"] + losses["loss_entropy"]
+            loss.backward()
+            allreduce_gradients(params)
+            grads = [p.grad for p in params if p.grad is not None]
+            grad_norm = torch.norm(torch.stack([g.norm() for g in grads])) if grads else torch.zeros(())
+            optim.step()
+            optim.zero_grad()
+        rec = {"iteration": it, "global_step": global_step, "frames": T * R, "rollout_s": round(rollout_s, 4),
+               "avg_step_reward": float(batch["reward"].mean()), "episode_return": float(batch["reward"].sum(0).mean()),
+               "loss_total": float(loss.detach()), "grad_global_norm": float(grad_norm),
+               **{k: float(v) for k, v in losses.items()}}
+        if eval_adapter is not None and eval_interval and it % eval_interval == 0:
+            e0 = time.perf_counter()
+            ev = collect(eval_adapter, policy_module, frames_per_batch, mode=True, break_when_any_done=True)
+            rec["eval_return"] = float(ev["reward"].sum(0).mean())
+            rec["eval_episode_len"] = int(ev["reward"].size(0))
+            rec["eval_ms"] = round((time.perf_counter() - e0) * 1e3, 2)
+            if stochastic_eval:
+                ev = collect(eval_adapter, policy_module, frames_per_batch, mode=False, break_when_any_done=True)
+                rec["eval_stochastic_return"] = float(ev["reward"].sum(0).mean())
+        if history is not None:
+            history.append(rec)
+        if rank == 0 and it % max(log_interval, 1) == 0:
+            if log_file is not None:
+                log_file.write(json.dumps(rec) + "\n"); log_file.flush()
+            if writer is not None:
+                for k, v in rec.items():
+                    if isinstance(v, (int, float)) and k not in ("iteration", "global_step"):
+                        writer.add_scalar(f"PPO/{k}", v, global_step)
+    if writer is not None:
+        writer.close()
+    if log_file is not None:
+        log_file.close()
+    if checkpoint_path is not None and rank == 0:
+        torch.save(policy_module.net.state_dict(), checkpoint_path)
+    return history

@@ -165,3 +165,57 @@ def make_workload(name: str, device="cuda", t: float = 21600.0, seed: int = 0, o
     g, Nmax = build_graph(frm, to, n_nodes)
     placed = warm_state(g, Nmax, agents, t, seed)
     return g, Nmax, placed
+
+
+def population(g: Data, n_agents: int, t0: float, spread: int, seed: int = 0, device=None):
+    """agent_features [A+1, 9] for a synthetic network: origin / destination intersections i.i.d.
+    uniform with o != d (as SRC / DEST node ids), integer departure times uniform in [t0, t0+spread), row 0 = the
+    dummy agent that never departs."""
+    N, n_int = int(g.num_roads), int(g.num_intersections)
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    af = torch.zeros(n_agents + 1, 9, dtype=torch.float32)
+    af[0, 2] = 48 * 3600.0
+    o = torch.randint(0, n_int, (n_agents,), generator=gen)
+    d = (o + torch.randint(1, max(n_int, 2), (n_agents,), generator=gen)) % n_int
+    af[1:, 0] = (N + 2 * o).to(torch.float32)
+    af[1:, 1] = (N + 2 * d + 1).to(torch.float32)
+    af[1:, 2] = t0 + torch.randint(0, max(spread, 1), (n_agents,), generator=gen).to(torch.float32)
+    af[1:, 4] = torch.randint(18, 80, (n_agents,), generator=gen).to(torch.float32)
+    return af.to(device if device is not None else g.x.device)
+
+
+def write_scenario(root: str, name: str, kind: str = "grid", args=(5,), n_agents: int = 200, t0: int = 21540,
+                   spread: int = 120, seed: int = 0):
+    """data/<name>/network.xml + population.xml under `root`, in the MATSim dialect the readers accept
+    (src/transportation_simulator.py:61-228, src/agents/base.py:38-242). Intersection ids are zero-padded so that
+    their string order equals their numeric order."""
+    import os
+    frm, to, n_nodes = (grid_links if kind == "grid" else ring_radial_links)(*args)
+    frm, to = reorder_links(frm, to, "node")
+    width = len(str(n_nodes))
+    nid = lambda v: f"{int(v):0{width}d}"
+    side = int(round(n_nodes ** 0.5))
+    d = os.path.join(root, "data", name)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "network.xml"), "w") as f:
+        f.write("<network>\n  <nodes>\n")
+        for v in range(n_nodes):
+            f.write(f'    <node id="{nid(v)}" x="{100.0 * (v % side)}" y="{100.0 * (v // side)}"/>\n')
+        f.write(f'  </nodes>\n  <links effectivecellsize="{CELL}">\n')
+        for i in range(frm.numel()):
+            f.write(f'    <link id="{i}" from="{nid(frm[i])}" to="{nid(to[i])}" length="{LINK_LENGTH}" '
+                    f'capacity="{LINK_CAPACITY}" freespeed="{LINK_FREESPEED}" permlanes="{LINK_LANES}"/>\n')
+        f.write("  </links>\n</network>\n")
+    gen = torch.Generator().manual_seed(seed)
+    with open(os.path.join(d, "population.xml"), "w") as f:
+        f.write("<population>\n")
+        for p in range(n_agents):
+            o = int(torch.randint(0, n_nodes, (1,), generator=gen))
+            dd = (o + int(torch.randint(1, n_nodes, (1,), generator=gen))) % n_nodes
+            dep = t0 + int(torch.randint(0, max(spread, 1), (1,), generator=gen))
+            hh, mm, ss = dep // 3600, (dep % 3600) // 60, dep % 60
+            f.write(f'  <person id="{p}" age="{20 + p % 50}" sex="{"f" if p % 2 else "m"}" car_avail="always">'
+                    f'<plan><act type="h" link="{nid(o)}" end_time="{hh:02d}:{mm:02d}:{ss:02d}"/>'
+                    f'<act type="w" link="{nid(dd)}"/></plan></person>\n')
+        f.write("</population>\n")
+    return d

@@ -110,7 +110,8 @@ class GroupCSR:
 
     by="source_rank": rows are the RANKS of the distinct source ids (GraphDistribution groups, declared divergence D1:
     the reference indexes by raw source id and only works when sources are exactly 0..K-1).
-    by="target": rows are target node ids 0..n_nodes-1 (policy backward)."""
+    by="target": rows are target node ids 0..n_nodes-1 (policy backward, value-net backward).
+    by="source": rows are source node ids 0..n_nodes-1 (value-net aggregation)."""
 
     def __init__(self, edge_index: torch.Tensor, by: str, n_nodes: int | None = None):
         E = edge_index.size(1)
@@ -121,6 +122,9 @@ class GroupCSR:
             other = edge_index[1]
         elif by == "target":
             key, rows, other = edge_index[1].long(), int(n_nodes), edge_index[0]
+            self.nodes = None
+        elif by == "source":
+            key, rows, other = edge_index[0].long(), int(n_nodes), edge_index[1]
             self.nodes = None
         else:
             raise ValueError(by)

@@ -134,3 +134,61 @@ def test_policy_embed_negative_road_index_and_range_error():
     net(nf.cuda(), None, None)
     with pytest.raises(IndexError):
         net.check_errors()
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
+def test_value_net_goldens(tag, golden_dir):
+    """MPNNValueNet (eval mode) against outputs and parameter gradients of the unmodified reference."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNet
+    z = np.load(os.path.join(golden_dir, "mpnn_nets.npz"))
+    g = lambda k: torch.from_numpy(z[k])
+    ei = g(f"value.{tag}.edge_index")
+    nf, ef, ai, tm = (g(f"value.{tag}.{k}").cuda() for k in ("node_features", "edge_features", "agent_index", "time"))
+    N = nf.size(-2)
+    net = MPNNValueNet(ei.cuda(), N, "cuda")
+    names = sorted(k for k, _ in net.named_parameters())
+    assert names == sorted(k[len(f"value.{tag}.param."):] for k in z.files if k.startswith(f"value.{tag}.param."))
+    net.agent_features = g(f"value.{tag}.agent_features").cuda()
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            p.copy_(g(f"value.{tag}.param.{k}"))
+    net.eval()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = net(nf, ef, ai, tm)
+    close(out, g(f"value.{tag}.out"))
+    (out * g(f"value.{tag}.w_out").cuda()).sum().backward()
+    for k, p in net.named_parameters():
+        close(p.grad, g(f"value.{tag}.grad.{k}"), rtol=1e-5, atol=1e-6)
+    net.check_errors()
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(nf, ef, ai, tm)
+
+
+@pytest.mark.parametrize("B", [None, 4])
+def test_value_net_vs_oracle_large(B):
+    """Thousands of nodes, nodes without out-edges, repeated edges: outputs and all gradients vs the oracle port."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNet
+    g = torch.Generator().manual_seed(11 + (B or 0))
+    N, E, A = 3000, 11000, 500
+    src = torch.randint(0, N - 300, (E,), generator=g)           # the last 300 nodes have no out-edge
+    ei = torch.stack([src, torch.randint(0, N, (E,), generator=g)])
+    lead = () if B is None else (B,)
+    nf = torch.rand(*lead, N, 7, generator=g) * 3
+    ef = torch.rand(*lead, E, 1, generator=g)
+    ai = torch.randint(0, A + 1, (*lead, N), generator=g)
+    tm = torch.rand(*lead, 1, generator=g) * 10
+    af = torch.rand(A + 1, 9, generator=g) * 2
+    net = MPNNValueNet(ei.cuda(), N, "cuda")
+    net.agent_features = af.cuda()
+    net.eval()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.named_parameters()}
+    ref = mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+    close(out, ref.detach(), rtol=1e-5, atol=1e-6)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    (out * w.cuda()).sum().backward()
+    for k, v in net.named_parameters():
+        close(v.grad, p[k].grad, rtol=2e-5, atol=2e-6)
