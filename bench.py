@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=8, help="oracle steps timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpnn", action="store_true")
+    ap.add_argument("--mpnn-batch", type=int, default=4, help="batch rows (frames) of the MPNN fwd+bwd measurement")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
     ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel family: 0 ELL (default), 1 CSR")
@@ -290,12 +291,133 @@ def run_native(args):
                       "per-step working set fits in L2 (small workload)"},
            "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clk.summary()}
 
+    if not args.no_mpnn:
+        out["mpnn"] = mpnn_bench(args, g, dev, world, rank, peak)
+        out["gpu_launches"] += out["mpnn"].pop("_launches_in_headline", 0)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
+        if "mpnn" in out:
+            out["mpnn"]["cpu_baseline"] = mpnn_cpu_baseline(args)
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def mpnn_bench(args, g, dev, world, rank, peak):
+    """Second half of BASELINE.json's metric: MPNN fwd+bwd edges/s on the FULL graph of the same workload (links +
+    SRC/DEST nodes): policy logits -> GraphDistribution log_prob + entropy -> PPO-style loss -> backward to the
+    embedding gradient; and, reported separately, MPNNValueNet forward + backward. Timed with CUDA events on the
+    current stream, max over ranks; every rank works on its own copy (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    from tarl_simulator_b200.distribution import GraphDistribution
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNet
+
+    B = args.mpnn_batch
+    ei = g.edge_index
+    E_full, N_tot = ei.size(1), g.x.size(0)
+    Nmax = (g.x.size(1) - 7) // 3
+    nf = g.x[:, 3 * Nmax:].unsqueeze(0).repeat(B, 1, 1).contiguous()
+    policy = MPNNPolicyNet(ei, N_tot, None, str(dev)) if N_tot > 4096 else MPNNPolicyNet(ei, N_tot, torch.ones(E_full, device=dev), str(dev))
+    gen = torch.Generator(device=dev).manual_seed(5 + rank)
+    with torch.no_grad():
+        d0 = GraphDistribution(policy(nf, None, None), ei)
+        action = d0.sample(uniforms=torch.rand(B, d0.nb_nodes, device=dev, generator=gen)).to(torch.bool)
+    adv = torch.randn(B, device=dev, generator=gen)
+    stream = torch.cuda.current_stream(dev)
+
+    def policy_iter():
+        policy.nodes_embedding.weight.grad = None
+        dd = GraphDistribution(policy(nf, None, None), ei)
+        lp = dd.log_prob(action)
+        ent = dd.entropy()
+        (-(lp * adv).mean() - 0.01 * ent.mean()).backward()
+
+    value = MPNNValueNet(ei, N_tot, str(dev))
+    value.agent_features = torch.rand(1024, 9, device=dev, generator=gen)
+    value.eval()
+    ef = g.edge_attr.reshape(1, E_full, 1).repeat(B, 1, 1).contiguous()
+    ai = torch.randint(0, 1024, (B, N_tot), device=dev, generator=gen)
+    tm = torch.full((B, 1), 21600.0, device=dev)
+    wv = torch.randn(B, 1, device=dev, generator=gen)
+
+    def value_iter():
+        for p_ in value.parameters():
+            p_.grad = None
+        (value(nf, ef, ai, tm) * wv).sum().backward()
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms / iters
+
+    iters = max(min(args.steps // 10, 50), 5)
+    pol_ms = timed(policy_iter, iters)
+    val_ms = timed(value_iter, iters)
+    # algorithmic bytes per edge (SURVEY.md §8d): policy 28 B + GraphDistribution 24 B = 52 B/edge (+4 B/node)
+    pol_bytes = B * (52 * E_full + 4 * N_tot)
+    val_bytes = B * (2 * (12 * E_full) + 2 * 68 * N_tot)          # fwd + bwd: 12 B/edge + 68 B/node each
+    return {"metric": "MPNN fwd+bwd edges/s", "unit": "edges/s", "batch_rows": B, "edges_full_graph": E_full,
+            "nodes_full_graph": N_tot, "iters": iters,
+            "policy_distribution": {"value": round(world * B * E_full / (pol_ms / 1e3), 1), "ms_per_iter": round(pol_ms, 4),
+                                    "what": "MPNNPolicyNet.forward -> GraphDistribution.log_prob + entropy -> backward (7 kernels)",
+                                    "roofline": {"bound": "hbm", "algorithmic_bytes": int(pol_bytes),
+                                                 "achieved": round(pol_bytes / (pol_ms / 1e3) / 1e9, 1), "peak": peak,
+                                                 "unit": "GB/s", "frac": round(pol_bytes / (pol_ms / 1e3) / 1e9 / peak, 4)}},
+            "value_net": {"value": round(world * B * E_full / (val_ms / 1e3), 1), "ms_per_iter": round(val_ms, 4),
+                          "what": "MPNNValueNet.forward (eval) -> backward (project, aggregate, node_grad, edge_grad, finish)",
+                          "roofline": {"bound": "hbm", "algorithmic_bytes": int(val_bytes),
+                                       "achieved": round(val_bytes / (val_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                                       "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}}}
+
+
+def mpnn_cpu_baseline(args):
+    """The oracle port of the same policy -> distribution -> backward iteration on the host cores, on a bounded
+    sample: one batch row of the full graph of the workload."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mpnn_port
+    from tarl_simulator_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g, Nmax, _ = synthetic.make_workload(args.workload, device="cpu", t=T0, seed=0, order=args.link_order)
+    ei = g.edge_index
+    E_full, N_tot = ei.size(1), g.x.size(0)
+    nf = g.x[:, 3 * Nmax:].contiguous()
+    w = torch.randn(N_tot, 1, requires_grad=True)
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    action = None
+    for it in range(3):
+        a = time.perf_counter()
+        w.grad = None
+        d = mpnn_port.GraphDistributionPort(mpnn_port.policy_logits(w, nf, ei), ei, 1.0)
+        if action is None:
+            action = d.sample(torch.rand(d.K, generator=gen))
+            a = time.perf_counter()
+        lp, ent = d.log_prob(action), d.entropy()
+        (-(lp.mean()) - 0.01 * ent.mean()).backward()
+        times.append(time.perf_counter() - a)
+    med = statistics.median(times[1:])
+    return {"value": round(E_full / med, 1), "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"2 iterations, 1 batch row of the full {args.workload} graph ({E_full} edges), oracle/mpnn_port.py",
+            "ms_per_iter": round(med * 1e3, 1)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
