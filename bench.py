@@ -186,14 +186,19 @@ def run_native(args):
         torch.cuda.synchronize(dev)
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step()
+
+    def run(n):     # n steps enqueued by one library call (tarl_store_run), routing decisions cycled from the bank
+        bank = [sel_bank[(state["i"] + k) % len(sel_bank)] for k in range(len(sel_bank))]
+        store.run(state["t"], n, dt=1.0, sel_bank=bank, delta_tt=delta_tt, variant=args.variant)
+        state["t"] += float(n)
+        state["i"] += n
+
+    run(warm)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local, period=0.005) as clk:
         ev0.record(stream)
-        for _ in range(args.steps):
-            step()
+        run(args.steps)
         ev1.record(stream)
         torch.cuda.synchronize(dev)
     barrier()

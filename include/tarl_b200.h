@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 3
+#define TARL_ABI_VERSION 4
 
 /* return codes */
 #define TARL_OK 0
@@ -134,7 +134,10 @@ typedef struct tarl_link_store {
     void* stat_a;       /* [N] 16-byte {FFTT, congestion_constant, ROAD_INDEX, MAXN}                     */
     void* stat_b;       /* [N] 16-byte {LENGTH, MAX_FLOW, 0, 0} (export only)                            */
     void* queue;        /* [R*N*(nmax-1)] 16-byte ring slots {agent id, arrival, exit, pad}              */
-    void* post;         /* [R*N] 16-byte scratch {NUM, tail id, head id, delta_tt} between the two phases */
+    void* post;         /* [R*N] 8-byte scratch {NUM, tail id} handed from the direction to the response phase */
+    void* pop_hint;     /* [R*N] bytes, zeroed ONCE by the caller: set by the direction phase on the upstream link
+                           whose head was admitted, consumed (and cleared) by the response phase to fetch the ring
+                           slots of a pop one dependent load earlier                                            */
 } tarl_link_store;
 
 /* x -> store. x element (r, n, c) at x[r*x_replica_stride + n*x_row_stride + c]; cc = congestion_constant[:N] or
@@ -167,6 +170,16 @@ typedef struct tarl_dual_ell {
 int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
                     const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
                     float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask);
+
+/* n_steps consecutive steps enqueued by one call (times t0, t0+dt, ...; in-kernel noise; step ids first_step_id, +1,
+ * ...): the loop SimulatorEnv.rollout / TransportationSimulator.run drive from Python, without a host round trip per
+ * step. sel_bank: NULL/0 (SELECTED_ROAD stays as it is) or n_bank device arrays [R*N] cycled through as the routing
+ * decisions of successive steps. hot_cur / hot_next alternate internally: after an odd n_steps the caller's two
+ * buffers have swapped roles. delta_tt / pop hold the LAST step's outputs. */
+int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                   const float* attr_in, uint64_t seed, uint32_t first_step_id, float t0, float dt, int32_t n_steps,
+                   const float* const* sel_bank, int32_t n_bank, float* delta_tt, uint8_t* pop, int32_t* flags,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).

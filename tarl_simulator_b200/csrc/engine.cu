@@ -104,8 +104,26 @@ __device__ __forceinline__ float gumbel_score(float p, float u) {     // src/dir
 
 struct Pick {
     float psum, id;
+    int src;          // store index (replica*N + link) of the upstream link whose head was picked
     bool have;
 };
+
+// Uniforms inside [kSafeULo, kSafeUHi] give Gumbel noise in [-2.82, 16.64]; then an edge with p = 0 (score
+// log(1e-12) + g <= -10.98) can never beat an edge with p >= kSafeAttr (score >= log(1e-3) - 2.82 = -9.73), and any
+// such score beats the lowest() start value: the arg-max of src/direction_mpnn.py:136-139 over ALL in-edges equals the
+// arg-max over the ELIGIBLE ones (strict '>' in ascending edge id either way), so ineligible edges need no logf and a
+// lone eligible edge needs no noise at all. Outside these bounds the literal scan over every in-edge runs.
+// The in-kernel Philox stream only produces uniforms inside the interval.
+constexpr float kSafeULo = 5.9604645e-08f, kSafeUHi = 0.99999994f, kSafeAttr = 1e-3f;
+
+__device__ __forceinline__ float philox_uniform(const Noise& nz, int L, int j, float (&un)[4], int& have_group) {
+    if (have_group != (j >> 2)) {
+        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+        have_group = j >> 2;
+    }
+    const int jj = j & 3;
+    return jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
+}
 
 // The whole in-edge scan of link d out of the CSR, in ascending original edge id: probability sum, then — only where it
 // is positive (src/direction_mpnn.py:142-144) — the Gumbel arg-max with strict '>' (lowest edge id wins ties).
@@ -115,36 +133,47 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
                                                float ridx_d) {
     const int base = L - d;
     const int k0 = g.in_ptr[d], k1 = g.in_ptr[d + 1];
-    Pick out = {0.0f, 0.0f, false};
+    Pick out = {0.0f, 0.0f, -1, false};
+    int n_elig = 0, lone = -1;
+    bool safe = true;
     for (int k = k0; k < k1; ++k) {
         const int Lu = base + g.in_src[k];
-        out.psum += edge_prob(s.hot_cur[2 * Lu], s.sel[Lu], t, free_d, room_d, ridx_d, attr_in[k]);
+        const float a = attr_in[k];
+        const float p = edge_prob(s.hot_cur[2 * Lu], s.sel[Lu], t, free_d, room_d, ridx_d, a);
+        out.psum += p;
+        if (p > 0.0f) { ++n_elig; lone = k; safe = safe && (a >= kSafeAttr); }
+        if (kExtNoise) {
+            const float uu = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k]];
+            safe = safe && (uu >= kSafeULo) && (uu <= kSafeUHi);
+        }
     }
     if (!(out.psum > 0.0f)) return out;
+    if (safe && n_elig == 1) {
+        const int Lu = base + g.in_src[lone];
+        out.id = s.hot_cur[2 * Lu].x; out.src = Lu; out.have = true;
+        return out;
+    }
     float best = -FLT_MAX;
     float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    int grp = -1;
     for (int k = k0; k < k1; ++k) {
-        const int j = k - k0;
         const int Lu = base + g.in_src[k];
         const float4 U = s.hot_cur[2 * Lu];
         const float p = edge_prob(U, s.sel[Lu], t, free_d, room_d, ridx_d, attr_in[k]);
-        float uu;
-        if (kExtNoise) {
-            uu = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k]];
-        } else {
-            if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
-            const int jj = j & 3;
-            uu = jj == 0 ? un[0] : (jj == 1 ? un[1] : (jj == 2 ? un[2] : un[3]));
-        }
+        if (safe && !(p > 0.0f)) continue;
+        const float uu = kExtNoise ? nz.ext[(int64_t)r * g.n_edges + g.in_eid[k]] : philox_uniform(nz, L, k - k0, un, grp);
         const float sc = gumbel_score(p, uu);
-        if (sc > best) { best = sc; out.id = U.x; out.have = true; }
+        if (sc > best) { best = sc; out.id = U.x; out.src = Lu; out.have = true; }
     }
     return out;
 }
 
-// Tail append on the link's own record (src/direction_mpnn.py:171-195, on EVERY link) and the post summary.
-__device__ __forceinline__ void append_and_publish(const Store& s, int L, float4 hA, float4 hB, const float4 st,
-                                                   const Pick pk, float t, int32_t* __restrict__ flags) {
+// Tail append on the link's own record (src/direction_mpnn.py:171-195, on EVERY link), the {NUM, tail id} summary the
+// response phase gathers, delta_travel_time for the link's out-edges (:94-96, from the PRE-step head), and the pop hint
+// for the upstream link whose head was admitted here.
+__device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const Store& s, int r, int n, int L, float4 hA,
+                                                   float4 hB, const float4 st, const Pick pk, float t,
+                                                   float* __restrict__ delta_tt, int32_t* __restrict__ flags) {
     const float num = hA.z, maxn = hA.w, fftt = st.x;
     int meta = __float_as_int(hB.w);
     const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
@@ -153,8 +182,13 @@ __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4
         if (!pk.have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
         else chosen = pk.id;
     }
-    const float dtt = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);      // :94-95, pre-step head
-    float num_post = num, tail_post = hB.y, head_post = hA.x;
+    if (delta_tt != nullptr) {
+        const float dtt = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);
+        float* out = delta_tt + (int64_t)r * g.n_edges;
+        const int k1 = g.out_ptr[n + 1];
+        for (int k = g.out_ptr[n]; k < k1; ++k) out[g.out_eid != nullptr ? g.out_eid[k] : k] = dtt;
+    }
+    float num_post = num, tail_post = hB.y;
     if (bad) {
         atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
     } else {
@@ -162,7 +196,6 @@ __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4
         const float dep_new = t + max_propagate_nan(fftt, st.y / ((maxn + 10.0f) - num));
         if (q == 0) {                       // the tail slot IS the head slot
             hA.x = chosen; hB.x = t; hA.y = dep_new;
-            head_post = chosen;
             tail_post = chosen;
             meta &= ~kMetaGarbage;
             if (chosen != 0.0f) { num_post = num + 1.0f; hB.y = chosen; }
@@ -177,16 +210,18 @@ __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4
             hB.z = dep_new;
         }
         hA.z = num_post;
+        if (chosen != 0.0f && pk.src >= 0) s.hint[pk.src] = 1;     // that link's head just moved here: it will pop
     }
     hB.w = __int_as_float(meta);
     s.hot_next[2 * (size_t)L] = hA;
     s.hot_next[2 * (size_t)L + 1] = hB;
-    s.post[L] = make_float4(num_post, tail_post, head_post, dtt);
+    s.post[L] = make_float2(num_post, tail_post);
 }
 
 template <bool kExtNoise>
 __global__ void __launch_bounds__(kThreads) k_csr_select_append(tarl_dual_csr g, Store s,
                                                                 const float* __restrict__ attr_in, Noise nz, float t,
+                                                                float* __restrict__ delta_tt,
                                                                 int32_t* __restrict__ flags) {
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
@@ -195,12 +230,13 @@ __global__ void __launch_bounds__(kThreads) k_csr_select_append(tarl_dual_csr g,
     const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
     const float4 st = s.stat_a[d];
     const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
-    append_and_publish(s, L, hA, hB, st, pk, t, flags);
+    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, flags);
 }
 
 template <int W, bool kExtNoise>
 __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g, tarl_dual_ell ell, Store s,
                                                                 const float* __restrict__ attr_in, Noise nz, float t,
+                                                                float* __restrict__ delta_tt,
                                                                 int32_t* __restrict__ flags) {
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
@@ -219,7 +255,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
     }
     const bool free_d = hA.z < (hA.w - 3.0f);
     const float room_d = hA.w - hA.z, ridx_d = st.z;
-    Pick pk = {0.0f, 0.0f, false};
+    Pick pk = {0.0f, 0.0f, -1, false};
     if (u[W - 1] == -2) {     // more than W in-edges: this link walks its CSR segment instead
         pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, free_d, room_d, ridx_d);
     } else {
@@ -234,42 +270,60 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
             }
         }
         float p[W];
+        int n_elig = 0, lone = 0;
+        bool safe = true;
 #pragma unroll
         for (int j = 0; j < W; ++j) {
             p[j] = 0.0f;
             if (u[j] >= 0) {
                 p[j] = edge_prob(U[j], S[j], t, free_d, room_d, ridx_d, a[j]);
                 pk.psum += p[j];
+                if (p[j] > 0.0f) { ++n_elig; lone = j; safe = safe && (a[j] >= kSafeAttr); }
             }
         }
         if (pk.psum > 0.0f) {
-            float best = -FLT_MAX;
-            float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-            const int k0 = kExtNoise ? g.in_ptr[d] : 0;
+            float uu[W];
+            if (kExtNoise) {
+                const int k0 = g.in_ptr[d];
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
-                if (u[j] >= 0) {
-                    float uu;
-                    if (kExtNoise) {
-                        uu = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k0 + j]];
-                    } else {
-                        if ((j & 3) == 0) philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
-                        uu = un[j & 3];
+                for (int j = 0; j < W; ++j) {
+                    uu[j] = 0.5f;
+                    if (u[j] >= 0) {
+                        uu[j] = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k0 + j]];
+                        safe = safe && (uu[j] >= kSafeULo) && (uu[j] <= kSafeUHi);
                     }
-                    const float sc = gumbel_score(p[j], uu);
-                    if (sc > best) { best = sc; pk.id = U[j].x; pk.have = true; }
+                }
+            }
+            if (safe && n_elig == 1) {
+#pragma unroll
+                for (int j = 0; j < W; ++j)
+                    if (j == lone) { pk.id = U[j].x; pk.src = base + u[j]; }
+                pk.have = true;
+            } else {
+                float best = -FLT_MAX;
+                float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    if (!kExtNoise && (j & 3) == 0)
+                        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+                    if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
+                        const float v = kExtNoise ? uu[j] : un[j & 3];
+                        const float sc = gumbel_score(p[j], v);
+                        if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
+                    }
                 }
             }
         }
     }
-    append_and_publish(s, L, hA, hB, st, pk, t, flags);
+    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, flags);
 }
 
 // ------------------------------------------------------------------------------------------------ response phase
 // The pop itself (src/response_mpnn.py:119-122) as a ring-head increment: new head <- logical slot 1, and the slot that
 // becomes logical Nmax-1 <- old logical Nmax-1 (the reference's shift leaves the last slot in place, i.e. duplicates it).
-__device__ __forceinline__ void pop_head(const Store& s, int L, float4 hB, float t) {
-    const float4 hA = s.hot_next[2 * (size_t)L];
+// `have` says q_head / q_last were fetched ahead of time (hinted links).
+__device__ __forceinline__ void pop_head(const Store& s, int L, float4 hA, float4 hB, float t, bool have, float4 q_head,
+                                         float4 q_last) {
     int meta = __float_as_int(hB.w);
     const int rh = meta & kMetaRingMask;
     const int M = s.M;
@@ -277,10 +331,13 @@ __device__ __forceinline__ void pop_head(const Store& s, int L, float4 hB, float
     const bool gv = meta & kMetaGarbage;
     const float4 garbage = make_float4(0.0f, t, hB.z, 0.0f);    // pending garbage was (re)written this very step
     float4* Q = s.queue + (size_t)L * M;
-    const float4 new_head = (gv && q == 1) ? garbage : Q[rh];
+    if (!have) {
+        q_head = Q[rh];
+        if (M > 1) q_last = Q[ring_pos(rh, M, M)];
+    }
+    const float4 new_head = (gv && q == 1) ? garbage : q_head;
     if (M > 1) {
-        const float4 last = (gv && q == M) ? garbage : Q[ring_pos(rh, M, M)];
-        Q[rh] = last;                                           // becomes logical slot M after the increment
+        Q[rh] = (gv && q == M) ? garbage : q_last;              // becomes logical slot M after the increment
     } else if (gv && q == 1) {
         Q[rh] = garbage;                                        // Nmax == 2: slot 1 keeps (a copy of) its value
     }
@@ -291,79 +348,76 @@ __device__ __forceinline__ void pop_head(const Store& s, int L, float4 hB, float
     s.hot_next[2 * (size_t)L + 1] = make_float4(new_head.y, hB.y, hB.z, __int_as_float(meta));
 }
 
-__device__ __forceinline__ bool accepts(const float4 P, const float4 D) {     // src/response_mpnn.py:66-83
-    return at_least_one(P.x) && at_least_one(D.x) && same_id(D.y, P.z);
+// src/response_mpnn.py:66-83: NUM_up > 0, NUM_dn > 0, tail(dn) == head(up). A = own post-append record, D = {NUM, tail}
+__device__ __forceinline__ bool accepts(const float4 A, const float2 D) {
+    return at_least_one(A.z) && at_least_one(D.x) && same_id(D.y, A.x);
 }
 
-__device__ __noinline__ bool scan_out_edges_csr(const tarl_dual_csr& g, const Store& s, int base, int u, const float4 P,
-                                                float* __restrict__ dtt_out) {
+__device__ __noinline__ bool scan_out_edges_csr(const tarl_dual_csr& g, const Store& s, int base, int u, const float4 A) {
     bool accept = false;
     const int k1 = g.out_ptr[u + 1];
-    for (int k = g.out_ptr[u]; k < k1; ++k) {
-        if (dtt_out != nullptr) dtt_out[g.out_eid != nullptr ? g.out_eid[k] : k] = P.w;
-        accept = accept || accepts(P, s.post[base + g.out_dst[k]]);
-    }
+    for (int k = g.out_ptr[u]; k < k1; ++k) accept = accept || accepts(A, s.post[base + g.out_dst[k]]);
     return accept;
 }
 
 __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, Store s, float t,
-                                                              float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
-                                                              int32_t* __restrict__ flags) {
+                                                              uint8_t* __restrict__ pop, int32_t* __restrict__ flags) {
     const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + u;
     bool accept = false;
-    float4 P = make_float4(0.f, 0.f, 0.f, 0.f), hB = P;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     if (u < s.N) {
-        P = s.post[L];
-        if (at_least_one(P.x)) hB = s.hot_next[2 * (size_t)L + 1];
-        accept = scan_out_edges_csr(g, s, base, u, P, delta_tt != nullptr ? delta_tt + (int64_t)r * g.n_edges : nullptr);
+        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
+        if (s.hint[L]) s.hint[L] = 0;
+        accept = scan_out_edges_csr(g, s, base, u, A);
         pop[L] = accept ? 1 : 0;
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
-    if (accept) pop_head(s, L, hB, t);
+    if (accept) pop_head(s, L, A, B, t, false, A, A);
 }
 
 template <int W>
 __global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
-                                                              float* __restrict__ delta_tt, uint8_t* __restrict__ pop,
-                                                              int32_t* __restrict__ flags) {
+                                                              uint8_t* __restrict__ pop, int32_t* __restrict__ flags) {
     const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + u;
-    bool accept = false;
-    float4 P = make_float4(0.f, 0.f, 0.f, 0.f), hB = P;
+    bool accept = false, hinted = false, fetched = false;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
     if (u < s.N) {
-        // level 1
-        P = s.post[L];
+        // level 1: own post-append record, out-neighbour ids, and whether a downstream link admitted this link's head
+        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
         int dn[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) dn[j] = ell.out_dst[(size_t)j * ell.pitch + u];
-        float* dtt_out = delta_tt != nullptr ? delta_tt + (int64_t)r * g.n_edges : nullptr;
-        const int k0 = (dtt_out != nullptr) ? g.out_ptr[u] : 0;
-        // level 2
-        if (at_least_one(P.x)) hB = s.hot_next[2 * (size_t)L + 1];   // a link with agents may pop: fetch early
+        hinted = s.hint[L] != 0;
+        // level 2: the neighbours' summaries and, for hinted links, the two ring slots a pop needs
         if (dn[W - 1] == -2) {
-            accept = scan_out_edges_csr(g, s, base, u, P, dtt_out);
+            accept = scan_out_edges_csr(g, s, base, u, A);
         } else {
-            float4 D[W];
+            float2 D[W];
 #pragma unroll
             for (int j = 0; j < W; ++j)
                 if (dn[j] >= 0) D[j] = s.post[base + dn[j]];
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                if (dn[j] >= 0) {
-                    if (dtt_out != nullptr) dtt_out[g.out_eid != nullptr ? g.out_eid[k0 + j] : k0 + j] = P.w;
-                    accept = accept || accepts(P, D[j]);
-                }
+            if (hinted) {
+                const int rh = __float_as_int(B.w) & kMetaRingMask;
+                const float4* Q = s.queue + (size_t)L * s.M;
+                q_head = Q[rh];
+                if (s.M > 1) q_last = Q[ring_pos(rh, s.M, s.M)];
+                fetched = true;
             }
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (dn[j] >= 0) accept = accept || accepts(A, D[j]);
         }
+        if (hinted) s.hint[L] = 0;
         pop[L] = accept ? 1 : 0;
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
-    if (accept) pop_head(s, L, hB, t);
+    if (accept) pop_head(s, L, A, B, t, fetched, q_head, q_last);
 }
 
 inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
@@ -376,7 +430,8 @@ namespace tarl {
 int make_store(const tarl_link_store* p, Store* s) {
     if (p == nullptr || p->n_links < 0 || p->n_replicas < 1 || p->nmax < 2 || p->nmax - 1 > kMetaRingMask) return TARL_E_BADARG;
     if (p->n_replicas > 65535 || (int64_t)p->n_links * p->n_replicas * 2 >= INT32_MAX) return TARL_E_BADARG;
-    if (p->n_links > 0 && (!p->hot_cur || !p->hot_next || !p->sel || !p->stat_a || !p->stat_b || !p->queue || !p->post))
+    if (p->n_links > 0 && (!p->hot_cur || !p->hot_next || !p->sel || !p->stat_a || !p->stat_b || !p->queue || !p->post ||
+                           !p->pop_hint))
         return TARL_E_BADARG;
     s->N = p->n_links; s->R = p->n_replicas; s->Nmax = p->nmax; s->M = p->nmax - 1;
     s->hot_cur = static_cast<const float4*>(p->hot_cur);
@@ -385,7 +440,8 @@ int make_store(const tarl_link_store* p, Store* s) {
     s->stat_a = static_cast<const float4*>(p->stat_a);
     s->stat_b = static_cast<const float4*>(p->stat_b);
     s->queue = static_cast<float4*>(p->queue);
-    s->post = static_cast<float4*>(p->post);
+    s->post = static_cast<float2*>(p->post);
+    s->hint = static_cast<uint8_t*>(p->pop_hint);
     return TARL_OK;
 }
 
@@ -418,12 +474,10 @@ int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stri
     return launch_status();
 }
 
-int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
-                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask) {
-    Store s;
-    int rc = make_store(store, &s);
-    if (rc != TARL_OK) return rc;
+namespace {
+
+int check_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s, const float* attr_in,
+               const float* noise, const uint8_t* pop, const int32_t* flags) {
     if (g == nullptr || flags == nullptr || g->n_links != s.N) return TARL_E_BADARG;
     if (s.N == 0) return TARL_OK;
     if (pop == nullptr || g->in_ptr == nullptr || g->out_ptr == nullptr) return TARL_E_BADARG;
@@ -433,25 +487,67 @@ int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl
         if ((ell->width != 4 && ell->width != 8) || ell->pitch < s.N) return TARL_E_BADARG;
         if (!ell->in_src || !ell->in_attr || !ell->out_dst) return TARL_E_BADARG;
     }
-    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    return TARL_OK;
+}
+
+void launch_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s, const float* attr_in,
+                 const Noise& nz, float t, float* delta_tt, uint8_t* pop, int32_t* flags, cudaStream_t cs,
+                 uint32_t phase_mask) {
     const dim3 grid(blocks_for(s.N), s.R);
-    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
+    const bool ext = nz.ext != nullptr;
     if (phase_mask & TARL_PHASE_SELECT_APPEND) {
         if (ell == nullptr) {
-            if (noise) k_csr_select_append<true><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, flags);
-            else k_csr_select_append<false><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, flags);
+            if (ext) k_csr_select_append<true><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, delta_tt, flags);
+            else k_csr_select_append<false><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, delta_tt, flags);
         } else if (ell->width == 4) {
-            if (noise) k_ell_select_append<4, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
-            else k_ell_select_append<4, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+            if (ext) k_ell_select_append<4, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            else k_ell_select_append<4, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
         } else {
-            if (noise) k_ell_select_append<8, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
-            else k_ell_select_append<8, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, flags);
+            if (ext) k_ell_select_append<8, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            else k_ell_select_append<8, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
         }
     }
     if (phase_mask & TARL_PHASE_RESPOND_SHIFT) {
-        if (ell == nullptr) k_csr_respond_pop<<<grid, kThreads, 0, cs>>>(*g, s, t, delta_tt, pop, flags);
-        else if (ell->width == 4) k_ell_respond_pop<4><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, delta_tt, pop, flags);
-        else k_ell_respond_pop<8><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, delta_tt, pop, flags);
+        if (ell == nullptr) k_csr_respond_pop<<<grid, kThreads, 0, cs>>>(*g, s, t, pop, flags);
+        else if (ell->width == 4) k_ell_respond_pop<4><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, pop, flags);
+        else k_ell_respond_pop<8><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, pop, flags);
+    }
+}
+
+}  // namespace
+
+int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
+                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask) {
+    Store s;
+    int rc = make_store(store, &s);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, noise, pop, flags)) != TARL_OK) return rc;
+    if (s.N == 0) return TARL_OK;
+    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
+    launch_step(g, ell, s, attr_in, nz, t, delta_tt, pop, flags, static_cast<cudaStream_t>(stream), phase_mask);
+    return launch_status();
+}
+
+int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                   const float* attr_in, uint64_t seed, uint32_t first_step_id, float t0, float dt, int32_t n_steps,
+                   const float* const* sel_bank, int32_t n_bank, float* delta_tt, uint8_t* pop, int32_t* flags,
+                   void* stream) {
+    Store s;
+    int rc = make_store(store, &s);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, nullptr, pop, flags)) != TARL_OK) return rc;
+    if (n_steps < 0 || n_bank < 0 || (n_bank > 0 && sel_bank == nullptr)) return TARL_E_BADARG;
+    if (s.N == 0) return TARL_OK;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < n_steps; ++i) {
+        if (n_bank > 0) s.sel = const_cast<float*>(sel_bank[i % n_bank]);
+        const Noise nz = {nullptr, (uint32_t)seed, (uint32_t)(seed >> 32), first_step_id + (uint32_t)i};
+        launch_step(g, ell, s, attr_in, nz, t0 + dt * (float)i, delta_tt, pop, flags, cs,
+                    TARL_PHASE_SELECT_APPEND | TARL_PHASE_RESPOND_SHIFT);
+        float4* written = s.hot_next;                       // ping-pong: what this step wrote is the next step's input
+        s.hot_next = const_cast<float4*>(s.hot_cur);
+        s.hot_cur = written;
     }
     return launch_status();
 }

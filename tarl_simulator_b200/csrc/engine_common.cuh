@@ -17,7 +17,7 @@ __device__ __forceinline__ float max_propagate_nan(float a, float b) {
     return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
 }
 
-// Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields four uniforms in (0,1).
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one call yields four uniforms in [2^-24, 1 - 2^-24].
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, float out[4]) {
 #pragma unroll
@@ -29,7 +29,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     const uint32_t c[4] = {c0, c1, c2, c3};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = ((float)(c[i] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    for (int i = 0; i < 4; ++i) out[i] = ((float)(c[i] >> 9) + 0.5f) * (1.0f / 8388608.0f);   // exact: in [2^-24, 1-2^-24]
 }
 
 // Device view of struct tarl_link_store. One 32-byte record per (replica, link), two float4 halves:
@@ -44,7 +44,8 @@ struct Store {
     const float4* stat_a;    // [N] {FFTT, cc, ROAD_INDEX, MAXN}
     const float4* stat_b;    // [N] {LENGTH, MAX_FLOW, 0, 0}
     float4* queue;           // [R*N*M]
-    float4* post;            // [R*N]
+    float2* post;            // [R*N] {NUM, tail id} after the direction phase
+    uint8_t* hint;           // [R*N] 1 = a downstream link admitted this link's head in the direction phase
 };
 
 __device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logical slot 1..M -> physical 0..M-1

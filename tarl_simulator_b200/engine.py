@@ -38,7 +38,8 @@ class LinkStore:
         self.stat_a = torch.zeros(max(self.N, 1), 4, **f32)
         self.stat_b = torch.zeros(max(self.N, 1), 4, **f32)
         self.queue = torch.zeros(max(L * self.M, 1), 4, **f32)
-        self.post = torch.zeros(max(L, 1), 4, **f32)
+        self.post = torch.zeros(max(L, 1), 2, **f32)
+        self.hint = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
         self.pop = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
         self.flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
         self.seed, self.step_id = int(seed), 0
@@ -51,7 +52,7 @@ class LinkStore:
         s.n_links, s.n_replicas, s.nmax, s.reserved = self.N, self.R, self.Nmax, 0
         s.hot_cur, s.hot_next = self.hot[self.cur].data_ptr(), self.hot[self.cur ^ 1].data_ptr()
         s.sel, s.stat_a, s.stat_b = self.sel.data_ptr(), self.stat_a.data_ptr(), self.stat_b.data_ptr()
-        s.queue, s.post = self.queue.data_ptr(), self.post.data_ptr()
+        s.queue, s.post, s.pop_hint = self.queue.data_ptr(), self.post.data_ptr(), self.hint.data_ptr()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -132,6 +133,34 @@ class LinkStore:
             self.cur ^= 1
             self.step_id += 1
             self.t_last = float(t)
+        return self.pop[: self.N * self.R].view(self.R, self.N)
+
+    def run(self, t0: float, n_steps: int, dt: float = 1.0, sel_bank=None, delta_tt: torch.Tensor | None = None,
+            variant: int = VARIANT_ELL):
+        """`n_steps` consecutive core steps enqueued by ONE call into the library (tarl_store_run; in-kernel noise).
+        sel_bank: optional list of fp32 [R*N] device tensors cycled through as successive steps' SELECTED_ROAD."""
+        ptrs = None
+        nb = 0
+        if sel_bank:
+            nb = len(sel_bank)
+            for b in sel_bank:
+                if b.dtype != torch.float32 or b.numel() != self.R * self.N or not b.is_contiguous() or b.device != self.device:
+                    raise ValueError("sel_bank entries must be contiguous fp32 [R*N] tensors on the store's device")
+            ptrs = (C.c_void_p * nb)(*[b.data_ptr() for b in sel_bank])
+        self._fill_struct()
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_run(
+                self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
+                self.attr_in.data_ptr(), self.seed, self.step_id, float(t0), float(dt), int(n_steps), ptrs, nb,
+                delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
+                self._stream())
+        _cabi.check(rc, "tarl_store_run")
+        if n_steps > 0:
+            self.cur ^= n_steps & 1
+            self.step_id += n_steps
+            self.t_last = float(t0) + float(dt) * (n_steps - 1)
+            if sel_bank:
+                self.sel = sel_bank[(n_steps - 1) % nb]
         return self.pop[: self.N * self.R].view(self.R, self.N)
 
     def clear_queues(self):

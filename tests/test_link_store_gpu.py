@@ -125,3 +125,67 @@ def test_store_philox_stream_is_deterministic_and_seeded():
     assert not torch.equal(outs[0], outs[2])
     c = core_port.Cols(Nmax)
     assert float((outs[0][:, c.NUM] - x0[:, c.NUM]).abs().sum()) > 0      # agents did move
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mode", ["tiny_attr", "extreme_noise"])
+def test_store_literal_scan_outside_the_safe_bounds(mode, variant):
+    """Edge weights below 1e-3 or uniforms outside [2^-24, 1-2^-24] switch the direction phase from the
+    eligible-edges-only arg-max to the literal scan over every in-edge; both must agree with the oracle (a tiny
+    weight lets an INELIGIBLE edge win the Gumbel arg-max, exactly as in src/direction_mpnn.py:136-144)."""
+    g = torch.Generator().manual_seed(77)
+    N, Nmax = 3000, 15
+    ei, w = cases.random_dual_graph(g, N, 4)
+    if mode == "tiny_attr":
+        w = w * torch.where(torch.rand(w.shape, generator=g) < 0.5, 1e-9, 1.0)
+    x0, _ = cases.random_road_state(g, N, Nmax, 500.0, ei)
+    c = core_port.Cols(Nmax)
+    cc = core_port.static_factors(x0, c)[1]
+    store, _ = make_store(x0, ei, w, Nmax, True)
+    x = x0.clone()
+    E = ei.size(1)
+    dtt = torch.empty(1, E, device="cuda")
+    chosen_ineligible = 0
+    for s in range(8):
+        t = 500.0 + s
+        sel = cases.random_selection(g, N, ei)
+        u = cases.uniforms(g, E)
+        if mode == "extreme_noise":
+            k = torch.rand(E, generator=g)
+            u = torch.where(k < 0.2, torch.full_like(u, 1e-30), u)           # Gumbel noise -4.2: still finite
+            u = torch.where(k > 0.9, torch.full_like(u, 1.0 - 2.0 ** -24), u)
+        store.set_selected_road(sel.cuda())
+        pop = store.step(t, noise=u.cuda(), delta_tt=dtt, variant=variant)
+        x[:, c.SEL] = sel
+        ref = core_port.core_step(x, ei, w, t, Nmax, u, cc)
+        assert torch.equal(store.export_x()[0].cpu(), x), f"x differs after step {s}"
+        assert torch.equal(dtt[0].cpu(), ref["delta_tt"])
+        chosen_ineligible += int((ref["chosen"] != 0).sum())
+    assert chosen_ineligible > 0
+    store.check_errors()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_store_run_equals_repeated_steps(variant):
+    """tarl_store_run (n steps enqueued by one call, SELECTED_ROAD bank cycled) == n calls of tarl_store_step."""
+    g = torch.Generator().manual_seed(5)
+    N, Nmax, R = 5000, 15, 2
+    ei, w = cases.random_dual_graph(g, N, 4)
+    x0, _ = cases.random_road_state(g, N, Nmax, 100.0, ei, garbage=False)
+    bank = [torch.stack([cases.random_selection(g, N, ei) for _ in range(R)]).reshape(-1).cuda() for _ in range(3)]
+    a, _ = make_store(x0, ei, w, Nmax, True, replicas=R, seed=11)
+    b, _ = make_store(x0, ei, w, Nmax, True, replicas=R, seed=11)
+    E = ei.size(1)
+    da, db = torch.empty(R, E, device="cuda"), torch.empty(R, E, device="cuda")
+    n = 7
+    for s in range(n):
+        a.set_selected_road(bank[s % 3].view(R, N))
+        pa = a.step(100.0 + s, delta_tt=da, variant=variant).clone()
+    pb = b.run(100.0, n, dt=1.0, sel_bank=bank, delta_tt=db, variant=variant)
+    assert torch.equal(a.export_x(), b.export_x())
+    assert torch.equal(da, db) and torch.equal(pa, pb)
+    assert a.step_id == b.step_id == n and a.t_last == b.t_last
+    more = b.run(107.0, 2, sel_bank=None, variant=variant)          # even count, no bank: SELECTED_ROAD stays
+    a.step(107.0, variant=variant); pa = a.step(108.0, variant=variant)
+    assert torch.equal(a.export_x(), b.export_x()) and torch.equal(pa, more)
+    a.check_errors(); b.check_errors()
