@@ -1,0 +1,21 @@
+"""Pick the judged columns out of an `ncu --page raw --csv` dump. Usage: python profiles/summarise_ncu.py raw.csv out.csv"""
+import csv
+import sys
+
+KEEP = ["ID", "Kernel Name", "Block Size", "Grid Size", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__bytes.sum.per_second", "gpu__time_duration.sum", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_warps",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_lg.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum"]
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = rows[0]
+idx = [hdr.index(k) for k in KEEP if k in hdr]
+out = csv.writer(open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout)
+for r in rows:
+    out.writerow([r[i] for i in idx])

@@ -26,6 +26,8 @@
 //          chain is two levels deep (edge slots -> neighbour records) with 2W gathers in flight per thread. Road
 //          networks have near-uniform small degree, which is exactly the case ELL is made for; links with more than W
 //          edges fall back to their CSR segment.
+#include <stdlib.h>
+
 #include "engine_common.cuh"
 
 using namespace tarl;
@@ -173,7 +175,8 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
 // for the upstream link whose head was admitted here.
 __device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const Store& s, int r, int n, int L, float4 hA,
                                                    float4 hB, const float4 st, const Pick pk, float t,
-                                                   float* __restrict__ delta_tt, int32_t* __restrict__ flags) {
+                                                   float* __restrict__ delta_tt, int k_out0, int k_out1,
+                                                   int32_t* __restrict__ flags) {
     const float num = hA.z, maxn = hA.w, fftt = st.x;
     int meta = __float_as_int(hB.w);
     const bool bad = !(num >= 0.0f) || !(num < (float)s.Nmax);
@@ -185,8 +188,7 @@ __device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const
     if (delta_tt != nullptr) {
         const float dtt = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);
         float* out = delta_tt + (int64_t)r * g.n_edges;
-        const int k1 = g.out_ptr[n + 1];
-        for (int k = g.out_ptr[n]; k < k1; ++k) out[g.out_eid != nullptr ? g.out_eid[k] : k] = dtt;
+        for (int k = k_out0; k < k_out1; ++k) out[g.out_eid != nullptr ? g.out_eid[k] : k] = dtt;
     }
     float num_post = num, tail_post = hB.y;
     if (bad) {
@@ -223,14 +225,18 @@ __global__ void __launch_bounds__(kThreads) k_csr_select_append(tarl_dual_csr g,
                                                                 const float* __restrict__ attr_in, Noise nz, float t,
                                                                 float* __restrict__ delta_tt,
                                                                 int32_t* __restrict__ flags) {
+    pdl_trigger();
+    pdl_wait();
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
     const int r = blockIdx.y;
     const int L = r * s.N + d;
     const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
     const float4 st = s.stat_a[d];
+    int k_out0 = 0, k_out1 = 0;
+    if (delta_tt != nullptr) { k_out0 = g.out_ptr[d]; k_out1 = g.out_ptr[d + 1]; }
     const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
-    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, flags);
+    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, k_out0, k_out1, flags);
 }
 
 template <int W, bool kExtNoise>
@@ -243,8 +249,8 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + d;
-    // level 1: everything addressed by the link id alone
-    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
+    // level 1: everything addressed by the link id alone — the static part before the dependency wait
+    pdl_trigger();
     const float4 st = s.stat_a[d];
     int u[W];
     float a[W];
@@ -253,6 +259,10 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
         u[j] = ell.in_src[(size_t)j * ell.pitch + d];
         a[j] = ell.in_attr[(size_t)j * ell.pitch + d];
     }
+    int k_out0 = 0, k_out1 = 0;
+    if (delta_tt != nullptr) { k_out0 = g.out_ptr[d]; k_out1 = g.out_ptr[d + 1]; }
+    pdl_wait();
+    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
     const bool free_d = hA.z < (hA.w - 3.0f);
     const float room_d = hA.w - hA.z, ridx_d = st.z;
     Pick pk = {0.0f, 0.0f, -1, false};
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
             }
         }
     }
-    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, flags);
+    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, k_out0, k_out1, flags);
 }
 
 // ------------------------------------------------------------------------------------------------ response phase
@@ -362,6 +372,8 @@ __device__ __noinline__ bool scan_out_edges_csr(const tarl_dual_csr& g, const St
 
 __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, Store s, float t,
                                                               uint8_t* __restrict__ pop, int32_t* __restrict__ flags) {
+    pdl_trigger();
+    pdl_wait();
     const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     const int base = r * s.N;
@@ -387,12 +399,14 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, t
     const int L = base + u;
     bool accept = false, hinted = false, fetched = false;
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
-    if (u < s.N) {
-        // level 1: own post-append record, out-neighbour ids, and whether a downstream link admitted this link's head
-        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
-        int dn[W];
+    pdl_trigger();
+    int dn[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) dn[j] = ell.out_dst[(size_t)j * ell.pitch + u];
+    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ell.out_dst[(size_t)j * ell.pitch + u] : -1;   // static: before the wait
+    pdl_wait();
+    if (u < s.N) {
+        // level 1: own post-append record and whether a downstream link admitted this link's head
+        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
         hinted = s.hint[L] != 0;
         // level 2: the neighbours' summaries and, for hinted links, the two ring slots a pop needs
         if (dn[W - 1] == -2) {
@@ -418,6 +432,19 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, t
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     if (accept) pop_head(s, L, A, B, t, fetched, q_head, q_last);
+}
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in engine_common.cuh).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t cs, Args... args) {
+    static const bool off = getenv("TARL_NO_PDL") != nullptr;      // tuning / A-B measurements only
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = cs;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
@@ -497,20 +524,20 @@ void launch_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& 
     const bool ext = nz.ext != nullptr;
     if (phase_mask & TARL_PHASE_SELECT_APPEND) {
         if (ell == nullptr) {
-            if (ext) k_csr_select_append<true><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, delta_tt, flags);
-            else k_csr_select_append<false><<<grid, kThreads, 0, cs>>>(*g, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_csr_select_append<true>, grid, cs, *g, s, attr_in, nz, t, delta_tt, flags);
+            else launch_pdl(k_csr_select_append<false>, grid, cs, *g, s, attr_in, nz, t, delta_tt, flags);
         } else if (ell->width == 4) {
-            if (ext) k_ell_select_append<4, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
-            else k_ell_select_append<4, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_ell_select_append<4, true>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            else launch_pdl(k_ell_select_append<4, false>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
         } else {
-            if (ext) k_ell_select_append<8, true><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
-            else k_ell_select_append<8, false><<<grid, kThreads, 0, cs>>>(*g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_ell_select_append<8, true>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            else launch_pdl(k_ell_select_append<8, false>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
         }
     }
     if (phase_mask & TARL_PHASE_RESPOND_SHIFT) {
-        if (ell == nullptr) k_csr_respond_pop<<<grid, kThreads, 0, cs>>>(*g, s, t, pop, flags);
-        else if (ell->width == 4) k_ell_respond_pop<4><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, pop, flags);
-        else k_ell_respond_pop<8><<<grid, kThreads, 0, cs>>>(*g, *ell, s, t, pop, flags);
+        if (ell == nullptr) launch_pdl(k_csr_respond_pop, grid, cs, *g, s, t, pop, flags);
+        else if (ell->width == 4) launch_pdl(k_ell_respond_pop<4>, grid, cs, *g, *ell, s, t, pop, flags);
+        else launch_pdl(k_ell_respond_pop<8>, grid, cs, *g, *ell, s, t, pop, flags);
     }
 }
 

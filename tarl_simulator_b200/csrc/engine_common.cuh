@@ -57,6 +57,14 @@ __device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logica
 __device__ __forceinline__ bool same_id(float a, float b) { return truncf(a) == truncf(b); }
 __device__ __forceinline__ bool at_least_one(float a) { return a >= 1.0f; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while the previous kernel of the stream is still draining. pdl_trigger() lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has started; pdl_wait() blocks until the PREVIOUS grid has completed and
+// its writes are visible. Everything a kernel does before pdl_wait() must therefore touch only data no kernel of the
+// step writes (topology, link statics). Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 int make_store(const tarl_link_store* p, Store* s);
 
 }  // namespace tarl
