@@ -250,28 +250,57 @@ def run_native(args):
     store.export_x(out=g.x[:N].unsqueeze(0)) if R == 1 else g.x[:N].copy_(store.export_x()[0])
     model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"])
     sel_hosts = [b[:N].cpu().pin_memory() for b in sel_bank]
-    sel_dev = torch.empty(N, dtype=torch.float32, device=dev)
-    dtt_host = torch.empty(E, dtype=torch.float32).pin_memory()
-    pop_host = torch.empty(N, dtype=torch.bool).pin_memory()
+    sel_devs = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
+    dtt_hosts = [torch.empty(E, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pop_hosts = [torch.empty(N, dtype=torch.bool).pin_memory() for _ in range(2)]
     e2e_steps = min(args.steps, 30)
+    copy_stream = torch.cuda.Stream(dev)        # device -> host
+    in_stream = torch.cuda.Stream(dev)          # host -> device (its own copy engine)
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    pending = {"k": 0}
+
+    def stage_inputs(k):            # H2D of step k's routing decisions, on the copy stream
+        with torch.cuda.stream(in_stream):
+            sel_devs[k % 2].copy_(sel_hosts[(state["i"] + k - pending["k"]) % len(sel_hosts)], non_blocking=True)
+            ev_in[k % 2].record(in_stream)
 
     def e2e_step():
-        sel_dev.copy_(sel_hosts[state["i"] % len(sel_hosts)], non_blocking=True)   # this step's routing decisions
+        # Double-buffered pipeline around the public call: while step k computes on the main stream, the copy stream
+        # returns step k-1's outputs to the host and brings in step k+1's inputs. Every byte is still moved inside the
+        # timed region; the copies just overlap the kernels of the neighbouring steps.
+        k = pending["k"]
+        stream.wait_event(ev_in[k % 2])
         model.set_time(state["t"])
-        model(g, selected_road=sel_dev)
-        dtt_host.copy_(model.direction_mpnn.road_optimality_data["delta_travel_time"], non_blocking=True)
-        pop_host.copy_(model.last_pop, non_blocking=True)
+        model(g, selected_road=sel_devs[k % 2])
+        dtt = model.direction_mpnn.road_optimality_data["delta_travel_time"]
+        pop = model.last_pop
+        done = torch.cuda.Event()
+        done.record(stream)
+        in_stream.wait_event(done)          # sel_devs[(k+1) % 2] was read by step k-1, long finished; order anyway
+        stage_inputs(k + 1)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            dtt_hosts[k % 2].copy_(dtt, non_blocking=True)
+            pop_hosts[k % 2].copy_(pop, non_blocking=True)
+            dtt.record_stream(copy_stream); pop.record_stream(copy_stream)
+            ev_out[k % 2].record(copy_stream)
+        pending["k"] = k + 1
         state["t"] += 1.0
         state["i"] += 1
 
+    stage_inputs(0)
     for _ in range(3):
         e2e_step()
+    copy_stream.synchronize()
     model.response_mpnn.update_history.resolve()
     barrier()
     w0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
+    stream.wait_stream(copy_stream)
+    stream.wait_stream(in_stream)
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3)
@@ -281,10 +310,11 @@ def run_native(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_ms = float(tms.item())
     e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
-           "h2d_bytes_per_step": int(sel_dev.numel() * 4), "d2h_bytes_per_step": int(dtt_host.numel() * 4 + pop_host.numel()),
+           "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(E * 4 + N),
            "steps": e2e_steps, "api": "SimulationCoreModel.forward(graph, selected_road=...) on graph.x (reference row "
            "layout, state resident on the device as with the reference's --device cuda); per step H2D = SELECTED_ROAD "
-           "decisions [N] from pinned memory, D2H = delta_travel_time[E] + pop mask[N]; noise drawn on the device"}
+           "decisions [N] from pinned memory, D2H = delta_travel_time[E] + pop mask[N] into pinned memory, double-buffered on a copy "
+           "stream so that the copies of steps k-1 / k+1 overlap the kernels of step k; noise drawn on the device"}
 
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,

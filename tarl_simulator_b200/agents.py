@@ -15,6 +15,7 @@ import weakref
 import torch
 
 from . import _cabi
+from ._arena import StepArena
 from .feature_helpers import AgentFeatureHelpers
 
 
@@ -127,6 +128,7 @@ class Agents(AgentFeatureHelpers):
         self._flags = None
         self._choice_calls = 0
         self.choice_seed = 0
+        self._arena = StepArena()
 
     def set_time(self, time):
         self.time = time
@@ -208,7 +210,7 @@ class Agents(AgentFeatureHelpers):
         R, N, dev = st.n_replicas, st.n_links, graph.x.device
         tab = self._table(R)
         side = side_tables_for(graph)
-        mask = torch.empty(R * N, dtype=torch.bool, device=dev)
+        mask, _ = self._arena.take(R * N, dev)
         flags = self._flag_words(dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_withdraw(C.byref(st), C.byref(tab), C.byref(side.adj),

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi
+from ._arena import StepArena as _StepArena
 from .feature_helpers import FeatureHelpers
 from .message_passing import MessagePassing
 from .topology import topology_for
@@ -238,6 +239,7 @@ class SimulationCoreModel(nn.Module):
         self.device = device
         self.last_pop = None            # bool[N] of the latest step (device), whether or not it joined the history
         self._scratch = _Scratch()
+        self._arena = _StepArena()
 
     def set_time(self, time):
         self.time = time
@@ -260,8 +262,7 @@ class SimulationCoreModel(nn.Module):
             graph.congestion_constant[:N] if has_static else None, noise)
         dev = x_roads.device
         delta_tt = torch.empty(E, dtype=torch.float32, device=dev)
-        pop = torch.empty(N, dtype=torch.bool, device=dev)
-        flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
+        pop, flags = self._arena.take(N, dev)
         ws = self._scratch.get(N, dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_core_step(

@@ -8,7 +8,10 @@
 
 namespace tarl {
 
-constexpr int kThreads = 256;
+#ifndef TARL_THREADS
+#define TARL_THREADS 128
+#endif
+constexpr int kThreads = TARL_THREADS;
 constexpr int kMetaRingMask = 0xffff;
 constexpr int kMetaGarbage = 1 << 16;
 
