@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=8, help="oracle steps timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpnn", action="store_true")
-    ap.add_argument("--mpnn-batch", type=int, default=4, help="batch rows (frames) of the MPNN fwd+bwd measurement")
+    ap.add_argument("--mpnn-batch", type=int, default=32, help="batch rows (frames) of the MPNN fwd+bwd measurement")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
     ap.add_argument("--variant", type=int, default=0, help="tarl_store_step kernel family: 0 ELL (default), 1 CSR")
@@ -359,7 +359,7 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     gen = torch.Generator(device=dev).manual_seed(5 + rank)
     with torch.no_grad():
         d0 = GraphDistribution(policy(nf, None, None), ei)
-        action = d0.sample(uniforms=torch.rand(B, d0.nb_nodes, device=dev, generator=gen)).to(torch.bool)
+        action = d0.sample(uniforms=torch.rand(B, d0.nb_nodes, device=dev, generator=gen), dtype=torch.bool)
     adv = torch.randn(B, device=dev, generator=gen)
     stream = torch.cuda.current_stream(dev)
 
@@ -373,7 +373,7 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     value = MPNNValueNet(ei, N_tot, str(dev))
     value.agent_features = torch.rand(1024, 9, device=dev, generator=gen)
     value.eval()
-    ef = g.edge_attr.reshape(1, E_full, 1).repeat(B, 1, 1).contiguous()
+    ef = g.edge_attr.reshape(1, E_full, 1).expand(B, -1, -1)      # what the environment hands out: one row, batch stride 0
     ai = torch.randint(0, 1024, (B, N_tot), device=dev, generator=gen)
     tm = torch.full((B, 1), 21600.0, device=dev)
     wv = torch.randn(B, 1, device=dev, generator=gen)

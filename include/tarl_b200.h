@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 4
+#define TARL_ABI_VERSION 6
 
 /* return codes */
 #define TARL_OK 0
@@ -195,69 +195,83 @@ typedef struct tarl_csr {
     const int32_t* eid;
 } tarl_csr;
 
+/* A [B, E]-shaped tensor with arbitrary element strides: element (b, e) at data[b*row_stride + e*col_stride].
+ * The policy kernels emit EDGE-major tensors (row_stride 1, col_stride B): the B rows of one edge are contiguous. */
+typedef struct tarl_rows {
+    void* data;
+    int64_t row_stride;
+    int64_t col_stride;
+} tarl_rows;
+
 /* Replaces MPNNPolicyNet.forward's active path (src/agents/mpnn_agent.py:117-192; update_edges :215-217):
  * logits[b,e] = nodes_embedding[ idx(b, edge_index[1][e]) ],  idx(b,n) = ROAD_INDEX(b,n) if >= 0 else n  (declared
  * divergence D2: the literal code raises on ROAD_INDEX = -1 rows). node_features: [B,N,*] fp32 with the given
- * element strides; node_emb [B,N] and node_idx [B,N] are caller-owned outputs (node_idx is what backward needs). */
+ * element strides. Outputs (caller-owned), batch row innermost: node_emb and node_idx (what backward needs) hold
+ * element (b, n) at n*B + b; logits holds element (b, e) at e*B + b. */
 int tarl_policy_embed_forward(const float* emb_weight, int32_t emb_rows, const float* node_features,
                               int64_t nf_batch_stride, int64_t nf_row_stride, int32_t road_index_col, int32_t batch,
                               int32_t n_nodes, const int32_t* edge_dst, int32_t n_edges, float* node_emb,
                               int32_t* node_idx, float* logits, int32_t* flags, void* stream);
 
 /* Gradient of the above w.r.t. nodes_embedding.weight (what embedding_dense_backward computes in the reference):
- * by_target = CSR of the full edge_index by target node. node_grad: [B,N] scratch. grad_weight [emb_rows] is
- * overwritten. Fixed summation order (no float atomics when idx is injective and batch-invariant). */
-int tarl_policy_embed_backward(const tarl_csr* by_target, const float* grad_logits, const int32_t* node_idx,
+ * by_target = CSR of the full edge_index by target node. grad_logits: [B,E] with any strides. node_grad: [N*B]
+ * scratch. grad_weight [emb_rows] is overwritten. Fixed summation order (no float atomics when idx is injective and
+ * batch-invariant). */
+int tarl_policy_embed_backward(const tarl_csr* by_target, const tarl_rows* grad_logits, const int32_t* node_idx,
                                int32_t batch, float* node_grad, float* grad_weight, int32_t emb_rows, void* stream);
 
 /* GraphDistribution (src/reinforcement_learning.py:15-96): categorical over the out-edges of every source node.
- * groups = CSR of edge_index by RANK of the source id (declared divergence D1). logits [B,E] in original edge order.
- * Any of proba [B,E], mode [B,E] (one-hot of the per-group arg-max, lowest edge id on ties), entropy [B],
- * log_prob [B] may be NULL. action: [B,E] one-hot in the dtype named by action_dtype (required for log_prob; a row
- * without exactly one selected edge per group gets -inf). partials: 3*B*tarl_graphdist_partial_count(K) floats. */
+ * groups = CSR of edge_index by RANK of the source id (declared divergence D1). logits [B,E], any strides.
+ * Any of proba [B,E], mode [B,E] (one-hot of the per-group arg-max, lowest edge id on ties; the CALLER zeroes it),
+ * entropy [B], log_prob [B] may be NULL. action: [B,E] one-hot in the dtype named by action_dtype (required for
+ * log_prob; a row without exactly one selected edge per group gets -inf).
+ * partials: 3*B*tarl_graphdist_partial_count(K, B) floats. */
 #define TARL_ACTION_U8 0
 #define TARL_ACTION_I64 1
 #define TARL_ACTION_F32 2
-int32_t tarl_graphdist_partial_count(int32_t n_groups);
-int tarl_graphdist_forward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                           const void* action, int32_t action_dtype, float* proba, float* mode, float* entropy,
-                           float* log_prob, float* partials, void* stream);
+int32_t tarl_graphdist_partial_count(int32_t n_groups, int32_t batch);
+int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                           const tarl_rows* action, int32_t action_dtype, const tarl_rows* proba, const tarl_rows* mode,
+                           float* entropy, float* log_prob, float* partials, void* stream);
 
 /* d(sum_b grad_log_prob[b]*log_prob[b] + grad_entropy[b]*entropy[b]) / d logits  -> grad_logits [B,E]. Either
  * upstream gradient may be NULL. log_prob (forward output, may be NULL) marks -inf rows, which get no gradient. */
-int tarl_graphdist_backward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                            const void* action, int32_t action_dtype, const float* grad_log_prob,
-                            const float* grad_entropy, const float* log_prob, float* grad_logits, void* stream);
+int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                            const tarl_rows* action, int32_t action_dtype, const float* grad_log_prob,
+                            const float* grad_entropy, const float* log_prob, const tarl_rows* grad_logits, void* stream);
 
-/* GraphDistribution.sample (:57-80): uniforms [B,K], one per (row, group) in ascending source id; onehot [B,E] int64
- * out. Inside a group edges are walked in ascending edge id (D3); batched rows are independent (D7). */
-int tarl_graphdist_sample(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                          const float* uniforms, int64_t* onehot, void* stream);
-
+/* GraphDistribution.sample (:57-80): uniforms [B,K], one per (row, group) in ascending source id; onehot [B,E] out in
+ * int64 (TARL_ACTION_I64, the reference's dtype) or uint8 / bool (TARL_ACTION_U8), zeroed by the CALLER. Inside a
+ * group edges are walked in ascending edge id (D3); batched rows are independent (D7). */
+int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                          const float* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, void* stream);
 
 /* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
  * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]
  * + w0); mean over the edges sharing edge_index[0]; v = tanh(a*mean + c). by_source / by_target: CSR of edge_index by
  * source / target NODE (n_rows = n_nodes), idx = the other endpoint, eid ascending inside a row.
- * node_features [B,N,>=7] (element strides given), edge_features [B,E], agent_index [B,N] int64, agent_features
- * [agent_rows, 9]. msg_weight [17] (= message_mlp.1.weight), msg_bias [1], node_weight [1], node_bias [1] are device
- * pointers. Outputs proj, mean, v: [B,N] each (proj and mean are what backward needs). */
+ * node_features [B,N,>=7] (element strides given), edge_features [B,E] with batch stride ef_batch_stride (0 = one
+ * row shared by the whole batch), agent_index [B,N] int64, agent_features [agent_rows, 9]. msg_weight [17]
+ * (= message_mlp.1.weight), msg_bias [1], node_weight [1], node_bias [1] are device pointers. Outputs proj, mean, v
+ * are NODE-major with the batch row innermost: element (b, n) at n*B + b (proj and mean are what backward needs). */
 int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
-                          int64_t nf_row_stride, const float* edge_features, const int64_t* agent_index,
-                          const float* agent_features, int32_t agent_rows, const float* msg_weight,
-                          const float* msg_bias, const float* node_weight, const float* node_bias, int32_t batch,
-                          int32_t n_nodes, float* proj, float* mean, float* v, int32_t* flags, void* stream);
+                          int64_t nf_row_stride, const float* edge_features, int64_t ef_batch_stride,
+                          const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
+                          const float* msg_weight, const float* msg_bias, const float* node_weight,
+                          const float* node_bias, int32_t batch, int32_t n_nodes, float* proj, float* mean, float* v,
+                          int32_t* flags, void* stream);
 
 /* Gradient of sum(grad_v * v) w.r.t. the four parameter tensors: grads[0:17] = d msg_weight, [17] = d msg_bias,
- * [18] = d node_weight, [19] = d node_bias. gm: [B,N] scratch; partials: 20*tarl_value_mp_partial_count(N,B) floats.
- * Fixed summation order (deterministic). */
+ * [18] = d node_weight, [19] = d node_bias. grad_v: element (b, n) at b*gv_batch_stride + n*gv_node_stride.
+ * gm: [N*B] scratch; partials: 20*tarl_value_mp_partial_count(N,B) floats. Fixed summation order (deterministic). */
 int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch);
 int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
                            int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
-                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
-                           const float* msg_weight, const float* msg_bias, const float* node_weight, int32_t batch,
-                           int32_t n_nodes, const float* proj, const float* mean, const float* v, const float* grad_v,
-                           float* gm, float* partials, float* grads, void* stream);
+                           int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                           int32_t agent_rows, const float* msg_weight, const float* msg_bias, const float* node_weight,
+                           int32_t batch, int32_t n_nodes, const float* proj, const float* mean, const float* v,
+                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, float* gm,
+                           float* partials, float* grads, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Population operations either side of the core step (csrc/agents.cu). Each works on either state layout.

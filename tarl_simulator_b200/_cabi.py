@@ -41,6 +41,19 @@ class CSR(C.Structure):
                 ("eid", C.c_void_p)]
 
 
+class Rows(C.Structure):
+    """struct tarl_rows: a [B, E] tensor with arbitrary element strides"""
+    _fields_ = [("data", C.c_void_p), ("row_stride", C.c_int64), ("col_stride", C.c_int64)]
+
+
+def rows(t):
+    """struct tarl_rows (by reference) for a 2-D tensor, or None."""
+    if t is None:
+        return None
+    assert t.dim() == 2
+    return C.byref(Rows(t.data_ptr(), t.stride(0) if t.size(0) > 1 else 0, t.stride(1) if t.size(1) > 1 else 1))
+
+
 class LinkStore(C.Structure):
     """struct tarl_link_store"""
     _fields_ = [("n_links", C.c_int32), ("n_replicas", C.c_int32), ("nmax", C.c_int32), ("reserved", C.c_int32),
@@ -76,6 +89,7 @@ _ELL = C.POINTER(DualELL)
 _AST = C.POINTER(AgentState)
 _ATB = C.POINTER(AgentTable)
 _AIX = C.POINTER(AgentIndex)
+_ROWS = C.POINTER(Rows)
 
 # name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
 SIGNATURES = {
@@ -91,16 +105,16 @@ SIGNATURES = {
     "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
     "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, C.c_uint64, C.c_uint32, _F, _F, _I32, _P, _I32, _P, _P, _P, _P]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
-    "tarl_policy_embed_backward": (C.c_int, [_CSR1, _P, _P, _I32, _P, _P, _I32, _P]),
-    "tarl_graphdist_partial_count": (_I32, [_I32]),
-    "tarl_graphdist_forward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
-    "tarl_graphdist_backward": (C.c_int, [_CSR1, _P, _F, _I32, _P, _I32, _P, _P, _P, _P, _P]),
-    "tarl_graphdist_sample": (C.c_int, [_CSR1, _P, _F, _I32, _P, _P, _P]),
+    "tarl_policy_embed_backward": (C.c_int, [_CSR1, _ROWS, _P, _I32, _P, _P, _I32, _P]),
+    "tarl_graphdist_partial_count": (_I32, [_I32, _I32]),
+    "tarl_graphdist_forward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _ROWS, _ROWS, _P, _P, _P, _P]),
+    "tarl_graphdist_backward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _P, _P, _P, _ROWS, _P]),
+    "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _P, _ROWS, _I32, _P]),
     "tarl_value_mp_partial_count": (_I32, [_I32, _I32]),
-    "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _P,
-                                        _P, _P]),
-    "tarl_value_mp_backward": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P, _P,
-                                         _P, _P, _P, _P, _P, _P]),
+    "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
+                                        _P, _P, _P]),
+    "tarl_value_mp_backward": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P,
+                                         _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_withdraw": (C.c_int, [_AST, _ATB, _CSR1, _F, _P, _P, _P, _P]),
     "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),

@@ -20,16 +20,20 @@ inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
 
 // ------------------------------------------------------------------------------------------------ policy embedding
-// node pass: idx[b,n] = ROAD_INDEX >= 0 ? ROAD_INDEX : n (D2);  emb[b,n] = W[idx]
+// Layout: everything the policy kernels produce is NODE-major / EDGE-major with the batch row innermost (element (b, n)
+// of emb / idx / node_grad at n*B + b, element (b, e) of logits at e*B + b), so that the B rows of one node or edge are
+// one contiguous vector: gathers by node id fetch all rows in one sector and edge ids are read once for all rows.
+// node pass: idx[n,b] = ROAD_INDEX >= 0 ? ROAD_INDEX : n (D2);  emb[n,b] = W[idx]. One thread per (node, row), row
+// innermost: the strided reads of the ROAD_INDEX column touch every sector of node_features whatever the mapping (28-byte
+// rows), the writes are fully coalesced.
 __global__ void __launch_bounds__(kThreads) k_policy_node(const float* __restrict__ w, int rows,
                                                           const float* __restrict__ nf, int64_t nf_bs, int64_t nf_rs,
                                                           int ridx_col, int B, int N, float* __restrict__ emb,
                                                           int32_t* __restrict__ idx, int32_t* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * N) return;
-    const int b = (int)(i / N), n = (int)(i % N);
-    const float r = nf[b * nf_bs + n * nf_rs + ridx_col];
-    long long k = (long long)r;  // .to(torch.long): truncation
+    const int n = (int)(i / B), b = (int)(i - (int64_t)n * B);
+    long long k = (long long)nf[b * nf_bs + n * nf_rs + ridx_col];  // .to(torch.long): truncation
     if (k < 0) k = n;
     if (k >= rows) {  // nn.Embedding raises IndexError
         atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_EMBED_RANGE);
@@ -39,47 +43,87 @@ __global__ void __launch_bounds__(kThreads) k_policy_node(const float* __restric
     emb[i] = w[k];
 }
 
-// edge pass: logits[b,e] = emb[b, dst[e]]
+// edge pass: logits[e, :] = emb[dst[e], :]. One thread per (edge, chunk of 4 rows) when B % 4 == 0 (the threads of one
+// edge copy one contiguous B-vector with 128-bit accesses), else one thread per (edge, row).
 __global__ void __launch_bounds__(kThreads) k_policy_edge(const float* __restrict__ emb, const int32_t* __restrict__ dst,
-                                                          int B, int N, int E, float* __restrict__ logits) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    const int n = dst[e];
-    for (int b = 0; b < B; ++b) logits[(int64_t)b * E + e] = emb[(int64_t)b * N + n];
+                                                          int B, int E, float* __restrict__ logits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((B & 3) == 0) {
+        const int C = B >> 2;
+        if (i >= (int64_t)E * C) return;
+        const int e = (int)(i / C), c = (int)(i - (int64_t)e * C);
+        reinterpret_cast<float4*>(logits)[i] = reinterpret_cast<const float4*>(emb)[(int64_t)dst[e] * C + c];
+    } else {
+        if (i >= (int64_t)E * B) return;
+        const int e = (int)(i / B), b = (int)(i - (int64_t)e * B);
+        logits[i] = emb[(int64_t)dst[e] * B + b];
+    }
 }
 
-// backward node pass: G[b,n] = sum over in-edges (ascending edge id) of grad_logits[b,e]
-__global__ void __launch_bounds__(kThreads) k_policy_node_grad(tarl_csr in, const float* __restrict__ gl, int B, int E,
-                                                               float* __restrict__ G) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= in.n_rows) return;
-    const int k0 = in.ptr[n], k1 = in.ptr[n + 1];
-    for (int b = 0; b < B; ++b) {
+// backward node pass: G[n,b] = sum over in-edges (ascending edge id) of grad_logits[b,e]. Edge-major gradient with
+// B % 4 == 0: one thread per (node, chunk of 4 rows), 128-bit gathers; any other strides: one thread per (node, row).
+__global__ void __launch_bounds__(kThreads) k_policy_node_grad(tarl_csr in, const float* __restrict__ gl, int64_t g_sb,
+                                                               int64_t g_se, int B, float* __restrict__ G) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g_sb == 1 && g_se == B && (B & 3) == 0) {
+        const int C = B >> 2;
+        if (i >= (int64_t)in.n_rows * C) return;
+        const int n = (int)(i / C), c = (int)(i - (int64_t)n * C);
+        const int k1 = in.ptr[n + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = in.ptr[n]; k < k1; ++k) {
+            const float4 v = reinterpret_cast<const float4*>(gl)[(int64_t)in.eid[k] * C + c];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(G)[i] = acc;
+    } else {
+        if (i >= (int64_t)in.n_rows * B) return;
+        const int n = (int)(i / B), b = (int)(i - (int64_t)n * B);
+        const int k1 = in.ptr[n + 1];
         float acc = 0.0f;
-        for (int k = k0; k < k1; ++k) acc += gl[(int64_t)b * E + in.eid[k]];
-        G[(int64_t)b * in.n_rows + n] = acc;
+        for (int k = in.ptr[n]; k < k1; ++k) acc += gl[b * g_sb + in.eid[k] * g_se];
+        G[i] = acc;
     }
 }
 
-// backward weight pass: gradW[idx[b,n]] += G[b,n]. Batch rows that share the index of row 0 (always, in practice: the
-// ROAD_INDEX column is static) are summed in registers in batch order; with an injective index map that makes every
-// weight row the target of exactly one atomicAdd, i.e. deterministic.
+// backward weight pass: gradW[idx[n,b]] += G[n,b]. A group of Bp lanes (Bp = B rounded up to a power of two, <= 32) owns
+// one node and reads its rows coalesced. Rows that share the index of row 0 (always, in practice: the ROAD_INDEX column
+// is static) are summed by a fixed shuffle tree; with an injective index map every weight row is then the target of
+// exactly one atomicAdd, i.e. the result is deterministic. Rows with a different index fall back to their own atomicAdd.
 __global__ void __launch_bounds__(kThreads) k_policy_weight_grad(const float* __restrict__ G, const int32_t* __restrict__ idx,
-                                                                 int B, int N, float* __restrict__ gw) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int k0 = idx[n];
+                                                                 int B, int Bp, int N, float* __restrict__ gw) {
+    const int sh = 31 - __clz(Bp);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)(i >> sh), lane_b = (int)(i & (Bp - 1));
+    const bool node_ok = n < N;
     float acc = 0.0f;
-    for (int b = 0; b < B; ++b) {
-        const int k = idx[(int64_t)b * N + n];
-        const float g = G[(int64_t)b * N + n];
-        if (k == k0) acc += g;
-        else atomicAdd(&gw[k], g);
+    int k0 = 0;
+    if (node_ok) {
+        k0 = idx[(int64_t)n * B];
+        for (int b = lane_b; b < B; b += Bp) {
+            const int k = idx[(int64_t)n * B + b];
+            const float g = G[(int64_t)n * B + b];
+            if (k == k0) acc += g;
+            else atomicAdd(&gw[k], g);
+        }
     }
-    atomicAdd(&gw[k0], acc);
+    for (int o = Bp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (node_ok && lane_b == 0) atomicAdd(&gw[k0], acc);
 }
 
 // ------------------------------------------------------------------------------------------------ GraphDistribution
+// Thread mapping: one thread per (source group, batch row) with the BATCH ROW INNERMOST — lanes [0, Bp) of a warp hold
+// the Bp rows of one group (Bp = batch rounded up to a power of two, <= 32), the next Bp lanes the next group. With
+// edge-major tensors (element (b, e) at e*B + b: what MPNNPolicyNet emits) the Bp lanes of a group read one
+// contiguous B-vector per edge and the group's edge ids are loaded once per group, not once per row. Any strides are
+// accepted (a row-major [B,E] tensor is correct, just less coalesced). A group's values are cached in registers
+// (kCache edges) so that logits are read once and every exp is evaluated once.
+constexpr int kCache = 6;
+
+struct View {          // element (b, e) of a [B, E] tensor at base[b*sb + e*se]
+    int64_t sb, se;
+};
+
 __device__ __forceinline__ float load_action(const void* a, int dtype, int64_t i) {
     switch (dtype) {
         case TARL_ACTION_U8: return (float)static_cast<const uint8_t*>(a)[i];
@@ -102,55 +146,140 @@ __device__ __forceinline__ T block_sum(T v, T* smem) {
     return r;  // valid in thread 0
 }
 
-// One thread per (batch row, source group). Softmax over the group's edges in ascending edge id, then whatever of
-// {proba, entropy, log_prob, mode} was asked for. Per-block partial sums keep the [B] reductions deterministic.
-__global__ void __launch_bounds__(kThreads) k_gd_forward(tarl_csr grp, const float* __restrict__ logits, float temp,
-                                                         int E, const void* __restrict__ action, int action_dtype,
-                                                         float* __restrict__ proba, float* __restrict__ mode,
-                                                         float* __restrict__ part_ent, float* __restrict__ part_lp,
-                                                         int32_t* __restrict__ part_bad) {
-    __shared__ float sm_f[kThreads / 32];
-    __shared__ int sm_i[kThreads / 32];
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    const float* lg = logits + (int64_t)b * E;
+// Sums v over the threads of the block that share (threadIdx.x % Bp); thread b < Bp returns row b's sum (fixed order).
+template <typename T>
+__device__ __forceinline__ T block_sum_rows(T v, int Bp, T* smem /* [kThreads/32 * 32] */) {
+    for (int o = 16; o >= Bp; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane < Bp) smem[wid * 32 + lane] = v;
+    __syncthreads();
+    T r = T(0);
+    if (threadIdx.x < Bp)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += smem[w * 32 + threadIdx.x];
+    return r;
+}
+
+struct GroupRows {     // what thread (g, b) needs to walk its group
+    int g, b, k0, k1;
+    bool live;
+};
+
+// Bp is a power of two: tile `tile` of the grid covers groups [tile*kThreads/Bp, (tile+1)*kThreads/Bp).
+__device__ __forceinline__ GroupRows locate(const tarl_csr& grp, int B, int Bp, int b_chunk, int tile) {
+    const int sh = 31 - __clz(Bp);
+    const int64_t i = (int64_t)tile * blockDim.x + threadIdx.x;
+    GroupRows t;
+    t.g = (int)(i >> sh);
+    t.b = b_chunk * 32 + (int)(i & (Bp - 1));
+    t.live = t.g < grp.n_rows && t.b < B;
+    t.k0 = t.live ? grp.ptr[t.g] : 0;
+    t.k1 = t.live ? grp.ptr[t.g + 1] : 0;
+    return t;
+}
+
+// Softmax of one group for one row. The first kCache edges live in registers (ex[j] = exp(z_j - max), statically
+// indexed: every loop over them is fully unrolled and predicated on j < deg); longer groups recompute the tail.
+struct Soft {
+    float ex[kCache];
+    float mx, inv_den;
+    int deg;
+};
+
+// Fast-math forms on the per-(edge, row) path, all far inside the 1e-5 relative / 1e-6 absolute parity bar of the
+// tests: __fdividef 2 ulp; __expf on arguments <= 0 (softmax after max subtraction) has relative error ~|x|*1e-7;
+// __logf has absolute error <= 2^-21.4, the size of one ulp of log(p) for |log p| ~ 1 and negligible next to the
+// p * log(p) products it feeds. With them the kernels are bandwidth- instead of instruction-bound.
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+
+__device__ __forceinline__ void soft_load(Soft& s, const tarl_csr& grp, const float* __restrict__ lg, View lv, int b, int k0,
+                                          int k1, float temp) {
+    s.deg = k1 - k0;
+    s.mx = -FLT_MAX;
+    const float* row = lg + b * lv.sb;
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        s.ex[j] = -FLT_MAX;
+        if (j < s.deg) {
+            s.ex[j] = fdiv(row[grp.eid[k0 + j] * lv.se], temp);
+            s.mx = fmaxf(s.mx, s.ex[j]);
+        }
+    }
+    for (int k = k0 + kCache; k < k1; ++k) s.mx = fmaxf(s.mx, fdiv(row[grp.eid[k] * lv.se], temp));
+    float den = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kCache; ++j)
+        if (j < s.deg) { s.ex[j] = fexp(s.ex[j] - s.mx); den += s.ex[j]; }
+    for (int k = k0 + kCache; k < k1; ++k) den += fexp(fdiv(row[grp.eid[k] * lv.se], temp) - s.mx);
+    s.inv_den = fdiv(1.0f, den);
+}
+
+__device__ __forceinline__ float tail_p(const Soft& s, const float* __restrict__ lg, View lv, int b, int e, float temp) {
+    return fexp(fdiv(lg[b * lv.sb + e * lv.se], temp) - s.mx) * s.inv_den;
+}
+
+struct FwdAcc {
+    float ent, lp, asum, best;
+    int best_e;
+};
+
+__device__ __forceinline__ void fwd_edge(FwdAcc& a, float p, int e, int b, const void* __restrict__ action, View av,
+                                         int action_dtype, float* __restrict__ proba, View pv) {
+    const float l = flog(p + kLogEps);
+    a.ent -= p * l;
+    if (action != nullptr) {
+        const float x = load_action(action, action_dtype, b * av.sb + e * av.se);
+        a.lp += x * l;
+        a.asum += x;
+    }
+    if (proba != nullptr) proba[b * pv.sb + e * pv.se] = p;
+    if (p > a.best) { a.best = p; a.best_e = e; }
+}
+
+// Softmax over the group's edges in ascending edge id, then whatever of {proba, entropy, log_prob, mode} was asked
+// for. Each CTA walks tiles of groups with a fixed stride and leaves one partial sum per (CTA, row): the [B]
+// reductions stay deterministic and the second stage stays small.
+__global__ void __launch_bounds__(kThreads) k_gd_forward(tarl_csr grp, const float* __restrict__ logits, View lv,
+                                                         float temp, int B, int Bp, int n_tiles,
+                                                         const void* __restrict__ action, View av, int action_dtype,
+                                                         float* __restrict__ proba, View pv, float* __restrict__ mode,
+                                                         View mv, float* __restrict__ part_ent,
+                                                         float* __restrict__ part_lp, int32_t* __restrict__ part_bad) {
+    __shared__ float sm_f[kThreads];
+    __shared__ int sm_i[kThreads];
     float ent = 0.0f, lp = 0.0f;
     int bad = 0;
-    if (g < grp.n_rows) {
-        const int k0 = grp.ptr[g], k1 = grp.ptr[g + 1];
-        float mx = -FLT_MAX;
-        for (int k = k0; k < k1; ++k) mx = fmaxf(mx, lg[grp.eid[k]] / temp);
-        float den = 0.0f;
-        for (int k = k0; k < k1; ++k) den += expf(lg[grp.eid[k]] / temp - mx);
-        float asum = 0.0f, best = -FLT_MAX;
-        int best_e = -1;
-        for (int k = k0; k < k1; ++k) {
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const GroupRows t = locate(grp, B, Bp, blockIdx.y, tile);
+        if (!t.live || t.k1 == t.k0) continue;
+        Soft s;
+        soft_load(s, grp, logits, lv, t.b, t.k0, t.k1, temp);
+        FwdAcc a = {0.0f, 0.0f, 0.0f, -FLT_MAX, -1};
+#pragma unroll
+        for (int j = 0; j < kCache; ++j)
+            if (j < s.deg) fwd_edge(a, s.ex[j] * s.inv_den, grp.eid[t.k0 + j], t.b, action, av, action_dtype, proba, pv);
+        for (int k = t.k0 + kCache; k < t.k1; ++k) {
             const int e = grp.eid[k];
-            const float p = expf(lg[e] / temp - mx) / den;
-            const float l = logf(p + kLogEps);
-            ent -= p * l;
-            if (action != nullptr) {
-                const float a = load_action(action, action_dtype, (int64_t)b * E + e);
-                lp += a * l;
-                asum += a;
-            }
-            if (proba != nullptr) proba[(int64_t)b * E + e] = p;
-            if (p > best) { best = p; best_e = e; }
+            fwd_edge(a, tail_p(s, logits, lv, t.b, e, temp), e, t.b, action, av, action_dtype, proba, pv);
         }
-        if (action != nullptr && asum != 1.0f) bad = 1;   // not exactly one selected edge in this group (:86-88)
-        if (mode != nullptr && best_e >= 0) mode[(int64_t)b * E + best_e] = 1.0f;
+        ent += a.ent; lp += a.lp;
+        if (action != nullptr && a.asum != 1.0f) bad = 1;   // not exactly one selected edge in this group (:86-88)
+        if (mode != nullptr && a.best_e >= 0) mode[t.b * mv.sb + a.best_e * mv.se] = 1.0f;
     }
     const int nb = gridDim.x;
+    const int row = blockIdx.y * 32 + threadIdx.x;      // valid for threadIdx.x < Bp
     if (part_ent != nullptr) {
-        const float s = block_sum(ent, sm_f);
-        if (threadIdx.x == 0) part_ent[(int64_t)b * nb + blockIdx.x] = s;
+        const float v = block_sum_rows(ent, Bp, sm_f);
+        if (threadIdx.x < Bp && row < B) part_ent[(int64_t)row * nb + blockIdx.x] = v;
     }
     if (part_lp != nullptr) {
-        const float s = block_sum(lp, sm_f);
-        const int c = block_sum(bad, sm_i);
-        if (threadIdx.x == 0) {
-            part_lp[(int64_t)b * nb + blockIdx.x] = s;
-            part_bad[(int64_t)b * nb + blockIdx.x] = c;
+        const float v = block_sum_rows(lp, Bp, sm_f);
+        const int c = block_sum_rows(bad, Bp, sm_i);
+        if (threadIdx.x < Bp && row < B) {
+            part_lp[(int64_t)row * nb + blockIdx.x] = v;
+            part_bad[(int64_t)row * nb + blockIdx.x] = c;
         }
     }
 }
@@ -184,61 +313,101 @@ __global__ void __launch_bounds__(kThreads) k_gd_finish(const float* __restrict_
 // grad_logits[b,e] = inv_t * ( g_lp[b] * (a_e r_e - p_e S_a)  -  g_ent[b] * p_e (c_e - S_c) ),
 //   r_e = p_e/(p_e+eps), c_e = log(p_e+eps) + r_e, S_a = sum_e a_e r_e, S_c = sum_e p_e c_e  (sums over the group).
 // Rows whose action was impossible carry log_prob = -inf assigned as a constant in the reference: no gradient.
-__global__ void __launch_bounds__(kThreads) k_gd_backward(tarl_csr grp, const float* __restrict__ logits, float temp,
-                                                          int E, const void* __restrict__ action, int action_dtype,
-                                                          const float* __restrict__ g_lp, const float* __restrict__ g_ent,
-                                                          const float* __restrict__ log_prob, float* __restrict__ grad) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (g >= grp.n_rows) return;
-    const float* lg = logits + (int64_t)b * E;
-    float wl = (g_lp != nullptr && action != nullptr) ? g_lp[b] : 0.0f;
-    if (log_prob != nullptr && log_prob[b] == -INFINITY) wl = 0.0f;
-    const float we = (g_ent != nullptr) ? g_ent[b] : 0.0f;
-    const int k0 = grp.ptr[g], k1 = grp.ptr[g + 1];
-    float mx = -FLT_MAX;
-    for (int k = k0; k < k1; ++k) mx = fmaxf(mx, lg[grp.eid[k]] / temp);
-    float den = 0.0f;
-    for (int k = k0; k < k1; ++k) den += expf(lg[grp.eid[k]] / temp - mx);
+__global__ void __launch_bounds__(kThreads) k_gd_backward(tarl_csr grp, const float* __restrict__ logits, View lv,
+                                                          float temp, int B, int Bp, const void* __restrict__ action,
+                                                          View av, int action_dtype, const float* __restrict__ g_lp,
+                                                          const float* __restrict__ g_ent,
+                                                          const float* __restrict__ log_prob, float* __restrict__ grad,
+                                                          View gv) {
+    const GroupRows t = locate(grp, B, Bp, blockIdx.y, blockIdx.x);
+    if (!t.live || t.k1 == t.k0) return;
+    float wl = (g_lp != nullptr && action != nullptr) ? g_lp[t.b] : 0.0f;
+    if (log_prob != nullptr && log_prob[t.b] == -INFINITY) wl = 0.0f;
+    const float we = (g_ent != nullptr) ? g_ent[t.b] : 0.0f;
+    Soft s;
+    soft_load(s, grp, logits, lv, t.b, t.k0, t.k1, temp);
     float Sa = 0.0f, Sc = 0.0f;
-    for (int k = k0; k < k1; ++k) {
-        const int e = grp.eid[k];
-        const float p = expf(lg[e] / temp - mx) / den;
-        const float r = p / (p + kLogEps);
-        const float c = logf(p + kLogEps) + r;
-        if (wl != 0.0f) Sa += load_action(action, action_dtype, (int64_t)b * E + e) * r;
-        Sc += p * c;
+    float cc[kCache], ar[kCache];       // c_e and a_e r_e of the cached edges
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        cc[j] = 0.0f; ar[j] = 0.0f;
+        if (j < s.deg) {
+            const float p = s.ex[j] * s.inv_den;
+            const float r = fdiv(p, p + kLogEps);
+            cc[j] = flog(p + kLogEps) + r;
+            if (wl != 0.0f) ar[j] = load_action(action, action_dtype, t.b * av.sb + grp.eid[t.k0 + j] * av.se) * r;
+            Sa += ar[j];
+            Sc += p * cc[j];
+        }
     }
-    for (int k = k0; k < k1; ++k) {
+    for (int k = t.k0 + kCache; k < t.k1; ++k) {
         const int e = grp.eid[k];
-        const float p = expf(lg[e] / temp - mx) / den;
-        const float r = p / (p + kLogEps);
-        const float c = logf(p + kLogEps) + r;
+        const float p = tail_p(s, logits, lv, t.b, e, temp);
+        const float r = fdiv(p, p + kLogEps);
+        if (wl != 0.0f) Sa += load_action(action, action_dtype, t.b * av.sb + e * av.se) * r;
+        Sc += p * (flog(p + kLogEps) + r);
+    }
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        if (j < s.deg) {
+            const float p = s.ex[j] * s.inv_den;
+            float v = -we * p * (cc[j] - Sc);
+            if (wl != 0.0f) v += wl * (ar[j] - p * Sa);
+            grad[t.b * gv.sb + grp.eid[t.k0 + j] * gv.se] = fdiv(v, temp);
+        }
+    }
+    for (int k = t.k0 + kCache; k < t.k1; ++k) {
+        const int e = grp.eid[k];
+        const float p = tail_p(s, logits, lv, t.b, e, temp);
+        const float r = fdiv(p, p + kLogEps);
+        const float c = flog(p + kLogEps) + r;
         float v = -we * p * (c - Sc);
-        if (wl != 0.0f) v += wl * (load_action(action, action_dtype, (int64_t)b * E + e) * r - p * Sa);
-        grad[(int64_t)b * E + e] = v / temp;
+        if (wl != 0.0f) v += wl * (load_action(action, action_dtype, t.b * av.sb + e * av.se) * r - p * Sa);
+        grad[t.b * gv.sb + e * gv.se] = fdiv(v, temp);
     }
 }
 
 // inverse-CDF sample, one uniform per (row, group): first edge (ascending edge id, D3) with u < cumulative proba (:62-80)
-__global__ void __launch_bounds__(kThreads) k_gd_sample(tarl_csr grp, const float* __restrict__ logits, float temp, int E,
-                                                        const float* __restrict__ u, long long* __restrict__ onehot) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (g >= grp.n_rows) return;
-    const float* lg = logits + (int64_t)b * E;
-    const int k0 = grp.ptr[g], k1 = grp.ptr[g + 1];
-    float mx = -FLT_MAX;
-    for (int k = k0; k < k1; ++k) mx = fmaxf(mx, lg[grp.eid[k]] / temp);
-    float den = 0.0f;
-    for (int k = k0; k < k1; ++k) den += expf(lg[grp.eid[k]] / temp - mx);
-    const float ug = u[(int64_t)b * grp.n_rows + g];
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_gd_sample(tarl_csr grp, const float* __restrict__ logits, View lv, float temp,
+                                                        int B, int Bp, const float* __restrict__ u, T* __restrict__ onehot,
+                                                        View ov) {
+    const GroupRows t = locate(grp, B, Bp, blockIdx.y, blockIdx.x);
+    if (!t.live || t.k1 == t.k0) return;
+    Soft s;
+    soft_load(s, grp, logits, lv, t.b, t.k0, t.k1, temp);
+    const float ug = u[(int64_t)t.b * grp.n_rows + t.g];
     float cum = 0.0f;
-    for (int k = k0; k < k1; ++k) {
-        const int e = grp.eid[k];
-        cum += expf(lg[e] / temp - mx) / den;
-        if (ug < cum) { onehot[(int64_t)b * E + e] = 1; break; }
+    int hit = -1;
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        if (j < s.deg && hit < 0) {
+            cum += s.ex[j] * s.inv_den;
+            if (ug < cum) hit = grp.eid[t.k0 + j];
+        }
     }
+    for (int k = t.k0 + kCache; k < t.k1 && hit < 0; ++k) {
+        const int e = grp.eid[k];
+        cum += tail_p(s, logits, lv, t.b, e, temp);
+        if (ug < cum) hit = e;
+    }
+    if (hit >= 0) onehot[t.b * ov.sb + hit * ov.se] = T(1);
+}
+
+inline int pow2_rows(int B) {
+    int p = 1;
+    while (p < B && p < 32) p <<= 1;
+    return p;
+}
+inline dim3 gd_grid(int K, int B) {      // one CTA per tile of kThreads/Bp groups
+    const int Bp = pow2_rows(B);
+    return dim3(blocks_for((int64_t)K * Bp), (B + 31) / 32);
+}
+constexpr int kFwdMaxCtas = 148 * 16;     // forward CTAs walk tiles with a stride: this bounds the partials per row
+inline dim3 gd_fwd_grid(int K, int B) {
+    dim3 g = gd_grid(K, B);
+    if (g.x > (unsigned)kFwdMaxCtas) g.x = kFwdMaxCtas;
+    return g;
 }
 
 int check_csr(const tarl_csr* c) {
@@ -247,6 +416,10 @@ int check_csr(const tarl_csr* c) {
     if (c->n_edges > 0 && c->eid == nullptr) return TARL_E_BADARG;
     return TARL_OK;
 }
+
+inline View view_of(const tarl_rows* r) { return r != nullptr ? View{r->row_stride, r->col_stride} : View{0, 0}; }
+template <typename T>
+inline T* data_of(const tarl_rows* r) { return r != nullptr ? static_cast<T*>(r->data) : nullptr; }
 
 }  // namespace
 
@@ -265,11 +438,12 @@ int tarl_policy_embed_forward(const float* emb_weight, int32_t emb_rows, const f
         emb_weight, emb_rows, node_features, nf_batch_stride, nf_row_stride, road_index_col, batch, n_nodes, node_emb,
         node_idx, flags);
     if (n_edges > 0)
-        k_policy_edge<<<blocks_for(n_edges), kThreads, 0, s>>>(node_emb, edge_dst, batch, n_nodes, n_edges, logits);
+        k_policy_edge<<<blocks_for((int64_t)n_edges * ((batch & 3) == 0 ? batch >> 2 : batch)), kThreads, 0, s>>>(
+            node_emb, edge_dst, batch, n_edges, logits);
     return launch_status();
 }
 
-int tarl_policy_embed_backward(const tarl_csr* by_target, const float* grad_logits, const int32_t* node_idx,
+int tarl_policy_embed_backward(const tarl_csr* by_target, const tarl_rows* grad_logits, const int32_t* node_idx,
                                int32_t batch, float* node_grad, float* grad_weight, int32_t emb_rows, void* stream) {
     int rc = check_csr(by_target);
     if (rc != TARL_OK) return rc;
@@ -277,18 +451,25 @@ int tarl_policy_embed_backward(const tarl_csr* by_target, const float* grad_logi
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(grad_weight, 0, sizeof(float) * (size_t)emb_rows, s) != cudaSuccess) return TARL_E_LAUNCH;
     if (batch == 0 || by_target->n_rows == 0) return TARL_OK;
-    if (!node_idx || !node_grad || (by_target->n_edges > 0 && !grad_logits)) return TARL_E_BADARG;
-    const int nb = blocks_for(by_target->n_rows);
-    k_policy_node_grad<<<nb, kThreads, 0, s>>>(*by_target, grad_logits, batch, by_target->n_edges, node_grad);
-    k_policy_weight_grad<<<nb, kThreads, 0, s>>>(node_grad, node_idx, batch, by_target->n_rows, grad_weight);
+    if (!node_idx || !node_grad || (by_target->n_edges > 0 && (!grad_logits || !grad_logits->data))) return TARL_E_BADARG;
+    const View gv = view_of(grad_logits);
+    const bool vec = gv.sb == 1 && gv.se == batch && (batch & 3) == 0;
+    k_policy_node_grad<<<blocks_for((int64_t)by_target->n_rows * (vec ? batch >> 2 : batch)), kThreads, 0, s>>>(
+        *by_target, data_of<const float>(grad_logits), gv.sb, gv.se, batch, node_grad);
+    int Bp = 1;
+    while (Bp < batch && Bp < 32) Bp <<= 1;
+    k_policy_weight_grad<<<blocks_for((int64_t)by_target->n_rows * Bp), kThreads, 0, s>>>(node_grad, node_idx, batch, Bp,
+                                                                                          by_target->n_rows, grad_weight);
     return launch_status();
 }
 
-int32_t tarl_graphdist_partial_count(int32_t n_groups) { return n_groups > 0 ? blocks_for(n_groups) : 0; }
+int32_t tarl_graphdist_partial_count(int32_t n_groups, int32_t batch) {
+    return (n_groups > 0 && batch > 0) ? gd_fwd_grid(n_groups, batch).x : 0;
+}
 
-int tarl_graphdist_forward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                           const void* action, int32_t action_dtype, float* proba, float* mode, float* entropy,
-                           float* log_prob, float* partials, void* stream) {
+int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                           const tarl_rows* action, int32_t action_dtype, const tarl_rows* proba, const tarl_rows* mode,
+                           float* entropy, float* log_prob, float* partials, void* stream) {
     int rc = check_csr(groups);
     if (rc != TARL_OK) return rc;
     if (batch < 0 || (action != nullptr && (action_dtype < 0 || action_dtype > 2))) return TARL_E_BADARG;
@@ -296,10 +477,10 @@ int tarl_graphdist_forward(const tarl_csr* groups, const float* logits, float te
     if (batch == 0) return TARL_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int E = groups->n_edges, K = groups->n_rows;
-    if (E > 0 && logits == nullptr) return TARL_E_BADARG;
-    if (mode != nullptr && E > 0 &&
-        cudaMemsetAsync(mode, 0, sizeof(float) * (size_t)batch * E, s) != cudaSuccess) return TARL_E_LAUNCH;
-    const int nb = K > 0 ? blocks_for(K) : 0;
+    if (E > 0 && (logits == nullptr || logits->data == nullptr)) return TARL_E_BADARG;
+    const dim3 grid = K > 0 ? gd_fwd_grid(K, batch) : dim3(0, 1);
+    const int nb = (int)grid.x;
+    const int n_tiles = K > 0 ? (int)gd_grid(K, batch).x : 0;
     float* part_ent = nullptr; float* part_lp = nullptr; int32_t* part_bad = nullptr;
     if (entropy != nullptr || log_prob != nullptr) {
         if (partials == nullptr && nb > 0) return TARL_E_WORKSPACE;
@@ -307,45 +488,51 @@ int tarl_graphdist_forward(const tarl_csr* groups, const float* logits, float te
         part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;
         part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
     }
-    if (nb > 0) {
-        dim3 grid(nb, batch);
-        k_gd_forward<<<grid, kThreads, 0, s>>>(*groups, logits, temperature, E, action, action_dtype, proba, mode,
+    if (nb > 0)
+        k_gd_forward<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits), temperature, batch,
+                                               pow2_rows(batch), n_tiles, data_of<const void>(action), view_of(action),
+                                               action_dtype,
+                                               data_of<float>(proba), view_of(proba), data_of<float>(mode), view_of(mode),
                                                part_ent, part_lp, part_bad);
-    }
     if (entropy != nullptr || log_prob != nullptr)
         k_gd_finish<<<batch, kThreads, 0, s>>>(part_ent, part_lp, part_bad, nb, entropy, log_prob);
     return launch_status();
 }
 
-int tarl_graphdist_backward(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                            const void* action, int32_t action_dtype, const float* grad_log_prob,
-                            const float* grad_entropy, const float* log_prob, float* grad_logits, void* stream) {
+int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                            const tarl_rows* action, int32_t action_dtype, const float* grad_log_prob,
+                            const float* grad_entropy, const float* log_prob, const tarl_rows* grad_logits, void* stream) {
     int rc = check_csr(groups);
     if (rc != TARL_OK) return rc;
     if (batch < 0 || (action != nullptr && (action_dtype < 0 || action_dtype > 2))) return TARL_E_BADARG;
     if (batch == 0 || groups->n_edges == 0) return TARL_OK;
-    if (!logits || !grad_logits) return TARL_E_BADARG;
+    if (!logits || !logits->data || !grad_logits || !grad_logits->data) return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // edges whose source has no group cannot exist (every edge has a source), so every grad entry is written
-    dim3 grid(blocks_for(groups->n_rows), batch);
-    k_gd_backward<<<grid, kThreads, 0, s>>>(*groups, logits, temperature, groups->n_edges, action, action_dtype,
-                                            grad_log_prob, grad_entropy, log_prob, grad_logits);
+    // every edge has a source, hence a group: every grad entry is written
+    k_gd_backward<<<gd_grid(groups->n_rows, batch), kThreads, 0, s>>>(
+        *groups, data_of<const float>(logits), view_of(logits), temperature, batch, pow2_rows(batch),
+        data_of<const void>(action), view_of(action), action_dtype, grad_log_prob, grad_entropy, log_prob,
+        data_of<float>(grad_logits), view_of(grad_logits));
     return launch_status();
 }
 
-int tarl_graphdist_sample(const tarl_csr* groups, const float* logits, float temperature, int32_t batch,
-                          const float* uniforms, int64_t* onehot, void* stream) {
+int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
+                          const float* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, void* stream) {
     int rc = check_csr(groups);
     if (rc != TARL_OK) return rc;
-    if (batch < 0) return TARL_E_BADARG;
+    if (batch < 0 || (onehot_dtype != TARL_ACTION_U8 && onehot_dtype != TARL_ACTION_I64)) return TARL_E_BADARG;
     if (batch == 0 || groups->n_edges == 0) return TARL_OK;
-    if (!logits || !uniforms || !onehot) return TARL_E_BADARG;
+    if (!logits || !logits->data || !uniforms || !onehot || !onehot->data) return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (cudaMemsetAsync(onehot, 0, sizeof(int64_t) * (size_t)batch * groups->n_edges, s) != cudaSuccess)
-        return TARL_E_LAUNCH;
-    dim3 grid(blocks_for(groups->n_rows), batch);
-    k_gd_sample<<<grid, kThreads, 0, s>>>(*groups, logits, temperature, groups->n_edges, uniforms,
-                                          reinterpret_cast<long long*>(onehot));
+    const dim3 grid = gd_grid(groups->n_rows, batch);
+    if (onehot_dtype == TARL_ACTION_U8)
+        k_gd_sample<uint8_t><<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits), temperature,
+                                                       batch, pow2_rows(batch), uniforms, data_of<uint8_t>(onehot),
+                                                       view_of(onehot));
+    else
+        k_gd_sample<long long><<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits),
+                                                         temperature, batch, pow2_rows(batch), uniforms,
+                                                         data_of<long long>(onehot), view_of(onehot));
     return launch_status();
 }
 

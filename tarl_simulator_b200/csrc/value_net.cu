@@ -9,6 +9,9 @@
 // (proj[b,n] = w[0:16] · x[b,n]) instead of being gathered as [E,16] rows per edge as PyG does: per edge the kernels
 // read one 4-byte projected scalar + the edge feature. Every reduction has a fixed order (segment sums in ascending
 // edge id, per-block partials summed by a second kernel), so results are run-to-run deterministic.
+// Layout: proj / mean / v / gm are NODE-major with the batch row innermost (element (b, n) at n*B + b) and one thread
+// handles one (node, row) pair with the row innermost, so the B lanes of a node gather one contiguous B-vector per
+// neighbour and read the node's edge list once. edge_features may be broadcast over the batch (batch stride 0).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,7 +28,7 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK 
 
 struct Inputs {
     const float* nf; int64_t nf_bs, nf_rs;     // node_features [B,N,>=7]
-    const float* ef;                           // edge_features [B,E]
+    const float* ef; int64_t ef_bs;            // edge_features [B,E], batch stride in elements (0 = shared by all rows)
     const long long* ai;                       // agent_index [B,N]
     const float* af; int af_rows;              // agent_features [rows,9]
     int B, N, E;
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) k_value_project(Inputs in, const flo
                                                             float* __restrict__ proj, int32_t* __restrict__ flags) {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= (int64_t)in.B * in.N) return;
-    const int b = (int)(i / in.N), n = (int)(i % in.N);
+    const int n = (int)(i / in.B), b = (int)(i % in.B);
     float x[kIn];
     load_x(in, b, n, x, flags);
     float acc = 0.0f;
@@ -59,23 +62,22 @@ __global__ void __launch_bounds__(kThreads) k_value_project(Inputs in, const flo
     proj[i] = acc;
 }
 
-// one thread per (batch row, source node): segment mean of tanh messages in ascending edge id, then the node update
+// one thread per (source node, batch row): segment mean of tanh messages in ascending edge id, then the node update
 __global__ void __launch_bounds__(kThreads) k_value_aggregate(tarl_csr by_src, Inputs in, const float* __restrict__ w,
                                                               const float* __restrict__ w0, const float* __restrict__ a,
                                                               const float* __restrict__ c, const float* __restrict__ proj,
                                                               float* __restrict__ mean, float* __restrict__ v) {
-    const int n = blockIdx.x * kThreads + threadIdx.x;
-    if (n >= in.N) return;
-    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)in.B * in.N) return;
+    const int n = (int)(i / in.B), b = (int)(i % in.B);
     const float we = w[kIn], bias = w0[0];
-    const float* pj = proj + (int64_t)b * in.N;
-    const float* ef = in.ef + (int64_t)b * in.E;
+    const float* ef = in.ef + b * in.ef_bs;
     const int k0 = by_src.ptr[n], k1 = by_src.ptr[n + 1];
     float acc = 0.0f;
-    for (int k = k0; k < k1; ++k) acc += tanhf(pj[by_src.idx[k]] + we * ef[by_src.eid[k]] + bias);
+    for (int k = k0; k < k1; ++k) acc += tanhf(proj[(int64_t)by_src.idx[k] * in.B + b] + we * ef[by_src.eid[k]] + bias);
     const float m = k1 > k0 ? acc / (float)(k1 - k0) : 0.0f;
-    mean[(int64_t)b * in.N + n] = m;
-    v[(int64_t)b * in.N + n] = tanhf(a[0] * m + c[0]);
+    mean[i] = m;
+    v[i] = tanhf(a[0] * m + c[0]);
 }
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -101,47 +103,46 @@ __device__ __forceinline__ void block_store(float (&vals)[kCount], float* __rest
     }
 }
 
-// node update backward: dv = g_v (1 - v^2); partial sums of d a, d c; gm = dv * a / deg handed to the edge pass
+// node update backward: dv = g_v (1 - v^2); partial sums of d a, d c; gm = dv * a / deg handed to the edge pass.
+// grad_v: element (b, n) at b*gv_sb + n*gv_sn.
 __global__ void __launch_bounds__(kThreads) k_value_node_grad(tarl_csr by_src, int B, int N, const float* __restrict__ a,
                                                               const float* __restrict__ mean, const float* __restrict__ v,
-                                                              const float* __restrict__ gv, float* __restrict__ gm,
-                                                              float* __restrict__ partials) {
-    const int n = blockIdx.x * kThreads + threadIdx.x;
-    const int b = blockIdx.y;
+                                                              const float* __restrict__ gv, int64_t gv_sb, int64_t gv_sn,
+                                                              float* __restrict__ gm, float* __restrict__ partials) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     float vals[2] = {0.0f, 0.0f};
-    if (n < N) {
-        const int64_t i = (int64_t)b * N + n;
+    if (i < (int64_t)B * N) {
+        const int n = (int)(i / B), b = (int)(i % B);
         const float vv = v[i];
-        const float dv = gv[i] * (1.0f - vv * vv);
+        const float dv = gv[b * gv_sb + n * gv_sn] * (1.0f - vv * vv);
         vals[0] = dv * mean[i];
         vals[1] = dv;
         const int deg = by_src.ptr[n + 1] - by_src.ptr[n];
         gm[i] = deg > 0 ? dv * a[0] / (float)deg : 0.0f;
     }
-    block_store<2>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * kGrads + 18);
+    block_store<2>(vals, partials + (size_t)blockIdx.x * kGrads + 18);
 }
 
-// message backward, one thread per (batch row, TARGET node): every in-edge's message is recomputed from this node's
+// message backward, one thread per (TARGET node, batch row): every in-edge's message is recomputed from this node's
 // own projection; the 16 input-weight gradients need the node's x once, not once per edge.
 __global__ void __launch_bounds__(kThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, const float* __restrict__ w,
                                                               const float* __restrict__ w0, const float* __restrict__ proj,
                                                               const float* __restrict__ gm, float* __restrict__ partials) {
-    const int n = blockIdx.x * kThreads + threadIdx.x;
-    const int b = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     float vals[18];
 #pragma unroll
     for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
-    if (n < in.N) {
+    if (i < (int64_t)in.B * in.N) {
+        const int n = (int)(i / in.B), b = (int)(i % in.B);
         const float we = w[kIn], bias = w0[0];
-        const float pn = proj[(int64_t)b * in.N + n];
-        const float* ef = in.ef + (int64_t)b * in.E;
-        const float* g = gm + (int64_t)b * in.N;
+        const float pn = proj[i];
+        const float* ef = in.ef + b * in.ef_bs;
         float gs = 0.0f, gwe = 0.0f;
         const int k1 = by_dst.ptr[n + 1];
         for (int k = by_dst.ptr[n]; k < k1; ++k) {
             const float f = ef[by_dst.eid[k]];
             const float m = tanhf(pn + we * f + bias);
-            const float gz = g[by_dst.idx[k]] * (1.0f - m * m);
+            const float gz = gm[(int64_t)by_dst.idx[k] * in.B + b] * (1.0f - m * m);
             gs += gz;
             gwe += gz * f;
         }
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_value_edge_grad(tarl_csr by_dst, I
         vals[16] = gwe;
         vals[17] = gs;
     }
-    block_store<18>(vals, partials + ((size_t)b * gridDim.x + blockIdx.x) * kGrads);
+    block_store<18>(vals, partials + (size_t)blockIdx.x * kGrads);
 }
 
 // grads[j] = sum over all blocks of partials[.., j]: one CTA per j, strided accumulation then a fixed tree
@@ -185,14 +186,15 @@ int check(const tarl_csr* c, int n_nodes) {
 extern "C" {
 
 int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch) {
-    return (n_nodes > 0 && batch > 0) ? blocks_for(n_nodes) * batch : 0;
+    return (n_nodes > 0 && batch > 0) ? blocks_for((int64_t)n_nodes * batch) : 0;
 }
 
 int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
-                          int64_t nf_row_stride, const float* edge_features, const int64_t* agent_index,
-                          const float* agent_features, int32_t agent_rows, const float* msg_weight,
-                          const float* msg_bias, const float* node_weight, const float* node_bias, int32_t batch,
-                          int32_t n_nodes, float* proj, float* mean, float* v, int32_t* flags, void* stream) {
+                          int64_t nf_row_stride, const float* edge_features, int64_t ef_batch_stride,
+                          const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
+                          const float* msg_weight, const float* msg_bias, const float* node_weight,
+                          const float* node_bias, int32_t batch, int32_t n_nodes, float* proj, float* mean, float* v,
+                          int32_t* flags, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc != TARL_OK) return rc;
@@ -201,21 +203,22 @@ int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features,
         !proj || !mean || !v || !flags || (by_source->n_edges > 0 && !edge_features))
         return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features,
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
-    k_value_project<<<blocks_for((int64_t)batch * n_nodes), kThreads, 0, s>>>(in, msg_weight, proj, flags);
-    k_value_aggregate<<<dim3(blocks_for(n_nodes), batch), kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias,
-                                                                            node_weight, node_bias, proj, mean, v);
+    const int nb = blocks_for((int64_t)batch * n_nodes);
+    k_value_project<<<nb, kThreads, 0, s>>>(in, msg_weight, proj, flags);
+    k_value_aggregate<<<nb, kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
     return launch_status();
 }
 
 int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
                            int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
-                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
-                           const float* msg_weight, const float* msg_bias, const float* node_weight, int32_t batch,
-                           int32_t n_nodes, const float* proj, const float* mean, const float* v, const float* grad_v,
-                           float* gm, float* partials, float* grads, void* stream) {
+                           int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                           int32_t agent_rows, const float* msg_weight, const float* msg_bias, const float* node_weight,
+                           int32_t batch, int32_t n_nodes, const float* proj, const float* mean, const float* v,
+                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, float* gm,
+                           float* partials, float* grads, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc == TARL_OK) rc = check(by_target, n_nodes);
@@ -227,13 +230,14 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
     if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !proj ||
         !mean || !v || !grad_v || !gm || !partials || (by_source->n_edges > 0 && !edge_features))
         return TARL_E_BADARG;
-    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features,
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
-    const dim3 grid(blocks_for(n_nodes), batch);
-    k_value_node_grad<<<grid, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, mean, v, grad_v, gm, partials);
-    k_value_edge_grad<<<grid, kThreads, 0, s>>>(*by_target, in, msg_weight, msg_bias, proj, gm, partials);
-    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
+    const int nb = blocks_for((int64_t)batch * n_nodes);
+    k_value_node_grad<<<nb, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, mean, v, grad_v, gv_batch_stride,
+                                              gv_node_stride, gm, partials);
+    k_value_edge_grad<<<nb, kThreads, 0, s>>>(*by_target, in, msg_weight, msg_bias, proj, gm, partials);
+    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, nb, grads);
     return launch_status();
 }
 

@@ -24,35 +24,40 @@ def _stream(device):
 
 
 def _action_arg(action: torch.Tensor, B: int, E: int):
+    """[B, E] view of the action in a dtype the kernels read directly (no copy for bool / uint8 / int64 / fp32)."""
     a = action.reshape(B, E)
     if a.dtype == torch.bool:
-        a, code = a.contiguous().view(torch.uint8), _cabi.ACTION_U8
-    elif a.dtype == torch.uint8:
-        a, code = a.contiguous(), _cabi.ACTION_U8
-    elif a.dtype == torch.int64:
-        a, code = a.contiguous(), _cabi.ACTION_I64
-    else:
-        a, code = a.to(torch.float32).contiguous(), _cabi.ACTION_F32
-    return a, code
+        return a.view(torch.uint8), _cabi.ACTION_U8
+    if a.dtype == torch.uint8:
+        return a, _cabi.ACTION_U8
+    if a.dtype == torch.int64:
+        return a, _cabi.ACTION_I64
+    return a.to(torch.float32), _cabi.ACTION_F32
+
+
+def _edge_major(B: int, E: int, dtype, device, zero: bool = False):
+    """A [B, E] tensor whose memory is edge-major (strides (1, B))."""
+    buf = (torch.zeros if zero else torch.empty)(E, B, dtype=dtype, device=device)
+    return buf.t()
 
 
 class _LogProbEntropy(torch.autograd.Function):
-    """(log_prob [B], entropy [B]) of logits [B,E]; `action` may be None (entropy only)."""
+    """(log_prob [B], entropy [B]) of logits [B,E] (any strides); `action` may be None (entropy only)."""
 
     @staticmethod
     def forward(ctx, logits, action, groups, temperature):
         B, E = logits.shape
         dev = logits.device
         lib = _cabi.lib()
-        nb = lib.tarl_graphdist_partial_count(groups.n_rows)
+        nb = lib.tarl_graphdist_partial_count(groups.n_rows, B)
         partials = torch.empty(max(3 * B * nb, 1), dtype=torch.float32, device=dev)
         ent = torch.empty(B, dtype=torch.float32, device=dev)
         lp = torch.empty(B, dtype=torch.float32, device=dev) if action is not None else None
         a, code = _action_arg(action, B, E) if action is not None else (None, 0)
         with torch.cuda.device(dev):
-            rc = lib.tarl_graphdist_forward(groups.ref(), logits.data_ptr(), temperature, B,
-                                            a.data_ptr() if a is not None else None, code, None, None, ent.data_ptr(),
-                                            lp.data_ptr() if lp is not None else None, partials.data_ptr(), _stream(dev))
+            rc = lib.tarl_graphdist_forward(groups.ref(), _cabi.rows(logits), temperature, B, _cabi.rows(a), code, None,
+                                            None, ent.data_ptr(), lp.data_ptr() if lp is not None else None,
+                                            partials.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_graphdist_forward")
         ctx.groups, ctx.temperature, ctx.code = groups, temperature, code
         ctx.save_for_backward(logits, a, lp)
@@ -66,15 +71,14 @@ class _LogProbEntropy(torch.autograd.Function):
         logits, a, lp = ctx.saved_tensors
         B, E = logits.shape
         dev = logits.device
-        grad = torch.empty_like(logits)
+        grad = _edge_major(B, E, torch.float32, dev) if (B > 1 and logits.stride(0) == 1) else torch.empty_like(logits)
         g_lp = g_lp.contiguous() if (g_lp is not None and a is not None) else None
         g_ent = g_ent.contiguous() if g_ent is not None else None
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_graphdist_backward(
-                ctx.groups.ref(), logits.data_ptr(), ctx.temperature, B, a.data_ptr() if a is not None else None,
-                ctx.code, g_lp.data_ptr() if g_lp is not None else None,
-                g_ent.data_ptr() if g_ent is not None else None, lp.data_ptr() if lp is not None else None,
-                grad.data_ptr(), _stream(dev))
+                ctx.groups.ref(), _cabi.rows(logits), ctx.temperature, B, _cabi.rows(a), ctx.code,
+                g_lp.data_ptr() if g_lp is not None else None, g_ent.data_ptr() if g_ent is not None else None,
+                lp.data_ptr() if lp is not None else None, _cabi.rows(grad), _stream(dev))
         _cabi.check(rc, "tarl_graphdist_backward")
         return grad, None, None, None
 
@@ -93,7 +97,7 @@ class GraphDistribution(Distribution):
         self.temperature = float(temperature)
         self._lead = logits.shape[:-1]
         self._E = logits.size(-1)
-        self._logits = logits.to(torch.float32).reshape(-1, self._E).contiguous()
+        self._logits = logits.to(torch.float32).reshape(-1, self._E)       # any strides: edge-major stays edge-major
         self._groups = group_csr_for(edge_index, "source_rank")
         self.nodes = self._groups.nodes
         self.nb_nodes = self._groups.n_rows
@@ -104,13 +108,14 @@ class GraphDistribution(Distribution):
         B, E = self._logits.shape
         dev = self._logits.device
         lg = self._logits.detach()
-        proba = torch.empty(B, E, dtype=torch.float32, device=dev) if want_proba else None
-        mode = torch.empty(B, E, dtype=torch.float32, device=dev) if want_mode else None
+        em = B > 1 and lg.stride(0) == 1
+        make = (lambda zero: _edge_major(B, E, torch.float32, dev, zero)) if em else \
+            (lambda zero: (torch.zeros if zero else torch.empty)(B, E, dtype=torch.float32, device=dev))
+        proba = make(False) if want_proba else None
+        mode = make(True) if want_mode else None
         with torch.cuda.device(dev):
-            rc = _cabi.lib().tarl_graphdist_forward(
-                self._groups.ref(), lg.data_ptr(), self.temperature, B, None, 0,
-                proba.data_ptr() if proba is not None else None, mode.data_ptr() if mode is not None else None,
-                None, None, None, _stream(dev))
+            rc = _cabi.lib().tarl_graphdist_forward(self._groups.ref(), _cabi.rows(lg), self.temperature, B, None, 0,
+                                                    _cabi.rows(proba), _cabi.rows(mode), None, None, None, _stream(dev))
         _cabi.check(rc, "tarl_graphdist_forward")
         if proba is not None:
             self._cache["proba"] = proba.reshape(*self._lead, E)
@@ -137,26 +142,35 @@ class GraphDistribution(Distribution):
         return self.mode
 
     # -- Distribution API ------------------------------------------------------------------------------------
-    def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None):
-        """One-hot int64 [sample_shape.., .., E]: inverse CDF with one uniform per (row, source group) (:57-80).
-        `uniforms` ([.., K]) injects the noise the reference draws with torch.rand."""
+    def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None, dtype=torch.int64):
+        """One-hot [sample_shape.., .., E]: inverse CDF with one uniform per (row, source group) (:57-80). int64 like
+        the reference by default; dtype=torch.bool writes one byte per edge instead of eight. `uniforms` ([.., K])
+        injects the noise the reference draws with torch.rand."""
         sample_shape = torch.Size(sample_shape)
         B, E = self._logits.shape
         dev = self._logits.device
         S = int(torch.Size(sample_shape).numel()) if len(sample_shape) else 1
         lg = self._logits.detach()
         if S > 1:
-            lg = lg.unsqueeze(0).expand(S, B, E).reshape(S * B, E).contiguous()
+            lg = lg.unsqueeze(0).expand(S, B, E).reshape(S * B, E)
         rows = S * B
         if uniforms is None:
             u = torch.rand(rows, self.nb_nodes, dtype=torch.float32, device=dev)
         else:
             u = uniforms.to(device=dev, dtype=torch.float32).reshape(rows, self.nb_nodes).contiguous()
-        out = torch.empty(rows, E, dtype=torch.int64, device=dev)
+        if dtype not in (torch.int64, torch.bool, torch.uint8):
+            raise ValueError("sample dtype must be int64, bool or uint8")
+        store = torch.int64 if dtype == torch.int64 else torch.uint8
+        em = rows > 1 and lg.stride(0) == 1 and len(self._lead) <= 1 and S == 1
+        out = _edge_major(rows, E, store, dev, zero=True) if em else torch.zeros(rows, E, dtype=store, device=dev)
         with torch.cuda.device(dev):
-            rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), lg.data_ptr(), self.temperature, rows,
-                                                   u.data_ptr(), out.data_ptr(), _stream(dev))
+            rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), _cabi.rows(lg), self.temperature, rows,
+                                                   u.data_ptr(), _cabi.rows(out),
+                                                   _cabi.ACTION_I64 if store == torch.int64 else _cabi.ACTION_U8,
+                                                   _stream(dev))
         _cabi.check(rc, "tarl_graphdist_sample")
+        if dtype == torch.bool:
+            out = out.view(torch.bool)
         return out.reshape(*sample_shape, *self._lead, E)
 
     def _lp_ent(self, action):

@@ -27,7 +27,10 @@ def _stream(device):
 
 
 class _PolicyEmbed(torch.autograd.Function):
-    """logits[b,e] = W[idx(b, dst[e])]  with idx(b,n) = ROAD_INDEX(b,n) if >= 0 else n."""
+    """logits[b,e] = W[idx(b, dst[e])]  with idx(b,n) = ROAD_INDEX(b,n) if >= 0 else n.
+
+    The result has shape [B, E] but EDGE-major memory (strides (1, B)): the B rows of one edge are contiguous, which
+    is what the GraphDistribution kernels read fastest. Consumers that need row-major memory call .contiguous()."""
 
     @staticmethod
     def forward(ctx, weight, node_features, dst32, by_target, flags):
@@ -35,9 +38,9 @@ class _PolicyEmbed(torch.autograd.Function):
         E = dst32.numel()
         dev = weight.device
         w = weight.detach().reshape(-1).contiguous()
-        node_emb = torch.empty(B, N, dtype=torch.float32, device=dev)
-        node_idx = torch.empty(B, N, dtype=torch.int32, device=dev)
-        logits = torch.empty(B, E, dtype=torch.float32, device=dev)
+        node_emb = torch.empty(N, B, dtype=torch.float32, device=dev)
+        node_idx = torch.empty(N, B, dtype=torch.int32, device=dev)
+        logits = torch.empty(E, B, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_policy_embed_forward(
                 w.data_ptr(), w.numel(), node_features.data_ptr(), node_features.stride(0), node_features.stride(1),
@@ -46,19 +49,18 @@ class _PolicyEmbed(torch.autograd.Function):
         _cabi.check(rc, "tarl_policy_embed_forward")
         ctx.by_target, ctx.rows, ctx.wshape = by_target, w.numel(), weight.shape
         ctx.save_for_backward(node_idx)
-        return logits
+        return logits.t()
 
     @staticmethod
     def backward(ctx, grad_logits):
         (node_idx,) = ctx.saved_tensors
-        B, N = node_idx.shape
+        N, B = node_idx.shape
         dev = grad_logits.device
-        g = grad_logits.contiguous()
-        node_grad = torch.empty(B, N, dtype=torch.float32, device=dev)
+        node_grad = torch.empty(N, B, dtype=torch.float32, device=dev)
         gw = torch.empty(ctx.rows, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = _cabi.lib().tarl_policy_embed_backward(ctx.by_target.ref(), g.data_ptr(), node_idx.data_ptr(), B,
-                                                        node_grad.data_ptr(), gw.data_ptr(), ctx.rows, _stream(dev))
+            rc = _cabi.lib().tarl_policy_embed_backward(ctx.by_target.ref(), _cabi.rows(grad_logits), node_idx.data_ptr(),
+                                                        B, node_grad.data_ptr(), gw.data_ptr(), ctx.rows, _stream(dev))
         _cabi.check(rc, "tarl_policy_embed_backward")
         return gw.reshape(ctx.wshape), None, None, None, None
 
@@ -128,7 +130,7 @@ class MPNNPolicyNet(MessagePassing, Agents):
         by_target = group_csr_for(self._ei_dev, "target", self.num_nodes)
         self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=nf.device)
         logits = _PolicyEmbed.apply(self.nodes_embedding.weight, nf, self._dst32, by_target, self._flags)
-        return logits if batched else logits.view(self.num_edges)
+        return logits if batched else logits.reshape(self.num_edges)
 
     def check_errors(self):
         if self._flags is not None:
@@ -138,26 +140,29 @@ class MPNNPolicyNet(MessagePassing, Agents):
 
 
 class _ValueMessagePassing(torch.autograd.Function):
-    """v [B,N] = update(mean-aggregate(message)) of MPNNValueNet; gradients w.r.t. the four parameter tensors."""
+    """v [B,N] = update(mean-aggregate(message)) of MPNNValueNet; gradients w.r.t. the four parameter tensors.
+    ef: [B,E] (a batch stride of 0 — an expanded edge_attr — is passed through, not materialised). The result has
+    shape [B,N] over node-major memory (strides (1, B))."""
 
     @staticmethod
     def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags):
         B, N, _ = nf.shape
         dev = nf.device
-        proj = torch.empty(B, N, dtype=torch.float32, device=dev)
-        mean = torch.empty(B, N, dtype=torch.float32, device=dev)
-        v = torch.empty(B, N, dtype=torch.float32, device=dev)
+        proj = torch.empty(N, B, dtype=torch.float32, device=dev)
+        mean = torch.empty(N, B, dtype=torch.float32, device=dev)
+        v = torch.empty(N, B, dtype=torch.float32, device=dev)
         pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
+        ef_bs = ef.stride(0) if B > 1 else 0
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_value_mp_forward(
-                by_source.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ai.data_ptr(), af.data_ptr(),
-                af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N, proj.data_ptr(),
-                mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+                by_source.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs, ai.data_ptr(),
+                af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
+                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_forward")
-        ctx.by_source, ctx.by_target = by_source, by_target
+        ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
         ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
         ctx.save_for_backward(pw, pb, nw, nf, ef, ai, af, proj, mean, v)
-        return v
+        return v.t()
 
     @staticmethod
     def backward(ctx, grad_v):
@@ -165,16 +170,15 @@ class _ValueMessagePassing(torch.autograd.Function):
         B, N, _ = nf.shape
         dev = nf.device
         lib = _cabi.lib()
-        gv = grad_v.contiguous()
-        gm = torch.empty(B, N, dtype=torch.float32, device=dev)
+        gm = torch.empty(N, B, dtype=torch.float32, device=dev)
         partials = torch.empty(max(20 * lib.tarl_value_mp_partial_count(N, B), 1), dtype=torch.float32, device=dev)
         grads = torch.empty(20, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = lib.tarl_value_mp_backward(
                 ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
-                ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), B, N,
-                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), gv.data_ptr(), gm.data_ptr(), partials.data_ptr(),
-                grads.data_ptr(), _stream(dev))
+                ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), B, N,
+                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
+                grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_backward")
         s = ctx.shapes
         return (grads[:17].reshape(s[0]), grads[17:18].reshape(s[1]), grads[18:19].reshape(s[2]),
@@ -221,7 +225,10 @@ class MPNNValueNet(MessagePassing, Agents):
         if nf.stride(2) != 1:
             nf = nf.contiguous()
         B, N = nf.size(0), nf.size(1)
-        ef = (edge_features if batched else edge_features.unsqueeze(0)).to(torch.float32).reshape(B, -1).contiguous()
+        ef = (edge_features if batched else edge_features.unsqueeze(0)).to(torch.float32)
+        ef = ef.squeeze(-1) if ef.dim() == 3 else ef
+        if ef.stride(-1) != 1 or (B > 1 and ef.stride(0) not in (0, ef.size(1))):
+            ef = ef.contiguous()
         ai = (agent_index if batched else agent_index.unsqueeze(0)).to(torch.int64).contiguous()
         af = self.agent_features.to(device=nf.device, dtype=torch.float32).contiguous()
         if self._ei_dev is None or self._ei_dev.device != nf.device:
@@ -233,7 +240,7 @@ class MPNNValueNet(MessagePassing, Agents):
         v = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
                                        by_target, self._flags)
         if not batched:
-            v = v.view(self.num_nodes)
+            v = v.reshape(self.num_nodes)
         return self.final_mlp(torch.cat((v, self.time_net(time)), dim=-1))
 
     def check_errors(self):

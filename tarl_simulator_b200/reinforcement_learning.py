@@ -159,7 +159,7 @@ class SimulatorEnv:
         """A uniformly random valid action: one out-edge per source node."""
         from .distribution import GraphDistribution
         logits = torch.zeros(self.num_edge, device=self.simulator.graph.x.device)
-        return GraphDistribution(logits, self.simulator.graph.edge_index).sample().to(torch.bool)
+        return GraphDistribution(logits, self.simulator.graph.edge_index).sample(dtype=torch.bool)
 
 
 class BatchedSimulatorEnv:

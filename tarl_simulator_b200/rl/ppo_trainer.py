@@ -47,7 +47,7 @@ class PolicyModule(nn.Module):
 
     def forward(self, obs, mode: bool = False):
         d = self.dist(obs)
-        action = (d.mode if mode else d.sample()).to(torch.bool)
+        action = d.mode.to(torch.bool) if mode else d.sample(dtype=torch.bool)
         out = {"action": action}
         if self.return_log_prob:
             out["sample_log_prob"] = d.log_prob(action).detach()
