@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=8, help="oracle steps timed for cpu_baseline (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpnn", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-replicas", type=int, default=1024, help="environment replicas in total (sharded over ranks)")
+    ap.add_argument("--ppo-steps", type=int, default=8, help="rollout steps per PPO iteration in the ppo section")
     ap.add_argument("--mpnn-batch", type=int, default=32, help="batch rows (frames) of the MPNN fwd+bwd measurement")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])
@@ -329,6 +332,8 @@ def run_native(args):
     if not args.no_mpnn:
         out["mpnn"] = mpnn_bench(args, g, dev, world, rank, peak)
         out["gpu_launches"] += out["mpnn"].pop("_launches_in_headline", 0)
+    if not args.no_ppo:
+        out["ppo"] = ppo_bench(args, dev, world, rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
         if "mpnn" in out:
@@ -420,6 +425,70 @@ def mpnn_bench(args, g, dev, world, rank, peak):
                           "roofline": {"bound": "hbm", "algorithmic_bytes": int(val_bytes),
                                        "achieved": round(val_bytes / (val_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                        "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}}}
+
+
+def ppo_bench(args, dev, world, rank):
+    """BASELINE.json configs[4]: PPO on the 100x100 grid with `--ppo-replicas` environment replicas sharded over the
+    ranks (strong scaling: the total is fixed), one gradient all-reduce per optimiser step over NCCL. Reports rollout
+    throughput (environment steps/s and link-steps/s through the whole _step: action, core, withdraw, insert, reward,
+    plus policy forward + sampling) and the time of one update. Timed on the device, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNetSimple
+    from tarl_simulator_b200.parallel import shard_replicas
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, collect, ppo_train
+
+    total = max(args.ppo_replicas, world)
+    first, R = shard_replicas(total, world, rank)
+    frm, to, n_nodes = synthetic.grid_links(100, device=dev)
+    frm, to = synthetic.reorder_links(frm, to, "node")
+    g, Nmax = synthetic.build_graph(frm, to, n_nodes)
+    af = synthetic.population(g, 100_000, 21540, 600, seed=7)
+    env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=100 + first)
+    N, N_tot, E_full = int(g.num_roads), g.x.size(0), g.edge_index.size(1)
+    torch.manual_seed(0)                                   # identical initial parameters on every rank
+    policy = MPNNPolicyNet(g.edge_index, N_tot, None, str(dev))
+    value = MPNNValueNetSimple(g.edge_index, N_tot, str(dev))
+    pm, vm = PolicyModule(policy, g.edge_index), ValueModule(value)
+    adapter = _EnvAdapter(env)
+    T = args.ppo_steps
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    ppo_train(env, pm, vm, total_frames=2, frames_per_batch=2, num_epochs=1, sub_batch_size=32)   # warm-up: optimiser
+    collect(adapter, pm, T)                               # state, CSR builds, allocator, kernels
+    roll_ms = timed(lambda: collect(adapter, pm, T))
+    hist = []
+    train_ms = timed(lambda: ppo_train(env, pm, vm, total_frames=T, frames_per_batch=T, num_epochs=1, sub_batch_size=32,
+                                       history=hist))
+    env.check_errors()
+    n_params = sum(p.numel() for p in list(policy.parameters()) + list(value.parameters()) if p.requires_grad)
+    return {"workload": "grid100 (39 600 links, 100 000 agents per replica), PPO as wired by the reference",
+            "replicas_total": total, "replicas_per_gpu": R, "rollout_steps": T, "scaling": "strong",
+            "rollout_ms": round(roll_ms, 2), "env_steps_per_s": round(total * T / (roll_ms / 1e3), 1),
+            "link_steps_per_s": round(total * T * N / (roll_ms / 1e3), 1),
+            "iteration_ms": round(train_ms, 2), "update_ms": round(max(train_ms - roll_ms, 0.0), 2),
+            "allreduce_bytes_per_update": 4 * n_params if world > 1 else 0,
+            "inserted_agents_per_replica": float(env.counters[:, 0].float().mean()),
+            "what": "rollout = policy forward + sample + env step (action, core step, withdraw, insert, reward) for every "
+                    "replica; iteration = rollout + GAE + one clipped-PPO minibatch step (32 frames) + gradient all-reduce"}
 
 
 def mpnn_cpu_baseline(args):

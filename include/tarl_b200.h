@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 6
+#define TARL_ABI_VERSION 7
 
 /* return codes */
 #define TARL_OK 0
@@ -342,9 +342,10 @@ int tarl_agents_choice(const tarl_agent_state* state, const tarl_csr* neighbours
                        int32_t n_choosers, const float* uniforms, uint64_t seed, uint32_t step_id, void* stream);
 
 /* Replaces the action write of SimulatorEnv._step (src/reinforcement_learning.py:223-231):
- * SELECTED_ROAD[edge_src[e]] = edge_dst[e] for every e of the FULL graph with action[r, e] != 0. */
+ * SELECTED_ROAD[edge_src[e]] = edge_dst[e] for every e of the FULL graph with action[r, e] != 0. action: [R, E_full]
+ * with any strides (what GraphDistribution.sample returns is edge-major). */
 int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_src, const int32_t* edge_dst,
-                             int32_t n_edges, const void* action, int32_t action_dtype, void* stream);
+                             int32_t n_edges, const tarl_rows* action, int32_t action_dtype, void* stream);
 
 /* state() (src/transportation_simulator.py:360-366) and the reward term of SimulatorEnv._step
  * (src/reinforcement_learning.py:266) from a link store: node_features [R, n_nodes, 7] = {MAXN, NUM, FFTT, LENGTH,

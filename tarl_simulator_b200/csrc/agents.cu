@@ -280,20 +280,24 @@ __global__ void __launch_bounds__(kThreads) k_choice(Acc acc, tarl_csr nbr, cons
 }
 
 // RL action: x[edge_index[0][e], SELECTED_ROAD] = edge_index[1][e] for every selected edge of the FULL graph
-// (reinforcement_learning.py:223-231). action: [R, E_full] one-hot per source group.
+// (reinforcement_learning.py:223-231). action: [R, E_full] one-hot per source group, any strides; the thread order
+// follows the action's memory order (replica innermost for an edge-major action) so that its bytes are read coalesced.
 template <class Acc>
 __global__ void __launch_bounds__(kThreads) k_apply_action(Acc acc, const int32_t* __restrict__ src,
-                                                           const int32_t* __restrict__ dst, int E,
-                                                           const void* __restrict__ action, int action_dtype) {
-    const int e = blockIdx.x * kThreads + threadIdx.x;
-    if (e >= E) return;
-    const int r = blockIdx.y;
-    const size_t i = (size_t)r * E + e;
+                                                           const int32_t* __restrict__ dst, int E, int R,
+                                                           const void* __restrict__ action, int64_t a_sr, int64_t a_se,
+                                                           int action_dtype, bool replica_innermost) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)E * R) return;
+    int e, r;
+    if (replica_innermost) { e = (int)(i / R); r = (int)(i - (int64_t)e * R); }
+    else { r = (int)(i / E); e = (int)(i - (int64_t)r * E); }
+    const int64_t o = r * a_sr + e * a_se;
     bool on;
     switch (action_dtype) {
-        case TARL_ACTION_U8: on = static_cast<const uint8_t*>(action)[i] != 0; break;
-        case TARL_ACTION_I64: on = static_cast<const long long*>(action)[i] != 0; break;
-        default: on = static_cast<const float*>(action)[i] != 0.0f; break;
+        case TARL_ACTION_U8: on = static_cast<const uint8_t*>(action)[o] != 0; break;
+        case TARL_ACTION_I64: on = static_cast<const long long*>(action)[o] != 0; break;
+        default: on = static_cast<const float*>(action)[o] != 0.0f; break;
     }
     if (on) acc.set_sel(r, src[e], (float)dst[e]);
 }
@@ -425,17 +429,22 @@ int tarl_agents_choice(const tarl_agent_state* state, const tarl_csr* neighbours
 }
 
 int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_src, const int32_t* edge_dst,
-                             int32_t n_edges, const void* action, int32_t action_dtype, void* stream) {
+                             int32_t n_edges, const tarl_rows* action, int32_t action_dtype, void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
     if (n_edges < 0 || action_dtype < 0 || action_dtype > 2) return TARL_E_BADARG;
     if (n_edges == 0) return TARL_OK;
-    if (!edge_src || !edge_dst || !action) return TARL_E_BADARG;
+    if (!edge_src || !edge_dst || !action || !action->data) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    const dim3 grid(blocks_for(n_edges), R);
-    if (is_store) k_apply_action<<<grid, kThreads, 0, cs>>>(sto, edge_src, edge_dst, n_edges, action, action_dtype);
-    else k_apply_action<<<grid, kThreads, 0, cs>>>(row, edge_src, edge_dst, n_edges, action, action_dtype);
+    const int grid = blocks_for((int64_t)n_edges * R);
+    const bool rin = R > 1 && action->row_stride == 1;
+    if (is_store)
+        k_apply_action<<<grid, kThreads, 0, cs>>>(sto, edge_src, edge_dst, n_edges, R, action->data, action->row_stride,
+                                                  action->col_stride, action_dtype, rin);
+    else
+        k_apply_action<<<grid, kThreads, 0, cs>>>(row, edge_src, edge_dst, n_edges, R, action->data, action->row_stride,
+                                                  action->col_stride, action_dtype, rin);
     return launch_status();
 }
 

@@ -72,6 +72,7 @@ class MPNNPolicyNet(MessagePassing, Agents):
     reference at this commit — no forward path uses them."""
 
     h = ObservationFeatureHelpers()
+    reads_dynamic_features = False      # the active path only reads the (static) ROAD_INDEX column of node_features
 
     def __init__(self, edge_index, num_nodes, free_flow_time_travel, device):
         Agents.__init__(self, device=device)
@@ -269,3 +270,7 @@ class MPNNValueNetSimple(MessagePassing, Agents):
     def forward(self, node_features, edge_features, agent_index, time):
         x = torch.cat((node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time), dim=-1)
         return self.final_mlp(x)
+
+    def forward_occupancy(self, num_agents, time):
+        """The same function of the only observation column it reads: num_agents [.., N_tot] = NUMBER_OF_AGENT."""
+        return self.final_mlp(torch.cat((num_agents, time), dim=-1))

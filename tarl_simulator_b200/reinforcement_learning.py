@@ -36,13 +36,14 @@ def _stream(device) -> C.c_void_p:
 
 
 def _action_code(action: torch.Tensor):
+    """2-D [R, E] view of the action (any strides) in a dtype the kernel reads directly."""
     if action.dtype == torch.bool:
-        return action.contiguous().view(torch.uint8), _cabi.ACTION_U8
+        return action.view(torch.uint8), _cabi.ACTION_U8
     if action.dtype == torch.uint8:
-        return action.contiguous(), _cabi.ACTION_U8
+        return action, _cabi.ACTION_U8
     if action.dtype == torch.int64:
-        return action.contiguous(), _cabi.ACTION_I64
-    return action.to(torch.float32).contiguous(), _cabi.ACTION_F32
+        return action, _cabi.ACTION_I64
+    return action.to(torch.float32), _cabi.ACTION_F32
 
 
 class SimulatorEnv:
@@ -104,13 +105,13 @@ class SimulatorEnv:
         sim, h = self.simulator, self.simulator.h
         g = sim.graph
         dev = g.x.device
-        action, code = _action_code(tensordict["action"].to(dev).reshape(-1))
+        action, code = _action_code(tensordict["action"].to(dev).reshape(1, -1))
         side = side_tables_for(g)
         b = _time.time()
         st = rows_state(g, h.Nmax, with_cc=False)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_apply_action(C.byref(st), side.src32.data_ptr(), side.dst32.data_ptr(),
-                                                      self.num_edge, action.data_ptr(), code, _stream(dev))
+                                                      self.num_edge, _cabi.rows(action), code, _stream(dev))
         _cabi.check(rc, "tarl_agents_apply_action")
         e = _time.time(); sim.choice_time += e - b; b = e
         sim.graph = sim.model_core(g) if self.noise is None else sim.model_core(g, noise=self.noise)
@@ -226,7 +227,7 @@ class BatchedSimulatorEnv:
         st = self._state()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_agents_apply_action(C.byref(st), self.side.src32.data_ptr(),
-                                                      self.side.dst32.data_ptr(), self.E_full, a.data_ptr(), code,
+                                                      self.side.dst32.data_ptr(), self.E_full, _cabi.rows(a), code,
                                                       _stream(self.device))
         _cabi.check(rc, "tarl_agents_apply_action")
 
@@ -288,6 +289,18 @@ class BatchedSimulatorEnv:
 
     def num_agents(self) -> torch.Tensor:
         return self.store.num_agents()
+
+    def compact_state(self):
+        """The dynamic observation columns without materialising [R, N_tot, 7]: (NUMBER_OF_AGENT [R, N_tot],
+        SELECTED_ROAD [R, N_tot], head agent id int64 [R, N_tot]); plain copies out of the store's arrays."""
+        R, N, M = self.R, self.N, self.n_nodes
+        hot = self.store.hot[self.store.cur][: R * N].view(R, N, 8)
+        num = torch.zeros(R, M, dtype=torch.float32, device=self.device)
+        num[:, :N] = hot[:, :, 2]
+        head = torch.zeros(R, M, dtype=torch.int64, device=self.device)
+        head[:, :N] = hot[:, :, 0]
+        sel = torch.cat((self.store.sel[: R * N].view(R, N), self.src_sel), dim=1)
+        return num, sel, head
 
     def export_x(self) -> torch.Tensor:
         """The full node table [R, N_tot, F] exactly as the reference would hold it."""

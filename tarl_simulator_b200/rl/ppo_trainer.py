@@ -155,8 +155,7 @@ class _EnvAdapter:
     def dynamic(self):
         """(NUM [R, N_tot], SELECTED_ROAD [R, N_tot], head agent id [R, N_tot]) of the current state."""
         if self.batched:
-            nf, ai = self.env.observe(node_features=True, agent_index=True)
-            return nf[..., OBS.NUMBER_OF_AGENT], nf[..., OBS.SELECTED_ROAD], ai
+            return self.env.compact_state()
         x, _, _, ai = self.env.simulator.state()
         return x[:, OBS.NUMBER_OF_AGENT].unsqueeze(0).clone(), x[:, OBS.SELECTED_ROAD].unsqueeze(0).clone(), ai.unsqueeze(0)
 
@@ -168,12 +167,17 @@ class _EnvAdapter:
         out = self.env._step({"action": action[0]})
         return out["reward"].reshape(1).to(torch.float32), out["done"].reshape(1).to(self.device)
 
-    def observation(self, num, sel, agent_index, time):
-        """Observation dict with a leading batch dimension from compact dynamic columns. time: [B] tensor."""
+    def observation(self, num, sel, agent_index, time, dynamic: bool = True):
+        """Observation dict with a leading batch dimension from compact dynamic columns. time: [B] tensor.
+        dynamic=False (for consumers that only read static columns, e.g. MPNNPolicyNet's ROAD_INDEX) hands out the
+        static template expanded over the batch (stride 0) instead of materialising [B, N_tot, 7]."""
         B = num.size(0)
-        nf = self.static.unsqueeze(0).repeat(B, 1, 1)
-        nf[..., OBS.NUMBER_OF_AGENT] = num
-        nf[..., OBS.SELECTED_ROAD] = sel
+        if not dynamic:
+            nf = self.static.unsqueeze(0).expand(B, -1, -1)
+        else:
+            nf = self.static.unsqueeze(0).repeat(B, 1, 1)
+            nf[..., OBS.NUMBER_OF_AGENT] = num
+            nf[..., OBS.SELECTED_ROAD] = sel
         return {"node_features": nf, "edge_features": self.edge_features.unsqueeze(0).expand(B, -1, -1),
                 "agent_index": agent_index, "time": time.reshape(B, 1).to(torch.float32)}
 
@@ -188,9 +192,10 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
             "next_agent_index", "next_time")
     buf = {k: [] for k in keys}
     num, sel, ai = adapter.dynamic()
+    dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
     for _ in range(frames):
         t = torch.full((adapter.R,), adapter.time(), device=adapter.device)
-        obs = adapter.observation(num, sel, ai, t)
+        obs = adapter.observation(num, sel, ai, t, dynamic=dynamic)
         act = policy_module(obs, mode=mode)
         reward, done = adapter.step(act["action"])
         nnum, nsel, nai = adapter.dynamic()
@@ -205,10 +210,19 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
 
 
 def _values(adapter, value_module, batch, prefix=""):
+    """V(s) for every frame of the batch, one time step (R frames) at a time to bound the transient memory."""
     T, R = batch["num"].shape[:2]
-    flat = lambda k: batch[prefix + k].reshape(T * R, *batch[prefix + k].shape[2:])
-    obs = adapter.observation(flat("num"), flat("sel"), flat("agent_index"), flat("time"))
-    return value_module(obs).reshape(T, R)
+    fast = getattr(value_module.net, "forward_occupancy", None)
+    out = []
+    for t in range(T):
+        time = batch[prefix + "time"][t].reshape(R, 1).to(torch.float32)
+        if fast is not None:
+            out.append(fast(batch[prefix + "num"][t], time).reshape(R))
+        else:
+            obs = adapter.observation(batch[prefix + "num"][t], batch[prefix + "sel"][t], batch[prefix + "agent_index"][t],
+                                      batch[prefix + "time"][t])
+            out.append(value_module(obs).reshape(R))
+    return torch.stack(out)
 
 
 def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_batch=32, num_epochs=1,
@@ -270,7 +284,7 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
         rec = {"iteration": it, "global_step": global_step, "frames": T * R, "rollout_s": round(rollout_s, 4),
                "avg_step_reward": float(batch["reward"].mean()), "episode_return": float(batch["reward"].sum(0).mean()),
                "loss_total": float(loss.detach()), "grad_global_norm": float(grad_norm),
-               **{k: float(v) for k, v in losses.items()}}
+               **{k: float(v.detach()) for k, v in losses.items()}}
         if eval_adapter is not None and eval_interval and it % eval_interval == 0:
             e0 = time.perf_counter()
             ev = collect(eval_adapter, policy_module, frames_per_batch, mode=True, break_when_any_done=True)
