@@ -130,6 +130,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(workload, replicas, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json), valid
+    only for the workload / replica count it was captured on; None otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+            t = json.load(f)
+        if t["workload"] == workload and t["replicas"] == replicas:
+            return t["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def step_bytes(N, E, Nmax, p):
     """algorithmic bytes of one core step."""
     return N * (69 + p * (24 * (Nmax - 1) + 4)) + 20 * E
@@ -160,6 +173,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("TARL_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     g, Nmax, placed = synthetic.make_workload(args.workload, device=dev, t=T0, seed=rank, order=args.link_order)
@@ -242,7 +256,9 @@ def run_native(args):
     step_ms = ms / args.steps
     sb = R * step_bytes(N, E, Nmax, p)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, R, dom),
+                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(pb[dom]), "kernel_ms": round(per[dom], 4),
                 "kernels_ms": {k: round(v, 4) for k, v in per.items()}, "pop_fraction": round(p, 4),
                 "step": {"algorithmic_bytes": int(sb), "achieved": round(sb / (step_ms / 1e3) / 1e9, 1),
@@ -307,6 +323,9 @@ def run_native(args):
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3)
+    if os.environ.get("TARL_BENCH_DEBUG"):
+        print(f"[rank {rank}] e2e: events {ev0.elapsed_time(ev1):.2f} ms, wall {(time.perf_counter() - w0) * 1e3:.2f} ms "
+              f"for {e2e_steps} steps", file=sys.stderr)
     model.response_mpnn.update_history.resolve()
     if world > 1:
         tms = torch.tensor([e2e_ms], device=dev)
