@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 7
+#define TARL_ABI_VERSION 8
 
 /* return codes */
 #define TARL_OK 0
@@ -138,6 +138,11 @@ typedef struct tarl_link_store {
     void* pop_hint;     /* [R*N] bytes, zeroed ONCE by the caller: set by the direction phase on the upstream link
                            whose head was admitted, consumed (and cleared) by the response phase to fetch the ring
                            slots of a pop one dependent load earlier                                            */
+    const int32_t* slot_link; /* [N] link id held by store slot s, or NULL = identity. The store may keep the links
+                                 in a locality order of its own (tarl_cluster_links): everything indexed [R*N] above
+                                 and the topology handed to tarl_store_step are then in SLOT order; import / export
+                                 and the population entry points translate through these two arrays.             */
+    const int32_t* link_slot; /* [N] inverse of slot_link, or NULL                                               */
 } tarl_link_store;
 
 /* x -> store. x element (r, n, c) at x[r*x_replica_stride + n*x_row_stride + c]; cc = congestion_constant[:N] or
@@ -170,6 +175,12 @@ typedef struct tarl_dual_ell {
 int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
                     const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
                     float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask);
+
+/* HOST-side helper (plain C++, host pointers): a locality order of the links for the store — clusters of `cluster`
+ * links grown breadth-first over the dual graph (adj = CSR listing each link's in- and out-neighbours), emitted one
+ * after the other: order[slot] = link id. A CTA tile of `cluster` consecutive slots then gathers mostly from itself. */
+int tarl_cluster_links(int32_t n_links, const int32_t* adj_ptr, const int32_t* adj_idx, int32_t cluster,
+                       int32_t* order);
 
 /* n_steps consecutive steps enqueued by one call (times t0, t0+dt, ...; in-kernel noise; step ids first_step_id, +1,
  * ...): the loop SimulatorEnv.rollout / TransportationSimulator.run drive from Python, without a host round trip per

@@ -58,7 +58,8 @@ class LinkStore(C.Structure):
     """struct tarl_link_store"""
     _fields_ = [("n_links", C.c_int32), ("n_replicas", C.c_int32), ("nmax", C.c_int32), ("reserved", C.c_int32),
                 ("hot_cur", C.c_void_p), ("hot_next", C.c_void_p), ("sel", C.c_void_p), ("stat_a", C.c_void_p),
-                ("stat_b", C.c_void_p), ("queue", C.c_void_p), ("post", C.c_void_p), ("pop_hint", C.c_void_p)]
+                ("stat_b", C.c_void_p), ("queue", C.c_void_p), ("post", C.c_void_p), ("pop_hint", C.c_void_p),
+                ("slot_link", C.c_void_p), ("link_slot", C.c_void_p)]
 
 
 class AgentState(C.Structure):
@@ -103,6 +104,7 @@ SIGNATURES = {
     "tarl_store_import": (C.c_int, [_STORE, _P, _I64, _I64, _P, _P, _P]),
     "tarl_store_export": (C.c_int, [_STORE, _P, _I64, _I64, _F, _P]),
     "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
+    "tarl_cluster_links": (C.c_int, [_I32, _P, _P, _I32, _P]),
     "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, C.c_uint64, C.c_uint32, _F, _F, _I32, _P, _I32, _P, _P, _P, _P]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_backward": (C.c_int, [_CSR1, _ROWS, _P, _I32, _P, _P, _I32, _P]),

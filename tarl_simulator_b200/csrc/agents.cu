@@ -77,14 +77,15 @@ struct StoreAcc {
     int n_nodes;
     float t_garbage;      // arrival time of a pending tail-garbage record = time of the latest core step
     int N, Nmax;
+    // links are addressed by their id; the store may hold them in its own slot order (Store::slot_of)
     __device__ float sel_of(int r, int node) const {
-        return node < N ? s.sel[(size_t)r * N + node] : src_sel[(size_t)r * (n_nodes - N) + (node - N)];
+        return node < N ? s.sel[(size_t)r * N + s.slot_of(node)] : src_sel[(size_t)r * (n_nodes - N) + (node - N)];
     }
     __device__ void set_sel(int r, int node, float v) const {
-        if (node < N) s.sel[(size_t)r * N + node] = v;
+        if (node < N) s.sel[(size_t)r * N + s.slot_of(node)] = v;
         else src_sel[(size_t)r * (n_nodes - N) + (node - N)] = v;
     }
-    __device__ float road_index(int, int n) const { return s.stat_a[n].z; }
+    __device__ float road_index(int, int n) const { return s.stat_a[s.slot_of(n)].z; }
 
     struct Link {
         float4* rec;      // the two halves of the hot record
@@ -95,13 +96,14 @@ struct StoreAcc {
         float num, maxn, fftt, t_garbage;
     };
     __device__ Link open(int r, int n) const {
-        const size_t L = (size_t)r * N + n;
+        const int slot = s.slot_of(n);
+        const size_t L = (size_t)r * N + slot;
         float4* rec = reinterpret_cast<float4*>(hot) + 2 * L;
         Link l;
         l.rec = rec; l.ring = s.queue + L * s.M; l.A = rec[0]; l.B = rec[1]; l.M = s.M;
         const int meta = __float_as_int(l.B.w);
         l.rh = meta & kMetaRingMask; l.gv = (meta & kMetaGarbage) != 0;
-        l.num = l.A.z; l.maxn = l.A.w; l.fftt = s.stat_a[n].x; l.t_garbage = t_garbage;
+        l.num = l.A.z; l.maxn = l.A.w; l.fftt = s.stat_a[slot].x; l.t_garbage = t_garbage;
         return l;
     }
     __device__ static float4 slot(const Link& l, int k) {      // logical FIFO slot k as {id, arrival, exit}
@@ -141,7 +143,7 @@ struct StoreAcc {
 __device__ __forceinline__ bool acc_has_cc(const RowAcc& a) { return a.cc != nullptr; }
 __device__ __forceinline__ float acc_cc(const RowAcc& a, int n) { return a.cc[n]; }
 __device__ __forceinline__ bool acc_has_cc(const StoreAcc&) { return true; }
-__device__ __forceinline__ float acc_cc(const StoreAcc& a, int n) { return a.s.stat_a[n].y; }
+__device__ __forceinline__ float acc_cc(const StoreAcc& a, int n) { return a.s.stat_a[a.s.slot_of(n)].y; }
 
 // ------------------------------------------------------------------------------------------------------------ insert
 __device__ __forceinline__ bool agent_ready(const AgentTable& at, int r, int a, float t) {
@@ -316,9 +318,10 @@ __global__ void __launch_bounds__(kThreads) k_observe(StoreAcc acc, float* __res
         float f[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -1.0f};
         long long head = 0;
         if (n < acc.N) {
-            const float4* rec = reinterpret_cast<const float4*>(acc.hot) + 2 * ((size_t)r * acc.N + n);
+            const int slot = acc.s.slot_of(n);
+            const float4* rec = reinterpret_cast<const float4*>(acc.hot) + 2 * ((size_t)r * acc.N + slot);
             const float4 A = rec[0];
-            const float4 sa = acc.s.stat_a[n], sb = acc.s.stat_b[n];
+            const float4 sa = acc.s.stat_a[slot], sb = acc.s.stat_b[slot];
             f[0] = A.w; f[1] = A.z; f[2] = sa.x; f[3] = sb.x; f[4] = sb.y; f[6] = sa.z;
             head = (long long)A.x;
             num_i = (int)A.z;

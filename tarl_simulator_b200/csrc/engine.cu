@@ -41,8 +41,9 @@ __global__ void __launch_bounds__(kThreads) k_store_import(Store s, const float*
                                                            float4* __restrict__ stat_b, int32_t* __restrict__ flags) {
     const int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= (int64_t)s.N * s.R) return;
-    const int r = (int)(L / s.N), n = (int)(L % s.N);
-    const float* row = x + r * rep_stride + (int64_t)n * row_stride;
+    const int r = (int)(L / s.N), n = (int)(L % s.N);      // n = store slot
+    const int link = s.link_of(n);
+    const float* row = x + r * rep_stride + (int64_t)link * row_stride;
     const int Nmax = s.Nmax, c0 = 3 * Nmax;
     const float maxn = row[c0], num = row[c0 + 1], fftt = row[c0 + 2];
     const bool bad = !(num >= 0.0f) || !(num <= (float)Nmax);
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) k_store_import(Store s, const float*
         s.queue[L * s.M + (k - 1)] = make_float4(row[k], row[Nmax + k], row[2 * Nmax + k], 0.0f);
     if (r == 0) {
         float ccn;
-        if (cc != nullptr) ccn = cc[n];
+        if (cc != nullptr) ccn = cc[link];
         else ccn = fftt * ((maxn + 10.0f) - (row[c0 + 4] * fftt) / 3600.0f);   // src/simulation_core_model.py:60-67
         stat_a[n] = make_float4(fftt, ccn, row[c0 + 6], maxn);
         stat_b[n] = make_float4(row[c0 + 3], row[c0 + 4], 0.0f, 0.0f);
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(kThreads) k_store_export(Store s, float* __res
                                                            int64_t rep_stride, float t_garbage) {
     const int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= (int64_t)s.N * s.R) return;
-    const int r = (int)(L / s.N), n = (int)(L % s.N);
-    float* row = x + r * rep_stride + (int64_t)n * row_stride;
+    const int r = (int)(L / s.N), n = (int)(L % s.N);      // n = store slot
+    float* row = x + r * rep_stride + (int64_t)s.link_of(n) * row_stride;
     const int Nmax = s.Nmax, c0 = 3 * Nmax;
     const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
     const int meta = __float_as_int(hB.w);
@@ -469,6 +470,9 @@ int make_store(const tarl_link_store* p, Store* s) {
     s->queue = static_cast<float4*>(p->queue);
     s->post = static_cast<float2*>(p->post);
     s->hint = static_cast<uint8_t*>(p->pop_hint);
+    s->slot_link = p->slot_link;
+    s->link_slot = p->link_slot;
+    if ((p->slot_link == nullptr) != (p->link_slot == nullptr)) return TARL_E_BADARG;
     return TARL_OK;
 }
 

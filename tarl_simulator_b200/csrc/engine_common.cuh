@@ -49,6 +49,10 @@ struct Store {
     float4* queue;           // [R*N*M]
     float2* post;            // [R*N] {NUM, tail id} after the direction phase
     uint8_t* hint;           // [R*N] 1 = a downstream link admitted this link's head in the direction phase
+    const int32_t* slot_link;   // [N] slot -> link id (nullptr = identity): the store's own locality order
+    const int32_t* link_slot;   // [N] link id -> slot
+    __device__ __forceinline__ int link_of(int slot) const { return slot_link != nullptr ? slot_link[slot] : slot; }
+    __device__ __forceinline__ int slot_of(int link) const { return link_slot != nullptr ? link_slot[link] : link; }
 };
 
 __device__ __forceinline__ int ring_pos(int rh, int logical, int M) {  // logical slot 1..M -> physical 0..M-1

@@ -173,7 +173,7 @@ class BatchedSimulatorEnv:
     the value net only NUM: `num_agents()` is a strided view)."""
 
     def __init__(self, graph, Nmax: int, agent_features: torch.Tensor, replicas: int, timestep: float = 1,
-                 seed: int = 0):
+                 seed: int = 0, cluster: bool | None = None):
         dev = graph.x.device
         if dev.type != "cuda":
             raise RuntimeError("BatchedSimulatorEnv lives on a CUDA device (no CPU fallback)")
@@ -181,7 +181,7 @@ class BatchedSimulatorEnv:
         self.N, self.n_nodes = int(graph.num_roads), graph.x.size(0)
         self.E_full = graph.edge_index.size(1)
         self.timestep = timestep
-        self.store = LinkStore.from_graph(graph, Nmax, replicas=replicas, seed=seed)
+        self.store = LinkStore.from_graph(graph, Nmax, replicas=replicas, seed=seed, cluster=cluster)
         F = 3 * self.Nmax + 7
         self.src_sel = graph.x[self.N:, F - 2].to(torch.float32).repeat(self.R, 1).contiguous()
         self.agent_features = agent_features.to(dev, torch.float32).unsqueeze(0).repeat(self.R, 1, 1).contiguous()
@@ -294,12 +294,11 @@ class BatchedSimulatorEnv:
         """The dynamic observation columns without materialising [R, N_tot, 7]: (NUMBER_OF_AGENT [R, N_tot],
         SELECTED_ROAD [R, N_tot], head agent id int64 [R, N_tot]); plain copies out of the store's arrays."""
         R, N, M = self.R, self.N, self.n_nodes
-        hot = self.store.hot[self.store.cur][: R * N].view(R, N, 8)
         num = torch.zeros(R, M, dtype=torch.float32, device=self.device)
-        num[:, :N] = hot[:, :, 2]
+        num[:, :N] = self.store.num_agents()
         head = torch.zeros(R, M, dtype=torch.int64, device=self.device)
-        head[:, :N] = hot[:, :, 0]
-        sel = torch.cat((self.store.sel[: R * N].view(R, N), self.src_sel), dim=1)
+        head[:, :N] = self.store.head_agents()
+        sel = torch.cat((self.store.selected_road(), self.src_sel), dim=1)
         return num, sel, head
 
     def export_x(self) -> torch.Tensor:

@@ -16,27 +16,28 @@ pytestmark = pytest.mark.gpu
 CORE_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "core_*.npz")))
 
 
-def make_store(x0, ei, w, Nmax, use_static, replicas=1, seed=0):
+def make_store(x0, ei, w, Nmax, use_static, replicas=1, seed=0, cluster=None):
     from tarl_simulator_b200.data import Data
     from tarl_simulator_b200.engine import LinkStore
     g = Data(x=x0.cuda(), edge_index_routes=ei.cuda(), edge_attr_routes=w.cuda(), num_roads=x0.size(0))
     if use_static:
         crit, cc = core_port.static_factors(x0, core_port.Cols(Nmax))
         g.critical_number, g.congestion_constant = crit.cuda(), cc.cuda()
-    return LinkStore.from_graph(g, Nmax, replicas=replicas, seed=seed), g
+    return LinkStore.from_graph(g, Nmax, replicas=replicas, seed=seed, cluster=cluster), g
 
 
 VARIANTS = [0, 1]     # ELL (default), CSR
 
 
+@pytest.mark.parametrize("cluster", [False, True])       # True: links kept in the store's own locality order
 @pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("name", CORE_CASES)
-def test_store_matches_reference_goldens(name, golden_dir, variant):
+def test_store_matches_reference_goldens(name, golden_dir, variant, cluster):
     d = np.load(os.path.join(golden_dir, name + ".npz"))
     Nmax = int(d["Nmax"])
     x0 = torch.from_numpy(d["x0"])
     ei, w = torch.from_numpy(d["edge_index"]), torch.from_numpy(d["edge_attr"])
-    store, _ = make_store(x0, ei, w, Nmax, bool(d["use_static"]))
+    store, _ = make_store(x0, ei, w, Nmax, bool(d["use_static"]), cluster=cluster)
     assert torch.equal(store.export_x()[0].cpu(), x0), "import -> export must be the identity"
     E = ei.size(1)
     dtt = torch.empty(1, E, device="cuda")
@@ -59,7 +60,7 @@ def test_store_replicas_match_oracle(seed, N, Nmax, R, max_out, variant):
     x0, _ = cases.random_road_state(g, N, Nmax, 500.0, ei)
     c = core_port.Cols(Nmax)
     cc = core_port.static_factors(x0, c)[1]
-    store, _ = make_store(x0, ei, w, Nmax, True, replicas=R)
+    store, _ = make_store(x0, ei, w, Nmax, True, replicas=R, cluster=bool(seed % 2 == 0))
     xs = [x0.clone() for _ in range(R)]
     E = ei.size(1)
     dtt = torch.empty(R, E, device="cuda")

@@ -85,17 +85,18 @@ def test_simulator_env_matches_reference(name, tmp_path):
     sim.agent.check_errors()
 
 
-def batched_env(d, sim, R):
+def batched_env(d, sim, R, cluster=None):
     from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
-    return BatchedSimulatorEnv(sim.graph, int(d["Nmax"]), torch.from_numpy(d["af0"]), replicas=R)
+    return BatchedSimulatorEnv(sim.graph, int(d["Nmax"]), torch.from_numpy(d["af0"]), replicas=R, cluster=cluster)
 
 
+@pytest.mark.parametrize("cluster", [False, True])
 @pytest.mark.parametrize("name", RL)
-def test_batched_env_matches_reference(name, tmp_path):
+def test_batched_env_matches_reference(name, tmp_path, cluster):
     d = golden(name)
     sim = product_simulator(d, tmp_path)
     R = 3
-    env = batched_env(d, sim, R)
+    env = batched_env(d, sim, R, cluster)
     env.reset()
     assert torch.equal(env.export_x()[1].cpu(), torch.from_numpy(d["x_reset"]))
     E = sim.graph.edge_index_routes.size(1)
@@ -119,13 +120,14 @@ def test_batched_env_matches_reference(name, tmp_path):
     assert env.counters[:, 1].tolist() == [done] * R
 
 
+@pytest.mark.parametrize("cluster", [False, True])
 @pytest.mark.parametrize("name", CLASSICAL)
-def test_batched_store_classical_order_matches_reference(name, tmp_path):
+def test_batched_store_classical_order_matches_reference(name, tmp_path, cluster):
     """insert -> withdraw -> choice -> core on the link store (the order of TransportationSimulator.run)."""
     d = golden(name)
     sim = product_simulator(d, tmp_path)
     R = 2
-    env = batched_env(d, sim, R)
+    env = batched_env(d, sim, R, cluster)
     for s in range(len(d["t"])):
         env.set_time(float(d["t"][s]))
         env.insert()
@@ -181,7 +183,7 @@ def test_inplace_and_store_match_oracle_on_random_grids(seed, n, A, spread, leng
     sim.config_parameters(start_time=0)
     sim.agent.set_time(0)
     sim.record_road_optimality = False
-    env = BatchedSimulatorEnv(sim.graph, Nmax, af, replicas=2)
+    env = BatchedSimulatorEnv(sim.graph, Nmax, af, replicas=2, cluster=bool(seed % 2))
     nodes, _, _ = agents_port.choosers_and_neighbours(graph.edge_index.cpu(), N, x_ref.size(0))
     moved = 0
     for s in range(steps):
