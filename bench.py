@@ -524,12 +524,19 @@ def ppo_bench(args, dev, world, rank):
                                        history=hist))
     env.check_errors()
     n_params = sum(p.numel() for p in list(policy.parameters()) + list(value.parameters()) if p.requires_grad)
+    in_sync = None
+    if world > 1:       # every rank must hold bit-identical parameters after the all-reduced update
+        flat = torch.cat([p.detach().reshape(-1) for p in list(policy.parameters()) + list(value.parameters())])
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
     return {"workload": "grid100 (39 600 links, 100 000 agents per replica), PPO as wired by the reference",
             "replicas_total": total, "replicas_per_gpu": R, "rollout_steps": T, "scaling": "strong",
             "rollout_ms": round(roll_ms, 2), "env_steps_per_s": round(total * T / (roll_ms / 1e3), 1),
             "link_steps_per_s": round(total * T * N / (roll_ms / 1e3), 1),
             "iteration_ms": round(train_ms, 2), "update_ms": round(max(train_ms - roll_ms, 0.0), 2),
-            "allreduce_bytes_per_update": 4 * n_params if world > 1 else 0,
+            "allreduce_bytes_per_update": 4 * n_params if world > 1 else 0, "parameters_identical_across_ranks": in_sync,
             "inserted_agents_per_replica": float(env.counters[:, 0].float().mean()),
             "what": "rollout = policy forward + sample + env step (action, core step, withdraw, insert, reward) for every "
                     "replica; iteration = rollout + GAE + one clipped-PPO minibatch step (32 frames) + gradient all-reduce"}

@@ -293,3 +293,75 @@ def test_cpu_tensors_are_refused():
              edge_index_routes=torch.zeros(2, 0, dtype=torch.long))
     with pytest.raises(RuntimeError):
         a.insert_agent_into_network(g, h)
+
+
+def _tiny_graph(Nmax=2, n_links=3):
+    """A ring of `n_links` single-slot links (Nmax = 2: one ring slot per link), SRC/DEST nodes per intersection."""
+    from tarl_simulator_b200.matsim_io import graph_from_links
+    ids = [f"{i}" for i in range(n_links)]
+    g, nm = graph_from_links(ids, ids[1:] + ids[:1], [5.0] * n_links, [1800.0] * n_links, [10.0] * n_links, [1.0] * n_links,
+                             dense=True)
+    assert nm == Nmax
+    return g, nm
+
+
+def test_minimal_queue_capacity_and_empty_population():
+    """Nmax = 2 (MAXN = 1, so MAXN-3-NUM < 0: nothing is ever admitted) and a population with only the dummy agent:
+    every kernel must be a clean no-op on both layouts, and the exported state must stay equal to the oracle's."""
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    from tarl_simulator_b200.transportation_simulator import TransportationSimulator
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    graph, Nmax = _tiny_graph()
+    c = Cols(Nmax)
+    N = int(graph.num_roads)
+    af = torch.zeros(1, 9); af[0, 2] = 48 * 3600.0
+    ref_graph = {k: getattr(graph, k) for k in ("edge_index", "edge_index_routes", "edge_attr_routes", "adj_matrix",
+                                                "congestion_constant")}
+    ref_graph["num_roads"] = N
+    x_ref, af_ref = graph.x.clone(), af.clone()
+    sim = TransportationSimulator("cuda")
+    sim.graph, sim.Nmax, sim.h = graph.to("cuda"), Nmax, FeatureHelpers(Nmax)
+    sim.agent.agent_features = af.cuda()
+    sim.config_parameters(start_time=0); sim.agent.set_time(0)
+    env = BatchedSimulatorEnv(sim.graph, Nmax, af, replicas=2)
+    g = torch.Generator().manual_seed(0)
+    nodes, _, _ = agents_port.choosers_and_neighbours(ref_graph["edge_index"], N, x_ref.size(0))
+    E = ref_graph["edge_index_routes"].size(1)
+    for s in range(5):
+        u_core, u_choice = cases.uniforms(g, E), torch.rand(nodes.numel(), generator=g)
+        agents_port.run_step(x_ref, af_ref, s, c, ref_graph, u_choice, u_core)
+        sim.run(noise=u_core.cuda(), choice_uniforms=u_choice.cuda())
+        env.set_time(float(s)); env.insert(); env.withdraw(); env.choice(uniforms=u_choice.cuda().repeat(2, 1))
+        env.store.step(env.time, noise=u_core.cuda().repeat(2, 1))
+        assert torch.equal(sim.graph.x.cpu(), x_ref)
+        assert torch.equal(env.export_x()[1].cpu(), x_ref)
+    assert float(x_ref[:, c.NUM].sum()) == 0.0
+    sim.agent.check_errors(); env.check_errors()
+
+
+def test_data_dependent_faults_are_flagged():
+    """An origin whose SELECTED_ROAD is not a road while one of its agents is ready, and a queued agent id outside
+    agent_features: the reference raises IndexError; here the sticky error word does."""
+    from tarl_simulator_b200.agents import Agents
+    from tarl_simulator_b200.data import Data
+    from tarl_simulator_b200.feature_helpers import FeatureHelpers
+    h = FeatureHelpers(Nmax=5)
+    c = Cols(5)
+    x = torch.zeros(3, c.F)
+    x[0, c.MAXN], x[0, c.FFTT] = 5, 3.0
+    x[1:, c.RIDX] = -1
+    x[1, c.SEL] = 7                                   # the SRC node points outside the roads
+    g = Data(x=x.cuda(), edge_index=torch.tensor([[1, 0], [0, 2]]).cuda(),
+             edge_index_routes=torch.empty((2, 0), dtype=torch.long).cuda(), edge_attr_routes=torch.empty((0, 1)).cuda(),
+             num_roads=1)
+    a = Agents("cuda")
+    a.agent_features = torch.tensor([[0, 0, 1e6, 0, 0, 0, 0, 0, 0], [1.0, 2, 0, 0, 0, 0, 0, 0, 0]]).cuda()
+    a.time = 0
+    a.insert_agent_into_network(g, h)
+    with pytest.raises(IndexError):
+        a.check_errors()
+    g.x[0, 0], g.x[0, c.NUM], g.x[0, c.DEP0] = 99.0, 1.0, 0.0      # agent id 99 does not exist
+    a.withdraw_agent_from_network(g, h)
+    with pytest.raises(IndexError):
+        a.check_errors()
+    assert float(g.x[0, c.NUM]) == 1.0                              # nothing was removed
