@@ -394,6 +394,253 @@ __global__ void __launch_bounds__(kThreads) k_gd_sample(tarl_csr grp, const floa
     if (hit >= 0) onehot[t.b * ov.sb + hit * ov.se] = T(1);
 }
 
+// ------------------------------------------------------------------------------------------------ 4 rows per thread
+// Fast path of the two training-time kernels for the layout the package itself produces: edge-major logits / gradient
+// (row stride 1, edge stride B), B in {4, 8, 16, 32} per grid.y slice, action absent or edge-major bytes. One thread
+// owns (group, 4 consecutive rows): every logits access is one 128-bit load, the action of an edge is one 32-bit load,
+// and edge ids / predicates / addresses are paid once per four rows.
+struct F4 {
+    float v[4];
+};
+__device__ __forceinline__ F4 ld4(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+
+struct Soft4 {
+    F4 ex[kCache];
+    F4 mx, inv_den;
+    int eid[kCache];
+    int deg;
+};
+
+__device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const float* __restrict__ lg, int B, int row0,
+                                           int k0, int k1, float inv_t) {
+    s.deg = k1 - k0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s.mx.v[q] = -FLT_MAX;
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        s.eid[j] = 0;
+        if (j < s.deg) {
+            s.eid[j] = grp.eid[k0 + j];
+            s.ex[j] = ld4(lg + (int64_t)s.eid[j] * B + row0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.ex[j].v[q] *= inv_t; s.mx.v[q] = fmaxf(s.mx.v[q], s.ex[j].v[q]); }
+        }
+    }
+    for (int k = k0 + kCache; k < k1; ++k) {
+        const F4 z = ld4(lg + (int64_t)grp.eid[k] * B + row0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s.mx.v[q] = fmaxf(s.mx.v[q], z.v[q] * inv_t);
+    }
+    F4 den = {{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        if (j < s.deg) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.ex[j].v[q] = fexp(s.ex[j].v[q] - s.mx.v[q]); den.v[q] += s.ex[j].v[q]; }
+        }
+    }
+    for (int k = k0 + kCache; k < k1; ++k) {
+        const F4 z = ld4(lg + (int64_t)grp.eid[k] * B + row0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) den.v[q] += fexp(z.v[q] * inv_t - s.mx.v[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s.inv_den.v[q] = fdiv(1.0f, den.v[q]);
+}
+
+__device__ __forceinline__ F4 tail4_p(const Soft4& s, const float* __restrict__ lg, int B, int row0, int e, float inv_t) {
+    F4 z = ld4(lg + (int64_t)e * B + row0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) z.v[q] = fexp(z.v[q] * inv_t - s.mx.v[q]) * s.inv_den.v[q];
+    return z;
+}
+
+__device__ __forceinline__ F4 action4(const uint8_t* __restrict__ act, int B, int row0, int e) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(act + (int64_t)e * B + row0);
+    return F4{{(float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24)}};
+}
+
+// (group, 4-row chunk) of this thread in tile `tile`; C = chunks per group (power of two), rows offset by grid.y * 32
+struct Where4 {
+    int g, row0, k0, k1;
+    bool live;
+};
+__device__ __forceinline__ Where4 locate4(const tarl_csr& grp, int B, int C, int tile) {
+    const int sh = 31 - __clz(C);
+    const int64_t i = (int64_t)tile * blockDim.x + threadIdx.x;
+    Where4 t;
+    t.g = (int)(i >> sh);
+    t.row0 = blockIdx.y * 32 + 4 * (int)(i & (C - 1));
+    t.live = t.g < grp.n_rows && t.row0 < B;
+    t.k0 = t.live ? grp.ptr[t.g] : 0;
+    t.k1 = t.live ? grp.ptr[t.g + 1] : 0;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) k_gd_forward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
+                                                             int B, int C, int n_tiles, const uint8_t* __restrict__ action,
+                                                             float* __restrict__ part_ent, float* __restrict__ part_lp,
+                                                             int32_t* __restrict__ part_bad) {
+    __shared__ float sm_f[kThreads];
+    __shared__ int sm_i[kThreads];
+    F4 ent = {{0.f, 0.f, 0.f, 0.f}}, lp = {{0.f, 0.f, 0.f, 0.f}};
+    int bad[4] = {0, 0, 0, 0};
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const Where4 t = locate4(grp, B, C, tile);
+        if (!t.live || t.k1 == t.k0) continue;
+        Soft4 s;
+        soft4_load(s, grp, logits, B, t.row0, t.k0, t.k1, inv_t);
+        F4 asum = {{0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+        for (int j = 0; j < kCache; ++j) {
+            if (j < s.deg) {
+                F4 a = {{0.f, 0.f, 0.f, 0.f}};
+                if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float p = s.ex[j].v[q] * s.inv_den.v[q];
+                    const float l = flog(p + kLogEps);
+                    ent.v[q] -= p * l;
+                    lp.v[q] += a.v[q] * l;
+                    asum.v[q] += a.v[q];
+                }
+            }
+        }
+        for (int k = t.k0 + kCache; k < t.k1; ++k) {
+            const int e = grp.eid[k];
+            const F4 p4 = tail4_p(s, logits, B, t.row0, e, inv_t);
+            F4 a = {{0.f, 0.f, 0.f, 0.f}};
+            if (action != nullptr) a = action4(action, B, t.row0, e);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float l = flog(p4.v[q] + kLogEps);
+                ent.v[q] -= p4.v[q] * l;
+                lp.v[q] += a.v[q] * l;
+                asum.v[q] += a.v[q];
+            }
+        }
+        if (action != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (asum.v[q] != 1.0f) bad[q] = 1;
+        }
+    }
+    // per-row partials: lanes that share (threadIdx.x % C) hold the same four rows
+    const int nb = gridDim.x;
+    const int c = threadIdx.x & (C - 1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int row = blockIdx.y * 32 + 4 * c + q;
+        if (part_ent != nullptr) {
+            const float v = block_sum_rows(ent.v[q], C, sm_f);
+            if (threadIdx.x < C && row < B) part_ent[(int64_t)row * nb + blockIdx.x] = v;
+        }
+        if (part_lp != nullptr) {
+            const float v = block_sum_rows(lp.v[q], C, sm_f);
+            const int n = block_sum_rows(bad[q], C, sm_i);
+            if (threadIdx.x < C && row < B) {
+                part_lp[(int64_t)row * nb + blockIdx.x] = v;
+                part_bad[(int64_t)row * nb + blockIdx.x] = n;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
+                                                              int B, int C, const uint8_t* __restrict__ action,
+                                                              const float* __restrict__ g_lp, const float* __restrict__ g_ent,
+                                                              const float* __restrict__ log_prob, float* __restrict__ grad) {
+    const Where4 t = locate4(grp, B, C, blockIdx.x);
+    if (!t.live || t.k1 == t.k0) return;
+    F4 wl, we;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int b = t.row0 + q;
+        wl.v[q] = (g_lp != nullptr && action != nullptr) ? g_lp[b] : 0.0f;
+        if (log_prob != nullptr && log_prob[b] == -INFINITY) wl.v[q] = 0.0f;
+        we.v[q] = (g_ent != nullptr) ? g_ent[b] : 0.0f;
+    }
+    Soft4 s;
+    soft4_load(s, grp, logits, B, t.row0, t.k0, t.k1, inv_t);
+    F4 Sa = {{0.f, 0.f, 0.f, 0.f}}, Sc = {{0.f, 0.f, 0.f, 0.f}};
+    // pass 1: the two group sums; pass 2 recomputes r_e and c_e instead of keeping them (48 registers less: occupancy)
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        if (j < s.deg) {
+            F4 a = {{0.f, 0.f, 0.f, 0.f}};
+            if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float p = s.ex[j].v[q] * s.inv_den.v[q];
+                const float r = fdiv(p, p + kLogEps);
+                Sa.v[q] += a.v[q] * r;
+                Sc.v[q] += p * (flog(p + kLogEps) + r);
+            }
+        }
+    }
+    for (int k = t.k0 + kCache; k < t.k1; ++k) {
+        const int e = grp.eid[k];
+        const F4 p4 = tail4_p(s, logits, B, t.row0, e, inv_t);
+        F4 a = {{0.f, 0.f, 0.f, 0.f}};
+        if (action != nullptr) a = action4(action, B, t.row0, e);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float r = fdiv(p4.v[q], p4.v[q] + kLogEps);
+            Sa.v[q] += a.v[q] * r;
+            Sc.v[q] += p4.v[q] * (flog(p4.v[q] + kLogEps) + r);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
+        if (j < s.deg) {
+            F4 a = {{0.f, 0.f, 0.f, 0.f}};
+            if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+            F4 out;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float p = s.ex[j].v[q] * s.inv_den.v[q];
+                const float r = fdiv(p, p + kLogEps);
+                const float c = flog(p + kLogEps) + r;
+                out.v[q] = (-we.v[q] * p * (c - Sc.v[q]) + wl.v[q] * (a.v[q] * r - p * Sa.v[q])) * inv_t;
+            }
+            st4(grad + (int64_t)s.eid[j] * B + t.row0, out);
+        }
+    }
+    for (int k = t.k0 + kCache; k < t.k1; ++k) {
+        const int e = grp.eid[k];
+        const F4 p4 = tail4_p(s, logits, B, t.row0, e, inv_t);
+        F4 a = {{0.f, 0.f, 0.f, 0.f}};
+        if (action != nullptr) a = action4(action, B, t.row0, e);
+        F4 out;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float r = fdiv(p4.v[q], p4.v[q] + kLogEps);
+            const float c = flog(p4.v[q] + kLogEps) + r;
+            out.v[q] = (-we.v[q] * p4.v[q] * (c - Sc.v[q]) + wl.v[q] * (a.v[q] * r - p4.v[q] * Sa.v[q])) * inv_t;
+        }
+        st4(grad + (int64_t)e * B + t.row0, out);
+    }
+}
+
+// The fast path applies when the tensors are edge-major, 16-byte aligned, B is 4, 8, 16 or a multiple of 32, and the
+// action (if any) is edge-major bytes.
+inline bool em4_ok(const tarl_rows* lg, int B, const tarl_rows* act, int act_dtype, const tarl_rows* extra = nullptr) {
+    if (!(B == 4 || B == 8 || B == 16 || (B % 32) == 0)) return false;
+    auto em = [&](const tarl_rows* r, size_t elem) {
+        return r->row_stride == 1 && r->col_stride == B && (reinterpret_cast<uintptr_t>(r->data) % (elem * 4)) == 0;
+    };
+    if (lg == nullptr || !em(lg, 4)) return false;
+    if (extra != nullptr && !em(extra, 4)) return false;
+    if (act != nullptr && (act_dtype != TARL_ACTION_U8 || !em(act, 1))) return false;
+    return true;
+}
+inline int em4_chunks(int B) { return (B >= 32 ? 32 : B) >> 2; }
+inline dim3 em4_grid(int K, int B) { return dim3(blocks_for((int64_t)K * em4_chunks(B)), (B + 31) / 32); }
+
 inline int pow2_rows(int B) {
     int p = 1;
     while (p < B && p < 32) p <<= 1;
@@ -464,7 +711,10 @@ int tarl_policy_embed_backward(const tarl_csr* by_target, const tarl_rows* grad_
 }
 
 int32_t tarl_graphdist_partial_count(int32_t n_groups, int32_t batch) {
-    return (n_groups > 0 && batch > 0) ? gd_fwd_grid(n_groups, batch).x : 0;
+    if (n_groups <= 0 || batch <= 0) return 0;        // an upper bound over both forward variants
+    const unsigned a = gd_fwd_grid(n_groups, batch).x, b = em4_grid(n_groups, batch).x;
+    const unsigned m = a > b ? a : b;
+    return (int32_t)(m > (unsigned)kFwdMaxCtas ? kFwdMaxCtas : m);
 }
 
 int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
@@ -478,9 +728,15 @@ int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, floa
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int E = groups->n_edges, K = groups->n_rows;
     if (E > 0 && (logits == nullptr || logits->data == nullptr)) return TARL_E_BADARG;
-    const dim3 grid = K > 0 ? gd_fwd_grid(K, batch) : dim3(0, 1);
+    const bool fast = proba == nullptr && mode == nullptr && temperature != 0.0f && em4_ok(logits, batch, action, action_dtype);
+    dim3 grid = K > 0 ? gd_fwd_grid(K, batch) : dim3(0, 1);
+    int n_tiles = K > 0 ? (int)gd_grid(K, batch).x : 0;
+    if (fast && K > 0) {
+        grid = em4_grid(K, batch);
+        n_tiles = (int)grid.x;
+        if (grid.x > (unsigned)kFwdMaxCtas) grid.x = kFwdMaxCtas;
+    }
     const int nb = (int)grid.x;
-    const int n_tiles = K > 0 ? (int)gd_grid(K, batch).x : 0;
     float* part_ent = nullptr; float* part_lp = nullptr; int32_t* part_bad = nullptr;
     if (entropy != nullptr || log_prob != nullptr) {
         if (partials == nullptr && nb > 0) return TARL_E_WORKSPACE;
@@ -488,7 +744,11 @@ int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, floa
         part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;
         part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
     }
-    if (nb > 0)
+    if (nb > 0 && fast)
+        k_gd_forward_em4<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
+                                                   em4_chunks(batch), n_tiles, data_of<const uint8_t>(action), part_ent,
+                                                   part_lp, part_bad);
+    else if (nb > 0)
         k_gd_forward<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits), temperature, batch,
                                                pow2_rows(batch), n_tiles, data_of<const void>(action), view_of(action),
                                                action_dtype,
@@ -509,6 +769,12 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
     if (!logits || !logits->data || !grad_logits || !grad_logits->data) return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // every edge has a source, hence a group: every grad entry is written
+    if (temperature != 0.0f && em4_ok(logits, batch, action, action_dtype, grad_logits)) {
+        k_gd_backward_em4<<<em4_grid(groups->n_rows, batch), kThreads, 0, s>>>(
+            *groups, data_of<const float>(logits), 1.0f / temperature, batch, em4_chunks(batch),
+            data_of<const uint8_t>(action), grad_log_prob, grad_entropy, log_prob, data_of<float>(grad_logits));
+        return launch_status();
+    }
     k_gd_backward<<<gd_grid(groups->n_rows, batch), kThreads, 0, s>>>(
         *groups, data_of<const float>(logits), view_of(logits), temperature, batch, pow2_rows(batch),
         data_of<const void>(action), view_of(action), action_dtype, grad_log_prob, grad_entropy, log_prob,
