@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "tarl_b200.h"
+#include "tile_map.cuh"
 
 namespace {
 
@@ -23,24 +24,37 @@ inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK 
 // Layout: everything the policy kernels produce is NODE-major / EDGE-major with the batch row innermost (element (b, n)
 // of emb / idx / node_grad at n*B + b, element (b, e) of logits at e*B + b), so that the B rows of one node or edge are
 // one contiguous vector: gathers by node id fetch all rows in one sector and edge ids are read once for all rows.
-// node pass: idx[n,b] = ROAD_INDEX >= 0 ? ROAD_INDEX : n (D2);  emb[n,b] = W[idx]. One thread per (node, row), row
-// innermost: the strided reads of the ROAD_INDEX column touch every sector of node_features whatever the mapping (28-byte
-// rows), the writes are fully coalesced.
-__global__ void __launch_bounds__(kThreads) k_policy_node(const float* __restrict__ w, int rows,
-                                                          const float* __restrict__ nf, int64_t nf_bs, int64_t nf_rs,
-                                                          int ridx_col, int B, int N, float* __restrict__ emb,
-                                                          int32_t* __restrict__ idx, int32_t* __restrict__ flags) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * N) return;
-    const int n = (int)(i / B), b = (int)(i - (int64_t)n * B);
-    long long k = (long long)nf[b * nf_bs + n * nf_rs + ridx_col];  // .to(torch.long): truncation
-    if (k < 0) k = n;
-    if (k >= rows) {  // nn.Embedding raises IndexError
-        atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_EMBED_RANGE);
-        k = 0;
-    }
-    idx[i] = (int32_t)k;
-    emb[i] = w[k];
+// node pass: idx[n,b] = ROAD_INDEX >= 0 ? ROAD_INDEX : n (D2);  emb[n,b] = W[idx]. Tiled (tile_map.cuh): the ROAD_INDEX
+// column of the row-major [B, N, C] observation is read with the node innermost (the 32 lanes of a warp stay inside
+// one ~1 KB span of one sample), idx / emb are written with the row innermost (one contiguous B-vector per node).
+__global__ void __launch_bounds__(tarl::kTileThreads) k_policy_node(const float* __restrict__ w, int rows,
+                                                                    const float* __restrict__ nf, int64_t nf_bs,
+                                                                    int64_t nf_rs, int ridx_col, int B, int Bp, int N,
+                                                                    float* __restrict__ emb, int32_t* __restrict__ idx,
+                                                                    int32_t* __restrict__ flags) {
+    __shared__ float sm_w[tarl::kTileSmem];
+    __shared__ int32_t sm_k[tarl::kTileSmem];
+    const tarl::Tile t = tarl::tile_here(B, Bp);
+    tarl::tile_walk_nodes(t, [&](int r, int j) {
+        const int n = t.n0 + j, b = t.b0 + r;
+        if (n >= N || r >= t.nrows) return;
+        long long k = (long long)nf[b * nf_bs + n * nf_rs + ridx_col];  // .to(torch.long): truncation
+        if (k < 0) k = n;
+        if (k >= rows) {  // nn.Embedding raises IndexError
+            atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_EMBED_RANGE);
+            k = 0;
+        }
+        sm_k[tarl::tile_slot(t, r, j)] = (int32_t)k;
+        sm_w[tarl::tile_slot(t, r, j)] = w[k];
+    });
+    __syncthreads();
+    tarl::tile_walk_rows(t, [&](int r, int j) {
+        const int n = t.n0 + j;
+        if (n >= N || r >= t.nrows) return;
+        const int64_t i = (int64_t)n * B + t.b0 + r;
+        idx[i] = sm_k[tarl::tile_slot(t, r, j)];
+        emb[i] = sm_w[tarl::tile_slot(t, r, j)];
+    });
 }
 
 // edge pass: logits[e, :] = emb[dst[e], :]. One thread per (edge, chunk of 4 rows) when B % 4 == 0 (the threads of one
@@ -681,9 +695,9 @@ int tarl_policy_embed_forward(const float* emb_weight, int32_t emb_rows, const f
     if (!emb_weight || !node_features || !node_emb || !node_idx || (n_edges > 0 && (!edge_dst || !logits)))
         return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    k_policy_node<<<blocks_for((int64_t)batch * n_nodes), kThreads, 0, s>>>(
-        emb_weight, emb_rows, node_features, nf_batch_stride, nf_row_stride, road_index_col, batch, n_nodes, node_emb,
-        node_idx, flags);
+    k_policy_node<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, 0, s>>>(
+        emb_weight, emb_rows, node_features, nf_batch_stride, nf_row_stride, road_index_col, batch,
+        tarl::tile_rows_pow2(batch), n_nodes, node_emb, node_idx, flags);
     if (n_edges > 0)
         k_policy_edge<<<blocks_for((int64_t)n_edges * ((batch & 3) == 0 ? batch >> 2 : batch)), kThreads, 0, s>>>(
             node_emb, edge_dst, batch, n_edges, logits);

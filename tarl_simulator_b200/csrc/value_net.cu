@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "tarl_b200.h"
+#include "tile_map.cuh"
 
 namespace {
 
@@ -49,17 +50,33 @@ __device__ __forceinline__ void load_x(const Inputs& in, int b, int n, float x[k
     for (int c = 0; c < kAgentDim; ++c) x[kNodeDim + c] = q[c];
 }
 
-__global__ void __launch_bounds__(kThreads) k_value_project(Inputs in, const float* __restrict__ w,
-                                                            float* __restrict__ proj, int32_t* __restrict__ flags) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= (int64_t)in.B * in.N) return;
-    const int n = (int)(i / in.B), b = (int)(i % in.B);
-    float x[kIn];
-    load_x(in, b, n, x, flags);
-    float acc = 0.0f;
+// proj[n,b] = w[0:16] . x[b,n]. Tiled (tile_map.cuh): x is assembled from the row-major observation with the node
+// innermost (node_features rows and agent_index entries of 32 consecutive nodes are contiguous; agent_features is a
+// small table), proj is written with the row innermost.
+__global__ void __launch_bounds__(tarl::kTileThreads) k_value_project(Inputs in, int Bp, const float* __restrict__ w,
+                                                                      float* __restrict__ proj,
+                                                                      int32_t* __restrict__ flags) {
+    __shared__ float sm[tarl::kTileSmem];
+    const tarl::Tile t = tarl::tile_here(in.B, Bp);
+    float wr[kIn];
 #pragma unroll
-    for (int c = 0; c < kIn; ++c) acc += w[c] * x[c];
-    proj[i] = acc;
+    for (int c = 0; c < kIn; ++c) wr[c] = w[c];
+    tarl::tile_walk_nodes(t, [&](int r, int j) {
+        const int n = t.n0 + j;
+        if (n >= in.N || r >= t.nrows) return;
+        float x[kIn];
+        load_x(in, t.b0 + r, n, x, flags);
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) acc += wr[c] * x[c];
+        sm[tarl::tile_slot(t, r, j)] = acc;
+    });
+    __syncthreads();
+    tarl::tile_walk_rows(t, [&](int r, int j) {
+        const int n = t.n0 + j;
+        if (n >= in.N || r >= t.nrows) return;
+        proj[(int64_t)n * in.B + t.b0 + r] = sm[tarl::tile_slot(t, r, j)];
+    });
 }
 
 // one thread per (source node, batch row): segment mean of tanh messages in ascending edge id, then the node update
@@ -104,38 +121,59 @@ __device__ __forceinline__ void block_store(float (&vals)[kCount], float* __rest
 }
 
 // node update backward: dv = g_v (1 - v^2); partial sums of d a, d c; gm = dv * a / deg handed to the edge pass.
-// grad_v: element (b, n) at b*gv_sb + n*gv_sn.
-__global__ void __launch_bounds__(kThreads) k_value_node_grad(tarl_csr by_src, int B, int N, const float* __restrict__ a,
-                                                              const float* __restrict__ mean, const float* __restrict__ v,
-                                                              const float* __restrict__ gv, int64_t gv_sb, int64_t gv_sn,
-                                                              float* __restrict__ gm, float* __restrict__ partials) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+// grad_v: element (b, n) at b*gv_sb + n*gv_sn. Same tiles as the edge pass (one partial row per tile).
+__global__ void __launch_bounds__(tarl::kTileThreads) k_value_node_grad(tarl_csr by_src, int B, int Bp, int N,
+                                                                        const float* __restrict__ a,
+                                                                        const float* __restrict__ mean,
+                                                                        const float* __restrict__ v,
+                                                                        const float* __restrict__ gv, int64_t gv_sb,
+                                                                        int64_t gv_sn, float* __restrict__ gm,
+                                                                        float* __restrict__ partials) {
+    __shared__ float sm[tarl::kTileSmem];
+    const tarl::Tile t = tarl::tile_here(B, Bp);
     float vals[2] = {0.0f, 0.0f};
-    if (i < (int64_t)B * N) {
-        const int n = (int)(i / B), b = (int)(i % B);
+    const float a0 = a[0];
+    // grad_v normally arrives row-major [B, N] (autograd of the dense head): staged with the node innermost
+    tarl::tile_walk_nodes(t, [&](int r, int j) {
+        const int n = t.n0 + j;
+        if (n >= N || r >= t.nrows) return;
+        sm[tarl::tile_slot(t, r, j)] = gv[(t.b0 + r) * gv_sb + n * gv_sn];
+    });
+    __syncthreads();
+    tarl::tile_walk_rows(t, [&](int r, int j) {
+        const int n = t.n0 + j, b = t.b0 + r;
+        if (n >= N || r >= t.nrows) return;
+        const int64_t i = (int64_t)n * B + b;
         const float vv = v[i];
-        const float dv = gv[b * gv_sb + n * gv_sn] * (1.0f - vv * vv);
-        vals[0] = dv * mean[i];
-        vals[1] = dv;
+        const float dv = sm[tarl::tile_slot(t, r, j)] * (1.0f - vv * vv);
+        vals[0] += dv * mean[i];
+        vals[1] += dv;
         const int deg = by_src.ptr[n + 1] - by_src.ptr[n];
-        gm[i] = deg > 0 ? dv * a[0] / (float)deg : 0.0f;
-    }
-    block_store<2>(vals, partials + (size_t)blockIdx.x * kGrads + 18);
+        gm[i] = deg > 0 ? dv * a0 / (float)deg : 0.0f;
+    });
+    block_store<2>(vals, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads + 18);
 }
 
-// message backward, one thread per (TARGET node, batch row): every in-edge's message is recomputed from this node's
-// own projection; the 16 input-weight gradients need the node's x once, not once per edge.
-__global__ void __launch_bounds__(kThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, const float* __restrict__ w,
-                                                              const float* __restrict__ w0, const float* __restrict__ proj,
-                                                              const float* __restrict__ gm, float* __restrict__ partials) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+// message backward over (TARGET node, batch row) tiles. Walk 1, rows innermost: every in-edge's message is recomputed
+// from the node's own projection and the gathered gm B-vectors -> gs[n,b] = sum of d z over the in-edges (ascending
+// edge id), kept in shared memory. Walk 2, nodes innermost: the 16 input-weight gradients gs * x[b,n,:] with x read
+// the way the observation is laid out (once per node and row, not once per edge).
+__global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, int Bp,
+                                                                        const float* __restrict__ w,
+                                                                        const float* __restrict__ w0,
+                                                                        const float* __restrict__ proj,
+                                                                        const float* __restrict__ gm,
+                                                                        float* __restrict__ partials) {
+    __shared__ float sm[tarl::kTileSmem];
+    const tarl::Tile t = tarl::tile_here(in.B, Bp);
     float vals[18];
 #pragma unroll
     for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
-    if (i < (int64_t)in.B * in.N) {
-        const int n = (int)(i / in.B), b = (int)(i % in.B);
-        const float we = w[kIn], bias = w0[0];
-        const float pn = proj[i];
+    const float we = w[kIn], bias = w0[0];
+    tarl::tile_walk_rows(t, [&](int r, int j) {
+        const int n = t.n0 + j, b = t.b0 + r;
+        if (n >= in.N || r >= t.nrows) return;
+        const float pn = proj[(int64_t)n * in.B + b];
         const float* ef = in.ef + b * in.ef_bs;
         float gs = 0.0f, gwe = 0.0f;
         const int k1 = by_dst.ptr[n + 1];
@@ -146,16 +184,23 @@ __global__ void __launch_bounds__(kThreads) k_value_edge_grad(tarl_csr by_dst, I
             gs += gz;
             gwe += gz * f;
         }
+        sm[tarl::tile_slot(t, r, j)] = gs;
+        vals[16] += gwe;
+        vals[17] += gs;
+    });
+    __syncthreads();
+    tarl::tile_walk_nodes(t, [&](int r, int j) {
+        const int n = t.n0 + j;
+        if (n >= in.N || r >= t.nrows) return;
+        const float gs = sm[tarl::tile_slot(t, r, j)];
         if (gs != 0.0f) {
             float x[kIn];
-            load_x(in, b, n, x, nullptr);
+            load_x(in, t.b0 + r, n, x, nullptr);
 #pragma unroll
-            for (int cI = 0; cI < kIn; ++cI) vals[cI] = gs * x[cI];
+            for (int cI = 0; cI < kIn; ++cI) vals[cI] += gs * x[cI];
         }
-        vals[16] = gwe;
-        vals[17] = gs;
-    }
-    block_store<18>(vals, partials + (size_t)blockIdx.x * kGrads);
+    });
+    block_store<18>(vals, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads);
 }
 
 // grads[j] = sum over all blocks of partials[.., j]: one CTA per j, strided accumulation then a fixed tree
@@ -186,7 +231,7 @@ int check(const tarl_csr* c, int n_nodes) {
 extern "C" {
 
 int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch) {
-    return (n_nodes > 0 && batch > 0) ? blocks_for((int64_t)n_nodes * batch) : 0;
+    return (n_nodes > 0 && batch > 0) ? tarl::tile_count(n_nodes, batch) : 0;
 }
 
 int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
@@ -207,7 +252,8 @@ int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
     const int nb = blocks_for((int64_t)batch * n_nodes);
-    k_value_project<<<nb, kThreads, 0, s>>>(in, msg_weight, proj, flags);
+    k_value_project<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, 0, s>>>(in, tarl::tile_rows_pow2(batch), msg_weight,
+                                                                                   proj, flags);
     k_value_aggregate<<<nb, kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
     return launch_status();
 }
@@ -233,11 +279,12 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
     const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
-    const int nb = blocks_for((int64_t)batch * n_nodes);
-    k_value_node_grad<<<nb, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, mean, v, grad_v, gv_batch_stride,
-                                              gv_node_stride, gm, partials);
-    k_value_edge_grad<<<nb, kThreads, 0, s>>>(*by_target, in, msg_weight, msg_bias, proj, gm, partials);
-    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, nb, grads);
+    const dim3 grid = tarl::tile_grid(n_nodes, batch);
+    const int Bp = tarl::tile_rows_pow2(batch);
+    k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
+                                                          gv_batch_stride, gv_node_stride, gm, partials);
+    k_value_edge_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_target, in, Bp, msg_weight, msg_bias, proj, gm, partials);
+    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
     return launch_status();
 }
 

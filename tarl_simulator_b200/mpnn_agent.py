@@ -242,7 +242,11 @@ class MPNNValueNet(MessagePassing, Agents):
                                        by_target, self._flags)
         if not batched:
             v = v.reshape(self.num_nodes)
-        return self.final_mlp(torch.cat((v, self.time_net(time)), dim=-1))
+        # final_mlp([v_nodes ‖ time_net(t)]) with the weight split instead of the concatenation (src/agents/mpnn_agent.py:359-361 of the
+        # reference): the [B, N+1] copy of v would cost more than the whole message passing
+        head = self.final_mlp[0]
+        N = self.num_nodes
+        return (v @ head.weight[0, :N]).unsqueeze(-1) + self.time_net(time) * head.weight[0, N] + head.bias
 
     def check_errors(self):
         if self._flags is not None:
