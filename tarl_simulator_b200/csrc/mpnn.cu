@@ -426,19 +426,24 @@ struct Soft4 {
     F4 ex[kCache];
     F4 mx, inv_den;
     int eid[kCache];
+    uint32_t aw[kCache];   // the 4 action bytes of each cached edge, fetched together with its logits
     int deg;
 };
 
-__device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const float* __restrict__ lg, int B, int row0,
-                                           int k0, int k1, float inv_t) {
-    s.deg = k1 - k0;
+// s.eid[0 .. min(deg, kCache)) and s.deg are filled by the caller (prefetched one tile ahead)
+__device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const float* __restrict__ lg,
+                                           const uint8_t* __restrict__ act, int B, int row0, int k0, int k1,
+                                           float inv_t) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) s.mx.v[q] = -FLT_MAX;
 #pragma unroll
     for (int j = 0; j < kCache; ++j) {
-        s.eid[j] = 0;
+        s.aw[j] = 0u;
+        if (act != nullptr && j < s.deg) s.aw[j] = *reinterpret_cast<const uint32_t*>(act + (int64_t)s.eid[j] * B + row0);
+    }
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) {
         if (j < s.deg) {
-            s.eid[j] = grp.eid[k0 + j];
             s.ex[j] = ld4(lg + (int64_t)s.eid[j] * B + row0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { s.ex[j].v[q] *= inv_t; s.mx.v[q] = fmaxf(s.mx.v[q], s.ex[j].v[q]); }
@@ -473,9 +478,11 @@ __device__ __forceinline__ F4 tail4_p(const Soft4& s, const float* __restrict__ 
     return z;
 }
 
-__device__ __forceinline__ F4 action4(const uint8_t* __restrict__ act, int B, int row0, int e) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(act + (int64_t)e * B + row0);
+__device__ __forceinline__ F4 action4_of(uint32_t w) {
     return F4{{(float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24)}};
+}
+__device__ __forceinline__ F4 action4(const uint8_t* __restrict__ act, int B, int row0, int e) {
+    return action4_of(*reinterpret_cast<const uint32_t*>(act + (int64_t)e * B + row0));
 }
 
 // (group, 4-row chunk) of this thread in tile `tile`; C = chunks per group (power of two), rows offset by grid.y * 32
@@ -495,7 +502,26 @@ __device__ __forceinline__ Where4 locate4(const tarl_csr& grp, int B, int C, int
     return t;
 }
 
-__global__ void __launch_bounds__(kThreads) k_gd_forward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
+// Software pipeline of the persistent em4 kernels: a thread walks tiles with a fixed stride; while tile i computes, the
+// edge ids of tile i+1 and the group bounds of tile i+2 are already in flight, so that only ONE level of the
+// ptr -> edge id -> logits chain (the logits / action gathers) is exposed per tile.
+struct Stage4 {
+    int row0, k0, deg;     // deg == 0: nothing to do (dead lane, empty group, or past the last tile)
+};
+__device__ __forceinline__ Stage4 stage4_bounds(const tarl_csr& grp, int B, int C, int tile, int n_tiles) {
+    Stage4 st = {0, 0, 0};
+    if (tile < n_tiles) {
+        const Where4 t = locate4(grp, B, C, tile);
+        st.row0 = t.row0; st.k0 = t.k0; st.deg = t.k1 - t.k0;
+    }
+    return st;
+}
+__device__ __forceinline__ void stage4_eids(const tarl_csr& grp, const Stage4& st, int (&eid)[kCache]) {
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) eid[j] = (j < st.deg) ? grp.eid[st.k0 + j] : 0;
+}
+
+__global__ void __launch_bounds__(kThreads, 3) k_gd_forward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
                                                              int B, int C, int n_tiles, const uint8_t* __restrict__ action,
                                                              float* __restrict__ part_ent, float* __restrict__ part_lp,
                                                              int32_t* __restrict__ part_bad) {
@@ -503,17 +529,27 @@ __global__ void __launch_bounds__(kThreads) k_gd_forward_em4(tarl_csr grp, const
     __shared__ int sm_i[kThreads];
     F4 ent = {{0.f, 0.f, 0.f, 0.f}}, lp = {{0.f, 0.f, 0.f, 0.f}};
     int bad[4] = {0, 0, 0, 0};
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const Where4 t = locate4(grp, B, C, tile);
-        if (!t.live || t.k1 == t.k0) continue;
+    const int stride = gridDim.x;
+    Stage4 nxt = stage4_bounds(grp, B, C, blockIdx.x, n_tiles);
+    int eid_nxt[kCache];
+    stage4_eids(grp, nxt, eid_nxt);
+    Stage4 nxt2 = stage4_bounds(grp, B, C, blockIdx.x + stride, n_tiles);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += stride) {
+        struct { int row0, k0, k1; } t = {nxt.row0, nxt.k0, nxt.k0 + nxt.deg};
         Soft4 s;
-        soft4_load(s, grp, logits, B, t.row0, t.k0, t.k1, inv_t);
+        s.deg = nxt.deg;
+#pragma unroll
+        for (int j = 0; j < kCache; ++j) s.eid[j] = eid_nxt[j];
+        nxt = nxt2;
+        stage4_eids(grp, nxt, eid_nxt);
+        nxt2 = stage4_bounds(grp, B, C, tile + 2 * stride, n_tiles);
+        if (s.deg == 0) continue;
+        soft4_load(s, grp, logits, action, B, t.row0, t.k0, t.k1, inv_t);
         F4 asum = {{0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int j = 0; j < kCache; ++j) {
             if (j < s.deg) {
-                F4 a = {{0.f, 0.f, 0.f, 0.f}};
-                if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+                const F4 a = action4_of(s.aw[j]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float p = s.ex[j].v[q] * s.inv_den.v[q];
@@ -565,11 +601,25 @@ __global__ void __launch_bounds__(kThreads) k_gd_forward_em4(tarl_csr grp, const
 }
 
 __global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
-                                                              int B, int C, const uint8_t* __restrict__ action,
+                                                              int B, int C, int n_tiles,
+                                                              const uint8_t* __restrict__ action,
                                                               const float* __restrict__ g_lp, const float* __restrict__ g_ent,
                                                               const float* __restrict__ log_prob, float* __restrict__ grad) {
-    const Where4 t = locate4(grp, B, C, blockIdx.x);
-    if (!t.live || t.k1 == t.k0) return;
+  const int stride = gridDim.x;
+  Stage4 nxt = stage4_bounds(grp, B, C, blockIdx.x, n_tiles);
+  int eid_nxt[kCache];
+  stage4_eids(grp, nxt, eid_nxt);
+  Stage4 nxt2 = stage4_bounds(grp, B, C, blockIdx.x + stride, n_tiles);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += stride) {
+    struct { int row0, k0, k1; } t = {nxt.row0, nxt.k0, nxt.k0 + nxt.deg};
+    Soft4 s;
+    s.deg = nxt.deg;
+#pragma unroll
+    for (int j = 0; j < kCache; ++j) s.eid[j] = eid_nxt[j];
+    nxt = nxt2;
+    stage4_eids(grp, nxt, eid_nxt);
+    nxt2 = stage4_bounds(grp, B, C, tile + 2 * stride, n_tiles);
+    if (s.deg == 0) continue;
     F4 wl, we;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -578,15 +628,13 @@ __global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, cons
         if (log_prob != nullptr && log_prob[b] == -INFINITY) wl.v[q] = 0.0f;
         we.v[q] = (g_ent != nullptr) ? g_ent[b] : 0.0f;
     }
-    Soft4 s;
-    soft4_load(s, grp, logits, B, t.row0, t.k0, t.k1, inv_t);
+    soft4_load(s, grp, logits, action, B, t.row0, t.k0, t.k1, inv_t);
     F4 Sa = {{0.f, 0.f, 0.f, 0.f}}, Sc = {{0.f, 0.f, 0.f, 0.f}};
     // pass 1: the two group sums; pass 2 recomputes r_e and c_e instead of keeping them (48 registers less: occupancy)
 #pragma unroll
     for (int j = 0; j < kCache; ++j) {
         if (j < s.deg) {
-            F4 a = {{0.f, 0.f, 0.f, 0.f}};
-            if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+            const F4 a = action4_of(s.aw[j]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float p = s.ex[j].v[q] * s.inv_den.v[q];
@@ -611,8 +659,7 @@ __global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, cons
 #pragma unroll
     for (int j = 0; j < kCache; ++j) {
         if (j < s.deg) {
-            F4 a = {{0.f, 0.f, 0.f, 0.f}};
-            if (action != nullptr) a = action4(action, B, t.row0, s.eid[j]);
+            const F4 a = action4_of(s.aw[j]);
             F4 out;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -638,6 +685,7 @@ __global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, cons
         }
         st4(grad + (int64_t)e * B + t.row0, out);
     }
+  }
 }
 
 // The fast path applies when the tensors are edge-major, 16-byte aligned, B is 4, 8, 16 or a multiple of 32, and the
@@ -664,6 +712,7 @@ inline dim3 gd_grid(int K, int B) {      // one CTA per tile of kThreads/Bp grou
     const int Bp = pow2_rows(B);
     return dim3(blocks_for((int64_t)K * Bp), (B + 31) / 32);
 }
+constexpr int kBwdMaxCtas = 148 * 8;      // persistent backward (tile stride): a few waves of resident CTAs
 constexpr int kFwdMaxCtas = 148 * 16;     // forward CTAs walk tiles with a stride: this bounds the partials per row
 inline dim3 gd_fwd_grid(int K, int B) {
     dim3 g = gd_grid(K, B);
@@ -784,8 +833,11 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // every edge has a source, hence a group: every grad entry is written
     if (temperature != 0.0f && em4_ok(logits, batch, action, action_dtype, grad_logits)) {
-        k_gd_backward_em4<<<em4_grid(groups->n_rows, batch), kThreads, 0, s>>>(
-            *groups, data_of<const float>(logits), 1.0f / temperature, batch, em4_chunks(batch),
+        dim3 grid = em4_grid(groups->n_rows, batch);
+        const int n_tiles = (int)grid.x;
+        if (grid.x > (unsigned)kBwdMaxCtas) grid.x = kBwdMaxCtas;
+        k_gd_backward_em4<<<grid, kThreads, 0, s>>>(
+            *groups, data_of<const float>(logits), 1.0f / temperature, batch, em4_chunks(batch), n_tiles,
             data_of<const uint8_t>(action), grad_log_prob, grad_entropy, log_prob, data_of<float>(grad_logits));
         return launch_status();
     }
