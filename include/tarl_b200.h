@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 8
+#define TARL_ABI_VERSION 9
 
 /* return codes */
 #define TARL_OK 0
@@ -364,6 +364,23 @@ int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_
  * sum of NUM over the links (integer atomics). Any output may be NULL. */
 int tarl_store_observe(const tarl_agent_state* state, float* node_features, int64_t* agent_index, int32_t* occupancy,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Metrics side channels, accumulated on the device (csrc/metrics.cu).
+ *
+ * Replaces the per-step histories behind TransportationSimulator.compute_node_metrics / plot_daily_counts /
+ * plot_road_optimality (src/transportation_simulator.py:351,453-510,563-669): the reference keeps one bool[N] per
+ * step in ResponseMPNN.update_history (src/response_mpnn.py:125) and Agents.withdraw_history
+ * (src/agents/base.py:402) plus a host copy of delta_travel_time[E] per step, and reduces them afterwards
+ * (hour = time // 3600; per-link aggregate = scatter_add over edge_index_routes[0]).
+ *   counts[r, hour, n]         += (pop[r, n] != 0) + (withdrawn[r, n] != 0)          int32 [R, n_hours, N]
+ *   optimality_now[r, n]        = sum of delta_tt[r, e] over the out-edges e of n, ascending edge id   [R, N]
+ *   optimality_sum[r, hour, n] += that sum                                           fp32 [R, n_hours, N]
+ * pop / withdrawn: uint8 [R, N] or NULL; delta_tt: fp32 [R, E] in original edge order or NULL; any output may be
+ * NULL. g supplies N, E and the out-edge segments (out_ptr, out_eid). 0 <= hour < n_hours. */
+int tarl_metrics_accumulate(const tarl_dual_csr* g, int32_t n_replicas, const uint8_t* pop, const uint8_t* withdrawn,
+                            const float* delta_tt, int32_t hour, int32_t n_hours, int32_t* counts,
+                            float* optimality_sum, float* optimality_now, void* stream);
 
 #ifdef __cplusplus
 }

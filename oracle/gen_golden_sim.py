@@ -105,8 +105,10 @@ def graph_arrays(graph):
     }
 
 
-def classical(name, xml, af, t0, steps, seed):
-    """TransportationSimulator.run loop (src/transportation_simulator.py:294-351)."""
+def classical(name, xml, af, t0, steps, seed, metrics=False):
+    """TransportationSimulator.run loop (src/transportation_simulator.py:294-351). metrics=True also records what the
+    reference's own compute_node_metrics (:563-669) returns at the end, and the per-link road-optimality series that
+    plot_road_optimality (:482-488) reduces from road_optimality_values."""
     ts = ref_loader.load("src.transportation_simulator")
     g = torch.Generator().manual_seed(seed)
     with tempfile.TemporaryDirectory() as tmp:
@@ -139,6 +141,16 @@ def classical(name, xml, af, t0, steps, seed):
         steps_rec["delta_tt"].append(sim.model_core.direction_mpnn.road_optimality_data["delta_travel_time"].numpy().copy())
     rec.update({k: np.array(v) for k, v in steps_rec.items()})
     rec["mode"] = np.array("classical")
+    if metrics:
+        nm = sim.compute_node_metrics(output_dir=None)          # the unmodified reference method
+        rec["nm_counts"] = np.array([nm[n]["hourly_counts"] for n in range(N)], dtype=np.int64)
+        rec["nm_avg_vc"] = np.array([nm[n]["avg_vc"] for n in range(N)], dtype=np.float32)
+        rec["nm_std_vc"] = np.array([nm[n]["std_vc"] for n in range(N)], dtype=np.float32)
+        v_mat = torch.stack([v for _, v in sim.road_optimality_values], dim=0)                  # :483
+        agg = torch.zeros(v_mat.size(0), N, dtype=v_mat.dtype)
+        agg.scatter_add_(1, sim.graph.edge_index_routes[0].unsqueeze(0).expand(v_mat.size(0), -1), v_mat)   # :487-488
+        rec["ro_agg"] = agg.numpy()
+        rec["ro_times"] = np.array([t for t, _ in sim.road_optimality_values], dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
     done = int(sim.agent.agent_features[:, 8].sum())
     print(f"{name}: N={N} E={E} Nmax={sim.Nmax} agents={af.size(0) - 1} steps={steps} done={done} "
@@ -237,6 +249,11 @@ def population_case(name):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
+    if only:                                  # e.g. `python oracle/gen_golden_sim.py sim_metrics_grid4`
+        global classical, rl_env, population_case
+        wrap = lambda f: (lambda name, *a, **k: f(name, *a, **k) if name in only else None)
+        classical, rl_env, population_case = wrap(classical), wrap(rl_env), wrap(population_case)
     # the reference's own test network (tests/conftest.py:94-120): 2 links A<->B, one agent SRC(A) -> DEST(B)
     two = network_xml([(0, "A", "B", 100, 10, 10, 1), (1, "B", "A", 100, 10, 10, 1)])
     af = torch.zeros(2, 9); af[0, 2] = 25 * 3600.0; af[1, 0] = 2; af[1, 1] = 5
@@ -259,6 +276,12 @@ def main():
     links, nodes = grid_links(3, g)
     rl_env("sim_rl_grid3", network_xml(links, nodes), random_population(g, len(links), 9, 250, 21540, 40), steps=120, seed=6)
     population_case("sim_population_xml")
+    # metrics side channels: the classical loop across an hour boundary (t = 3540 .. 3699), then the reference's own
+    # compute_node_metrics and the road-optimality reduction
+    g = torch.Generator().manual_seed(8)
+    links, nodes = grid_links(4, g)
+    classical("sim_metrics_grid4", network_xml(links, nodes), random_population(g, len(links), 16, 500, 3540, 80), t0=3540,
+              steps=160, seed=8, metrics=True)
 
 
 if __name__ == "__main__":

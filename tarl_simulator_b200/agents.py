@@ -123,6 +123,8 @@ class Agents(AgentFeatureHelpers):
         self.time = 0
         self.device = device
         self.withdraw_history: list = []
+        self.keep_history = True        # False: the masks only feed on-device counters (metrics.LinkMetrics)
+        self.last_withdrawn = None      # bool[N] of the latest withdraw call (device)
         self._index = None
         self._scratch = {}
         self._flags = None
@@ -217,7 +219,9 @@ class Agents(AgentFeatureHelpers):
                                                   float(self.time), mask.data_ptr(), None, flags.data_ptr(),
                                                   _stream(dev))
         _cabi.check(rc, "tarl_agents_withdraw")
-        self.withdraw_history.append((self.time, mask if graph.x.dim() == 2 else mask.view(R, N)))
+        self.last_withdrawn = mask if graph.x.dim() == 2 else mask.view(R, N)
+        if self.keep_history:
+            self.withdraw_history.append((self.time, self.last_withdrawn))
         return graph.x
 
     @torch.no_grad()

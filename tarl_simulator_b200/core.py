@@ -58,6 +58,7 @@ class UpdateHistory(list):
     def __init__(self, items=()):
         super().__init__(items)
         self._pending = []
+        self.keep = True        # False: masks are not retained (on-device counters instead); error bits still raise
 
     def push(self, time, mask: torch.Tensor, flags: torch.Tensor):
         self._pending.append((time, mask, flags))
@@ -72,7 +73,7 @@ class UpdateHistory(list):
         err = 0
         for (time, mask, _), fl in zip(pend, host.tolist()):
             err |= fl[_cabi.FLAG_ERROR]
-            if fl[_cabi.FLAG_ANY_POP]:
+            if fl[_cabi.FLAG_ANY_POP] and self.keep:
                 super().append((time, mask))
         if err:
             raise RuntimeError("core step fault: " + _cabi.decode_error_bits(err))

@@ -92,6 +92,8 @@ class SimulatorEnv:
         sim.on_way_before = 0
         sim.done_before = 0
         sim.model_core.response_mpnn.update_history = []
+        if sim.metrics is not None:
+            sim.metrics.reset()
         sim.set_time(EPISODE_START)
         out = self._observation()
         sim.agent.reset()
@@ -121,6 +123,9 @@ class SimulatorEnv:
         g.x = sim.agent.insert_agent_into_network(g, h)
         e = _time.time(); sim.inserting_time += e - b
         reward = (-torch.sum(g.x[:, h.NUMBER_OF_AGENT])).flatten()                                   # :266-267
+        if sim.node_metrics:
+            sim.link_metrics().record(sim.time, pop=sim.model_core.last_pop, withdrawn=sim.agent.last_withdrawn,
+                                      delta_tt=sim.model_core.direction_mpnn.road_optimality_data["delta_travel_time"])
         sim.set_time(sim.time + sim.timestep)                                                        # D6
         done = torch.tensor(sim.time > EPISODE_END)
         af = sim.agent.agent_features
@@ -195,6 +200,7 @@ class BatchedSimulatorEnv:
         self.occupancy = torch.zeros(self.R, **i32)
         self.withdrawn = torch.zeros(self.R, self.N, dtype=torch.bool, device=dev)
         self.delta_tt = None                                   # optional [R, E] output of the core step
+        self.metrics = None                                    # metrics.LinkMetrics once enable_metrics() was called
         self.time = float(EPISODE_START)
         self._table = _cabi.AgentTable(self.agent_features.data_ptr(), self.agent_features.stride(0),
                                        self.agent_features.size(1), 0)
@@ -217,10 +223,25 @@ class BatchedSimulatorEnv:
         self.agent_features[..., Agents.ON_WAY] = 0.0
         self.agent_features[..., Agents.DONE] = 0.0
         self.counters.zero_()
+        if self.metrics is not None:
+            self.metrics.reset()
         self.time = float(EPISODE_START)
 
     def set_time(self, t):
         self.time = float(t)
+
+    def enable_metrics(self, optimality: bool = False):
+        """Hourly hand-off / withdrawal counters per (replica, link) accumulated on the device every step — the
+        batched counterpart of compute_node_metrics' histories (src/transportation_simulator.py:584-613).
+        optimality=True also keeps the per-link road-optimality aggregate (needs the [R, E] delta_tt output)."""
+        from .metrics import LinkMetrics
+        if self.store.slot_link is not None:
+            raise NotImplementedError("metrics need the store in link-id order (cluster=False)")
+        self.metrics = LinkMetrics(self.graph.edge_index_routes, self.N, replicas=self.R, optimality=optimality,
+                                   device=self.device)
+        if optimality and self.delta_tt is None:
+            self.delta_tt = torch.empty(self.R, self.store.E, dtype=torch.float32, device=self.device)
+        return self.metrics
 
     def apply_action(self, action: torch.Tensor):
         a, code = _action_code(action.reshape(self.R, self.E_full))
@@ -278,6 +299,9 @@ class BatchedSimulatorEnv:
         self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
         self.withdraw()
         self.insert()
+        if self.metrics is not None:
+            self.metrics.record(self.time, pop=self.store.pop[: self.R * self.N], withdrawn=self.withdrawn,
+                                delta_tt=self.delta_tt if self.metrics.optimality_now is not None else None)
         nf, ai = self.observe(node_features=observe, agent_index=observe)
         self.time += self.timestep
         out = {"reward": -self.occupancy.to(torch.float32), "occupancy": self.occupancy,

@@ -291,6 +291,15 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
             rec["eval_return"] = float(ev["reward"].sum(0).mean())
             rec["eval_episode_len"] = int(ev["reward"].size(0))
             rec["eval_ms"] = round((time.perf_counter() - e0) * 1e3, 2)
+            sim = getattr(eval_env, "simulator", None)          # node metrics of the evaluation episode
+            if sim is not None:                                 # (src/rl/ppo_trainer.py:117-127)
+                counts = sim.hourly_counts()
+                if counts is not None:
+                    cap = sim.graph.x[: counts.size(0), sim.h.MAX_FLOW].to(torch.float32).clone()
+                    cap[cap == 0] = float("nan")
+                    vc = counts.float() / cap.unsqueeze(1)
+                    rec["eval_avg_vc_mean"] = float(torch.nanmean(torch.nanmean(vc, dim=1)))
+                    rec["eval_std_vc_mean"] = float(torch.nanmean(torch.std(vc, dim=1, unbiased=False)))
             if stochastic_eval:
                 ev = collect(eval_adapter, policy_module, frames_per_batch, mode=False, break_when_any_done=True)
                 rec["eval_stochastic_return"] = float(ev["reward"].sum(0).mean())
