@@ -382,6 +382,24 @@ int tarl_metrics_accumulate(const tarl_dual_csr* g, int32_t n_replicas, const ui
                             const float* delta_tt, int32_t hour, int32_t n_hours, int32_t* counts,
                             float* optimality_sum, float* optimality_now, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * MPNNValueNetSimple forward on the tensor cores (csrc/value_mlp.cu: tcgen05.mma kind::tf32 with 3xTF32 error
+ * compensation, operands staged by TMA, A split into TMEM, fp32 accumulation in TMEM).
+ *
+ * Replaces MPNNValueNetSimple.forward (src/agents/mpnn_agent.py:428-450) for n_rows observations at once:
+ *   out[m] = w3 . relu(W2 relu(W1 [occupancy[m, 0:n_nodes] ‖ time[m]] + b1) + b2) + b3
+ * occupancy: fp32, element (m, n) at occupancy[m*occ_row_stride + n] = NUMBER_OF_AGENT of node n in observation m
+ *   (16-byte aligned base, occ_row_stride a multiple of 4: TMA addressing; anything else is TARL_E_BADARG and the
+ *   caller uses its library GEMM). time: element m at time[m*time_stride].
+ * w1 [64, n_nodes+1], b1 [64], w2 [64, 64], b2 [64], w3 [64], b3 [1]: final_mlp.{0,2,4}.{weight,bias}, row-major.
+ * workspace: tarl_value_mlp_workspace_bytes(n_rows, n_nodes) bytes, 1024-byte aligned. out: [n_rows].
+ * Inference only (no gradient): the PPO update's 32-frame backward stays on the library GEMM. */
+size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes);
+int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
+                           int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, void* workspace, size_t workspace_bytes,
+                           float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,442 @@
+// value_mlp.cu — MPNNValueNetSimple's forward on the 5th-generation tensor cores (sm_100a: tcgen05.mma, TMEM, TMA).
+//
+// Reference semantics: /root/reference/src/agents/mpnn_agent.py:407-450 —
+//   v = Linear(64,1)( relu( Linear(64,64)( relu( Linear(N_tot+1, 64)( [NUMBER_OF_AGENT[:, 0:N_tot] ‖ time] ) ) ) ) )
+// evaluated for M observation rows at once (every frame of a PPO rollout: M = replicas, K = N_tot + 1 ~ 6e4..1.5e6).
+// The first layer is a skinny GEMM  H[M,64] = A[M,K] · W1[64,K]^T  that reads A exactly once: 32 flop per byte of A,
+// i.e. HBM-bound on the tensor pipe and compute-bound on the fp32 SIMT pipe — the one place on this path where tensor
+// cores pay. The parity bar is 1e-5 relative in fp32, which plain TF32 (10-bit mantissa) misses, so the product is
+// error-compensated: a = a_hi + a_lo, w = w_hi + w_lo with *_hi the value rounded to TF32 and *_lo the (rounded)
+// remainder, and
+//   a·w ~= a_hi·w_hi + a_lo·w_hi + a_hi·w_lo          (three kind::tf32 MMAs, fp32 accumulation in TMEM)
+// which leaves a relative error of ~2^-23 per product with a random sign.
+//
+// Data flow per CTA (one 128-row tile of A x one K-slice), 6 warps:
+//   warp 0      TMA producer: A tile [128 x 32] fp32 and the matching [64 x 32] tiles of W_hi / W_lo into a 6-stage
+//               shared-memory ring (128-byte swizzle), completion on mbarriers (cp.async.bulk.tensor).
+//   warps 2-5   splitters: thread r owns row r of the tile — reads its 128 bytes from shared memory, splits each value
+//               into hi/lo and stores both into TENSOR MEMORY (tcgen05.st, lane r, 32 + 32 columns per stage). A is
+//               then an MMA operand straight from TMEM: its hi/lo copies never touch shared memory, whose bandwidth
+//               would otherwise cap the kernel (3 MMAs x (A + B) re-read per k-step).
+//   warp 1      MMA issuer (one thread): per k-step of 8 columns three tcgen05.mma.kind::tf32 (A from TMEM, B from
+//               shared memory through a K-major SWIZZLE_128B descriptor) into a 128 x 64 fp32 accumulator in TMEM;
+//               tcgen05.commit releases the ring slot / publishes the accumulator.
+//   warps 2-5   promotion: the tensor core adds into its fp32 accumulator with truncation, a bias that over the
+//               ~2e4 accumulation steps of a K = 6e4 row reaches 1e-4 relative (measured). Every 128 columns the MMA
+//               therefore switches between two TMEM accumulators and these warps tcgen05.ld the finished one and
+//               add it into fp32 registers with round-to-nearest (the same remedy as for FP8 accumulators); at the
+//               end one row per thread goes to the split-K partial buffer.
+// A second small kernel sums the K-slices in a fixed order (deterministic), adds the time column and the bias and
+// runs the 64x64 and 64x1 layers per row.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tarl_b200.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 32, STAGES = 6;
+constexpr int kHidden = 64;
+constexpr int kThreadsGemm = 192;
+constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4, kStageBytes = kABytes + 2 * kBBytes;
+constexpr uint32_t kTmemCols = 512;                    // 2 x 64 accumulator + 6 x (32 hi + 32 lo)
+constexpr uint32_t kColAcc = 0, kColA = 128;
+constexpr int kChunk = 4;                              // k-blocks (128 columns of A) accumulated in TMEM before promotion
+constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, one 128 x 64 x 8 TF32 step
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// K-major operand tile in shared memory, rows of 128 bytes, SWIZZLE_128B (what the TMA wrote): 8-row groups are
+// 1024 bytes apart (stride byte offset), the leading offset is unused for swizzled K-major layouts, descriptor
+// version 1 (sm_100). The tile base must be 1024-byte aligned. Stepping 8 TF32 columns = +32 bytes on the address.
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);       // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                             // leading byte offset (ignored), bits [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version, bits [46,48)
+    d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+constexpr uint32_t kHiMask = 0xFFFFE000u;               // sign + exponent + the 10 mantissa bits TF32 keeps
+// Round to nearest TF32 (ties away from zero). Truncation would do for the arithmetic, but its error always points
+// towards zero: over K ~ 6e4 same-signed products the 2^-21 relative bias does not average out (measured 3e-5 on the
+// output), whereas rounded splits leave ~2^-23 per product with a random sign. The MMA then finds nothing to truncate.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & kHiMask); }
+
+// ------------------------------------------------------------------------------------------------ weight split
+// W1 [64, K] (K = n_nodes + 1, rows not 16-byte aligned in general) -> W_hi, W_lo [64, Kp] (Kp a multiple of 32, zero
+// padded, TMA-addressable) and the time column w_time [64].
+__global__ void __launch_bounds__(256) k_value_mlp_split_w(const float* __restrict__ w1, int n_nodes, int Kp,
+                                                           float* __restrict__ w_hi, float* __restrict__ w_lo,
+                                                           float* __restrict__ w_time) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (int64_t)kHidden * Kp) return;
+    const int j = (int)(i / Kp), k = (int)(i - (int64_t)j * Kp);
+    float w = 0.0f;
+    if (k < n_nodes) w = w1[(int64_t)j * (n_nodes + 1) + k];
+    const float hi = tf32_rn(w);
+    w_hi[i] = hi;
+    w_lo[i] = tf32_rn(w - hi);
+    if (k == 0) w_time[j] = w1[(int64_t)j * (n_nodes + 1) + n_nodes];
+}
+
+// ------------------------------------------------------------------------------------------------ first layer
+__global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid_constant__ CUtensorMap map_a,
+                                                                    const __grid_constant__ CUtensorMap map_wh,
+                                                                    const __grid_constant__ CUtensorMap map_wl, int M,
+                                                                    int kb_total, int kb_per_slice,
+                                                                    float* __restrict__ partials) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles: 1024-byte aligned
+    const uint32_t bars = base + STAGES * kStageBytes;
+    auto sm_a = [&](int s) { return base + s * kStageBytes; };
+    auto sm_wh = [&](int s) { return base + s * kStageBytes + kABytes; };
+    auto sm_wl = [&](int s) { return base + s * kStageBytes + kABytes + kBBytes; };
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto aready = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto accfull = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+    auto accfree = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    const int kb0 = blockIdx.y * kb_per_slice;
+    const int nkb = min(kb_per_slice, kb_total - kb0);
+    const int n_chunks = (nkb + kChunk - 1) / kChunk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+            mbar_init(aready(s), 128);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accfull(b), 1);
+            mbar_init(accfree(b), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                                     // TMEM allocation: one whole warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {                                                 // ===== TMA producer
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_expect_tx(full(s), kStageBytes);
+                const int k = (kb0 + kb) * BK;
+                tma_load_2d(sm_a(s), &map_a, full(s), k, m0);
+                tma_load_2d(sm_wh(s), &map_wh, full(s), k, 0);
+                tma_load_2d(sm_wl(s), &map_wl, full(s), k, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                                 // ===== MMA issuer
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                const int chunk = kb / kChunk, b = chunk & 1, first = (kb % kChunk) == 0;
+                if (first) mbar_wait(accfree(b), ((chunk >> 1) & 1) ^ 1);    // accumulator b drained (free at start)
+                mbar_wait(full(s), ph);                                  // W tiles landed (async proxy -> this thread)
+                mbar_wait(aready(s), ph);                                // A hi/lo of this stage are in TMEM
+                tc_fence_after();
+                const uint64_t dh = kmajor_sw128_desc(sm_wh(s)), dl = kmajor_sw128_desc(sm_wl(s));
+                const uint32_t a_hi = tmem_base + kColA + s * 64, a_lo = a_hi + 32;
+                const uint32_t acc = tmem_base + kColAcc + b * BN;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dh + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+                    tc_mma_tf32_ts(acc, a_lo + 8 * k, dh + 2 * k, kIdesc, 1u);
+                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dl + 2 * k, kIdesc, 1u);
+                }
+                tc_commit(empty(s));                                     // slot (smem + TMEM A columns) reusable
+                if ((kb % kChunk) == kChunk - 1 || kb == nkb - 1) tc_commit(accfull(b));
+            }
+        }
+    } else {                                                             // ===== splitters + promotion
+        const int q = warp & 3;                                          // the TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float sum[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) sum[j] = 0.0f;
+        auto promote = [&](int chunk) {                                  // sum += accumulator of `chunk` (fp32, RN)
+            const int b = chunk & 1;
+            mbar_wait(accfull(b), (chunk >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc_ld32(lane_addr + kColAcc + b * BN + h * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[h * 32 + j] += __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+            mbar_arrive(accfree(b));
+        };
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+            mbar_wait(full(s), ph);
+            const uint32_t row_addr = sm_a(s) + row * 128;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t chunk = (uint32_t)(half * 4 + c) ^ (uint32_t)(row & 7);     // SWIZZLE_128B
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(row_addr + (chunk << 4)));
+                    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h = tf32_rn(f[e]);
+                        hi[4 * c + e] = __float_as_uint(h);
+                        lo[4 * c + e] = __float_as_uint(tf32_rn(f[e] - h));
+                    }
+                }
+                tc_st16(lane_addr + kColA + s * 64 + half * 16, hi);
+                tc_st16(lane_addr + kColA + s * 64 + 32 + half * 16, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(aready(s));
+            // one chunk behind the splitting, so that the wait for the MMA never stalls the A pipeline
+            if ((kb % kChunk) == kChunk - 1 && kb / kChunk >= 1) promote(kb / kChunk - 1);
+        }
+        const int done = nkb / kChunk >= 1 ? nkb / kChunk - 1 : 0;       // chunks already promoted inside the loop
+        for (int c = done; c < n_chunks; ++c) promote(c);
+        const int m = m0 + row;
+        if (m < M) {
+            float4* out = reinterpret_cast<float4*>(partials + ((size_t)blockIdx.y * M + m) * kHidden);
+#pragma unroll
+            for (int c = 0; c < BN / 4; ++c) out[c] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layers 2 and 3
+// One thread per observation row: h1 = relu(sum of the K-slices (ascending) + time * w_time + b1); h2 = relu(W2 h1 +
+// b2); v = w3 . h2 + b3. W2 is read from shared memory as a broadcast.
+__global__ void __launch_bounds__(128) k_value_mlp_tail(const float* __restrict__ partials, int n_slices, int M,
+                                                        const float* __restrict__ time, int64_t time_stride,
+                                                        const float* __restrict__ w_time, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        const float* __restrict__ w3, const float* __restrict__ b3,
+                                                        float* __restrict__ out) {
+    __shared__ float s_w2[kHidden * kHidden];
+    __shared__ float s_vec[4 * kHidden];                 // w_time | b1 | b2 | w3
+    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s_w2[i] = w2[i];
+    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) {
+        s_vec[i] = w_time[i]; s_vec[kHidden + i] = b1[i]; s_vec[2 * kHidden + i] = b2[i]; s_vec[3 * kHidden + i] = w3[i];
+    }
+    __syncthreads();
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float h1[kHidden];
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) h1[j] = 0.0f;
+    for (int s = 0; s < n_slices; ++s) {
+        const float4* p = reinterpret_cast<const float4*>(partials + ((size_t)s * M + m) * kHidden);
+#pragma unroll
+        for (int c = 0; c < kHidden / 4; ++c) {
+            const float4 v = p[c];
+            h1[4 * c] += v.x; h1[4 * c + 1] += v.y; h1[4 * c + 2] += v.z; h1[4 * c + 3] += v.w;
+        }
+    }
+    const float t = time[m * time_stride];
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) h1[j] = fmaxf(h1[j] + t * s_vec[j] + s_vec[kHidden + j], 0.0f);
+    float v = b3[0];
+    for (int j = 0; j < kHidden; ++j) {
+        float acc = s_vec[2 * kHidden + j];
+#pragma unroll
+        for (int i = 0; i < kHidden; ++i) acc += s_w2[j * kHidden + i] * h1[i];
+        v += s_vec[3 * kHidden + j] * fmaxf(acc, 0.0f);
+    }
+    out[m] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Plan {
+    int Kp, kb_total, tiles, slices, kb_per_slice;
+    size_t off_wh, off_wl, off_wt, off_part, bytes;
+};
+
+Plan make_plan(int M, int n_nodes) {
+    Plan p;
+    p.kb_total = (n_nodes + BK - 1) / BK;
+    p.Kp = p.kb_total * BK;
+    p.tiles = (M + BM - 1) / BM;
+    int want = 148 / (p.tiles > 0 ? p.tiles : 1);        // K-slices so that tiles x slices fills the 148 SMs once
+    if (want < 1) want = 1;
+    if (want > p.kb_total) want = p.kb_total > 0 ? p.kb_total : 1;
+    p.kb_per_slice = (p.kb_total + want - 1) / want;
+    if (p.kb_per_slice < 1) p.kb_per_slice = 1;
+    p.slices = p.kb_total > 0 ? (p.kb_total + p.kb_per_slice - 1) / p.kb_per_slice : 0;
+    p.off_wh = 0;
+    p.off_wl = align_up(p.off_wh + (size_t)kHidden * p.Kp * 4, 1024);
+    p.off_wt = align_up(p.off_wl + (size_t)kHidden * p.Kp * 4, 1024);
+    p.off_part = align_up(p.off_wt + kHidden * 4, 1024);
+    p.bytes = align_up(p.off_part + (size_t)p.slices * M * kHidden * 4, 1024);
+    return p;
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled encode_fn() {
+    static EncodeTiled fn = nullptr;
+    if (fn == nullptr) {        // resolved at run time: the library carries no link-time dependency on libcuda
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiled>(p);
+    }
+    return fn;
+}
+
+// fp32 [rows, cols] with `row_stride` elements between rows, boxes of [box_rows x 32], 128-byte swizzle, zero fill
+bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int64_t row_stride, int box_rows) {
+    EncodeTiled enc = encode_fn();
+    if (enc == nullptr) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_stride * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes) {
+    if (n_rows <= 0 || n_nodes <= 0) return 0;
+    return make_plan(n_rows, n_nodes).bytes;
+}
+
+int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
+                           int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, void* workspace, size_t workspace_bytes,
+                           float* out, void* stream) {
+    if (n_rows < 0 || n_nodes <= 0) return TARL_E_BADARG;
+    if (n_rows == 0) return TARL_OK;
+    if (!occupancy || !time || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !out || !workspace) return TARL_E_BADARG;
+    // TMA addressing: 16-byte aligned base and row pitch
+    if ((reinterpret_cast<uintptr_t>(occupancy) & 15) != 0 || (occ_row_stride & 3) != 0 || occ_row_stride < n_nodes ||
+        (reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+        return TARL_E_BADARG;
+    const Plan p = make_plan(n_rows, n_nodes);
+    if (workspace_bytes < p.bytes) return TARL_E_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* w_hi = reinterpret_cast<float*>(ws + p.off_wh);
+    float* w_lo = reinterpret_cast<float*>(ws + p.off_wl);
+    float* w_time = reinterpret_cast<float*>(ws + p.off_wt);
+    float* partials = reinterpret_cast<float*>(ws + p.off_part);
+    CUtensorMap map_a, map_wh, map_wl;
+    if (!make_map(&map_a, occupancy, n_rows, n_nodes, occ_row_stride, BM) ||
+        !make_map(&map_wh, w_hi, kHidden, p.Kp, p.Kp, BN) || !make_map(&map_wl, w_lo, kHidden, p.Kp, p.Kp, BN))
+        return TARL_E_LAUNCH;
+    if (cudaFuncSetAttribute(k_value_mlp_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
+        return TARL_E_LAUNCH;
+    const int64_t n_w = (int64_t)kHidden * p.Kp;
+    k_value_mlp_split_w<<<(unsigned)((n_w + 255) / 256), 256, 0, s>>>(w1, n_nodes, p.Kp, w_hi, w_lo, w_time);
+    k_value_mlp_gemm<<<dim3(p.tiles, p.slices), kThreadsGemm, kSmemBytes, s>>>(map_a, map_wh, map_wl, n_rows, p.kb_total,
+                                                                              p.kb_per_slice, partials);
+    k_value_mlp_tail<<<(n_rows + 127) / 128, 128, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
+                                                          w3, b3, out);
+    return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+}
+
+}  // extern "C"

@@ -271,10 +271,43 @@ class MPNNValueNetSimple(MessagePassing, Agents):
                                        nn.Linear(64, 1))
         self.to(device)
 
+        self._ws = None
+
     def forward(self, node_features, edge_features, agent_index, time):
         x = torch.cat((node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time), dim=-1)
         return self.final_mlp(x)
 
     def forward_occupancy(self, num_agents, time):
-        """The same function of the only observation column it reads: num_agents [.., N_tot] = NUMBER_OF_AGENT."""
+        """The same function of the only observation column it reads: num_agents [.., N_tot] = NUMBER_OF_AGENT.
+        Without autograd (rollouts, GAE: every frame of a batch) and with a TMA-addressable occupancy matrix this is
+        the tcgen05 kernel of csrc/value_mlp.cu (3xTF32, fp32-accurate); otherwise — the 32-frame PPO update that
+        needs gradients — the library GEMM."""
+        if self._tensor_core_ok(num_agents, time):
+            return self._forward_tensor_core(num_agents, time)
         return self.final_mlp(torch.cat((num_agents, time), dim=-1))
+
+    def _tensor_core_ok(self, num, time) -> bool:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.final_mlp.parameters()):
+            return False
+        return (num.is_cuda and num.dim() == 2 and num.dtype == torch.float32 and num.size(1) == self.num_nodes
+                and num.size(0) > 0 and num.stride(1) == 1 and num.stride(0) % 4 == 0 and num.data_ptr() % 16 == 0
+                and time.numel() == num.size(0) and time.dtype == torch.float32 and time.device == num.device
+                and self.final_mlp[0].weight.device == num.device)
+
+    def _forward_tensor_core(self, num, time):
+        M, dev = num.size(0), num.device
+        lib = _cabi.lib()
+        need = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
+        if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
+        l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
+        params = [t.detach().contiguous() for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
+        tm = time.reshape(-1)
+        out = torch.empty(M, 1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_value_mlp_forward(num.data_ptr(), num.stride(0), tm.data_ptr(), tm.stride(0) if M > 1 else 1,
+                                            M, self.num_nodes, *[t.data_ptr() for t in params], ws_ptr, need,
+                                            out.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mlp_forward")
+        return out

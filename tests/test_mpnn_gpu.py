@@ -192,3 +192,37 @@ def test_value_net_vs_oracle_large(B):
     (out * w.cuda()).sum().backward()
     for k, v in net.named_parameters():
         close(v.grad, p[k].grad, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("M,N,pad", [(1, 40, 0), (100, 1000, 0), (128, 1003, 1), (300, 4096, 0), (1024, 59600, 0), (130, 24, 0)])
+def test_value_mlp_tensor_core_forward_matches_fp64(M, N, pad):
+    """MPNNValueNetSimple.forward_occupancy on the tcgen05 path (3xTF32) against the same MLP in float64: 1e-5
+    relative (the fp32 library GEMM is held to the same bar beside it). Covers the K tail (N not a multiple of 32),
+    the M tail, a padded row pitch and split-K."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNetSimple
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    ei = torch.zeros(2, 1, dtype=torch.long, device="cuda")
+    net = MPNNValueNetSimple(ei, N, "cuda")
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn(p.shape, device="cuda", generator=g) * (0.05 if p.dim() == 2 and p.size(1) > 64 else 0.3))
+    buf = torch.zeros(M, N + pad * (4 - N % 4 if N % 4 else 0), device="cuda")
+    num = buf[:, :N]
+    num.copy_(torch.randint(0, 15, (M, N), device="cuda", generator=g).float() * (torch.rand(M, N, device="cuda", generator=g) < 0.7))
+    num[:, ::7] += torch.rand(M, num[:, ::7].size(1), device="cuda", generator=g)          # non-integers too
+    time = (torch.arange(M, device="cuda", dtype=torch.float32).reshape(M, 1) % 7.0) * (3600.0 if M == 300 else 1.0)
+    with torch.no_grad():
+        assert net._tensor_core_ok(num, time) == (num.stride(0) % 4 == 0)
+        if not net._tensor_core_ok(num, time):
+            pytest.skip("row pitch not TMA-addressable: the library GEMM serves it")
+        got = net.forward_occupancy(num, time)
+        lib = net.final_mlp(torch.cat((num, time), dim=-1))
+        ref = net.final_mlp.double()(torch.cat((num, time), dim=-1).double())
+        net.final_mlp.float()
+    torch.cuda.synchronize()
+    scale = ref.abs().max().clamp_min(1.0)
+    assert float((got.double() - ref).abs().max() / scale) < 1e-5, "tcgen05 path"
+    assert float((lib.double() - ref).abs().max() / scale) < 1e-5, "library path"
+    # with autograd on, the library GEMM is used and gradients flow
+    out = net.forward_occupancy(num, time)
+    assert out.requires_grad
