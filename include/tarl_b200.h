@@ -392,13 +392,15 @@ int tarl_metrics_accumulate(const tarl_dual_csr* g, int32_t n_replicas, const ui
  *   (16-byte aligned base, occ_row_stride a multiple of 4: TMA addressing; anything else is TARL_E_BADARG and the
  *   caller uses its library GEMM). time: element m at time[m*time_stride].
  * w1 [64, n_nodes+1], b1 [64], w2 [64, 64], b2 [64], w3 [64], b3 [1]: final_mlp.{0,2,4}.{weight,bias}, row-major.
+ * weights_changed: 0 = w1 is what the previous call on this workspace (same n_rows, n_nodes) was given, so its TF32
+ *   hi/lo split kept in the workspace is reused; anything else re-splits.
  * workspace: tarl_value_mlp_workspace_bytes(n_rows, n_nodes) bytes, 1024-byte aligned. out: [n_rows].
  * Inference only (no gradient): the PPO update's 32-frame backward stays on the library GEMM. */
 size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes);
 int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
                            int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
-                           const float* b2, const float* w3, const float* b3, void* workspace, size_t workspace_bytes,
-                           float* out, void* stream);
+                           const float* b2, const float* w3, const float* b3, int32_t weights_changed, void* workspace,
+                           size_t workspace_bytes, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,3 +37,7 @@ with torch.no_grad():
         ev1.record(); torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / 20
         print(f"{name}: {ms*1e3:.1f} us for M={M}, K={N+1}: A bytes {M*N*4/1e6:.0f} MB -> {M*N*4/ms/1e6:.0f} GB/s")
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(5): net.forward_occupancy(num, time)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=6, max_name_column_width=60))

@@ -1,0 +1,15 @@
+"""Scratch: time of the three value-MLP kernels (torch.profiler) at M rows."""
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from tarl_simulator_b200.mpnn_agent import MPNNValueNetSimple
+M, N = int(sys.argv[1]), int(sys.argv[2])
+net = MPNNValueNetSimple(torch.zeros(2, 1, dtype=torch.long, device="cuda"), N, "cuda")
+num = torch.rand(M, N, device="cuda"); time = torch.rand(M, 1, device="cuda")
+with torch.no_grad():
+    for _ in range(3): net.forward_occupancy(num, time)
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(10): net.forward_occupancy(num, time)
+        torch.cuda.synchronize()
+for e in prof.key_averages():
+    if "k_value" in e.key: print("%-24s %8.1f us" % (e.key.split("::")[-1][:22], e.device_time_total / e.count))

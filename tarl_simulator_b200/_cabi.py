@@ -124,7 +124,7 @@ SIGNATURES = {
     "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P]),
     "tarl_metrics_accumulate": (C.c_int, [_CSR, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
     "tarl_value_mlp_workspace_bytes": (_SZ, [_I32, _I32]),
-    "tarl_value_mlp_forward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P]),
+    "tarl_value_mlp_forward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
 }
 
 _lib = None

@@ -31,6 +31,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tarl_b200.h"
 
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                                                                     const __grid_constant__ CUtensorMap map_wh,
                                                                     const __grid_constant__ CUtensorMap map_wl, int M,
                                                                     int kb_total, int kb_per_slice,
-                                                                    float* __restrict__ partials) {
+                                                                    float* __restrict__ partials, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles: 1024-byte aligned
     const uint32_t bars = base + STAGES * kStageBytes;
@@ -201,11 +202,13 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, ph = (kb / STAGES) & 1;
                 mbar_wait(empty(s), ph ^ 1);
-                mbar_expect_tx(full(s), kStageBytes);
+                mbar_expect_tx(full(s), (dbg & 1) ? kABytes : kStageBytes);
                 const int k = (kb0 + kb) * BK;
                 tma_load_2d(sm_a(s), &map_a, full(s), k, m0);
-                tma_load_2d(sm_wh(s), &map_wh, full(s), k, 0);
-                tma_load_2d(sm_wl(s), &map_wl, full(s), k, 0);
+                if (!(dbg & 1)) {
+                    tma_load_2d(sm_wh(s), &map_wh, full(s), k, 0);
+                    tma_load_2d(sm_wl(s), &map_wl, full(s), k, 0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                 const uint32_t a_hi = tmem_base + kColA + s * 64, a_lo = a_hi + 32;
                 const uint32_t acc = tmem_base + kColAcc + b * BN;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
+                for (int k = 0; k < ((dbg & 4) ? 1 : BK / 8); ++k) {
                     tc_mma_tf32_ts(acc, a_hi + 8 * k, dh + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
                     tc_mma_tf32_ts(acc, a_lo + 8 * k, dh + 2 * k, kIdesc, 1u);
                     tc_mma_tf32_ts(acc, a_hi + 8 * k, dl + 2 * k, kIdesc, 1u);
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
             mbar_wait(full(s), ph);
             const uint32_t row_addr = sm_a(s) + row * 128;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < ((dbg & 2) ? 0 : 2); ++half) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -301,45 +304,45 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------ layers 2 and 3
-// One thread per observation row: h1 = relu(sum of the K-slices (ascending) + time * w_time + b1); h2 = relu(W2 h1 +
-// b2); v = w3 . h2 + b3. W2 is read from shared memory as a broadcast.
-__global__ void __launch_bounds__(128) k_value_mlp_tail(const float* __restrict__ partials, int n_slices, int M,
-                                                        const float* __restrict__ time, int64_t time_stride,
-                                                        const float* __restrict__ w_time, const float* __restrict__ b1,
-                                                        const float* __restrict__ w2, const float* __restrict__ b2,
-                                                        const float* __restrict__ w3, const float* __restrict__ b3,
-                                                        float* __restrict__ out) {
-    __shared__ float s_w2[kHidden * kHidden];
-    __shared__ float s_vec[4 * kHidden];                 // w_time | b1 | b2 | w3
-    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s_w2[i] = w2[i];
-    for (int i = threadIdx.x; i < kHidden; i += blockDim.x) {
-        s_vec[i] = w_time[i]; s_vec[kHidden + i] = b1[i]; s_vec[2 * kHidden + i] = b2[i]; s_vec[3 * kHidden + i] = w3[i];
-    }
+// One WARP per observation row, lane j owns hidden units j and j + 32: h1 = relu(sum of the K-slices (ascending,
+// coalesced 256-byte rows) + time * w_time + b1); h2 = relu(W2 h1 + b2) with W2 transposed in shared memory (lanes
+// read consecutive words, h1 is a broadcast); v = w3 . h2 + b3 by a shuffle tree.
+constexpr int kTailWarps = 8;
+__global__ void __launch_bounds__(kTailWarps * 32) k_value_mlp_tail(const float* __restrict__ partials, int n_slices, int M,
+                                                                    const float* __restrict__ time, int64_t time_stride,
+                                                                    const float* __restrict__ w_time,
+                                                                    const float* __restrict__ b1,
+                                                                    const float* __restrict__ w2,
+                                                                    const float* __restrict__ b2,
+                                                                    const float* __restrict__ w3,
+                                                                    const float* __restrict__ b3, float* __restrict__ out) {
+    __shared__ float s_w2t[kHidden][kHidden + 1];        // [i][j] = W2[j][i]
+    __shared__ float s_h1[kTailWarps][kHidden];
+    for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s_w2t[i % kHidden][i / kHidden] = w2[i];
     __syncthreads();
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.x * kTailWarps + warp;
     if (m >= M) return;
-    float h1[kHidden];
-#pragma unroll
-    for (int j = 0; j < kHidden; ++j) h1[j] = 0.0f;
+    float a0 = 0.0f, a1 = 0.0f;
     for (int s = 0; s < n_slices; ++s) {
-        const float4* p = reinterpret_cast<const float4*>(partials + ((size_t)s * M + m) * kHidden);
-#pragma unroll
-        for (int c = 0; c < kHidden / 4; ++c) {
-            const float4 v = p[c];
-            h1[4 * c] += v.x; h1[4 * c + 1] += v.y; h1[4 * c + 2] += v.z; h1[4 * c + 3] += v.w;
-        }
+        const float* p = partials + ((size_t)s * M + m) * kHidden;
+        a0 += p[lane];
+        a1 += p[lane + 32];
     }
     const float t = time[m * time_stride];
-#pragma unroll
-    for (int j = 0; j < kHidden; ++j) h1[j] = fmaxf(h1[j] + t * s_vec[j] + s_vec[kHidden + j], 0.0f);
-    float v = b3[0];
-    for (int j = 0; j < kHidden; ++j) {
-        float acc = s_vec[2 * kHidden + j];
-#pragma unroll
-        for (int i = 0; i < kHidden; ++i) acc += s_w2[j * kHidden + i] * h1[i];
-        v += s_vec[3 * kHidden + j] * fmaxf(acc, 0.0f);
+    s_h1[warp][lane] = fmaxf(a0 + t * w_time[lane] + b1[lane], 0.0f);
+    s_h1[warp][lane + 32] = fmaxf(a1 + t * w_time[lane + 32] + b1[lane + 32], 0.0f);
+    __syncwarp();
+    float c0 = b2[lane], c1 = b2[lane + 32];
+#pragma unroll 16
+    for (int i = 0; i < kHidden; ++i) {
+        const float h = s_h1[warp][i];
+        c0 += s_w2t[i][lane] * h;
+        c1 += s_w2t[i][lane + 32] * h;
     }
-    out[m] = v;
+    float v = w3[lane] * fmaxf(c0, 0.0f) + w3[lane + 32] * fmaxf(c1, 0.0f);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[m] = v + b3[0];
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -407,8 +410,8 @@ size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes) {
 
 int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
                            int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
-                           const float* b2, const float* w3, const float* b3, void* workspace, size_t workspace_bytes,
-                           float* out, void* stream) {
+                           const float* b2, const float* w3, const float* b3, int32_t weights_changed, void* workspace,
+                           size_t workspace_bytes, float* out, void* stream) {
     if (n_rows < 0 || n_nodes <= 0) return TARL_E_BADARG;
     if (n_rows == 0) return TARL_OK;
     if (!occupancy || !time || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !out || !workspace) return TARL_E_BADARG;
@@ -431,10 +434,11 @@ int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const
     if (cudaFuncSetAttribute(k_value_mlp_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
         return TARL_E_LAUNCH;
     const int64_t n_w = (int64_t)kHidden * p.Kp;
-    k_value_mlp_split_w<<<(unsigned)((n_w + 255) / 256), 256, 0, s>>>(w1, n_nodes, p.Kp, w_hi, w_lo, w_time);
+    if (weights_changed)
+        k_value_mlp_split_w<<<(unsigned)((n_w + 255) / 256), 256, 0, s>>>(w1, n_nodes, p.Kp, w_hi, w_lo, w_time);
     k_value_mlp_gemm<<<dim3(p.tiles, p.slices), kThreadsGemm, kSmemBytes, s>>>(map_a, map_wh, map_wl, n_rows, p.kb_total,
-                                                                              p.kb_per_slice, partials);
-    k_value_mlp_tail<<<(n_rows + 127) / 128, 128, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
+                                                                              p.kb_per_slice, partials, getenv("TARL_VMLP_DEBUG") ? atoi(getenv("TARL_VMLP_DEBUG")) : 0);
+    k_value_mlp_tail<<<(n_rows + kTailWarps - 1) / kTailWarps, kTailWarps * 32, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
                                                           w3, b3, out);
     return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
 }

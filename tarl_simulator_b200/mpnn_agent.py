@@ -272,6 +272,7 @@ class MPNNValueNetSimple(MessagePassing, Agents):
         self.to(device)
 
         self._ws = None
+        self._ws_key = None
 
     def forward(self, node_features, edge_features, agent_index, time):
         x = torch.cat((node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time), dim=-1)
@@ -298,16 +299,21 @@ class MPNNValueNetSimple(MessagePassing, Agents):
         M, dev = num.size(0), num.device
         lib = _cabi.lib()
         need = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
+        l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
+        # the workspace keeps the TF32 hi/lo split of W1: redone only when the weight (or the problem shape) changes
+        key = (M, l1.weight.data_ptr(), l1.weight._version)
         if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+            self._ws_key = None
+        changed = self._ws_key != key
+        self._ws_key = key
         ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
-        l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
         params = [t.detach().contiguous() for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
         tm = time.reshape(-1)
         out = torch.empty(M, 1, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = lib.tarl_value_mlp_forward(num.data_ptr(), num.stride(0), tm.data_ptr(), tm.stride(0) if M > 1 else 1,
-                                            M, self.num_nodes, *[t.data_ptr() for t in params], ws_ptr, need,
-                                            out.data_ptr(), _stream(dev))
+                                            M, self.num_nodes, *[t.data_ptr() for t in params], int(changed), ws_ptr,
+                                            need, out.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mlp_forward")
         return out
