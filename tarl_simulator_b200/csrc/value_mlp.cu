@@ -11,18 +11,20 @@
 //   a·w ~= a_hi·w_hi + a_lo·w_hi + a_hi·w_lo          (three kind::tf32 MMAs, fp32 accumulation in TMEM)
 // which leaves a relative error of ~2^-23 per product with a random sign.
 //
-// Data flow per CTA (one 128-row tile of A x one K-slice), 6 warps:
-//   warp 0      TMA producer: A tile [128 x 32] fp32 and the matching [64 x 32] tiles of W_hi / W_lo into a 6-stage
-//               shared-memory ring (128-byte swizzle), completion on mbarriers (cp.async.bulk.tensor).
+// Data flow per CTA (one 128-row tile of A x one K-slice), 7 warps:
+//   warps 0, 6  TMA producers: A tiles [128 x 32] fp32 into an 8-slot shared-memory ring, the matching [64 x 32]
+//               tiles of W_hi / W_lo into a 4-slot ring (128-byte swizzle), completion on mbarriers
+//               (cp.async.bulk.tensor).
 //   warps 2-5   splitters: thread r owns row r of the tile — reads its 128 bytes from shared memory, splits each value
 //               into hi/lo and stores both into TENSOR MEMORY (tcgen05.st, lane r, 32 + 32 columns per stage). A is
 //               then an MMA operand straight from TMEM: its hi/lo copies never touch shared memory, whose bandwidth
 //               would otherwise cap the kernel (3 MMAs x (A + B) re-read per k-step).
-//   warp 1      MMA issuer (one thread): per k-step of 8 columns three tcgen05.mma.kind::tf32 (A from TMEM, B from
-//               shared memory through a K-major SWIZZLE_128B descriptor) into a 128 x 64 fp32 accumulator in TMEM;
-//               tcgen05.commit releases the ring slot / publishes the accumulator.
+//   warp 1      MMA issuer (one thread): per k-step of 8 columns two tcgen05.mma.kind::tf32 (A from TMEM, B from
+//               shared memory through a K-major SWIZZLE_128B descriptor): a_hi x [w_hi; w_lo] (N = 128) and
+//               a_lo x w_hi (N = 64) into a 128 x 128 fp32 accumulator in TMEM; tcgen05.commit releases the ring
+//               slots / publishes the accumulator.
 //   warps 2-5   promotion: the tensor core adds into its fp32 accumulator with truncation, a bias that over the
-//               ~2e4 accumulation steps of a K = 6e4 row reaches 1e-4 relative (measured). Every 128 columns the MMA
+//               ~2e4 accumulation steps of a K = 6e4 row reaches 1e-4 relative (measured). Every 256 columns the MMA
 //               therefore switches between two TMEM accumulators and these warps tcgen05.ld the finished one and
 //               add it into fp32 registers with round-to-nearest (the same remedy as for FP8 accumulators); at the
 //               end one row per thread goes to the split-K partial buffer.
@@ -37,14 +39,19 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, STAGES = 6;
+constexpr int BM = 128, BN = 64, BK = 32;
+#ifndef TARL_VMLP_GROUP
+#define TARL_VMLP_GROUP 2
+#endif
+constexpr int kGroup = TARL_VMLP_GROUP;                // A tiles requested together (NA must be a multiple)
+constexpr int NA = 8, NW = 4, NT = 4;                  // ring depths: A tiles (smem), W tiles (smem), A hi/lo (TMEM)
 constexpr int kHidden = 64;
-constexpr int kThreadsGemm = 192;
-constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4, kStageBytes = kABytes + 2 * kBBytes;
-constexpr uint32_t kTmemCols = 512;                    // 2 x 64 accumulator + 6 x (32 hi + 32 lo)
-constexpr uint32_t kColAcc = 0, kColA = 128;
-constexpr int kChunk = 4;                              // k-blocks (128 columns of A) accumulated in TMEM before promotion
-constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int kThreadsGemm = 224;
+constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
+constexpr uint32_t kTmemCols = 512;                    // 2 x 128 accumulator + 4 x (32 hi + 32 lo)
+constexpr uint32_t kColAcc = 0, kAccCols = 2 * BN, kColA = 2 * kAccCols;
+constexpr int kChunk = 8;                              // k-blocks (256 columns of A) accumulated in TMEM before promotion
+constexpr size_t kSmemBytes = (size_t)NA * kABytes + (size_t)NW * 2 * kBBytes + 1024 /* alignment slack */ + 512 /* barriers */;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -125,8 +132,9 @@ __device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+constexpr uint32_t idesc_tf32(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+constexpr uint32_t kIdesc64 = idesc_tf32(BN), kIdesc128 = idesc_tf32(2 * BN);
 
 constexpr uint32_t kHiMask = 0xFFFFE000u;               // sign + exponent + the 10 mantissa bits TF32 keeps
 // Round to nearest TF32 (ties away from zero). Truncation would do for the arithmetic, but its error always points
@@ -152,23 +160,30 @@ __global__ void __launch_bounds__(256) k_value_mlp_split_w(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ first layer
+// Three rings decouple the three latencies: A tiles in shared memory (TMA -> splitters; a slot is free again as soon
+// as its rows sit in registers, so its cycle is HBM latency + split, not + MMA), A hi/lo in TMEM (splitters -> MMA),
+// W tiles in shared memory (TMA from L2 -> MMA).
 __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_wh,
                                                                     const __grid_constant__ CUtensorMap map_wl, int M,
                                                                     int kb_total, int kb_per_slice,
-                                                                    float* __restrict__ partials, int dbg) {
+                                                                    float* __restrict__ partials) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles: 1024-byte aligned
-    const uint32_t bars = base + STAGES * kStageBytes;
-    auto sm_a = [&](int s) { return base + s * kStageBytes; };
-    auto sm_wh = [&](int s) { return base + s * kStageBytes + kABytes; };
-    auto sm_wl = [&](int s) { return base + s * kStageBytes + kABytes + kBBytes; };
-    auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto aready = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    auto accfull = [&](int b) { return bars + 8u * (3 * STAGES + b); };
-    auto accfree = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+    const uint32_t w_base = base + NA * kABytes;
+    const uint32_t bars = w_base + NW * 2 * kBBytes;
+    auto sm_a = [&](int s) { return base + s * kABytes; };
+    auto sm_wh = [&](int s) { return w_base + s * 2 * kBBytes; };
+    auto sm_wl = [&](int s) { return w_base + s * 2 * kBBytes + kBBytes; };
+    auto a_full = [&](int s) { return bars + 8u * s; };
+    auto a_empty = [&](int s) { return bars + 8u * (NA + s); };
+    auto w_full = [&](int s) { return bars + 8u * (2 * NA + s); };
+    auto w_empty = [&](int s) { return bars + 8u * (2 * NA + NW + s); };
+    auto t_ready = [&](int s) { return bars + 8u * (2 * NA + 2 * NW + s); };
+    auto t_empty = [&](int s) { return bars + 8u * (2 * NA + 2 * NW + NT + s); };
+    auto accfull = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + b); };
+    auto accfree = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * NA + 2 * NW + 2 * NT + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
     const int kb0 = blockIdx.y * kb_per_slice;
@@ -176,15 +191,10 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     const int n_chunks = (nkb + kChunk - 1) / kChunk;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
-            mbar_init(aready(s), 128);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(accfull(b), 1);
-            mbar_init(accfree(b), 128);
-        }
+        for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 128); }
+        for (int s = 0; s < NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int s = 0; s < NT; ++s) { mbar_init(t_ready(s), 128); mbar_init(t_empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(accfull(b), 1); mbar_init(accfree(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                                     // TMEM allocation: one whole warp
@@ -198,42 +208,56 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {                                                 // ===== TMA producer
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-                mbar_wait(empty(s), ph ^ 1);
-                mbar_expect_tx(full(s), (dbg & 1) ? kABytes : kStageBytes);
-                const int k = (kb0 + kb) * BK;
-                tma_load_2d(sm_a(s), &map_a, full(s), k, m0);
-                if (!(dbg & 1)) {
-                    tma_load_2d(sm_wh(s), &map_wh, full(s), k, 0);
-                    tma_load_2d(sm_wl(s), &map_wl, full(s), k, 0);
+        if (lane == 0) {                                                 // ===== TMA producer, A tiles (HBM)
+            // kGroup consecutive k-blocks are requested back to back: per row of A that is kGroup x 128 contiguous
+            // bytes arriving at the memory controller together instead of 128-byte pieces one k-block period apart
+            for (int kg = 0; kg < nkb; kg += kGroup) {
+                const int n = min(kGroup, nkb - kg);
+                for (int i = 0; i < n; ++i) mbar_wait(a_empty((kg + i) % NA), (((kg + i) / NA) & 1) ^ 1);
+                for (int i = 0; i < n; ++i) {
+                    const int kb = kg + i, s = kb % NA;
+                    mbar_expect_tx(a_full(s), kABytes);
+                    tma_load_2d(sm_a(s), &map_a, a_full(s), (kb0 + kb) * BK, m0);
                 }
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {                                                 // ===== TMA producer, W tiles (L2)
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NW, ph = (kb / NW) & 1;
+                mbar_wait(w_empty(s), ph ^ 1);
+                mbar_expect_tx(w_full(s), 2 * kBBytes);
+                tma_load_2d(sm_wh(s), &map_wh, w_full(s), (kb0 + kb) * BK, 0);
+                tma_load_2d(sm_wl(s), &map_wl, w_full(s), (kb0 + kb) * BK, 0);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                                 // ===== MMA issuer
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+                const int sw = kb % NW, pw = (kb / NW) & 1, st = kb % NT, pt = (kb / NT) & 1;
                 const int chunk = kb / kChunk, b = chunk & 1, first = (kb % kChunk) == 0;
                 if (first) mbar_wait(accfree(b), ((chunk >> 1) & 1) ^ 1);    // accumulator b drained (free at start)
-                mbar_wait(full(s), ph);                                  // W tiles landed (async proxy -> this thread)
-                mbar_wait(aready(s), ph);                                // A hi/lo of this stage are in TMEM
+                mbar_wait(w_full(sw), pw);                               // W tiles landed (async proxy -> this thread)
+                mbar_wait(t_ready(st), pt);                              // A hi/lo of this k-block are in TMEM
                 tc_fence_after();
-                const uint64_t dh = kmajor_sw128_desc(sm_wh(s)), dl = kmajor_sw128_desc(sm_wl(s));
-                const uint32_t a_hi = tmem_base + kColA + s * 64, a_lo = a_hi + 32;
-                const uint32_t acc = tmem_base + kColAcc + b * BN;
+                // The W slot holds W_hi (rows 0-63) directly followed by W_lo (rows 64-127): ONE N = 128 MMA gives
+                // a_hi.w_hi (accumulator columns 0-63) and a_hi.w_lo (columns 64-127); a second, N = 64, adds
+                // a_lo.w_hi onto columns 0-63. (Measured: a 128 x 64 x 8 MMA costs ~75 cycles to dispatch, more than
+                // twice its 32-cycle floor, so three N = 64 MMAs per k-step made the issuing thread the bottleneck.)
+                const uint64_t dw = kmajor_sw128_desc(sm_wh(sw));
+                const uint32_t a_hi = tmem_base + kColA + st * 64, a_lo = a_hi + 32;
+                const uint32_t acc = tmem_base + kColAcc + b * kAccCols;
 #pragma unroll
-                for (int k = 0; k < ((dbg & 4) ? 1 : BK / 8); ++k) {
-                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dh + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
-                    tc_mma_tf32_ts(acc, a_lo + 8 * k, dh + 2 * k, kIdesc, 1u);
-                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dl + 2 * k, kIdesc, 1u);
+                for (int k = 0; k < BK / 8; ++k) {
+                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dw + 2 * k, kIdesc128, (first && k == 0) ? 0u : 1u);
+                    tc_mma_tf32_ts(acc, a_lo + 8 * k, dw + 2 * k, kIdesc64, 1u);
                 }
-                tc_commit(empty(s));                                     // slot (smem + TMEM A columns) reusable
+                tc_commit(w_empty(sw));                                  // W slot reusable
+                tc_commit(t_empty(st));                                  // TMEM A columns reusable
                 if ((kb % kChunk) == kChunk - 1 || kb == nkb - 1) tc_commit(accfull(b));
             }
         }
-    } else {                                                             // ===== splitters + promotion
+    } else {                                                             // ===== splitters + promotion (warps 2-5)
         const int q = warp & 3;                                          // the TMEM lane quarter this warp may touch
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -245,44 +269,50 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
             mbar_wait(accfull(b), (chunk >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 4; ++h) {                                // columns 64-127 (a_hi.w_lo) fold onto 0-63
                 uint32_t v[32];
-                tc_ld32(lane_addr + kColAcc + b * BN + h * 32, v);
+                tc_ld32(lane_addr + kColAcc + b * kAccCols + h * 32, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[h * 32 + j] += __uint_as_float(v[j]);
+                for (int j = 0; j < 32; ++j) sum[(h & 1) * 32 + j] += __uint_as_float(v[j]);
             }
             tc_fence_before();
             mbar_arrive(accfree(b));
         };
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-            mbar_wait(full(s), ph);
-            const uint32_t row_addr = sm_a(s) + row * 128;
+            const int sa = kb % NA, pa = (kb / NA) & 1, st = kb % NT, pt = (kb / NT) & 1;
+            mbar_wait(a_full(sa), pa);
+            const uint32_t row_addr = sm_a(sa) + row * 128;
+            uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int half = 0; half < ((dbg & 2) ? 0 : 2); ++half) {
-                uint32_t hi[16], lo[16];
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t chunk = (uint32_t)c ^ (uint32_t)(row & 7);                      // SWIZZLE_128B
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(row_addr + (chunk << 4)));
+                const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t chunk = (uint32_t)(half * 4 + c) ^ (uint32_t)(row & 7);     // SWIZZLE_128B
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                                 : "r"(row_addr + (chunk << 4)));
-                    const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float h = tf32_rn(f[e]);
-                        hi[4 * c + e] = __float_as_uint(h);
-                        lo[4 * c + e] = __float_as_uint(tf32_rn(f[e] - h));
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const float h = tf32_rn(f[e]);
+                    hi[4 * c + e] = __float_as_uint(h);
+                    lo[4 * c + e] = __float_as_uint(tf32_rn(f[e] - h));
                 }
-                tc_st16(lane_addr + kColA + s * 64 + half * 16, hi);
-                tc_st16(lane_addr + kColA + s * 64 + 32 + half * 16, lo);
+            }
+            mbar_arrive(a_empty(sa));                                    // the row is in registers: slot back to the TMA
+            mbar_wait(t_empty(st), pt ^ 1);                              // MMAs that read these TMEM columns are done
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t h16[16], l16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { h16[j] = hi[half * 16 + j]; l16[j] = lo[half * 16 + j]; }
+                tc_st16(lane_addr + kColA + st * 64 + half * 16, h16);
+                tc_st16(lane_addr + kColA + st * 64 + 32 + half * 16, l16);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(aready(s));
+            mbar_arrive(t_ready(st));
             // one chunk behind the splitting, so that the wait for the MMA never stalls the A pipeline
             if ((kb % kChunk) == kChunk - 1 && kb / kChunk >= 1) promote(kb / kChunk - 1);
         }
@@ -437,7 +467,7 @@ int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const
     if (weights_changed)
         k_value_mlp_split_w<<<(unsigned)((n_w + 255) / 256), 256, 0, s>>>(w1, n_nodes, p.Kp, w_hi, w_lo, w_time);
     k_value_mlp_gemm<<<dim3(p.tiles, p.slices), kThreadsGemm, kSmemBytes, s>>>(map_a, map_wh, map_wl, n_rows, p.kb_total,
-                                                                              p.kb_per_slice, partials, getenv("TARL_VMLP_DEBUG") ? atoi(getenv("TARL_VMLP_DEBUG")) : 0);
+                                                                              p.kb_per_slice, partials);
     k_value_mlp_tail<<<(n_rows + kTailWarps - 1) / kTailWarps, kTailWarps * 32, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
                                                           w3, b3, out);
     return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
