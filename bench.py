@@ -454,6 +454,9 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     iters = max(min(args.steps // 10, 50), 5)
     pol_ms = timed(policy_iter, iters)
     val_ms = timed(value_iter, iters)
+    del policy, value, nf, ai, action
+    torch.cuda.empty_cache()
+    vmlp = value_mlp_bench(dev, timed, world, peak)
     # algorithmic bytes per edge: policy 28 B + GraphDistribution 24 B = 52 B/edge (+4 B/node)
     pol_bytes = B * (52 * E_full + 4 * N_tot)
     val_bytes = B * (2 * (12 * E_full) + 2 * 68 * N_tot)          # fwd + bwd: 12 B/edge + 68 B/node each
@@ -468,7 +471,50 @@ def mpnn_bench(args, g, dev, world, rank, peak):
                           "what": "MPNNValueNet.forward (eval) -> backward (project, aggregate, node_grad, edge_grad, finish)",
                           "roofline": {"bound": "hbm", "algorithmic_bytes": int(val_bytes),
                                        "achieved": round(val_bytes / (val_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                                       "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}}}
+                                       "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}},
+            "value_mlp": vmlp}
+
+
+def value_mlp_bench(dev, timed, world, peak):
+    """MPNNValueNetSimple (the value net Runner wires, src/runner.py:68) evaluated for one environment step of 1024
+    grid100 replicas: [1024, 59600] occupancies -> values. tcgen05 path (csrc/value_mlp.cu: 3xTF32, TMA, TMEM) beside
+    the library GEMM path of the same module. The layer reads the occupancy matrix once: HBM-bound on the tensor pipe
+    (32 flop per byte), so the roofline is algorithmic bytes (the matrix) over the measured HBM peak; the tensor-pipe
+    share is in the ncu summary under profiles/."""
+    import torch
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNetSimple
+    M, N_tot = 1024, 59600
+    net = MPNNValueNetSimple(torch.zeros(2, 1, dtype=torch.long, device=dev), N_tot, str(dev))
+    g = torch.Generator(device=dev).manual_seed(11)
+    num = torch.randint(0, 12, (M, N_tot), device=dev, generator=g).float()
+    tm = torch.full((M, 1), 21600.0, device=dev)
+    with torch.no_grad():
+        assert net._tensor_core_ok(num, tm)
+        a = net.forward_occupancy(num, tm)
+        b = net.final_mlp(torch.cat((num, tm), dim=-1))
+        rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+
+        def tc():
+            net.forward_occupancy(num, tm)
+
+        def lib():
+            net.final_mlp(torch.cat((num, tm), dim=-1))
+
+        tc_ms = timed(tc, 20)
+        lib_ms = timed(lib, 20)
+    a_bytes = M * N_tot * 4
+    flops = 2 * M * (N_tot + 1) * 64
+    return {"metric": "value MLP observation rows/s", "rows": M, "nodes": N_tot,
+            "tcgen05": {"value": round(world * M / (tc_ms / 1e3), 1), "ms": round(tc_ms, 4),
+                        "what": "tarl_value_mlp_forward: TMA -> TMEM split -> tcgen05.mma kind::tf32 (3xTF32), split-K, "
+                                "fused 64x64 + 64x1 tail; W1 hi/lo split cached"},
+            "library": {"value": round(world * M / (lib_ms / 1e3), 1), "ms": round(lib_ms, 4),
+                        "what": "torch.cat + nn.Linear x3 (cuBLAS fp32 SIMT)"},
+            "max_rel_diff_vs_library": rel,
+            "roofline": {"bound": "hbm", "algorithmic_bytes": a_bytes, "achieved": round(a_bytes / (tc_ms / 1e3) / 1e9, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(a_bytes / (tc_ms / 1e3) / 1e9 / peak, 4),
+                         "useful_tflops": round(flops / (tc_ms / 1e3) / 1e12, 2),
+                         "issued_tf32_tflops": round(3 * flops / (tc_ms / 1e3) / 1e12, 2)}}
 
 
 def ppo_bench(args, dev, world, rank):

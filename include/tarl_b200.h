@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 9
+#define TARL_ABI_VERSION 10
 
 /* return codes */
 #define TARL_OK 0
@@ -251,11 +251,16 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
                             const tarl_rows* action, int32_t action_dtype, const float* grad_log_prob,
                             const float* grad_entropy, const float* log_prob, const tarl_rows* grad_logits, void* stream);
 
-/* GraphDistribution.sample (:57-80): uniforms [B,K], one per (row, group) in ascending source id; onehot [B,E] out in
- * int64 (TARL_ACTION_I64, the reference's dtype) or uint8 / bool (TARL_ACTION_U8), zeroed by the CALLER. Inside a
- * group edges are walked in ascending edge id (D3); batched rows are independent (D7). */
+/* GraphDistribution.sample (:57-80): uniforms [B,K] (any strides; group-major memory reads fastest), one per (row,
+ * group) in ascending source id; onehot [B,E] out in
+ * int64 (TARL_ACTION_I64, the reference's dtype) or uint8 / bool (TARL_ACTION_U8), every entry written. Inside a
+ * group edges are walked in ascending edge id (D3); batched rows are independent (D7).
+ * log_prob: NULL, or [B] out = log_prob of the sampled action, accumulated in the same pass (needs `partials` as for
+ * tarl_graphdist_forward). Only with edge-major fp32 logits, an edge-major uint8 one-hot and B in {4, 8, 16, 32k}
+ * (the layout MPNNPolicyNet emits); TARL_E_BADARG otherwise — callers then use tarl_graphdist_forward. */
 int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
-                          const float* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, void* stream);
+                          const tarl_rows* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, float* log_prob,
+                          float* partials, void* stream);
 
 /* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
  * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]
@@ -325,6 +330,9 @@ typedef struct tarl_agent_index {
     const int32_t* org_ptr;   /* [n_nodes+1] */
     const int32_t* org_agent; /* [n_rows]    */
     const int32_t* origins;   /* [n_origins] */
+    const float* dep_sorted;  /* [n_rows] or NULL: DEPARTURE_TIME of the agents of node o in ASCENDING order at
+                                 [org_ptr[o] .. org_ptr[o+1]) (static and identical in every replica); lets
+                                 tarl_agents_insert count the departed agents of an origin without reading their rows */
 } tarl_agent_index;
 
 /* Replaces Agents.insert_agent_into_network (src/agents/base.py:244-331): every agent with DEPARTURE_TIME <= t,
@@ -332,10 +340,13 @@ typedef struct tarl_agent_index {
  * in ascending agent id (declared divergence D3) are appended at the tail with arrival t and exit time
  * t + max(FFTT, cc/(MAXN+10-NUM_before)); NUM += admitted; ON_WAY = 1.
  * Scratch (caller-owned int32): head [R*N] initialised to -1 ONCE by the caller (the kernels leave it at -1),
- * next [R*n_origins], cursor [R*n_origins]. counters: NULL or [R*2] {inserted, withdrawn} running totals. */
+ * next [R*n_origins], cursor [R*n_origins]. counters: NULL or [R*2] {inserted, withdrawn} running totals.
+ * inserted: NULL, or [R*n_origins] agents inserted so far per (replica, origin) — maintained here, zeroed by the caller
+ * whenever it resets ON_WAY / DONE, valid only while nothing else edits those columns; with index->dep_sorted it lets
+ * origins without a waiting agent be skipped without touching agent_features (identical results). */
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
-                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* flags,
-                       void* stream);
+                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
+                       int32_t* flags, void* stream);
 
 /* Replaces Agents.withdraw_agent_from_network (src/agents/base.py:334-403): per link the maximal prefix of queue
  * slots k < NUM whose exit time <= t and whose agent's DESTINATION node is adjacent to the link — adjacency = CSR of
@@ -357,6 +368,13 @@ int tarl_agents_choice(const tarl_agent_state* state, const tarl_csr* neighbours
  * with any strides (what GraphDistribution.sample returns is edge-major). */
 int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_src, const int32_t* edge_dst,
                              int32_t n_edges, const tarl_rows* action, int32_t action_dtype, void* stream);
+
+/* The same write with the edges grouped by source node: groups = CSR of the FULL edge_index by source RANK (ptr
+ * [K+1], eid [E_full] ascending inside a group; idx unused), group_node [K] = node id of each group. Tiled so that
+ * both the action reads (replica innermost) and the SELECTED_ROAD writes (node innermost) are coalesced; a group with
+ * several selected edges keeps the last one in ascending edge id, one without leaves SELECTED_ROAD untouched. */
+int tarl_agents_apply_action_groups(const tarl_agent_state* state, const tarl_csr* groups, const int32_t* group_node,
+                                    const int32_t* edge_dst, const tarl_rows* action, int32_t action_dtype, void* stream);
 
 /* state() (src/transportation_simulator.py:360-366) and the reward term of SimulatorEnv._step
  * (src/reinforcement_learning.py:266) from a link store: node_features [R, n_nodes, 7] = {MAXN, NUM, FFTT, LENGTH,

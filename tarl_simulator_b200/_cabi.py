@@ -79,7 +79,7 @@ class AgentTable(C.Structure):
 class AgentIndex(C.Structure):
     """struct tarl_agent_index"""
     _fields_ = [("n_nodes", C.c_int32), ("n_origins", C.c_int32), ("org_ptr", C.c_void_p), ("org_agent", C.c_void_p),
-                ("origins", C.c_void_p)]
+                ("origins", C.c_void_p), ("dep_sorted", C.c_void_p)]
 
 
 _P, _F, _I32, _I64, _SZ = C.c_void_p, C.c_float, C.c_int32, C.c_int64, C.c_size_t
@@ -111,16 +111,17 @@ SIGNATURES = {
     "tarl_graphdist_partial_count": (_I32, [_I32, _I32]),
     "tarl_graphdist_forward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _ROWS, _ROWS, _P, _P, _P, _P]),
     "tarl_graphdist_backward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _P, _P, _P, _ROWS, _P]),
-    "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _P, _ROWS, _I32, _P]),
+    "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _ROWS, _I32, _P, _P, _P]),
     "tarl_value_mp_partial_count": (_I32, [_I32, _I32]),
     "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
                                         _P, _P, _P]),
     "tarl_value_mp_backward": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P,
                                          _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
-    "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P]),
+    "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_withdraw": (C.c_int, [_AST, _ATB, _CSR1, _F, _P, _P, _P, _P]),
     "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),
     "tarl_agents_apply_action": (C.c_int, [_AST, _P, _P, _I32, _ROWS, _I32, _P]),
+    "tarl_agents_apply_action_groups": (C.c_int, [_AST, _CSR1, _P, _P, _ROWS, _I32, _P]),
     "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P]),
     "tarl_metrics_accumulate": (C.c_int, [_CSR, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
     "tarl_value_mlp_workspace_bytes": (_SZ, [_I32, _I32]),

@@ -39,8 +39,14 @@ class PopulationIndex:
         self.origins = torch.nonzero(counts > 0).flatten().to(torch.int32)
         self.n_origins = int(self.origins.numel())
         self.n_nodes = n_nodes
+        # DEPARTURE_TIME of every origin's agents in ascending order (static: lets insertion count the departed
+        # agents of an origin without reading their rows, see tarl_agents_insert's `inserted`)
+        dep = agent_features[..., AgentFeatureHelpers.DEPARTURE_TIME].reshape(-1, agent_features.size(-2))[0].to(torch.float32)
+        by_dep = torch.argsort(dep, stable=True)
+        order = by_dep[torch.argsort(origin[by_dep], stable=True)]
+        self.dep_sorted = dep[order].contiguous()
         self.struct = _cabi.AgentIndex(n_nodes, self.n_origins, self.org_ptr.data_ptr(), self.org_agent.data_ptr(),
-                                       self.origins.data_ptr())
+                                       self.origins.data_ptr(), self.dep_sorted.data_ptr())
 
     def ref(self):
         return C.byref(self.struct)
@@ -201,7 +207,7 @@ class Agents(AgentFeatureHelpers):
         flags = self._flag_words(dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(tab), idx.ref(), float(self.time),
-                                                head.data_ptr(), nxt.data_ptr(), cur.data_ptr(), None,
+                                                head.data_ptr(), nxt.data_ptr(), cur.data_ptr(), None, None,
                                                 flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_agents_insert")
         return graph.x

@@ -19,6 +19,7 @@
 //   k_insert_admit  thread per (replica, road with a list): merges by smallest agent id until the room is used up
 // The merge result does not depend on the order of the list, so the atomics leave no nondeterminism behind.
 #include "engine_common.cuh"
+#include "tile_map.cuh"
 
 using namespace tarl;
 
@@ -154,13 +155,26 @@ __device__ __forceinline__ bool agent_ready(const AgentTable& at, int r, int a, 
 template <class Acc>
 __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_index ai, AgentTable at, float t,
                                                            int32_t* __restrict__ head, int32_t* __restrict__ next,
-                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ flags) {
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
+                                                           const int32_t* __restrict__ inserted) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= ai.n_origins) return;
     const int r = blockIdx.y;
     const int o = ai.origins[i];
-    const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
     const size_t ri = (size_t)r * ai.n_origins + i;
+    if (inserted != nullptr && ai.dep_sorted != nullptr) {
+        // How many of this origin's agents have departed by now (static, ascending departure times) against how many
+        // this replica has inserted so far: equal = nobody is waiting, and neither the road's list nor the scan over
+        // the origin's agent rows (the whole cost of an insertion step in steady state) is needed.
+        int lo = ai.org_ptr[o], hi = ai.org_ptr[o + 1];
+        const int k0 = lo;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (ai.dep_sorted[mid] <= t) lo = mid + 1; else hi = mid;
+        }
+        if (lo - k0 <= inserted[ri]) { next[ri] = -2; return; }
+    }
+    const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
     cursor[ri] = ai.org_ptr[o];
     if (road < 0 || road >= acc.N) {          // not a road: harmless unless one of this origin's agents is ready, in
         bool any = false;                     // which case the reference would index a non-road row (or wrap around)
@@ -175,7 +189,8 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
 template <class Acc>
 __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_index ai, AgentTable at, float t,
                                                            int32_t* __restrict__ head, const int32_t* __restrict__ next,
-                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ counters) {
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
+                                                           int32_t* __restrict__ inserted) {
     const int n = blockIdx.x * kThreads + threadIdx.x;
     if (n >= acc.N) return;
     const int r = blockIdx.y;
@@ -207,6 +222,7 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
         Acc::put(l, q0 + admitted, (float)best_a, t, dep);                       // :310-325
         at.row(r, best_a)[kOnWay] = 1.0f;                                        // :328
         cur[best_i] += 1;
+        if (inserted != nullptr) inserted[(size_t)r * ai.n_origins + best_i] += 1;   // an origin sits in ONE road's list
         ++admitted;
     }
     if (admitted > 0) {
@@ -304,6 +320,48 @@ __global__ void __launch_bounds__(kThreads) k_apply_action(Acc acc, const int32_
     if (on) acc.set_sel(r, src[e], (float)dst[e]);
 }
 
+// The same write with the edges grouped by source node (CSR of the full graph by source rank, what GraphDistribution
+// samples over). The action is edge-major (replica innermost) while SELECTED_ROAD is node-major inside a replica, so a
+// thread per (edge, replica) scatters its writes one sector each; here a CTA owns a tile of (source nodes x replicas)
+// (tile_map.cuh): it scans each group's edges with the replica innermost (one 32-byte sector of action bytes per edge
+// and 32 replicas), keeps the destination of the LAST selected edge in ascending edge id (what sequential index_put
+// leaves behind), and writes with the node innermost. Groups without a selected edge are left untouched.
+template <class Acc>
+__global__ void __launch_bounds__(tarl::kTileThreads) k_apply_action_groups(Acc acc, tarl_csr grp,
+                                                                            const int32_t* __restrict__ group_node,
+                                                                            const int32_t* __restrict__ dst, int R, int Bp,
+                                                                            const void* __restrict__ action, int64_t a_sr,
+                                                                            int64_t a_se, int action_dtype) {
+    __shared__ float sm[tarl::kTileSmem];
+    const tarl::Tile t = tarl::tile_here(R, Bp);
+    tarl::tile_walk_rows(t, [&](int rr, int j) {
+        const int g = t.n0 + j, r = t.b0 + rr;
+        float chosen = -1.0f;
+        if (g < grp.n_rows && rr < t.nrows) {
+            const int k1 = grp.ptr[g + 1];
+            for (int k = grp.ptr[g]; k < k1; ++k) {
+                const int e = grp.eid[k];
+                const int64_t o = r * a_sr + e * a_se;
+                bool on;
+                switch (action_dtype) {
+                    case TARL_ACTION_U8: on = static_cast<const uint8_t*>(action)[o] != 0; break;
+                    case TARL_ACTION_I64: on = static_cast<const long long*>(action)[o] != 0; break;
+                    default: on = static_cast<const float*>(action)[o] != 0.0f; break;
+                }
+                if (on) chosen = (float)dst[e];
+            }
+        }
+        sm[tarl::tile_slot(t, rr, j)] = chosen;
+    });
+    __syncthreads();
+    tarl::tile_walk_nodes(t, [&](int rr, int j) {
+        const int g = t.n0 + j;
+        if (g >= grp.n_rows || rr >= t.nrows) return;
+        const float v = sm[tarl::tile_slot(t, rr, j)];
+        if (v >= 0.0f) acc.set_sel(t.b0 + rr, group_node[g], v);
+    });
+}
+
 // ------------------------------------------------------------------------------------------------------- observation
 // state() of the reference on the store (transportation_simulator.py:360-366): node_features[r, n, 0:7] =
 // {MAXN, NUM, FFTT, LENGTH, MAX_FLOW, SELECTED_ROAD, ROAD_INDEX}, agent_index[r, n] = head agent id; non-road nodes
@@ -373,8 +431,8 @@ int check_agents(const tarl_agent_table* t, int R, AgentTable* at) {
 extern "C" {
 
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
-                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* flags,
-                       void* stream) {
+                       float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
+                       int32_t* flags, void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -386,11 +444,11 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const dim3 g1(blocks_for(index->n_origins), R), g2(blocks_for(N), R);
     if (is_store) {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted);
     } else {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted);
     }
     return launch_status();
 }
@@ -448,6 +506,27 @@ int tarl_agents_apply_action(const tarl_agent_state* state, const int32_t* edge_
     else
         k_apply_action<<<grid, kThreads, 0, cs>>>(row, edge_src, edge_dst, n_edges, R, action->data, action->row_stride,
                                                   action->col_stride, action_dtype, rin);
+    return launch_status();
+}
+
+int tarl_agents_apply_action_groups(const tarl_agent_state* state, const tarl_csr* groups, const int32_t* group_node,
+                                    const int32_t* edge_dst, const tarl_rows* action, int32_t action_dtype, void* stream) {
+    RowAcc row; StoreAcc sto; bool is_store; int R;
+    int rc = check_state(state, &row, &sto, &is_store, &R);
+    if (rc != TARL_OK) return rc;
+    if (groups == nullptr || groups->n_rows < 0 || groups->n_edges < 0 || action_dtype < 0 || action_dtype > 2)
+        return TARL_E_BADARG;
+    if (groups->n_rows == 0 || groups->n_edges == 0) return TARL_OK;
+    if (!groups->ptr || !groups->eid || !group_node || !edge_dst || !action || !action->data) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const dim3 grid = tarl::tile_grid(groups->n_rows, R);
+    const int Bp = tarl::tile_rows_pow2(R);
+    if (is_store)
+        k_apply_action_groups<<<grid, tarl::kTileThreads, 0, cs>>>(sto, *groups, group_node, edge_dst, R, Bp, action->data,
+                                                                   action->row_stride, action->col_stride, action_dtype);
+    else
+        k_apply_action_groups<<<grid, tarl::kTileThreads, 0, cs>>>(row, *groups, group_node, edge_dst, R, Bp, action->data,
+                                                                   action->row_stride, action->col_stride, action_dtype);
     return launch_status();
 }
 

@@ -384,13 +384,13 @@ __global__ void __launch_bounds__(kThreads) k_gd_backward(tarl_csr grp, const fl
 // inverse-CDF sample, one uniform per (row, group): first edge (ascending edge id, D3) with u < cumulative proba (:62-80)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_gd_sample(tarl_csr grp, const float* __restrict__ logits, View lv, float temp,
-                                                        int B, int Bp, const float* __restrict__ u, T* __restrict__ onehot,
-                                                        View ov) {
+                                                        int B, int Bp, const float* __restrict__ u, View uv,
+                                                        T* __restrict__ onehot, View ov) {
     const GroupRows t = locate(grp, B, Bp, blockIdx.y, blockIdx.x);
     if (!t.live || t.k1 == t.k0) return;
     Soft s;
     soft_load(s, grp, logits, lv, t.b, t.k0, t.k1, temp);
-    const float ug = u[(int64_t)t.b * grp.n_rows + t.g];
+    const float ug = u[t.b * uv.sb + t.g * uv.se];
     float cum = 0.0f;
     int hit = -1;
 #pragma unroll
@@ -405,7 +405,13 @@ __global__ void __launch_bounds__(kThreads) k_gd_sample(tarl_csr grp, const floa
         cum += tail_p(s, logits, lv, t.b, e, temp);
         if (ug < cum) hit = e;
     }
-    if (hit >= 0) onehot[t.b * ov.sb + hit * ov.se] = T(1);
+    // Every edge of the group is written (1 at the hit, 0 elsewhere): with edge-major output the lanes of a warp store
+    // consecutive bytes of one edge's row vector, whereas writing only the hit — a different edge in every row —
+    // would dirty one sector per (group, row). Every edge has a source, so the whole one-hot tensor is written here.
+    for (int k = t.k0; k < t.k1; ++k) {
+        const int e = grp.eid[k];
+        onehot[t.b * ov.sb + e * ov.se] = T(e == hit ? 1 : 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ 4 rows per thread
@@ -507,12 +513,13 @@ __device__ __forceinline__ Where4 locate4(const tarl_csr& grp, int B, int C, int
 // ptr -> edge id -> logits chain (the logits / action gathers) is exposed per tile.
 struct Stage4 {
     int row0, k0, deg;     // deg == 0: nothing to do (dead lane, empty group, or past the last tile)
+    int g;
 };
 __device__ __forceinline__ Stage4 stage4_bounds(const tarl_csr& grp, int B, int C, int tile, int n_tiles) {
-    Stage4 st = {0, 0, 0};
+    Stage4 st = {0, 0, 0, 0};
     if (tile < n_tiles) {
         const Where4 t = locate4(grp, B, C, tile);
-        st.row0 = t.row0; st.k0 = t.k0; st.deg = t.k1 - t.k0;
+        st.row0 = t.row0; st.k0 = t.k0; st.deg = t.k1 - t.k0; st.g = t.g;
     }
     return st;
 }
@@ -590,6 +597,98 @@ __global__ void __launch_bounds__(kThreads, 3) k_gd_forward_em4(tarl_csr grp, co
             if (threadIdx.x < C && row < B) part_ent[(int64_t)row * nb + blockIdx.x] = v;
         }
         if (part_lp != nullptr) {
+            const float v = block_sum_rows(lp.v[q], C, sm_f);
+            const int n = block_sum_rows(bad[q], C, sm_i);
+            if (threadIdx.x < C && row < B) {
+                part_lp[(int64_t)row * nb + blockIdx.x] = v;
+                part_bad[(int64_t)row * nb + blockIdx.x] = n;
+            }
+        }
+    }
+}
+
+// Sampling on the same fast path: inverse CDF per (group, row) with one uniform each, the one-hot written as one
+// 32-bit store per (edge, 4 rows) — every edge has a source, so the whole tensor is written — and, optionally, the
+// log-probability of what was drawn (sum over the groups of log(p_hit + eps); a group without a hit makes the row
+// -inf, as log_prob() of that action would, src/reinforcement_learning.py:86-91) accumulated in the same pass, so that
+// a rollout needs no second sweep over the logits.
+__global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
+                                                            int B, int C, int n_tiles, const float* __restrict__ u,
+                                                            int64_t u_sb, int64_t u_sg, uint8_t* __restrict__ onehot,
+                                                            float* __restrict__ part_lp, int32_t* __restrict__ part_bad) {
+    __shared__ float sm_f[kThreads];
+    __shared__ int sm_i[kThreads];
+    F4 lp = {{0.f, 0.f, 0.f, 0.f}};
+    int bad[4] = {0, 0, 0, 0};
+    const int stride = gridDim.x;
+    Stage4 nxt = stage4_bounds(grp, B, C, blockIdx.x, n_tiles);
+    int eid_nxt[kCache];
+    stage4_eids(grp, nxt, eid_nxt);
+    Stage4 nxt2 = stage4_bounds(grp, B, C, blockIdx.x + stride, n_tiles);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += stride) {
+        struct { int row0, k0, k1, g; } t = {nxt.row0, nxt.k0, nxt.k0 + nxt.deg, nxt.g};
+        Soft4 s;
+        s.deg = nxt.deg;
+#pragma unroll
+        for (int j = 0; j < kCache; ++j) s.eid[j] = eid_nxt[j];
+        nxt = nxt2;
+        stage4_eids(grp, nxt, eid_nxt);
+        nxt2 = stage4_bounds(grp, B, C, tile + 2 * stride, n_tiles);
+        if (s.deg == 0) continue;
+        float ug[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ug[q] = u[(t.row0 + q) * u_sb + t.g * u_sg];
+        soft4_load(s, grp, logits, nullptr, B, t.row0, t.k0, t.k1, inv_t);
+        F4 cum = {{0.f, 0.f, 0.f, 0.f}};
+        int hit[4] = {-1, -1, -1, -1};         // position inside the group
+        float ph[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < kCache; ++j) {
+            if (j < s.deg) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float p = s.ex[j].v[q] * s.inv_den.v[q];
+                    cum.v[q] += p;
+                    if (hit[q] < 0 && ug[q] < cum.v[q]) { hit[q] = j; ph[q] = p; }
+                }
+            }
+        }
+        for (int k = t.k0 + kCache; k < t.k1; ++k) {
+            const F4 p4 = tail4_p(s, logits, B, t.row0, grp.eid[k], inv_t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                cum.v[q] += p4.v[q];
+                if (hit[q] < 0 && ug[q] < cum.v[q]) { hit[q] = k - t.k0; ph[q] = p4.v[q]; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kCache; ++j) {
+            if (j < s.deg) {
+                const uint32_t w = (hit[0] == j ? 1u : 0u) | (hit[1] == j ? 1u << 8 : 0u) | (hit[2] == j ? 1u << 16 : 0u) |
+                                   (hit[3] == j ? 1u << 24 : 0u);
+                *reinterpret_cast<uint32_t*>(onehot + (int64_t)s.eid[j] * B + t.row0) = w;
+            }
+        }
+        for (int k = t.k0 + kCache; k < t.k1; ++k) {
+            const int j = k - t.k0;
+            const uint32_t w = (hit[0] == j ? 1u : 0u) | (hit[1] == j ? 1u << 8 : 0u) | (hit[2] == j ? 1u << 16 : 0u) |
+                               (hit[3] == j ? 1u << 24 : 0u);
+            *reinterpret_cast<uint32_t*>(onehot + (int64_t)grp.eid[k] * B + t.row0) = w;
+        }
+        if (part_lp != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (hit[q] < 0) bad[q] = 1;
+                else lp.v[q] += flog(ph[q] + kLogEps);
+            }
+        }
+    }
+    if (part_lp != nullptr) {
+        const int nb = gridDim.x;
+        const int c = threadIdx.x & (C - 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int row = blockIdx.y * 32 + 4 * c + q;
             const float v = block_sum_rows(lp.v[q], C, sm_f);
             const int n = block_sum_rows(bad[q], C, sm_i);
             if (threadIdx.x < C && row < B) {
@@ -849,21 +948,39 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
 }
 
 int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
-                          const float* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, void* stream) {
+                          const tarl_rows* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, float* log_prob,
+                          float* partials, void* stream) {
     int rc = check_csr(groups);
     if (rc != TARL_OK) return rc;
     if (batch < 0 || (onehot_dtype != TARL_ACTION_U8 && onehot_dtype != TARL_ACTION_I64)) return TARL_E_BADARG;
     if (batch == 0 || groups->n_edges == 0) return TARL_OK;
-    if (!logits || !logits->data || !uniforms || !onehot || !onehot->data) return TARL_E_BADARG;
+    if (!logits || !logits->data || !uniforms || !uniforms->data || !onehot || !onehot->data) return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (temperature != 0.0f && onehot_dtype == TARL_ACTION_U8 && em4_ok(logits, batch, onehot, onehot_dtype)) {
+        dim3 grid = em4_grid(groups->n_rows, batch);
+        const int n_tiles = (int)grid.x;
+        if (grid.x > (unsigned)kFwdMaxCtas) grid.x = kFwdMaxCtas;
+        const int nb = (int)grid.x;
+        if (log_prob != nullptr && partials == nullptr) return TARL_E_WORKSPACE;
+        float* part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;       // same layout as the forward's
+        int32_t* part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
+        k_gd_sample_em4<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
+                                                  em4_chunks(batch), n_tiles, data_of<const float>(uniforms),
+                                                  uniforms->row_stride, uniforms->col_stride, data_of<uint8_t>(onehot),
+                                                  part_lp, part_bad);
+        if (log_prob != nullptr) k_gd_finish<<<batch, kThreads, 0, s>>>(nullptr, part_lp, part_bad, nb, nullptr, log_prob);
+        return launch_status();
+    }
+    if (log_prob != nullptr) return TARL_E_BADARG;       // the fused log-probability exists on the fast path only
     const dim3 grid = gd_grid(groups->n_rows, batch);
     if (onehot_dtype == TARL_ACTION_U8)
         k_gd_sample<uint8_t><<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits), temperature,
-                                                       batch, pow2_rows(batch), uniforms, data_of<uint8_t>(onehot),
-                                                       view_of(onehot));
+                                                       batch, pow2_rows(batch), data_of<const float>(uniforms),
+                                                       view_of(uniforms), data_of<uint8_t>(onehot), view_of(onehot));
     else
         k_gd_sample<long long><<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), view_of(logits),
-                                                         temperature, batch, pow2_rows(batch), uniforms,
+                                                         temperature, batch, pow2_rows(batch),
+                                                         data_of<const float>(uniforms), view_of(uniforms),
                                                          data_of<long long>(onehot), view_of(onehot));
     return launch_status();
 }

@@ -44,7 +44,13 @@ constexpr int BM = 128, BN = 64, BK = 32;
 #define TARL_VMLP_GROUP 2
 #endif
 constexpr int kGroup = TARL_VMLP_GROUP;                // A tiles requested together (NA must be a multiple)
-constexpr int NA = 8, NW = 4, NT = 4;                  // ring depths: A tiles (smem), W tiles (smem), A hi/lo (TMEM)
+#ifndef TARL_VMLP_NA
+#define TARL_VMLP_NA 8
+#endif
+#ifndef TARL_VMLP_NW
+#define TARL_VMLP_NW 4
+#endif
+constexpr int NA = TARL_VMLP_NA, NW = TARL_VMLP_NW, NT = 4;                  // ring depths: A tiles (smem), W tiles (smem), A hi/lo (TMEM)
 constexpr int kHidden = 64;
 constexpr int kThreadsGemm = 224;
 constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;

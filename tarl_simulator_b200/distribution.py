@@ -142,10 +142,12 @@ class GraphDistribution(Distribution):
         return self.mode
 
     # -- Distribution API ------------------------------------------------------------------------------------
-    def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None, dtype=torch.int64):
+    def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None, dtype=torch.int64,
+               out: torch.Tensor | None = None, return_log_prob: bool = False):
         """One-hot [sample_shape.., .., E]: inverse CDF with one uniform per (row, source group) (:57-80). int64 like
         the reference by default; dtype=torch.bool writes one byte per edge instead of eight. `uniforms` ([.., K])
-        injects the noise the reference draws with torch.rand."""
+        injects the noise the reference draws with torch.rand. `out` (optional): a buffer of the result's shape and
+        storage dtype to write into (any strides; every entry is written), e.g. a frame of a preallocated trajectory."""
         sample_shape = torch.Size(sample_shape)
         B, E = self._logits.shape
         dev = self._logits.device
@@ -154,24 +156,45 @@ class GraphDistribution(Distribution):
         if S > 1:
             lg = lg.unsqueeze(0).expand(S, B, E).reshape(S * B, E)
         rows = S * B
-        if uniforms is None:
-            u = torch.rand(rows, self.nb_nodes, dtype=torch.float32, device=dev)
+        if uniforms is None:       # group-major memory: the rows of one group are read as one vector
+            u = torch.rand(self.nb_nodes, rows, dtype=torch.float32, device=dev).t()
         else:
-            u = uniforms.to(device=dev, dtype=torch.float32).reshape(rows, self.nb_nodes).contiguous()
+            u = uniforms.to(device=dev, dtype=torch.float32).reshape(rows, self.nb_nodes)
         if dtype not in (torch.int64, torch.bool, torch.uint8):
             raise ValueError("sample dtype must be int64, bool or uint8")
         store = torch.int64 if dtype == torch.int64 else torch.uint8
         em = rows > 1 and lg.stride(0) == 1 and len(self._lead) <= 1 and S == 1
-        out = _edge_major(rows, E, store, dev, zero=True) if em else torch.zeros(rows, E, dtype=store, device=dev)
+        if out is not None:
+            if out.numel() != rows * E or out.dtype not in (store, torch.bool if store == torch.uint8 else store) or out.device != dev:
+                raise ValueError("out must be a buffer of the sample's shape and dtype")
+            out = out.reshape(rows, E)
+            out = out.view(torch.uint8) if out.dtype == torch.bool else out
+        else:
+            out = _edge_major(rows, E, store, dev) if em else torch.empty(rows, E, dtype=store, device=dev)
+        # the log-probability of the draw comes out of the same kernel on the layout MPNNPolicyNet emits
+        fused = (return_log_prob and store == torch.uint8 and rows > 1 and S == 1 and self.temperature != 0.0
+                 and (rows in (4, 8, 16) or rows % 32 == 0) and lg.stride(0) == 1 and lg.stride(1) == rows
+                 and out.stride(0) == 1 and out.stride(1) == rows and lg.data_ptr() % 16 == 0 and out.data_ptr() % 4 == 0)
+        lp = partials = None
+        if fused:
+            lp = torch.empty(rows, dtype=torch.float32, device=dev)
+            partials = torch.empty(3 * rows * max(_cabi.lib().tarl_graphdist_partial_count(self.nb_nodes, rows), 1),
+                                   dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), _cabi.rows(lg), self.temperature, rows,
-                                                   u.data_ptr(), _cabi.rows(out),
+                                                   _cabi.rows(u), _cabi.rows(out),
                                                    _cabi.ACTION_I64 if store == torch.int64 else _cabi.ACTION_U8,
-                                                   _stream(dev))
+                                                   lp.data_ptr() if fused else None,
+                                                   partials.data_ptr() if fused else None, _stream(dev))
         _cabi.check(rc, "tarl_graphdist_sample")
         if dtype == torch.bool:
             out = out.view(torch.bool)
-        return out.reshape(*sample_shape, *self._lead, E)
+        out = out.reshape(*sample_shape, *self._lead, E)
+        if not return_log_prob:
+            return out
+        if not fused:
+            return out, self.log_prob(out).detach()
+        return out, lp.reshape(self._lead)
 
     def _lp_ent(self, action):
         return _LogProbEntropy.apply(self._logits, action, self._groups, self.temperature)

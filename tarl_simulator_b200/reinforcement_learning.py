@@ -25,6 +25,7 @@ import torch
 from . import _cabi
 from .agents import Agents, PopulationIndex, rows_state, side_tables_for
 from .engine import LinkStore
+from .topology import group_csr_for
 from .transportation_simulator import TransportationSimulator
 
 EPISODE_START = 3600 * 6 - 60       # _reset, :203
@@ -196,6 +197,7 @@ class BatchedSimulatorEnv:
         self._head = torch.full((max(self.R * self.N, 1),), -1, **i32)
         self._next = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
         self._cursor = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
+        self._inserted = torch.zeros(max(self.R * self.index.n_origins, 1), **i32)   # per (replica, origin), see insert()
         self.counters = torch.zeros(self.R, 2, **i32)          # running totals {inserted, withdrawn} per replica
         self.occupancy = torch.zeros(self.R, **i32)
         self.withdrawn = torch.zeros(self.R, self.N, dtype=torch.bool, device=dev)
@@ -223,6 +225,7 @@ class BatchedSimulatorEnv:
         self.agent_features[..., Agents.ON_WAY] = 0.0
         self.agent_features[..., Agents.DONE] = 0.0
         self.counters.zero_()
+        self._inserted.zero_()
         if self.metrics is not None:
             self.metrics.reset()
         self.time = float(EPISODE_START)
@@ -246,11 +249,14 @@ class BatchedSimulatorEnv:
     def apply_action(self, action: torch.Tensor):
         a, code = _action_code(action.reshape(self.R, self.E_full))
         st = self._state()
+        grp = group_csr_for(self.graph.edge_index, "source_rank")
+        if getattr(self, "_group_nodes", None) is None:
+            self._group_nodes = grp.nodes.to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            rc = _cabi.lib().tarl_agents_apply_action(C.byref(st), self.side.src32.data_ptr(),
-                                                      self.side.dst32.data_ptr(), self.E_full, _cabi.rows(a), code,
-                                                      _stream(self.device))
-        _cabi.check(rc, "tarl_agents_apply_action")
+            rc = _cabi.lib().tarl_agents_apply_action_groups(C.byref(st), grp.ref(), self._group_nodes.data_ptr(),
+                                                             self.side.dst32.data_ptr(), _cabi.rows(a), code,
+                                                             _stream(self.device))
+        _cabi.check(rc, "tarl_agents_apply_action_groups")
 
     def choice(self, uniforms: torch.Tensor | None = None, seed: int = 0):
         """Random routing for every replica (Agents.choice on the store)."""
@@ -277,8 +283,8 @@ class BatchedSimulatorEnv:
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(self._table), self.index.ref(), self.time,
                                                 self._head.data_ptr(), self._next.data_ptr(), self._cursor.data_ptr(),
-                                                self.counters.data_ptr(), self.store.flags.data_ptr(),
-                                                _stream(self.device))
+                                                self.counters.data_ptr(), self._inserted.data_ptr(),
+                                                self.store.flags.data_ptr(), _stream(self.device))
         _cabi.check(rc, "tarl_agents_insert")
 
     def observe(self, node_features: bool = True, agent_index: bool = True):
@@ -314,15 +320,22 @@ class BatchedSimulatorEnv:
     def num_agents(self) -> torch.Tensor:
         return self.store.num_agents()
 
-    def compact_state(self):
+    def compact_state(self, out=None):
         """The dynamic observation columns without materialising [R, N_tot, 7]: (NUMBER_OF_AGENT [R, N_tot],
-        SELECTED_ROAD [R, N_tot], head agent id int64 [R, N_tot]); plain copies out of the store's arrays."""
+        SELECTED_ROAD [R, N_tot], head agent id int64 [R, N_tot]); plain copies out of the store's arrays, optionally
+        into three given buffers."""
         R, N, M = self.R, self.N, self.n_nodes
-        num = torch.zeros(R, M, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = (torch.empty(R, M, dtype=torch.float32, device=self.device),
+                   torch.empty(R, M, dtype=torch.float32, device=self.device),
+                   torch.empty(R, M, dtype=torch.int64, device=self.device))
+        num, sel, head = out
         num[:, :N] = self.store.num_agents()
-        head = torch.zeros(R, M, dtype=torch.int64, device=self.device)
+        num[:, N:] = 0.0
         head[:, :N] = self.store.head_agents()
-        sel = torch.cat((self.store.selected_road(), self.src_sel), dim=1)
+        head[:, N:] = 0
+        sel[:, :N] = self.store.selected_road()
+        sel[:, N:] = self.src_sel
         return num, sel, head
 
     def export_x(self) -> torch.Tensor:

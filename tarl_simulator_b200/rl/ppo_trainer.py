@@ -45,12 +45,22 @@ class PolicyModule(nn.Module):
         logits = self.net(obs["node_features"], obs.get("edge_features"), obs.get("agent_index"))
         return GraphDistribution(logits, self.edge_index)
 
-    def forward(self, obs, mode: bool = False):
+    def forward(self, obs, mode: bool = False, out: torch.Tensor | None = None):
+        """out (optional): a bool [.., E] buffer (e.g. one frame of a preallocated trajectory) for the action."""
         d = self.dist(obs)
-        action = d.mode.to(torch.bool) if mode else d.sample(dtype=torch.bool)
+        if mode:
+            action = d.mode.to(torch.bool)
+            if out is not None:
+                out.copy_(action.reshape(out.shape))
+                action = out
+            lp = d.log_prob(action).detach() if self.return_log_prob else None
+        elif self.return_log_prob:
+            action, lp = d.sample(dtype=torch.bool, out=out, return_log_prob=True)
+        else:
+            action, lp = d.sample(dtype=torch.bool, out=out), None
         out = {"action": action}
-        if self.return_log_prob:
-            out["sample_log_prob"] = d.log_prob(action).detach()
+        if lp is not None:
+            out["sample_log_prob"] = lp
         return out
 
 
@@ -152,12 +162,18 @@ class _EnvAdapter:
     def time(self):
         return float(self.env.time if self.batched else self.env.simulator.time)
 
-    def dynamic(self):
-        """(NUM [R, N_tot], SELECTED_ROAD [R, N_tot], head agent id [R, N_tot]) of the current state."""
+    def dynamic(self, out=None):
+        """(NUM [R, N_tot], SELECTED_ROAD [R, N_tot], head agent id [R, N_tot]) of the current state, optionally
+        written into the three given buffers (frames of a preallocated trajectory)."""
         if self.batched:
-            return self.env.compact_state()
+            return self.env.compact_state(out)
         x, _, _, ai = self.env.simulator.state()
-        return x[:, OBS.NUMBER_OF_AGENT].unsqueeze(0).clone(), x[:, OBS.SELECTED_ROAD].unsqueeze(0).clone(), ai.unsqueeze(0)
+        vals = (x[:, OBS.NUMBER_OF_AGENT].unsqueeze(0), x[:, OBS.SELECTED_ROAD].unsqueeze(0), ai.unsqueeze(0))
+        if out is None:
+            return vals[0].clone(), vals[1].clone(), vals[2]
+        for o, v in zip(out, vals):
+            o.copy_(v)
+        return out
 
     def step(self, action):
         """action [R, E_full] bool. Returns (reward [R], done [R])."""
@@ -186,27 +202,43 @@ class _EnvAdapter:
 def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode: bool = False,
             break_when_any_done: bool = False):
     """`frames` steps of every replica after a reset. Returns a dict of [T, R, ...] tensors (compact observations:
-    NUM, SELECTED_ROAD and head ids per node; the static columns are re-attached when a minibatch is formed)."""
+    NUM, SELECTED_ROAD and head ids per node; the static columns are re-attached when a minibatch is formed).
+    The trajectory is written in place into preallocated [T+1, R, ..] buffers — frame t+1 of a step is the next
+    step's frame t, so `next_*` are views shifted by one — and the one-hot actions go straight from the sampling
+    kernel into their frame (edge-major inside a frame: [T, R, E] with the replica innermost)."""
     adapter.reset()
-    keys = ("num", "sel", "agent_index", "time", "action", "sample_log_prob", "reward", "done", "next_num", "next_sel",
-            "next_agent_index", "next_time")
-    buf = {k: [] for k in keys}
-    num, sel, ai = adapter.dynamic()
+    R, M, dev = adapter.R, adapter.n_nodes, adapter.device
+    E = adapter.graph.edge_index.size(1)
+    T = int(frames)
+    num = torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
+    sel = torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
+    ai = torch.empty(T + 1, R, M, dtype=torch.int64, device=dev)
+    times = torch.empty(T + 1, R, dtype=torch.float32, device=dev)
+    if R > 1:
+        action = torch.empty(T, E, R, dtype=torch.bool, device=dev).permute(0, 2, 1)
+    else:
+        action = torch.empty(T, R, E, dtype=torch.bool, device=dev)
+    small = {k: [] for k in ("sample_log_prob", "reward", "done")}
+    adapter.dynamic(out=(num[0], sel[0], ai[0]))
+    times[0] = adapter.time()
     dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
-    for _ in range(frames):
-        t = torch.full((adapter.R,), adapter.time(), device=adapter.device)
-        obs = adapter.observation(num, sel, ai, t, dynamic=dynamic)
-        act = policy_module(obs, mode=mode)
+    n = 0
+    for t in range(T):
+        obs = adapter.observation(num[t], sel[t], ai[t], times[t], dynamic=dynamic)
+        act = policy_module(obs, mode=mode, out=action[t])
         reward, done = adapter.step(act["action"])
-        nnum, nsel, nai = adapter.dynamic()
-        nt = torch.full((adapter.R,), adapter.time(), device=adapter.device)
-        for k, v in zip(keys, (num, sel, ai, t, act["action"], act.get("sample_log_prob", torch.zeros_like(t)), reward,
-                               done, nnum, nsel, nai, nt)):
-            buf[k].append(v)
-        num, sel, ai = nnum, nsel, nai
+        adapter.dynamic(out=(num[t + 1], sel[t + 1], ai[t + 1]))
+        times[t + 1] = adapter.time()
+        small["sample_log_prob"].append(act.get("sample_log_prob", torch.zeros(R, device=dev)))
+        small["reward"].append(reward)
+        small["done"].append(done)
+        n = t + 1
         if break_when_any_done and bool(done.any()):
             break
-    return {k: torch.stack(v) for k, v in buf.items()}
+    out = {"num": num[:n], "sel": sel[:n], "agent_index": ai[:n], "time": times[:n], "action": action[:n],
+           "next_num": num[1:n + 1], "next_sel": sel[1:n + 1], "next_agent_index": ai[1:n + 1], "next_time": times[1:n + 1]}
+    out.update({k: torch.stack(v) for k, v in small.items()})
+    return out
 
 
 def _values(adapter, value_module, batch, prefix=""):
@@ -267,7 +299,8 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
                 adv = standardise(adv)
             n = min(sub_batch_size, T * R)
             pick = torch.randperm(T * R, generator=gen)[:n].to(adapter.device)
-            flat = lambda x: x.reshape(T * R, *x.shape[2:])[pick]
+            ti, ri = pick // R, pick % R
+            flat = lambda x: x[ti, ri]                    # gathers n frames whatever the strides of the trajectory
             obs = adapter.observation(flat(batch["num"]), flat(batch["sel"]), flat(batch["agent_index"]), flat(batch["time"]))
             d = policy_module.dist(obs)
             log_prob = d.log_prob(flat(batch["action"]))
