@@ -12,7 +12,9 @@ KEEP = ["ID", "Kernel Name", "Block Size", "Grid Size", "dram__bytes_read.sum", 
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_lg.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
-        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum"]
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
 idx = [hdr.index(k) for k in KEEP if k in hdr]
