@@ -16,7 +16,8 @@
 // the same road; with the population indexed ONCE by origin (ascending agent id inside an origin) the per-road work is
 // a k-way merge over the (almost always one) origins that currently select the road:
 //   k_insert_offer  thread per (replica, origin with agents): pushes the origin on its road's list (atomicExch)
-//   k_insert_admit  thread per (replica, road with a list): merges by smallest agent id until the room is used up
+//   k_insert_admit  thread per (replica, origin at the head of its road's list): merges by smallest agent id until the
+//                   room is used up
 // The merge result does not depend on the order of the list, so the atomics leave no nondeterminism behind.
 #include "engine_common.cuh"
 #include "tile_map.cuh"
@@ -191,12 +192,18 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
                                                            int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
                                                            int32_t* __restrict__ inserted) {
-    const int n = blockIdx.x * kThreads + threadIdx.x;
-    if (n >= acc.N) return;
+    // One thread per (replica, origin): the origin that ended up at the HEAD of its road's list serves the road. (A
+    // thread per road would launch N threads per replica to find the few roads with a list.)
+    const int i0 = blockIdx.x * kThreads + threadIdx.x;
+    if (i0 >= ai.n_origins) return;
     const int r = blockIdx.y;
+    if (next[(size_t)r * ai.n_origins + i0] == -2) return;                        // not listed this step
+    const long long road = (long long)acc.sel_of(r, ai.origins[i0]);
+    if (road < 0 || road >= acc.N) return;
+    const int n = (int)road;
     const size_t L = (size_t)r * acc.N + n;
     const int h = head[L];
-    if (h < 0) return;
+    if (h != i0) return;
     head[L] = -1;                                                                // ready for the next call
     typename Acc::Link l = acc.open(r, n);
     const long long cap = (long long)((l.maxn - 3.0f) - l.num);                  // base.py:262-267
@@ -442,7 +449,7 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if (index->n_origins == 0 || N == 0) return TARL_OK;
     if (!index->org_ptr || !index->org_agent || !index->origins || !head || !next || !cursor) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    const dim3 g1(blocks_for(index->n_origins), R), g2(blocks_for(N), R);
+    const dim3 g1(blocks_for(index->n_origins), R), g2 = g1;
     if (is_store) {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted);
         k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted);
