@@ -40,17 +40,11 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 32;
-#ifndef TARL_VMLP_GROUP
-#define TARL_VMLP_GROUP 2
-#endif
-constexpr int kGroup = TARL_VMLP_GROUP;                // A tiles requested together (NA must be a multiple)
-#ifndef TARL_VMLP_NA
-#define TARL_VMLP_NA 8
-#endif
-#ifndef TARL_VMLP_NW
-#define TARL_VMLP_NW 4
-#endif
-constexpr int NA = TARL_VMLP_NA, NW = TARL_VMLP_NW, NT = 4;                  // ring depths: A tiles (smem), W tiles (smem), A hi/lo (TMEM)
+constexpr int kGroup = 2;                              // A tiles requested together (NA must be a multiple)
+// ring depths: A tiles (smem), W tiles (smem) and A hi/lo (TMEM). The last two are released by the same event (the
+// MMAs of a k-block completing), so they share one depth and ONE "free" barrier: a tcgen05.commit costs the issuing
+// thread ~150 cycles (measured), more than a third of the 384-cycle MMA floor of a k-block.
+constexpr int NA = 8, NT = 4, NW = NT;
 constexpr int kHidden = 64;
 constexpr int kThreadsGemm = 224;
 constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
@@ -184,9 +178,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     auto a_full = [&](int s) { return bars + 8u * s; };
     auto a_empty = [&](int s) { return bars + 8u * (NA + s); };
     auto w_full = [&](int s) { return bars + 8u * (2 * NA + s); };
-    auto w_empty = [&](int s) { return bars + 8u * (2 * NA + NW + s); };
+    auto slot_free = [&](int s) { return bars + 8u * (2 * NA + NW + s); };    // W slot s and TMEM A slot s
     auto t_ready = [&](int s) { return bars + 8u * (2 * NA + 2 * NW + s); };
-    auto t_empty = [&](int s) { return bars + 8u * (2 * NA + 2 * NW + NT + s); };
     auto accfull = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + b); };
     auto accfree = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + 2 + b); };
     const uint32_t tmem_slot = bars + 8u * (2 * NA + 2 * NW + 2 * NT + 4);
@@ -198,8 +191,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 128); }
-        for (int s = 0; s < NW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-        for (int s = 0; s < NT; ++s) { mbar_init(t_ready(s), 128); mbar_init(t_empty(s), 1); }
+        for (int s = 0; s < NW; ++s) { mbar_init(w_full(s), 1); mbar_init(slot_free(s), 1); }
+        for (int s = 0; s < NT; ++s) mbar_init(t_ready(s), 128);
         for (int b = 0; b < 2; ++b) { mbar_init(accfull(b), 1); mbar_init(accfree(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -231,7 +224,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
         if (lane == 0) {                                                 // ===== TMA producer, W tiles (L2)
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % NW, ph = (kb / NW) & 1;
-                mbar_wait(w_empty(s), ph ^ 1);
+                mbar_wait(slot_free(s), ph ^ 1);
                 mbar_expect_tx(w_full(s), 2 * kBBytes);
                 tma_load_2d(sm_wh(s), &map_wh, w_full(s), (kb0 + kb) * BK, 0);
                 tma_load_2d(sm_wl(s), &map_wl, w_full(s), (kb0 + kb) * BK, 0);
@@ -258,8 +251,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                     tc_mma_tf32_ts(acc, a_hi + 8 * k, dw + 2 * k, kIdesc128, (first && k == 0) ? 0u : 1u);
                     tc_mma_tf32_ts(acc, a_lo + 8 * k, dw + 2 * k, kIdesc64, 1u);
                 }
-                tc_commit(w_empty(sw));                                  // W slot reusable
-                tc_commit(t_empty(st));                                  // TMEM A columns reusable
+                tc_commit(slot_free(st));                                // W slot and TMEM A columns reusable
                 if ((kb % kChunk) == kChunk - 1 || kb == nkb - 1) tc_commit(accfull(b));
             }
         }
@@ -306,7 +298,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                 }
             }
             mbar_arrive(a_empty(sa));                                    // the row is in registers: slot back to the TMA
-            mbar_wait(t_empty(st), pt ^ 1);                              // MMAs that read these TMEM columns are done
+            mbar_wait(slot_free(st), pt ^ 1);                            // MMAs that read these TMEM columns are done
             tc_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
