@@ -254,3 +254,34 @@ def test_fast_sampling_path_matches_generic_kernel_and_its_log_prob(B):
     # uniforms in group-major memory (what sample() draws itself) give the same result
     a2 = d_em.sample(uniforms=u.t().contiguous().t(), dtype=torch.bool)
     assert torch.equal(a2, a_em)
+
+
+def test_value_mlp_split_cache_follows_the_weights():
+    """The TF32 hi/lo split of W1 is cached in the module's workspace: an optimiser step (in-place update), a
+    load_state_dict and a change of the number of rows must all be noticed."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNetSimple
+    torch.manual_seed(0)
+    N = 2048
+    net = MPNNValueNetSimple(torch.zeros(2, 1, dtype=torch.long, device="cuda"), N, "cuda")
+    num = torch.randint(0, 9, (64, N), device="cuda").float()
+    tm = torch.rand(64, 1, device="cuda")
+
+    def both(n=64):
+        with torch.no_grad():
+            return net.forward_occupancy(num[:n], tm[:n]), net.final_mlp(torch.cat((num[:n], tm[:n]), dim=-1))
+
+    a, b = both()
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+    opt = torch.optim.SGD(net.parameters(), lr=0.5)
+    net.final_mlp(torch.cat((num, tm), dim=-1)).sum().backward()
+    opt.step()                                           # in place: same storage, new version
+    a2, b2 = both()
+    assert not torch.allclose(b2, b, rtol=1e-3, atol=1e-3) and torch.allclose(a2, b2, rtol=1e-5, atol=1e-5)
+    sd = {k: v * 0.5 for k, v in net.state_dict().items()}
+    net.load_state_dict(sd)
+    a3, b3 = both()
+    assert torch.allclose(a3, b3, rtol=1e-5, atol=1e-5) and not torch.allclose(b3, b2, rtol=1e-3, atol=1e-3)
+    a4, b4 = both(32)                                     # another problem shape on the same workspace
+    assert torch.allclose(a4, b4, rtol=1e-5, atol=1e-5)
+    a5, b5 = both(64)
+    assert torch.allclose(a5, b5, rtol=1e-5, atol=1e-5)
