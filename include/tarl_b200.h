@@ -379,9 +379,10 @@ int tarl_agents_apply_action_groups(const tarl_agent_state* state, const tarl_cs
 /* state() (src/transportation_simulator.py:360-366) and the reward term of SimulatorEnv._step
  * (src/reinforcement_learning.py:266) from a link store: node_features [R, n_nodes, 7] = {MAXN, NUM, FFTT, LENGTH,
  * MAX_FLOW, SELECTED_ROAD, ROAD_INDEX}, agent_index [R, n_nodes] int64 = head agent ids, occupancy [R] int32 =
- * sum of NUM over the links (integer atomics). Any output may be NULL. */
+ * sum of NUM over the links (integer atomics); num_agents / selected_road [R, n_nodes] = the NUMBER_OF_AGENT and
+ * SELECTED_ROAD columns alone (the compact observation a rollout stores per frame). Any output may be NULL. */
 int tarl_store_observe(const tarl_agent_state* state, float* node_features, int64_t* agent_index, int32_t* occupancy,
-                       void* stream);
+                       float* num_agents, float* selected_road, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Metrics side channels, accumulated on the device (csrc/metrics.cu).

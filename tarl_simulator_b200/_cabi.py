@@ -122,7 +122,7 @@ SIGNATURES = {
     "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),
     "tarl_agents_apply_action": (C.c_int, [_AST, _P, _P, _I32, _ROWS, _I32, _P]),
     "tarl_agents_apply_action_groups": (C.c_int, [_AST, _CSR1, _P, _P, _ROWS, _I32, _P]),
-    "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P]),
+    "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P, _P, _P]),
     "tarl_metrics_accumulate": (C.c_int, [_CSR, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
     "tarl_value_mlp_workspace_bytes": (_SZ, [_I32, _I32]),
     "tarl_value_mlp_forward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),

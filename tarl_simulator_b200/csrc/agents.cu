@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_apply_action_groups(Acc 
 // are {0,0,0,0,0,sel,-1} / 0. occupancy[r] += sum_n NUM (integer atomics: the reward is -occupancy, :266).
 __global__ void __launch_bounds__(kThreads) k_observe(StoreAcc acc, float* __restrict__ node_features,
                                                       long long* __restrict__ agent_index,
-                                                      int32_t* __restrict__ occupancy) {
+                                                      int32_t* __restrict__ occupancy, float* __restrict__ num_agents,
+                                                      float* __restrict__ selected_road) {
     const int n = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     int num_i = 0;
@@ -386,16 +387,21 @@ __global__ void __launch_bounds__(kThreads) k_observe(StoreAcc acc, float* __res
             const int slot = acc.s.slot_of(n);
             const float4* rec = reinterpret_cast<const float4*>(acc.hot) + 2 * ((size_t)r * acc.N + slot);
             const float4 A = rec[0];
-            const float4 sa = acc.s.stat_a[slot], sb = acc.s.stat_b[slot];
-            f[0] = A.w; f[1] = A.z; f[2] = sa.x; f[3] = sb.x; f[4] = sb.y; f[6] = sa.z;
+            f[0] = A.w; f[1] = A.z;
+            if (node_features != nullptr) {
+                const float4 sa = acc.s.stat_a[slot], sb = acc.s.stat_b[slot];
+                f[2] = sa.x; f[3] = sb.x; f[4] = sb.y; f[6] = sa.z;
+            }
             head = (long long)A.x;
             num_i = (int)A.z;
         }
-        f[5] = acc.sel_of(r, n);
         const size_t o = (size_t)r * acc.n_nodes + n;
+        if (node_features != nullptr || selected_road != nullptr) f[5] = acc.sel_of(r, n);
         if (node_features != nullptr)
             for (int c = 0; c < 7; ++c) node_features[o * 7 + c] = f[c];
         if (agent_index != nullptr) agent_index[o] = head;
+        if (num_agents != nullptr) num_agents[o] = f[1];
+        if (selected_road != nullptr) selected_road[o] = f[5];
     }
     if (occupancy != nullptr) {
         for (int off = 16; off > 0; off >>= 1) num_i += __shfl_xor_sync(0xffffffffu, num_i, off);
@@ -538,7 +544,7 @@ int tarl_agents_apply_action_groups(const tarl_agent_state* state, const tarl_cs
 }
 
 int tarl_store_observe(const tarl_agent_state* state, float* node_features, int64_t* agent_index, int32_t* occupancy,
-                       void* stream) {
+                       float* num_agents, float* selected_road, void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -548,7 +554,8 @@ int tarl_store_observe(const tarl_agent_state* state, float* node_features, int6
     if (occupancy != nullptr && cudaMemsetAsync(occupancy, 0, sizeof(int32_t) * (size_t)R, cs) != cudaSuccess)
         return TARL_E_LAUNCH;
     const dim3 grid(blocks_for(sto.n_nodes), R);
-    k_observe<<<grid, kThreads, 0, cs>>>(sto, node_features, reinterpret_cast<long long*>(agent_index), occupancy);
+    k_observe<<<grid, kThreads, 0, cs>>>(sto, node_features, reinterpret_cast<long long*>(agent_index), occupancy,
+                                         num_agents, selected_road);
     return launch_status();
 }
 

@@ -287,19 +287,35 @@ class BatchedSimulatorEnv:
                                                 self.store.flags.data_ptr(), _stream(self.device))
         _cabi.check(rc, "tarl_agents_insert")
 
-    def observe(self, node_features: bool = True, agent_index: bool = True):
+    def observe(self, node_features: bool = True, agent_index: bool = True, compact_out=None):
+        """One pass over the link store: occupancy (always), and on request node_features [R, N_tot, 7], agent_index
+        [R, N_tot], and/or the compact observation written into compact_out = (NUM [R, N_tot] fp32, SELECTED_ROAD
+        [R, N_tot] fp32, head agent id [R, N_tot] int64) — contiguous buffers, e.g. a frame of a trajectory."""
         st = self._state()
         nf = torch.empty(self.R, self.n_nodes, 7, dtype=torch.float32, device=self.device) if node_features else None
         ai = torch.empty(self.R, self.n_nodes, dtype=torch.int64, device=self.device) if agent_index else None
+        num = sel = None
+        if compact_out is not None:
+            num, sel, head = compact_out
+            for t_, dt in ((num, torch.float32), (sel, torch.float32), (head, torch.int64)):
+                if t_.dtype != dt or t_.shape != (self.R, self.n_nodes) or not t_.is_contiguous():
+                    raise ValueError("compact_out must be contiguous (fp32, fp32, int64) [R, N_tot] buffers")
+            if ai is None:
+                ai = head
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_store_observe(C.byref(st), nf.data_ptr() if nf is not None else None,
                                                 ai.data_ptr() if ai is not None else None, self.occupancy.data_ptr(),
-                                                _stream(self.device))
+                                                num.data_ptr() if num is not None else None,
+                                                sel.data_ptr() if sel is not None else None, _stream(self.device))
         _cabi.check(rc, "tarl_store_observe")
-        return nf, ai
+        if compact_out is not None and ai is not compact_out[2]:
+            compact_out[2].copy_(ai)
+        return nf, (ai if agent_index else None)
 
-    def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False):
-        """One _step for every replica. action None = keep the current SELECTED_ROAD values."""
+    def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False,
+             compact_out=None):
+        """One _step for every replica. action None = keep the current SELECTED_ROAD values. compact_out: see
+        observe() — the post-step compact observation comes out of the same pass that computes the reward."""
         if action is not None:
             self.apply_action(action)
         self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
@@ -308,7 +324,7 @@ class BatchedSimulatorEnv:
         if self.metrics is not None:
             self.metrics.record(self.time, pop=self.store.pop[: self.R * self.N], withdrawn=self.withdrawn,
                                 delta_tt=self.delta_tt if self.metrics.optimality_now is not None else None)
-        nf, ai = self.observe(node_features=observe, agent_index=observe)
+        nf, ai = self.observe(node_features=observe, agent_index=observe, compact_out=compact_out)
         self.time += self.timestep
         out = {"reward": -self.occupancy.to(torch.float32), "occupancy": self.occupancy,
                "done": torch.full((self.R,), self.time > EPISODE_END, dtype=torch.bool, device=self.device),
@@ -329,6 +345,9 @@ class BatchedSimulatorEnv:
             out = (torch.empty(R, M, dtype=torch.float32, device=self.device),
                    torch.empty(R, M, dtype=torch.float32, device=self.device),
                    torch.empty(R, M, dtype=torch.int64, device=self.device))
+        if all(t_.is_contiguous() for t_ in out):
+            self.observe(node_features=False, agent_index=False, compact_out=out)
+            return out
         num, sel, head = out
         num[:, :N] = self.store.num_agents()
         num[:, N:] = 0.0

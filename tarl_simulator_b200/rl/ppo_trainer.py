@@ -175,13 +175,16 @@ class _EnvAdapter:
             o.copy_(v)
         return out
 
-    def step(self, action):
-        """action [R, E_full] bool. Returns (reward [R], done [R])."""
+    def step(self, action, out=None):
+        """action [R, E_full] bool. Returns (reward [R], done [R]); `out` (optional): the three buffers of dynamic()
+        for the post-step state (on the link store they are filled by the pass that computes the reward)."""
         if self.batched:
-            out = self.env.step(action)
-            return out["reward"], out["done"]
-        out = self.env._step({"action": action[0]})
-        return out["reward"].reshape(1).to(torch.float32), out["done"].reshape(1).to(self.device)
+            res = self.env.step(action, compact_out=out)
+            return res["reward"], res["done"]
+        res = self.env._step({"action": action[0]})
+        if out is not None:
+            self.dynamic(out=out)
+        return res["reward"].reshape(1).to(torch.float32), res["done"].reshape(1).to(self.device)
 
     def observation(self, num, sel, agent_index, time, dynamic: bool = True):
         """Observation dict with a leading batch dimension from compact dynamic columns. time: [B] tensor.
@@ -226,8 +229,7 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
     for t in range(T):
         obs = adapter.observation(num[t], sel[t], ai[t], times[t], dynamic=dynamic)
         act = policy_module(obs, mode=mode, out=action[t])
-        reward, done = adapter.step(act["action"])
-        adapter.dynamic(out=(num[t + 1], sel[t + 1], ai[t + 1]))
+        reward, done = adapter.step(act["action"], out=(num[t + 1], sel[t + 1], ai[t + 1]))
         times[t + 1] = adapter.time()
         small["sample_log_prob"].append(act.get("sample_log_prob", torch.zeros(R, device=dev)))
         small["reward"].append(reward)
