@@ -256,7 +256,8 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
  * int64 (TARL_ACTION_I64, the reference's dtype) or uint8 / bool (TARL_ACTION_U8), every entry written. Inside a
  * group edges are walked in ascending edge id (D3); batched rows are independent (D7).
  * log_prob: NULL, or [B] out = log_prob of the sampled action, accumulated in the same pass (needs `partials` as for
- * tarl_graphdist_forward). Only with edge-major fp32 logits, an edge-major uint8 one-hot and B in {4, 8, 16, 32k}
+ * tarl_graphdist_forward). Only with edge-major fp32 logits (or ONE logits row broadcast over the batch: row stride
+ * 0), an edge-major uint8 one-hot and B in {4, 8, 16, 32k}
  * (the layout MPNNPolicyNet emits); TARL_E_BADARG otherwise — callers then use tarl_graphdist_forward. */
 int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
                           const tarl_rows* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, float* log_prob,

@@ -426,6 +426,14 @@ __device__ __forceinline__ F4 ld4(const float* p) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     return F4{{t.x, t.y, t.z, t.w}};
 }
+// logits of one edge for 4 rows: edge-major [E][B], or ONE row shared by every batch row (kBcast: an
+// expanded [1, E] tensor — the active policy path does not depend on the dynamic observation, so a rollout over R
+// replicas has a single logits row)
+template <bool kBcast>
+__device__ __forceinline__ F4 ld4_logits(const float* lg, int B, int e, int row0) {
+    if (kBcast) { const float z = lg[e]; return F4{{z, z, z, z}}; }
+    return ld4(lg + (int64_t)e * B + row0);
+}
 __device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 
 struct Soft4 {
@@ -437,6 +445,7 @@ struct Soft4 {
 };
 
 // s.eid[0 .. min(deg, kCache)) and s.deg are filled by the caller (prefetched one tile ahead)
+template <bool kBcast = false>
 __device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const float* __restrict__ lg,
                                            const uint8_t* __restrict__ act, int B, int row0, int k0, int k1,
                                            float inv_t) {
@@ -450,13 +459,13 @@ __device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const 
 #pragma unroll
     for (int j = 0; j < kCache; ++j) {
         if (j < s.deg) {
-            s.ex[j] = ld4(lg + (int64_t)s.eid[j] * B + row0);
+            s.ex[j] = ld4_logits<kBcast>(lg, B, s.eid[j], row0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { s.ex[j].v[q] *= inv_t; s.mx.v[q] = fmaxf(s.mx.v[q], s.ex[j].v[q]); }
         }
     }
     for (int k = k0 + kCache; k < k1; ++k) {
-        const F4 z = ld4(lg + (int64_t)grp.eid[k] * B + row0);
+        const F4 z = ld4_logits<kBcast>(lg, B, grp.eid[k], row0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) s.mx.v[q] = fmaxf(s.mx.v[q], z.v[q] * inv_t);
     }
@@ -469,7 +478,7 @@ __device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const 
         }
     }
     for (int k = k0 + kCache; k < k1; ++k) {
-        const F4 z = ld4(lg + (int64_t)grp.eid[k] * B + row0);
+        const F4 z = ld4_logits<kBcast>(lg, B, grp.eid[k], row0);
 #pragma unroll
         for (int q = 0; q < 4; ++q) den.v[q] += fexp(z.v[q] * inv_t - s.mx.v[q]);
     }
@@ -477,8 +486,9 @@ __device__ __forceinline__ void soft4_load(Soft4& s, const tarl_csr& grp, const 
     for (int q = 0; q < 4; ++q) s.inv_den.v[q] = fdiv(1.0f, den.v[q]);
 }
 
+template <bool kBcast = false>
 __device__ __forceinline__ F4 tail4_p(const Soft4& s, const float* __restrict__ lg, int B, int row0, int e, float inv_t) {
-    F4 z = ld4(lg + (int64_t)e * B + row0);
+    F4 z = ld4_logits<kBcast>(lg, B, e, row0);
 #pragma unroll
     for (int q = 0; q < 4; ++q) z.v[q] = fexp(z.v[q] * inv_t - s.mx.v[q]) * s.inv_den.v[q];
     return z;
@@ -612,8 +622,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_gd_forward_em4(tarl_csr grp, co
 // log-probability of what was drawn (sum over the groups of log(p_hit + eps); a group without a hit makes the row
 // -inf, as log_prob() of that action would, src/reinforcement_learning.py:86-91) accumulated in the same pass, so that
 // a rollout needs no second sweep over the logits.
-__global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
-                                                            int B, int C, int n_tiles, const float* __restrict__ u,
+template <bool kBcast>
+__global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, const float* __restrict__ logits,
+                                                            float inv_t, int B, int C, int n_tiles,
+                                                            const float* __restrict__ u,
                                                             int64_t u_sb, int64_t u_sg, uint8_t* __restrict__ onehot,
                                                             float* __restrict__ part_lp, int32_t* __restrict__ part_bad) {
     __shared__ float sm_f[kThreads];
@@ -638,7 +650,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, con
         float ug[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) ug[q] = u[(t.row0 + q) * u_sb + t.g * u_sg];
-        soft4_load(s, grp, logits, nullptr, B, t.row0, t.k0, t.k1, inv_t);
+        soft4_load<kBcast>(s, grp, logits, nullptr, B, t.row0, t.k0, t.k1, inv_t);
         F4 cum = {{0.f, 0.f, 0.f, 0.f}};
         int hit[4] = {-1, -1, -1, -1};         // position inside the group
         float ph[4] = {0.f, 0.f, 0.f, 0.f};
@@ -654,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, con
             }
         }
         for (int k = t.k0 + kCache; k < t.k1; ++k) {
-            const F4 p4 = tail4_p(s, logits, B, t.row0, grp.eid[k], inv_t);
+            const F4 p4 = tail4_p<kBcast>(s, logits, B, t.row0, grp.eid[k], inv_t);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 cum.v[q] += p4.v[q];
@@ -813,6 +825,13 @@ inline dim3 gd_grid(int K, int B) {      // one CTA per tile of kThreads/Bp grou
 }
 constexpr int kBwdMaxCtas = 148 * 8;      // persistent backward (tile stride): a few waves of resident CTAs
 constexpr int kFwdMaxCtas = 148 * 16;     // forward CTAs walk tiles with a stride: this bounds the partials per row
+// The caps count CTAs of the WHOLE grid: with many row chunks (grid.y = B / 32 = 32 for a 1024-replica rollout) each
+// chunk gets cap / grid.y CTAs in x, so that a CTA still walks tens of tiles — the prefetch pipeline has something to
+// prefetch and the per-CTA block reductions of the partial sums are amortised.
+inline unsigned em4_cap(int cap, const dim3& g) {
+    const unsigned per = (unsigned)cap / (g.y > 0 ? g.y : 1);
+    return per > 0 ? per : 1;
+}
 inline dim3 gd_fwd_grid(int K, int B) {
     dim3 g = gd_grid(K, B);
     if (g.x > (unsigned)kFwdMaxCtas) g.x = kFwdMaxCtas;
@@ -896,7 +915,7 @@ int tarl_graphdist_forward(const tarl_csr* groups, const tarl_rows* logits, floa
     if (fast && K > 0) {
         grid = em4_grid(K, batch);
         n_tiles = (int)grid.x;
-        if (grid.x > (unsigned)kFwdMaxCtas) grid.x = kFwdMaxCtas;
+        if (grid.x > em4_cap(kFwdMaxCtas, grid)) grid.x = em4_cap(kFwdMaxCtas, grid);
     }
     const int nb = (int)grid.x;
     float* part_ent = nullptr; float* part_lp = nullptr; int32_t* part_bad = nullptr;
@@ -934,7 +953,7 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
     if (temperature != 0.0f && em4_ok(logits, batch, action, action_dtype, grad_logits)) {
         dim3 grid = em4_grid(groups->n_rows, batch);
         const int n_tiles = (int)grid.x;
-        if (grid.x > (unsigned)kBwdMaxCtas) grid.x = kBwdMaxCtas;
+        if (grid.x > em4_cap(kBwdMaxCtas, grid)) grid.x = em4_cap(kBwdMaxCtas, grid);
         k_gd_backward_em4<<<grid, kThreads, 0, s>>>(
             *groups, data_of<const float>(logits), 1.0f / temperature, batch, em4_chunks(batch), n_tiles,
             data_of<const uint8_t>(action), grad_log_prob, grad_entropy, log_prob, data_of<float>(grad_logits));
@@ -956,18 +975,23 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
     if (batch == 0 || groups->n_edges == 0) return TARL_OK;
     if (!logits || !logits->data || !uniforms || !uniforms->data || !onehot || !onehot->data) return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (temperature != 0.0f && onehot_dtype == TARL_ACTION_U8 && em4_ok(logits, batch, onehot, onehot_dtype)) {
+    // logits: edge-major, or one row broadcast over the batch (row stride 0, unit column stride)
+    const bool bcast = batch > 1 && logits->row_stride == 0 && logits->col_stride == 1;
+    tarl_rows lg_as_em = *logits;
+    if (bcast) { lg_as_em.data = reinterpret_cast<void*>(uintptr_t(16)); lg_as_em.row_stride = 1; lg_as_em.col_stride = batch; }   // passes the layout test
+    if (temperature != 0.0f && onehot_dtype == TARL_ACTION_U8 &&
+        em4_ok(bcast ? &lg_as_em : logits, batch, onehot, onehot_dtype)) {
         dim3 grid = em4_grid(groups->n_rows, batch);
         const int n_tiles = (int)grid.x;
-        if (grid.x > (unsigned)kFwdMaxCtas) grid.x = kFwdMaxCtas;
+        if (grid.x > em4_cap(kFwdMaxCtas, grid)) grid.x = em4_cap(kFwdMaxCtas, grid);
         const int nb = (int)grid.x;
         if (log_prob != nullptr && partials == nullptr) return TARL_E_WORKSPACE;
         float* part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;       // same layout as the forward's
         int32_t* part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
-        k_gd_sample_em4<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
-                                                  em4_chunks(batch), n_tiles, data_of<const float>(uniforms),
-                                                  uniforms->row_stride, uniforms->col_stride, data_of<uint8_t>(onehot),
-                                                  part_lp, part_bad);
+        auto kernel = bcast ? k_gd_sample_em4<true> : k_gd_sample_em4<false>;
+        kernel<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
+                                         em4_chunks(batch), n_tiles, data_of<const float>(uniforms), uniforms->row_stride,
+                                         uniforms->col_stride, data_of<uint8_t>(onehot), part_lp, part_bad);
         if (log_prob != nullptr) k_gd_finish<<<batch, kThreads, 0, s>>>(nullptr, part_lp, part_bad, nb, nullptr, log_prob);
         return launch_status();
     }

@@ -163,7 +163,7 @@ class GraphDistribution(Distribution):
         if dtype not in (torch.int64, torch.bool, torch.uint8):
             raise ValueError("sample dtype must be int64, bool or uint8")
         store = torch.int64 if dtype == torch.int64 else torch.uint8
-        em = rows > 1 and lg.stride(0) == 1 and len(self._lead) <= 1 and S == 1
+        em = rows > 1 and lg.stride(0) in (0, 1) and len(self._lead) <= 1 and S == 1
         if out is not None:
             if out.numel() != rows * E or out.dtype not in (store, torch.bool if store == torch.uint8 else store) or out.device != dev:
                 raise ValueError("out must be a buffer of the sample's shape and dtype")
@@ -173,8 +173,10 @@ class GraphDistribution(Distribution):
             out = _edge_major(rows, E, store, dev) if em else torch.empty(rows, E, dtype=store, device=dev)
         # the log-probability of the draw comes out of the same kernel on the layout MPNNPolicyNet emits
         fused = (return_log_prob and store == torch.uint8 and rows > 1 and S == 1 and self.temperature != 0.0
-                 and (rows in (4, 8, 16) or rows % 32 == 0) and lg.stride(0) == 1 and lg.stride(1) == rows
-                 and out.stride(0) == 1 and out.stride(1) == rows and lg.data_ptr() % 16 == 0 and out.data_ptr() % 4 == 0)
+                 and (rows in (4, 8, 16) or rows % 32 == 0)
+                 and ((lg.stride(0) == 1 and lg.stride(1) == rows and lg.data_ptr() % 16 == 0)       # edge-major
+                      or (lg.stride(0) == 0 and lg.stride(1) == 1))                                  # one row for all
+                 and out.stride(0) == 1 and out.stride(1) == rows and out.data_ptr() % 4 == 0)
         lp = partials = None
         if fused:
             lp = torch.empty(rows, dtype=torch.float32, device=dev)

@@ -122,6 +122,11 @@ class MPNNPolicyNet(MessagePassing, Agents):
         batched = node_features.dim() == 3
         nf = node_features if batched else node_features.unsqueeze(0)
         nf = nf.to(torch.float32)
+        # An observation expanded over the batch (stride 0: the rollout hands the static template to every replica,
+        # and the active path reads nothing else) has ONE distinct row: compute it once, return it expanded.
+        B_out = nf.size(0)
+        if B_out > 1 and nf.stride(0) == 0:
+            nf = nf[:1]
         if nf.stride(2) != 1:
             nf = nf.contiguous()
         ei = self.edge_index
@@ -131,6 +136,8 @@ class MPNNPolicyNet(MessagePassing, Agents):
         by_target = group_csr_for(self._ei_dev, "target", self.num_nodes)
         self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=nf.device)
         logits = _PolicyEmbed.apply(self.nodes_embedding.weight, nf, self._dst32, by_target, self._flags)
+        if logits.size(0) != B_out:
+            logits = logits.contiguous().expand(B_out, -1)
         return logits if batched else logits.reshape(self.num_edges)
 
     def check_errors(self):

@@ -285,3 +285,35 @@ def test_value_mlp_split_cache_follows_the_weights():
     assert torch.allclose(a4, b4, rtol=1e-5, atol=1e-5)
     a5, b5 = both(64)
     assert torch.allclose(a5, b5, rtol=1e-5, atol=1e-5)
+
+
+def test_policy_on_an_expanded_observation_and_sampling_from_one_logits_row():
+    """A rollout hands MPNNPolicyNet the static observation expanded over the replicas (batch stride 0): the net
+    computes one row and returns it expanded; sampling / log_prob / entropy from such logits must equal what the
+    materialised [B, N, 7] observation gives, and gradients must flow through the expansion."""
+    from tarl_simulator_b200.distribution import GraphDistribution
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N, E, B = 500, 2100, 32
+    ei = torch.stack([torch.randint(0, N - 20, (E,), device="cuda", generator=g), torch.randint(0, N, (E,), device="cuda", generator=g)])
+    one = torch.rand(1, N, 7, device="cuda", generator=g)
+    one[..., 6] = torch.arange(N, device="cuda").float()
+    net = MPNNPolicyNet(ei, N, torch.ones(E, device="cuda"), "cuda")
+    lg_x = net(one.expand(B, -1, -1), None, None)                 # stride-0 batch
+    lg_m = net(one.repeat(B, 1, 1), None, None)                   # materialised
+    assert lg_x.shape == lg_m.shape == (B, E) and lg_x.stride(0) == 0
+    assert torch.equal(lg_x, lg_m)
+    d_x, d_m = GraphDistribution(lg_x, ei), GraphDistribution(lg_m, ei)
+    u = torch.rand(B, d_x.nb_nodes, device="cuda", generator=g)
+    out = torch.empty(E, B, dtype=torch.bool, device="cuda").t()
+    a_x, lp_x = d_x.sample(uniforms=u, dtype=torch.bool, out=out, return_log_prob=True)
+    a_m, lp_m = d_m.sample(uniforms=u, dtype=torch.bool, return_log_prob=True)
+    assert a_x.data_ptr() == out.data_ptr() and torch.equal(a_x, a_m)
+    assert torch.allclose(lp_x, lp_m, rtol=1e-6, atol=1e-4)
+    assert torch.allclose(d_x.log_prob(a_x), d_m.log_prob(a_m), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(d_x.entropy(), d_m.entropy(), rtol=1e-6, atol=1e-4)
+    (d_x.log_prob(a_x).sum() + d_x.entropy().sum()).backward()
+    gx = net.nodes_embedding.weight.grad.clone()
+    net.nodes_embedding.weight.grad = None
+    (d_m.log_prob(a_m).sum() + d_m.entropy().sum()).backward()
+    assert torch.allclose(gx, net.nodes_embedding.weight.grad, rtol=1e-4, atol=1e-5)
