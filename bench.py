@@ -308,7 +308,7 @@ def run_native(args):
     sel_devs = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
     dtt_hosts = [torch.empty(E, dtype=torch.float32).pin_memory() for _ in range(2)]
     pop_hosts = [torch.empty(N, dtype=torch.bool).pin_memory() for _ in range(2)]
-    e2e_steps = min(args.steps, 30)
+    e2e_steps = min(args.steps, 100)
     copy_stream = torch.cuda.Stream(dev)        # device -> host
     in_stream = torch.cuda.Stream(dev)          # host -> device (its own copy engine)
     ev_in = [torch.cuda.Event() for _ in range(2)]
