@@ -384,14 +384,26 @@ def run_native(args):
                       "per-step working set fits in L2 (small workload)"},
            "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clk.summary()}
 
+    # The secondary blocks must not take the headline line down with them: a failure is reported in place. (With
+    # several ranks an exception on one rank would leave the others in a collective, so it is still fatal there.)
+    def guarded(fn, *a):
+        if world > 1:
+            return fn(*a)
+        try:
+            return fn(*a)
+        except Exception as exc:        # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            return {"error": f"{type(exc).__name__}: {exc}"}
+
     if not args.no_mpnn:
-        out["mpnn"] = mpnn_bench(args, g, dev, world, rank, peak)
+        out["mpnn"] = guarded(mpnn_bench, args, g, dev, world, rank, peak)
         out["gpu_launches"] += out["mpnn"].pop("_launches_in_headline", 0)
     if not args.no_ppo:
-        out["ppo"] = ppo_bench(args, dev, world, rank)
+        out["ppo"] = guarded(ppo_bench, args, dev, world, rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, sample_steps=args.cpu_steps)
-        if "mpnn" in out:
+        if "mpnn" in out and "error" not in out["mpnn"]:
             out["mpnn"]["cpu_baseline"] = mpnn_cpu_baseline(args)
     if world > 1:
         dist.destroy_process_group()
