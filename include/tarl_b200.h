@@ -270,13 +270,15 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
  * node_features [B,N,>=7] (element strides given), edge_features [B,E] with batch stride ef_batch_stride (0 = one
  * row shared by the whole batch), agent_index [B,N] int64, agent_features [agent_rows, 9]. msg_weight [17]
  * (= message_mlp.1.weight), msg_bias [1], node_weight [1], node_bias [1] are device pointers. Outputs proj, mean, v
- * are NODE-major with the batch row innermost: element (b, n) at n*B + b (proj and mean are what backward needs). */
+ * are NODE-major with the batch row innermost: element (b, n) at n*B + b (proj and mean are what backward needs).
+ * agent_proj: [agent_rows] scratch (the agent part of the projection, msg_weight[7:16] . agent row, computed once per
+ * agent row and gathered per node). */
 int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
                           int64_t nf_row_stride, const float* edge_features, int64_t ef_batch_stride,
                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
                           const float* msg_weight, const float* msg_bias, const float* node_weight,
-                          const float* node_bias, int32_t batch, int32_t n_nodes, float* proj, float* mean, float* v,
-                          int32_t* flags, void* stream);
+                          const float* node_bias, int32_t batch, int32_t n_nodes, float* agent_proj, float* proj,
+                          float* mean, float* v, int32_t* flags, void* stream);
 
 /* Gradient of sum(grad_v * v) w.r.t. the four parameter tensors: grads[0:17] = d msg_weight, [17] = d msg_bias,
  * [18] = d node_weight, [19] = d node_bias. grad_v: element (b, n) at b*gv_batch_stride + n*gv_node_stride.

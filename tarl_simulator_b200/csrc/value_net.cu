@@ -53,23 +53,79 @@ __device__ __forceinline__ void load_x(const Inputs& in, int b, int n, float x[k
 // proj[n,b] = w[0:16] . x[b,n]. Tiled (tile_map.cuh): x is assembled from the row-major observation with the node
 // innermost (node_features rows and agent_index entries of 32 consecutive nodes are contiguous; agent_features is a
 // small table), proj is written with the row innermost.
+// The 7 node features of 32 consecutive nodes of one sample are 224 contiguous floats when the observation is dense
+// ([B, N, 7] with unit strides): the warp loads them coalesced (7 instructions, 7 wavefronts) into its own shared
+// buffer and every lane picks its 7 (stride 7: conflict-free), instead of 7 strided loads of 28 sectors each.
+// n_first = first node of the warp's segment; lanes beyond the graph read nothing. Warp-synchronous.
+constexpr int kWarpsPerCta = tarl::kTileThreads / 32;
+__device__ __forceinline__ void load_nf_staged(const Inputs& in, bool dense, int b, int n_first, int lane, bool lane_live,
+                                               float* __restrict__ warp_buf, float x[kNodeDim]) {
+    if (dense) {
+        const float* p = in.nf + b * in.nf_bs + (int64_t)n_first * kNodeDim;
+        const int n_valid = min(32, in.N - n_first) * kNodeDim;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < kNodeDim; ++k) {
+            const int o = lane + 32 * k;
+            if (o < n_valid) warp_buf[o] = p[o];
+        }
+        __syncwarp();
+        if (lane_live) {
+#pragma unroll
+            for (int c = 0; c < kNodeDim; ++c) x[c] = warp_buf[lane * kNodeDim + c];
+        }
+    } else if (lane_live) {
+        const float* p = in.nf + b * in.nf_bs + (int64_t)(n_first + lane) * in.nf_rs;
+#pragma unroll
+        for (int c = 0; c < kNodeDim; ++c) x[c] = p[c];
+    }
+}
+
+__device__ __forceinline__ long long agent_row(const Inputs& in, int b, int n, int32_t* flags) {
+    long long a = in.ai[(int64_t)b * in.N + n];
+    if (a < 0) a += in.af_rows;                                   // torch advanced indexing wraps negatives
+    if (a < 0 || a >= in.af_rows) {
+        if (flags != nullptr) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_AGENT_RANGE);
+        a = 0;
+    }
+    return a;
+}
+
+// pa[a] = w[7:16] . agent_features[a, 0:9]: the agent part of the message projection, once per agent row instead of
+// once per (node, sample) — the projection then gathers one float per node instead of nine.
+__global__ void __launch_bounds__(256) k_value_agent_project(const float* __restrict__ af, int af_rows,
+                                                             const float* __restrict__ w, float* __restrict__ pa) {
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a >= af_rows) return;
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kAgentDim; ++c) acc += w[kNodeDim + c] * af[(int64_t)a * kAgentDim + c];
+    pa[a] = acc;
+}
+
 __global__ void __launch_bounds__(tarl::kTileThreads) k_value_project(Inputs in, int Bp, const float* __restrict__ w,
+                                                                      const float* __restrict__ pa,
                                                                       float* __restrict__ proj,
                                                                       int32_t* __restrict__ flags) {
     __shared__ float sm[tarl::kTileSmem];
+    __shared__ float sm_nf[kWarpsPerCta][32 * kNodeDim];
     const tarl::Tile t = tarl::tile_here(in.B, Bp);
-    float wr[kIn];
+    const bool dense = in.nf_rs == kNodeDim;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float wr[kNodeDim];
 #pragma unroll
-    for (int c = 0; c < kIn; ++c) wr[c] = w[c];
+    for (int c = 0; c < kNodeDim; ++c) wr[c] = w[c];
     tarl::tile_walk_nodes(t, [&](int r, int j) {
         const int n = t.n0 + j;
-        if (n >= in.N || r >= t.nrows) return;
-        float x[kIn];
-        load_x(in, t.b0 + r, n, x, flags);
+        const bool live = n < in.N && r < t.nrows;
+        const bool row_live = r < t.nrows && t.n0 + (j - lane) < in.N;      // warp-uniform
+        float x[kNodeDim];
+        if (row_live) load_nf_staged(in, dense, t.b0 + r, n - lane, lane, live, sm_nf[warp], x);
+        if (!live) return;
         float acc = 0.0f;
 #pragma unroll
-        for (int c = 0; c < kIn; ++c) acc += wr[c] * x[c];
-        sm[tarl::tile_slot(t, r, j)] = acc;
+        for (int c = 0; c < kNodeDim; ++c) acc += wr[c] * x[c];
+        sm[tarl::tile_slot(t, r, j)] = acc + pa[agent_row(in, t.b0 + r, n, flags)];
     });
     __syncthreads();
     tarl::tile_walk_rows(t, [&](int r, int j) {
@@ -189,6 +245,8 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr
         vals[17] += gs;
     });
     __syncthreads();
+    // (staging the node features through shared memory as k_value_project does was measured slower here: 0.78 ->
+    // 1.13 ms; this walk is not bound by its load instructions)
     tarl::tile_walk_nodes(t, [&](int r, int j) {
         const int n = t.n0 + j;
         if (n >= in.N || r >= t.nrows) return;
@@ -238,22 +296,23 @@ int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features,
                           int64_t nf_row_stride, const float* edge_features, int64_t ef_batch_stride,
                           const int64_t* agent_index, const float* agent_features, int32_t agent_rows,
                           const float* msg_weight, const float* msg_bias, const float* node_weight,
-                          const float* node_bias, int32_t batch, int32_t n_nodes, float* proj, float* mean, float* v,
-                          int32_t* flags, void* stream) {
+                          const float* node_bias, int32_t batch, int32_t n_nodes, float* agent_proj, float* proj,
+                          float* mean, float* v, int32_t* flags, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc != TARL_OK) return rc;
     if (batch == 0 || n_nodes == 0) return TARL_OK;
     if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !node_bias ||
-        !proj || !mean || !v || !flags || (by_source->n_edges > 0 && !edge_features))
+        !agent_proj || !proj || !mean || !v || !flags || (by_source->n_edges > 0 && !edge_features))
         return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
     const int nb = blocks_for((int64_t)batch * n_nodes);
+    k_value_agent_project<<<(agent_rows + 255) / 256, 256, 0, s>>>(agent_features, agent_rows, msg_weight, agent_proj);
     k_value_project<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, 0, s>>>(in, tarl::tile_rows_pow2(batch), msg_weight,
-                                                                                   proj, flags);
+                                                                                   agent_proj, proj, flags);
     k_value_aggregate<<<nb, kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
     return launch_status();
 }

@@ -159,13 +159,14 @@ class _ValueMessagePassing(torch.autograd.Function):
         proj = torch.empty(N, B, dtype=torch.float32, device=dev)
         mean = torch.empty(N, B, dtype=torch.float32, device=dev)
         v = torch.empty(N, B, dtype=torch.float32, device=dev)
+        agent_proj = torch.empty(af.size(0), dtype=torch.float32, device=dev)     # scratch: w[7:16] . agent row
         pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
         ef_bs = ef.stride(0) if B > 1 else 0
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_value_mp_forward(
                 by_source.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs, ai.data_ptr(),
                 af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
-                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+                agent_proj.data_ptr(), proj.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_forward")
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
         ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
