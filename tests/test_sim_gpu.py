@@ -365,3 +365,60 @@ def test_data_dependent_faults_are_flagged():
     with pytest.raises(IndexError):
         a.check_errors()
     assert float(g.x[0, c.NUM]) == 1.0                              # nothing was removed
+
+
+def test_full_size_environment_invariants():
+    """BASELINE.json configs[3] at full size (999 000 links, 2 000 000 agents), where no oracle finishes: size-independent
+    properties of the whole environment step on the link store — every agent is in at most one queue slot and every
+    queued agent is flagged ON_WAY, the reward is minus the sum of the queue counters, the insertion / withdrawal
+    counters agree with the agent table (inserted = on the way + arrived), NUM never leaves [0, MAXN], arrivals only
+    ever increase, and two replicas fed the same noise stay bit-identical.
+
+    NOT an invariant, by the reference's own behaviour: "queued agents == agents on the way". The response phase
+    (src/response_mpnn.py:66-83) is evaluated on the post-direction state of ALL links at once, so an agent handed
+    into an EMPTY link d is, for that one evaluation, the head of d and still the tail of the link u it came from; if
+    d has a turn back into u (config_network creates U-turn edges, src/transportation_simulator.py:160) d pops it as
+    well and the agent is in no queue any more while its ON_WAY flag stays set. The reference's golden trajectories
+    show it (tests/golden/sim_rl_grid3: agent 54 at t = 21546) and the kernels reproduce it bit for bit; here it only
+    means `queued <= on the way`."""
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    frm, to, n_nodes = synthetic.ring_radial_links(500, 500, device="cuda")
+    frm, to = synthetic.reorder_links(frm, to, "node")
+    g, Nmax = synthetic.build_graph(frm, to, n_nodes)
+    N = int(g.num_roads)
+    assert N == 999_000 and Nmax == 15
+    af = synthetic.population(g, 2_000_000, 21540, 60, seed=11)
+    R = 2
+    env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=3)
+    env.reset()
+    E = g.edge_index_routes.size(1)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    done_before = torch.zeros(R, device="cuda")
+    for s in range(40):
+        if s % 2 == 0:                                            # the same routing draw in both replicas
+            env.choice(uniforms=torch.rand(env.side.n_choosers, device="cuda", generator=gen).repeat(R, 1))
+        u = torch.rand(E, device="cuda", generator=gen).clamp_(min=1e-7).repeat(R, 1)
+        out = env.step(None, noise=u)
+        if s % 8 != 7:
+            continue
+        x = env.export_x()
+        num = x[:, :N, 3 * Nmax + 1]
+        maxn = x[:, :N, 3 * Nmax]
+        assert bool((num >= 0).all()) and bool((num <= maxn).all())
+        on_way = env.agent_features[..., 7].sum(1)
+        done = env.agent_features[..., 8].sum(1)
+        assert bool((num.sum(1) <= on_way).all())                                # see the docstring
+        assert torch.equal(-out["reward"], num.sum(1))                           # reward = -occupancy
+        assert torch.equal(env.counters[:, 0].float(), on_way + done)            # inserted = on the way + arrived
+        assert torch.equal(env.counters[:, 1].float(), done)
+        assert bool((done >= done_before).all())
+        done_before = done
+        ids = x[0, :N, :Nmax]
+        live = torch.arange(Nmax, device="cuda").unsqueeze(0) < num[0].unsqueeze(1)
+        q = ids[live].long()
+        assert q.numel() == int(num[0].sum()) and q.numel() == torch.unique(q).numel() and int(q.min()) >= 1
+        assert bool((env.agent_features[0, q, 7] == 1).all())                    # every queued agent is flagged ON_WAY
+        assert torch.equal(x[0], x[1]) and torch.equal(env.agent_features[0], env.agent_features[1])
+    assert float(on_way.min()) > 100_000 and float(num.sum(1).min()) > 100_000      # the network did fill up
+    env.check_errors()
