@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(kThreads) k_policy_weight_grad(const float* __
 // edge-major tensors (element (b, e) at e*B + b: what MPNNPolicyNet emits) the Bp lanes of a group read one
 // contiguous B-vector per edge and the group's edge ids are loaded once per group, not once per row. Any strides are
 // accepted (a row-major [B,E] tensor is correct, just less coalesced). A group's values are cached in registers
-// (kCache edges) so that logits are read once and every exp is evaluated once.
-constexpr int kCache = 6;
+// (kCache edges) so that logits are read once and every exp is evaluated once; longer groups recompute their tail.
+// 5 = the out-degree of a road link in the full graph of a 4-way network (4 turns incl. the U-turn + its DEST edge):
+// every unrolled, predicated slot beyond the real degree costs registers and issue slots (6 -> 5: backward 0.69 ->
+// 0.54 ms, forward 0.41 -> 0.37 ms at 32 rows x 6.0 M edges).
+constexpr int kCache = 5;
 
 struct View {          // element (b, e) of a [B, E] tensor at base[b*sb + e*se]
     int64_t sb, se;
