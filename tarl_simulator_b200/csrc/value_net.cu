@@ -153,6 +153,44 @@ __global__ void __launch_bounds__(kThreads) k_value_aggregate(tarl_csr by_src, I
     v[i] = tanhf(a[0] * m + c[0]);
 }
 
+// The same with one thread per (source node, 4 consecutive batch rows) when B % 4 == 0: 128-bit gathers of the
+// projected B-vectors and 128-bit stores, and the node's edge list / edge features are read once per four rows.
+__global__ void __launch_bounds__(kThreads) k_value_aggregate4(tarl_csr by_src, Inputs in, const float* __restrict__ w,
+                                                               const float* __restrict__ w0, const float* __restrict__ a,
+                                                               const float* __restrict__ c, const float* __restrict__ proj,
+                                                               float* __restrict__ mean, float* __restrict__ v) {
+    const int C = in.B >> 2;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)C * in.N) return;
+    const int n = (int)(i / C), b0 = 4 * (int)(i % C);
+    const float we = w[kIn], bias = w0[0];
+    const int k0 = by_src.ptr[n], k1 = by_src.ptr[n + 1];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = k0; k < k1; ++k) {
+        const float4 p = *reinterpret_cast<const float4*>(proj + (int64_t)by_src.idx[k] * in.B + b0);
+        const int e = by_src.eid[k];
+        float f[4];
+        f[0] = in.ef[(int64_t)b0 * in.ef_bs + e];
+        if (in.ef_bs == 0) { f[1] = f[2] = f[3] = f[0]; }
+        else {
+#pragma unroll
+            for (int q = 1; q < 4; ++q) f[q] = in.ef[(int64_t)(b0 + q) * in.ef_bs + e];
+        }
+        acc[0] += tanhf(p.x + we * f[0] + bias);
+        acc[1] += tanhf(p.y + we * f[1] + bias);
+        acc[2] += tanhf(p.z + we * f[2] + bias);
+        acc[3] += tanhf(p.w + we * f[3] + bias);
+    }
+    float m[4], vv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        m[q] = k1 > k0 ? acc[q] / (float)(k1 - k0) : 0.0f;
+        vv[q] = tanhf(a[0] * m[q] + c[0]);
+    }
+    *reinterpret_cast<float4*>(mean + (int64_t)n * in.B + b0) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(v + (int64_t)n * in.B + b0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+
 __device__ __forceinline__ float warp_sum(float x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
@@ -214,7 +252,7 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_node_grad(tarl_csr
 // from the node's own projection and the gathered gm B-vectors -> gs[n,b] = sum of d z over the in-edges (ascending
 // edge id), kept in shared memory. Walk 2, nodes innermost: the 16 input-weight gradients gs * x[b,n,:] with x read
 // the way the observation is laid out (once per node and row, not once per edge).
-__global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, int Bp,
+__global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr by_dst, Inputs in, int Bp, bool vec4,
                                                                         const float* __restrict__ w,
                                                                         const float* __restrict__ w0,
                                                                         const float* __restrict__ proj,
@@ -226,24 +264,62 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr
 #pragma unroll
     for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
     const float we = w[kIn], bias = w0[0];
-    tarl::tile_walk_rows(t, [&](int r, int j) {
-        const int n = t.n0 + j, b = t.b0 + r;
-        if (n >= in.N || r >= t.nrows) return;
-        const float pn = proj[(int64_t)n * in.B + b];
-        const float* ef = in.ef + b * in.ef_bs;
-        float gs = 0.0f, gwe = 0.0f;
-        const int k1 = by_dst.ptr[n + 1];
-        for (int k = by_dst.ptr[n]; k < k1; ++k) {
-            const float f = ef[by_dst.eid[k]];
-            const float m = tanhf(pn + we * f + bias);
-            const float gz = gm[(int64_t)by_dst.idx[k] * in.B + b] * (1.0f - m * m);
-            gs += gz;
-            gwe += gz * f;
+    if (vec4) {
+        // (target node, 4 consecutive rows) per thread: 128-bit loads of proj / gm, the in-edge list once per four rows
+        const int C = t.Bp >> 2, shc = t.sh - 2;
+        for (int p = threadIdx.x; p < (tarl::kTilePairs >> 2); p += tarl::kTileThreads) {
+            const int r0 = 4 * (p & (C - 1)), j = p >> shc;
+            const int n = t.n0 + j, b0 = t.b0 + r0;
+            if (n >= in.N || r0 >= t.nrows) continue;
+            const float4 pn = *reinterpret_cast<const float4*>(proj + (int64_t)n * in.B + b0);
+            float gs[4] = {0.f, 0.f, 0.f, 0.f}, gwe = 0.0f;
+            const int k1 = by_dst.ptr[n + 1];
+            for (int k = by_dst.ptr[n]; k < k1; ++k) {
+                const int e = by_dst.eid[k];
+                const float4 g4 = *reinterpret_cast<const float4*>(gm + (int64_t)by_dst.idx[k] * in.B + b0);
+                float f[4];
+                f[0] = in.ef[(int64_t)b0 * in.ef_bs + e];
+                if (in.ef_bs == 0) { f[1] = f[2] = f[3] = f[0]; }
+                else {
+#pragma unroll
+                    for (int q = 1; q < 4; ++q) f[q] = in.ef[(int64_t)(b0 + q) * in.ef_bs + e];
+                }
+                const float pq[4] = {pn.x, pn.y, pn.z, pn.w}, gq[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float m = tanhf(pq[q] + we * f[q] + bias);
+                    const float gz = gq[q] * (1.0f - m * m);
+                    gs[q] += gz;
+                    gwe += gz * f[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sm[tarl::tile_slot(t, r0 + q, j)] = gs[q];
+                vals[17] += gs[q];
+            }
+            vals[16] += gwe;
         }
-        sm[tarl::tile_slot(t, r, j)] = gs;
-        vals[16] += gwe;
-        vals[17] += gs;
-    });
+    } else {
+        tarl::tile_walk_rows(t, [&](int r, int j) {
+            const int n = t.n0 + j, b = t.b0 + r;
+            if (n >= in.N || r >= t.nrows) return;
+            const float pn = proj[(int64_t)n * in.B + b];
+            const float* ef = in.ef + b * in.ef_bs;
+            float gs = 0.0f, gwe = 0.0f;
+            const int k1 = by_dst.ptr[n + 1];
+            for (int k = by_dst.ptr[n]; k < k1; ++k) {
+                const float f = ef[by_dst.eid[k]];
+                const float m = tanhf(pn + we * f + bias);
+                const float gz = gm[(int64_t)by_dst.idx[k] * in.B + b] * (1.0f - m * m);
+                gs += gz;
+                gwe += gz * f;
+            }
+            sm[tarl::tile_slot(t, r, j)] = gs;
+            vals[16] += gwe;
+            vals[17] += gs;
+        });
+    }
     __syncthreads();
     // (staging the node features through shared memory as k_value_project does was measured slower here: 0.78 ->
     // 1.13 ms; this walk is not bound by its load instructions)
@@ -313,7 +389,13 @@ int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features,
     k_value_agent_project<<<(agent_rows + 255) / 256, 256, 0, s>>>(agent_features, agent_rows, msg_weight, agent_proj);
     k_value_project<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, 0, s>>>(in, tarl::tile_rows_pow2(batch), msg_weight,
                                                                                    agent_proj, proj, flags);
-    k_value_aggregate<<<nb, kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
+    const bool vec4 = (batch & 3) == 0 && ((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(mean) |
+                                            reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    if (vec4)
+        k_value_aggregate4<<<blocks_for((int64_t)(batch >> 2) * n_nodes), kThreads, 0, s>>>(
+            *by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
+    else
+        k_value_aggregate<<<nb, kThreads, 0, s>>>(*by_source, in, msg_weight, msg_bias, node_weight, node_bias, proj, mean, v);
     return launch_status();
 }
 
@@ -342,7 +424,10 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
     const int Bp = tarl::tile_rows_pow2(batch);
     k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
                                                           gv_batch_stride, gv_node_stride, gm, partials);
-    k_value_edge_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_target, in, Bp, msg_weight, msg_bias, proj, gm, partials);
+    // 4 rows per thread when every row chunk of the tile is a whole multiple of 4 rows and the B-vectors are 16-byte aligned
+    const bool vec4 = (batch & 3) == 0 && Bp >= 4 &&
+                      ((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(gm)) & 15) == 0;
+    k_value_edge_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_target, in, Bp, vec4, msg_weight, msg_bias, proj, gm, partials);
     k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
     return launch_status();
 }
