@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 10
+#define TARL_ABI_VERSION 11
 
 /* return codes */
 #define TARL_OK 0
@@ -291,6 +291,31 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
                            int32_t batch, int32_t n_nodes, const float* proj, const float* mean, const float* v,
                            const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, float* gm,
                            float* partials, float* grads, void* stream);
+
+/* The same propagate in TRAIN mode: nn.Dropout(p) on the [B*E, 17] message input (src/agents/mpnn_agent.py:278,
+ * 385-386; ATen computes x * (mask / (1 - p))). Every (row, edge) pair has a 17-bit keep word (bit k = input k
+ * survives; k < 16 the target node's inputs, k = 16 the edge feature): either injected — keep_bits [B, E] with batch
+ * stride keep_batch_stride, e.g. the mask the reference itself drew — or, with keep_bits == NULL, drawn in the kernel
+ * from Philox4x32-10 keyed by `seed` (tarl_value_mp_dropout_bits writes the words of that stream: what the kernels
+ * will use for the same seed / p). msg: [E*B] output, element (b, e) at e*B + b (the tanh messages; backward reads
+ * them back). mean, v as in tarl_value_mp_forward. */
+int tarl_value_mp_dropout_bits(uint64_t seed, float p, int32_t batch, int32_t n_edges, uint32_t* keep_bits, void* stream);
+int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                                  int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                                  int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                                  int32_t agent_rows, const float* msg_weight, const float* msg_bias,
+                                  const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
+                                  const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
+                                  float* msg, float* mean, float* v, int32_t* flags, void* stream);
+/* grads / gm / partials as in tarl_value_mp_backward; keep_bits / seed / p must be the forward call's. */
+int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                                   int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                                   int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                                   int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
+                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
+                                   const float* msg, const float* mean, const float* v, const float* grad_v,
+                                   int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
+                                   float* grads, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Population operations either side of the core step (csrc/agents.cu). Each works on either state layout.

@@ -150,6 +150,46 @@ def gen_nets(out):
     np.savez_compressed(os.path.join(out, "mpnn_nets.npz"), **blob)
 
 
-def main(out):
-    gen_graph_distribution(out)
-    gen_nets(out)
+def gen_value_train(out):
+    """MPNNValueNet in TRAIN mode: the message dropout (nn.Dropout(0.05) on the [B*E, 17] message input,
+    src/agents/mpnn_agent.py:278) draws from torch's global generator. The mask the unmodified reference used is
+    recovered by replaying the same draw (same seed, same shape) and stored with the outputs; the two dropouts of
+    time_net are set to p = 0 on the instance so that the output is a function of that one mask."""
+    mp = ref_loader.load("src.agents.mpnn_agent")
+    import mpnn_port
+    g = torch.Generator().manual_seed(33)
+    blob = {}
+    for tag, B in (("u", None), ("b", 4)):
+        N, E, A = 14, 37, 20
+        ei, nf, ef, ai, tm, af = _small_net_inputs(g, N, E, A, B)
+        torch.manual_seed(7)
+        net = mp.MPNNValueNet(ei, N, "cpu")
+        net.agent_features = af
+        net.train()
+        net.time_net[1].p = 0.0
+        net.time_net[4].p = 0.0
+        rows = (B or 1) * E
+        torch.manual_seed(1234)
+        keep = torch.nn.functional.dropout(torch.ones(rows, 17), net.message_mlp[0].p, True) != 0
+        keep = keep.view(*(() if B is None else (B,)), E, 17)
+        torch.manual_seed(1234)
+        v = net(nf, ef, ai, tm)
+        wv = torch.randn(v.shape, generator=g)
+        (v * wv).sum().backward()
+        sd = {k: p.detach().clone() for k, p in net.named_parameters()}
+        chk = mpnn_port.value_net_forward(sd, nf, ef, af, ai, tm, ei, keep=keep)
+        assert torch.allclose(chk, v.detach(), rtol=1e-6, atol=1e-7), "recovered mask is not the one the reference drew"
+        blob.update({f"{tag}.{k}": t.numpy() for k, t in dict(
+            edge_index=ei, node_features=nf, edge_features=ef, agent_index=ai, time=tm, agent_features=af,
+            keep_bits=mpnn_port.pack_keep_bits(keep), out=v.detach(), w_out=wv).items()})
+        blob.update({f"{tag}.param.{k}": t.numpy() for k, t in sd.items()})
+        blob.update({f"{tag}.grad.{k}": p.grad.numpy() for k, p in net.named_parameters()})
+        print(f"value train {tag}: dropped {int((~keep).sum())} of {keep.numel()} inputs, value={v.detach().flatten().tolist()[:2]}")
+    np.savez_compressed(os.path.join(out, "mpnn_value_train.npz"), **blob)
+
+
+def main(out, only_new=False):
+    if not only_new:
+        gen_graph_distribution(out)
+        gen_nets(out)
+    gen_value_train(out)

@@ -12,6 +12,14 @@
 // Layout: proj / mean / v / gm are NODE-major with the batch row innermost (element (b, n) at n*B + b) and one thread
 // handles one (node, row) pair with the row innermost, so the B lanes of a node gather one contiguous B-vector per
 // neighbour and read the node's edge list once. edge_features may be broadcast over the batch (batch stride 0).
+//
+// Train mode (nn.Dropout(0.05) on the [B*E, 17] message input, :278,385-386): every (row, edge) pair has its own
+// 17-bit keep mask, so the per-node projection no longer factors out. The *_dropout entry points compute the message
+// per (TARGET node, row) — the node's 16 inputs are loaded once and every in-edge applies its own mask — into an
+// edge-major message buffer msg[e*B + b] that the source-side mean and the backward pass read back. The mask is
+// either injected ([B, E] words, bit k = input k survives; parity tests replay the mask the reference drew) or drawn
+// in the kernel: Philox4x32-10 keyed by the seed, counter (edge, row, draw), 16-bit fields compared with
+// round(p * 65536) — a documented stream of its own (declared divergence D4, as for the core step's noise).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -353,6 +361,151 @@ __global__ void __launch_bounds__(kThreads) k_value_finish(const float* __restri
     if (threadIdx.x == 0) grads[j] = sm[0];
 }
 
+// ---- train mode: message dropout ------------------------------------------------------------------------------------
+struct Drop {
+    const uint32_t* bits; int64_t bits_bs;   // injected keep words [B, E] (batch stride in elements), or nullptr
+    uint32_t seed_lo, seed_hi, thresh;       // in-kernel stream: input k of (row, edge) is dropped iff field_k < thresh
+    float scale;                             // 1 / (1 - p) (0 when p == 1: everything dropped)
+};
+
+__device__ __forceinline__ void philox_raw(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// keep word of (row b, edge e): bit k set = message input k survives (k < 16 node inputs, k = 16 edge feature)
+__device__ __forceinline__ uint32_t keep_word(const Drop& d, int b, int e) {
+    if (d.bits != nullptr) return d.bits[(int64_t)b * d.bits_bs + e];
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {            // 3 draws x 8 sixteen-bit fields; the first 17 are used
+        uint32_t r[4];
+        philox_raw((uint32_t)e, (uint32_t)b, (uint32_t)j, 0x44524f50u, d.seed_lo, d.seed_hi, r);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int k = 8 * j + q;
+            if (k <= kIn) {
+                const uint32_t field = (r[q >> 1] >> (16 * (q & 1))) & 0xffffu;
+                word |= (field >= d.thresh ? 1u : 0u) << k;
+            }
+        }
+    }
+    return word;
+}
+
+__global__ void __launch_bounds__(kThreads) k_value_dropout_bits(Drop d, int B, int E, uint32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)B * E) return;
+    const int e = (int)(i / B), b = (int)(i % B);
+    out[(int64_t)b * E + e] = keep_word(d, b, e);
+}
+
+// one thread per (TARGET node, batch row), row innermost: msg[e,b] = tanh(sum_k keep_k * (x_k * scale) * w_k + w0)
+// for every in-edge e of the node (x * (mask / (1 - p)) as ATen's dropout computes it, then the 17-term dot product)
+__global__ void __launch_bounds__(kThreads) k_value_message_dropout(tarl_csr by_dst, Inputs in, Drop d,
+                                                                    const float* __restrict__ w,
+                                                                    const float* __restrict__ w0,
+                                                                    float* __restrict__ msg, int32_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)in.B * in.N) return;
+    const int n = (int)(i / in.B), b = (int)(i % in.B);
+    const int k0 = by_dst.ptr[n], k1 = by_dst.ptr[n + 1];
+    if (k0 == k1) {
+        agent_row(in, b, n, flags);                       // range fault reported even for nodes nobody points at
+        return;
+    }
+    float x[kIn];
+    load_x(in, b, n, x, flags);
+#pragma unroll
+    for (int c = 0; c < kIn; ++c) x[c] = (x[c] * d.scale) * w[c];
+    const float we = w[kIn], bias = w0[0];
+    const float* ef = in.ef + b * in.ef_bs;
+    for (int k = k0; k < k1; ++k) {
+        const int e = by_dst.eid[k];
+        const uint32_t word = keep_word(d, b, e);
+        float z = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) z += ((word >> c) & 1u) ? x[c] : 0.0f;
+        z += ((word >> kIn) & 1u) ? (ef[e] * d.scale) * we : 0.0f;
+        msg[(int64_t)e * in.B + b] = tanhf(z + bias);
+    }
+}
+
+// one thread per (source node, batch row): mean of the stored messages in ascending edge id, then the node update
+__global__ void __launch_bounds__(kThreads) k_value_aggregate_msg(tarl_csr by_src, int B, int N,
+                                                                  const float* __restrict__ a, const float* __restrict__ c,
+                                                                  const float* __restrict__ msg, float* __restrict__ mean,
+                                                                  float* __restrict__ v) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (int64_t)B * N) return;
+    const int n = (int)(i / B), b = (int)(i % B);
+    const int k0 = by_src.ptr[n], k1 = by_src.ptr[n + 1];
+    float acc = 0.0f;
+    for (int k = k0; k < k1; ++k) acc += msg[(int64_t)by_src.eid[k] * B + b];
+    const float m = k1 > k0 ? acc / (float)(k1 - k0) : 0.0f;
+    mean[i] = m;
+    v[i] = tanhf(a[0] * m + c[0]);
+}
+
+// message backward with dropout, over the same (target node, row) tiles as k_value_edge_grad (one partial row per
+// tile): d z = gm[source, b] * (1 - msg^2); d w_k += d z * keep_k * scale * x_k; d w_16 += d z * keep_16 * scale * f;
+// d w0 += d z.
+__global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
+                                                                                const float* __restrict__ msg,
+                                                                                const float* __restrict__ gm,
+                                                                                float* __restrict__ partials) {
+    const tarl::Tile t = tarl::tile_here(in.B, Bp);
+    float vals[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
+    tarl::tile_walk_rows(t, [&](int r, int j) {
+        const int n = t.n0 + j, b = t.b0 + r;
+        if (n >= in.N || r >= t.nrows) return;
+        const int k0 = by_dst.ptr[n], k1 = by_dst.ptr[n + 1];
+        if (k0 == k1) return;
+        float x[kIn], gx[kIn];
+        load_x(in, b, n, x, nullptr);
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) gx[c] = 0.0f;
+        const float* ef = in.ef + b * in.ef_bs;
+        float gwe = 0.0f, gs = 0.0f;
+        for (int k = k0; k < k1; ++k) {
+            const int e = by_dst.eid[k];
+            const float m = msg[(int64_t)e * in.B + b];
+            const float gz = gm[(int64_t)by_dst.idx[k] * in.B + b] * (1.0f - m * m);
+            const uint32_t word = keep_word(d, b, e);
+#pragma unroll
+            for (int c = 0; c < kIn; ++c) gx[c] += ((word >> c) & 1u) ? gz : 0.0f;
+            gwe += ((word >> kIn) & 1u) ? gz * (ef[e] * d.scale) : 0.0f;
+            gs += gz;
+        }
+#pragma unroll
+        for (int c = 0; c < kIn; ++c) vals[c] += gx[c] * (x[c] * d.scale);
+        vals[16] += gwe;
+        vals[17] += gs;
+    });
+    block_store<18>(vals, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads);
+}
+
+Drop make_drop(const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p) {
+    Drop d;
+    d.bits = keep_bits;
+    d.bits_bs = keep_batch_stride;
+    d.seed_lo = (uint32_t)seed;
+    d.seed_hi = (uint32_t)(seed >> 32);
+    const double t = (double)p * 65536.0 + 0.5;
+    d.thresh = t < 0.0 ? 0u : (t > 65536.0 ? 65536u : (uint32_t)t);
+    d.scale = p < 1.0f ? 1.0f / (1.0f - p) : 0.0f;
+    return d;
+}
+
 int check(const tarl_csr* c, int n_nodes) {
     if (c == nullptr || c->n_rows != n_nodes || c->n_edges < 0) return TARL_E_BADARG;
     if (n_nodes > 0 && c->ptr == nullptr) return TARL_E_BADARG;
@@ -428,6 +581,74 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
     const bool vec4 = (batch & 3) == 0 && Bp >= 4 &&
                       ((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(gm)) & 15) == 0;
     k_value_edge_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_target, in, Bp, vec4, msg_weight, msg_bias, proj, gm, partials);
+    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
+    return launch_status();
+}
+
+int tarl_value_mp_dropout_bits(uint64_t seed, float p, int32_t batch, int32_t n_edges, uint32_t* keep_bits, void* stream) {
+    if (batch < 0 || n_edges < 0 || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
+    if (batch == 0 || n_edges == 0) return TARL_OK;
+    if (keep_bits == nullptr) return TARL_E_BADARG;
+    k_value_dropout_bits<<<blocks_for((int64_t)batch * n_edges), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        make_drop(nullptr, 0, seed, p), batch, n_edges, keep_bits);
+    return launch_status();
+}
+
+int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                                  int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                                  int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                                  int32_t agent_rows, const float* msg_weight, const float* msg_bias,
+                                  const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
+                                  const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
+                                  float* msg, float* mean, float* v, int32_t* flags, void* stream) {
+    if (batch < 0 || n_nodes < 0 || agent_rows < 1 || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
+    int rc = check(by_source, n_nodes);
+    if (rc == TARL_OK) rc = check(by_target, n_nodes);
+    if (rc != TARL_OK) return rc;
+    if (by_source->n_edges != by_target->n_edges) return TARL_E_BADARG;
+    if (batch == 0 || n_nodes == 0) return TARL_OK;
+    if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !node_bias ||
+        !mean || !v || !flags || (by_source->n_edges > 0 && (!edge_features || !msg)))
+        return TARL_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
+                       reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
+                       by_source->n_edges};
+    const int nb = blocks_for((int64_t)batch * n_nodes);
+    k_value_message_dropout<<<nb, kThreads, 0, s>>>(*by_target, in, make_drop(keep_bits, keep_batch_stride, seed, p),
+                                                    msg_weight, msg_bias, msg, flags);
+    k_value_aggregate_msg<<<nb, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, node_bias, msg, mean, v);
+    return launch_status();
+}
+
+int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
+                                   int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
+                                   int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
+                                   int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
+                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
+                                   const float* msg, const float* mean, const float* v, const float* grad_v,
+                                   int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
+                                   float* grads, void* stream) {
+    if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
+    int rc = check(by_source, n_nodes);
+    if (rc == TARL_OK) rc = check(by_target, n_nodes);
+    if (rc != TARL_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (batch == 0 || n_nodes == 0) {
+        return cudaMemsetAsync(grads, 0, sizeof(float) * kGrads, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+    }
+    if (!node_features || !agent_index || !agent_features || !node_weight || !mean || !v || !grad_v || !gm ||
+        !partials || (by_source->n_edges > 0 && (!edge_features || !msg)))
+        return TARL_E_BADARG;
+    const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
+                       reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
+                       by_source->n_edges};
+    const dim3 grid = tarl::tile_grid(n_nodes, batch);
+    const int Bp = tarl::tile_rows_pow2(batch);
+    k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
+                                                          gv_batch_stride, gv_node_stride, gm, partials);
+    k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, 0, s>>>(
+        *by_target, in, Bp, make_drop(keep_bits, keep_batch_stride, seed, p), msg, gm, partials);
     k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
     return launch_status();
 }

@@ -194,6 +194,57 @@ class _ValueMessagePassing(torch.autograd.Function):
                 grads[19:20].reshape(s[3]), None, None, None, None, None, None, None)
 
 
+class _ValueMessagePassingDropout(torch.autograd.Function):
+    """_ValueMessagePassing in train mode: nn.Dropout(p) on the [B*E, 17] message input (src/agents/mpnn_agent.py:278).
+    keep_bits: int32 [B, E] injected keep words (bit k = input k survives) or None = drawn in the kernels from the
+    Philox stream of `seed` (backward regenerates the same words)."""
+
+    @staticmethod
+    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags, keep_bits, seed, p):
+        B, N, _ = nf.shape
+        dev = nf.device
+        E = by_source.n_edges
+        msg = torch.empty(max(E, 1), B, dtype=torch.float32, device=dev)
+        mean = torch.empty(N, B, dtype=torch.float32, device=dev)
+        v = torch.empty(N, B, dtype=torch.float32, device=dev)
+        pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
+        ef_bs = ef.stride(0) if B > 1 else 0
+        kb_ptr, kb_bs = (keep_bits.data_ptr(), keep_bits.stride(0)) if keep_bits is not None else (None, 0)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_value_mp_forward_dropout(
+                by_source.ref(), by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs,
+                ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
+                kb_ptr, kb_bs, seed, p, msg.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mp_forward_dropout")
+        ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
+        ctx.drop = (keep_bits, seed, p)
+        ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
+        ctx.save_for_backward(nw, nf, ef, ai, af, msg, mean, v)
+        return v.t()
+
+    @staticmethod
+    def backward(ctx, grad_v):
+        nw, nf, ef, ai, af, msg, mean, v = ctx.saved_tensors
+        B, N, _ = nf.shape
+        dev = nf.device
+        lib = _cabi.lib()
+        keep_bits, seed, p = ctx.drop
+        kb_ptr, kb_bs = (keep_bits.data_ptr(), keep_bits.stride(0)) if keep_bits is not None else (None, 0)
+        gm = torch.empty(N, B, dtype=torch.float32, device=dev)
+        partials = torch.empty(max(20 * lib.tarl_value_mp_partial_count(N, B), 1), dtype=torch.float32, device=dev)
+        grads = torch.empty(20, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_value_mp_backward_dropout(
+                ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
+                ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), nw.data_ptr(), B, N, kb_ptr, kb_bs, seed, p,
+                msg.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
+                grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mp_backward_dropout")
+        s = ctx.shapes
+        return (grads[:17].reshape(s[0]), grads[17:18].reshape(s[1]), grads[18:19].reshape(s[2]),
+                grads[19:20].reshape(s[3])) + (None,) * 10
+
+
 class MPNNValueNet(MessagePassing, Agents):
     """State value by one round of message passing over the full graph (src/agents/mpnn_agent.py:267-402):
     per edge tanh(Linear(17→1)([x_target(16) ‖ edge_attr])), mean over each source node's out-edges,
@@ -201,9 +252,13 @@ class MPNNValueNet(MessagePassing, Agents):
     reference's (`message_mlp.1.*`, `node_mlp.0.*`, `final_mlp.0.*`, `time_net.{0,3,6}.*`). The gather / aggregate /
     update and their backward are csrc/value_net.cu; the two dense heads (time_net, final_mlp) are library GEMVs.
 
-    The reference applies Dropout(0.05) to every [E,17] message input in train mode; an RNG-dependent mask cannot be
-    matched across implementations, so the kernels implement the deterministic (eval / p = 0) path and train mode
-    with p > 0 raises (SURVEY.md §7 "hard parts")."""
+    Train mode: the reference applies Dropout(0.05) to every [B*E, 17] message input (:278). The mask cannot factor
+    through the per-node projection, so a second kernel set (`tarl_value_mp_*_dropout`) computes the messages per
+    (target node, row) with a 17-bit keep word per (row, edge). The words are drawn in the kernels from a Philox
+    stream whose seed comes from torch's default CPU generator (so `torch.manual_seed` reproduces a run; declared
+    divergence D4: not the reference's bit stream), or injected through `keep_bits` (int32 [B, E] / [E], bit k = input
+    k survives) — the parity tests inject the mask the unmodified reference drew. `dropout_words(B)` returns the words
+    of the last train-mode forward. time_net's own dropouts are torch modules."""
 
     h = ObservationFeatureHelpers()
 
@@ -223,12 +278,25 @@ class MPNNValueNet(MessagePassing, Agents):
         self.to(device)
         self._ei_dev = None
         self._flags = None
+        self.keep_bits = None           # injected message-dropout keep words for the NEXT train-mode forward (tests)
+        self._last_drop = None
+
+    def dropout_words(self):
+        """int32 [B, E] keep words of the last train-mode forward (bit k = message input k survived)."""
+        if self._last_drop is None:
+            return None
+        keep_bits, seed, p, B = self._last_drop
+        if keep_bits is not None:
+            return keep_bits
+        out = torch.empty(B, self.num_edges, dtype=torch.int32, device=self._flags.device)
+        with torch.cuda.device(out.device):
+            rc = _cabi.lib().tarl_value_mp_dropout_bits(seed, p, B, self.num_edges, out.data_ptr(), _stream(out.device))
+        _cabi.check(rc, "tarl_value_mp_dropout_bits")
+        return out
 
     def forward(self, node_features, edge_features, agent_index, time):
         if not node_features.is_cuda:
             raise RuntimeError("MPNNValueNet computes on CUDA devices only (no CPU fallback)")
-        if self.training and self.message_mlp[0].p > 0:
-            raise NotImplementedError("MPNNValueNet: message dropout is RNG-dependent; call .eval() or set p = 0")
         batched = node_features.dim() == 3
         nf = (node_features if batched else node_features.unsqueeze(0)).to(torch.float32)
         if nf.stride(2) != 1:
@@ -246,8 +314,18 @@ class MPNNValueNet(MessagePassing, Agents):
         by_target = group_csr_for(self._ei_dev, "target", self.num_nodes)
         self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=nf.device)
         lin, upd = self.message_mlp[1], self.node_mlp[0]
-        v = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
-                                       by_target, self._flags)
+        p_drop = float(self.message_mlp[0].p)
+        if self.training and p_drop > 0:
+            keep_bits, self.keep_bits = self.keep_bits, None
+            if keep_bits is not None:
+                keep_bits = keep_bits.to(device=nf.device, dtype=torch.int32).reshape(B, self.num_edges).contiguous()
+            seed = int(torch.randint(0, 2 ** 62, (1,)))          # torch's default CPU generator: no device sync
+            self._last_drop = (keep_bits, seed, p_drop, B)
+            v = _ValueMessagePassingDropout.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
+                                                  by_target, self._flags, keep_bits, seed, p_drop)
+        else:
+            v = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
+                                           by_target, self._flags)
         if not batched:
             v = v.reshape(self.num_nodes)
         # final_mlp([v_nodes ‖ time_net(t)]) with the weight split instead of the concatenation (src/agents/mpnn_agent.py:359-361 of the

@@ -160,9 +160,117 @@ def test_value_net_goldens(tag, golden_dir):
     for k, p in net.named_parameters():
         close(p.grad, g(f"value.{tag}.grad.{k}"), rtol=1e-5, atol=1e-6)
     net.check_errors()
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
+def test_value_net_train_mode_goldens(tag, golden_dir):
+    """MPNNValueNet in TRAIN mode with the message-dropout mask the unmodified reference drew injected: outputs and
+    parameter gradients of the reference (tests/golden/mpnn_value_train.npz)."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNet
+    z = np.load(os.path.join(golden_dir, "mpnn_value_train.npz"))
+    g = lambda k: torch.from_numpy(z[k])
+    ei = g(f"{tag}.edge_index")
+    nf, ef, ai, tm = (g(f"{tag}.{k}").cuda() for k in ("node_features", "edge_features", "agent_index", "time"))
+    net = MPNNValueNet(ei.cuda(), nf.size(-2), "cuda")
+    net.agent_features = g(f"{tag}.agent_features").cuda()
+    with torch.no_grad():
+        for k, p in net.named_parameters():
+            p.copy_(g(f"{tag}.param.{k}"))
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(nf, ef, ai, tm)
+    net.time_net[1].p = 0.0                  # as in the generator: the output depends on the message mask alone
+    net.time_net[4].p = 0.0
+    net.keep_bits = g(f"{tag}.keep_bits").cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = net(nf, ef, ai, tm)
+    close(out, g(f"{tag}.out"))
+    (out * g(f"{tag}.w_out").cuda()).sum().backward()
+    for k, p in net.named_parameters():
+        close(p.grad, g(f"{tag}.grad.{k}"), rtol=1e-5, atol=1e-6)
+    net.check_errors()
+    assert torch.equal(net.dropout_words().cpu().reshape(-1), g(f"{tag}.keep_bits").reshape(-1))
+
+
+@pytest.mark.parametrize("B,injected", [(None, True), (5, True), (4, False), (32, False)])
+def test_value_net_train_mode_vs_oracle_large(B, injected):
+    """Train mode on thousands of nodes: injected random masks, and the in-kernel Philox stream read back through
+    dropout_words() and handed to the oracle — forward and every gradient must agree with the SAME mask."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNet
+    g = torch.Generator().manual_seed(23 + (B or 0))
+    N, E, A = 3000, 11000, 500
+    src = torch.randint(0, N - 300, (E,), generator=g)           # the last 300 nodes have no out-edge
+    ei = torch.stack([src, torch.randint(0, N - 100, (E,), generator=g)])    # ... and 100 nodes no in-edge
+    lead = () if B is None else (B,)
+    nf = torch.rand(*lead, N, 7, generator=g) * 3
+    ef = torch.rand(*lead, E, 1, generator=g)
+    ai = torch.randint(0, A + 1, (*lead, N), generator=g)
+    tm = torch.rand(*lead, 1, generator=g) * 10
+    af = torch.rand(A + 1, 9, generator=g) * 2
+    net = MPNNValueNet(ei.cuda(), N, "cuda")
+    net.agent_features = af.cuda()
+    net.train()
+    net.time_net[1].p = 0.0
+    net.time_net[4].p = 0.0
+    net.message_mlp[0].p = 0.2 if injected else 0.05
+    if injected:
+        keep = torch.rand(*lead, E, 17, generator=g) >= 0.2
+        net.keep_bits = mpnn_port.pack_keep_bits(keep).cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(99)
+    out = net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+    words = net.dropout_words().cpu().reshape(*lead, E)
+    keep_used = mpnn_port.unpack_keep_bits(words)
+    if injected:
+        assert torch.equal(keep_used, keep)
+    else:
+        assert int(words.max()) < (1 << 17)
+        frac = keep_used.float().mean().item()                  # 17 * B * E Bernoulli(0.95) draws
+        assert abs(frac - 0.95) < 4 * (0.95 * 0.05 / keep_used.numel()) ** 0.5 + 1e-4, frac
+        per_input = keep_used.float().reshape(-1, 17).mean(0)
+        assert (per_input - 0.95).abs().max() < 0.01
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.named_parameters()}
+    ref = mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei, keep=keep_used, drop_p=net.message_mlp[0].p)
+    close(out, ref.detach(), rtol=1e-5, atol=1e-6)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    (out * w.cuda()).sum().backward()
+    for k, v in net.named_parameters():
+        close(v.grad, p[k].grad, rtol=2e-5, atol=2e-6)
+    net.check_errors()
+    if not injected:
+        # the stream follows torch's default generator: same seed -> same words and value, next draw -> different
+        torch.manual_seed(99)
+        out2 = net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+        assert torch.equal(out2, out) and torch.equal(net.dropout_words().cpu().reshape(*lead, E), words)
+        net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+        assert not torch.equal(net.dropout_words().cpu().reshape(*lead, E), words)
+        # eval mode is untouched by all this
+        net.eval()
+        ev = net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+        close(ev, mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei).detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_value_net_train_mode_drop_everything():
+    """p = 1: nn.Dropout zeroes every message input, the message is tanh(bias) on every edge."""
+    from tarl_simulator_b200.mpnn_agent import MPNNValueNet
+    g = torch.Generator().manual_seed(3)
+    N, E = 50, 200
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+    net = MPNNValueNet(ei.cuda(), N, "cuda")
+    net.agent_features = torch.rand(8, 9, generator=g).cuda()
+    net.train()
+    net.time_net[1].p = 0.0
+    net.time_net[4].p = 0.0
+    net.message_mlp[0].p = 1.0
+    nf, ef = torch.rand(N, 7, generator=g), torch.rand(E, 1, generator=g)
+    ai, tm = torch.randint(0, 8, (N,), generator=g), torch.rand(1, generator=g)
+    out = net(nf.cuda(), ef.cuda(), ai.cuda(), tm.cuda())
+    assert int(net.dropout_words().abs().max()) == 0
+    p = {k: v.detach().cpu() for k, v in net.named_parameters()}
+    has_out = torch.zeros(N).scatter_(0, ei[0], 1.0)
+    v = torch.tanh(p["node_mlp.0.weight"][0, 0] * torch.tanh(p["message_mlp.1.bias"][0]) * has_out + p["node_mlp.0.bias"][0])
+    te = net.time_net(tm.cuda()).detach().cpu()
+    ref = torch.cat((v, te)) @ p["final_mlp.0.weight"][0] + p["final_mlp.0.bias"]
+    close(out, ref, rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("B", [None, 4])

@@ -104,6 +104,29 @@ def test_graph_distribution_known_answer(golden_dir):
 
 
 @pytest.mark.parametrize("tag", ["u", "b"])
+def test_value_net_train_mode_port(tag, golden_dir):
+    """MPNNValueNet in train mode: the port with the message-dropout mask the unmodified reference drew (recovered by
+    oracle/gen_golden_mpnn.py) reproduces the reference's output and parameter gradients."""
+    z = np.load(os.path.join(golden_dir, "mpnn_value_train.npz"))
+    g = lambda k: torch.from_numpy(z[k])
+    ei = g(f"{tag}.edge_index")
+    nf, ef, ai, tm, af = (g(f"{tag}.{k}") for k in ("node_features", "edge_features", "agent_index", "time", "agent_features"))
+    keep = mpnn_port.unpack_keep_bits(g(f"{tag}.keep_bits"))
+    assert 0 < int((~keep).sum()) < keep.numel() // 8            # the golden really drops something
+    assert torch.equal(mpnn_port.pack_keep_bits(keep), g(f"{tag}.keep_bits"))
+    names = [k[len(f"{tag}.param."):] for k in z.files if k.startswith(f"{tag}.param.")]
+    p = {k: g(f"{tag}.param.{k}").clone().requires_grad_(True) for k in names}
+    v = mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei, keep=keep)
+    torch.testing.assert_close(v.detach(), g(f"{tag}.out"), rtol=1e-5, atol=1e-6)
+    (v * g(f"{tag}.w_out")).sum().backward()
+    for k in names:
+        torch.testing.assert_close(p[k].grad, g(f"{tag}.grad.{k}"), rtol=1e-4, atol=1e-6)
+    # and the mask matters: eval mode gives a different value
+    v_eval = mpnn_port.value_net_forward(p, nf, ef, af, ai, tm, ei)
+    assert not torch.allclose(v_eval.detach(), g(f"{tag}.out"), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
 def test_nets_port(tag, golden_dir):
     z = np.load(os.path.join(golden_dir, "mpnn_nets.npz"))
     g = lambda k: torch.from_numpy(z[k])
