@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 11
+#define TARL_ABI_VERSION 12
 
 /* return codes */
 #define TARL_OK 0
@@ -262,6 +262,21 @@ int tarl_graphdist_backward(const tarl_csr* groups, const tarl_rows* logits, flo
 int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float temperature, int32_t batch,
                           const tarl_rows* uniforms, const tarl_rows* onehot, int32_t onehot_dtype, float* log_prob,
                           float* partials, void* stream);
+
+/* Rollout form of the two calls a policy step makes — GraphDistribution.sample (src/reinforcement_learning.py:57-80)
+ * and the action write of SimulatorEnv._step, x[edge_index[0][mask], SELECTED_ROAD] = edge_index[1][mask] (:223-231) —
+ * for `batch` replicas that share ONE logits row (logits_row [E]; the active policy path does not read the dynamic
+ * observation). Draws one edge per (replica, source group) from uniforms [batch, K], writes the byte one-hot
+ * EDGE-major (element (b, e) at e*batch + b; batch % 4 == 0, 4-byte aligned), optionally the log-probability of the
+ * draw (log_prob [batch], partials as for tarl_graphdist_sample), and stores the target node of the drawn edge into
+ * SELECTED_ROAD of the group's source node: sel_links [batch, n_links] for road links (node id < n_links),
+ * sel_sources [batch, n_nodes - n_links] for the other nodes; group_node [K] = source node of each group, edge_dst
+ * [E] = edge_index[1] as int32. A group without a hit (uniform >= the rounded cumulative sum) leaves SELECTED_ROAD
+ * untouched and makes the row's log-probability -inf, exactly as the two separate calls do. */
+int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
+                                const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
+                                const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
+                                int32_t n_links, int32_t n_nodes, void* stream);
 
 /* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
  * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]

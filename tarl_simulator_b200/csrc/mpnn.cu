@@ -714,6 +714,213 @@ __global__ void __launch_bounds__(kThreads, 2) k_gd_sample_em4(tarl_csr grp, con
     }
 }
 
+// Rollout sampling: ONE logits row for every batch row (the active policy path does not read the dynamic observation,
+// so R replicas share their logits). The softmax of a group is then the same for every replica: a CTA computes the
+// cumulative distribution of 32 consecutive groups ONCE (phase 0, shared memory), and the per-replica work left is one
+// uniform, <= 8 compares and the one-hot bytes (phase 1: thread = (group, 4 replicas), replica innermost — 128-bit
+// uniform loads, 32-bit one-hot stores, a group's row vector contiguous). Optionally the draw is APPLIED in the same
+// pass — SELECTED_ROAD[replica, source node] = target of the drawn edge (src/reinforcement_learning.py:223-231) —
+// which needs the node innermost: the hit positions are parked as bytes in shared memory and phase 2 walks them with
+// the 32 groups on the lanes (128 contiguous bytes of SELECTED_ROAD per replica). The one-hot is still written (the
+// trajectory keeps it for the PPO update), but nobody has to read it back to step the environment.
+// Arithmetic per (group, row) is exactly that of k_gd_sample / k_gd_sample_em4 (z * inv_t, max, __expf, sum in
+// ascending edge id, one reciprocal, cumulative sum), so the three kernels draw the same edges from the same uniforms.
+constexpr int kBcGroups = 32;         // groups per tile
+constexpr int kBcDeg = 8;             // edges per group kept in shared memory; longer groups take the slow walk
+constexpr int kBcRows = 1024;         // batch rows per grid.y slice (4 per thread)
+constexpr int kBcPitch = kBcRows + 4; // bytes: lane stride of 257 words -> phase 2 reads are bank-conflict-free
+constexpr uint8_t kBcNoHit = 0xff, kBcBig = 0xfe;
+
+struct BcApply {
+    const int32_t* group_node;   // [K] source node of each group
+    const int32_t* edge_dst;     // [E] target node of each edge (the value SELECTED_ROAD receives)
+    float* sel_links;            // [batch, n_links]
+    float* sel_sources;          // [batch, n_nodes - n_links]
+    int n_links, n_nodes;
+};
+
+__global__ void __launch_bounds__(kThreads) k_gd_sample_bcast(tarl_csr grp, const float* __restrict__ lg, float inv_t, int B,
+                                                              int n_tiles, const float* __restrict__ u, int64_t u_sb,
+                                                              int64_t u_sg, uint8_t* __restrict__ onehot,
+                                                              float* __restrict__ part_lp, int32_t* __restrict__ part_bad,
+                                                              BcApply ap) {
+    __shared__ float sm_z[kBcGroups][kBcDeg], sm_cdf[kBcGroups][kBcDeg], sm_logp[kBcGroups][kBcDeg];
+    __shared__ int sm_eid[kBcGroups][kBcDeg], sm_dst[kBcGroups][kBcDeg];
+    __shared__ int sm_deg[kBcGroups], sm_k0[kBcGroups];
+    __shared__ float sm_red[kThreads];
+    __shared__ int sm_redi[kThreads];
+    __shared__ __align__(16) uint8_t sm_hit[kBcGroups * kBcPitch];
+    const bool apply = ap.sel_links != nullptr;
+    const int row_base = blockIdx.y * kBcRows;
+    const int rows_here = min(kBcRows, B - row_base);             // multiple of 4
+    const int chunks = rows_here >> 2;
+    int cp = 1;                                                   // chunks rounded up to a power of two (<= 256)
+    while (cp < chunks) cp <<= 1;
+    const int gpar = kThreads / cp;                               // groups handled side by side in phase 1
+    const int c = threadIdx.x & (cp - 1), gsub = threadIdx.x / cp;
+    const int row0 = row_base + 4 * c;
+    const bool rows_live = c < chunks;
+    const bool u_vec = u_sb == 1 && (u_sg & 3) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0;
+    float lp[4] = {0.f, 0.f, 0.f, 0.f};
+    int bad[4] = {0, 0, 0, 0};
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int g0 = tile * kBcGroups;
+        __syncthreads();                                          // previous tile's phase 2 is done with shared memory
+        // ---- phase 0: the 32 groups' distributions, once for every row
+        {
+            const int gl = threadIdx.x >> 3, j = threadIdx.x & 7, g = g0 + gl;
+            int k0 = 0, deg = 0;
+            if (g < grp.n_rows) { k0 = grp.ptr[g]; deg = grp.ptr[g + 1] - k0; }
+            if (j == 0) { sm_deg[gl] = deg; sm_k0[gl] = k0; }
+            if (j < deg && deg <= kBcDeg) {
+                const int e = grp.eid[k0 + j];
+                sm_eid[gl][j] = e;
+                sm_z[gl][j] = lg[e] * inv_t;
+                if (apply) sm_dst[gl][j] = ap.edge_dst[e];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kBcGroups) {
+            const int gl = threadIdx.x, deg = sm_deg[gl];
+            if (deg > 0 && deg <= kBcDeg) {
+                float mx = -FLT_MAX;
+                for (int j = 0; j < deg; ++j) mx = fmaxf(mx, sm_z[gl][j]);
+                float den = 0.0f;
+                for (int j = 0; j < deg; ++j) { const float ex = fexp(sm_z[gl][j] - mx); sm_z[gl][j] = ex; den += ex; }
+                const float inv_den = fdiv(1.0f, den);
+                float cum = 0.0f;
+                for (int j = 0; j < deg; ++j) {
+                    const float p = sm_z[gl][j] * inv_den;
+                    cum += p;
+                    sm_cdf[gl][j] = cum;
+                    sm_logp[gl][j] = flog(p + kLogEps);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 1: one uniform per (group, row) -> hit position, one-hot bytes, log-probability of the draw
+        for (int gl = gsub; gl < kBcGroups; gl += gpar) {
+            const int g = g0 + gl, deg = sm_deg[gl];
+            if (!rows_live || g >= grp.n_rows || deg == 0) continue;
+            float ug[4];
+            if (u_vec) {
+                const float4 t4 = *reinterpret_cast<const float4*>(u + (int64_t)g * u_sg + row0);
+                ug[0] = t4.x; ug[1] = t4.y; ug[2] = t4.z; ug[3] = t4.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ug[q] = u[(int64_t)(row0 + q) * u_sb + (int64_t)g * u_sg];
+            }
+            int hit[4] = {-1, -1, -1, -1};
+            if (deg <= kBcDeg) {
+#pragma unroll
+                for (int j = 0; j < kBcDeg; ++j) {
+                    if (j < deg) {
+                        const float cum = sm_cdf[gl][j];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (hit[q] < 0 && ug[q] < cum) hit[q] = j;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kBcDeg; ++j) {
+                    if (j < deg) {
+                        const uint32_t w = (hit[0] == j ? 1u : 0u) | (hit[1] == j ? 1u << 8 : 0u) |
+                                           (hit[2] == j ? 1u << 16 : 0u) | (hit[3] == j ? 1u << 24 : 0u);
+                        *reinterpret_cast<uint32_t*>(onehot + (int64_t)sm_eid[gl][j] * B + row0) = w;
+                    }
+                }
+                if (part_lp != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (hit[q] < 0) bad[q] = 1;
+                        else lp[q] += sm_logp[gl][hit[q]];
+                    }
+                }
+                if (apply)
+                    *reinterpret_cast<uint32_t*>(sm_hit + gl * kBcPitch + 4 * c) =
+                        (uint32_t)(hit[0] & 0xff) | (uint32_t)(hit[1] & 0xff) << 8 | (uint32_t)(hit[2] & 0xff) << 16 |
+                        (uint32_t)(hit[3] & 0xff) << 24;                      // -1 -> kBcNoHit
+            } else {
+                // a group longer than the shared-memory cache: every thread walks the logits row itself (same order)
+                const int k0 = sm_k0[gl], k1 = k0 + deg;
+                float mx = -FLT_MAX;
+                for (int k = k0; k < k1; ++k) mx = fmaxf(mx, lg[grp.eid[k]] * inv_t);
+                float den = 0.0f;
+                for (int k = k0; k < k1; ++k) den += fexp(lg[grp.eid[k]] * inv_t - mx);
+                const float inv_den = fdiv(1.0f, den);
+                float cum = 0.0f, ph[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int k = k0; k < k1; ++k) {
+                    const float p = fexp(lg[grp.eid[k]] * inv_t - mx) * inv_den;
+                    cum += p;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (hit[q] < 0 && ug[q] < cum) { hit[q] = k - k0; ph[q] = p; }
+                }
+                for (int k = k0; k < k1; ++k) {
+                    const int j = k - k0;
+                    const uint32_t w = (hit[0] == j ? 1u : 0u) | (hit[1] == j ? 1u << 8 : 0u) |
+                                       (hit[2] == j ? 1u << 16 : 0u) | (hit[3] == j ? 1u << 24 : 0u);
+                    *reinterpret_cast<uint32_t*>(onehot + (int64_t)grp.eid[k] * B + row0) = w;
+                }
+                if (part_lp != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (hit[q] < 0) bad[q] = 1;
+                        else lp[q] += flog(ph[q] + kLogEps);
+                    }
+                }
+                if (apply) {
+                    *reinterpret_cast<uint32_t*>(sm_hit + gl * kBcPitch + 4 * c) = 0x01010101u * kBcBig;
+                    const int node = ap.group_node[g];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (hit[q] < 0) continue;
+                        const float v = (float)ap.edge_dst[grp.eid[k0 + hit[q]]];
+                        if (node < ap.n_links) ap.sel_links[(int64_t)(row0 + q) * ap.n_links + node] = v;
+                        else ap.sel_sources[(int64_t)(row0 + q) * (ap.n_nodes - ap.n_links) + (node - ap.n_links)] = v;
+                    }
+                }
+            }
+        }
+        if (!apply) continue;
+        __syncthreads();
+        // ---- phase 2: SELECTED_ROAD with the node innermost (lanes = the tile's 32 groups, warps stride over the rows)
+        {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            const int g = g0 + lane;
+            const int deg = sm_deg[lane];
+            const bool live = g < grp.n_rows && deg > 0 && deg <= kBcDeg;
+            const int node = live ? ap.group_node[g] : 0;
+            const bool is_link = node < ap.n_links;
+            float* const base = is_link ? ap.sel_links + node : ap.sel_sources + (node - ap.n_links);
+            const int64_t pitch = is_link ? ap.n_links : ap.n_nodes - ap.n_links;
+            for (int r = warp; r < rows_here; r += kThreads / 32) {
+                if (!live) continue;
+                const uint8_t h = sm_hit[lane * kBcPitch + r];
+                if (h < kBcDeg) base[(int64_t)(row_base + r) * pitch] = (float)sm_dst[lane][h];
+            }
+        }
+    }
+    if (part_lp != nullptr) {
+        const int nb = gridDim.x;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            __syncthreads();
+            sm_red[threadIdx.x] = lp[q];
+            sm_redi[threadIdx.x] = bad[q];
+            __syncthreads();
+            if (threadIdx.x < chunks) {                            // c == threadIdx.x, gsub == 0
+                float v = 0.0f;
+                int n = 0;
+                for (int i = 0; i < gpar; ++i) { v += sm_red[i * cp + threadIdx.x]; n += sm_redi[i * cp + threadIdx.x]; }
+                const int row = row_base + 4 * threadIdx.x + q;
+                part_lp[(int64_t)row * nb + blockIdx.x] = v;
+                part_bad[(int64_t)row * nb + blockIdx.x] = n;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) k_gd_backward_em4(tarl_csr grp, const float* __restrict__ logits, float inv_t,
                                                               int B, int C, int n_tiles,
                                                               const uint8_t* __restrict__ action,
@@ -852,6 +1059,25 @@ inline View view_of(const tarl_rows* r) { return r != nullptr ? View{r->row_stri
 template <typename T>
 inline T* data_of(const tarl_rows* r) { return r != nullptr ? static_cast<T*>(r->data) : nullptr; }
 
+
+// launch of k_gd_sample_bcast (+ the log-probability finish); apply.sel_links == nullptr: sample only
+int launch_sample_bcast(const tarl_csr* groups, const float* logits_row, float temperature, int batch,
+                        const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials, const BcApply& apply,
+                        cudaStream_t s) {
+    if (log_prob != nullptr && partials == nullptr) return TARL_E_WORKSPACE;
+    const int n_tiles = (groups->n_rows + kBcGroups - 1) / kBcGroups;
+    int nb = tarl_graphdist_partial_count(groups->n_rows, batch);           // bounds the partials per row
+    if (nb > n_tiles) nb = n_tiles;
+    if (nb < 1) nb = 1;
+    const dim3 grid((unsigned)nb, (unsigned)((batch + kBcRows - 1) / kBcRows));
+    float* part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;     // same layout as the forward's
+    int32_t* part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
+    k_gd_sample_bcast<<<grid, kThreads, 0, s>>>(*groups, logits_row, 1.0f / temperature, batch, n_tiles,
+                                                data_of<const float>(uniforms), uniforms->row_stride, uniforms->col_stride,
+                                                onehot, part_lp, part_bad, apply);
+    if (log_prob != nullptr) k_gd_finish<<<batch, kThreads, 0, s>>>(nullptr, part_lp, part_bad, nb, nullptr, log_prob);
+    return launch_status();
+}
 }  // namespace
 
 extern "C" {
@@ -991,7 +1217,10 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
         if (log_prob != nullptr && partials == nullptr) return TARL_E_WORKSPACE;
         float* part_lp = log_prob ? partials + (size_t)batch * nb : nullptr;       // same layout as the forward's
         int32_t* part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
-        auto kernel = bcast ? k_gd_sample_em4<true> : k_gd_sample_em4<false>;
+        if (bcast)      // one logits row for every batch row: the group's distribution is computed once per CTA
+            return launch_sample_bcast(groups, data_of<const float>(logits), temperature, batch, uniforms,
+                                       data_of<uint8_t>(onehot), log_prob, partials, BcApply{}, s);
+        auto kernel = k_gd_sample_em4<false>;
         kernel<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
                                          em4_chunks(batch), n_tiles, data_of<const float>(uniforms), uniforms->row_stride,
                                          uniforms->col_stride, data_of<uint8_t>(onehot), part_lp, part_bad);
@@ -1010,6 +1239,22 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
                                                          data_of<const float>(uniforms), view_of(uniforms),
                                                          data_of<long long>(onehot), view_of(onehot));
     return launch_status();
+}
+
+int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
+                                const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
+                                const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
+                                int32_t n_links, int32_t n_nodes, void* stream) {
+    int rc = check_csr(groups);
+    if (rc != TARL_OK) return rc;
+    if (batch < 0 || (batch & 3) != 0 || temperature == 0.0f || n_links < 0 || n_nodes < n_links) return TARL_E_BADARG;
+    if (batch == 0 || groups->n_edges == 0) return TARL_OK;
+    if (!logits_row || !uniforms || !uniforms->data || !onehot || (reinterpret_cast<uintptr_t>(onehot) & 3) != 0 ||
+        !group_node || !edge_dst || !sel_links || (n_nodes > n_links && !sel_sources))
+        return TARL_E_BADARG;
+    const BcApply ap = {group_node, edge_dst, sel_links, sel_sources, n_links, n_nodes};
+    return launch_sample_bcast(groups, logits_row, temperature, batch, uniforms, onehot, log_prob, partials, ap,
+                               static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

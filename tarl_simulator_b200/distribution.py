@@ -83,6 +83,25 @@ class _LogProbEntropy(torch.autograd.Function):
         return grad, None, None, None
 
 
+class ActionSink:
+    """Where a sampled action goes inside an environment: SELECTED_ROAD of R replicas, road links [R, N] and the other
+    source nodes [R, N_tot - N], both contiguous and in node-id order, for the graph `edge_index` describes.
+    GraphDistribution.sample(sink=...) sets `applied` when it wrote them."""
+
+    def __init__(self, edge_index, groups, sel_links, sel_sources, n_links, n_nodes):
+        self.edge_index, self.groups = edge_index, groups
+        self.sel_links, self.sel_sources = sel_links, sel_sources
+        self.n_links, self.n_nodes = int(n_links), int(n_nodes)
+        self.group_node = groups.nodes.to(torch.int32).contiguous()
+        self.edge_dst = edge_index[1].to(torch.int32).contiguous()
+        self.applied = False
+
+    def matches(self, dist, rows: int) -> bool:
+        return (dist._groups is self.groups and self.sel_links.size(0) == rows and self.sel_links.is_contiguous()
+                and (self.sel_sources is None or self.sel_sources.is_contiguous())
+                and self.sel_links.device == dist._logits.device)
+
+
 class GraphDistribution(Distribution):
     arg_constraints = {}
     has_rsample = False
@@ -143,11 +162,15 @@ class GraphDistribution(Distribution):
 
     # -- Distribution API ------------------------------------------------------------------------------------
     def sample(self, sample_shape=torch.Size(), uniforms: torch.Tensor | None = None, dtype=torch.int64,
-               out: torch.Tensor | None = None, return_log_prob: bool = False):
+               out: torch.Tensor | None = None, return_log_prob: bool = False, sink=None):
         """One-hot [sample_shape.., .., E]: inverse CDF with one uniform per (row, source group) (:57-80). int64 like
         the reference by default; dtype=torch.bool writes one byte per edge instead of eight. `uniforms` ([.., K])
         injects the noise the reference draws with torch.rand. `out` (optional): a buffer of the result's shape and
-        storage dtype to write into (any strides; every entry is written), e.g. a frame of a preallocated trajectory."""
+        storage dtype to write into (any strides; every entry is written), e.g. a frame of a preallocated trajectory.
+        `sink` (optional, rollouts): an `ActionSink` of the environment the action is meant for. When every row shares
+        one logits row and the sample is an edge-major byte one-hot, the kernel that draws the edges also writes
+        SELECTED_ROAD of every replica (what SimulatorEnv._step does with the action, :223-231) and `sink.applied`
+        becomes True — the environment then steps without reading the one-hot back; otherwise the sink is untouched."""
         sample_shape = torch.Size(sample_shape)
         B, E = self._logits.shape
         dev = self._logits.device
@@ -182,6 +205,28 @@ class GraphDistribution(Distribution):
             lp = torch.empty(rows, dtype=torch.float32, device=dev)
             partials = torch.empty(3 * rows * max(_cabi.lib().tarl_graphdist_partial_count(self.nb_nodes, rows), 1),
                                    dtype=torch.float32, device=dev)
+        if sink is not None:
+            sink.applied = False
+        if (sink is not None and S == 1 and rows > 1 and rows % 4 == 0 and store == torch.uint8 and self.temperature != 0.0
+                and lg.stride(0) == 0 and lg.stride(1) == 1 and out.stride(0) == 1 and out.stride(1) == rows
+                and out.data_ptr() % 4 == 0 and sink.matches(self, rows)):
+            if return_log_prob and not fused:      # any multiple of 4 rows has the fused log-probability here
+                lp = torch.empty(rows, dtype=torch.float32, device=dev)
+                partials = torch.empty(3 * rows * max(_cabi.lib().tarl_graphdist_partial_count(self.nb_nodes, rows), 1),
+                                       dtype=torch.float32, device=dev)
+                fused = True
+            with torch.cuda.device(dev):
+                rc = _cabi.lib().tarl_graphdist_sample_apply(
+                    self._groups.ref(), lg.data_ptr(), self.temperature, rows, _cabi.rows(u), out.data_ptr(),
+                    lp.data_ptr() if fused else None, partials.data_ptr() if fused else None,
+                    sink.group_node.data_ptr(), sink.edge_dst.data_ptr(), sink.sel_links.data_ptr(),
+                    sink.sel_sources.data_ptr() if sink.sel_sources is not None else None, sink.n_links, sink.n_nodes,
+                    _stream(dev))
+            _cabi.check(rc, "tarl_graphdist_sample_apply")
+            sink.applied = True
+            out = out.view(torch.bool) if dtype == torch.bool else out
+            out = out.reshape(*sample_shape, *self._lead, E)
+            return (out, lp.reshape(self._lead)) if return_log_prob else out
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), _cabi.rows(lg), self.temperature, rows,
                                                    _cabi.rows(u), _cabi.rows(out),

@@ -258,6 +258,21 @@ class BatchedSimulatorEnv:
                                                              _stream(self.device))
         _cabi.check(rc, "tarl_agents_apply_action_groups")
 
+    def action_sink(self):
+        """ActionSink over this environment's SELECTED_ROAD arrays (None when the store keeps the links in its own
+        locality order): lets GraphDistribution.sample write the routing decisions in the pass that draws them."""
+        if self.store.slot_link is not None:
+            return None
+        from .distribution import ActionSink
+        grp = group_csr_for(self.graph.edge_index, "source_rank")
+        sel = self.store.sel
+        key = (sel.data_ptr(), id(grp))
+        if getattr(self, "_sink_key", None) != key:
+            self._sink = ActionSink(self.graph.edge_index, grp, sel[: self.R * self.N].view(self.R, self.N),
+                                    self.src_sel if self.n_nodes > self.N else None, self.N, self.n_nodes)
+            self._sink_key = key
+        return self._sink
+
     def choice(self, uniforms: torch.Tensor | None = None, seed: int = 0):
         """Random routing for every replica (Agents.choice on the store)."""
         st = self._state()

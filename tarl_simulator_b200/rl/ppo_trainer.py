@@ -45,8 +45,10 @@ class PolicyModule(nn.Module):
         logits = self.net(obs["node_features"], obs.get("edge_features"), obs.get("agent_index"))
         return GraphDistribution(logits, self.edge_index)
 
-    def forward(self, obs, mode: bool = False, out: torch.Tensor | None = None):
-        """out (optional): a bool [.., E] buffer (e.g. one frame of a preallocated trajectory) for the action."""
+    def forward(self, obs, mode: bool = False, out: torch.Tensor | None = None, sink=None):
+        """out (optional): a bool [.., E] buffer (e.g. one frame of a preallocated trajectory) for the action.
+        sink (optional): the environment's ActionSink — see GraphDistribution.sample; the result carries
+        "applied": True when the sampling kernel already wrote SELECTED_ROAD."""
         d = self.dist(obs)
         if mode:
             action = d.mode.to(torch.bool)
@@ -55,10 +57,10 @@ class PolicyModule(nn.Module):
                 action = out
             lp = d.log_prob(action).detach() if self.return_log_prob else None
         elif self.return_log_prob:
-            action, lp = d.sample(dtype=torch.bool, out=out, return_log_prob=True)
+            action, lp = d.sample(dtype=torch.bool, out=out, return_log_prob=True, sink=sink)
         else:
-            action, lp = d.sample(dtype=torch.bool, out=out), None
-        out = {"action": action}
+            action, lp = d.sample(dtype=torch.bool, out=out, sink=sink), None
+        out = {"action": action, "applied": bool(sink is not None and not mode and sink.applied)}
         if lp is not None:
             out["sample_log_prob"] = lp
         return out
@@ -175,11 +177,15 @@ class _EnvAdapter:
             o.copy_(v)
         return out
 
-    def step(self, action, out=None):
+    def action_sink(self):
+        return self.env.action_sink() if self.batched else None
+
+    def step(self, action, out=None, applied: bool = False):
         """action [R, E_full] bool. Returns (reward [R], done [R]); `out` (optional): the three buffers of dynamic()
-        for the post-step state (on the link store they are filled by the pass that computes the reward)."""
+        for the post-step state (on the link store they are filled by the pass that computes the reward).
+        applied=True: the policy step already wrote this action into SELECTED_ROAD (ActionSink)."""
         if self.batched:
-            res = self.env.step(action, compact_out=out)
+            res = self.env.step(None if applied else action, compact_out=out)
             return res["reward"], res["done"]
         res = self.env._step({"action": action[0]})
         if out is not None:
@@ -225,11 +231,12 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
     adapter.dynamic(out=(num[0], sel[0], ai[0]))
     times[0] = adapter.time()
     dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
+    sink = adapter.action_sink() if isinstance(policy_module, PolicyModule) else None
     n = 0
     for t in range(T):
         obs = adapter.observation(num[t], sel[t], ai[t], times[t], dynamic=dynamic)
-        act = policy_module(obs, mode=mode, out=action[t])
-        reward, done = adapter.step(act["action"], out=(num[t + 1], sel[t + 1], ai[t + 1]))
+        act = policy_module(obs, mode=mode, out=action[t], sink=sink)
+        reward, done = adapter.step(act["action"], out=(num[t + 1], sel[t + 1], ai[t + 1]), applied=act.get("applied", False))
         times[t + 1] = adapter.time()
         small["sample_log_prob"].append(act.get("sample_log_prob", torch.zeros(R, device=dev)))
         small["reward"].append(reward)

@@ -425,3 +425,89 @@ def test_policy_on_an_expanded_observation_and_sampling_from_one_logits_row():
     net.nodes_embedding.weight.grad = None
     (d_m.log_prob(a_m).sum() + d_m.entropy().sum()).backward()
     assert torch.allclose(gx, net.nodes_embedding.weight.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("R", [4, 36, 128, 1024])
+def test_sampling_kernel_applies_the_action_to_the_environment(R):
+    """Rollout fast path: with one logits row for all replicas, GraphDistribution.sample(sink=env.action_sink()) writes
+    SELECTED_ROAD in the pass that draws the edges. One-hot, log-probability and every SELECTED_ROAD cell must equal
+    sample() followed by env.apply_action(action); a uniform of 1.0 (no hit) leaves the node's decision untouched."""
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.distribution import GraphDistribution
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(R)
+    frm, to, n_nodes = synthetic.grid_links(7, device=dev)
+    g, Nmax = synthetic.build_graph(frm, to, n_nodes)
+    af = synthetic.population(g, 300, 21540, 60, seed=1)
+    env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=5)
+    E = g.edge_index.size(1)
+    row = torch.randn(1, E, device=dev, generator=gen) * 2
+    d = GraphDistribution(row.expand(R, -1), g.edge_index)
+    u = torch.rand(d.nb_nodes, R, device=dev, generator=gen).t()
+    u[R // 2, 3] = 1.0                                          # no hit for (replica R/2, group 3)
+    sel0 = torch.rand(R, env.N, device=dev, generator=gen).mul(50).floor()
+    src0 = torch.rand(env.src_sel.shape, device=dev, generator=gen).mul(50).floor()
+
+    def start():
+        env.store.sel[: R * env.N].view(R, env.N).copy_(sel0)
+        env.src_sel.copy_(src0)
+
+    start()
+    out_a = torch.empty(E, R, dtype=torch.bool, device=dev).t()
+    a, lp_a = d.sample(uniforms=u, dtype=torch.bool, out=out_a, return_log_prob=True)
+    env.apply_action(a)
+    sel_a, src_a = env.store.sel[: R * env.N].clone(), env.src_sel.clone()
+    start()
+    sink = env.action_sink()
+    out_b = torch.empty(E, R, dtype=torch.bool, device=dev).t()
+    b, lp_b = d.sample(uniforms=u, dtype=torch.bool, out=out_b, return_log_prob=True, sink=sink)
+    assert sink.applied
+    assert torch.equal(a, b)
+    assert torch.allclose(lp_a, lp_b, rtol=1e-5, atol=1e-4) and bool(torch.isinf(lp_a[R // 2])) and int(torch.isinf(lp_a).sum()) == 1
+    assert torch.equal(env.store.sel[: R * env.N], sel_a) and torch.equal(env.src_sel, src_a)
+    assert not torch.equal(sel_a.view(R, env.N), sel0)          # ... and the action did change the decisions
+    node = int(d.nodes[3])
+    untouched = sel0[R // 2, node] if node < env.N else src0[R // 2, node - env.N]
+    now = sel_a.view(R, env.N)[R // 2, node] if node < env.N else src_a[R // 2, node - env.N]
+    assert float(now) == float(untouched)
+    # without the log-probability, and a sink of another environment size is refused (falls back, not applied)
+    start()
+    c = d.sample(uniforms=u, dtype=torch.bool, sink=sink)
+    assert sink.applied and torch.equal(c, a) and torch.equal(env.store.sel[: R * env.N], sel_a)
+    if R > 4:
+        d4 = GraphDistribution(row.expand(4, -1), g.edge_index)
+        d4.sample(uniforms=u[:4], dtype=torch.bool, sink=sink)
+        assert not sink.applied
+
+
+def test_one_logits_row_sampling_matches_the_generic_kernel_on_long_groups():
+    """k_gd_sample_bcast keeps 8 edges of a group in shared memory; longer groups walk the logits row. Same edges as
+    the generic kernel on the materialised logits, with and without the action sink."""
+    from tarl_simulator_b200.distribution import ActionSink, GraphDistribution
+    from tarl_simulator_b200.topology import group_csr_for
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    N, E, B = 400, 2600, 64
+    ei = torch.stack([torch.randint(0, N - 30, (E,), device="cuda", generator=gen),
+                      torch.randint(0, N, (E,), device="cuda", generator=gen)])
+    ei[0, :40] = 11                                               # a 40+-edge group
+    ei[0, 40:49] = 12                                             # a 9+-edge group (one past the cache)
+    row = torch.randn(1, E, device="cuda", generator=gen) * 2
+    d_x, d_m = GraphDistribution(row.expand(B, -1), ei), GraphDistribution(row.repeat(B, 1), ei)
+    u = torch.rand(B, d_x.nb_nodes, device="cuda", generator=gen)
+    a_m = d_m.sample(uniforms=u, dtype=torch.bool)
+    a_x, lp = d_x.sample(uniforms=u, dtype=torch.bool, return_log_prob=True)
+    assert torch.equal(a_x, a_m)
+    ref = d_m.log_prob(a_m)
+    assert torch.allclose(lp, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+    n_links = 250                                                 # nodes >= 250 play the part of the SRC nodes
+    sel_l = torch.full((B, n_links), -1.0, device="cuda")
+    sel_s = torch.full((B, N - n_links), -1.0, device="cuda")
+    sink = ActionSink(ei, group_csr_for(ei, "source_rank"), sel_l, sel_s, n_links, N)
+    out = torch.empty(E, B, dtype=torch.bool, device="cuda").t()
+    a_s = d_x.sample(uniforms=u, dtype=torch.bool, out=out, sink=sink)
+    assert sink.applied and torch.equal(a_s, a_m)
+    want = torch.full((B, N), -1.0, device="cuda")
+    b_idx, e_idx = torch.nonzero(a_m, as_tuple=True)
+    want[b_idx, ei[0][e_idx]] = ei[1][e_idx].float()
+    assert torch.equal(torch.cat((sel_l, sel_s), dim=1), want)
