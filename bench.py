@@ -558,7 +558,7 @@ def ppo_bench(args, dev, world, rank):
     from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNetSimple
     from tarl_simulator_b200.parallel import shard_replicas
     from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
-    from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, collect, ppo_train
+    from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, collect, occupancy_only, ppo_train
 
     total = max(args.ppo_replicas, world)
     first, R = shard_replicas(total, world, rank)
@@ -593,8 +593,9 @@ def ppo_bench(args, dev, world, rank):
         return ms
 
     ppo_train(env, pm, vm, total_frames=2, frames_per_batch=2, num_epochs=1, sub_batch_size=32)   # warm-up: optimiser
-    collect(adapter, pm, T)                               # state, CSR builds, allocator, kernels
-    roll_ms = timed(lambda: collect(adapter, pm, T))
+    slim = occupancy_only(pm, vm)                         # what ppo_train itself passes for this pair of nets
+    collect(adapter, pm, T, occupancy_only=slim)          # state, CSR builds, allocator, kernels
+    roll_ms = timed(lambda: collect(adapter, pm, T, occupancy_only=slim))
     hist = []
     train_ms = timed(lambda: ppo_train(env, pm, vm, total_frames=T, frames_per_batch=T, num_epochs=1, sub_batch_size=32,
                                        history=hist))

@@ -30,6 +30,10 @@ for _ in range(iters):
     (-(lp * adv).mean() - 0.01 * ent.mean()).backward()
     for p_ in value.parameters(): p_.grad = None
     (value(nf, ef, ai, tm) * wv).sum().backward()
+    value.train(); value.time_net[1].p = 0.0; value.time_net[4].p = 0.0          # message dropout kernels
+    for p_ in value.parameters(): p_.grad = None
+    (value(nf, ef, ai, tm) * wv).sum().backward()
+    value.eval()
     with torch.no_grad():
         vs.forward_occupancy(occ, tv)
         d1 = GraphDistribution(policy(nf, None, None), ei)

@@ -15,12 +15,12 @@ env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=100)
 policy = MPNNPolicyNet(g.edge_index, g.x.size(0), None, "cuda")
 pm = PolicyModule(policy, g.edge_index)
 ad = _EnvAdapter(env)
-collect(ad, pm, 8); collect(ad, pm, 8)
+collect(ad, pm, 8, occupancy_only=True); collect(ad, pm, 8, occupancy_only=True)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); collect(ad, pm, 8); e1.record(); torch.cuda.synchronize()
+e0.record(); collect(ad, pm, 8, occupancy_only=True); e1.record(); torch.cuda.synchronize()
 print("collect(8): %.2f ms" % e0.elapsed_time(e1))
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
-    collect(ad, pm, 8)
+    collect(ad, pm, 8, occupancy_only=True)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))

@@ -729,7 +729,7 @@ constexpr int kBcGroups = 32;         // groups per tile
 constexpr int kBcDeg = 8;             // edges per group kept in shared memory; longer groups take the slow walk
 constexpr int kBcRows = 1024;         // batch rows per grid.y slice (4 per thread)
 constexpr int kBcPitch = kBcRows + 4; // bytes: lane stride of 257 words -> phase 2 reads are bank-conflict-free
-constexpr uint8_t kBcNoHit = 0xff, kBcBig = 0xfe;
+constexpr uint8_t kBcBig = 0xfe;  // hit byte of a long group (applied directly); 0xff = no hit; < kBcDeg = position
 
 struct BcApply {
     const int32_t* group_node;   // [K] source node of each group
@@ -739,7 +739,7 @@ struct BcApply {
     int n_links, n_nodes;
 };
 
-__global__ void __launch_bounds__(kThreads) k_gd_sample_bcast(tarl_csr grp, const float* __restrict__ lg, float inv_t, int B,
+__global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, const float* __restrict__ lg, float inv_t, int B,
                                                               int n_tiles, const float* __restrict__ u, int64_t u_sb,
                                                               int64_t u_sg, uint8_t* __restrict__ onehot,
                                                               float* __restrict__ part_lp, int32_t* __restrict__ part_bad,
@@ -799,12 +799,19 @@ __global__ void __launch_bounds__(kThreads) k_gd_sample_bcast(tarl_csr grp, cons
         }
         __syncthreads();
         // ---- phase 1: one uniform per (group, row) -> hit position, one-hot bytes, log-probability of the draw
+        // the uniforms of the NEXT group are requested before this group's compares and stores (one load in flight
+        // per thread would otherwise be all the memory parallelism this phase has)
+        float4 u_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (u_vec && rows_live && g0 + gsub < grp.n_rows)
+            u_nxt = *reinterpret_cast<const float4*>(u + (int64_t)(g0 + gsub) * u_sg + row0);
         for (int gl = gsub; gl < kBcGroups; gl += gpar) {
             const int g = g0 + gl, deg = sm_deg[gl];
+            const float4 t4 = u_nxt;
+            if (u_vec && rows_live && gl + gpar < kBcGroups && g + gpar < grp.n_rows)
+                u_nxt = *reinterpret_cast<const float4*>(u + (int64_t)(g + gpar) * u_sg + row0);
             if (!rows_live || g >= grp.n_rows || deg == 0) continue;
             float ug[4];
             if (u_vec) {
-                const float4 t4 = *reinterpret_cast<const float4*>(u + (int64_t)g * u_sg + row0);
                 ug[0] = t4.x; ug[1] = t4.y; ug[2] = t4.z; ug[3] = t4.w;
             } else {
 #pragma unroll

@@ -305,15 +305,16 @@ class BatchedSimulatorEnv:
     def observe(self, node_features: bool = True, agent_index: bool = True, compact_out=None):
         """One pass over the link store: occupancy (always), and on request node_features [R, N_tot, 7], agent_index
         [R, N_tot], and/or the compact observation written into compact_out = (NUM [R, N_tot] fp32, SELECTED_ROAD
-        [R, N_tot] fp32, head agent id [R, N_tot] int64) — contiguous buffers, e.g. a frame of a trajectory."""
+        [R, N_tot] fp32, head agent id [R, N_tot] int64) — contiguous buffers, e.g. a frame of a trajectory; the second
+        and third may be None (a rollout whose nets read the occupancy only keeps 4 of the 16 bytes per node)."""
         st = self._state()
         nf = torch.empty(self.R, self.n_nodes, 7, dtype=torch.float32, device=self.device) if node_features else None
         ai = torch.empty(self.R, self.n_nodes, dtype=torch.int64, device=self.device) if agent_index else None
-        num = sel = None
+        num = sel = head = None
         if compact_out is not None:
             num, sel, head = compact_out
             for t_, dt in ((num, torch.float32), (sel, torch.float32), (head, torch.int64)):
-                if t_.dtype != dt or t_.shape != (self.R, self.n_nodes) or not t_.is_contiguous():
+                if t_ is not None and (t_.dtype != dt or t_.shape != (self.R, self.n_nodes) or not t_.is_contiguous()):
                     raise ValueError("compact_out must be contiguous (fp32, fp32, int64) [R, N_tot] buffers")
             if ai is None:
                 ai = head
@@ -323,8 +324,8 @@ class BatchedSimulatorEnv:
                                                 num.data_ptr() if num is not None else None,
                                                 sel.data_ptr() if sel is not None else None, _stream(self.device))
         _cabi.check(rc, "tarl_store_observe")
-        if compact_out is not None and ai is not compact_out[2]:
-            compact_out[2].copy_(ai)
+        if head is not None and ai is not head:
+            head.copy_(ai)
         return nf, (ai if agent_index else None)
 
     def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False,
@@ -360,7 +361,7 @@ class BatchedSimulatorEnv:
             out = (torch.empty(R, M, dtype=torch.float32, device=self.device),
                    torch.empty(R, M, dtype=torch.float32, device=self.device),
                    torch.empty(R, M, dtype=torch.int64, device=self.device))
-        if all(t_.is_contiguous() for t_ in out):
+        if all(t_ is None or t_.is_contiguous() for t_ in out) and out[0] is not None:
             self.observe(node_features=False, agent_index=False, compact_out=out)
             return out
         num, sel, head = out

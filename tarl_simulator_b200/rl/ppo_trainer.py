@@ -202,41 +202,54 @@ class _EnvAdapter:
         else:
             nf = self.static.unsqueeze(0).repeat(B, 1, 1)
             nf[..., OBS.NUMBER_OF_AGENT] = num
-            nf[..., OBS.SELECTED_ROAD] = sel
+            if sel is not None:           # None: an occupancy-only trajectory (its consumers do not read this column)
+                nf[..., OBS.SELECTED_ROAD] = sel
         return {"node_features": nf, "edge_features": self.edge_features.unsqueeze(0).expand(B, -1, -1),
                 "agent_index": agent_index, "time": time.reshape(B, 1).to(torch.float32)}
 
 
 @torch.no_grad()
+def occupancy_only(policy_module, value_module) -> bool:
+    """True when neither net reads anything of the dynamic observation but NUMBER_OF_AGENT: the policy's active path
+    embeds the static ROAD_INDEX (`reads_dynamic_features = False`) and the value net offers `forward_occupancy`
+    (MPNNValueNetSimple, the pair src/runner.py wires). A rollout for them keeps the occupancy frames only."""
+    return (not getattr(policy_module.net, "reads_dynamic_features", True)
+            and value_module is not None and hasattr(value_module.net, "forward_occupancy"))
+
+
 def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode: bool = False,
-            break_when_any_done: bool = False):
+            break_when_any_done: bool = False, occupancy_only: bool = False):
     """`frames` steps of every replica after a reset. Returns a dict of [T, R, ...] tensors (compact observations:
     NUM, SELECTED_ROAD and head ids per node; the static columns are re-attached when a minibatch is formed).
     The trajectory is written in place into preallocated [T+1, R, ..] buffers — frame t+1 of a step is the next
     step's frame t, so `next_*` are views shifted by one — and the one-hot actions go straight from the sampling
-    kernel into their frame (edge-major inside a frame: [T, R, E] with the replica innermost)."""
+    kernel into their frame (edge-major inside a frame: [T, R, E] with the replica innermost).
+    occupancy_only=True (see occupancy_only()): SELECTED_ROAD and head-id frames are neither written nor kept
+    ("sel" / "agent_index" are None in the result) — 4 instead of 16 bytes per node and frame."""
     adapter.reset()
     R, M, dev = adapter.R, adapter.n_nodes, adapter.device
     E = adapter.graph.edge_index.size(1)
     T = int(frames)
     num = torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
-    sel = torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
-    ai = torch.empty(T + 1, R, M, dtype=torch.int64, device=dev)
+    slim = bool(occupancy_only) and adapter.batched
+    sel = None if slim else torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
+    ai = None if slim else torch.empty(T + 1, R, M, dtype=torch.int64, device=dev)
+    frame = (lambda t: (num[t], None, None)) if slim else (lambda t: (num[t], sel[t], ai[t]))
     times = torch.empty(T + 1, R, dtype=torch.float32, device=dev)
     if R > 1:
         action = torch.empty(T, E, R, dtype=torch.bool, device=dev).permute(0, 2, 1)
     else:
         action = torch.empty(T, R, E, dtype=torch.bool, device=dev)
     small = {k: [] for k in ("sample_log_prob", "reward", "done")}
-    adapter.dynamic(out=(num[0], sel[0], ai[0]))
+    adapter.dynamic(out=frame(0))
     times[0] = adapter.time()
     dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
     sink = adapter.action_sink() if isinstance(policy_module, PolicyModule) else None
     n = 0
     for t in range(T):
-        obs = adapter.observation(num[t], sel[t], ai[t], times[t], dynamic=dynamic)
+        obs = adapter.observation(*frame(t), times[t], dynamic=dynamic)
         act = policy_module(obs, mode=mode, out=action[t], sink=sink)
-        reward, done = adapter.step(act["action"], out=(num[t + 1], sel[t + 1], ai[t + 1]), applied=act.get("applied", False))
+        reward, done = adapter.step(act["action"], out=frame(t + 1), applied=act.get("applied", False))
         times[t + 1] = adapter.time()
         small["sample_log_prob"].append(act.get("sample_log_prob", torch.zeros(R, device=dev)))
         small["reward"].append(reward)
@@ -244,8 +257,10 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
         n = t + 1
         if break_when_any_done and bool(done.any()):
             break
-    out = {"num": num[:n], "sel": sel[:n], "agent_index": ai[:n], "time": times[:n], "action": action[:n],
-           "next_num": num[1:n + 1], "next_sel": sel[1:n + 1], "next_agent_index": ai[1:n + 1], "next_time": times[1:n + 1]}
+    cut = lambda x, a, b: None if x is None else x[a:b]
+    out = {"num": num[:n], "sel": cut(sel, 0, n), "agent_index": cut(ai, 0, n), "time": times[:n], "action": action[:n],
+           "next_num": num[1:n + 1], "next_sel": cut(sel, 1, n + 1), "next_agent_index": cut(ai, 1, n + 1),
+           "next_time": times[1:n + 1]}
     out.update({k: torch.stack(v) for k, v in small.items()})
     return out
 
@@ -296,7 +311,7 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
     n_iters = max(total_frames // frames_per_batch, 1)
     for it in range(n_iters):
         t0 = time.perf_counter()
-        batch = collect(adapter, policy_module, frames_per_batch)
+        batch = collect(adapter, policy_module, frames_per_batch, occupancy_only=occupancy_only(policy_module, value_module))
         T, R = batch["reward"].shape
         global_step += frames_per_batch
         rollout_s = time.perf_counter() - t0
@@ -309,7 +324,7 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
             n = min(sub_batch_size, T * R)
             pick = torch.randperm(T * R, generator=gen)[:n].to(adapter.device)
             ti, ri = pick // R, pick % R
-            flat = lambda x: x[ti, ri]                    # gathers n frames whatever the strides of the trajectory
+            flat = lambda x: None if x is None else x[ti, ri]     # gathers n frames whatever the strides of the trajectory
             obs = adapter.observation(flat(batch["num"]), flat(batch["sel"]), flat(batch["agent_index"]), flat(batch["time"]))
             d = policy_module.dist(obs)
             log_prob = d.log_prob(flat(batch["action"]))

@@ -65,3 +65,37 @@ def test_ppo_on_batched_env_updates_parameters(scenario):
     assert not torch.equal(before, policy.nodes_embedding.weight.detach())
     assert int(env.counters[:, 0].min()) > 0                   # every replica inserted agents
     env.check_errors()
+
+
+def test_occupancy_only_rollout_equals_the_full_rollout(scenario):
+    """collect(occupancy_only=True) — the trajectory of nets that read NUMBER_OF_AGENT only — must hold the same
+    occupancies, actions, log-probabilities and rewards as the full trajectory; the sampling kernel applies the action
+    in both (action sink), and stepping with env.step(action) instead gives the same episode."""
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNetSimple
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, collect, occupancy_only
+    from tarl_simulator_b200.transportation_simulator import TransportationSimulator
+    sim = TransportationSimulator("cuda")
+    sim.load_network(scenario)
+    sim.agent.load(scenario)
+    g = sim.graph
+    torch.manual_seed(5)
+    policy = MPNNPolicyNet(g.edge_index, g.x.size(0), torch.ones(g.edge_index.size(1)), "cuda")
+    pm = PolicyModule(policy, g.edge_index)
+    assert occupancy_only(pm, ValueModule(MPNNValueNetSimple(g.edge_index, g.x.size(0), "cuda")))
+    runs = []
+    for slim, use_sink in ((False, True), (True, True), (False, False)):
+        env = BatchedSimulatorEnv(g, sim.Nmax, sim.agent.agent_features, replicas=8, seed=3)
+        ad = _EnvAdapter(env)
+        if not use_sink:
+            ad.action_sink = lambda: None
+        torch.manual_seed(11)
+        runs.append(collect(ad, pm, 25, occupancy_only=slim))
+        env.check_errors()
+    full, slim, plain = runs
+    assert slim["sel"] is None and slim["agent_index"] is None and full["sel"] is not None
+    for k in ("num", "next_num", "action", "sample_log_prob", "reward", "done", "time"):
+        assert torch.equal(full[k], slim[k]), k
+        assert torch.equal(full[k], plain[k]), k
+    assert torch.equal(full["sel"], plain["sel"]) and torch.equal(full["agent_index"], plain["agent_index"])
+    assert float(full["num"].sum()) > 0
