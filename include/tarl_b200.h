@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 12
+#define TARL_ABI_VERSION 13
 
 /* return codes */
 #define TARL_OK 0
@@ -386,10 +386,13 @@ typedef struct tarl_agent_index {
  * next [R*n_origins], cursor [R*n_origins]. counters: NULL or [R*2] {inserted, withdrawn} running totals.
  * inserted: NULL, or [R*n_origins] agents inserted so far per (replica, origin) — maintained here, zeroed by the caller
  * whenever it resets ON_WAY / DONE, valid only while nothing else edits those columns; with index->dep_sorted it lets
- * origins without a waiting agent be skipped without touching agent_features (identical results). */
+ * origins without a waiting agent be skipped without touching agent_features (identical results).
+ * worklist / work_count: both NULL, or scratch [R*n_origins] / [R]: the origins that queue for a road this step are
+ * compacted per replica and the admission runs over that list only (identical results; the listed origins are a few
+ * per cent of all (replica, origin) pairs and each carries a chain of dependent gathers). */
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
-                       int32_t* flags, void* stream);
+                       int32_t* flags, int32_t* worklist, int32_t* work_count, void* stream);
 
 /* Replaces Agents.withdraw_agent_from_network (src/agents/base.py:334-403): per link the maximal prefix of queue
  * slots k < NUM whose exit time <= t and whose agent's DESTINATION node is adjacent to the link — adjacency = CSR of

@@ -208,7 +208,7 @@ class Agents(AgentFeatureHelpers):
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(tab), idx.ref(), float(self.time),
                                                 head.data_ptr(), nxt.data_ptr(), cur.data_ptr(), None, None,
-                                                flags.data_ptr(), _stream(dev))
+                                                flags.data_ptr(), None, None, _stream(dev))
         _cabi.check(rc, "tarl_agents_insert")
         return graph.x
 

@@ -153,14 +153,12 @@ __device__ __forceinline__ bool agent_ready(const AgentTable& at, int r, int a, 
     return p[kDepartureTime] <= t && p[kOnWay] == 0.0f && p[kDone] == 0.0f;     // base.py:247-251
 }
 
+// What one (replica, origin) pair does in the offer phase; returns true when the origin was pushed onto a road's list.
 template <class Acc>
-__global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_index ai, AgentTable at, float t,
-                                                           int32_t* __restrict__ head, int32_t* __restrict__ next,
-                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
-                                                           const int32_t* __restrict__ inserted) {
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= ai.n_origins) return;
-    const int r = blockIdx.y;
+__device__ __forceinline__ bool insert_offer_one(const Acc& acc, const tarl_agent_index& ai, const AgentTable& at, float t,
+                                                 int32_t* __restrict__ head, int32_t* __restrict__ next,
+                                                 int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
+                                                 const int32_t* __restrict__ inserted, int r, int i) {
     const int o = ai.origins[i];
     const size_t ri = (size_t)r * ai.n_origins + i;
     if (inserted != nullptr && ai.dep_sorted != nullptr) {
@@ -173,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
             const int mid = (lo + hi) >> 1;
             if (ai.dep_sorted[mid] <= t) lo = mid + 1; else hi = mid;
         }
-        if (lo - k0 <= inserted[ri]) { next[ri] = -2; return; }
+        if (lo - k0 <= inserted[ri]) { next[ri] = -2; return false; }
     }
     const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
     cursor[ri] = ai.org_ptr[o];
@@ -182,21 +180,53 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
         for (int k = ai.org_ptr[o]; k < ai.org_ptr[o + 1] && !any; ++k) any = agent_ready(at, r, ai.org_agent[k], t);
         if (any) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_INSERT_TARGET);
         next[ri] = -2;
-        return;
+        return false;
     }
     next[ri] = atomicExch(&head[(size_t)r * acc.N + road], i);
+    return true;
+}
+
+// worklist (optional): the listed origins of replica r are appended to work[r*n_origins + ..], their number kept in
+// work_count[r] (zeroed by the launcher) — in steady state ~2 % of the origins are listed, spread one or two per warp,
+// and the admit phase (a chain of dependent gathers per listed origin) runs over the compact list instead of over
+// every (replica, origin) pair. One atomic per warp that lists anything (a counter per replica); the order inside the list is arbitrary and does not matter (each
+// road is served by the one origin at the head of its list, merging by agent id).
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_index ai, AgentTable at, float t,
+                                                           int32_t* __restrict__ head, int32_t* __restrict__ next,
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
+                                                           const int32_t* __restrict__ inserted,
+                                                           int32_t* __restrict__ work, int32_t* __restrict__ work_count) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    bool listed = false;
+    if (i < ai.n_origins) listed = insert_offer_one(acc, ai, at, t, head, next, cursor, flags, inserted, r, i);
+    if (work == nullptr) return;
+    const unsigned m = __ballot_sync(0xffffffffu, listed);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&work_count[r], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (listed) work[(size_t)r * ai.n_origins + base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
 template <class Acc>
 __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_index ai, AgentTable at, float t,
                                                            int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
-                                                           int32_t* __restrict__ inserted) {
-    // One thread per (replica, origin): the origin that ended up at the HEAD of its road's list serves the road. (A
-    // thread per road would launch N threads per replica to find the few roads with a list.)
-    const int i0 = blockIdx.x * kThreads + threadIdx.x;
-    if (i0 >= ai.n_origins) return;
+                                                           int32_t* __restrict__ inserted, const int32_t* __restrict__ work,
+                                                           const int32_t* __restrict__ work_count) {
+    // One thread per (replica, origin) — or, with a worklist, per LISTED origin: the origin that ended up at the HEAD of
+    // its road's list serves the road. (A thread per road would launch N threads per replica to find the few roads
+    // with a list.)
+    int i0 = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
+    if (work != nullptr) {
+        if (i0 >= work_count[r]) return;
+        i0 = work[(size_t)r * ai.n_origins + i0];
+    }
+    if (i0 >= ai.n_origins) return;
     if (next[(size_t)r * ai.n_origins + i0] == -2) return;                        // not listed this step
     const long long road = (long long)acc.sel_of(r, ai.origins[i0]);
     if (road < 0 || road >= acc.N) return;
@@ -445,7 +475,7 @@ extern "C" {
 
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
-                       int32_t* flags, void* stream) {
+                       int32_t* flags, int32_t* worklist, int32_t* work_count, void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -456,12 +486,14 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if (!index->org_ptr || !index->org_agent || !index->origins || !head || !next || !cursor) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const dim3 g1(blocks_for(index->n_origins), R), g2 = g1;
+    if ((worklist != nullptr) != (work_count != nullptr)) return TARL_E_BADARG;
+    if (worklist != nullptr && cudaMemsetAsync(work_count, 0, sizeof(int32_t) * R, cs) != cudaSuccess) return TARL_E_LAUNCH;
     if (is_store) {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count);
     } else {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count);
     }
     return launch_status();
 }

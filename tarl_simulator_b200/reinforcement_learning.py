@@ -198,6 +198,8 @@ class BatchedSimulatorEnv:
         self._next = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
         self._cursor = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
         self._inserted = torch.zeros(max(self.R * self.index.n_origins, 1), **i32)   # per (replica, origin), see insert()
+        self._work = torch.empty(max(self.R * self.index.n_origins, 1), **i32)       # listed origins of a step, compacted
+        self._work_count = torch.zeros(self.R, **i32)
         self.counters = torch.zeros(self.R, 2, **i32)          # running totals {inserted, withdrawn} per replica
         self.occupancy = torch.zeros(self.R, **i32)
         self.withdrawn = torch.zeros(self.R, self.N, dtype=torch.bool, device=dev)
@@ -299,7 +301,8 @@ class BatchedSimulatorEnv:
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(self._table), self.index.ref(), self.time,
                                                 self._head.data_ptr(), self._next.data_ptr(), self._cursor.data_ptr(),
                                                 self.counters.data_ptr(), self._inserted.data_ptr(),
-                                                self.store.flags.data_ptr(), _stream(self.device))
+                                                self.store.flags.data_ptr(), self._work.data_ptr(),
+                                                self._work_count.data_ptr(), _stream(self.device))
         _cabi.check(rc, "tarl_agents_insert")
 
     def observe(self, node_features: bool = True, agent_index: bool = True, compact_out=None):
