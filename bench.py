@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--no-mpnn", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
     ap.add_argument("--ppo-replicas", type=int, default=1024, help="environment replicas in total (sharded over ranks)")
-    ap.add_argument("--ppo-steps", type=int, default=8, help="rollout steps per PPO iteration in the ppo section")
+    ap.add_argument("--ppo-steps", type=int, default=32, help="rollout steps per PPO iteration in the ppo section")
     ap.add_argument("--mpnn-batch", type=int, default=32, help="batch rows (frames) of the MPNN fwd+bwd measurement")
     ap.add_argument("--replicas", type=int, default=1, help="independent network replicas stepped per GPU")
     ap.add_argument("--link-order", default="node", choices=["node", "direction", "shuffled"])

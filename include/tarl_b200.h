@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 13
+#define TARL_ABI_VERSION 14
 
 /* return codes */
 #define TARL_OK 0
@@ -389,18 +389,26 @@ typedef struct tarl_agent_index {
  * origins without a waiting agent be skipped without touching agent_features (identical results).
  * worklist / work_count: both NULL, or scratch [R*n_origins] / [R]: the origins that queue for a road this step are
  * compacted per replica and the admission runs over that list only (identical results; the listed origins are a few
- * per cent of all (replica, origin) pairs and each carries a chain of dependent gathers). */
+ * per cent of all (replica, origin) pairs and each carries a chain of dependent gathers).
+ * num_out / occupancy: both NULL, or (link store only) the occupancy observation tarl_agents_withdraw left behind in
+ * this very step — num_out [R, n_nodes], occupancy [R] — which the roads that admit agents patch in place. */
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
-                       int32_t* flags, int32_t* worklist, int32_t* work_count, void* stream);
+                       int32_t* flags, int32_t* worklist, int32_t* work_count, float* num_out, int32_t* occupancy,
+                       void* stream);
 
 /* Replaces Agents.withdraw_agent_from_network (src/agents/base.py:334-403): per link the maximal prefix of queue
  * slots k < NUM whose exit time <= t and whose agent's DESTINATION node is adjacent to the link — adjacency = CSR of
  * the FULL edge_index by source node (idx = targets), the sparse form of adj_matrix[ROAD_INDEX, DESTINATION] — is
  * removed; the three queue segments shift left by that count with zero fill; the agents get DONE = 1, ON_WAY = 0,
- * ARRIVAL_TIME = t. mask: NULL or [R*N] (the entry of withdraw_history). */
+ * ARRIVAL_TIME = t. mask: NULL or [R*N] (the entry of withdraw_history).
+ * num_out / occupancy: both NULL, or (link store only) num_out [R, n_nodes] fp32 receives NUMBER_OF_AGENT of every node
+ * after the withdrawal (0 for the non-road nodes) and occupancy [R] their sum — the observation / reward of
+ * SimulatorEnv._step (src/reinforcement_learning.py:266) for nets that read the occupancy only, produced by the pass
+ * that already holds every record; pass the same two pointers to the tarl_agents_insert call that follows. */
 int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_csr* adjacency,
-                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, void* stream);
+                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, float* num_out, int32_t* occupancy,
+                         void* stream);
 
 /* Replaces Agents.choice (src/agents/base.py:446-494): every node listed in choosers (roads with a downstream road,
  * SRC nodes with an outgoing road) draws one of its neighbours[node] (ascending road id) uniformly into

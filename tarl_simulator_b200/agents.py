@@ -208,7 +208,7 @@ class Agents(AgentFeatureHelpers):
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(tab), idx.ref(), float(self.time),
                                                 head.data_ptr(), nxt.data_ptr(), cur.data_ptr(), None, None,
-                                                flags.data_ptr(), None, None, _stream(dev))
+                                                flags.data_ptr(), None, None, None, None, _stream(dev))
         _cabi.check(rc, "tarl_agents_insert")
         return graph.x
 
@@ -222,7 +222,7 @@ class Agents(AgentFeatureHelpers):
         flags = self._flag_words(dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_withdraw(C.byref(st), C.byref(tab), C.byref(side.adj),
-                                                  float(self.time), mask.data_ptr(), None, flags.data_ptr(),
+                                                  float(self.time), mask.data_ptr(), None, flags.data_ptr(), None, None,
                                                   _stream(dev))
         _cabi.check(rc, "tarl_agents_withdraw")
         self.last_withdrawn = mask if graph.x.dim() == 2 else mask.view(R, N)

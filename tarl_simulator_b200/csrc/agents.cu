@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
                                                            int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
                                                            int32_t* __restrict__ inserted, const int32_t* __restrict__ work,
-                                                           const int32_t* __restrict__ work_count) {
+                                                           const int32_t* __restrict__ work_count,
+                                                           float* __restrict__ num_out, int32_t* __restrict__ occupancy,
+                                                           int n_nodes) {
     // One thread per (replica, origin) — or, with a worklist, per LISTED origin: the origin that ended up at the HEAD of
     // its road's list serves the road. (A thread per road would launch N threads per replica to find the few roads
     // with a list.)
@@ -265,6 +267,10 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
     if (admitted > 0) {
         Acc::commit_insert(l, admitted);                                         // :327
         if (counters != nullptr) atomicAdd(&counters[2 * r], admitted);
+        if (num_out != nullptr) {               // occupancy observation left behind by k_withdraw_observe: patch it
+            num_out[(size_t)r * n_nodes + n] = l.num + (float)admitted;
+            atomicAdd(&occupancy[r], admitted);
+        }
     }
 }
 
@@ -280,13 +286,11 @@ __device__ __forceinline__ bool adjacent(const tarl_csr& adj, long long row, lon
     return false;
 }
 
+// one link of one replica; returns its NUM after the withdrawal
 template <class Acc>
-__global__ void __launch_bounds__(kThreads) k_withdraw(Acc acc, AgentTable at, tarl_csr adj, float t,
-                                                       uint8_t* __restrict__ mask, int32_t* __restrict__ counters,
-                                                       int32_t* __restrict__ flags) {
-    const int n = blockIdx.x * kThreads + threadIdx.x;
-    if (n >= acc.N) return;
-    const int r = blockIdx.y;
+__device__ __forceinline__ float withdraw_one(const Acc& acc, const AgentTable& at, const tarl_csr& adj, float t,
+                                              uint8_t* __restrict__ mask, int32_t* __restrict__ counters,
+                                              int32_t* __restrict__ flags, int r, int n) {
     typename Acc::Link l = acc.open(r, n);
     int c = 0;
     long long ridx = -1;
@@ -299,13 +303,44 @@ __global__ void __launch_bounds__(kThreads) k_withdraw(Acc acc, AgentTable at, t
         ++c;
     }
     if (mask != nullptr) mask[(size_t)r * acc.N + n] = c > 0 ? 1 : 0;
-    if (c == 0) return;
+    if (c == 0) return l.num;
     for (int k = 0; k < c; ++k) {                                                // :398-400
         float* p = at.row(r, (long long)Acc::slot_id(l, k));
         p[kDone] = 1.0f; p[kOnWay] = 0.0f; p[kArrivalTime] = t;
     }
     Acc::withdraw(l, c);
     if (counters != nullptr) atomicAdd(&counters[2 * r + 1], c);
+    return l.num - (float)c;
+}
+
+
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_withdraw(Acc acc, AgentTable at, tarl_csr adj, float t,
+                                                       uint8_t* __restrict__ mask, int32_t* __restrict__ counters,
+                                                       int32_t* __restrict__ flags) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    if (n >= acc.N) return;
+    const int r = blockIdx.y;
+    withdraw_one(acc, at, adj, t, mask, counters, flags, r, n);
+}
+
+// The same pass also leaving the occupancy observation behind (rollouts whose nets read NUMBER_OF_AGENT only): this
+// kernel has every link's record in registers anyway, so it writes num_out[r, n] = NUM after the withdrawal (0 for the
+// non-road nodes: the grid covers n_nodes) and adds the NUMs into occupancy[r] (integer atomics, one per warp); the
+// insertion that follows patches the few roads it touches (k_insert_admit). A separate observe pass would read all the
+// records once more.
+__global__ void __launch_bounds__(kThreads) k_withdraw_observe(StoreAcc acc, AgentTable at, tarl_csr adj, float t,
+                                                               uint8_t* __restrict__ mask, int32_t* __restrict__ counters,
+                                                               int32_t* __restrict__ flags, float* __restrict__ num_out,
+                                                               int32_t* __restrict__ occupancy) {
+    const int n = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    float num = 0.0f;
+    if (n < acc.N) num = withdraw_one(acc, at, adj, t, mask, counters, flags, r, n);
+    if (n < acc.n_nodes) num_out[(size_t)r * acc.n_nodes + n] = num;
+    int num_i = (int)num;
+    for (int off = 16; off > 0; off >>= 1) num_i += __shfl_xor_sync(0xffffffffu, num_i, off);
+    if ((threadIdx.x & 31) == 0 && num_i != 0) atomicAdd(&occupancy[r], num_i);
 }
 
 // ------------------------------------------------------------------------------------------------------------ choice
@@ -475,7 +510,8 @@ extern "C" {
 
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
-                       int32_t* flags, int32_t* worklist, int32_t* work_count, void* stream) {
+                       int32_t* flags, int32_t* worklist, int32_t* work_count, float* num_out, int32_t* occupancy,
+                       void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -487,19 +523,23 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const dim3 g1(blocks_for(index->n_origins), R), g2 = g1;
     if ((worklist != nullptr) != (work_count != nullptr)) return TARL_E_BADARG;
+    if ((num_out != nullptr) != (occupancy != nullptr) || (num_out != nullptr && !is_store)) return TARL_E_BADARG;
     if (worklist != nullptr && cudaMemsetAsync(work_count, 0, sizeof(int32_t) * R, cs) != cudaSuccess) return TARL_E_LAUNCH;
     if (is_store) {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
+                                                num_out, occupancy, sto.n_nodes);
     } else {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
-        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count);
+        k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
+                                                nullptr, nullptr, 0);
     }
     return launch_status();
 }
 
 int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_csr* adjacency,
-                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, void* stream) {
+                         float t, uint8_t* mask, int32_t* counters, int32_t* flags, float* num_out, int32_t* occupancy,
+                         void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -510,6 +550,13 @@ int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* 
     if (adjacency->n_rows > 0 && (!adjacency->ptr || (adjacency->n_edges > 0 && !adjacency->idx))) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     const dim3 grid(blocks_for(N), R);
+    if ((num_out != nullptr) != (occupancy != nullptr) || (num_out != nullptr && !is_store)) return TARL_E_BADARG;
+    if (num_out != nullptr) {
+        if (cudaMemsetAsync(occupancy, 0, sizeof(int32_t) * (size_t)R, cs) != cudaSuccess) return TARL_E_LAUNCH;
+        const dim3 grid_nodes(blocks_for(sto.n_nodes), R);
+        k_withdraw_observe<<<grid_nodes, kThreads, 0, cs>>>(sto, at, *adjacency, t, mask, counters, flags, num_out, occupancy);
+        return launch_status();
+    }
     if (is_store) k_withdraw<<<grid, kThreads, 0, cs>>>(sto, at, *adjacency, t, mask, counters, flags);
     else k_withdraw<<<grid, kThreads, 0, cs>>>(row, at, *adjacency, t, mask, counters, flags);
     return launch_status();

@@ -287,22 +287,30 @@ class BatchedSimulatorEnv:
                                                 self.side.n_choosers, up, seed, self.store.step_id, _stream(self.device))
         _cabi.check(rc, "tarl_agents_choice")
 
-    def withdraw(self):
+    def withdraw(self, num_out: torch.Tensor | None = None):
+        """num_out (optional, contiguous fp32 [R, N_tot]): also leave NUMBER_OF_AGENT of every node after the
+        withdrawal there and their sum in self.occupancy — pass the same buffer to the insert() that follows."""
         st = self._state()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_agents_withdraw(C.byref(st), C.byref(self._table), C.byref(self.side.adj), self.time,
                                                   self.withdrawn.data_ptr(), self.counters.data_ptr(),
-                                                  self.store.flags.data_ptr(), _stream(self.device))
+                                                  self.store.flags.data_ptr(),
+                                                  num_out.data_ptr() if num_out is not None else None,
+                                                  self.occupancy.data_ptr() if num_out is not None else None,
+                                                  _stream(self.device))
         _cabi.check(rc, "tarl_agents_withdraw")
 
-    def insert(self):
+    def insert(self, num_out: torch.Tensor | None = None):
         st = self._state()
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(self._table), self.index.ref(), self.time,
                                                 self._head.data_ptr(), self._next.data_ptr(), self._cursor.data_ptr(),
                                                 self.counters.data_ptr(), self._inserted.data_ptr(),
                                                 self.store.flags.data_ptr(), self._work.data_ptr(),
-                                                self._work_count.data_ptr(), _stream(self.device))
+                                                self._work_count.data_ptr(),
+                                                num_out.data_ptr() if num_out is not None else None,
+                                                self.occupancy.data_ptr() if num_out is not None else None,
+                                                _stream(self.device))
         _cabi.check(rc, "tarl_agents_insert")
 
     def observe(self, node_features: bool = True, agent_index: bool = True, compact_out=None):
@@ -338,12 +346,19 @@ class BatchedSimulatorEnv:
         if action is not None:
             self.apply_action(action)
         self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
-        self.withdraw()
-        self.insert()
+        # occupancy-only observation (compact_out = (NUM frame, None, None)): withdraw holds every record anyway and
+        # leaves NUM + the reward behind, insert patches the roads it touches — no separate observe pass
+        fused = (not observe and compact_out is not None and compact_out[1] is None and compact_out[2] is None
+                 and compact_out[0].dtype == torch.float32 and compact_out[0].shape == (self.R, self.n_nodes)
+                 and compact_out[0].is_contiguous())
+        self.withdraw(num_out=compact_out[0] if fused else None)
+        self.insert(num_out=compact_out[0] if fused else None)
         if self.metrics is not None:
             self.metrics.record(self.time, pop=self.store.pop[: self.R * self.N], withdrawn=self.withdrawn,
                                 delta_tt=self.delta_tt if self.metrics.optimality_now is not None else None)
-        nf, ai = self.observe(node_features=observe, agent_index=observe, compact_out=compact_out)
+        nf = ai = None
+        if not fused:
+            nf, ai = self.observe(node_features=observe, agent_index=observe, compact_out=compact_out)
         self.time += self.timestep
         out = {"reward": -self.occupancy.to(torch.float32), "occupancy": self.occupancy,
                "done": torch.full((self.R,), self.time > EPISODE_END, dtype=torch.bool, device=self.device),

@@ -261,6 +261,9 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
     out = {"num": num[:n], "sel": cut(sel, 0, n), "agent_index": cut(ai, 0, n), "time": times[:n], "action": action[:n],
            "next_num": num[1:n + 1], "next_sel": cut(sel, 1, n + 1), "next_agent_index": cut(ai, 1, n + 1),
            "next_time": times[1:n + 1]}
+    # frame t+1 IS the next observation of step t (no reset inside a rollout): consumers that evaluate something on
+    # every observation (the value net in GAE) can do it once over the n+1 frames instead of on both shifted views
+    out["_frames"] = {"num": num[:n + 1], "sel": cut(sel, 0, n + 1), "agent_index": cut(ai, 0, n + 1), "time": times[:n + 1]}
     out.update({k: torch.stack(v) for k, v in small.items()})
     return out
 
@@ -317,8 +320,12 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
         rollout_s = time.perf_counter() - t0
         for _ in range(num_epochs):
             with torch.no_grad():
-                value = _values(adapter, value_module, batch)
-                next_value = _values(adapter, value_module, batch, "next_")
+                if "_frames" in batch:          # V over the T+1 frames once: value = V[:-1], next_value = V[1:]
+                    v_all = _values(adapter, value_module, batch["_frames"])
+                    value, next_value = v_all[:-1], v_all[1:]
+                else:
+                    value = _values(adapter, value_module, batch)
+                    next_value = _values(adapter, value_module, batch, "next_")
                 adv, target = gae(value, next_value, batch["reward"], batch["done"], batch["done"])
                 adv = standardise(adv)
             n = min(sub_batch_size, T * R)

@@ -99,3 +99,30 @@ def test_occupancy_only_rollout_equals_the_full_rollout(scenario):
         assert torch.equal(full[k], plain[k]), k
     assert torch.equal(full["sel"], plain["sel"]) and torch.equal(full["agent_index"], plain["agent_index"])
     assert float(full["num"].sum()) > 0
+
+
+def test_gae_values_once_over_the_frames_equal_both_shifted_views(scenario):
+    """ppo_train evaluates the value net once over the T+1 frames of a rollout (frame t+1 is step t's next
+    observation); that must equal evaluating it on the observations and on the next observations separately."""
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNet, MPNNValueNetSimple
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, _values, collect
+    from tarl_simulator_b200.transportation_simulator import TransportationSimulator
+    sim = TransportationSimulator("cuda")
+    sim.load_network(scenario)
+    sim.agent.load(scenario)
+    g = sim.graph
+    env = BatchedSimulatorEnv(g, sim.Nmax, sim.agent.agent_features, replicas=4, seed=3)
+    ad = _EnvAdapter(env)
+    pm = PolicyModule(MPNNPolicyNet(g.edge_index, g.x.size(0), torch.ones(g.edge_index.size(1)), "cuda"), g.edge_index)
+    simple = ValueModule(MPNNValueNetSimple(g.edge_index, g.x.size(0), "cuda"))
+    full = MPNNValueNet(g.edge_index, g.x.size(0), "cuda")
+    full.agent_features = sim.agent.agent_features.cuda()
+    full.eval()
+    for vm, slim in ((simple, True), (simple, False), (ValueModule(full), False)):
+        batch = collect(ad, pm, 12, occupancy_only=slim)
+        with torch.no_grad():
+            v_all = _values(ad, vm, batch["_frames"])
+            v, nv = _values(ad, vm, batch), _values(ad, vm, batch, "next_")
+        assert v_all.shape == (13, 4)
+        assert torch.equal(v_all[:-1], v) and torch.equal(v_all[1:], nv)
