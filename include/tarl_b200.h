@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 14
+#define TARL_ABI_VERSION 15
 
 /* return codes */
 #define TARL_OK 0
@@ -272,11 +272,14 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
  * SELECTED_ROAD of the group's source node: sel_links [batch, n_links] for road links (node id < n_links),
  * sel_sources [batch, n_nodes - n_links] for the other nodes; group_node [K] = source node of each group, edge_dst
  * [E] = edge_index[1] as int32. A group without a hit (uniform >= the rounded cumulative sum) leaves SELECTED_ROAD
- * untouched and makes the row's log-probability -inf, exactly as the two separate calls do. */
+ * untouched and makes the row's log-probability -inf, exactly as the two separate calls do. uniforms == NULL: the
+ * uniforms are drawn in the kernel (Philox4x32-10 keyed by `seed`, counter (group, 4-row chunk)) instead of being
+ * produced by torch.rand and read back — the reference draws them from torch's global generator (:62), so which
+ * stream they come from is declared divergence D4 either way. */
 int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
                                 const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
                                 const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
-                                int32_t n_links, int32_t n_nodes, void* stream);
+                                int32_t n_links, int32_t n_nodes, uint64_t seed, void* stream);
 
 /* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
  * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]
@@ -387,7 +390,7 @@ typedef struct tarl_agent_index {
  * inserted: NULL, or [R*n_origins] agents inserted so far per (replica, origin) — maintained here, zeroed by the caller
  * whenever it resets ON_WAY / DONE, valid only while nothing else edits those columns; with index->dep_sorted it lets
  * origins without a waiting agent be skipped without touching agent_features (identical results).
- * worklist / work_count: both NULL, or scratch [R*n_origins] / [R]: the origins that queue for a road this step are
+ * worklist / work_count: both NULL, or scratch [R*n_origins] / [R + n_origins]: the origins that queue for a road this step are
  * compacted per replica and the admission runs over that list only (identical results; the listed origins are a few
  * per cent of all (replica, origin) pairs and each carries a chain of dependent gathers).
  * num_out / occupancy: both NULL, or (link store only) the occupancy observation tarl_agents_withdraw left behind in

@@ -112,7 +112,8 @@ SIGNATURES = {
     "tarl_graphdist_forward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _ROWS, _ROWS, _P, _P, _P, _P]),
     "tarl_graphdist_backward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _P, _P, _P, _ROWS, _P]),
     "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _ROWS, _I32, _P, _P, _P]),
-    "tarl_graphdist_sample_apply": (C.c_int, [_CSR1, _P, _F, _I32, _ROWS, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
+    "tarl_graphdist_sample_apply": (C.c_int, [_CSR1, _P, _F, _I32, _ROWS, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, C.c_uint64,
+                                              _P]),
     "tarl_value_mp_partial_count": (_I32, [_I32, _I32]),
     "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
                                         _P, _P, _P, _P]),

@@ -153,25 +153,38 @@ __device__ __forceinline__ bool agent_ready(const AgentTable& at, int r, int a, 
     return p[kDepartureTime] <= t && p[kOnWay] == 0.0f && p[kDone] == 0.0f;     // base.py:247-251
 }
 
+// number of agents of origin node o whose DEPARTURE_TIME <= t (binary search in the origin's sorted departure times)
+__device__ __forceinline__ int departed_by(const tarl_agent_index& ai, int o, float t) {
+    int lo = ai.org_ptr[o], hi = ai.org_ptr[o + 1];
+    const int k0 = lo;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ai.dep_sorted[mid] <= t) lo = mid + 1; else hi = mid;
+    }
+    return lo - k0;
+}
+
+__global__ void __launch_bounds__(kThreads) k_insert_departed(tarl_agent_index ai, float t, int32_t* __restrict__ departed) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i < ai.n_origins) departed[i] = departed_by(ai, ai.origins[i], t);
+}
+
 // What one (replica, origin) pair does in the offer phase; returns true when the origin was pushed onto a road's list.
 template <class Acc>
 __device__ __forceinline__ bool insert_offer_one(const Acc& acc, const tarl_agent_index& ai, const AgentTable& at, float t,
                                                  int32_t* __restrict__ head, int32_t* __restrict__ next,
                                                  int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
-                                                 const int32_t* __restrict__ inserted, int r, int i) {
+                                                 const int32_t* __restrict__ inserted,
+                                                 const int32_t* __restrict__ departed, int r, int i) {
     const int o = ai.origins[i];
     const size_t ri = (size_t)r * ai.n_origins + i;
     if (inserted != nullptr && ai.dep_sorted != nullptr) {
         // How many of this origin's agents have departed by now (static, ascending departure times) against how many
         // this replica has inserted so far: equal = nobody is waiting, and neither the road's list nor the scan over
-        // the origin's agent rows (the whole cost of an insertion step in steady state) is needed.
-        int lo = ai.org_ptr[o], hi = ai.org_ptr[o + 1];
-        const int k0 = lo;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (ai.dep_sorted[mid] <= t) lo = mid + 1; else hi = mid;
-        }
-        if (lo - k0 <= inserted[ri]) { next[ri] = -2; return false; }
+        // the origin's agent rows (the whole cost of an insertion step in steady state) is needed. The count does not
+        // depend on the replica: with a `departed` scratch it was computed once per origin (k_insert_departed).
+        const int n_dep = departed != nullptr ? departed[i] : departed_by(ai, o, t);
+        if (n_dep <= inserted[ri]) { next[ri] = -2; return false; }
     }
     const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
     cursor[ri] = ai.org_ptr[o];
@@ -196,11 +209,12 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
                                                            int32_t* __restrict__ head, int32_t* __restrict__ next,
                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
                                                            const int32_t* __restrict__ inserted,
-                                                           int32_t* __restrict__ work, int32_t* __restrict__ work_count) {
+                                                           int32_t* __restrict__ work, int32_t* __restrict__ work_count,
+                                                           const int32_t* __restrict__ departed) {
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     bool listed = false;
-    if (i < ai.n_origins) listed = insert_offer_one(acc, ai, at, t, head, next, cursor, flags, inserted, r, i);
+    if (i < ai.n_origins) listed = insert_offer_one(acc, ai, at, t, head, next, cursor, flags, inserted, departed, r, i);
     if (work == nullptr) return;
     const unsigned m = __ballot_sync(0xffffffffu, listed);
     if (m == 0u) return;
@@ -525,12 +539,19 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if ((worklist != nullptr) != (work_count != nullptr)) return TARL_E_BADARG;
     if ((num_out != nullptr) != (occupancy != nullptr) || (num_out != nullptr && !is_store)) return TARL_E_BADARG;
     if (worklist != nullptr && cudaMemsetAsync(work_count, 0, sizeof(int32_t) * R, cs) != cudaSuccess) return TARL_E_LAUNCH;
+    // work_count = [R] counters followed by n_origins words of scratch: the departed agents per origin at time t,
+    // computed once per origin instead of once per (replica, origin)
+    int32_t* dep_scratch = nullptr;
+    if (work_count != nullptr && inserted != nullptr && index->dep_sorted != nullptr && R > 1) {
+        dep_scratch = work_count + R;
+        k_insert_departed<<<blocks_for(index->n_origins), kThreads, 0, cs>>>(*index, t, dep_scratch);
+    }
     if (is_store) {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count, dep_scratch);
         k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
                                                 num_out, occupancy, sto.n_nodes);
     } else {
-        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count);
+        k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count, dep_scratch);
         k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
                                                 nullptr, nullptr, 0);
     }

@@ -179,9 +179,8 @@ class GraphDistribution(Distribution):
         if S > 1:
             lg = lg.unsqueeze(0).expand(S, B, E).reshape(S * B, E)
         rows = S * B
-        if uniforms is None:       # group-major memory: the rows of one group are read as one vector
-            u = torch.rand(self.nb_nodes, rows, dtype=torch.float32, device=dev).t()
-        else:
+        u = None                   # drawn below unless the kernel draws its own (sink path)
+        if uniforms is not None:
             u = uniforms.to(device=dev, dtype=torch.float32).reshape(rows, self.nb_nodes)
         if dtype not in (torch.int64, torch.bool, torch.uint8):
             raise ValueError("sample dtype must be int64, bool or uint8")
@@ -215,18 +214,23 @@ class GraphDistribution(Distribution):
                 partials = torch.empty(3 * rows * max(_cabi.lib().tarl_graphdist_partial_count(self.nb_nodes, rows), 1),
                                        dtype=torch.float32, device=dev)
                 fused = True
+            # no injected uniforms: the kernel draws them (Philox keyed by a seed from torch's default CPU generator, so
+            # torch.manual_seed reproduces a rollout) instead of reading back a torch.rand tensor
+            seed = int(torch.randint(0, 2 ** 62, (1,))) if u is None else 0
             with torch.cuda.device(dev):
                 rc = _cabi.lib().tarl_graphdist_sample_apply(
-                    self._groups.ref(), lg.data_ptr(), self.temperature, rows, _cabi.rows(u), out.data_ptr(),
-                    lp.data_ptr() if fused else None, partials.data_ptr() if fused else None,
+                    self._groups.ref(), lg.data_ptr(), self.temperature, rows, _cabi.rows(u) if u is not None else None,
+                    out.data_ptr(), lp.data_ptr() if fused else None, partials.data_ptr() if fused else None,
                     sink.group_node.data_ptr(), sink.edge_dst.data_ptr(), sink.sel_links.data_ptr(),
                     sink.sel_sources.data_ptr() if sink.sel_sources is not None else None, sink.n_links, sink.n_nodes,
-                    _stream(dev))
+                    seed, _stream(dev))
             _cabi.check(rc, "tarl_graphdist_sample_apply")
             sink.applied = True
             out = out.view(torch.bool) if dtype == torch.bool else out
             out = out.reshape(*sample_shape, *self._lead, E)
             return (out, lp.reshape(self._lead)) if return_log_prob else out
+        if u is None:              # group-major memory: the rows of one group are read as one vector
+            u = torch.rand(self.nb_nodes, rows, dtype=torch.float32, device=dev).t()
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_graphdist_sample(self._groups.ref(), _cabi.rows(lg), self.temperature, rows,
                                                    _cabi.rows(u), _cabi.rows(out),

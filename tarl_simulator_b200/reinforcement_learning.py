@@ -199,7 +199,7 @@ class BatchedSimulatorEnv:
         self._cursor = torch.empty(max(self.R * self.index.n_origins, 1), **i32)
         self._inserted = torch.zeros(max(self.R * self.index.n_origins, 1), **i32)   # per (replica, origin), see insert()
         self._work = torch.empty(max(self.R * self.index.n_origins, 1), **i32)       # listed origins of a step, compacted
-        self._work_count = torch.zeros(self.R, **i32)
+        self._work_count = torch.zeros(self.R + self.index.n_origins, **i32)         # + departed-per-origin scratch
         self.counters = torch.zeros(self.R, 2, **i32)          # running totals {inserted, withdrawn} per replica
         self.occupancy = torch.zeros(self.R, **i32)
         self.withdrawn = torch.zeros(self.R, self.N, dtype=torch.bool, device=dev)
@@ -224,8 +224,8 @@ class BatchedSimulatorEnv:
     def reset(self):
         """_reset (:186-219): empty queues, ON_WAY = DONE = 0, t = 06:00 − 60 s."""
         self.store.clear_queues()
-        self.agent_features[..., Agents.ON_WAY] = 0.0
-        self.agent_features[..., Agents.DONE] = 0.0
+        assert Agents.DONE == Agents.ON_WAY + 1
+        self.agent_features[..., Agents.ON_WAY:Agents.DONE + 1] = 0.0      # one strided pass over the table, not two
         self.counters.zero_()
         self._inserted.zero_()
         if self.metrics is not None:

@@ -69,8 +69,8 @@ def test_ppo_on_batched_env_updates_parameters(scenario):
 
 def test_occupancy_only_rollout_equals_the_full_rollout(scenario):
     """collect(occupancy_only=True) — the trajectory of nets that read NUMBER_OF_AGENT only — must hold the same
-    occupancies, actions, log-probabilities and rewards as the full trajectory; the sampling kernel applies the action
-    in both (action sink), and stepping with env.step(action) instead gives the same episode."""
+    occupancies, actions, log-probabilities and rewards as the full trajectory (the sampling kernel applies the action
+    and draws its own uniforms in both); a rollout without the action sink is a valid episode too."""
     from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet, MPNNValueNetSimple
     from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
     from tarl_simulator_b200.rl.ppo_trainer import PolicyModule, ValueModule, _EnvAdapter, collect, occupancy_only
@@ -96,9 +96,16 @@ def test_occupancy_only_rollout_equals_the_full_rollout(scenario):
     assert slim["sel"] is None and slim["agent_index"] is None and full["sel"] is not None
     for k in ("num", "next_num", "action", "sample_log_prob", "reward", "done", "time"):
         assert torch.equal(full[k], slim[k]), k
-        assert torch.equal(full[k], plain[k]), k
-    assert torch.equal(full["sel"], plain["sel"]) and torch.equal(full["agent_index"], plain["agent_index"])
     assert float(full["num"].sum()) > 0
+    # Without the sink the uniforms come from torch.rand instead of the kernel's own stream: another episode of the same
+    # process (the equivalence of the two write paths under the SAME uniforms is test_mpnn_gpu's sink test). Every
+    # replica still selects exactly one edge per source group, and the observation is consistent with its reward.
+    groups = int(torch.unique(g.edge_index[0]).numel())
+    for run in (full, plain):
+        assert bool((run["action"].sum(-1) == groups).all())
+        assert torch.equal(run["next_num"].sum(-1), -run["reward"])
+        sel_of_links = run["next_sel"][..., : env.N]
+        assert bool(((sel_of_links >= 0) & (sel_of_links < g.x.size(0))).all())
 
 
 def test_gae_values_once_over_the_frames_equal_both_shifted_views(scenario):
