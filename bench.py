@@ -484,6 +484,11 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     iters = max(min(args.steps // 10, 50), 5)
     pol_ms = timed(policy_iter, iters)
     val_ms = timed(value_iter, iters)
+    # the same net in TRAIN mode: nn.Dropout(0.05) on the [B*E, 17] message input (src/agents/mpnn_agent.py:278); the
+    # keep words are drawn in the kernel; time_net's own dropouts are torch modules and stay on
+    value.train()
+    val_train_ms = timed(value_iter, max(iters // 5, 3))
+    value.eval()
     del policy, value, nf, ai, action
     torch.cuda.empty_cache()
     vmlp = value_mlp_bench(dev, timed, world, peak)
@@ -502,6 +507,12 @@ def mpnn_bench(args, g, dev, world, rank, peak):
                           "roofline": {"bound": "hbm", "algorithmic_bytes": int(val_bytes),
                                        "achieved": round(val_bytes / (val_ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                                        "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}},
+            "value_net_train_mode": {"value": round(world * B * E_full / (val_train_ms / 1e3), 1),
+                                     "ms_per_iter": round(val_train_ms, 4),
+                                     "what": "MPNNValueNet.forward (train: message dropout p = 0.05, keep words drawn in "
+                                             "the kernel) -> backward (message_dropout, aggregate_msg, node_grad, "
+                                             "edge_grad_dropout, finish): the per-node projection does not factor "
+                                             "through a per-edge mask, every (row, edge) gathers its 16 inputs' products"},
             "value_mlp": vmlp}
 
 

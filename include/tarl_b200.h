@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 15
+#define TARL_ABI_VERSION 16
 
 /* return codes */
 #define TARL_OK 0
@@ -315,7 +315,9 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
  * survives; k < 16 the target node's inputs, k = 16 the edge feature): either injected — keep_bits [B, E] with batch
  * stride keep_batch_stride, e.g. the mask the reference itself drew — or, with keep_bits == NULL, drawn in the kernel
  * from Philox4x32-10 keyed by `seed` (tarl_value_mp_dropout_bits writes the words of that stream: what the kernels
- * will use for the same seed / p). msg: [E*B] output, element (b, e) at e*B + b (the tanh messages; backward reads
+ * will use for the same seed / p). keep_words: NULL, or [E*B] scratch (element (b, e) at e*B + b): with keep_bits ==
+ * NULL the forward pass stores the words it draws there and the backward pass reads them back instead of drawing them
+ * again. msg: [E*B] output, element (b, e) at e*B + b (the tanh messages; backward reads
  * them back). mean, v as in tarl_value_mp_forward. */
 int tarl_value_mp_dropout_bits(uint64_t seed, float p, int32_t batch, int32_t n_edges, uint32_t* keep_bits, void* stream);
 int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
@@ -324,14 +326,15 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                                   int32_t agent_rows, const float* msg_weight, const float* msg_bias,
                                   const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                  float* msg, float* mean, float* v, int32_t* flags, void* stream);
+                                  uint32_t* keep_words, float* msg, float* mean, float* v, int32_t* flags, void* stream);
 /* grads / gm / partials as in tarl_value_mp_backward; keep_bits / seed / p must be the forward call's. */
 int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
                                    int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
                                    int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                                    int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                   const float* msg, const float* mean, const float* v, const float* grad_v,
+                                   const uint32_t* keep_words, const float* msg, const float* mean, const float* v,
+                                   const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream);
 

@@ -121,9 +121,9 @@ SIGNATURES = {
                                          _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tarl_value_mp_dropout_bits": (C.c_int, [C.c_uint64, _F, _I32, _I32, _P, _P]),
     "tarl_value_mp_forward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32,
-                                                _I32, _P, _I64, C.c_uint64, _F, _P, _P, _P, _P, _P]),
+                                                _I32, _P, _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P]),
     "tarl_value_mp_backward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I32, _I32, _P,
-                                                 _I64, C.c_uint64, _F, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
+                                                 _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_withdraw": (C.c_int, [_AST, _ATB, _CSR1, _F, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),

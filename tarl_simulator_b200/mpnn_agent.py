@@ -197,7 +197,7 @@ class _ValueMessagePassing(torch.autograd.Function):
 class _ValueMessagePassingDropout(torch.autograd.Function):
     """_ValueMessagePassing in train mode: nn.Dropout(p) on the [B*E, 17] message input (src/agents/mpnn_agent.py:278).
     keep_bits: int32 [B, E] injected keep words (bit k = input k survives) or None = drawn in the kernels from the
-    Philox stream of `seed` (backward regenerates the same words)."""
+    Philox stream of `seed` (kept edge-major for the backward pass)."""
 
     @staticmethod
     def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags, keep_bits, seed, p):
@@ -210,12 +210,16 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
         pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
         ef_bs = ef.stride(0) if B > 1 else 0
         kb_ptr, kb_bs = (keep_bits.data_ptr(), keep_bits.stride(0)) if keep_bits is not None else (None, 0)
+        # words drawn in the kernel are kept (edge-major) for the backward pass instead of being drawn again
+        words = torch.empty(max(E, 1), B, dtype=torch.int32, device=dev) if keep_bits is None else None
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_value_mp_forward_dropout(
                 by_source.ref(), by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs,
                 ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
-                kb_ptr, kb_bs, seed, p, msg.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+                kb_ptr, kb_bs, seed, p, words.data_ptr() if words is not None else None, msg.data_ptr(), mean.data_ptr(),
+                v.data_ptr(), flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_forward_dropout")
+        ctx.words = words
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
         ctx.drop = (keep_bits, seed, p)
         ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
@@ -237,7 +241,7 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
             rc = lib.tarl_value_mp_backward_dropout(
                 ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
                 ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), nw.data_ptr(), B, N, kb_ptr, kb_bs, seed, p,
-                msg.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
+                ctx.words.data_ptr() if ctx.words is not None else None, msg.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
                 grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_backward_dropout")
         s = ctx.shapes

@@ -511,3 +511,38 @@ def test_one_logits_row_sampling_matches_the_generic_kernel_on_long_groups():
     b_idx, e_idx = torch.nonzero(a_m, as_tuple=True)
     want[b_idx, ei[0][e_idx]] = ei[1][e_idx].float()
     assert torch.equal(torch.cat((sel_l, sel_s), dim=1), want)
+
+
+def test_sampling_kernel_own_uniform_stream():
+    """Without injected uniforms the rollout sampling kernel draws its own (Philox keyed by a seed taken from torch's
+    default generator): empirical frequencies over 8192 replicas must follow the softmax of the shared logits row,
+    torch.manual_seed must reproduce a draw, consecutive draws must differ, and replicas must not repeat each other."""
+    from tarl_simulator_b200.distribution import ActionSink, GraphDistribution
+    from tarl_simulator_b200.topology import group_csr_for
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    N, E, R = 60, 260, 8192
+    ei = torch.stack([torch.randint(0, N, (E,), device="cuda", generator=gen), torch.randint(0, N, (E,), device="cuda", generator=gen)])
+    row = torch.randn(1, E, device="cuda", generator=gen)
+    d = GraphDistribution(row.expand(R, -1), ei)
+    sel = torch.zeros(R, N, device="cuda")
+    sink = ActionSink(ei, group_csr_for(ei, "source_rank"), sel, None, N, N)
+
+    def draw():
+        out = torch.empty(E, R, dtype=torch.bool, device="cuda").t()
+        a, lp = d.sample(dtype=torch.bool, out=out, return_log_prob=True, sink=sink)
+        assert sink.applied
+        return a.clone(), lp.clone()
+
+    torch.manual_seed(123)
+    a1, lp1 = draw()
+    a2, _ = draw()
+    torch.manual_seed(123)
+    a3, lp3 = draw()
+    assert torch.equal(a1, a3) and torch.equal(lp1, lp3) and not torch.equal(a1, a2)
+    assert bool((a1.sum(1) == d.nb_nodes).all())                       # one edge per source group in every replica
+    assert len({bytes(r.cpu().numpy().tobytes()) for r in a1[:64]}) > 60        # replicas draw independently
+    p = d.proba[0] if d.proba.dim() == 2 else d.proba                  # softmax of the shared row, per edge
+    freq = a1.float().mean(0)
+    sigma = (p * (1 - p) / R).sqrt()
+    assert bool(((freq - p).abs() <= 5 * sigma + 1e-3).all()), float(((freq - p).abs() / (sigma + 1e-6)).max())
+    assert torch.allclose(lp1, d.log_prob(a1), rtol=1e-5, atol=1e-4)
