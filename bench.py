@@ -415,7 +415,7 @@ def run_native(args):
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -716,11 +716,23 @@ def run_reference(args):
            "config": {"workload": name, "links": cb["links"]},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.perf_counter() - t0, 1)}
-    print(json.dumps(out))
+    emit(out)
 
+
+def emit(out):
+    """The ONE JSON line, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(out) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under torchrun, for
+    # one) goes to stderr instead — fd 1 is pointed at stderr for the whole run and the line is written to the saved fd
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

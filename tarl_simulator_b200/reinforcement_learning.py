@@ -340,9 +340,11 @@ class BatchedSimulatorEnv:
         return nf, (ai if agent_index else None)
 
     def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False,
-             compact_out=None):
+             compact_out=None, lean: bool = False):
         """One _step for every replica. action None = keep the current SELECTED_ROAD values. compact_out: see
-        observe() — the post-step compact observation comes out of the same pass that computes the reward."""
+        observe() — the post-step compact observation comes out of the same pass that computes the reward.
+        lean=True returns nothing: reward = -self.occupancy (which may be pointed at a row of a caller-owned [T, R] int32
+        buffer beforehand), done = self.time > EPISODE_END."""
         if action is not None:
             self.apply_action(action)
         self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
@@ -360,6 +362,8 @@ class BatchedSimulatorEnv:
         if not fused:
             nf, ai = self.observe(node_features=observe, agent_index=observe, compact_out=compact_out)
         self.time += self.timestep
+        if lean:            # rollouts: the caller reads self.occupancy / self.time itself (no per-step tensors, no launches)
+            return None
         out = {"reward": -self.occupancy.to(torch.float32), "occupancy": self.occupancy,
                "done": torch.full((self.R,), self.time > EPISODE_END, dtype=torch.bool, device=self.device),
                "time": self.time}
