@@ -693,7 +693,8 @@ def cpu_baseline(args, sample_steps, warmup=1, workload=None):
     return {"value": round(N / med, 1), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{sample_steps} core steps of the full {name} workload ({N} links), median; "
                       f"oracle/core_port.py (op-for-op torch restatement of the reference, {cores} ATen threads)",
-            "ms_per_step": round(med * 1e3, 2), "links": N}
+            "ms_per_step": round(med * 1e3, 2), "links": N, "dual_edges": int(ei.size(1)), "agents": int(placed),
+            "Nmax": int(Nmax)}
 
 
 def run_reference(args):
@@ -713,7 +714,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": name, "links": cb["links"]},
+           "config": {"workload": name, "links": cb["links"], "dual_edges": cb["dual_edges"], "agents": cb["agents"],
+                      "Nmax": cb["Nmax"], "link_order": getattr(args, "link_order", "node"), "replicas_per_gpu": 1,
+                      "state": "reference row layout on the host, noise injected per step (torch.rand outside the timed call)"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.perf_counter() - t0, 1)}
     emit(out)
