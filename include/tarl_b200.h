@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 16
+#define TARL_ABI_VERSION 17
 
 /* return codes */
 #define TARL_OK 0
@@ -415,6 +415,18 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
 int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_csr* adjacency,
                          float t, uint8_t* mask, int32_t* counters, int32_t* flags, float* num_out, int32_t* occupancy,
                          void* stream);
+
+/* tarl_store_step followed by tarl_agents_withdraw(num_out, occupancy) at the same t as ONE pass over the records: the
+ * response phase of the core step ends with every link's final record in registers, so the same thread withdraws
+ * (src/agents/base.py:334-403) where the head is due, writes NUMBER_OF_AGENT into num_out [R, n_nodes] (0 for the
+ * non-road nodes; needs n_nodes - n_links <= n_links) and adds it into occupancy [R] (zeroed here). Results are those
+ * of the two separate calls. ELLPACK topology and a store in link-id order only (TARL_E_BADARG otherwise: make the two
+ * calls). withdrawn: [R*N] mask, counters: NULL or [R*2]. Follow with tarl_agents_insert(num_out, occupancy). */
+int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                             const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
+                             float* delta_tt, uint8_t* pop, int32_t* flags, const tarl_agent_table* agents,
+                             const tarl_csr* adjacency, int32_t n_nodes, uint8_t* withdrawn, int32_t* counters,
+                             float* num_out, int32_t* occupancy, void* stream);
 
 /* Replaces Agents.choice (src/agents/base.py:446-494): every node listed in choosers (roads with a downstream road,
  * SRC nodes with an outgoing road) draws one of its neighbours[node] (ascending road id) uniformly into

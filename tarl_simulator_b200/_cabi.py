@@ -104,6 +104,8 @@ SIGNATURES = {
     "tarl_store_import": (C.c_int, [_STORE, _P, _I64, _I64, _P, _P, _P]),
     "tarl_store_export": (C.c_int, [_STORE, _P, _I64, _I64, _F, _P]),
     "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
+    "tarl_store_step_withdraw": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _ATB, _CSR1, _I32,
+                                           _P, _P, _P, _P, _P]),
     "tarl_cluster_links": (C.c_int, [_I32, _P, _P, _I32, _P]),
     "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, C.c_uint64, C.c_uint32, _F, _F, _I32, _P, _I32, _P, _P, _P, _P]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),

@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "engine_common.cuh"
+#include "population.cuh"
 
 using namespace tarl;
 
@@ -333,8 +334,8 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
 // The pop itself (src/response_mpnn.py:119-122) as a ring-head increment: new head <- logical slot 1, and the slot that
 // becomes logical Nmax-1 <- old logical Nmax-1 (the reference's shift leaves the last slot in place, i.e. duplicates it).
 // `have` says q_head / q_last were fetched ahead of time (hinted links).
-__device__ __forceinline__ void pop_head(const Store& s, int L, float4 hA, float4 hB, float t, bool have, float4 q_head,
-                                         float4 q_last) {
+__device__ __forceinline__ float pop_head(const Store& s, int L, float4 hA, float4 hB, float t, bool have, float4 q_head,
+                                          float4 q_last) {
     int meta = __float_as_int(hB.w);
     const int rh = meta & kMetaRingMask;
     const int M = s.M;
@@ -357,6 +358,7 @@ __device__ __forceinline__ void pop_head(const Store& s, int L, float4 hA, float
     if (gv && q == 1) meta &= ~kMetaGarbage;                    // the garbage became the head slot
     s.hot_next[2 * (size_t)L] = make_float4(new_head.x, new_head.z, hA.z - 1.0f, hA.w);
     s.hot_next[2 * (size_t)L + 1] = make_float4(new_head.y, hB.y, hB.z, __int_as_float(meta));
+    return new_head.z;                                          // exit time of the new head
 }
 
 // src/response_mpnn.py:66-83: NUM_up > 0, NUM_dn > 0, tail(dn) == head(up). A = own post-append record, D = {NUM, tail}
@@ -433,6 +435,90 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, t
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     if (accept) pop_head(s, L, A, B, t, fetched, q_head, q_last);
+}
+
+// ---------------------------------------------------------------- response phase + withdrawal + occupancy observation
+// One environment step of the RL loop is core step -> withdrawal -> insertion -> observation / reward
+// (src/reinforcement_learning.py:237-266). The withdrawal of a link touches that link's queue and its agents' rows only,
+// and the response phase ends with the link's final record of the core step in registers — so the thread that popped
+// (or not) also withdraws: only links whose head is due (NUM > 0, exit time <= t: a few per cent) take the rare path
+// (withdraw_one of population.cuh on the records just written), every thread leaves NUM in the trajectory frame and the
+// warps add it into the replica's occupancy. A separate withdrawal pass would read every record once more (1.3 GB per
+// step of 1024 grid100 replicas). Used for rollouts whose nets read the occupancy only; links in link-id order.
+struct WithdrawArgs {
+    AgentTable at;
+    tarl_csr adj;
+    uint8_t* mask;        // [R*N] withdrawn mask (the entry of withdraw_history)
+    int32_t* counters;    // [R*2] running totals {inserted, withdrawn} or nullptr
+    float* num_out;       // [R, n_nodes]
+    int32_t* occupancy;   // [R]
+    float* src_sel;
+    int n_nodes;
+};
+
+__device__ __noinline__ float withdraw_due_link(const Store& s, const WithdrawArgs& wa, float t, int32_t* flags, int r, int u) {
+    const StoreAcc acc = {s, reinterpret_cast<float*>(s.hot_next), wa.src_sel, wa.n_nodes, t, s.N, s.Nmax};
+    return withdraw_one(acc, wa.at, wa.adj, t, wa.mask, wa.counters, flags, r, u);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual_csr g, tarl_dual_ell ell,
+                                                                       const __grid_constant__ Store s, float t,
+                                                                       uint8_t* __restrict__ pop,
+                                                                       int32_t* __restrict__ flags,
+                                                                       const __grid_constant__ WithdrawArgs wa) {
+    // (__grid_constant__: the rare path takes `s` and `wa` by reference; without it every thread would first copy both
+    // structs from the parameter space into local memory — 200 bytes per thread, measured 1.2 ms instead of 0.4 ms)
+    const int u = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    const int base = r * s.N;
+    const int L = base + u;
+    bool accept = false, hinted = false, fetched = false;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
+    pdl_trigger();
+    int dn[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ell.out_dst[(size_t)j * ell.pitch + u] : -1;   // static: before the wait
+    pdl_wait();
+    if (u < s.N) {
+        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
+        hinted = s.hint[L] != 0;
+        if (dn[W - 1] == -2) {
+            accept = scan_out_edges_csr(g, s, base, u, A);
+        } else {
+            float2 D[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (dn[j] >= 0) D[j] = s.post[base + dn[j]];
+            if (hinted) {
+                const int rh = __float_as_int(B.w) & kMetaRingMask;
+                const float4* Q = s.queue + (size_t)L * s.M;
+                q_head = Q[rh];
+                if (s.M > 1) q_last = Q[ring_pos(rh, s.M, s.M)];
+                fetched = true;
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (dn[j] >= 0) accept = accept || accepts(A, D[j]);
+        }
+        if (hinted) s.hint[L] = 0;
+        pop[L] = accept ? 1 : 0;
+    }
+    if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
+    float head_exit = A.y, num = A.z;
+    if (accept) { head_exit = pop_head(s, L, A, B, t, fetched, q_head, q_last); num = A.z - 1.0f; }
+    if (u < s.N) {
+        if (0.0f < num && head_exit <= t) num = withdraw_due_link(s, wa, t, flags, r, u);     // slot 0 is due: :362-366
+        else wa.mask[L] = 0;
+        wa.num_out[(size_t)r * wa.n_nodes + u] = num;
+    } else {
+        num = 0.0f;
+    }
+    const int extra = wa.n_nodes - s.N;                           // the non-road nodes of the frame hold no agents
+    if (u < extra) wa.num_out[(size_t)r * wa.n_nodes + s.N + u] = 0.0f;
+    int num_i = (int)num;
+    for (int off = 16; off > 0; off >>= 1) num_i += __shfl_xor_sync(0xffffffffu, num_i, off);
+    if ((threadIdx.x & 31) == 0 && num_i != 0) atomicAdd(&wa.occupancy[r], num_i);
 }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in engine_common.cuh).
@@ -557,6 +643,34 @@ int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl
     if (s.N == 0) return TARL_OK;
     const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
     launch_step(g, ell, s, attr_in, nz, t, delta_tt, pop, flags, static_cast<cudaStream_t>(stream), phase_mask);
+    return launch_status();
+}
+
+int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                             const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
+                             float* delta_tt, uint8_t* pop, int32_t* flags, const tarl_agent_table* agents,
+                             const tarl_csr* adjacency, int32_t n_nodes, uint8_t* withdrawn, int32_t* counters,
+                             float* num_out, int32_t* occupancy, void* stream) {
+    Store s;
+    int rc = make_store(store, &s);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, noise, pop, flags)) != TARL_OK) return rc;
+    if (ell == nullptr || s.slot_link != nullptr) return TARL_E_BADARG;          // ELL kernels, links in link-id order
+    if (agents == nullptr || agents->agent_features == nullptr || agents->n_rows < 1 || adjacency == nullptr ||
+        adjacency->ptr == nullptr || (adjacency->n_edges > 0 && adjacency->idx == nullptr) || withdrawn == nullptr ||
+        num_out == nullptr || occupancy == nullptr || n_nodes < s.N || n_nodes - s.N > s.N)
+        return TARL_E_BADARG;
+    if (s.R > 1 && agents->replica_stride < (int64_t)agents->n_rows * 9) return TARL_E_BADARG;
+    if (s.N == 0) return TARL_OK;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(occupancy, 0, sizeof(int32_t) * (size_t)s.R, cs) != cudaSuccess) return TARL_E_LAUNCH;
+    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
+    launch_step(g, ell, s, attr_in, nz, t, delta_tt, pop, flags, cs, TARL_PHASE_SELECT_APPEND);
+    const WithdrawArgs wa = {AgentTable{agents->agent_features, s.R > 1 ? agents->replica_stride : 0, agents->n_rows},
+                             *adjacency, withdrawn, counters, num_out, occupancy, nullptr, n_nodes};
+    const dim3 grid(blocks_for(s.N), s.R);
+    if (ell->width == 4) launch_pdl(k_ell_respond_pop_withdraw<4>, grid, cs, *g, *ell, s, t, pop, flags, wa);
+    else launch_pdl(k_ell_respond_pop_withdraw<8>, grid, cs, *g, *ell, s, t, pop, flags, wa);
     return launch_status();
 }
 

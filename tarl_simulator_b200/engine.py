@@ -158,9 +158,12 @@ class LinkStore:
         return self._to_links(self.sel[: self.R * self.N].view(self.R, self.N))
 
     def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
-             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_ELL):
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_ELL, withdraw=None):
         """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
-        for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8)."""
+        for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8).
+        withdraw (optional, ELL variant and link-id order only — see can_fuse_withdraw()): dict(table=_cabi.AgentTable,
+        adjacency=CSR struct, n_nodes, mask, counters, num_out, occupancy) — the withdrawal at the same t and the
+        occupancy observation ride on the response phase (tarl_store_step_withdraw)."""
         if noise is not None:
             noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
             if noise.numel() != self.R * self.E:
@@ -168,6 +171,23 @@ class LinkStore:
         if delta_tt is not None and (delta_tt.numel() != self.R * self.E or delta_tt.dtype != torch.float32 or not delta_tt.is_contiguous()):
             raise ValueError("delta_tt must be a contiguous fp32 [R, E] tensor")
         self._fill_struct()
+        if withdraw is not None:
+            if not self.can_fuse_withdraw(variant, phase_mask):
+                raise ValueError("withdraw= needs the ELL variant, both phases and a store in link-id order")
+            w = withdraw
+            with torch.cuda.device(self.device):
+                rc = _cabi.lib().tarl_store_step_withdraw(
+                    self.topo.ref(), C.byref(self._ell[0]), C.byref(self._struct), self.attr_in.data_ptr(),
+                    noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
+                    delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
+                    C.byref(w["table"]), C.byref(w["adjacency"]), int(w["n_nodes"]), w["mask"].data_ptr(),
+                    w["counters"].data_ptr() if w.get("counters") is not None else None, w["num_out"].data_ptr(),
+                    w["occupancy"].data_ptr(), self._stream())
+            _cabi.check(rc, "tarl_store_step_withdraw")
+            self.cur ^= 1
+            self.step_id += 1
+            self.t_last = float(t)
+            return self._to_links(self.pop[: self.N * self.R].view(self.R, self.N))
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_store_step(
                 self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
@@ -181,6 +201,10 @@ class LinkStore:
             self.step_id += 1
             self.t_last = float(t)
         return self._to_links(self.pop[: self.N * self.R].view(self.R, self.N))
+
+    def can_fuse_withdraw(self, variant: int = VARIANT_ELL, phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP) -> bool:
+        return (variant == VARIANT_ELL and self.slot_link is None and self.N > 0
+                and phase_mask == (PHASE_SELECT_APPEND | PHASE_RESPOND_POP))
 
     def run(self, t0: float, n_steps: int, dt: float = 1.0, sel_bank=None, delta_tt: torch.Tensor | None = None,
             variant: int = VARIANT_ELL):

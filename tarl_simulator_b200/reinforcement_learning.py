@@ -347,13 +347,20 @@ class BatchedSimulatorEnv:
         buffer beforehand), done = self.time > EPISODE_END."""
         if action is not None:
             self.apply_action(action)
-        self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
         # occupancy-only observation (compact_out = (NUM frame, None, None)): withdraw holds every record anyway and
         # leaves NUM + the reward behind, insert patches the roads it touches — no separate observe pass
         fused = (not observe and compact_out is not None and compact_out[1] is None and compact_out[2] is None
                  and compact_out[0].dtype == torch.float32 and compact_out[0].shape == (self.R, self.n_nodes)
                  and compact_out[0].is_contiguous())
-        self.withdraw(num_out=compact_out[0] if fused else None)
+        if fused and self.n_nodes - self.N <= self.N and self.store.can_fuse_withdraw():
+            # ... and the withdrawal itself rides on the response phase of the core step: one pass over the records
+            self.store.step(self.time, noise=noise, delta_tt=self.delta_tt,
+                            withdraw=dict(table=self._table, adjacency=self.side.adj, n_nodes=self.n_nodes,
+                                          mask=self.withdrawn, counters=self.counters, num_out=compact_out[0],
+                                          occupancy=self.occupancy))
+        else:
+            self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
+            self.withdraw(num_out=compact_out[0] if fused else None)
         self.insert(num_out=compact_out[0] if fused else None)
         if self.metrics is not None:
             self.metrics.record(self.time, pop=self.store.pop[: self.R * self.N], withdrawn=self.withdrawn,

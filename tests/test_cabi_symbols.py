@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_ctypes_table_matches_header(built_lib):
     assert sorted(_cabi.SIGNATURES) == declared_symbols()
-    assert _cabi.lib().tarl_abi_version() == 16
+    assert _cabi.lib().tarl_abi_version() == 17
     assert b"workspace" in _cabi.lib().tarl_error_string(-2)
 
 
