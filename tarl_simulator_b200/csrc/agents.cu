@@ -99,7 +99,7 @@ __device__ __forceinline__ bool insert_offer_one(const Acc& acc, const tarl_agen
                                                  int32_t* __restrict__ head, int32_t* __restrict__ next,
                                                  int32_t* __restrict__ cursor, int32_t* __restrict__ flags,
                                                  const int32_t* __restrict__ inserted,
-                                                 const int32_t* __restrict__ departed, int r, int i) {
+                                                 const int32_t* __restrict__ departed, bool mark_unlisted, int r, int i) {
     const int o = ai.origins[i];
     const size_t ri = (size_t)r * ai.n_origins + i;
     if (inserted != nullptr && ai.dep_sorted != nullptr) {
@@ -108,7 +108,9 @@ __device__ __forceinline__ bool insert_offer_one(const Acc& acc, const tarl_agen
         // the origin's agent rows (the whole cost of an insertion step in steady state) is needed. The count does not
         // depend on the replica: with a `departed` scratch it was computed once per origin (k_insert_departed).
         const int n_dep = departed != nullptr ? departed[i] : departed_by(ai, o, t);
-        if (n_dep <= inserted[ri]) { next[ri] = -2; return false; }
+        // (next[ri] = -2 tells a per-(replica, origin) admit pass "not listed"; with a worklist only listed origins are
+        // visited and the 4-byte store per pair and step — 40 MB at 1024 x 10 000 origins — is left out)
+        if (n_dep <= inserted[ri]) { if (mark_unlisted) next[ri] = -2; return false; }
     }
     const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
     cursor[ri] = ai.org_ptr[o];
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
     const int i = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     bool listed = false;
-    if (i < ai.n_origins) listed = insert_offer_one(acc, ai, at, t, head, next, cursor, flags, inserted, departed, r, i);
+    if (i < ai.n_origins) listed = insert_offer_one(acc, ai, at, t, head, next, cursor, flags, inserted, departed, work == nullptr, r, i);
     if (work == nullptr) return;
     const unsigned m = __ballot_sync(0xffffffffu, listed);
     if (m == 0u) return;
