@@ -422,3 +422,40 @@ def test_full_size_environment_invariants():
         assert torch.equal(x[0], x[1]) and torch.equal(env.agent_features[0], env.agent_features[1])
     assert float(on_way.min()) > 100_000 and float(num.sum(1).min()) > 100_000      # the network did fill up
     env.check_errors()
+
+
+@pytest.mark.parametrize("inject_noise", [False, True])
+def test_fused_step_withdraw_observe_equals_the_separate_passes(inject_noise):
+    """The occupancy-only environment step (core step whose response phase also withdraws and leaves NUM / the reward
+    behind, insertion patching them: tarl_store_step_withdraw) against the step with separate passes on a twin
+    environment: whole exported state, agent table, withdrawn masks, counters, occupancy and the NUM frame after every
+    one of 260 steps of short trips on a 6 x 6 grid (hundreds of withdrawals, queues that fill up)."""
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    dev = torch.device("cuda")
+    frm, to, n_nodes = synthetic.grid_links(6, device=dev)
+    g, Nmax = synthetic.build_graph(frm, to, n_nodes)
+    af = synthetic.population(g, 500, 21540, 90, seed=2)
+    R = 3
+    a = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=9)
+    b = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=9)
+    assert a.store.can_fuse_withdraw() and a.n_nodes - a.N <= a.N
+    a.reset(); b.reset()
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    E = a.store.E
+    frame = torch.empty(R, a.n_nodes, device=dev)
+    F = 3 * Nmax + 7
+    for s in range(260):
+        a.choice(seed=100 + s); b.choice(seed=100 + s)            # the same routing decisions in both
+        noise = torch.rand(R, E, device=dev, generator=gen).clamp_(min=1e-6) if inject_noise else None
+        a.step(None, noise=noise, compact_out=(frame, None, None), lean=True)      # fused
+        out = b.step(None, noise=noise, observe=True)                               # separate passes
+        xa, xb = a.export_x(), b.export_x()
+        assert torch.equal(xa, xb), s
+        assert torch.equal(a.agent_features, b.agent_features), s
+        assert torch.equal(a.withdrawn, b.withdrawn) and torch.equal(a.counters, b.counters), s
+        assert torch.equal(a.occupancy, b.occupancy) and torch.equal(out["reward"], -a.occupancy.float()), s
+        assert torch.equal(frame[:, : a.N], xb[:, : a.N, F - 6]) and float(frame[:, a.N:].abs().sum()) == 0.0, s
+        assert torch.equal(frame, out["node_features"][..., 1]), s
+    assert int(a.counters[:, 1].min()) > 10                        # withdrawals did happen in every replica
+    a.check_errors(); b.check_errors()
