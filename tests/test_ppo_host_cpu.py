@@ -80,3 +80,32 @@ def test_replica_sharding():
     assert [shard_replicas(10, 4, r) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
     with pytest.raises(ValueError):
         shard_replicas(3, 4, 0)
+
+
+def test_occupancy_only_predicate_and_trajectory_views():
+    """Host logic of the slim rollouts: which pairs of nets qualify, and that the trajectory dict keeps the shifted
+    views (next_* of step t is frame t+1, same storage) with None for the frames an occupancy-only rollout drops."""
+    from types import SimpleNamespace
+    from tarl_simulator_b200.rl.ppo_trainer import _trajectory, occupancy_only
+    static_policy = SimpleNamespace(net=SimpleNamespace(reads_dynamic_features=False))
+    dynamic_policy = SimpleNamespace(net=SimpleNamespace())
+    simple_value = SimpleNamespace(net=SimpleNamespace(forward_occupancy=lambda n, t: n))
+    full_value = SimpleNamespace(net=SimpleNamespace())
+    assert occupancy_only(static_policy, simple_value)
+    assert not occupancy_only(dynamic_policy, simple_value)
+    assert not occupancy_only(static_policy, full_value)
+    assert not occupancy_only(static_policy, None)
+    T, R, M, E = 5, 2, 7, 11
+    num = torch.arange((T + 1) * R * M, dtype=torch.float32).view(T + 1, R, M)
+    times = torch.arange(T + 1, dtype=torch.float32).unsqueeze(1).expand(T + 1, R)
+    action = torch.zeros(T, R, E, dtype=torch.bool)
+    out = _trajectory(num, None, None, times, action, 3)
+    assert out["sel"] is None and out["next_agent_index"] is None and out["_frames"]["sel"] is None
+    assert out["num"].shape == (3, R, M) and out["_frames"]["num"].shape == (4, R, M)
+    assert torch.equal(out["next_num"], num[1:4]) and out["next_num"].data_ptr() == num[1].data_ptr()
+    assert torch.equal(out["next_time"][:, 0], torch.tensor([1.0, 2.0, 3.0]))
+    sel = torch.zeros(T + 1, R, M)
+    ai = torch.zeros(T + 1, R, M, dtype=torch.int64)
+    out = _trajectory(num, sel, ai, times, action, T)
+    assert out["sel"].shape == (T, R, M) and out["next_sel"].data_ptr() == sel[1].data_ptr()
+    assert out["_frames"]["agent_index"].shape == (T + 1, R, M)
