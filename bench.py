@@ -130,11 +130,14 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+TRAFFIC_FILE = "traffic_r02.json"
+
+
 def measured_traffic(workload, replicas, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r01.json), valid
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic_r02.json), valid
     only for the workload / replica count it was captured on; None otherwise."""
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic_r01.json")) as f:
+        with open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)) as f:
             t = json.load(f)
         if t["workload"] == workload and t["replicas"] == replicas:
             return t["kernels"][kernel]["dram_bytes_per_launch"]
@@ -143,18 +146,19 @@ def measured_traffic(workload, replicas, kernel):
     return None
 
 
-def step_bytes(N, E, Nmax, p):
-    """algorithmic bytes of one core step."""
-    return N * (69 + p * (24 * (Nmax - 1) + 4)) + 20 * E
+def step_bytes(N, E, Nmax, p, noise_read=False):
+    """algorithmic bytes of one core step, B_step = N (69 + p (24 (Nmax-1) + 4)) + 20 E. 4 of the
+    20 B per dual edge are the uniform the direction phase reads; SURVEY sets them to 0 when the noise is generated
+    in-kernel, which is what the timed run does (noise_read=False -> 16 E)."""
+    return N * (69 + p * (24 * (Nmax - 1) + 4)) + (20 if noise_read else 16) * E
 
 
-def phase_bytes(N, E, Nmax, p):
-    """The same budget split over the three kernels."""
-    return {
-        "k_offer": N * 36,                                   # head triplet 12 + {MAXN,NUM,FFTT,SEL,RIDX} 20 + cc 4
-        "k_select_append": N * 16 + 16 * E,                  # tail triplet 12 + NUM 4 ; per edge idx 4 + attr 4 + noise 4 + dtt 4
-        "k_respond_shift": N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4),
-    }
+def phase_bytes(N, E, Nmax, p, noise_read=False):
+    """The same budget split over the two phases of the store step: direction = per link read head
+    triplet 12 + {MAXN, NUM, FFTT, SEL, RIDX} 20 + cc 4, write tail triplet 12 + NUM 4 (52 N); per dual edge col-idx
+    4 + edge_attr 4 (+ noise 4) + delta_tt 4. Response = 17 N + 4 E + p N (24 (Nmax-1) + 4)."""
+    return {"direction": N * 52 + (16 if noise_read else 12) * E,
+            "response": N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -173,7 +177,8 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("TARL_NCCL_DEBUG", "WARN")   # keep NCCL's banner off stdout (one JSON line)
+        # NCCL_DEBUG is left as the environment has it: whatever NCCL prints goes to stderr (fd 1 is pointed at
+        # stderr for the whole run, see __main__), the JSON line is written to the saved stdout
         dist.init_process_group("nccl", device_id=dev)
 
     g, Nmax, placed = synthetic.make_workload(args.workload, device=dev, t=T0, seed=rank, order=args.link_order)
@@ -184,11 +189,11 @@ def run_native(args):
     # aggregate (src/direction_mpnn.py:137). delta_travel_time[E] and the pop mask[N] are produced every step.
     store = LinkStore.from_graph(g, Nmax, replicas=args.replicas, seed=1234 + rank)
     R = args.replicas
-    delta_tt = torch.empty(R, E, dtype=torch.float32, device=dev)
     # Agents.choice re-draws SELECTED_ROAD for every link every step (src/agents/base.py:446-494); the draw itself is
     # not part of the core step, so a bank of pre-drawn decision vectors is cycled through as the step's input.
     sel_bank = [synthetic.random_out_neighbour(g, 1000 + 17 * rank + i).repeat(R) for i in range(8)]
     state = {"t": T0, "i": 0}
+    ell = args.variant == 0
 
     def use_bank(i):      # this step's routing decisions (a pointer swap when the store keeps link-id order)
         if store.slot_link is None:
@@ -198,7 +203,7 @@ def run_native(args):
 
     def step(mask=PHASE_SELECT_APPEND | PHASE_RESPOND_POP):
         use_bank(state["i"])
-        store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=mask, variant=args.variant)
+        store.step(state["t"], noise=None, delta_tt_link=True, pop_bits=True, phase_mask=mask, variant=args.variant)
         if mask & PHASE_RESPOND_POP:
             state["t"] += 1.0
             state["i"] += 1
@@ -212,7 +217,7 @@ def run_native(args):
 
     def run(n):     # n steps enqueued by one library call (tarl_store_run), routing decisions cycled from the bank
         bank = [sel_bank[(state["i"] + k) % len(sel_bank)] for k in range(len(sel_bank))]
-        store.run(state["t"], n, dt=1.0, sel_bank=bank, delta_tt=delta_tt, variant=args.variant)
+        store.run(state["t"], n, dt=1.0, sel_bank=bank, variant=args.variant, delta_tt_link=True, pop_bits=True)
         state["t"] += float(n)
         state["i"] += n
 
@@ -234,40 +239,42 @@ def run_native(args):
     store.check_errors()
 
     # ---- per-kernel durations (CUDA events on the launching stream) and the pop fraction p
-    names = {0: ["k_ell_select_append", "k_ell_respond_pop"], 1: ["k_csr_select_append", "k_csr_respond_pop"]}[args.variant]
+    names = ["k_ell_select_append", "k_ell_respond_pop"] if ell else ["k_csr_select_append", "k_csr_respond_pop"]
+    masks = [PHASE_SELECT_APPEND, PHASE_RESPOND_POP]
+    K = len(names)
     pairs = {k: 0.0 for k in names}
     reps = min(args.steps, 20)
     pops_dev = torch.zeros((), dtype=torch.int64, device=dev)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3 * reps)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range((K + 1) * reps)]
     for i in range(reps):          # (a) an event pair around every single launch: includes the launch gap of each
-        evs[3 * i].record(stream)
-        step(PHASE_SELECT_APPEND)
-        evs[3 * i + 1].record(stream)
-        step(PHASE_RESPOND_POP)
-        evs[3 * i + 2].record(stream)
+        for j in range(K):
+            evs[(K + 1) * i + j].record(stream)
+            step(masks[j])
+        evs[(K + 1) * i + K].record(stream)
         pops_dev += store.pop[: N * R].sum()
     torch.cuda.synchronize(dev)
     for i in range(reps):
-        pairs[names[0]] += evs[3 * i].elapsed_time(evs[3 * i + 1])
-        pairs[names[1]] += evs[3 * i + 1].elapsed_time(evs[3 * i + 2])
+        for j in range(K):
+            pairs[names[j]] += evs[(K + 1) * i + j].elapsed_time(evs[(K + 1) * i + j + 1])
     pops = int(pops_dev.item())
     p = pops / (reps * N * R)
     pairs = {k: v / reps for k, v in pairs.items()}
     # (b) the direction kernel alone, `reps` launches back to back between ONE event pair (it reads the current
-    # records and writes the other buffer, so repeating it on a fixed state repeats exactly the same traffic); the
-    # response kernel's share is what remains of the pipelined step. This is the per-launch duration the roofline uses.
+    # records and writes the other buffer, so repeating it on a fixed state repeats exactly the same traffic; the
+    # launches are captured in a CUDA graph and replayed, so that the host's per-call time — Python + ctypes, ~35 us,
+    # the same order as the kernel — is not part of what the event pair brackets). The response kernel's share is what
+    # remains of the pipelined step. This is the per-launch duration the roofline uses.
     use_bank(state["i"])
     for _ in range(3):
-        store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=PHASE_SELECT_APPEND, variant=args.variant)
+        store.step(state["t"], noise=None, delta_tt_link=True, pop_bits=True, phase_mask=PHASE_SELECT_APPEND, variant=args.variant)
     torch.cuda.synchronize(dev)
-    # the launches are captured in a CUDA graph and replayed, so that the host's per-call time (Python + ctypes,
-    # ~35 us, the same order as the kernel) is not part of what the event pair brackets
     side = torch.cuda.Stream(dev)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(side):
         with torch.cuda.graph(graph, stream=side):
             for _ in range(reps):
-                store.step(state["t"], noise=None, delta_tt=delta_tt, phase_mask=PHASE_SELECT_APPEND, variant=args.variant)
+                store.step(state["t"], noise=None, delta_tt_link=True, pop_bits=True, phase_mask=PHASE_SELECT_APPEND,
+                           variant=args.variant)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize(dev)
@@ -281,33 +288,48 @@ def run_native(args):
     per = {names[0]: sel_ms, names[1]: max(ms / args.steps - sel_ms, 0.0)}
     store.check_errors()
     peak, peak_src = peaks()
-    pb = {names[0]: R * (N * 52 + 16 * E),
-          names[1]: R * (N * 17 + 4 * E + p * N * (24 * (Nmax - 1) + 4))}
+    # algorithmic bytes per launch: SURVEY.md §8(d)'s per-unit figures, noise term dropped (drawn in-kernel)
+    ph = phase_bytes(N, E, Nmax, p)
+    pb = {names[0]: R * ph["direction"], names[1]: R * ph["response"]}
     dom = max(per, key=per.get)
     achieved = pb[dom] / (per[dom] / 1e3) / 1e9
     step_ms = ms / args.steps
     sb = R * step_bytes(N, E, Nmax, p)
+    # what this formulation has to move at the least: delta_tt is emitted per upstream LINK (4 N
+    # instead of 4 E; the [E] form is materialised by whoever reads it)
+    moved = {"direction": N * 56 + 8 * E, "response": ph["response"]}
+    traffic = measured_traffic(args.workload, R, dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": measured_traffic(args.workload, R, dom),
-                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
+                "frac": round(achieved / peak, 4), "traffic": traffic,
+                "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(pb[dom]), "kernel_ms": round(per[dom], 4),
+                "algorithmic_bytes_per_launch": int(pb[dom]),
+                "algorithmic_bytes_how": "SURVEY.md 8(d): direction 52 N + 12 E (noise drawn in-kernel: its 4 B/edge are "
+                                         "not counted), response 17 N + 4 E + p N (24 (Nmax-1) + 4)",
+                "kernel_ms": round(per[dom], 4),
                 "kernels_ms": {k: round(v, 4) for k, v in per.items()},
                 "kernels_ms_how": f"{names[0]}: {reps} launches captured in one CUDA graph, replayed between one CUDA-event "
                                   f"pair; {names[1]}: pipelined step time minus that",
                 "kernels_ms_event_pair_per_launch": {k: round(v, 4) for k, v in pairs.items()},
                 "pop_fraction": round(p, 4),
+                "dram_frac_of_measured_traffic": (round(traffic / (per[dom] / 1e3) / 1e9 / peak, 4)
+                                                  if traffic is not None else None),
                 "step": {"algorithmic_bytes": int(sb), "achieved": round(sb / (step_ms / 1e3) / 1e9, 1),
-                         "frac": round(sb / (step_ms / 1e3) / 1e9 / peak, 4)}}
+                         "frac": round(sb / (step_ms / 1e3) / 1e9 / peak, 4),
+                         "bytes_this_formulation_must_move": int(R * (moved["direction"] + moved["response"]))}}
 
-    # ---- end to end through the public drop-in API, host buffers both ways (in-place kernels on graph.x)
-    h = synthetic.FeatureHelpers(Nmax)
+    # ---- end to end through the public drop-in API, host buffers both ways
+    # SimulationCoreModel.forward keeps the road state in its resident link store while graph.x is not edited between
+    # calls (core.py); graph.x itself is brought up to date when somebody reads it (nobody does inside this loop, as
+    # nobody does inside TransportationSimulator.run between two metrics reads).
     store.export_x(out=g.x[:N].unsqueeze(0)) if R == 1 else g.x[:N].copy_(store.export_x()[0])
-    model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"])
+    model = SimulationCoreModel(Nmax=Nmax, device=str(dev), time=state["t"], resident="always", seed=4321 + rank)
+    model.pack_pop = True
+    words = (N + 31) // 32
     sel_hosts = [b[:N].cpu().pin_memory() for b in sel_bank]
     sel_devs = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
-    dtt_hosts = [torch.empty(E, dtype=torch.float32).pin_memory() for _ in range(2)]
-    pop_hosts = [torch.empty(N, dtype=torch.bool).pin_memory() for _ in range(2)]
+    dtt_hosts = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pop_hosts = [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(2)]
     e2e_steps = min(args.steps, 100)
     copy_stream = torch.cuda.Stream(dev)        # device -> host
     in_stream = torch.cuda.Stream(dev)          # host -> device (its own copy engine)
@@ -322,19 +344,16 @@ def run_native(args):
 
     def e2e_step():
         # Double-buffered pipeline around the public call: while step k computes on the main stream, the copy stream
-        # returns step k-1's outputs to the host and brings in step k+1's inputs. Every byte is still moved inside the
+        # returns step k-1's outputs to the host and brings in step k+2's inputs. Every byte is still moved inside the
         # timed region; the copies just overlap the kernels of the neighbouring steps.
         k = pending["k"]
         stream.wait_event(ev_in[k % 2])
         model.set_time(state["t"])
         model(g, selected_road=sel_devs[k % 2])
-        dtt = model.direction_mpnn.road_optimality_data["delta_travel_time"]
-        pop = model.last_pop
+        dtt = model.direction_mpnn.road_optimality_data["delta_travel_time_per_link"]
+        pop = model.last_pop_bits
         done = torch.cuda.Event()
         done.record(stream)
-        # inputs are staged TWO steps ahead, into the buffer step k has just finished reading: step k+1's decisions
-        # arrived while step k-1 ran, so no host-to-device copy sits between two steps' kernels (staging k+1 here put
-        # 0.08 ms of H2D on the critical path of every step: 0.40 ms/step where D2H alone needs 0.31)
         in_stream.wait_event(done)
         stage_inputs(k + 2)
         with torch.cuda.stream(copy_stream):
@@ -347,16 +366,15 @@ def run_native(args):
         state["t"] += 1.0
         state["i"] += 1
 
-    # Warm-up long enough for the caching allocator to reach its steady state (every step allocates delta_tt[E] and the
-    # pop mask, released through record_stream one step later), then several windows of e2e_steps; the MEDIAN window is
-    # reported and every window is listed: a single 40 ms window is at the mercy of one host hiccup (measured spread on
-    # otherwise identical boxes: 0.3 - 2.4 G link-steps/s with one window).
+    # Warm-up long enough for the caching allocator to reach its steady state, then several windows of e2e_steps; the
+    # MEDIAN window is reported and every window is listed (a single window is at the mercy of one host hiccup).
     stage_inputs(0)
     stage_inputs(1)
     for _ in range(20):
         e2e_step()
     copy_stream.synchronize()
     model.response_mpnn.update_history.resolve()
+    assert model.last_path == "resident"
     windows = []
     for _ in range(5):
         barrier()
@@ -373,24 +391,34 @@ def run_native(args):
     e2e_ms = statistics.median(windows)
     if os.environ.get("TARL_BENCH_DEBUG"):
         print(f"[rank {rank}] e2e windows (ms for {e2e_steps} steps): {[round(w, 2) for w in windows]}", file=sys.stderr)
-    model.response_mpnn.update_history.resolve()
+    # the [E] contract of road_optimality_data["delta_travel_time"] on the host side: expanding the per-link vector
+    # that crossed the bus with edge_index_routes[0] gives exactly what the device would have materialised
+    copy_stream.synchronize()
+    k_last = (pending["k"] - 1) % 2
+    full = model.direction_mpnn.road_optimality_data["delta_travel_time"]
+    contract_ok = bool(torch.equal(dtt_hosts[k_last][g.edge_index_routes[0].cpu()], full.cpu()))
     if world > 1:
         tms = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e_ms = float(tms.item())
     e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
-           "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(E * 4 + N),
-           "steps": e2e_steps, "windows_ms": [round(w, 3) for w in windows], "window": "median of 5", "api": "SimulationCoreModel.forward(graph, selected_road=...) on graph.x (reference row "
-           "layout, state resident on the device as with the reference's --device cuda); per step H2D = SELECTED_ROAD "
-           "decisions [N] from pinned memory, D2H = delta_travel_time[E] + pop mask[N] into pinned memory, double-buffered on copy "
-           "streams so that the copies of steps k-1 / k+2 overlap the kernels of step k; noise drawn on the device"}
+           "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4 + words * 4),
+           "steps": e2e_steps, "windows_ms": [round(w, 3) for w in windows], "window": "median of 5",
+           "kernel_path": model.last_path, "delta_tt_edge_form_reproduced_on_host": contract_ok,
+           "api": "SimulationCoreModel.forward(graph, selected_road=...): state resident on the device (link store "
+                  "behind graph.x, exported when graph.x is read); per step H2D = SELECTED_ROAD decisions [N] fp32 from "
+                  "pinned memory, D2H = delta_travel_time per upstream link [N] fp32 (the [E] vector of "
+                  "road_optimality_data is that value repeated on each out-edge: expanded on whichever side reads it) + "
+                  "pop mask as bits [N/8 bytes] into pinned memory, double-buffered on copy streams so that the copies "
+                  "of steps k-1 / k+2 overlap the kernels of step k; noise drawn on the device"}
 
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "links": N, "dual_edges": E, "agents": placed, "Nmax": Nmax,
                       "link_order": args.link_order, "replicas_per_gpu": R, "kernel_variant": {0: "ell", 1: "csr"}[args.variant], "parallelism": f"independent replicas x{world}",
-                      "state": "resident link store (tarl_store_step), noise drawn in-kernel, delta_tt + pop mask written every step",
+                      "state": "resident link store (tarl_store_run), noise drawn in-kernel; delta_travel_time per upstream "
+                               "link, pop mask (bytes) and pop bits written every step",
                       "l2": "per-step working set larger than the 126 MB L2" if N * R * 150 > 130e6 else
                       "per-step working set fits in L2 (small workload)"},
            "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clk.summary()}
@@ -710,9 +738,10 @@ def run_reference(args):
     name = args.workload
     budget_s = 150.0
     est = {"ring_radial_1m": 1.4, "grid100": 0.045}.get(name, 0.05)
-    steps, warm = args.steps, min(args.warmup, 2)
-    if (steps + warm) * est > budget_s:
-        steps = max(3, int(budget_s / est) - warm)
+    steps, warm = args.steps, args.warmup
+    if (steps + warm) * est > budget_s:      # a bounded sample: the CPU path needs ~0.3-1.6 s per 1M-link step
+        warm = min(warm, 2)
+        steps = max(3, min(steps, int(budget_s / est) - warm))
     t0 = time.perf_counter()
     cb = cpu_baseline(args, sample_steps=steps, warmup=warm, workload=name)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -720,7 +749,11 @@ def run_reference(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": name, "links": cb["links"], "dual_edges": cb["dual_edges"], "agents": cb["agents"],
                       "Nmax": cb["Nmax"], "link_order": getattr(args, "link_order", "node"), "replicas_per_gpu": 1,
-                      "state": "reference row layout on the host, noise injected per step (torch.rand outside the timed call)"},
+                      "kernel_variant": "cpu", "parallelism": "ONE CPU replica on rank 0 whatever --gpus is (the other "
+                                                              "ranks exit): only the N = 1 ratio is like for like",
+                      "state": "reference row layout on the host, noise injected per step (torch.rand outside the timed call)",
+                      "l2": "n/a (host)"},
+           "steps_requested": args.steps, "warmup_requested": args.warmup,
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": round(time.perf_counter() - t0, 1)}
     emit(out)

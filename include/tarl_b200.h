@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 17
+#define TARL_ABI_VERSION 18
 
 /* return codes */
 #define TARL_OK 0
@@ -157,7 +157,10 @@ int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stri
 
 /* Optional ELLPACK copy of the first `width` edges of every link, column-major: entry j of link n at [j*pitch + n].
  * -1 = no such edge. A link with MORE than `width` in-edges (out-edges) carries -2 in column width-1 of in_src
- * (out_dst) and is served from its CSR segment instead. Edge order inside a link is the CSR's (ascending edge id). */
+ * (out_dst) and is served from its CSR segment instead; so does — in in_src — a link with an in-edge whose
+ * edge_attr_routes is not >= 1e-3 (below that bound an INELIGIBLE edge can win the Gumbel arg-max of
+ * src/direction_mpnn.py:136-139, so the link needs the literal scan over every in-edge; the streaming kernel never
+ * decides such a link). Edge order inside a link is the CSR's (ascending edge id). */
 typedef struct tarl_dual_ell {
     int32_t width;          /* 4 or 8                                                        */
     int32_t pitch;          /* elements between consecutive columns, >= n_links               */
@@ -166,15 +169,44 @@ typedef struct tarl_dual_ell {
     const int32_t* out_dst; /* [width*pitch] downstream link of the j-th out-edge             */
 } tarl_dual_ell;
 
+/* Inputs and outputs of one store step (all device pointers, caller-owned).
+ * noise: [R*E] uniforms in original edge order per replica, or NULL to draw them in-kernel: Philox4x32-10 keyed by
+ *   `seed`, counter = (replica*N + link, 0, step_id, in-edge rank / 4), uniform number (in-edge rank % 4) of the block,
+ *   in-edge rank = position of the edge among the link's in-edges in ascending edge id — a documented stream of its
+ *   own, not torch's (the reference draws torch.rand_like at src/direction_mpnn.py:137; declared divergence D4).
+ *   tarl_store_noise writes that stream out in the [R*E] form, so that the CPU oracle can replay a step exactly.
+ * delta_tt_link: NULL or [R*N]: delta_travel_time (src/direction_mpnn.py:94-96) is a function of the UPSTREAM link of an
+ *   edge only, so the step emits one value per link; tarl_expand_delta_tt turns it into the reference's [E] vector.
+ * pop: [R*N] bytes (the mask of update_history). pop_bits: NULL or [R * ceil(N/32)] words, bit (n % 32) of word
+ *   r*ceil(N/32) + n/32 = pop[r, n] — the form that travels to the host. flags: TARL_FLAG_* words. */
+typedef struct tarl_step_io {
+    const float* noise;
+    uint64_t seed;
+    uint32_t step_id;
+    float t;
+    float* delta_tt_link;
+    uint8_t* pop;
+    uint32_t* pop_bits;
+    int32_t* flags;
+} tarl_step_io;
+
 /* SimulationCoreModel.forward on the store (src/simulation_core_model.py:41-83): reads hot_cur, writes hot_next.
  * ell: NULL (every link walks its CSR segment) or the ELLPACK copy above (same results, shorter dependent-load chain).
- * attr_in: edge_attr_routes permuted into g->in_* order. noise: [R*E] uniforms in original edge order per replica, or
- * NULL to draw them in-kernel (Philox4x32-10 keyed by seed, counter = (replica*N+link, 0, step_id, in-edge rank/4) — a
- * documented stream of its own, not torch's). delta_tt: [R*E] or NULL. pop: [R*N]. phase_mask: TARL_PHASE_SELECT_APPEND
- * | TARL_PHASE_RESPOND_SHIFT (both for a full step). */
+ * attr_in: edge_attr_routes permuted into g->in_* order. phase_mask: TARL_PHASE_SELECT_APPEND |
+ * TARL_PHASE_RESPOND_SHIFT (both for a full step). Two launches per step. */
 int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
-                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask);
+                    const float* attr_in, const tarl_step_io* io, void* stream, uint32_t phase_mask);
+
+/* The uniforms tarl_store_step(noise = NULL) uses for (seed, step_id), written out as [R*E] in original edge order:
+ * a step replayed with noise = that array is bit-identical to the step with the in-kernel stream, and the CPU oracle
+ * can be fed the same numbers (tests/test_store_replay_gpu.py). */
+int tarl_store_noise(const tarl_dual_csr* g, int32_t n_replicas, uint64_t seed, uint32_t step_id, float* noise,
+                     void* stream);
+
+/* road_optimality_data["delta_travel_time"] (src/direction_mpnn.py:94-99): out[r, e] = delta_tt_link[r, source link of
+ * e], original edge order. edge_src: [E] int32 = edge_index_routes[0]. */
+int tarl_expand_delta_tt(const int32_t* edge_src, int32_t n_edges, int32_t n_links, int32_t n_replicas,
+                         const float* delta_tt_link, float* delta_tt, void* stream);
 
 /* HOST-side helper (plain C++, host pointers): a locality order of the links for the store — clusters of `cluster`
  * links grown breadth-first over the dual graph (adj = CSR listing each link's in- and out-neighbours), emitted one
@@ -184,13 +216,13 @@ int tarl_cluster_links(int32_t n_links, const int32_t* adj_ptr, const int32_t* a
 
 /* n_steps consecutive steps enqueued by one call (times t0, t0+dt, ...; in-kernel noise; step ids first_step_id, +1,
  * ...): the loop SimulatorEnv.rollout / TransportationSimulator.run drive from Python, without a host round trip per
- * step. sel_bank: NULL/0 (SELECTED_ROAD stays as it is) or n_bank device arrays [R*N] cycled through as the routing
+ * step. io: first step's time (io->t) and step id, in-kernel noise only (io->noise must be NULL). sel_bank: NULL/0
+ * (SELECTED_ROAD stays as it is) or n_bank device arrays [R*N] cycled through as the routing
  * decisions of successive steps. hot_cur / hot_next alternate internally: after an odd n_steps the caller's two
- * buffers have swapped roles. delta_tt / pop hold the LAST step's outputs. */
+ * buffers have swapped roles. delta_tt_link / pop / pop_bits hold the LAST step's outputs. */
 int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                   const float* attr_in, uint64_t seed, uint32_t first_step_id, float t0, float dt, int32_t n_steps,
-                   const float* const* sel_bank, int32_t n_bank, float* delta_tt, uint8_t* pop, int32_t* flags,
-                   void* stream);
+                   const float* attr_in, const tarl_step_io* io, float dt, int32_t n_steps,
+                   const float* const* sel_bank, int32_t n_bank, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).
@@ -423,8 +455,7 @@ int tarl_agents_withdraw(const tarl_agent_state* state, const tarl_agent_table* 
  * of the two separate calls. ELLPACK topology and a store in link-id order only (TARL_E_BADARG otherwise: make the two
  * calls). withdrawn: [R*N] mask, counters: NULL or [R*2]. Follow with tarl_agents_insert(num_out, occupancy). */
 int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                             const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
-                             float* delta_tt, uint8_t* pop, int32_t* flags, const tarl_agent_table* agents,
+                             const float* attr_in, const tarl_step_io* io, const tarl_agent_table* agents,
                              const tarl_csr* adjacency, int32_t n_nodes, uint8_t* withdrawn, int32_t* counters,
                              float* num_out, int32_t* occupancy, void* stream);
 

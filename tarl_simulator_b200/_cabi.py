@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
+ABI_VERSION = 18       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -62,6 +63,12 @@ class LinkStore(C.Structure):
                 ("slot_link", C.c_void_p), ("link_slot", C.c_void_p)]
 
 
+class StepIO(C.Structure):
+    """struct tarl_step_io"""
+    _fields_ = [("noise", C.c_void_p), ("seed", C.c_uint64), ("step_id", C.c_uint32), ("t", C.c_float),
+                ("delta_tt_link", C.c_void_p), ("pop", C.c_void_p), ("pop_bits", C.c_void_p), ("flags", C.c_void_p)]
+
+
 class AgentState(C.Structure):
     """struct tarl_agent_state"""
     _fields_ = [("x", C.c_void_p), ("x_row_stride", C.c_int64), ("x_replica_stride", C.c_int64),
@@ -91,6 +98,7 @@ _AST = C.POINTER(AgentState)
 _ATB = C.POINTER(AgentTable)
 _AIX = C.POINTER(AgentIndex)
 _ROWS = C.POINTER(Rows)
+_SIO = C.POINTER(StepIO)
 
 # name -> (restype, argtypes); the single source of truth checked against include/tarl_b200.h by the tests
 SIGNATURES = {
@@ -103,11 +111,12 @@ SIGNATURES = {
     "tarl_core_step_phases": (C.c_int, [_CSR, _P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P, _P, _SZ, _P, C.c_uint32]),
     "tarl_store_import": (C.c_int, [_STORE, _P, _I64, _I64, _P, _P, _P]),
     "tarl_store_export": (C.c_int, [_STORE, _P, _I64, _I64, _F, _P]),
-    "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _P, C.c_uint32]),
-    "tarl_store_step_withdraw": (C.c_int, [_CSR, _ELL, _STORE, _P, _P, C.c_uint64, C.c_uint32, _F, _P, _P, _P, _ATB, _CSR1, _I32,
-                                           _P, _P, _P, _P, _P]),
+    "tarl_store_step": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _P, C.c_uint32]),
+    "tarl_store_noise": (C.c_int, [_CSR, _I32, C.c_uint64, C.c_uint32, _P, _P]),
+    "tarl_expand_delta_tt": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P]),
+    "tarl_store_step_withdraw": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _ATB, _CSR1, _I32, _P, _P, _P, _P, _P]),
     "tarl_cluster_links": (C.c_int, [_I32, _P, _P, _I32, _P]),
-    "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, C.c_uint64, C.c_uint32, _F, _F, _I32, _P, _I32, _P, _P, _P, _P]),
+    "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _F, _I32, _P, _I32, _P]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_backward": (C.c_int, [_CSR1, _ROWS, _P, _I32, _P, _P, _I32, _P]),
     "tarl_graphdist_partial_count": (_I32, [_I32, _I32]),

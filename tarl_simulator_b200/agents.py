@@ -97,8 +97,12 @@ def side_tables_for(graph) -> GraphSideTables:
 
 
 def rows_state(graph, Nmax: int, with_cc: bool = True) -> _cabi.AgentState:
-    """struct tarl_agent_state for the reference row layout of graph.x ([N_tot, F] or [R, N_tot, F])."""
+    """struct tarl_agent_state for the reference row layout of graph.x ([N_tot, F] or [R, N_tot, F]). Every caller
+    hands the raw pointer to a kernel that writes the rows: the graph is told (Data.rows_written) so that a resident
+    link store shadowing them (core.py) knows its copy is stale."""
     x = graph.x
+    if hasattr(graph, "rows_written"):
+        graph.rows_written()
     if not x.is_cuda:
         raise RuntimeError("tarl_simulator_b200 computes on CUDA devices only (no CPU fallback): move graph.x to cuda")
     F = 3 * Nmax + 7

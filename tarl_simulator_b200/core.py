@@ -2,8 +2,17 @@
 
 Drop-in for src/simulation_core_model.py, src/direction_mpnn.py and src/response_mpnn.py of the reference: same class
 names, constructor arguments, `forward` signatures, side outputs (`road_optimality_data["delta_travel_time"]`,
-`update_history`) and in-place mutation of `graph.x[:num_roads]`. The arithmetic is three CUDA kernels behind the C
-ABI (csrc/core_step.cu); there is no PyTorch or CPU implementation of it in this package.
+`update_history`) and mutation of `graph.x[:num_roads]`. The arithmetic is CUDA kernels behind the C ABI; there is no
+PyTorch or CPU implementation of it in this package.
+
+Two kernel families serve `SimulationCoreModel.forward(graph)`, bit-identical in what they leave in `graph.x`:
+  * in place on the reference's rows (csrc/core_step.cu) — when `graph.x` was edited since the previous call (the
+    classical loop edits it three times per step: insert, withdraw, choice), or for graphs that are not this package's
+    `Data`;
+  * the resident link store (csrc/engine.cu, ~1x the algorithmic bytes instead of ~3.5x) — when consecutive calls find
+    `graph.x` untouched: the state then lives in the store and `graph.x` is brought up to date when it is next READ
+    (`Data.x` is a property, data.py), so a loop of `model(graph, selected_road=...)` calls never pays for rows nobody
+    looks at. `resident="never"` / `"always"` pin the choice.
 """
 from __future__ import annotations
 
@@ -15,6 +24,7 @@ import torch.nn as nn
 
 from . import _cabi
 from ._arena import StepArena as _StepArena
+from .data import Data
 from .feature_helpers import FeatureHelpers
 from .message_passing import MessagePassing
 from .topology import topology_for
@@ -224,6 +234,78 @@ def _sel_ptr(sel, N, dev):
     return sel.data_ptr()
 
 
+class LazyOptimality(dict):
+    """`DirectionMPNN.road_optimality_data` of a step taken on the link store. delta_travel_time
+    (src/direction_mpnn.py:94-99) depends on the UPSTREAM link of a dual edge only, so the step emits one value per
+    link — key "delta_travel_time_per_link", fp32 [N] — and the reference's [E] vector in original edge order, key
+    "delta_travel_time", is materialised (one gather launch, then cached) when it is first asked for."""
+
+    def __init__(self, store, per_link: torch.Tensor):
+        super().__init__()
+        self._store = store
+        dict.__setitem__(self, "delta_travel_time_per_link", per_link)
+
+    def __missing__(self, key):
+        if key != "delta_travel_time":
+            raise KeyError(key)
+        per_link = dict.__getitem__(self, "delta_travel_time_per_link")
+        store, self._store = self._store, None
+        full = store.expand_delta_tt(per_link=per_link).view(-1)
+        dict.__setitem__(self, key, full)
+        return full
+
+    def __contains__(self, key):
+        return key == "delta_travel_time" or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return list(dict.keys(self) | {"delta_travel_time"})
+
+
+class _ResidentRows:
+    """The road rows of one graph held in a LinkStore between forward calls (attached to the graph as `_resident`).
+    `dirty`: the store is ahead of graph.x (Data.x exports on the next read). The signature (tensor identity, data
+    pointer, version counter, raw-write epoch) tells whether graph.x changed behind the store's back."""
+
+    def __init__(self, graph, Nmax: int, seed: int):
+        self.graph_ref = graph
+        self.N, self.Nmax, self.seed = int(graph.num_roads), int(Nmax), int(seed)
+        self.store = None             # built on the first load(): the classical loop never needs one
+        self.topology_key = (id(graph.edge_index_routes), graph.edge_index_routes._version,
+                             id(graph.edge_attr_routes), graph.edge_attr_routes._version)
+        self.dirty = False
+        self.loaded = None            # signature of graph.x the store's content corresponds to
+        self.seen = None              # signature of graph.x at the end of the latest forward (either kernel family)
+
+    @staticmethod
+    def signature(graph):
+        x = graph.__dict__["_x"]
+        return (id(x), x.data_ptr(), x._version, graph.__dict__.get("_rows_epoch", 0))
+
+    def load(self, graph):
+        x = graph.__dict__["_x"]
+        if self.store is None:
+            from .engine import LinkStore
+            self.store = LinkStore(graph.edge_index_routes, graph.edge_attr_routes, self.N, self.Nmax, 1, x.device,
+                                   self.seed)
+        has_static = hasattr(graph, "critical_number") and hasattr(graph, "congestion_constant")
+        self.store.import_x(x[: self.N], graph.congestion_constant[: self.N] if has_static else None)
+        self.loaded = self.signature(graph)
+        self.dirty = False
+
+    def sync_rows(self):
+        """graph.x <- store (exact, every cell). Runs on torch's current stream, like everything else here."""
+        g = self.graph_ref
+        x = g.__dict__["_x"]
+        if self.signature(g) != self.loaded:
+            raise RuntimeError("graph.x was modified through an alias while its rows lived in the resident link store; "
+                               "read graph.x (which synchronises it) before writing, or use resident='never'")
+        self.store.export_x(out=x[: self.N])
+        self.dirty = False
+
+
 class SimulationCoreModel(nn.Module):
     """One network timestep on the road sub-graph (src/simulation_core_model.py:10-88): DirectionMPNN then
     ResponseMPNN, in place on `graph.x[:graph.num_roads]`. Insertion and withdrawal of agents are not part of it.
@@ -231,14 +313,24 @@ class SimulationCoreModel(nn.Module):
     Parameters mirror the reference: `Nmax`, `device`, `time`, `torch_compile` (accepted and ignored: there is no
     tracing compiler on this path). `forward(graph, noise=None)` additionally accepts the E uniforms to inject."""
 
-    def __init__(self, Nmax: int, device: str, time: int, torch_compile: bool = False):
+    def __init__(self, Nmax: int, device: str, time: int, torch_compile: bool = False, resident: str = "auto",
+                 seed: int = 0):
+        """resident: "auto" (see the module docstring), "always", "never". seed: keys the in-kernel noise stream of
+        resident steps taken without injected noise (the in-place kernels draw torch.rand on the device instead)."""
         super().__init__()
+        if resident not in ("auto", "always", "never"):
+            raise ValueError("resident must be 'auto', 'always' or 'never'")
         self.direction_mpnn = DirectionMPNN(Nmax=Nmax, time=time)
         self.response_mpnn = ResponseMPNN(Nmax=Nmax, time=time)
         self.time = time
         self.Nmax = Nmax
         self.device = device
+        self.resident = resident
+        self.seed = int(seed)
+        self.pack_pop = False           # True: resident steps also leave the pop mask as bits in last_pop_bits
         self.last_pop = None            # bool[N] of the latest step (device), whether or not it joined the history
+        self.last_pop_bits = None       # int32[ceil(N/32)] of the latest resident step when pack_pop is set
+        self.last_path = None           # "resident" / "inplace": which kernel family served the latest call
         self._scratch = _Scratch()
         self._arena = _StepArena()
 
@@ -251,6 +343,9 @@ class SimulationCoreModel(nn.Module):
         """`selected_road` (optional, fp32 [N] on the device): this step's SELECTED_ROAD column, applied inside the
         first kernel instead of by a separate strided write into graph.x beforehand."""
         N = int(graph.num_roads)
+        rs = self._resident_for(graph, N)
+        if rs is not None:
+            return self._forward_resident(graph, rs, N, noise, selected_road)
         x_roads = graph.x[:N]                       # a view: every write lands in graph.x (reference :52,:81)
         _require_cuda_rows(x_roads, self.Nmax)
         ei = graph.edge_index_routes
@@ -276,6 +371,70 @@ class SimulationCoreModel(nn.Module):
         self.direction_mpnn._flags = flags
         self.response_mpnn.update_history.push(self.time, pop, flags)
         self.last_pop = pop
+        self.last_path = "inplace"
+        if isinstance(graph, Data):
+            graph.rows_written()
+            r = graph.__dict__.get("_resident")
+            if r is not None:
+                r.seen = r.signature(graph)
+        return graph
+
+    # ------------------------------------------------------------------------------------------ resident link store
+    def _resident_for(self, graph, N: int):
+        """The graph's _ResidentRows if this call is to run on the link store, else None (in-place kernels)."""
+        if self.resident == "never" or not isinstance(graph, Data) or N == 0 or "_x" not in graph.__dict__:
+            return None
+        x = graph.__dict__["_x"]
+        if not x.is_cuda or x.dim() != 2:
+            return None                                       # the in-place path raises the proper error
+        rs = graph.__dict__.get("_resident")
+        key = (id(graph.edge_index_routes), graph.edge_index_routes._version,
+               id(graph.edge_attr_routes), graph.edge_attr_routes._version)
+        if rs is not None and (rs.Nmax != self.Nmax or rs.topology_key != key or rs.N != N):
+            if rs.dirty:
+                rs.sync_rows()
+            rs = None
+            graph.__dict__.pop("_resident", None)
+        if rs is None:
+            _require_cuda_rows(x[:N], self.Nmax)
+            rs = _ResidentRows(graph, self.Nmax, self.seed)
+            graph.__dict__["_resident"] = rs
+        sig = rs.signature(graph)
+        if rs.dirty:
+            if sig != rs.loaded:
+                rs.sync_rows()                                # raises: written through an alias
+            return rs                                         # the store is ahead of x and x is untouched: keep going
+        if sig == rs.loaded:
+            return rs                                         # x was read (exported) but not written since
+        if self.resident == "always" or sig == rs.seen:       # untouched since the previous call: move in
+            rs.load(graph)
+            return rs
+        return None                                           # edited between calls: in place this time
+
+    def _forward_resident(self, graph, rs, N, noise, selected_road):
+        store = rs.store
+        dev = store.device
+        if selected_road is not None:
+            if selected_road.dtype != torch.float32 or selected_road.device != dev or selected_road.numel() != N:
+                raise ValueError("selected_road must be a fp32 [N] tensor on x's device")
+            store.sel[:N].copy_(selected_road.reshape(-1), non_blocking=True)
+        if noise is not None:
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+            if noise.numel() != store.E:
+                raise ValueError("noise must hold one uniform per dual edge")
+        pop, flags = self._arena.take(N, dev)
+        out = {"pop": pop, "flags": flags, "delta_tt_link": torch.empty(N, dtype=torch.float32, device=dev)}
+        if self.pack_pop:
+            out["pop_bits"] = torch.empty(store.words, dtype=torch.int32, device=dev)
+        store.step(float(self.time), noise=noise, out=out)
+        rs.dirty = True
+        rs.seen = rs.loaded
+        self.direction_mpnn.road_optimality_data = LazyOptimality(store, out["delta_tt_link"])
+        self.direction_mpnn._flags = flags
+        self.response_mpnn.update_history.push(self.time, pop, flags)
+        self.last_pop = pop
+        self.last_pop_bits = out.get("pop_bits")
+        self.last_path = "resident"
         return graph
 
     def check_errors(self):

@@ -33,6 +33,7 @@
 
 using namespace tarl;
 
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------ import / export
@@ -173,11 +174,11 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
 }
 
 // Tail append on the link's own record (src/direction_mpnn.py:171-195, on EVERY link), the {NUM, tail id} summary the
-// response phase gathers, delta_travel_time for the link's out-edges (:94-96, from the PRE-step head), and the pop hint
-// for the upstream link whose head was admitted here.
-__device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const Store& s, int r, int n, int L, float4 hA,
-                                                   float4 hB, const float4 st, const Pick pk, float t,
-                                                   float* __restrict__ delta_tt, int k_out0, int k_out1,
+// response phase gathers, delta_travel_time of the link's head (:94-96, from the PRE-step state: ONE value per upstream
+// link — every out-edge of the link carries the same number, tarl_expand_delta_tt materialises the [E] form), and the
+// pop hint for the upstream link whose head was admitted here.
+__device__ __forceinline__ void append_and_publish(const Store& s, int L, float4 hA, float4 hB, const float4 st,
+                                                   const Pick pk, float t, float* __restrict__ dtt_link,
                                                    int32_t* __restrict__ flags) {
     const float num = hA.z, maxn = hA.w, fftt = st.x;
     int meta = __float_as_int(hB.w);
@@ -187,11 +188,7 @@ __device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const
         if (!pk.have) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_NO_WINNER);
         else chosen = pk.id;
     }
-    if (delta_tt != nullptr) {
-        const float dtt = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);
-        float* out = delta_tt + (int64_t)r * g.n_edges;
-        for (int k = k_out0; k < k_out1; ++k) out[g.out_eid != nullptr ? g.out_eid[k] : k] = dtt;
-    }
+    if (dtt_link != nullptr) dtt_link[L] = max_propagate_nan((hA.y - hB.x) - fftt, 0.0f);
     float num_post = num, tail_post = hB.y;
     if (bad) {
         atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_QUEUE_RANGE);
@@ -222,29 +219,56 @@ __device__ __forceinline__ void append_and_publish(const tarl_dual_csr& g, const
     s.post[L] = make_float2(num_post, tail_post);
 }
 
+// The general form of the direction phase for one link: in-edge scan out of the CSR (any degree, any edge weight, any
+// noise), arg-max, append. The CSR kernels run it on every link; the ELL kernels on the links their columns cannot describe.
 template <bool kExtNoise>
-__global__ void __launch_bounds__(kThreads) k_csr_select_append(tarl_dual_csr g, Store s,
-                                                                const float* __restrict__ attr_in, Noise nz, float t,
-                                                                float* __restrict__ delta_tt,
+__device__ __noinline__ void select_append_general(const tarl_dual_csr& g, const Store& s,
+                                                   const float* __restrict__ attr_in, const Noise& nz, float t,
+                                                   float* __restrict__ dtt_link, int32_t* __restrict__ flags, int r,
+                                                   int d, int L) {
+    const float4 hA = s.hot_cur[2 * (size_t)L], hB = s.hot_cur[2 * (size_t)L + 1];
+    const float4 st = s.stat_a[d];
+    const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
+    append_and_publish(s, L, hA, hB, st, pk, t, dtt_link, flags);
+}
+
+template <bool kExtNoise>
+__global__ void __launch_bounds__(kThreads) k_csr_select_append(const __grid_constant__ tarl_dual_csr g,
+                                                                const __grid_constant__ Store s,
+                                                                const float* __restrict__ attr_in,
+                                                                const __grid_constant__ Noise nz, float t,
+                                                                float* __restrict__ dtt_link,
                                                                 int32_t* __restrict__ flags) {
     pdl_trigger();
     pdl_wait();
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
     const int r = blockIdx.y;
-    const int L = r * s.N + d;
-    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
-    const float4 st = s.stat_a[d];
-    int k_out0 = 0, k_out1 = 0;
-    if (delta_tt != nullptr) { k_out0 = g.out_ptr[d]; k_out1 = g.out_ptr[d + 1]; }
-    const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
-    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, k_out0, k_out1, flags);
+    select_append_general<kExtNoise>(g, s, attr_in, nz, t, dtt_link, flags, r, d, r * s.N + d);
 }
 
+// The streaming form: one thread per link, the first W in-edges out of the ELLPACK columns.
+//   level 1 (addressed by the link id alone): statics, W upstream ids and edge weights before the dependency wait, own
+//            record after it;
+//   level 2: W gathers of upstream A-halves + SELECTED_ROAD, all in flight together.
+// Eligibility p_e (src/direction_mpnn.py:81-91), probability sum in ascending edge id, and — only where the sum is
+// positive — the pick. With uniforms in [2^-24, 1-2^-24] and eligible weights >= 1e-3 an ineligible edge can never beat
+// an eligible one (see kSafe* above): a lone eligible edge wins without noise or logf, several eligible edges draw Philox
+// uniforms and compare Gumbel scores among themselves. Links whose in-edges do not fit the W columns, or carry a weight
+// outside the safe bounds, have -2 in column W-1 (topology.py) and walk their CSR segment (the literal scan).
+// (Measured and rejected in round 2: listing the contested links — 10 % of the links at bench load, present in 97 % of the
+// warps — for a second, dense kernel. The streaming kernel loses a third of its instructions and 16 registers but not a
+// microsecond — it is bound by its two dependent load levels, not by issue slots or occupancy — and the second kernel
+// adds a third dependent launch to the step: 61 -> 68 us per step.)
+#ifndef TARL_SELECT_MINBLOCKS
+#define TARL_SELECT_MINBLOCKS 9      // resident CTAs per SM the W = 4 kernel is compiled for (56 registers, no spills)
+#endif
 template <int W, bool kExtNoise>
-__global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g, tarl_dual_ell ell, Store s,
-                                                                const float* __restrict__ attr_in, Noise nz, float t,
-                                                                float* __restrict__ delta_tt,
+__global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) k_ell_select_append(const __grid_constant__ tarl_dual_csr g,
+                                                                tarl_dual_ell ell, const __grid_constant__ Store s,
+                                                                const float* __restrict__ attr_in,
+                                                                const __grid_constant__ Noise nz, float t,
+                                                                float* __restrict__ dtt_link,
                                                                 int32_t* __restrict__ flags) {
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
@@ -261,73 +285,72 @@ __global__ void __launch_bounds__(kThreads) k_ell_select_append(tarl_dual_csr g,
         u[j] = ell.in_src[(size_t)j * ell.pitch + d];
         a[j] = ell.in_attr[(size_t)j * ell.pitch + d];
     }
-    int k_out0 = 0, k_out1 = 0;
-    if (delta_tt != nullptr) { k_out0 = g.out_ptr[d]; k_out1 = g.out_ptr[d + 1]; }
     pdl_wait();
-    const float4 hA = s.hot_cur[2 * L], hB = s.hot_cur[2 * L + 1];
+    if (u[W - 1] == -2) {     // more than W in-edges or an unsafe weight: this link walks its CSR segment instead
+        select_append_general<kExtNoise>(g, s, attr_in, nz, t, dtt_link, flags, r, d, L);
+        return;
+    }
+    const float4 hA = s.hot_cur[2 * (size_t)L], hB = s.hot_cur[2 * (size_t)L + 1];
     const bool free_d = hA.z < (hA.w - 3.0f);
     const float room_d = hA.w - hA.z, ridx_d = st.z;
     Pick pk = {0.0f, 0.0f, -1, false};
-    if (u[W - 1] == -2) {     // more than W in-edges: this link walks its CSR segment instead
-        pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, free_d, room_d, ridx_d);
-    } else {
-        // level 2: the neighbours' records, all gathers in flight together
-        float4 U[W];
-        float S[W];
+    // level 2: the neighbours' records, all gathers in flight together
+    float4 U[W];
+    float S[W];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            if (u[j] >= 0) {
-                U[j] = s.hot_cur[2 * (base + u[j])];
-                S[j] = s.sel[base + u[j]];
-            }
+    for (int j = 0; j < W; ++j) {
+        if (u[j] >= 0) {
+#ifdef TARL_ABLATE_GATHER       // tuning only (wrong results): what would the kernel cost without its second load level?
+            U[j] = hA; S[j] = st.z + (float)j;
+#else
+            U[j] = s.hot_cur[2 * (size_t)(base + u[j])];
+            S[j] = s.sel[base + u[j]];
+#endif
         }
-        float p[W];
-        int n_elig = 0, lone = 0;
+    }
+    float p[W];
+    int n_elig = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        p[j] = 0.0f;
+        if (u[j] >= 0) {
+            p[j] = edge_prob(U[j], S[j], t, free_d, room_d, ridx_d, a[j]);
+            pk.psum += p[j];
+            if (p[j] > 0.0f) { ++n_elig; pk.id = U[j].x; pk.src = base + u[j]; }
+        }
+    }
+    if (pk.psum > 0.0f) {
         bool safe = true;
+        float uu[W];
+        if (kExtNoise) {          // injected uniforms may lie outside the safe interval
+            const int k0 = g.in_ptr[d];
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            p[j] = 0.0f;
-            if (u[j] >= 0) {
-                p[j] = edge_prob(U[j], S[j], t, free_d, room_d, ridx_d, a[j]);
-                pk.psum += p[j];
-                if (p[j] > 0.0f) { ++n_elig; lone = j; safe = safe && (a[j] >= kSafeAttr); }
-            }
-        }
-        if (pk.psum > 0.0f) {
-            float uu[W];
-            if (kExtNoise) {
-                const int k0 = g.in_ptr[d];
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    uu[j] = 0.5f;
-                    if (u[j] >= 0) {
-                        uu[j] = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k0 + j]];
-                        safe = safe && (uu[j] >= kSafeULo) && (uu[j] <= kSafeUHi);
-                    }
+            for (int j = 0; j < W; ++j) {
+                uu[j] = 0.5f;
+                if (u[j] >= 0) {
+                    uu[j] = nz.ext[(int64_t)r * g.n_edges + g.in_eid[k0 + j]];
+                    safe = safe && (uu[j] >= kSafeULo) && (uu[j] <= kSafeUHi);
                 }
             }
-            if (safe && n_elig == 1) {
+        }
+        if (safe && n_elig == 1) {
+            pk.have = true;       // a lone eligible edge wins without noise
+        } else {
+            float best = -FLT_MAX;
+            float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+            pk.src = -1;
 #pragma unroll
-                for (int j = 0; j < W; ++j)
-                    if (j == lone) { pk.id = U[j].x; pk.src = base + u[j]; }
-                pk.have = true;
-            } else {
-                float best = -FLT_MAX;
-                float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    if (!kExtNoise && (j & 3) == 0)
-                        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
-                    if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
-                        const float v = kExtNoise ? uu[j] : un[j & 3];
-                        const float sc = gumbel_score(p[j], v);
-                        if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
-                    }
+            for (int j = 0; j < W; ++j) {
+                if (!kExtNoise && (j & 3) == 0)
+                    philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+                if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
+                    const float sc = gumbel_score(p[j], kExtNoise ? uu[j] : un[j & 3]);
+                    if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
                 }
             }
         }
     }
-    append_and_publish(g, s, r, d, L, hA, hB, st, pk, t, delta_tt, k_out0, k_out1, flags);
+    append_and_publish(s, L, hA, hB, st, pk, t, dtt_link, flags);
 }
 
 // ------------------------------------------------------------------------------------------------ response phase
@@ -373,8 +396,16 @@ __device__ __noinline__ bool scan_out_edges_csr(const tarl_dual_csr& g, const St
     return accept;
 }
 
+// bit (u % 32) of word r*ceil(N/32) + u/32 = pop[r, u]: one ballot and one store per warp (kThreads % 32 == 0, so a
+// warp never straddles two words)
+__device__ __forceinline__ void publish_pop_bits(uint32_t* __restrict__ pop_bits, bool accept, int r, int u, int N) {
+    const unsigned m = __ballot_sync(0xffffffffu, accept);
+    if (pop_bits != nullptr && (threadIdx.x & 31) == 0 && u < N) pop_bits[r * ((N + 31) >> 5) + (u >> 5)] = m;
+}
+
 __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, Store s, float t,
-                                                              uint8_t* __restrict__ pop, int32_t* __restrict__ flags) {
+                                                              uint8_t* __restrict__ pop, uint32_t* __restrict__ pop_bits,
+                                                              int32_t* __restrict__ flags) {
     pdl_trigger();
     pdl_wait();
     const int u = blockIdx.x * kThreads + threadIdx.x;
@@ -389,13 +420,15 @@ __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, S
         accept = scan_out_edges_csr(g, s, base, u, A);
         pop[L] = accept ? 1 : 0;
     }
+    publish_pop_bits(pop_bits, accept, r, u, s.N);
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     if (accept) pop_head(s, L, A, B, t, false, A, A);
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
-                                                              uint8_t* __restrict__ pop, int32_t* __restrict__ flags) {
+__global__ void __launch_bounds__(kThreads, W == 4 ? 16 : 1) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
+                                                              uint8_t* __restrict__ pop, uint32_t* __restrict__ pop_bits,
+                                                              int32_t* __restrict__ flags) {
     const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     const int base = r * s.N;
@@ -435,6 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop(tarl_dual_csr g, t
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     if (accept) pop_head(s, L, A, B, t, fetched, q_head, q_last);
+    publish_pop_bits(pop_bits, accept, r, u, s.N);      // last: nothing else is live any more
 }
 
 // ---------------------------------------------------------------- response phase + withdrawal + occupancy observation
@@ -467,6 +501,7 @@ template <int W>
 __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual_csr g, tarl_dual_ell ell,
                                                                        const __grid_constant__ Store s, float t,
                                                                        uint8_t* __restrict__ pop,
+                                                                       uint32_t* __restrict__ pop_bits,
                                                                        int32_t* __restrict__ flags,
                                                                        const __grid_constant__ WithdrawArgs wa) {
     // (__grid_constant__: the rare path takes `s` and `wa` by reference; without it every thread would first copy both
@@ -506,6 +541,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
         if (hinted) s.hint[L] = 0;
         pop[L] = accept ? 1 : 0;
     }
+    publish_pop_bits(pop_bits, accept, r, u, s.N);
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     float head_exit = A.y, num = A.z;
     if (accept) { head_exit = pop_head(s, L, A, B, t, fetched, q_head, q_last); num = A.z - 1.0f; }
@@ -596,12 +632,12 @@ int tarl_store_export(const tarl_link_store* store, float* x, int64_t x_row_stri
 namespace {
 
 int check_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s, const float* attr_in,
-               const float* noise, const uint8_t* pop, const int32_t* flags) {
-    if (g == nullptr || flags == nullptr || g->n_links != s.N) return TARL_E_BADARG;
+               const tarl_step_io* io) {
+    if (g == nullptr || io == nullptr || io->flags == nullptr || g->n_links != s.N) return TARL_E_BADARG;
     if (s.N == 0) return TARL_OK;
-    if (pop == nullptr || g->in_ptr == nullptr || g->out_ptr == nullptr) return TARL_E_BADARG;
+    if (io->pop == nullptr || g->in_ptr == nullptr || g->out_ptr == nullptr) return TARL_E_BADARG;
     if (g->n_edges > 0 && (attr_in == nullptr || g->in_src == nullptr || g->out_dst == nullptr)) return TARL_E_BADARG;
-    if (noise != nullptr && g->n_edges > 0 && g->in_eid == nullptr) return TARL_E_BADARG;
+    if (io->noise != nullptr && g->n_edges > 0 && g->in_eid == nullptr) return TARL_E_BADARG;
     if (ell != nullptr) {
         if ((ell->width != 4 && ell->width != 8) || ell->pitch < s.N) return TARL_E_BADARG;
         if (!ell->in_src || !ell->in_attr || !ell->out_dst) return TARL_E_BADARG;
@@ -610,53 +646,96 @@ int check_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s,
 }
 
 void launch_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s, const float* attr_in,
-                 const Noise& nz, float t, float* delta_tt, uint8_t* pop, int32_t* flags, cudaStream_t cs,
-                 uint32_t phase_mask) {
+                 const tarl_step_io& io, cudaStream_t cs, uint32_t phase_mask) {
     const dim3 grid(blocks_for(s.N), s.R);
+    const Noise nz = {io.noise, (uint32_t)io.seed, (uint32_t)(io.seed >> 32), io.step_id};
     const bool ext = nz.ext != nullptr;
+    const float t = io.t;
+    float* dtt = io.delta_tt_link;
+    int32_t* flags = io.flags;
     if (phase_mask & TARL_PHASE_SELECT_APPEND) {
         if (ell == nullptr) {
-            if (ext) launch_pdl(k_csr_select_append<true>, grid, cs, *g, s, attr_in, nz, t, delta_tt, flags);
-            else launch_pdl(k_csr_select_append<false>, grid, cs, *g, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_csr_select_append<true>, grid, cs, *g, s, attr_in, nz, t, dtt, flags);
+            else launch_pdl(k_csr_select_append<false>, grid, cs, *g, s, attr_in, nz, t, dtt, flags);
         } else if (ell->width == 4) {
-            if (ext) launch_pdl(k_ell_select_append<4, true>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
-            else launch_pdl(k_ell_select_append<4, false>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_ell_select_append<4, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
+            else launch_pdl(k_ell_select_append<4, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
         } else {
-            if (ext) launch_pdl(k_ell_select_append<8, true>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
-            else launch_pdl(k_ell_select_append<8, false>, grid, cs, *g, *ell, s, attr_in, nz, t, delta_tt, flags);
+            if (ext) launch_pdl(k_ell_select_append<8, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
+            else launch_pdl(k_ell_select_append<8, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
         }
     }
     if (phase_mask & TARL_PHASE_RESPOND_SHIFT) {
-        if (ell == nullptr) launch_pdl(k_csr_respond_pop, grid, cs, *g, s, t, pop, flags);
-        else if (ell->width == 4) launch_pdl(k_ell_respond_pop<4>, grid, cs, *g, *ell, s, t, pop, flags);
-        else launch_pdl(k_ell_respond_pop<8>, grid, cs, *g, *ell, s, t, pop, flags);
+        if (ell == nullptr) launch_pdl(k_csr_respond_pop, grid, cs, *g, s, t, io.pop, io.pop_bits, flags);
+        else if (ell->width == 4) launch_pdl(k_ell_respond_pop<4>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags);
+        else launch_pdl(k_ell_respond_pop<8>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags);
     }
+}
+
+// ---------------------------------------------------------------------------------------------- noise / delta_tt forms
+__global__ void __launch_bounds__(kThreads) k_store_noise(tarl_dual_csr g, int R, uint32_t seed_lo, uint32_t seed_hi,
+                                                          uint32_t step_id, float* __restrict__ out) {
+    const int d = blockIdx.x * kThreads + threadIdx.x;
+    if (d >= g.n_links) return;
+    const int r = blockIdx.y;
+    const int L = r * g.n_links + d;
+    const Noise nz = {nullptr, seed_lo, seed_hi, step_id};
+    float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
+    int grp = -1;
+    const int k0 = g.in_ptr[d], k1 = g.in_ptr[d + 1];
+    for (int k = k0; k < k1; ++k)
+        out[(int64_t)r * g.n_edges + g.in_eid[k]] = philox_uniform(nz, L, k - k0, un, grp);
+}
+
+__global__ void __launch_bounds__(256) k_expand_delta_tt(const int32_t* __restrict__ edge_src, int E, int N,
+                                                         const float* __restrict__ dtt_link, float* __restrict__ out) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= E) return;
+    const int r = blockIdx.y;
+    out[(int64_t)r * E + e] = dtt_link[(int64_t)r * N + edge_src[e]];
 }
 
 }  // namespace
 
 int tarl_store_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                    const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
-                    float* delta_tt, uint8_t* pop, int32_t* flags, void* stream, uint32_t phase_mask) {
+                    const float* attr_in, const tarl_step_io* io, void* stream, uint32_t phase_mask) {
     Store s;
     int rc = make_store(store, &s);
     if (rc != TARL_OK) return rc;
-    if ((rc = check_step(g, ell, s, attr_in, noise, pop, flags)) != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, io)) != TARL_OK) return rc;
     if (s.N == 0) return TARL_OK;
-    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
-    launch_step(g, ell, s, attr_in, nz, t, delta_tt, pop, flags, static_cast<cudaStream_t>(stream), phase_mask);
+    launch_step(g, ell, s, attr_in, *io, static_cast<cudaStream_t>(stream), phase_mask);
+    return launch_status();
+}
+
+int tarl_store_noise(const tarl_dual_csr* g, int32_t n_replicas, uint64_t seed, uint32_t step_id, float* noise,
+                     void* stream) {
+    if (g == nullptr || g->n_links < 0 || n_replicas < 1 || n_replicas > 65535) return TARL_E_BADARG;
+    if (g->n_links == 0 || g->n_edges == 0) return TARL_OK;
+    if (noise == nullptr || g->in_ptr == nullptr || g->in_eid == nullptr) return TARL_E_BADARG;
+    k_store_noise<<<dim3(blocks_for(g->n_links), n_replicas), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        *g, n_replicas, (uint32_t)seed, (uint32_t)(seed >> 32), step_id, noise);
+    return launch_status();
+}
+
+int tarl_expand_delta_tt(const int32_t* edge_src, int32_t n_edges, int32_t n_links, int32_t n_replicas,
+                         const float* delta_tt_link, float* delta_tt, void* stream) {
+    if (n_edges < 0 || n_links < 0 || n_replicas < 1 || n_replicas > 65535) return TARL_E_BADARG;
+    if (n_edges == 0) return TARL_OK;
+    if (edge_src == nullptr || delta_tt_link == nullptr || delta_tt == nullptr) return TARL_E_BADARG;
+    k_expand_delta_tt<<<dim3((n_edges + 255) / 256, n_replicas), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        edge_src, n_edges, n_links, delta_tt_link, delta_tt);
     return launch_status();
 }
 
 int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                             const float* attr_in, const float* noise, uint64_t seed, uint32_t step_id, float t,
-                             float* delta_tt, uint8_t* pop, int32_t* flags, const tarl_agent_table* agents,
+                             const float* attr_in, const tarl_step_io* io, const tarl_agent_table* agents,
                              const tarl_csr* adjacency, int32_t n_nodes, uint8_t* withdrawn, int32_t* counters,
                              float* num_out, int32_t* occupancy, void* stream) {
     Store s;
     int rc = make_store(store, &s);
     if (rc != TARL_OK) return rc;
-    if ((rc = check_step(g, ell, s, attr_in, noise, pop, flags)) != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, io)) != TARL_OK) return rc;
     if (ell == nullptr || s.slot_link != nullptr) return TARL_E_BADARG;          // ELL kernels, links in link-id order
     if (agents == nullptr || agents->agent_features == nullptr || agents->n_rows < 1 || adjacency == nullptr ||
         adjacency->ptr == nullptr || (adjacency->n_edges > 0 && adjacency->idx == nullptr) || withdrawn == nullptr ||
@@ -666,32 +745,33 @@ int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, c
     if (s.N == 0) return TARL_OK;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     if (cudaMemsetAsync(occupancy, 0, sizeof(int32_t) * (size_t)s.R, cs) != cudaSuccess) return TARL_E_LAUNCH;
-    const Noise nz = {noise, (uint32_t)seed, (uint32_t)(seed >> 32), step_id};
-    launch_step(g, ell, s, attr_in, nz, t, delta_tt, pop, flags, cs, TARL_PHASE_SELECT_APPEND);
+    launch_step(g, ell, s, attr_in, *io, cs, TARL_PHASE_SELECT_APPEND);
     const WithdrawArgs wa = {AgentTable{agents->agent_features, s.R > 1 ? agents->replica_stride : 0, agents->n_rows},
                              *adjacency, withdrawn, counters, num_out, occupancy, nullptr, n_nodes};
     const dim3 grid(blocks_for(s.N), s.R);
-    if (ell->width == 4) launch_pdl(k_ell_respond_pop_withdraw<4>, grid, cs, *g, *ell, s, t, pop, flags, wa);
-    else launch_pdl(k_ell_respond_pop_withdraw<8>, grid, cs, *g, *ell, s, t, pop, flags, wa);
+    if (ell->width == 4)
+        launch_pdl(k_ell_respond_pop_withdraw<4>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa);
+    else
+        launch_pdl(k_ell_respond_pop_withdraw<8>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa);
     return launch_status();
 }
 
 int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
-                   const float* attr_in, uint64_t seed, uint32_t first_step_id, float t0, float dt, int32_t n_steps,
-                   const float* const* sel_bank, int32_t n_bank, float* delta_tt, uint8_t* pop, int32_t* flags,
-                   void* stream) {
+                   const float* attr_in, const tarl_step_io* io, float dt, int32_t n_steps,
+                   const float* const* sel_bank, int32_t n_bank, void* stream) {
     Store s;
     int rc = make_store(store, &s);
     if (rc != TARL_OK) return rc;
-    if ((rc = check_step(g, ell, s, attr_in, nullptr, pop, flags)) != TARL_OK) return rc;
-    if (n_steps < 0 || n_bank < 0 || (n_bank > 0 && sel_bank == nullptr)) return TARL_E_BADARG;
+    if ((rc = check_step(g, ell, s, attr_in, io)) != TARL_OK) return rc;
+    if (io->noise != nullptr || n_steps < 0 || n_bank < 0 || (n_bank > 0 && sel_bank == nullptr)) return TARL_E_BADARG;
     if (s.N == 0) return TARL_OK;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    tarl_step_io step = *io;
     for (int i = 0; i < n_steps; ++i) {
         if (n_bank > 0) s.sel = const_cast<float*>(sel_bank[i % n_bank]);
-        const Noise nz = {nullptr, (uint32_t)seed, (uint32_t)(seed >> 32), first_step_id + (uint32_t)i};
-        launch_step(g, ell, s, attr_in, nz, t0 + dt * (float)i, delta_tt, pop, flags, cs,
-                    TARL_PHASE_SELECT_APPEND | TARL_PHASE_RESPOND_SHIFT);
+        step.step_id = io->step_id + (uint32_t)i;
+        step.t = io->t + dt * (float)i;
+        launch_step(g, ell, s, attr_in, step, cs, TARL_PHASE_SELECT_APPEND | TARL_PHASE_RESPOND_SHIFT);
         float4* written = s.hot_next;                       // ping-pong: what this step wrote is the next step's input
         s.hot_next = const_cast<float4*>(s.hot_cur);
         s.hot_cur = written;

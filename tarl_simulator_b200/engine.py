@@ -75,7 +75,11 @@ class LinkStore:
         self.post = torch.zeros(max(L, 1), 2, **f32)
         self.hint = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
         self.pop = torch.zeros(max(L, 1), dtype=torch.uint8, device=dev)
+        self.words = (self.N + 31) // 32                              # pop mask words per replica (bit form)
+        self.pop_bits = torch.zeros(max(self.R * self.words, 1), dtype=torch.int32, device=dev)
+        self.dtt_link = torch.zeros(max(L, 1), **f32)                 # delta_travel_time per (replica, upstream link)
         self.flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
+        self._io = _cabi.StepIO()
         self.seed, self.step_id = int(seed), 0
         self.t_last = 0.0
         self._struct = _cabi.LinkStore()
@@ -157,10 +161,59 @@ class LinkStore:
         """SELECTED_ROAD [R, N] in link-id order."""
         return self._to_links(self.sel[: self.R * self.N].view(self.R, self.N))
 
+    def _step_io(self, t, noise, step_id, want_dtt: bool, want_bits: bool, out=None):
+        """out (optional): dict of caller-owned per-step output buffers replacing the store's own — "pop" (uint8 / bool
+        [R*N]), "flags" (int32 [FLAG_COUNT], zeroed), "delta_tt_link" (fp32 [R*N]), "pop_bits" (int32 [R*words])."""
+        io = self._io
+        out = out or {}
+        io.noise = noise.data_ptr() if noise is not None else None
+        io.seed, io.step_id, io.t = self.seed, step_id, float(t)
+        dtt = out.get("delta_tt_link")
+        io.delta_tt_link = dtt.data_ptr() if dtt is not None else (self.dtt_link.data_ptr() if want_dtt else None)
+        bits = out.get("pop_bits")
+        io.pop = out["pop"].data_ptr() if out.get("pop") is not None else self.pop.data_ptr()
+        io.pop_bits = bits.data_ptr() if bits is not None else (self.pop_bits.data_ptr() if want_bits else None)
+        io.flags = out["flags"].data_ptr() if out.get("flags") is not None else self.flags.data_ptr()
+        return C.byref(io)
+
+    def expand_delta_tt(self, out: torch.Tensor | None = None, per_link: torch.Tensor | None = None) -> torch.Tensor:
+        """road_optimality_data["delta_travel_time"] of the latest step in the reference's form: [R, E] fp32 in
+        original edge order, out[r, e] = delta_tt_link[r, source link of e] (tarl_expand_delta_tt). per_link: the
+        [R*N] per-link values to expand (default: the store's own buffer, i.e. the latest step's)."""
+        if out is None:
+            out = torch.empty(self.R, self.E, dtype=torch.float32, device=self.device)
+        if out.numel() != self.R * self.E or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise ValueError("delta_tt must be a contiguous fp32 [R, E] tensor")
+        src = self.dtt_link if per_link is None else per_link
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_expand_delta_tt(self.topo.src32.data_ptr(), self.E, self.N, self.R,
+                                                  src.data_ptr(), out.data_ptr(), self._stream())
+        _cabi.check(rc, "tarl_expand_delta_tt")
+        return out
+
+    def delta_tt_link(self) -> torch.Tensor:
+        """delta_travel_time of the latest step per (replica, upstream link), link-id order: [R, N]."""
+        return self._to_links(self.dtt_link[: self.R * self.N].view(self.R, self.N))
+
+    def noise_of_step(self, step_id: int | None = None) -> torch.Tensor:
+        """The [R, E] uniforms (original edge order) the in-kernel Philox stream yields for `step_id` (default: the
+        next step): step(noise=that) is bit-identical to step(noise=None), and the CPU oracle can replay it."""
+        out = torch.full((self.R, self.E), 0.5, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_noise(self.topo.ref(), self.R, self.seed,
+                                              self.step_id if step_id is None else int(step_id), out.data_ptr(),
+                                              self._stream())
+        _cabi.check(rc, "tarl_store_noise")
+        return out
+
     def step(self, t: float, noise: torch.Tensor | None = None, delta_tt: torch.Tensor | None = None,
-             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_ELL, withdraw=None):
+             phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP, variant: int = VARIANT_ELL, withdraw=None,
+             delta_tt_link: bool = False, pop_bits: bool = False, out=None):
         """One core step for all replicas. noise: [R, E] (or [E] when R == 1) uniforms in original edge order, or None
-        for the in-kernel Philox stream. delta_tt: optional [R, E] output. Returns the pop mask view [R, N] (uint8).
+        for the in-kernel Philox stream. delta_tt: optional [R, E] output in the reference's per-edge form (one more
+        launch: the step itself emits one value per upstream link, self.dtt_link — delta_tt_link=True asks for that
+        alone). pop_bits=True also leaves the pop mask as bits in self.pop_bits. Returns the pop mask view [R, N]
+        (uint8).
         withdraw (optional, ELL variant and link-id order only — see can_fuse_withdraw()): dict(table=_cabi.AgentTable,
         adjacency=CSR struct, n_nodes, mask, counters, num_out, occupancy) — the withdrawal at the same t and the
         occupancy observation ride on the response phase (tarl_store_step_withdraw)."""
@@ -171,31 +224,26 @@ class LinkStore:
         if delta_tt is not None and (delta_tt.numel() != self.R * self.E or delta_tt.dtype != torch.float32 or not delta_tt.is_contiguous()):
             raise ValueError("delta_tt must be a contiguous fp32 [R, E] tensor")
         self._fill_struct()
+        io = self._step_io(t, noise, self.step_id, delta_tt is not None or delta_tt_link, pop_bits, out)
         if withdraw is not None:
             if not self.can_fuse_withdraw(variant, phase_mask):
                 raise ValueError("withdraw= needs the ELL variant, both phases and a store in link-id order")
             w = withdraw
             with torch.cuda.device(self.device):
                 rc = _cabi.lib().tarl_store_step_withdraw(
-                    self.topo.ref(), C.byref(self._ell[0]), C.byref(self._struct), self.attr_in.data_ptr(),
-                    noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
-                    delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
+                    self.topo.ref(), C.byref(self._ell[0]), C.byref(self._struct), self.attr_in.data_ptr(), io,
                     C.byref(w["table"]), C.byref(w["adjacency"]), int(w["n_nodes"]), w["mask"].data_ptr(),
                     w["counters"].data_ptr() if w.get("counters") is not None else None, w["num_out"].data_ptr(),
                     w["occupancy"].data_ptr(), self._stream())
             _cabi.check(rc, "tarl_store_step_withdraw")
-            self.cur ^= 1
-            self.step_id += 1
-            self.t_last = float(t)
-            return self._to_links(self.pop[: self.N * self.R].view(self.R, self.N))
-        with torch.cuda.device(self.device):
-            rc = _cabi.lib().tarl_store_step(
-                self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
-                self.attr_in.data_ptr(),
-                noise.data_ptr() if noise is not None else None, self.seed, self.step_id, float(t),
-                delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
-                self._stream(), phase_mask)
-        _cabi.check(rc, "tarl_store_step")
+        else:
+            with torch.cuda.device(self.device):
+                rc = _cabi.lib().tarl_store_step(
+                    self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
+                    self.attr_in.data_ptr(), io, self._stream(), phase_mask)
+            _cabi.check(rc, "tarl_store_step")
+        if delta_tt is not None and (phase_mask & PHASE_SELECT_APPEND):
+            self.expand_delta_tt(delta_tt)
         if phase_mask & PHASE_RESPOND_POP:
             self.cur ^= 1
             self.step_id += 1
@@ -207,9 +255,11 @@ class LinkStore:
                 and phase_mask == (PHASE_SELECT_APPEND | PHASE_RESPOND_POP))
 
     def run(self, t0: float, n_steps: int, dt: float = 1.0, sel_bank=None, delta_tt: torch.Tensor | None = None,
-            variant: int = VARIANT_ELL):
+            variant: int = VARIANT_ELL, delta_tt_link: bool = True, pop_bits: bool = False):
         """`n_steps` consecutive core steps enqueued by ONE call into the library (tarl_store_run; in-kernel noise).
-        sel_bank: optional list of fp32 [R*N] device tensors cycled through as successive steps' SELECTED_ROAD."""
+        sel_bank: optional list of fp32 [R*N] device tensors cycled through as successive steps' SELECTED_ROAD.
+        Every step writes delta_travel_time per upstream link (self.dtt_link) and the pop mask; delta_tt ([R, E]) is
+        materialised once, from the last step."""
         ptrs = None
         nb = 0
         if sel_bank:
@@ -228,13 +278,14 @@ class LinkStore:
                 sel_bank = [cache[(b.data_ptr(), b._version)] for b in sel_bank]
             ptrs = (C.c_void_p * nb)(*[b.data_ptr() for b in sel_bank])
         self._fill_struct()
+        io = self._step_io(t0, None, self.step_id, delta_tt is not None or delta_tt_link, pop_bits)
         with torch.cuda.device(self.device):
             rc = _cabi.lib().tarl_store_run(
                 self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
-                self.attr_in.data_ptr(), self.seed, self.step_id, float(t0), float(dt), int(n_steps), ptrs, nb,
-                delta_tt.data_ptr() if delta_tt is not None else None, self.pop.data_ptr(), self.flags.data_ptr(),
-                self._stream())
+                self.attr_in.data_ptr(), io, float(dt), int(n_steps), ptrs, nb, self._stream())
         _cabi.check(rc, "tarl_store_run")
+        if delta_tt is not None and n_steps > 0:
+            self.expand_delta_tt(delta_tt)          # the LAST step's values
         if n_steps > 0:
             self.cur ^= n_steps & 1
             self.step_id += n_steps

@@ -52,7 +52,9 @@ class DualTopology:
     def ell(self, edge_attr: torch.Tensor):
         """ELLPACK copy of the first W edges of every link (struct tarl_dual_ell), W = 4 or 8 by maximum degree.
         Cached per edge_attr tensor. Column j of link n sits at [j*pitch + n]; links with more than W edges carry -2
-        in the last column and are served from the CSR."""
+        in the last column and are served from the CSR — and so are, on the in-edge side, links with an in-edge whose
+        weight is not >= 1e-3 (there an ineligible edge can win the Gumbel arg-max: they take the literal scan over
+        every in-edge)."""
         key = (edge_attr.data_ptr(), edge_attr._version)
         hit = getattr(self, "_ell", None)
         if hit is not None and hit[0] == key:
@@ -78,7 +80,12 @@ class DualTopology:
         in_attr = fill(self.in_ptr, in_deg, attr[self.in_eid.long()])
         out_dst = fill(self.out_ptr, out_deg, self.out_dst)
         if N:
-            in_src[W - 1, :N][in_deg > W] = -2
+            general = in_deg > W
+            if E:
+                unsafe = ~(attr >= 1e-3)                       # also catches NaN
+                general = general | (torch.zeros(N, dtype=torch.long, device=dev).index_add_(
+                    0, self.dst32.long(), unsafe.long()) > 0)
+            in_src[W - 1, :N][general] = -2
             out_dst[W - 1, :N][out_deg > W] = -2
         struct = _cabi.DualELL(W, pitch, in_src.data_ptr(), in_attr.data_ptr(), out_dst.data_ptr())
         pack = (struct, in_src, in_attr, out_dst)

@@ -17,6 +17,11 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(tarl_[a-z0-9_]+)\s*\(", text)))
 
 
+def header_abi_version():
+    text = open(os.path.join(ROOT, "include", "tarl_b200.h")).read()
+    return int(re.search(r"#define\s+TARL_ABI_VERSION\s+(\d+)", text).group(1))
+
+
 @pytest.fixture(scope="module")
 def built_lib():
     from tarl_simulator_b200.build import build
@@ -36,7 +41,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_ctypes_table_matches_header(built_lib):
     assert sorted(_cabi.SIGNATURES) == declared_symbols()
-    assert _cabi.lib().tarl_abi_version() == 17
+    assert _cabi.lib().tarl_abi_version() == _cabi.ABI_VERSION == header_abi_version()
     assert b"workspace" in _cabi.lib().tarl_error_string(-2)
 
 
