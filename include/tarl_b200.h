@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 18
+#define TARL_ABI_VERSION 19
 
 /* return codes */
 #define TARL_OK 0
@@ -182,6 +182,8 @@ typedef struct tarl_dual_ell {
 typedef struct tarl_step_io {
     const float* noise;
     uint64_t seed;
+    const uint64_t* seed_dev; /* NULL, or a device word holding the key instead of `seed`: a step captured in a CUDA graph
+                                 then draws new noise on every replay once the caller has changed the word */
     uint32_t step_id;
     float t;
     float* delta_tt_link;
@@ -307,11 +309,15 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
  * untouched and makes the row's log-probability -inf, exactly as the two separate calls do. uniforms == NULL: the
  * uniforms are drawn in the kernel (Philox4x32-10 keyed by `seed`, counter (group, 4-row chunk)) instead of being
  * produced by torch.rand and read back — the reference draws them from torch's global generator (:62), so which
- * stream they come from is declared divergence D4 either way. */
+ * stream they come from is declared divergence D4 either way. The counter is (group, (row_offset + row) / 4, draw_id):
+ * row_offset = global index of this call's first row (replicas sharded over ranks draw different uniforms from one
+ * seed), draw_id = which draw of the seed this is (the step of a rollout); seed_dev: NULL, or a device word holding the
+ * key instead of `seed` (a call captured in a CUDA graph then draws differently on every replay). row_offset % 4 == 0. */
 int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
                                 const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
                                 const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
-                                int32_t n_links, int32_t n_nodes, uint64_t seed, void* stream);
+                                int32_t n_links, int32_t n_nodes, uint64_t seed, const uint64_t* seed_dev,
+                                uint32_t draw_id, int32_t row_offset, void* stream);
 
 /* MPNNValueNet's propagate (src/agents/mpnn_agent.py:300-402, dropout off): per node x = [node_features(7) ‖
  * agent_features[agent_index](9)]; per edge e of the FULL graph msg = tanh(w·[x[edge_index[1][e]] ‖ edge_features[e]]
@@ -505,7 +511,36 @@ int tarl_metrics_accumulate(const tarl_dual_csr* g, int32_t n_replicas, const ui
                             float* optimality_sum, float* optimality_now, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * MPNNValueNetSimple forward on the tensor cores (csrc/value_mlp.cu: tcgen05.mma kind::tf32 with 3xTF32 error
+ * The PPO update's non-network arithmetic on the device (csrc/optim.cu).
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Generalized advantage estimation over a [T, R] trajectory — what torchrl's GAE(gamma, lmbda, average_gae=True) does at
+ * src/rl/ppo_trainer.py:21-27,132 of the reference: delta_t = r_t + gamma V(s_t+1) (1 - terminated_t) - V(s_t);
+ * A_t = delta_t + gamma lmbda (1 - done_t) A_t+1; value_target = A + V. value / next_value: element (t, r) at
+ * [t*value_step_stride + r] (a [T+1, R] array of V over the frames serves both: next_value = value + stride).
+ * reward [T, R] fp32, done / terminated [T, R] bytes. partials: 2*tarl_gae_partial_count(R) doubles = per-CTA {sum A,
+ * sum A^2} in a fixed order (the caller adds them up, all-reduces over the ranks and calls tarl_standardise). */
+int32_t tarl_gae_partial_count(int32_t n_replicas);
+int tarl_gae(const float* value, const float* next_value, int64_t value_step_stride, const float* reward,
+             const uint8_t* done, const uint8_t* terminated, int32_t n_steps, int32_t n_replicas, float gamma, float lmbda,
+             float* advantage, float* value_target, double* partials, void* stream);
+
+/* advantage <- (advantage - mean) / max(std, 1e-4) with the unbiased std, from stats = {count, sum, sum of squares}
+ * (device doubles: no host round trip between the reduction and its use). */
+int tarl_standardise(float* advantage, int64_t n, const double* stats, void* stream);
+
+/* One torch.optim.Adam step (src/rl/ppo_trainer.py:39,142: lr 1e-3, betas 0.9 / 0.999, eps 1e-8, no weight decay) over
+ * a flat fp32 bucket of n parameters — the bucket the gradient all-reduce works on. step: 1 for the first update.
+ * grad_scale multiplies every gradient first (1 / world size after a summing all-reduce). grad_norm: NULL, or a device
+ * float receiving the global L2 norm of the scaled gradient (the value the reference logs at :141); then
+ * norm_partials must hold tarl_adam_partial_count(n) doubles. */
+int32_t tarl_adam_partial_count(int64_t n);
+int tarl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int32_t step, float grad_scale, double* norm_partials, float* grad_norm,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MPNNValueNetSimple forward (tensor cores) and backward (csrc/value_mlp.cu: tcgen05.mma kind::tf32 with 3xTF32 error
  * compensation, operands staged by TMA, A split into TMEM, fp32 accumulation in TMEM).
  *
  * Replaces MPNNValueNetSimple.forward (src/agents/mpnn_agent.py:428-450) for n_rows observations at once:
@@ -517,12 +552,24 @@ int tarl_metrics_accumulate(const tarl_dual_csr* g, int32_t n_replicas, const ui
  * weights_changed: 0 = w1 is what the previous call on this workspace (same n_rows, n_nodes) was given, so its TF32
  *   hi/lo split kept in the workspace is reused; anything else re-splits.
  * workspace: tarl_value_mlp_workspace_bytes(n_rows, n_nodes) bytes, 1024-byte aligned. out: [n_rows].
- * Inference only (no gradient): the PPO update's 32-frame backward stays on the library GEMM. */
+ * save_z1 / save_z2: NULL (inference), or [n_rows, 64] each: the pre-activations of the two hidden layers, which
+ * tarl_value_mlp_backward needs (training-mode forward of the PPO update, src/rl/ppo_trainer.py:132-145). */
 size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes);
 int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
                            int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, int32_t weights_changed, void* workspace,
-                           size_t workspace_bytes, float* out, void* stream);
+                           size_t workspace_bytes, float* out, float* save_z1, float* save_z2, void* stream);
+
+/* Gradient of sum_m grad_out[m] * out[m] w.r.t. final_mlp.{0,2,4}.{weight,bias} (what autograd computes through the three
+ * nn.Linear of src/agents/mpnn_agent.py:428-450; the observation is a leaf, so there is no input gradient):
+ * grad_w1 [64, n_nodes+1] (last column = the time input), grad_b1 [64], grad_w2 [64, 64], grad_b2 [64], grad_w3 [64],
+ * grad_b3 [1], all overwritten. z1 / z2: what the forward call saved. scratch: (2*n_rows + 1) * 64 floats.
+ * dW1 = g_z1^T A reads the occupancy matrix once and writes the gradient once (16 flop per byte, reduction depth
+ * n_rows: HBM-bound on the fp32 pipe, exact fp32 sums in ascending row order); any row pitch >= n_nodes. */
+int tarl_value_mlp_backward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
+                            int32_t n_rows, int32_t n_nodes, const float* w2, const float* w3, const float* z1,
+                            const float* z2, const float* grad_out, float* scratch, float* grad_w1, float* grad_b1,
+                            float* grad_w2, float* grad_b2, float* grad_w3, float* grad_b3, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 18       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 19       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -65,7 +65,8 @@ class LinkStore(C.Structure):
 
 class StepIO(C.Structure):
     """struct tarl_step_io"""
-    _fields_ = [("noise", C.c_void_p), ("seed", C.c_uint64), ("step_id", C.c_uint32), ("t", C.c_float),
+    _fields_ = [("noise", C.c_void_p), ("seed", C.c_uint64), ("seed_dev", C.c_void_p), ("step_id", C.c_uint32),
+                ("t", C.c_float),
                 ("delta_tt_link", C.c_void_p), ("pop", C.c_void_p), ("pop_bits", C.c_void_p), ("flags", C.c_void_p)]
 
 
@@ -124,7 +125,7 @@ SIGNATURES = {
     "tarl_graphdist_backward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _P, _P, _P, _ROWS, _P]),
     "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _ROWS, _I32, _P, _P, _P]),
     "tarl_graphdist_sample_apply": (C.c_int, [_CSR1, _P, _F, _I32, _ROWS, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, C.c_uint64,
-                                              _P]),
+                                              _P, C.c_uint32, _I32, _P]),
     "tarl_value_mp_partial_count": (_I32, [_I32, _I32]),
     "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
                                         _P, _P, _P, _P]),
@@ -142,25 +143,44 @@ SIGNATURES = {
     "tarl_agents_apply_action_groups": (C.c_int, [_AST, _CSR1, _P, _P, _ROWS, _I32, _P]),
     "tarl_store_observe": (C.c_int, [_AST, _P, _P, _P, _P, _P, _P]),
     "tarl_metrics_accumulate": (C.c_int, [_CSR, _I32, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
+    "tarl_gae_partial_count": (_I32, [_I32]),
+    "tarl_gae": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P]),
+    "tarl_standardise": (C.c_int, [_P, _I64, _P, _P]),
+    "tarl_adam_partial_count": (_I32, [_I64]),
+    "tarl_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P, _P]),
     "tarl_value_mlp_workspace_bytes": (_SZ, [_I32, _I32]),
-    "tarl_value_mlp_forward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P]),
+    "tarl_value_mlp_forward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P, _P, _P, _P]),
+    "tarl_value_mlp_backward": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
 
 
 def lib():
-    """The loaded library. Raises RuntimeError if it has not been built (python -m tarl_simulator_b200.build)."""
+    """The loaded library. A missing or stale libtarl_b200.so (a fresh clone: the .so is a build artefact and not in the
+    history) is built on first use with nvcc, in-tree (tarl_simulator_b200.build); without nvcc this raises — there is
+    no CPU or PyTorch fallback for the kernels."""
     global _lib
     if _lib is None:
+        if "TARL_B200_LIB" not in os.environ:
+            try:
+                from .build import build
+                build()                                  # no-op when the library is newer than its sources
+            except Exception as exc:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing and could not be built ({exc}). Build it with "
+                        "`python -m tarl_simulator_b200.build` (needs nvcc). tarl_simulator_b200 has no CPU or PyTorch "
+                        "fallback for its kernels.") from exc
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m tarl_simulator_b200.build` (needs nvcc). "
-                "tarl_simulator_b200 has no CPU or PyTorch fallback for its kernels.")
+            raise RuntimeError(f"{LIB_PATH} is missing (TARL_B200_LIB points nowhere)")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
+        if handle.tarl_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{LIB_PATH} has ABI version {handle.tarl_abi_version()}, this binding expects "
+                               f"{ABI_VERSION}: rebuild with `python -m tarl_simulator_b200.build --force`")
         _lib = handle
     return _lib
 

@@ -23,6 +23,7 @@ PER_FILE = {
     "core_step.cu": ["-fmad=false"],
     "engine.cu": ["-fmad=false"],
     "agents.cu": ["-fmad=false"],
+    "optim.cu": ["-fmad=false"],       # Adam / GAE in the operation order of the libraries they restate
 }
 
 

@@ -91,7 +91,17 @@ __global__ void __launch_bounds__(kThreads) k_store_export(Store s, float* __res
 struct Noise {
     const float* ext;        // [R*E] uniforms in original edge order, or nullptr for the in-kernel Philox stream
     uint32_t seed_lo, seed_hi, step_id;
+    const unsigned long long* seed_dev;   // nullptr, or where the Philox key lives on the device (replaces seed_lo / hi:
+                                          // a launch captured in a CUDA graph can then draw differently on every replay)
 };
+
+__device__ __forceinline__ void philox_key(const Noise& nz, uint32_t& lo, uint32_t& hi) {
+    lo = nz.seed_lo; hi = nz.seed_hi;
+    if (nz.seed_dev != nullptr) {
+        const unsigned long long k = *nz.seed_dev;
+        lo = (uint32_t)k; hi = (uint32_t)(k >> 32);
+    }
+}
 
 // p_e of src/direction_mpnn.py:81-91 for the edge u -> d. U = A half of the upstream record (pre-step).
 __device__ __forceinline__ float edge_prob(const float4 U, float sel_u, float t, bool free_d, float room_d, float ridx_d,
@@ -123,7 +133,9 @@ constexpr float kSafeULo = 5.9604645e-08f, kSafeUHi = 0.99999994f, kSafeAttr = 1
 
 __device__ __forceinline__ float philox_uniform(const Noise& nz, int L, int j, float (&un)[4], int& have_group) {
     if (have_group != (j >> 2)) {
-        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+        uint32_t klo, khi;
+        philox_key(nz, klo, khi);
+        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), klo, khi, un);
         have_group = j >> 2;
     }
     const int jj = j & 3;
@@ -339,10 +351,12 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
             float best = -FLT_MAX;
             float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
             pk.src = -1;
+            uint32_t klo = 0u, khi = 0u;
+            if (!kExtNoise) philox_key(nz, klo, khi);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 if (!kExtNoise && (j & 3) == 0)
-                    philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), nz.seed_lo, nz.seed_hi, un);
+                    philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), klo, khi, un);
                 if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
                     const float sc = gumbel_score(p[j], kExtNoise ? uu[j] : un[j & 3]);
                     if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
@@ -556,7 +570,9 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
     if (u < extra) wa.num_out[(size_t)r * wa.n_nodes + s.N + u] = 0.0f;
     int num_i = (int)num;
     for (int off = 16; off > 0; off >>= 1) num_i += __shfl_xor_sync(0xffffffffu, num_i, off);
+#ifndef TARL_ABLATE_OCC      // tuning only: what do the per-warp atomics on one word per replica cost?
     if ((threadIdx.x & 31) == 0 && num_i != 0) atomicAdd(&wa.occupancy[r], num_i);
+#endif
 }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in engine_common.cuh).
@@ -648,7 +664,8 @@ int check_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s,
 void launch_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& s, const float* attr_in,
                  const tarl_step_io& io, cudaStream_t cs, uint32_t phase_mask) {
     const dim3 grid(blocks_for(s.N), s.R);
-    const Noise nz = {io.noise, (uint32_t)io.seed, (uint32_t)(io.seed >> 32), io.step_id};
+    const Noise nz = {io.noise, (uint32_t)io.seed, (uint32_t)(io.seed >> 32), io.step_id,
+                      reinterpret_cast<const unsigned long long*>(io.seed_dev)};
     const bool ext = nz.ext != nullptr;
     const float t = io.t;
     float* dtt = io.delta_tt_link;
@@ -679,7 +696,7 @@ __global__ void __launch_bounds__(kThreads) k_store_noise(tarl_dual_csr g, int R
     if (d >= g.n_links) return;
     const int r = blockIdx.y;
     const int L = r * g.n_links + d;
-    const Noise nz = {nullptr, seed_lo, seed_hi, step_id};
+    const Noise nz = {nullptr, seed_lo, seed_hi, step_id, nullptr};
     float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
     int grp = -1;
     const int k0 = g.in_ptr[d], k1 = g.in_ptr[d + 1];

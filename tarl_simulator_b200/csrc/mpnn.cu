@@ -744,7 +744,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, c
                                                               int n_tiles, const float* __restrict__ u, int64_t u_sb,
                                                               int64_t u_sg, uint8_t* __restrict__ onehot,
                                                               float* __restrict__ part_lp, int32_t* __restrict__ part_bad,
-                                                              BcApply ap, uint32_t seed_lo, uint32_t seed_hi) {
+                                                              BcApply ap, uint32_t seed_lo, uint32_t seed_hi,
+                                                              const unsigned long long* __restrict__ seed_dev,
+                                                              uint32_t draw_id, int row_offset) {
     __shared__ float sm_z[kBcGroups][kBcDeg], sm_cdf[kBcGroups][kBcDeg], sm_logp[kBcGroups][kBcDeg];
     __shared__ int sm_eid[kBcGroups][kBcDeg], sm_dst[kBcGroups][kBcDeg];
     __shared__ int sm_deg[kBcGroups], sm_k0[kBcGroups];
@@ -765,6 +767,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, c
     // call = the four uniforms of this thread (a stream of its own, D4; torch.rand + its read back cost a third of
     // this kernel's traffic)
     const bool u_own = u == nullptr;
+    if (u_own && seed_dev != nullptr) {
+        const unsigned long long k = *seed_dev;
+        seed_lo = (uint32_t)k; seed_hi = (uint32_t)(k >> 32);
+    }
     const bool u_vec = !u_own && u_sb == 1 && (u_sg & 3) == 0 && (reinterpret_cast<uintptr_t>(u) & 15) == 0;
     float lp[4] = {0.f, 0.f, 0.f, 0.f};
     int bad[4] = {0, 0, 0, 0};
@@ -817,7 +823,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, c
             if (!rows_live || g >= grp.n_rows || deg == 0) continue;
             float ug[4];
             if (u_own) {
-                tarl::philox4x32_10((uint32_t)g, (uint32_t)(row0 >> 2), 0u, 0x53414d50u, seed_lo, seed_hi, ug);
+                tarl::philox4x32_10((uint32_t)g, (uint32_t)((row_offset + row0) >> 2), draw_id, 0x53414d50u, seed_lo, seed_hi, ug);
             } else if (u_vec) {
                 ug[0] = t4.x; ug[1] = t4.y; ug[2] = t4.z; ug[3] = t4.w;
             } else {
@@ -1077,7 +1083,7 @@ inline T* data_of(const tarl_rows* r) { return r != nullptr ? static_cast<T*>(r-
 // launch of k_gd_sample_bcast (+ the log-probability finish); apply.sel_links == nullptr: sample only
 int launch_sample_bcast(const tarl_csr* groups, const float* logits_row, float temperature, int batch,
                         const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials, const BcApply& apply,
-                        uint64_t seed, cudaStream_t s) {
+                        uint64_t seed, const uint64_t* seed_dev, uint32_t draw_id, int row_offset, cudaStream_t s) {
     if (log_prob != nullptr && partials == nullptr) return TARL_E_WORKSPACE;
     const int n_tiles = (groups->n_rows + kBcGroups - 1) / kBcGroups;
     int nb = tarl_graphdist_partial_count(groups->n_rows, batch);           // bounds the partials per row
@@ -1089,7 +1095,8 @@ int launch_sample_bcast(const tarl_csr* groups, const float* logits_row, float t
     k_gd_sample_bcast<<<grid, kThreads, 0, s>>>(*groups, logits_row, 1.0f / temperature, batch, n_tiles,
                                                 uniforms ? data_of<const float>(uniforms) : nullptr,
                                                 uniforms ? uniforms->row_stride : 0, uniforms ? uniforms->col_stride : 0,
-                                                onehot, part_lp, part_bad, apply, (uint32_t)seed, (uint32_t)(seed >> 32));
+                                                onehot, part_lp, part_bad, apply, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                reinterpret_cast<const unsigned long long*>(seed_dev), draw_id, row_offset);
     if (log_prob != nullptr) k_gd_finish<<<batch, kThreads, 0, s>>>(nullptr, part_lp, part_bad, nb, nullptr, log_prob);
     return launch_status();
 }
@@ -1234,7 +1241,7 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
         int32_t* part_bad = log_prob ? reinterpret_cast<int32_t*>(partials + 2 * (size_t)batch * nb) : nullptr;
         if (bcast)      // one logits row for every batch row: the group's distribution is computed once per CTA
             return launch_sample_bcast(groups, data_of<const float>(logits), temperature, batch, uniforms,
-                                       data_of<uint8_t>(onehot), log_prob, partials, BcApply{}, 0, s);
+                                       data_of<uint8_t>(onehot), log_prob, partials, BcApply{}, 0, nullptr, 0u, 0, s);
         auto kernel = k_gd_sample_em4<false>;
         kernel<<<grid, kThreads, 0, s>>>(*groups, data_of<const float>(logits), 1.0f / temperature, batch,
                                          em4_chunks(batch), n_tiles, data_of<const float>(uniforms), uniforms->row_stride,
@@ -1259,10 +1266,12 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
 int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
                                 const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
                                 const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
-                                int32_t n_links, int32_t n_nodes, uint64_t seed, void* stream) {
+                                int32_t n_links, int32_t n_nodes, uint64_t seed, const uint64_t* seed_dev,
+                                uint32_t draw_id, int32_t row_offset, void* stream) {
     int rc = check_csr(groups);
     if (rc != TARL_OK) return rc;
     if (batch < 0 || (batch & 3) != 0 || temperature == 0.0f || n_links < 0 || n_nodes < n_links) return TARL_E_BADARG;
+    if (row_offset < 0 || (row_offset & 3) != 0) return TARL_E_BADARG;
     if (batch == 0 || groups->n_edges == 0) return TARL_OK;
     if (uniforms != nullptr && uniforms->data == nullptr) uniforms = nullptr;      // no uniforms: drawn in the kernel
     if (!logits_row || !onehot || (reinterpret_cast<uintptr_t>(onehot) & 3) != 0 ||
@@ -1270,7 +1279,7 @@ int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row,
         return TARL_E_BADARG;
     const BcApply ap = {group_node, edge_dst, sel_links, sel_sources, n_links, n_nodes};
     return launch_sample_bcast(groups, logits_row, temperature, batch, uniforms, onehot, log_prob, partials, ap, seed,
-                               static_cast<cudaStream_t>(stream));
+                               seed_dev, draw_id, row_offset, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,155 @@
+// optim.cu — the device side of the PPO update that is not a network (sm_100a): generalized advantage estimation over a
+// [T, R] trajectory and the Adam step over one flat fp32 parameter bucket.
+//
+// Reference semantics (the reference takes both from libraries, restated here as the spec):
+//   * torchrl 0.5.0 GAE as wired at /root/reference/src/rl/ppo_trainer.py:21-27 (gamma 0.99, lambda 0.95,
+//     average_gae=True): delta_t = r_t + gamma V(s_{t+1}) (1 - terminated_t) - V(s_t);
+//     A_t = delta_t + gamma lambda (1 - done_t) A_{t+1}; value_target = A + V. The standardisation of A over the batch
+//     needs a reduction over every rank's frames: the kernel leaves per-CTA partial sums (fp64) in a fixed order.
+//   * torch.optim.Adam(lr) as constructed at /root/reference/src/rl/ppo_trainer.py:39 (betas 0.9 / 0.999, eps 1e-8, no
+//     weight decay, no amsgrad), in the operation order of torch's single-tensor path:
+//     m = m + (g - m)(1 - b1); v = b2 v + (1 - b2) g g; denom = sqrt(v) / sqrt(1 - b2^k) + eps; p -= lr/(1 - b1^k) m/denom.
+//     One launch over the flat bucket the gradient all-reduce uses, instead of ~6 launches per parameter tensor; the
+//     global gradient norm the reference logs (:141, no clipping) comes out of the same pass.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tarl_b200.h"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+// one thread per replica walks its T steps backwards (coalesced over replicas at every t)
+__global__ void __launch_bounds__(kThreads) k_gae(const float* __restrict__ value, const float* __restrict__ next_value,
+                                                  int64_t v_stride, const float* __restrict__ reward,
+                                                  const uint8_t* __restrict__ done, const uint8_t* __restrict__ terminated,
+                                                  int T, int R, float gamma, float lmbda, float* __restrict__ adv,
+                                                  float* __restrict__ target, double* __restrict__ partials) {
+    __shared__ double sm[2][kThreads];
+    const int r = blockIdx.x * kThreads + threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    if (r < R) {
+        float running = 0.0f;
+        for (int t = T - 1; t >= 0; --t) {
+            const int64_t i = (int64_t)t * R + r;
+            const float v = value[(int64_t)t * v_stride + r], nv = next_value[(int64_t)t * v_stride + r];
+            const float not_term = 1.0f - (terminated[i] ? 1.0f : 0.0f), not_done = 1.0f - (done[i] ? 1.0f : 0.0f);
+            const float delta = reward[i] + gamma * nv * not_term - v;
+            running = delta + gamma * lmbda * not_done * running;
+            adv[i] = running;
+            target[i] = running + v;
+            s += (double)running;
+            ss += (double)running * (double)running;
+        }
+    }
+    sm[0][threadIdx.x] = s; sm[1][threadIdx.x] = ss;
+    __syncthreads();
+    for (int off = kThreads / 2; off > 0; off >>= 1) {            // fixed tree: deterministic
+        if (threadIdx.x < off) { sm[0][threadIdx.x] += sm[0][threadIdx.x + off]; sm[1][threadIdx.x] += sm[1][threadIdx.x + off]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = sm[0][0]; partials[2 * blockIdx.x + 1] = sm[1][0]; }
+}
+
+// stats = {n, sum A, sum A^2} after the all-reduce: A <- (A - mean) / max(std, 1e-4), unbiased std (average_gae=True)
+__global__ void __launch_bounds__(256) k_standardise(float* __restrict__ adv, int64_t n, const double* __restrict__ stats) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const double cnt = stats[0], mean = stats[1] / cnt;
+    double var = (stats[2] - cnt * mean * mean) / (cnt > 1.0 ? cnt - 1.0 : 1.0);
+    if (var < 0.0) var = 0.0;
+    double sd = sqrt(var);
+    if (sd < 1e-4) sd = 1e-4;
+    adv[i] = (float)(((double)adv[i] - mean) / sd);
+}
+
+constexpr int kAdamThreads = 256, kAdamPerThread = 4;
+
+__global__ void __launch_bounds__(kAdamThreads) k_adam(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n, float b1,
+                                                       float b2, float eps, float step_size, float bc2_sqrt,
+                                                       float grad_scale, double* __restrict__ norm_partials) {
+    __shared__ double sm[kAdamThreads];
+    const int64_t base = ((int64_t)blockIdx.x * kAdamThreads + threadIdx.x) * kAdamPerThread;
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < kAdamPerThread; ++k) {
+        const int64_t i = base + k;
+        if (i < n) {
+            const float gi = g[i] * grad_scale;
+            ss += (double)gi * (double)gi;
+            const float mi = m[i] + (gi - m[i]) * (1.0f - b1);               // exp_avg.lerp_(grad, 1 - beta1)
+            const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;              // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            m[i] = mi; v[i] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            p[i] = p[i] - step_size * (mi / denom);                         // addcdiv_(exp_avg, denom, value = -step_size)
+        }
+    }
+    sm[threadIdx.x] = ss;
+    __syncthreads();
+    for (int off = kAdamThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && norm_partials != nullptr) norm_partials[blockIdx.x] = sm[0];
+}
+
+__global__ void k_norm_finish(const double* __restrict__ partials, int n, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partials[i];
+    *out = (float)sqrt(s);
+}
+
+inline int status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
+
+}  // namespace
+
+extern "C" {
+
+int32_t tarl_gae_partial_count(int32_t n_replicas) { return n_replicas <= 0 ? 0 : (n_replicas + kThreads - 1) / kThreads; }
+
+int tarl_gae(const float* value, const float* next_value, int64_t value_step_stride, const float* reward,
+             const uint8_t* done, const uint8_t* terminated, int32_t n_steps, int32_t n_replicas, float gamma, float lmbda,
+             float* advantage, float* value_target, double* partials, void* stream) {
+    if (n_steps < 0 || n_replicas < 0) return TARL_E_BADARG;
+    if (n_steps == 0 || n_replicas == 0) return TARL_OK;
+    if (!value || !next_value || !reward || !done || !terminated || !advantage || !value_target || !partials)
+        return TARL_E_BADARG;
+    k_gae<<<tarl_gae_partial_count(n_replicas), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        value, next_value, value_step_stride, reward, done, terminated, n_steps, n_replicas, gamma, lmbda, advantage,
+        value_target, partials);
+    return status();
+}
+
+int tarl_standardise(float* advantage, int64_t n, const double* stats, void* stream) {
+    if (n < 0) return TARL_E_BADARG;
+    if (n == 0) return TARL_OK;
+    if (!advantage || !stats) return TARL_E_BADARG;
+    k_standardise<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(advantage, n, stats);
+    return status();
+}
+
+int32_t tarl_adam_partial_count(int64_t n) {
+    const int64_t per_cta = (int64_t)kAdamThreads * kAdamPerThread;
+    return n <= 0 ? 0 : (int32_t)((n + per_cta - 1) / per_cta);
+}
+
+int tarl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int32_t step, float grad_scale, double* norm_partials, float* grad_norm,
+                   void* stream) {
+    if (n < 0 || step < 1) return TARL_E_BADARG;
+    if (n == 0) return TARL_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || (grad_norm != nullptr && norm_partials == nullptr)) return TARL_E_BADARG;
+    // bias corrections in double, as Python floats are in torch's single-tensor path
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const int ctas = tarl_adam_partial_count(n);
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    k_adam<<<ctas, kAdamThreads, 0, cs>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1),
+                                          (float)sqrt(bc2), grad_scale, norm_partials);
+    if (grad_norm != nullptr) k_norm_finish<<<1, 32, 0, cs>>>(norm_partials, ctas, grad_norm);
+    return status();
+}
+
+}  // extern "C"

@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(kTailWarps * 32) k_value_mlp_tail(const float*
                                                                     const float* __restrict__ w2,
                                                                     const float* __restrict__ b2,
                                                                     const float* __restrict__ w3,
-                                                                    const float* __restrict__ b3, float* __restrict__ out) {
+                                                                    const float* __restrict__ b3, float* __restrict__ out,
+                                                                    float* __restrict__ save_z1,
+                                                                    float* __restrict__ save_z2) {
     __shared__ float s_w2t[kHidden][kHidden + 1];        // [i][j] = W2[j][i]
     __shared__ float s_h1[kTailWarps][kHidden];
     for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s_w2t[i % kHidden][i / kHidden] = w2[i];
@@ -358,8 +360,10 @@ __global__ void __launch_bounds__(kTailWarps * 32) k_value_mlp_tail(const float*
         a1 += p[lane + 32];
     }
     const float t = time[m * time_stride];
-    s_h1[warp][lane] = fmaxf(a0 + t * w_time[lane] + b1[lane], 0.0f);
-    s_h1[warp][lane + 32] = fmaxf(a1 + t * w_time[lane + 32] + b1[lane + 32], 0.0f);
+    const float z1a = a0 + t * w_time[lane] + b1[lane], z1b = a1 + t * w_time[lane + 32] + b1[lane + 32];
+    if (save_z1 != nullptr) { save_z1[(size_t)m * kHidden + lane] = z1a; save_z1[(size_t)m * kHidden + lane + 32] = z1b; }
+    s_h1[warp][lane] = fmaxf(z1a, 0.0f);
+    s_h1[warp][lane + 32] = fmaxf(z1b, 0.0f);
     __syncwarp();
     float c0 = b2[lane], c1 = b2[lane + 32];
 #pragma unroll 16
@@ -368,9 +372,109 @@ __global__ void __launch_bounds__(kTailWarps * 32) k_value_mlp_tail(const float*
         c0 += s_w2t[i][lane] * h;
         c1 += s_w2t[i][lane + 32] * h;
     }
+    if (save_z2 != nullptr) { save_z2[(size_t)m * kHidden + lane] = c0; save_z2[(size_t)m * kHidden + lane + 32] = c1; }
     float v = w3[lane] * fmaxf(c0, 0.0f) + w3[lane + 32] * fmaxf(c1, 0.0f);
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) out[m] = v + b3[0];
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Gradient of sum_m grad_out[m] * out[m] w.r.t. the six parameter tensors (observations are leaves: no input gradient).
+// With z1 / z2 the pre-activations the forward pass kept:
+//   g_z2 = grad_out (x) w3 . [z2 > 0]        dW3 = sum_m grad_out relu(z2)     db3 = sum grad_out    db2 = sum_m g_z2
+//   g_z1 = (g_z2 W2) . [z1 > 0]              dW2 = g_z2^T relu(z1)             db1 = sum_m g_z1
+//   dW1[:, :N] = g_z1^T A   (k_value_mlp_dw1)                                  dW1[:, N] = g_z1^T time
+// Everything but dW1 is a few thousand flops per row: one CTA, sums over the rows in ascending order (deterministic).
+constexpr int kBwdThreads = 1024;
+__global__ void __launch_bounds__(kBwdThreads) k_value_mlp_bwd_small(int M, const float* __restrict__ z1,
+                                                                     const float* __restrict__ z2,
+                                                                     const float* __restrict__ grad_out,
+                                                                     const float* __restrict__ time, int64_t time_stride,
+                                                                     const float* __restrict__ w2,
+                                                                     const float* __restrict__ w3,
+                                                                     float* __restrict__ g_z1, float* __restrict__ g_z2,
+                                                                     float* __restrict__ d_wtime, float* __restrict__ db1,
+                                                                     float* __restrict__ dw2, float* __restrict__ db2,
+                                                                     float* __restrict__ dw3, float* __restrict__ db3) {
+    __shared__ float s_w2[kHidden][kHidden + 1];          // [j][i] = W2[j][i]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kHidden * kHidden; i += kBwdThreads) s_w2[i / kHidden][i % kHidden] = w2[i];
+    for (int i = tid; i < M * kHidden; i += kBwdThreads) {
+        const int m = i / kHidden, j = i - m * kHidden;
+        g_z2[i] = z2[i] > 0.0f ? grad_out[m] * w3[j] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = tid; i < M * kHidden; i += kBwdThreads) {
+        const int m = i / kHidden, c = i - m * kHidden;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int j = 0; j < kHidden; ++j) acc += g_z2[m * kHidden + j] * s_w2[j][c];
+        g_z1[i] = z1[i] > 0.0f ? acc : 0.0f;
+    }
+    __syncthreads();
+    for (int i = tid; i < kHidden * kHidden; i += kBwdThreads) {      // dW2[j][c] = sum_m g_z2[m][j] relu(z1[m][c])
+        const int j = i / kHidden, c = i - j * kHidden;
+        float acc = 0.0f;
+        for (int m = 0; m < M; ++m) acc += g_z2[m * kHidden + j] * fmaxf(z1[m * kHidden + c], 0.0f);
+        dw2[i] = acc;
+    }
+    if (tid < kHidden) {
+        float a3 = 0.0f, a2 = 0.0f, a1 = 0.0f, at = 0.0f;
+        for (int m = 0; m < M; ++m) {
+            a3 += grad_out[m] * fmaxf(z2[m * kHidden + tid], 0.0f);
+            a2 += g_z2[m * kHidden + tid];
+            const float g = g_z1[m * kHidden + tid];
+            a1 += g;
+            at += g * time[m * time_stride];
+        }
+        dw3[tid] = a3; db2[tid] = a2; db1[tid] = a1; d_wtime[tid] = at;
+    }
+    if (tid == kHidden) {
+        float a = 0.0f;
+        for (int m = 0; m < M; ++m) a += grad_out[m];
+        db3[0] = a;
+    }
+}
+
+// dW1[j, n] = sum_m g_z1[m, j] * A[m, n]: the occupancy matrix is read once (coalesced over n), the [64, N + 1] gradient
+// written once — 16 flop per byte moved with a reduction only M (= 32 frames in the PPO update) deep: HBM-bound on the
+// plain fp32 pipe, exact fp32 accumulation in ascending row order, no tensor cores needed. One thread per column n
+// keeps the 64 partial sums of its column in registers; g_z1 goes through shared memory in chunks of kDwRows rows.
+constexpr int kDwThreads = 128, kDwRows = 32;
+__global__ void __launch_bounds__(kDwThreads) k_value_mlp_dw1(const float* __restrict__ a, int64_t a_stride, int M,
+                                                              int n_nodes, const float* __restrict__ g_z1,
+                                                              const float* __restrict__ d_wtime,
+                                                              float* __restrict__ dw1) {
+    __shared__ float s_g[kDwRows][kHidden];
+    const int n = blockIdx.x * kDwThreads + threadIdx.x;
+    const bool live = n < n_nodes;
+    float acc[kHidden];
+#pragma unroll
+    for (int j = 0; j < kHidden; ++j) acc[j] = 0.0f;
+    for (int m0 = 0; m0 < M; m0 += kDwRows) {
+        const int rows = min(kDwRows, M - m0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * kHidden; i += kDwThreads) s_g[i / kHidden][i % kHidden] = g_z1[(size_t)m0 * kHidden + i];
+        __syncthreads();
+        if (live) {
+            float av[kDwRows];
+#pragma unroll
+            for (int r = 0; r < kDwRows; ++r) av[r] = r < rows ? a[(int64_t)(m0 + r) * a_stride + n] : 0.0f;
+#pragma unroll
+            for (int r = 0; r < kDwRows; ++r) {
+                if (r < rows) {
+#pragma unroll
+                    for (int j = 0; j < kHidden; ++j) acc[j] += s_g[r][j] * av[r];
+                }
+            }
+        }
+    }
+    const int64_t pitch = (int64_t)n_nodes + 1;
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < kHidden; ++j) dw1[j * pitch + n] = acc[j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < kHidden) dw1[threadIdx.x * pitch + n_nodes] = d_wtime[threadIdx.x];   // time column
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -439,7 +543,7 @@ size_t tarl_value_mlp_workspace_bytes(int32_t n_rows, int32_t n_nodes) {
 int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
                            int32_t n_rows, int32_t n_nodes, const float* w1, const float* b1, const float* w2,
                            const float* b2, const float* w3, const float* b3, int32_t weights_changed, void* workspace,
-                           size_t workspace_bytes, float* out, void* stream) {
+                           size_t workspace_bytes, float* out, float* save_z1, float* save_z2, void* stream) {
     if (n_rows < 0 || n_nodes <= 0) return TARL_E_BADARG;
     if (n_rows == 0) return TARL_OK;
     if (!occupancy || !time || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !out || !workspace) return TARL_E_BADARG;
@@ -467,7 +571,33 @@ int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const
     k_value_mlp_gemm<<<dim3(p.tiles, p.slices), kThreadsGemm, kSmemBytes, s>>>(map_a, map_wh, map_wl, n_rows, p.kb_total,
                                                                               p.kb_per_slice, partials);
     k_value_mlp_tail<<<(n_rows + kTailWarps - 1) / kTailWarps, kTailWarps * 32, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
-                                                          w3, b3, out);
+                                                          w3, b3, out, save_z1, save_z2);
+    return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+}
+
+int tarl_value_mlp_backward(const float* occupancy, int64_t occ_row_stride, const float* time, int64_t time_stride,
+                            int32_t n_rows, int32_t n_nodes, const float* w2, const float* w3, const float* z1,
+                            const float* z2, const float* grad_out, float* scratch, float* grad_w1, float* grad_b1,
+                            float* grad_w2, float* grad_b2, float* grad_w3, float* grad_b3, void* stream) {
+    if (n_rows < 0 || n_nodes <= 0) return TARL_E_BADARG;
+    if (!grad_w1 || !grad_b1 || !grad_w2 || !grad_b2 || !grad_w3 || !grad_b3) return TARL_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_rows == 0) {
+        cudaMemsetAsync(grad_w1, 0, sizeof(float) * (size_t)kHidden * ((size_t)n_nodes + 1), s);
+        cudaMemsetAsync(grad_b1, 0, sizeof(float) * kHidden, s); cudaMemsetAsync(grad_w2, 0, sizeof(float) * kHidden * kHidden, s);
+        cudaMemsetAsync(grad_b2, 0, sizeof(float) * kHidden, s); cudaMemsetAsync(grad_w3, 0, sizeof(float) * kHidden, s);
+        cudaMemsetAsync(grad_b3, 0, sizeof(float), s);
+        return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+    }
+    if (!occupancy || !time || !w2 || !w3 || !z1 || !z2 || !grad_out || !scratch || occ_row_stride < n_nodes)
+        return TARL_E_BADARG;
+    float* g_z1 = scratch;                                   // [n_rows, 64]
+    float* g_z2 = scratch + (size_t)n_rows * kHidden;        // [n_rows, 64]
+    float* d_wtime = g_z2 + (size_t)n_rows * kHidden;        // [64]
+    k_value_mlp_bwd_small<<<1, kBwdThreads, 0, s>>>(n_rows, z1, z2, grad_out, time, time_stride, w2, w3, g_z1, g_z2, d_wtime,
+                                                    grad_b1, grad_w2, grad_b2, grad_w3, grad_b3);
+    k_value_mlp_dw1<<<(n_nodes + kDwThreads - 1) / kDwThreads, kDwThreads, 0, s>>>(occupancy, occ_row_stride, n_rows, n_nodes,
+                                                                                 g_z1, d_wtime, grad_w1);
     return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
 }
 

@@ -88,13 +88,17 @@ class ActionSink:
     source nodes [R, N_tot - N], both contiguous and in node-id order, for the graph `edge_index` describes.
     GraphDistribution.sample(sink=...) sets `applied` when it wrote them."""
 
-    def __init__(self, edge_index, groups, sel_links, sel_sources, n_links, n_nodes):
+    def __init__(self, edge_index, groups, sel_links, sel_sources, n_links, n_nodes, row_offset: int = 0):
         self.edge_index, self.groups = edge_index, groups
         self.sel_links, self.sel_sources = sel_links, sel_sources
         self.n_links, self.n_nodes = int(n_links), int(n_nodes)
         self.group_node = groups.nodes.to(torch.int32).contiguous()
         self.edge_dst = edge_index[1].to(torch.int32).contiguous()
         self.applied = False
+        # Which uniforms the sampling kernel draws for itself (Philox4x32-10, counter (group, global row / 4, draw)):
+        self.row_offset = int(row_offset)      # global index of the first replica (ranks of a data-parallel job differ)
+        self.seed_dev = None                   # int64 [1] device tensor holding the key, or None: a host seed per call
+        self.draw_id = 0                       # advanced by every draw taken with the device key
 
     def matches(self, dist, rows: int) -> bool:
         return (dist._groups is self.groups and self.sel_links.size(0) == rows and self.sel_links.is_contiguous()
@@ -214,16 +218,23 @@ class GraphDistribution(Distribution):
                 partials = torch.empty(3 * rows * max(_cabi.lib().tarl_graphdist_partial_count(self.nb_nodes, rows), 1),
                                        dtype=torch.float32, device=dev)
                 fused = True
-            # no injected uniforms: the kernel draws them (Philox keyed by a seed from torch's default CPU generator, so
-            # torch.manual_seed reproduces a rollout) instead of reading back a torch.rand tensor
-            seed = int(torch.randint(0, 2 ** 62, (1,))) if u is None else 0
+            # no injected uniforms: the kernel draws them instead of reading back a torch.rand tensor. Key: the sink's
+            # device word when it has one (rollouts replayed from a CUDA graph), else a seed from torch's default CPU
+            # generator (torch.manual_seed reproduces a rollout); rows of different ranks differ through row_offset
+            seed, seed_dev, draw = 0, None, 0
+            if u is None:
+                if sink.seed_dev is not None:
+                    seed_dev, draw = sink.seed_dev.data_ptr(), sink.draw_id
+                    sink.draw_id += 1
+                else:
+                    seed = (int(torch.randint(0, 2 ** 62, (1,))) + getattr(sink, "salt", 0)) & ((1 << 62) - 1)
             with torch.cuda.device(dev):
                 rc = _cabi.lib().tarl_graphdist_sample_apply(
                     self._groups.ref(), lg.data_ptr(), self.temperature, rows, _cabi.rows(u) if u is not None else None,
                     out.data_ptr(), lp.data_ptr() if fused else None, partials.data_ptr() if fused else None,
                     sink.group_node.data_ptr(), sink.edge_dst.data_ptr(), sink.sel_links.data_ptr(),
                     sink.sel_sources.data_ptr() if sink.sel_sources is not None else None, sink.n_links, sink.n_nodes,
-                    seed, _stream(dev))
+                    seed, seed_dev, draw, sink.row_offset, _stream(dev))
             _cabi.check(rc, "tarl_graphdist_sample_apply")
             sink.applied = True
             out = out.view(torch.bool) if dtype == torch.bool else out

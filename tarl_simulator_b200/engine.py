@@ -81,6 +81,7 @@ class LinkStore:
         self.flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
         self._io = _cabi.StepIO()
         self.seed, self.step_id = int(seed), 0
+        self.seed_dev = None          # optional int64 [1] device tensor: the key of the in-kernel noise lives there
         self.t_last = 0.0
         self._struct = _cabi.LinkStore()
         self._fill_struct()
@@ -168,6 +169,7 @@ class LinkStore:
         out = out or {}
         io.noise = noise.data_ptr() if noise is not None else None
         io.seed, io.step_id, io.t = self.seed, step_id, float(t)
+        io.seed_dev = self.seed_dev.data_ptr() if self.seed_dev is not None else None
         dtt = out.get("delta_tt_link")
         io.delta_tt_link = dtt.data_ptr() if dtt is not None else (self.dtt_link.data_ptr() if want_dtt else None)
         bits = out.get("pop_bits")

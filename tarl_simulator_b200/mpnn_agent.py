@@ -324,6 +324,9 @@ class MPNNValueNet(MessagePassing, Agents):
             if keep_bits is not None:
                 keep_bits = keep_bits.to(device=nf.device, dtype=torch.int32).reshape(B, self.num_edges).contiguous()
             seed = int(torch.randint(0, 2 ** 62, (1,)))          # torch's default CPU generator: no device sync
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                # ranks seeded alike (identical initial parameters) must still drop different message inputs
+                seed = (seed + torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & ((1 << 62) - 1)
             self._last_drop = (keep_bits, seed, p_drop, B)
             v = _ValueMessagePassingDropout.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
                                                   by_target, self._flags, keep_bits, seed, p_drop)
@@ -345,9 +348,48 @@ class MPNNValueNet(MessagePassing, Agents):
                 raise IndexError(_cabi.decode_error_bits(bits))
 
 
+class _ValueMLP(torch.autograd.Function):
+    """MPNNValueNetSimple's three layers on the kernels of csrc/value_mlp.cu: forward = tcgen05 GEMM (3xTF32) + fused
+    tail, keeping the two pre-activations when a gradient will be asked for; backward = the parameter gradients (the
+    observation is a leaf). net: the module (workspace / weight-split cache lives there)."""
+
+    @staticmethod
+    def forward(ctx, net, num, tm, w1, b1, w2, b2, w3, b3):
+        M, dev = num.size(0), num.device
+        train = any(ctx.needs_input_grad[3:])
+        z1 = torch.empty(M, 64, dtype=torch.float32, device=dev) if train else None
+        z2 = torch.empty(M, 64, dtype=torch.float32, device=dev) if train else None
+        out = net._launch_forward(num, tm, (w1, b1, w2, b2, w3, b3), z1, z2)
+        if train:
+            ctx.save_for_backward(num, tm, w2, w3, z1, z2)
+            ctx.n_nodes = net.num_nodes
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        num, tm, w2, w3, z1, z2 = ctx.saved_tensors
+        M, N, dev = num.size(0), ctx.n_nodes, num.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = g_out.reshape(-1).to(torch.float32).contiguous()
+        dw1 = torch.empty(64, N + 1, **f32)
+        db1, dw2, db2 = torch.empty(64, **f32), torch.empty(64, 64, **f32), torch.empty(64, **f32)
+        dw3, db3 = torch.empty(1, 64, **f32), torch.empty(1, **f32)
+        scratch = torch.empty((2 * M + 1) * 64, **f32)
+        w2c, w3c = w2.detach().contiguous(), w3.detach().contiguous()
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_value_mlp_backward(
+                num.data_ptr(), num.stride(0) if M > 1 else N, tm.data_ptr(), tm.stride(0) if M > 1 else 1, M, N,
+                w2c.data_ptr(), w3c.data_ptr(), z1.data_ptr(), z2.data_ptr(), g.data_ptr(), scratch.data_ptr(),
+                dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), db2.data_ptr(), dw3.data_ptr(), db3.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_value_mlp_backward")
+        return None, None, None, dw1, db1, dw2, db2, dw3, db3
+
+
 class MPNNValueNetSimple(MessagePassing, Agents):
     """State value from the per-link occupancies: MLP([NUMBER_OF_AGENT column ‖ time]), (N+1)→64→64→1 with ReLU
-    (src/agents/mpnn_agent.py:407-450) — the value net Runner wires (src/runner.py:68). Dense GEMMs: library calls."""
+    (src/agents/mpnn_agent.py:407-450) — the value net Runner wires (src/runner.py:68). `final_mlp` keeps the
+    reference's parameter names and shapes (state_dict compatible); it is never CALLED: forward, with or without
+    gradients, runs on the kernels of csrc/value_mlp.cu (tcgen05 first layer, fused tail, hand-written backward)."""
 
     def __init__(self, edge_index, num_nodes, device):
         Agents.__init__(self, device=device)
@@ -363,47 +405,58 @@ class MPNNValueNetSimple(MessagePassing, Agents):
 
         self._ws = None
         self._ws_key = None
+        self.last_path = None            # "tcgen05" / "tcgen05+pad": how the latest call reached the kernel (tests)
 
     def forward(self, node_features, edge_features, agent_index, time):
-        x = torch.cat((node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time), dim=-1)
-        return self.final_mlp(x)
+        """The reference's signature: reads the NUMBER_OF_AGENT column of node_features ([.., N_tot, 7]) and time."""
+        return self.forward_occupancy(node_features[..., ObservationFeatureHelpers.NUMBER_OF_AGENT], time)
 
     def forward_occupancy(self, num_agents, time):
-        """The same function of the only observation column it reads: num_agents [.., N_tot] = NUMBER_OF_AGENT.
-        Without autograd (rollouts, GAE: every frame of a batch) and with a TMA-addressable occupancy matrix this is
-        the tcgen05 kernel of csrc/value_mlp.cu (3xTF32, fp32-accurate); otherwise — the 32-frame PPO update that
-        needs gradients — the library GEMM."""
-        if self._tensor_core_ok(num_agents, time):
-            return self._forward_tensor_core(num_agents, time)
-        return self.final_mlp(torch.cat((num_agents, time), dim=-1))
+        """The same function of the only observation column it reads: num_agents [.., N_tot] = NUMBER_OF_AGENT, time
+        [.., 1]. Returns [.., 1]. The occupancy matrix must be TMA-addressable (16-byte aligned rows of unit stride);
+        anything else — a strided column view, a pitch that is not a multiple of four floats — is copied into a padded
+        buffer first (one pass over it; rollouts hand out addressable frames)."""
+        if not num_agents.is_cuda:
+            raise RuntimeError("MPNNValueNetSimple computes on CUDA devices only (no CPU fallback)")
+        lead = num_agents.shape[:-1]
+        num = num_agents.reshape(-1, self.num_nodes).to(torch.float32)
+        M = num.size(0)
+        tm = time.reshape(-1).to(torch.float32)
+        if tm.numel() != M:
+            raise ValueError("time must hold one value per observation row")
+        if M == 0:
+            return torch.zeros(*lead, 1, dtype=torch.float32, device=num.device)
+        self.last_path = "tcgen05"
+        if not (num.stride(1) == 1 and (M == 1 or num.stride(0) % 4 == 0) and num.data_ptr() % 16 == 0):
+            pitch = (self.num_nodes + 3) // 4 * 4
+            padded = torch.empty(M, pitch, dtype=torch.float32, device=num.device)
+            padded[:, : self.num_nodes].copy_(num)
+            num = padded[:, : self.num_nodes]
+            self.last_path = "tcgen05+pad"
+        l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
+        out = _ValueMLP.apply(self, num, tm, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
+        return out.reshape(*lead, 1)
 
-    def _tensor_core_ok(self, num, time) -> bool:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.final_mlp.parameters()):
-            return False
-        return (num.is_cuda and num.dim() == 2 and num.dtype == torch.float32 and num.size(1) == self.num_nodes
-                and num.size(0) > 0 and num.stride(1) == 1 and num.stride(0) % 4 == 0 and num.data_ptr() % 16 == 0
-                and time.numel() == num.size(0) and time.dtype == torch.float32 and time.device == num.device
-                and self.final_mlp[0].weight.device == num.device)
-
-    def _forward_tensor_core(self, num, time):
+    def _launch_forward(self, num, tm, params, z1=None, z2=None):
         M, dev = num.size(0), num.device
         lib = _cabi.lib()
         need = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
-        l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
+        w1 = params[0]
         # the workspace keeps the TF32 hi/lo split of W1: redone only when the weight (or the problem shape) changes
-        key = (M, l1.weight.data_ptr(), l1.weight._version)
+        key = (M, w1.data_ptr(), w1._version)
         if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
             self._ws_key = None
         changed = self._ws_key != key
         self._ws_key = key
         ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
-        params = [t.detach().contiguous() for t in (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)]
-        tm = time.reshape(-1)
+        params = [t.detach().contiguous() for t in params]
         out = torch.empty(M, 1, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = lib.tarl_value_mlp_forward(num.data_ptr(), num.stride(0), tm.data_ptr(), tm.stride(0) if M > 1 else 1,
+            rc = lib.tarl_value_mlp_forward(num.data_ptr(), num.stride(0) if M > 1 else (self.num_nodes + 3) // 4 * 4,
+                                            tm.data_ptr(), tm.stride(0) if M > 1 else 1,
                                             M, self.num_nodes, *[t.data_ptr() for t in params], int(changed), ws_ptr,
-                                            need, out.data_ptr(), _stream(dev))
+                                            need, out.data_ptr(), z1.data_ptr() if z1 is not None else None,
+                                            z2.data_ptr() if z2 is not None else None, _stream(dev))
         _cabi.check(rc, "tarl_value_mlp_forward")
         return out

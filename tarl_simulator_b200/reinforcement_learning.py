@@ -179,7 +179,10 @@ class BatchedSimulatorEnv:
     the value net only NUM: `num_agents()` is a strided view)."""
 
     def __init__(self, graph, Nmax: int, agent_features: torch.Tensor, replicas: int, timestep: float = 1,
-                 seed: int = 0, cluster: bool | None = None):
+                 seed: int = 0, cluster: bool | None = None, first_replica: int = 0):
+        """first_replica: global index of this environment's first replica when a job shards its replicas over several
+        ranks (parallel.shard_replicas): it enters every in-kernel noise stream, so that no two ranks draw the same
+        actions or the same hand-off noise from one job-wide seed."""
         dev = graph.x.device
         if dev.type != "cuda":
             raise RuntimeError("BatchedSimulatorEnv lives on a CUDA device (no CPU fallback)")
@@ -187,7 +190,13 @@ class BatchedSimulatorEnv:
         self.N, self.n_nodes = int(graph.num_roads), graph.x.size(0)
         self.E_full = graph.edge_index.size(1)
         self.timestep = timestep
-        self.store = LinkStore.from_graph(graph, Nmax, replicas=replicas, seed=seed, cluster=cluster)
+        self.first_replica = int(first_replica)
+        self.seed = int(seed)
+        salt = (self.first_replica * 0x9E3779B97F4A7C15) & ((1 << 62) - 1)
+        self.store = LinkStore.from_graph(graph, Nmax, replicas=replicas, seed=(int(seed) + salt) & ((1 << 62) - 1),
+                                          cluster=cluster)
+        self._salt = salt
+        self.seed_words = None          # int64 [2] on the device once begin_rollout() was called: {core noise, sampling}
         F = 3 * self.Nmax + 7
         self.src_sel = graph.x[self.N:, F - 2].to(torch.float32).repeat(self.R, 1).contiguous()
         self.agent_features = agent_features.to(dev, torch.float32).unsqueeze(0).repeat(self.R, 1, 1).contiguous()
@@ -220,6 +229,26 @@ class BatchedSimulatorEnv:
         st.src_sel = self.src_sel.data_ptr()
         st.t_garbage = float(s.t_last)
         return st
+
+    def begin_rollout(self, seed: int):
+        """Puts the noise streams of the coming rollout under ONE host number: the keys of the core step's hand-off
+        noise and of the action sampling move into two device words (so that the launches of a rollout can be captured
+        in a CUDA graph once and still draw new noise on every replay), and the per-rollout counters that enter the
+        Philox counters (step id, draw id) restart at 0. Call before reset()."""
+        mask = (1 << 62) - 1
+        core = (int(seed) + self._salt) & mask
+        sample = ((int(seed) ^ 0x5DEECE66D) + self._salt) & mask
+        if self.seed_words is None:
+            self.seed_words = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self.store.seed_dev = self.seed_words[0:1]
+        self.seed_words[0].fill_(core)
+        self.seed_words[1].fill_(sample)
+        self.store.step_id = 0
+        self.store.cur = 0              # a captured rollout has the ping-pong roles of its first step baked in
+        sink = self.action_sink()
+        if sink is not None:
+            sink.seed_dev = self.seed_words[1:2]
+            sink.draw_id = 0
 
     def reset(self):
         """_reset (:186-219): empty queues, ON_WAY = DONE = 0, t = 06:00 − 60 s."""
@@ -270,8 +299,13 @@ class BatchedSimulatorEnv:
         sel = self.store.sel
         key = (sel.data_ptr(), id(grp))
         if getattr(self, "_sink_key", None) != key:
+            old = getattr(self, "_sink", None)
             self._sink = ActionSink(self.graph.edge_index, grp, sel[: self.R * self.N].view(self.R, self.N),
-                                    self.src_sel if self.n_nodes > self.N else None, self.N, self.n_nodes)
+                                    self.src_sel if self.n_nodes > self.N else None, self.N, self.n_nodes,
+                                    row_offset=(self.first_replica // 4) * 4)
+            self._sink.salt = self._salt
+            if old is not None:
+                self._sink.seed_dev, self._sink.draw_id = old.seed_dev, old.draw_id
             self._sink_key = key
         return self._sink
 

@@ -15,9 +15,18 @@ the reference's settings:
 Multi-GPU (one process per GPU, torch.distributed initialised by the launcher): every rank rolls out its own
 replicas with no communication; per optimiser step ONE all-reduce of the flat fp32 gradient bucket (averaged), plus
 a 3-scalar all-reduce for the advantage statistics, so that all ranks apply identical updates.
+
+On a CUDA device nothing of an iteration runs on the host but the launches themselves: the rollout of a
+BatchedSimulatorEnv is captured in ONE CUDA graph (all T steps; noise keys live in device words, so every replay draws
+anew), the value net sees all (T+1) R frames in one call, GAE is one kernel (csrc/optim.cu), the minibatch is drawn with
+a device permutation, parameters and gradients live in one flat bucket each — the all-reduce and the single-launch
+Adam step work on them in place — and the logged scalars cross the bus in one copy per iteration. The *_host functions
+are the same formulas in plain torch: the specification the kernels are tested against, and what the world-size-2 gloo
+tests of the plumbing run on CPU tensors; ppo_train itself never calls them on a CUDA environment.
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 import time
@@ -27,8 +36,13 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import _cabi
 from ..distribution import GraphDistribution
 from ..feature_helpers import ObservationFeatureHelpers as OBS
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class PolicyModule(nn.Module):
@@ -78,8 +92,9 @@ class ValueModule(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def gae(value, next_value, reward, done, terminated, gamma=0.99, lmbda=0.95):
-    """torchrl 0.5.0 generalized_advantage_estimate over the leading time dimension. All inputs [T, ...]."""
+def gae_host(value, next_value, reward, done, terminated, gamma=0.99, lmbda=0.95):
+    """torchrl 0.5.0 generalized_advantage_estimate over the leading time dimension, in plain torch. All inputs
+    [T, ...]. The specification of tarl_gae (tests) — ppo_train uses gae_device."""
     not_term = 1.0 - terminated.to(value.dtype)
     not_done = 1.0 - done.to(value.dtype)
     delta = reward + gamma * next_value * not_term - value
@@ -91,17 +106,48 @@ def gae(value, next_value, reward, done, terminated, gamma=0.99, lmbda=0.95):
     return adv, adv + value
 
 
-def standardise(adv, group=None):
-    """average_gae=True: (A - mean) / std.clamp_min(1e-4), unbiased std; statistics over every rank's frames."""
+def standardise_host(adv, group=None):
+    """average_gae=True: (A - mean) / std.clamp_min(1e-4), unbiased std; statistics over every rank's frames. Plain
+    torch (specification / gloo tests)."""
     n = torch.tensor(float(adv.numel()), device=adv.device, dtype=torch.float64)
-    stats = torch.stack([n, adv.double().sum(), (adv.double() ** 2).sum()])
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(stats, group=group)
+    stats = reduce_stats(torch.stack([n, adv.double().sum(), (adv.double() ** 2).sum()]), group)
     n, s, ss = stats[0], stats[1], stats[2]
     mean = s / n
     var = (ss - n * mean * mean) / torch.clamp(n - 1, min=1.0)
     std = torch.sqrt(torch.clamp(var, min=0.0)).clamp_min(1e-4)
     return ((adv.double() - mean) / std).to(adv.dtype)
+
+
+def gae_device(v_frames, reward, done, terminated=None, gamma=0.99, lmbda=0.95, group=None):
+    """GAE + standardisation on the device (tarl_gae, tarl_standardise). v_frames: V over the T+1 frames of a rollout,
+    [T+1, R] contiguous (value = v_frames[:-1], next_value = v_frames[1:]); reward [T, R] fp32; done / terminated [T, R]
+    bool. Returns (standardised advantage [T, R], value_target [T, R]). The batch statistics are summed over the ranks
+    by one 3-double all-reduce; nothing comes back to the host."""
+    if not v_frames.is_cuda:
+        raise RuntimeError("gae_device computes on CUDA devices only (gae_host is the plain-torch formula)")
+    T, R = reward.shape
+    dev = reward.device
+    terminated = done if terminated is None else terminated
+    v_frames = v_frames.to(torch.float32).contiguous()
+    reward = reward.to(torch.float32).contiguous()
+    done8 = done.contiguous().view(torch.uint8)
+    term8 = terminated.contiguous().view(torch.uint8)
+    adv = torch.empty(T, R, dtype=torch.float32, device=dev)
+    target = torch.empty(T, R, dtype=torch.float32, device=dev)
+    lib = _cabi.lib()
+    partials = torch.empty(max(lib.tarl_gae_partial_count(R), 1), 2, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tarl_gae(v_frames.data_ptr(), v_frames[1:].data_ptr() if T > 0 else v_frames.data_ptr(), R,
+                          reward.data_ptr(), done8.data_ptr(), term8.data_ptr(), T, R, gamma, lmbda, adv.data_ptr(),
+                          target.data_ptr(), partials.data_ptr(), _stream(dev))
+    _cabi.check(rc, "tarl_gae")
+    # (torch.full is a fill kernel; `stats[0] = python_float` would be a synchronising host-to-device copy)
+    stats = torch.cat([torch.full((1,), float(T * R), dtype=torch.float64, device=dev), partials.sum(0)])
+    reduce_stats(stats, group)
+    with torch.cuda.device(dev):
+        rc = lib.tarl_standardise(adv.data_ptr(), T * R, stats.data_ptr(), _stream(dev))
+    _cabi.check(rc, "tarl_standardise")
+    return adv, target
 
 
 def clip_ppo_loss(log_prob, sample_log_prob, advantage, entropy, value, value_target, clip_epsilon=0.2,
@@ -123,25 +169,135 @@ def clip_ppo_loss(log_prob, sample_log_prob, advantage, entropy, value, value_ta
     return out
 
 
-def allreduce_gradients(params, group=None):
-    """One flat fp32 bucket, averaged over ranks (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
-    flat /= dist.get_world_size(group)
-    off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+def reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """{count, sum, sum of squares} of the advantages summed over the ranks, in place (one tiny all-reduce)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, group=group)
+    return stats
+
+
+class GradBucket:
+    """Parameters and gradients of a set of nn.Parameters as ONE flat fp32 buffer each (plain torch plumbing, any
+    device): every parameter is re-pointed at a slice of `flat` and its .grad at a slice of `grad`, so that the
+    backward pass accumulates straight into the buffer the gradient all-reduce — and, on CUDA, the single-launch
+    optimiser step — works on: no concatenation, no copy back."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        if any(p.device != dev or p.dtype != torch.float32 for p in self.params):
+            raise RuntimeError("GradBucket needs fp32 parameters on one device")
+        n = sum(p.numel() for p in self.params)
+        self.n, self.device = n, dev
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.grad[off:off + k].view(p.shape)
+                off += k
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def holds(self, params) -> bool:
+        """True when `params` are exactly the parameters of this bucket and still live in it."""
+        params = list(params)
+        if len(params) != len(self.params) or any(a is not b for a, b in zip(params, self.params)):
+            return False
+        off = 0
+        for p in self.params:
+            if p.data_ptr() != self.flat.data_ptr() + 4 * off:
+                return False
+            off += p.numel()
+        return True
+
+    def check_views(self):
+        """autograd keeps accumulating into the bucket only while every .grad is still the view handed out here."""
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                raise RuntimeError("a parameter's .grad was replaced: the gradient bucket is out of sync")
+            off += p.numel()
+
+    def broadcast(self, src: int = 0, group=None):
+        """Every rank starts from rank `src`'s parameters (only gradients are exchanged afterwards)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(self.flat, src=src, group=group)
+
+    def allreduce(self, group=None) -> int:
+        """Sum of the gradient bucket over the ranks, in place (NCCL over NVLink on the GPU box, gloo in the CPU
+        tests). Returns the world size: the consumer scales by its inverse."""
+        if dist.is_available() and dist.is_initialized():
+            world = dist.get_world_size(group)
+            if world > 1:
+                dist.all_reduce(self.grad, group=group)
+            return world
+        return 1
+
+
+class FlatAdam(GradBucket):
+    """Adam over the flat bucket in one launch (tarl_adam_step, csrc/optim.cu) — the reference's torch.optim.Adam(lr)
+    at src/rl/ppo_trainer.py:39 steps ~8 tensors with ~6 launches each — with the averaging of the all-reduced gradient
+    and the global gradient norm the reference logs (:141) folded into the same pass."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params)
+        if self.device.type != "cuda":
+            raise RuntimeError("FlatAdam steps on a CUDA device (no CPU fallback)")
+        n, dev = self.n, self.device
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.steps = float(lr), (float(betas[0]), float(betas[1])), float(eps), 0
+        self.norm_partials = torch.empty(max(_cabi.lib().tarl_adam_partial_count(n), 1), dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def reset_state(self, lr=None):
+        """A fresh optimiser on the same bucket (what constructing torch.optim.Adam anew does at the reference's
+        src/rl/ppo_trainer.py:39): moments and step count start over, parameter storage — which captured rollouts
+        read — stays where it is."""
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.grad.zero_()
+        self.steps = 0
+        if lr is not None:
+            self.lr = float(lr)
+        off = 0
+        for p in self.params:
+            p.grad = self.grad[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    def step(self, group=None):
+        """All-reduce of the gradient bucket, then one launch: scale by 1 / world, global gradient norm (left in
+        self.grad_norm, a device scalar), Adam update of every parameter."""
+        world = self.allreduce(group)
+        self.steps += 1
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_adam_step(self.flat.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                            self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1],
+                                            self.eps, self.steps, 1.0 / world, self.norm_partials.data_ptr(),
+                                            self.grad_norm.data_ptr(), _stream(self.device))
+        _cabi.check(rc, "tarl_adam_step")
+        for p in self.params:           # the kernel wrote through raw pointers: whoever caches by version (the TF32
+            torch.autograd.graph.increment_version(p)      # split of the value net's W1, csrc/value_mlp.cu) must see it
+        return self.grad_norm
 
 
 # ---------------------------------------------------------------------------------------------------------------
 class _EnvAdapter:
     """Uniform [R]-batched view of SimulatorEnv (R = 1, reference row layout) and BatchedSimulatorEnv (link store)."""
+
+    @classmethod
+    def of(cls, env):
+        """The adapter of an environment, kept on it: trajectory buffers, captured rollouts and the parameter bucket
+        survive from one ppo_train / collect call to the next."""
+        hit = env.__dict__.get("_tarl_adapter")
+        if hit is None:
+            hit = env.__dict__["_tarl_adapter"] = cls(env)
+        return hit
 
     def __init__(self, env):
         self.env = env
@@ -154,6 +310,30 @@ class _EnvAdapter:
         Nmax = env.Nmax if self.batched else env.simulator.Nmax
         self.static = g.x[..., 3 * Nmax:].reshape(-1, 7)[: self.n_nodes].clone()      # MAXN .. ROAD_INDEX template
         self.edge_features = g.edge_attr
+        self._traj = {}           # (T, slim) -> preallocated trajectory buffers, reused by every rollout of that shape
+        self._graphs = {}         # (T, ...) -> captured rollout (torch.cuda.CUDAGraph + what it leaves on the host side)
+
+    def trajectory_buffers(self, T: int, slim: bool):
+        """[T+1, R, ..] frames + per-step outputs, allocated once per (T, slim): a rollout writes them in place (frame t+1
+        of a step is the next step's frame t), the update reads them, the next rollout overwrites them — and a rollout
+        captured in a CUDA graph needs its outputs at fixed addresses anyway."""
+        key = (int(T), bool(slim))
+        hit = self._traj.get(key)
+        if hit is None:
+            R, M, dev = self.R, self.n_nodes, self.device
+            E = self.graph.edge_index.size(1)
+            hit = {"num": torch.empty(T + 1, R, M, dtype=torch.float32, device=dev),
+                   "sel": None if slim else torch.empty(T + 1, R, M, dtype=torch.float32, device=dev),
+                   "ai": None if slim else torch.empty(T + 1, R, M, dtype=torch.int64, device=dev),
+                   "times": torch.empty(T + 1, R, dtype=torch.float32, device=dev),
+                   "action": (torch.empty(T, E, R, dtype=torch.bool, device=dev).permute(0, 2, 1) if R > 1 else
+                              torch.empty(T, R, E, dtype=torch.bool, device=dev)),
+                   "occ": torch.zeros(T, R, dtype=torch.int32, device=dev),
+                   "lps": torch.zeros(T, R, dtype=torch.float32, device=dev)}
+            if len(self._traj) >= 4:
+                self._traj.clear(); self._graphs.clear()
+            self._traj[key] = hit
+        return hit
 
     def reset(self):
         if self.batched:
@@ -226,28 +406,21 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
     kernel into their frame (edge-major inside a frame: [T, R, E] with the replica innermost).
     occupancy_only=True (see occupancy_only()): SELECTED_ROAD and head-id frames are neither written nor kept
     ("sel" / "agent_index" are None in the result) — 4 instead of 16 bytes per node and frame."""
-    adapter.reset()
     R, M, dev = adapter.R, adapter.n_nodes, adapter.device
-    E = adapter.graph.edge_index.size(1)
     T = int(frames)
-    num = torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
     slim = bool(occupancy_only) and adapter.batched
-    sel = None if slim else torch.empty(T + 1, R, M, dtype=torch.float32, device=dev)
-    ai = None if slim else torch.empty(T + 1, R, M, dtype=torch.int64, device=dev)
+    buf = adapter.trajectory_buffers(T, slim)
+    num, sel, ai, times, action = buf["num"], buf["sel"], buf["ai"], buf["times"], buf["action"]
     frame = (lambda t: (num[t], None, None)) if slim else (lambda t: (num[t], sel[t], ai[t]))
-    times = torch.empty(T + 1, R, dtype=torch.float32, device=dev)
-    if R > 1:
-        action = torch.empty(T, E, R, dtype=torch.bool, device=dev).permute(0, 2, 1)
-    else:
-        action = torch.empty(T, R, E, dtype=torch.bool, device=dev)
+    dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
+    sink = adapter.action_sink() if isinstance(policy_module, PolicyModule) else None
+    if adapter.batched and not dynamic and isinstance(policy_module, PolicyModule) and not mode:
+        return _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_when_any_done)
+    adapter.reset()
     small = {k: [] for k in ("sample_log_prob", "reward", "done")}
     adapter.dynamic(out=frame(0))
     times[0] = adapter.time()
-    dynamic = getattr(policy_module.net, "reads_dynamic_features", True)
-    sink = adapter.action_sink() if isinstance(policy_module, PolicyModule) else None
     n = 0
-    if adapter.batched and not dynamic and isinstance(policy_module, PolicyModule) and not mode:
-        return _collect_static_policy(adapter, policy_module, T, frame, num, sel, ai, action, sink, break_when_any_done)
     for t in range(T):
         obs = adapter.observation(*frame(t), times[t], dynamic=dynamic)
         act = policy_module(obs, mode=mode, out=action[t], sink=sink)
@@ -257,8 +430,14 @@ def collect(adapter: _EnvAdapter, policy_module: PolicyModule, frames: int, mode
         small["reward"].append(reward)
         small["done"].append(done)
         n = t + 1
-        if break_when_any_done and bool(done.any()):
-            break
+        if bool(done.any()):
+            if break_when_any_done:
+                break
+            # the reference's SyncDataCollector resets a finished environment and carries on: frame t+1 becomes the
+            # first observation of the new episode (step t is marked done, so nothing bootstraps across the seam)
+            adapter.reset()
+            adapter.dynamic(out=frame(t + 1))
+            times[t + 1] = adapter.time()
     out = _trajectory(num, sel, ai, times, action, n)
     out.update({k: torch.stack(v) for k, v in small.items()})
     return out
@@ -275,60 +454,127 @@ def _trajectory(num, sel, ai, times, action, n):
     return out
 
 
-def _collect_static_policy(adapter, policy_module, T, frame, num, sel, ai, action, sink, break_when_any_done):
+def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_when_any_done):
     """The loop of collect() for a policy whose logits do not depend on the dynamic observation (MPNNPolicyNet's
     active path) on the link store: the distribution is built ONCE per rollout (the parameters do not change inside
     one) and a step is one sampling call + one environment step, with no per-step tensors on the host side — rewards
     accumulate in a [T, R] int32 buffer the environment's occupancy pointer walks through, times and done flags are
-    host numbers turned into tensors at the end. At 128 replicas per GPU the per-step host work (0.41 ms) was longer
-    than the step's kernels (0.32 ms)."""
+    host numbers.
+
+    All of it — the policy's logits row, the T sampling launches and the T environment steps — is a fixed sequence of
+    launches on fixed buffers: the second rollout of a shape is captured in a CUDA graph and every later one is a single
+    replay (at 128 replicas per GPU a step's launches took the host longer, 0.36 ms, than the GPU, 0.27 ms). What varies
+    between rollouts lives on the device: the parameters (read by the captured policy kernels) and the two noise keys
+    (BatchedSimulatorEnv.begin_rollout). TARL_NO_ROLLOUT_GRAPH=1 keeps the eager loop (same results: same launches)."""
     env, R, dev = adapter.env, adapter.R, adapter.device
     from ..reinforcement_learning import EPISODE_END
-    obs = adapter.observation(frame(0)[0], None, None, torch.zeros(R, device=dev), dynamic=False)
-    d = policy_module.dist(obs)
-    occ = torch.zeros(T, R, dtype=torch.int32, device=dev)
-    lps = torch.empty(T, R, dtype=torch.float32, device=dev)
-    host_time, host_done = [adapter.time()], []
-    keep_occ = env.occupancy
-    n = 0
-    try:
-        for t in range(T):
-            if policy_module.return_log_prob:
-                _, lp = d.sample(dtype=torch.bool, out=action[t], return_log_prob=True, sink=sink)
-                lps[t] = lp
-            else:
-                d.sample(dtype=torch.bool, out=action[t], sink=sink)
-                lps[t] = 0.0
-            applied = sink is not None and sink.applied
-            env.occupancy = occ[t]
-            env.step(None if applied else action[t], compact_out=frame(t + 1), lean=True)
-            host_time.append(adapter.time())
-            host_done.append(env.time > EPISODE_END)
-            n = t + 1
-            if break_when_any_done and host_done[-1]:
-                break
-    finally:
-        env.occupancy = keep_occ
-    times = torch.tensor(host_time, dtype=torch.float32, device=dev).unsqueeze(1).expand(n + 1, R)
+    num, sel, ai, action, occ, lps = buf["num"], buf["sel"], buf["ai"], buf["action"], buf["occ"], buf["lps"]
+    seed = int(torch.randint(0, 2 ** 62, (1,)))          # torch's default CPU generator: torch.manual_seed reproduces
+    env.begin_rollout(seed)
+    adapter.reset()
+    adapter.dynamic(out=frame(0))
+    t0, dt = adapter.time(), float(env.timestep)
+    steps_to_done = T
+    for k in range(T):                                    # host arithmetic: after which step does the episode end?
+        if t0 + dt * (k + 1) > EPISODE_END:
+            steps_to_done = k + 1
+            break
+    n = steps_to_done if (break_when_any_done and steps_to_done < T) else T
+    want_lp = bool(policy_module.return_log_prob)
+    if sink is not None:
+        sink = adapter.action_sink()                      # begin_rollout may have rebuilt it
+
+    def body():
+        obs = adapter.observation(frame(0)[0], None, None, torch.zeros(R, device=dev), dynamic=False)
+        d = policy_module.dist(obs)
+        keep_occ = env.occupancy
+        try:
+            for t in range(n):
+                if want_lp:
+                    _, lp = d.sample(dtype=torch.bool, out=action[t], return_log_prob=True, sink=sink)
+                    lps[t].copy_(lp)
+                else:
+                    d.sample(dtype=torch.bool, out=action[t], sink=sink)
+                applied = sink is not None and sink.applied
+                env.occupancy = occ[t]
+                env.step(None if applied else action[t], compact_out=frame(t + 1), lean=True)
+                if env.time > EPISODE_END and t + 1 < n:  # auto-reset (see collect): not part of a captured rollout
+                    adapter.reset()
+                    adapter.dynamic(out=frame(t + 1))
+        finally:
+            env.occupancy = keep_occ
+
+    crosses_end = steps_to_done < T
+    use_graph = (not os.environ.get("TARL_NO_ROLLOUT_GRAPH") and not crosses_end and sink is not None
+                 and env.metrics is None and n == T)
+    key = (T, want_lp, num.data_ptr(), action.data_ptr(), id(policy_module), t0, dt,
+           tuple(p.data_ptr() for p in policy_module.parameters()))
+    if not want_lp:
+        lps.zero_()
+    entry = adapter._graphs.get(key) if use_graph else None
+    if entry is not None and entry["graph"] is not None:
+        entry["graph"].replay()
+        env.time = entry["time"]
+        st = env.store
+        st.cur, st.step_id, st.t_last = entry["cur"], entry["step_id"], entry["t_last"]
+        sink.draw_id, sink.applied = entry["draw_id"], True
+    elif use_graph and entry is not None:                 # second rollout of this shape: capture it, then run it
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        st = env.store
+        before = (env.time, st.cur, st.step_id, st.t_last, sink.draw_id)
+        with torch.cuda.graph(graph):
+            body()
+        entry.update(graph=graph, time=env.time, cur=st.cur, step_id=st.step_id, t_last=st.t_last, draw_id=sink.draw_id)
+        env.time, st.cur, st.step_id, st.t_last, sink.draw_id = before        # capture ran nothing
+        graph.replay()
+        env.time = entry["time"]
+        st.cur, st.step_id, st.t_last = entry["cur"], entry["step_id"], entry["t_last"]
+        sink.draw_id = entry["draw_id"]
+    else:
+        body()
+        if use_graph:
+            adapter._graphs[key] = {"graph": None}        # seen once (kernels loaded, caches warm): capture next time
+    # times and done flags are host arithmetic and the same for every rollout of this shape: built (and copied to the
+    # device) once, so that no rollout ends in a host-to-device copy the host has to wait for
+    ck = ("clock", n, t0, dt, bool(break_when_any_done))
+    clock = buf.get(ck)
+    if clock is None:
+        host_time, host_done, now = [t0], [], t0
+        for k in range(n):
+            now += dt
+            host_done.append(now > EPISODE_END)
+            if now > EPISODE_END and k + 1 < n:           # frames after a seam carry the new episode's clock
+                from ..reinforcement_learning import EPISODE_START
+                now = float(EPISODE_START)
+            host_time.append(now)
+        clock = buf[ck] = (torch.tensor(host_time, dtype=torch.float32, device=dev).unsqueeze(1).expand(n + 1, R),
+                           torch.tensor(host_done, dtype=torch.bool, device=dev).unsqueeze(1).expand(n, R))
+    times, done = clock
     out = _trajectory(num, sel, ai, times, action, n)
     out["sample_log_prob"] = lps[:n]
     out["reward"] = -occ[:n].to(torch.float32)
-    out["done"] = torch.tensor(host_done, dtype=torch.bool, device=dev).unsqueeze(1).expand(n, R)
+    out["done"] = done
     return out
 
 
 def _values(adapter, value_module, batch, prefix=""):
-    """V(s) for every frame of the batch, one time step (R frames) at a time to bound the transient memory."""
+    """V(s) for every frame of the batch: [T, R]. A value net that reads the occupancy only sees all T R frames in ONE
+    call (the frames of a rollout are one contiguous [T, R, N_tot] array: a [T R, N_tot] occupancy matrix for the
+    tcgen05 kernel, whose grid then has work for every SM even at 128 replicas per GPU); other nets go one time step
+    (R frames) at a time to bound the transient memory."""
     T, R = batch["num"].shape[:2]
     fast = getattr(value_module.net, "forward_occupancy", None)
+    num, tm = batch[prefix + "num"], batch[prefix + "time"]
+    if fast is not None and num.is_contiguous() and T * R <= 65536:
+        return fast(num.reshape(T * R, -1), tm.reshape(T * R, 1).to(torch.float32).contiguous()).reshape(T, R)
     out = []
     for t in range(T):
-        time = batch[prefix + "time"][t].reshape(R, 1).to(torch.float32)
+        time = tm[t].reshape(R, 1).to(torch.float32)
         if fast is not None:
-            out.append(fast(batch[prefix + "num"][t], time).reshape(R))
+            out.append(fast(num[t], time).reshape(R))
         else:
-            obs = adapter.observation(batch[prefix + "num"][t], batch[prefix + "sel"][t], batch[prefix + "agent_index"][t],
-                                      batch[prefix + "time"][t])
+            obs = adapter.observation(num[t], batch[prefix + "sel"][t], batch[prefix + "agent_index"][t], tm[t])
             out.append(value_module(obs).reshape(R))
     return torch.stack(out)
 
@@ -338,17 +584,23 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
               log_interval=1, stochastic_eval=False, lr=1e-3, seed=0, history=None):
     """See the module docstring. `total_frames` / `frames_per_batch` count environment steps (each step advances
     every replica of a BatchedSimulatorEnv); `history` (optional list) receives one dict of scalars per iteration."""
-    adapter = _EnvAdapter(env)
-    eval_adapter = _EnvAdapter(eval_env) if eval_env is not None else None
+    adapter = _EnvAdapter.of(env)
+    eval_adapter = _EnvAdapter.of(eval_env) if eval_env is not None else None
     params = [p for p in list(policy_module.parameters()) + list(value_module.parameters()) if p.requires_grad]
     seen, uniq = set(), []
     for p in params:
         if id(p) not in seen:
             seen.add(id(p)); uniq.append(p)
     params = uniq
-    optim = torch.optim.Adam(params, lr=lr)
+    optim = adapter.__dict__.get("_optim")
+    if optim is not None and optim.holds(params):
+        optim.reset_state(lr)         # same nets as the previous call: their storage (and captured rollouts) stay valid
+    else:
+        optim = adapter._optim = FlatAdam(params, lr=lr)
+    optim.broadcast(0)                # ranks seeded differently would otherwise train divergent replicas silently
     rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
-    gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * rank)
+    dev = adapter.device
+    gen = torch.Generator(device=dev).manual_seed(seed + 7919 * rank)      # minibatch draws, on the device
     writer = None
     log_file = None
     if log_dir is not None and rank == 0:
@@ -360,25 +612,23 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
         except Exception:
             writer = None
     global_step = 0
-    n_iters = max(total_frames // frames_per_batch, 1)
+    n_iters = max(-(-total_frames // frames_per_batch), 1)       # the collector yields until total_frames are covered
     for it in range(n_iters):
         t0 = time.perf_counter()
         batch = collect(adapter, policy_module, frames_per_batch, occupancy_only=occupancy_only(policy_module, value_module))
         T, R = batch["reward"].shape
         global_step += frames_per_batch
-        rollout_s = time.perf_counter() - t0
+        rollout_s = time.perf_counter() - t0      # host time to enqueue the rollout (no synchronisation here)
         for _ in range(num_epochs):
             with torch.no_grad():
                 if "_frames" in batch:          # V over the T+1 frames once: value = V[:-1], next_value = V[1:]
                     v_all = _values(adapter, value_module, batch["_frames"])
-                    value, next_value = v_all[:-1], v_all[1:]
                 else:
-                    value = _values(adapter, value_module, batch)
-                    next_value = _values(adapter, value_module, batch, "next_")
-                adv, target = gae(value, next_value, batch["reward"], batch["done"], batch["done"])
-                adv = standardise(adv)
+                    v_all = torch.cat([_values(adapter, value_module, batch),
+                                       _values(adapter, value_module, batch, "next_")[-1:]])
+                adv, target = gae_device(v_all, batch["reward"], batch["done"], batch["done"])
             n = min(sub_batch_size, T * R)
-            pick = torch.randperm(T * R, generator=gen)[:n].to(adapter.device)
+            pick = torch.randperm(T * R, generator=gen, device=dev)[:n]
             ti, ri = pick // R, pick % R
             flat = lambda x: None if x is None else x[ti, ri]     # gathers n frames whatever the strides of the trajectory
             obs = adapter.observation(flat(batch["num"]), flat(batch["sel"]), flat(batch["agent_index"]), flat(batch["time"]))
@@ -389,15 +639,16 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
             losses = clip_ppo_loss(log_prob, flat(batch["sample_log_prob"]), flat(adv), entropy, v, flat(target))
             loss = losses["loss_objective"] + losses["loss_critic"] + losses["loss_entropy"]
             loss.backward()
-            allreduce_gradients(params)
-            grads = [p.grad for p in params if p.grad is not None]
-            grad_norm = torch.norm(torch.stack([g.norm() for g in grads])) if grads else torch.zeros(())
-            optim.step()
+            optim.check_views()
+            grad_norm = optim.step().clone()          # all-reduce + averaged-gradient norm + Adam: one launch
             optim.zero_grad()
-        rec = {"iteration": it, "global_step": global_step, "frames": T * R, "rollout_s": round(rollout_s, 4),
-               "avg_step_reward": float(batch["reward"].mean()), "episode_return": float(batch["reward"].sum(0).mean()),
-               "loss_total": float(loss.detach()), "grad_global_norm": float(grad_norm),
-               **{k: float(v.detach()) for k, v in losses.items()}}
+        rec = {"iteration": it, "global_step": global_step, "frames": T * R, "rollout_s": round(rollout_s, 4)}
+        # every logged scalar crosses the bus in ONE copy, and only when somebody will look at it
+        if history is not None or (rank == 0 and it % max(log_interval, 1) == 0 and (log_file or writer)):
+            names = ["avg_step_reward", "episode_return", "loss_total", "grad_global_norm"] + list(losses)
+            vals = torch.stack([batch["reward"].mean(), batch["reward"].sum(0).mean(), loss.detach(),
+                                grad_norm.reshape(())] + [losses[k].detach().to(torch.float32) for k in losses]).cpu()
+            rec.update({k: float(x) for k, x in zip(names, vals.tolist())})
         if eval_adapter is not None and eval_interval and it % eval_interval == 0:
             e0 = time.perf_counter()
             ev = collect(eval_adapter, policy_module, frames_per_batch, mode=True, break_when_any_done=True)
@@ -430,5 +681,22 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
     if log_file is not None:
         log_file.close()
     if checkpoint_path is not None and rank == 0:
-        torch.save(policy_module.net.state_dict(), checkpoint_path)
+        torch.save(reference_state_dict(policy_module), checkpoint_path)
     return history
+
+
+REFERENCE_POLICY_PREFIX = "module.0.module."
+
+
+def reference_state_dict(policy_module):
+    """policy.pt as the reference writes it (src/rl/ppo_trainer.py:157-159): the state dict of the
+    ProbabilisticActor(TensorDictModule(policy_net)) wrapper, i.e. the net's keys under "module.0.module.". A file
+    written here therefore loads into the reference's wrapped module, and load_policy_state reads both forms."""
+    return {REFERENCE_POLICY_PREFIX + k: v.detach().clone() for k, v in policy_module.net.state_dict().items()}
+
+
+def load_policy_state(policy_module, state):
+    """Loads a policy.pt written by this package or by the reference (wrapper-prefixed keys), or bare net keys."""
+    if any(k.startswith(REFERENCE_POLICY_PREFIX) for k in state):
+        state = {k[len(REFERENCE_POLICY_PREFIX):]: v for k, v in state.items() if k.startswith(REFERENCE_POLICY_PREFIX)}
+    return policy_module.net.load_state_dict(state)

@@ -1,6 +1,7 @@
-"""CPU tests of the host-side PPO logic (no kernels involved): GAE / ClipPPOLoss restatements against hand-written
-loops, and the multi-GPU plumbing (flat-bucket gradient all-reduce, global advantage statistics, replica sharding)
-under a world_size-2 gloo group."""
+"""CPU tests of the host-side PPO logic (no kernels involved): the plain-torch GAE / ClipPPOLoss formulas (the
+specification the device kernels are tested against in tests/test_ppo_device_gpu.py) against hand-written loops, and
+the multi-GPU plumbing ppo_train runs on every device — the flat parameter / gradient bucket with its in-place
+all-reduce and broadcast, the global advantage statistics, replica sharding — under a world_size-2 gloo group."""
 import os
 
 import pytest
@@ -16,7 +17,7 @@ def test_gae_matches_naive_recursion():
     T, R = 17, 3
     v, nv, r = (torch.randn(T, R, generator=g) for _ in range(3))
     done = torch.rand(T, R, generator=g) < 0.15
-    adv, target = P.gae(v, nv, r, done, done)
+    adv, target = P.gae_host(v, nv, r, done, done)
     for j in range(R):
         run = 0.0
         for t in reversed(range(T)):
@@ -29,9 +30,9 @@ def test_gae_matches_naive_recursion():
 
 def test_standardise_single_process():
     a = torch.randn(50, 4)
-    s = P.standardise(a)
+    s = P.standardise_host(a)
     assert torch.allclose(s, (a - a.mean()) / a.std().clamp_min(1e-4), atol=1e-5)
-    assert torch.equal(P.standardise(torch.zeros(8)), torch.zeros(8))       # std clamp: 0 / 1e-4
+    assert torch.equal(P.standardise_host(torch.zeros(8)), torch.zeros(8))       # std clamp: 0 / 1e-4
 
 
 def test_clip_ppo_loss_formulas():
@@ -50,15 +51,20 @@ def test_clip_ppo_loss_formulas():
 def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))     # same init on all ranks
+    torch.manual_seed(rank)                       # DIFFERENT initial parameters: the broadcast must level them
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))
+    bucket = P.GradBucket(list(net.parameters()))
+    init = bucket.flat.clone()
+    bucket.broadcast(0)
     x = torch.randn(16, 5, generator=torch.Generator().manual_seed(100 + rank))
     net(x).pow(2).mean().backward()
+    bucket.check_views()                          # autograd accumulated into the bucket, not into fresh tensors
     local = [p.grad.clone() for p in net.parameters()]
-    P.allreduce_gradients(list(net.parameters()))
+    world_seen = bucket.allreduce()
     adv = torch.randn(30, generator=torch.Generator().manual_seed(200 + rank)) * (1 + rank)
-    torch.save({"local": local, "reduced": [p.grad.clone() for p in net.parameters()], "adv": adv,
-                "std": P.standardise(adv)}, os.path.join(out_dir, f"r{rank}.pt"))
+    torch.save({"local": local, "summed": [p.grad.clone() for p in net.parameters()], "adv": adv, "world": world_seen,
+                "init": init, "start": bucket.flat.clone(), "std": P.standardise_host(adv)},
+               os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -66,9 +72,12 @@ def test_two_rank_gradient_allreduce_and_global_statistics(tmp_path):
     world, port = 2, 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     r = [torch.load(tmp_path / f"r{k}.pt") for k in range(world)]
-    for k, g in enumerate(r[0]["reduced"]):
-        assert torch.allclose(g, (r[0]["local"][k] + r[1]["local"][k]) / 2, atol=1e-7)
-        assert torch.equal(g, r[1]["reduced"][k])                          # every rank applies the same update
+    assert r[0]["world"] == r[1]["world"] == 2
+    assert not torch.equal(r[0]["init"], r[1]["init"]) and torch.equal(r[0]["start"], r[1]["start"])
+    assert torch.equal(r[0]["start"], r[0]["init"])                        # rank 0's parameters won
+    for k, g in enumerate(r[0]["summed"]):
+        assert torch.allclose(g, r[0]["local"][k] + r[1]["local"][k], atol=1e-7)
+        assert torch.equal(g, r[1]["summed"][k])                           # every rank applies the same update
     both = torch.cat([r[0]["adv"], r[1]["adv"]])
     ref = (both - both.mean()) / both.std().clamp_min(1e-4)
     assert torch.allclose(torch.cat([r[0]["std"], r[1]["std"]]), ref, atol=1e-5)
