@@ -527,6 +527,7 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     # algorithmic bytes per edge: policy 28 B + GraphDistribution 24 B = 52 B/edge (+4 B/node)
     pol_bytes = B * (52 * E_full + 4 * N_tot)
     val_bytes = B * (2 * (12 * E_full) + 2 * 68 * N_tot)          # fwd + bwd: 12 B/edge + 68 B/node each
+    train_bytes = B * (36 * E_full + 92 * N_tot)                  # train mode: a keep word and a message per (row, edge)
     return {"metric": "MPNN fwd+bwd edges/s", "unit": "edges/s", "batch_rows": B, "edges_full_graph": E_full,
             "nodes_full_graph": N_tot, "iters": iters,
             "policy_distribution": {"value": round(world * B * E_full / (pol_ms / 1e3), 1), "ms_per_iter": round(pol_ms, 4),
@@ -541,6 +542,13 @@ def mpnn_bench(args, g, dev, world, rank, peak):
                                        "frac": round(val_bytes / (val_ms / 1e3) / 1e9 / peak, 4)}},
             "value_net_train_mode": {"value": round(world * B * E_full / (val_train_ms / 1e3), 1),
                                      "ms_per_iter": round(val_train_ms, 4),
+                                     "roofline": {"bound": "hbm", "algorithmic_bytes": int(train_bytes),
+                                                  "achieved": round(train_bytes / (val_train_ms / 1e3) / 1e9, 1),
+                                                  "peak": peak, "unit": "GB/s",
+                                                  "frac": round(train_bytes / (val_train_ms / 1e3) / 1e9 / peak, 4),
+                                                  "how": "per (row, edge): message 4 w + 4 r, keep word 4 w + 8 r, d z 4 w + "
+                                                         "4 r, gm gather 4 = 36 B; per (row, node): the 16 message inputs "
+                                                         "assembled twice (28 + 8 B each) + mean / v / gm 20 B = 92 B"},
                                      "what": "MPNNValueNet.forward (train: message dropout p = 0.05, keep words drawn in "
                                              "the kernel) -> backward (message_dropout, aggregate_msg, node_grad, "
                                              "edge_grad_dropout, finish): the per-node projection does not factor "

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 19
+#define TARL_ABI_VERSION 21
 
 /* return codes */
 #define TARL_OK 0
@@ -312,10 +312,14 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
  * stream they come from is declared divergence D4 either way. The counter is (group, (row_offset + row) / 4, draw_id):
  * row_offset = global index of this call's first row (replicas sharded over ranks draw different uniforms from one
  * seed), draw_id = which draw of the seed this is (the step of a rollout); seed_dev: NULL, or a device word holding the
- * key instead of `seed` (a call captured in a CUDA graph then draws differently on every replay). row_offset % 4 == 0. */
+ * key instead of `seed` (a call captured in a CUDA graph then draws differently on every replay). row_offset % 4 == 0.
+ * prev_links / prev_sources: NULL, or the SELECTED_ROAD arrays of the previous step when sel_links / sel_sources are a
+ * SECOND pair of buffers (a rollout alternates two pairs so that the draw of step t+1 can run while step t still reads
+ * its decisions): a group without a hit then copies its previous value instead of leaving the entry untouched. */
 int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
                                 const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
                                 const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
+                                const float* prev_links, const float* prev_sources,
                                 int32_t n_links, int32_t n_nodes, uint64_t seed, const uint64_t* seed_dev,
                                 uint32_t draw_id, int32_t row_offset, void* stream);
 
@@ -355,8 +359,12 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
  * from Philox4x32-10 keyed by `seed` (tarl_value_mp_dropout_bits writes the words of that stream: what the kernels
  * will use for the same seed / p). keep_words: NULL, or [E*B] scratch (element (b, e) at e*B + b): with keep_bits ==
  * NULL the forward pass stores the words it draws there and the backward pass reads them back instead of drawing them
- * again. msg: [E*B] output, element (b, e) at e*B + b (the tanh messages; backward reads
- * them back). mean, v as in tarl_value_mp_forward. */
+ * again. msg: [E*B] output (the tanh messages; backward reads them back and overwrites them). Both are kept in
+ * BY-TARGET order: element (b, e) at pos(e)*B + b, pos(e) = position of edge e in by_target (a target node's in-edges are
+ * contiguous: the backward pass finds them without loading an edge id first). source_pos: [E] int32, entry j = pos of
+ * the j-th edge of by_source (static, built once per graph). mean, v as in tarl_value_mp_forward.
+ * In-kernel stream for p <= 1/16: ONE Philox block per (row, edge) — 17 top nibbles decide 15 of 16 inputs, the rare
+ * zero nibbles take a low byte from the block's 7 spare bytes; larger p: two blocks, 17 twelve-bit fields. */
 int tarl_value_mp_dropout_bits(uint64_t seed, float p, int32_t batch, int32_t n_edges, uint32_t* keep_bits, void* stream);
 int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
                                   int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
@@ -364,14 +372,16 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                                   int32_t agent_rows, const float* msg_weight, const float* msg_bias,
                                   const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                  uint32_t* keep_words, float* msg, float* mean, float* v, int32_t* flags, void* stream);
-/* grads / gm / partials as in tarl_value_mp_backward; keep_bits / seed / p must be the forward call's. */
+                                  const int32_t* source_pos, uint32_t* keep_words, float* msg, float* mean, float* v,
+                                  int32_t* flags, void* stream);
+/* grads / gm / partials as in tarl_value_mp_backward; keep_bits / seed / p must be the forward call's. msg is
+ * OVERWRITTEN (it becomes d z, the gradient at the tanh's argument). */
 int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
                                    int64_t nf_batch_stride, int64_t nf_row_stride, const float* edge_features,
                                    int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                                    int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                   const uint32_t* keep_words, const float* msg, const float* mean, const float* v,
+                                   const uint32_t* keep_words, float* msg, const float* mean, const float* v,
                                    const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream);

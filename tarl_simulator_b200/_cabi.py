@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 19       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 21       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -124,8 +124,8 @@ SIGNATURES = {
     "tarl_graphdist_forward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _ROWS, _ROWS, _P, _P, _P, _P]),
     "tarl_graphdist_backward": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _I32, _P, _P, _P, _ROWS, _P]),
     "tarl_graphdist_sample": (C.c_int, [_CSR1, _ROWS, _F, _I32, _ROWS, _ROWS, _I32, _P, _P, _P]),
-    "tarl_graphdist_sample_apply": (C.c_int, [_CSR1, _P, _F, _I32, _ROWS, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, C.c_uint64,
-                                              _P, C.c_uint32, _I32, _P]),
+    "tarl_graphdist_sample_apply": (C.c_int, [_CSR1, _P, _F, _I32, _ROWS, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32,
+                                              C.c_uint64, _P, C.c_uint32, _I32, _P]),
     "tarl_value_mp_partial_count": (_I32, [_I32, _I32]),
     "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
                                         _P, _P, _P, _P]),
@@ -133,7 +133,7 @@ SIGNATURES = {
                                          _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tarl_value_mp_dropout_bits": (C.c_int, [C.c_uint64, _F, _I32, _I32, _P, _P]),
     "tarl_value_mp_forward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32,
-                                                _I32, _P, _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P]),
+                                                _I32, _P, _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P, _P]),
     "tarl_value_mp_backward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I32, _I32, _P,
                                                  _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
     "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -193,7 +193,23 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
         for (int i = h; i >= 0; i = nx[i]) {
             const int end = ai.org_ptr[ai.origins[i] + 1];
             int k = cur[i];
-            while (k < end && !agent_ready(at, r, ai.org_agent[k], t)) ++k;
+            // first ready agent at or after k. Four candidates per round: their ids and then their rows are loaded
+            // together — two dependent loads per FOUR skipped agents instead of per agent (the walk over agents that
+            // are already on their way or done is the longest dependent chain of an insertion step)
+            while (k < end) {
+                int cand[4];
+                bool rdy[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cand[q] = k + q < end ? ai.org_agent[k + q] : -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rdy[q] = cand[q] >= 0 && agent_ready(at, r, cand[q], t);
+                int first = 4;
+#pragma unroll
+                for (int q = 3; q >= 0; --q) first = rdy[q] ? q : first;
+                k += first;
+                if (first < 4) break;
+            }
+            if (k > end) k = end;
             cur[i] = k;
             if (k < end && ai.org_agent[k] < best_a) { best_a = ai.org_agent[k]; best_i = i; }
         }

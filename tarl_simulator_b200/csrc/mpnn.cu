@@ -738,6 +738,8 @@ struct BcApply {
     float* sel_links;            // [batch, n_links]
     float* sel_sources;          // [batch, n_nodes - n_links]
     int n_links, n_nodes;
+    const float* prev_links;     // nullptr, or the SELECTED_ROAD arrays of the PREVIOUS step when this call writes a fresh
+    const float* prev_sources;   // pair of buffers: a group without a hit then carries its previous value over
 };
 
 __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, const float* __restrict__ lg, float inv_t, int B,
@@ -894,10 +896,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, c
                     const int node = ap.group_node[g];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        if (hit[q] < 0) continue;
+                        const bool lk = node < ap.n_links;
+                        const int64_t at = lk ? (int64_t)(row0 + q) * ap.n_links + node
+                                              : (int64_t)(row0 + q) * (ap.n_nodes - ap.n_links) + (node - ap.n_links);
+                        if (hit[q] < 0) {
+                            if (ap.prev_links != nullptr) { if (lk) ap.sel_links[at] = ap.prev_links[at]; else ap.sel_sources[at] = ap.prev_sources[at]; }
+                            continue;
+                        }
                         const float v = (float)ap.edge_dst[grp.eid[k0 + hit[q]]];
-                        if (node < ap.n_links) ap.sel_links[(int64_t)(row0 + q) * ap.n_links + node] = v;
-                        else ap.sel_sources[(int64_t)(row0 + q) * (ap.n_nodes - ap.n_links) + (node - ap.n_links)] = v;
+                        if (lk) ap.sel_links[at] = v; else ap.sel_sources[at] = v;
                     }
                 }
             }
@@ -913,11 +920,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_gd_sample_bcast(tarl_csr grp, c
             const int node = live ? ap.group_node[g] : 0;
             const bool is_link = node < ap.n_links;
             float* const base = is_link ? ap.sel_links + node : ap.sel_sources + (node - ap.n_links);
+            const float* const prev = ap.prev_links == nullptr ? nullptr
+                                      : (is_link ? ap.prev_links + node : ap.prev_sources + (node - ap.n_links));
             const int64_t pitch = is_link ? ap.n_links : ap.n_nodes - ap.n_links;
             for (int r = warp; r < rows_here; r += kThreads / 32) {
                 if (!live) continue;
                 const uint8_t h = sm_hit[lane * kBcPitch + r];
                 if (h < kBcDeg) base[(int64_t)(row_base + r) * pitch] = (float)sm_dst[lane][h];
+                else if (prev != nullptr && h != kBcBig) base[(int64_t)(row_base + r) * pitch] = prev[(int64_t)(row_base + r) * pitch];
             }
         }
     }
@@ -1266,6 +1276,7 @@ int tarl_graphdist_sample(const tarl_csr* groups, const tarl_rows* logits, float
 int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row, float temperature, int32_t batch,
                                 const tarl_rows* uniforms, uint8_t* onehot, float* log_prob, float* partials,
                                 const int32_t* group_node, const int32_t* edge_dst, float* sel_links, float* sel_sources,
+                                const float* prev_links, const float* prev_sources,
                                 int32_t n_links, int32_t n_nodes, uint64_t seed, const uint64_t* seed_dev,
                                 uint32_t draw_id, int32_t row_offset, void* stream) {
     int rc = check_csr(groups);
@@ -1277,7 +1288,8 @@ int tarl_graphdist_sample_apply(const tarl_csr* groups, const float* logits_row,
     if (!logits_row || !onehot || (reinterpret_cast<uintptr_t>(onehot) & 3) != 0 ||
         !group_node || !edge_dst || !sel_links || (n_nodes > n_links && !sel_sources))
         return TARL_E_BADARG;
-    const BcApply ap = {group_node, edge_dst, sel_links, sel_sources, n_links, n_nodes};
+    if (prev_links != nullptr && n_nodes > n_links && prev_sources == nullptr) return TARL_E_BADARG;
+    const BcApply ap = {group_node, edge_dst, sel_links, sel_sources, n_links, n_nodes, prev_links, prev_sources};
     return launch_sample_bcast(groups, logits_row, temperature, batch, uniforms, onehot, log_prob, partials, ap, seed,
                                seed_dev, draw_id, row_offset, static_cast<cudaStream_t>(stream));
 }

@@ -381,13 +381,51 @@ __device__ __forceinline__ void philox_raw(uint32_t c0, uint32_t c1, uint32_t c2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// keep word of (row b, edge e): bit k set = message input k survives (k < 16 node inputs, k = 16 edge feature)
+// keep word of (row b, edge e): bit k set = message input k survives (k < 16 node inputs, k = 16 edge feature).
+// Input k is dropped iff a 12-bit uniform u_k < thresh = round(p * 4096). For thresh <= 256 (p <= 1/16: the reference's
+// 0.05) ONE Philox call serves all 17 inputs: 17 four-bit fields are the TOP nibbles of the u_k — a non-zero nibble
+// means u_k >= 256 >= thresh, kept, with no further bits (15 of 16 fields) — and the rare zero nibbles take their low
+// byte from the 7 spare bytes of the same 128 bits (u_k = low byte); a word with more than 7 zero nibbles (6e-6 of them)
+// draws a second block. Exactly Bernoulli(thresh / 4096) per input, independent; half the instructions of the generic
+// form below (two calls, 17 twelve-bit fields), which serves larger p.
+// flags of the zero nibbles of x (bit k = nibble k of x is 0), k = 0..7, without a loop
+__device__ __forceinline__ uint32_t zero_nibbles(uint32_t x) {
+    uint32_t z = ~(x | (x >> 1) | (x >> 2) | (x >> 3)) & 0x11111111u;             // bit 4k
+    z = (z | (z >> 3)) & 0x03030303u;                                             // 2 flags per byte
+    z = (z | (z >> 6)) & 0x000f000fu;                                             // 4 flags per half word
+    return (z | (z >> 12)) & 0xffu;
+}
+
 __device__ __forceinline__ uint32_t philox_keep_word(const Drop& d, int b, int e) {
+    if (d.thresh <= 256u) {
+        uint32_t r[4];
+        philox_raw((uint32_t)e, (uint32_t)b, 0u, 0x44524f50u, d.seed_lo, d.seed_hi, r);
+        // top nibbles: inputs 0-7 in r[0], 8-15 in r[1], 16 in the low nibble of r[2]
+        uint32_t zero = zero_nibbles(r[0]) | (zero_nibbles(r[1]) << 8) | (((r[2] & 0xfu) == 0u) ? (1u << 16) : 0u);
+        uint32_t word = 0x1ffffu;
+        int used = 0;                                                             // spare bytes: r[3] (4), then r[2] >> 4 (3)
+        while (zero != 0u) {                                                      // 1.06 iterations on average
+            const int k = __ffs((int)zero) - 1;
+            zero &= zero - 1u;
+            uint32_t byte;
+            if (used < 4) byte = (r[3] >> (8 * used)) & 0xffu;
+            else if (used < 7) byte = (r[2] >> (4 + 8 * (used - 4))) & 0xffu;
+            else {                                                                // more than 7 zero nibbles: 6e-6 of the words
+                uint32_t q[4];
+                philox_raw((uint32_t)e, (uint32_t)b, (uint32_t)(1 + ((used - 7) >> 4)), 0x44524f50u, d.seed_lo, d.seed_hi, q);
+                const int i = (used - 7) & 15;
+                byte = (q[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            }
+            ++used;
+            if (byte < d.thresh) word &= ~(1u << k);
+        }
+        return word;
+    }
     uint32_t word = 0;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {            // 2 draws x 2 sixty-four-bit halves x 5 twelve-bit fields; the first 17 are used
         uint32_t r[4];
-        philox_raw((uint32_t)e, (uint32_t)b, (uint32_t)j, 0x44524f50u, d.seed_lo, d.seed_hi, r);
+        philox_raw((uint32_t)e, (uint32_t)b, (uint32_t)j, 0x44524f51u, d.seed_lo, d.seed_hi, r);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint64_t v = (uint64_t)r[2 * h] | ((uint64_t)r[2 * h + 1] << 32);
@@ -400,9 +438,12 @@ __device__ __forceinline__ uint32_t philox_keep_word(const Drop& d, int b, int e
     }
     return word;
 }
-__device__ __forceinline__ uint32_t keep_word(const Drop& d, int B, int b, int e) {
-    if (d.bits != nullptr) return d.bits[(int64_t)b * d.bits_bs + e];            // injected, [B, E]
-    if (d.words != nullptr) return d.words[(int64_t)e * B + b];                  // what the forward pass drew, [E, B]
+// k = position of edge e in the by-target CSR: the buffers the train-mode passes hand each other (messages, drawn
+// words, d z) are kept in THAT order — element (b, k) at k*B + b — so that a (target node, row) pair finds its in-edges'
+// entries at addresses that depend on k alone: no edge-id load sits in front of them.
+__device__ __forceinline__ uint32_t keep_word(const Drop& d, int B, int b, int e, int k) {
+    if (d.bits != nullptr) return d.bits[(int64_t)b * d.bits_bs + e];            // injected, [B, E] by edge id
+    if (d.words != nullptr) return d.words[(int64_t)k * B + b];                  // what the forward pass drew, [E, B] by k
     return philox_keep_word(d, b, e);
 }
 
@@ -417,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) k_value_dropout_bits(Drop d, int B, 
 // the observation is laid out and parked in shared memory as products (x_k * scale) * w_k — 16 planes of the tile.
 // Walk 2, rows innermost: msg[e,b] = tanh(sum_k keep_k * product_k + keep_16 * (f * scale) * w_16 + w0) for every
 // in-edge e of the node (x * (mask / (1 - p)) as ATen's dropout computes it, then the 17-term dot product), written
-// edge-major with the row innermost. (A thread per pair that loads its inputs itself, rows innermost, reads one sector
+// with the row innermost at the edge's by-target position k (see keep_word). (A thread per pair that loads its inputs itself, rows innermost, reads one sector
 // per lane and input: measured 2.8 ms instead of ~1 ms at 32 rows x 6.0 M edges.)
 constexpr int kDropSmemBytes = kIn * tarl::kTileSmem * (int)sizeof(float);
 __global__ void __launch_bounds__(tarl::kTileThreads) k_value_message_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
@@ -451,19 +492,20 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_message_dropout(ta
         const float* ef = in.ef + b * in.ef_bs;
         for (int k = k0; k < k1; ++k) {
             const int e = by_dst.eid[k];
-            const uint32_t word = keep_word(d, in.B, b, e);
-            if (words_out != nullptr) words_out[(int64_t)e * in.B + b] = word;   // backward reads them instead of redrawing
+            const uint32_t word = keep_word(d, in.B, b, e, k);
+            if (words_out != nullptr) words_out[(int64_t)k * in.B + b] = word;   // backward reads them instead of redrawing
             float z = 0.0f;
 #pragma unroll
             for (int c = 0; c < kIn; ++c) z += ((word >> c) & 1u) ? x[c] : 0.0f;
             z += ((word >> kIn) & 1u) ? (ef[e] * d.scale) * we : 0.0f;
-            msg[(int64_t)e * in.B + b] = tanhf(z + bias);
+            msg[(int64_t)k * in.B + b] = tanhf(z + bias);
         }
     });
 }
 
 // one thread per (source node, batch row): mean of the stored messages in ascending edge id, then the node update
-__global__ void __launch_bounds__(kThreads) k_value_aggregate_msg(tarl_csr by_src, int B, int N,
+__global__ void __launch_bounds__(kThreads) k_value_aggregate_msg(tarl_csr by_src, const int32_t* __restrict__ src_pos,
+                                                                  int B, int N,
                                                                   const float* __restrict__ a, const float* __restrict__ c,
                                                                   const float* __restrict__ msg, float* __restrict__ mean,
                                                                   float* __restrict__ v) {
@@ -472,18 +514,71 @@ __global__ void __launch_bounds__(kThreads) k_value_aggregate_msg(tarl_csr by_sr
     const int n = (int)(i / B), b = (int)(i % B);
     const int k0 = by_src.ptr[n], k1 = by_src.ptr[n + 1];
     float acc = 0.0f;
-    for (int k = k0; k < k1; ++k) acc += msg[(int64_t)by_src.eid[k] * B + b];
+    for (int k = k0; k < k1; ++k) acc += msg[(int64_t)src_pos[k] * B + b];       // ascending edge id, as scatter-mean adds
     const float m = k1 > k0 ? acc / (float)(k1 - k0) : 0.0f;
     mean[i] = m;
     v[i] = tanhf(a[0] * m + c[0]);
 }
 
-// message backward with dropout, over the same (target node, row) tiles as k_value_edge_grad (one partial row per
-// tile): d z = gm[source, b] * (1 - msg^2); d w_k += d z * keep_k * scale * x_k; d w_16 += d z * keep_16 * scale * f;
-// d w0 += d z. The inputs x_k * scale are staged like the forward pass stages its products.
+// Message backward with dropout, in two passes.
+// Pass 1, edge-parallel and streaming (one thread per by-target position k and 4 rows): d z = gm[source, b] * (1 - msg^2)
+// overwrites the message in place; the two gradients that need nothing of the target node ride along —
+// d w_16 += d z * keep_16 * scale * f and d w0 += d z — as per-CTA partial sums (fixed grid, fixed order).
+constexpr int kDzCtas = 148 * 8;
+__global__ void __launch_bounds__(kThreads) k_value_dz(tarl_csr by_dst, Inputs in, Drop d, float* __restrict__ msg,
+                                                       const float* __restrict__ gm, float* __restrict__ partials) {
+    const int B = in.B;
+    const int64_t total = (int64_t)by_dst.n_edges * B;
+    float vals[2] = {0.0f, 0.0f};
+    const bool vec = (B & 3) == 0;
+    const int64_t step = (int64_t)gridDim.x * kThreads;
+    if (vec) {
+        const int64_t quads = total >> 2;
+        const int qpe = B >> 2;                                   // quads per edge
+        const int qsh = (qpe & (qpe - 1)) == 0 ? 31 - __clz(qpe) : -1;
+        for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < quads; q += step) {
+            const int k = qsh >= 0 ? (int)(q >> qsh) : (int)(q / qpe);
+            const int b = (int)(q - (int64_t)k * qpe) << 2;
+            const int e = by_dst.eid[k];
+            const float4 m = *reinterpret_cast<const float4*>(msg + (int64_t)k * B + b);
+            const float4 g = *reinterpret_cast<const float4*>(gm + (int64_t)by_dst.idx[k] * B + b);
+            float4 z;
+            z.x = g.x * (1.0f - m.x * m.x); z.y = g.y * (1.0f - m.y * m.y);
+            z.z = g.z * (1.0f - m.z * m.z); z.w = g.w * (1.0f - m.w * m.w);
+            *reinterpret_cast<float4*>(msg + (int64_t)k * B + b) = z;
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t word = keep_word(d, B, b + r, e, k);
+                if ((word >> kIn) & 1u) vals[0] += zz[r] * (in.ef[(int64_t)(b + r) * in.ef_bs + e] * d.scale);
+                vals[1] += zz[r];
+            }
+        }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += step) {
+            const int k = (int)(i / B), b = (int)(i - (int64_t)k * B);
+            const int e = by_dst.eid[k];
+            const float m = msg[i];
+            const float z = gm[(int64_t)by_dst.idx[k] * B + b] * (1.0f - m * m);
+            msg[i] = z;
+            const uint32_t word = keep_word(d, B, b, e, k);
+            if ((word >> kIn) & 1u) vals[0] += z * (in.ef[(int64_t)b * in.ef_bs + e] * d.scale);
+            vals[1] += z;
+        }
+    }
+    float all[kGrads];
+#pragma unroll
+    for (int j = 0; j < kGrads; ++j) all[j] = 0.0f;
+    all[16] = vals[0]; all[17] = vals[1];
+    block_store<kGrads>(all, partials + (size_t)blockIdx.x * kGrads);
+}
+
+// Pass 2, (target node, row) tiles as in the forward pass: d w_k += (sum over in-edges of keep_k * d z) * scale * x_k.
+// The in-edges' d z and keep words sit at k*B + b: nothing has to be loaded to find them, and the next edge's pair is
+// requested before the current one is consumed (the round-1 form walked edge id -> message, word, source -> gm one
+// dependent load after the other: 4.7 ms at 7 % of the DRAM bandwidth for 32 rows x 6.0 M edges).
 __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
-                                                                                const float* __restrict__ msg,
-                                                                                const float* __restrict__ gm,
+                                                                                const float* __restrict__ dz,
                                                                                 float* __restrict__ partials) {
     extern __shared__ float xs[];                                 // [kIn][kTileSmem]
     const tarl::Tile t = tarl::tile_here(in.B, Bp);
@@ -498,9 +593,10 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad_dropout(
         for (int c = 0; c < kIn; ++c) xs[c * tarl::kTileSmem + slot] = x[c] * d.scale;
     });
     __syncthreads();
-    float vals[18];
+    float vals[kIn];
 #pragma unroll
-    for (int j = 0; j < 18; ++j) vals[j] = 0.0f;
+    for (int j = 0; j < kIn; ++j) vals[j] = 0.0f;
+    const bool stored = d.bits == nullptr && d.words != nullptr;  // words at k*B + b: prefetchable
     tarl::tile_walk_rows(t, [&](int r, int j) {
         const int n = t.n0 + j, b = t.b0 + r;
         if (n >= in.N || r >= t.nrows) return;
@@ -509,25 +605,28 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad_dropout(
         float gx[kIn];
 #pragma unroll
         for (int c = 0; c < kIn; ++c) gx[c] = 0.0f;
-        const float* ef = in.ef + b * in.ef_bs;
-        float gwe = 0.0f, gs = 0.0f;
+        float gz_nxt = dz[(int64_t)k0 * in.B + b];
+        uint32_t w_nxt = stored ? d.words[(int64_t)k0 * in.B + b] : 0u;
         for (int k = k0; k < k1; ++k) {
-            const int e = by_dst.eid[k];
-            const float m = msg[(int64_t)e * in.B + b];
-            const float gz = gm[(int64_t)by_dst.idx[k] * in.B + b] * (1.0f - m * m);
-            const uint32_t word = keep_word(d, in.B, b, e);
+            const float gz = gz_nxt;
+            uint32_t word = w_nxt;
+            if (k + 1 < k1) {
+                gz_nxt = dz[(int64_t)(k + 1) * in.B + b];
+                if (stored) w_nxt = d.words[(int64_t)(k + 1) * in.B + b];
+            }
+            if (!stored) word = keep_word(d, in.B, b, by_dst.eid[k], k);
 #pragma unroll
             for (int c = 0; c < kIn; ++c) gx[c] += ((word >> c) & 1u) ? gz : 0.0f;
-            gwe += ((word >> kIn) & 1u) ? gz * (ef[e] * d.scale) : 0.0f;
-            gs += gz;
         }
         const int slot = tarl::tile_slot(t, r, j);
 #pragma unroll
         for (int c = 0; c < kIn; ++c) vals[c] += gx[c] * xs[c * tarl::kTileSmem + slot];
-        vals[16] += gwe;
-        vals[17] += gs;
     });
-    block_store<18>(vals, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads);
+    float all[18];
+#pragma unroll
+    for (int j = 0; j < kIn; ++j) all[j] = vals[j];
+    all[16] = 0.0f; all[17] = 0.0f;
+    block_store<18>(all, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads);
 }
 
 // both dropout kernels stage 16 planes of a tile: 66 KB of dynamic shared memory, opted in once per process
@@ -567,7 +666,8 @@ int check(const tarl_csr* c, int n_nodes) {
 extern "C" {
 
 int32_t tarl_value_mp_partial_count(int32_t n_nodes, int32_t batch) {
-    return (n_nodes > 0 && batch > 0) ? tarl::tile_count(n_nodes, batch) : 0;
+    // one row per (node, row) tile + the rows of the train-mode d z pass (a fixed grid)
+    return (n_nodes > 0 && batch > 0) ? tarl::tile_count(n_nodes, batch) + kDzCtas : 0;
 }
 
 int tarl_value_mp_forward(const tarl_csr* by_source, const float* node_features, int64_t nf_batch_stride,
@@ -649,7 +749,8 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                                   int32_t agent_rows, const float* msg_weight, const float* msg_bias,
                                   const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                  uint32_t* keep_words, float* msg, float* mean, float* v, int32_t* flags, void* stream) {
+                                  const int32_t* source_pos, uint32_t* keep_words, float* msg, float* mean, float* v,
+                                  int32_t* flags, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc == TARL_OK) rc = check(by_target, n_nodes);
@@ -657,7 +758,7 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
     if (by_source->n_edges != by_target->n_edges) return TARL_E_BADARG;
     if (batch == 0 || n_nodes == 0) return TARL_OK;
     if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !node_bias ||
-        !mean || !v || !flags || (by_source->n_edges > 0 && (!edge_features || !msg)))
+        !mean || !v || !flags || (by_source->n_edges > 0 && (!edge_features || !msg || !source_pos)))
         return TARL_E_BADARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
@@ -668,7 +769,7 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
     k_value_message_dropout<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, kDropSmemBytes, s>>>(
         *by_target, in, tarl::tile_rows_pow2(batch), make_drop(keep_bits, keep_batch_stride, seed, p), msg_weight, msg_bias,
         msg, keep_bits == nullptr ? keep_words : nullptr, flags);
-    k_value_aggregate_msg<<<nb, kThreads, 0, s>>>(*by_source, batch, n_nodes, node_weight, node_bias, msg, mean, v);
+    k_value_aggregate_msg<<<nb, kThreads, 0, s>>>(*by_source, source_pos, batch, n_nodes, node_weight, node_bias, msg, mean, v);
     return launch_status();
 }
 
@@ -677,7 +778,7 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                                    int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                   const uint32_t* keep_words, const float* msg, const float* mean, const float* v,
+                                   const uint32_t* keep_words, float* msg, const float* mean, const float* v,
                                    const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream) {
@@ -700,9 +801,14 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
     k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
                                                           gv_batch_stride, gv_node_stride, gm, partials);
     if ((rc = drop_smem_ready()) != TARL_OK) return rc;
-    k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, kDropSmemBytes, s>>>(
-        *by_target, in, Bp, make_drop(keep_bits, keep_batch_stride, seed, p, keep_words), msg, gm, partials);
-    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, (int)(grid.x * grid.y), grads);
+    const Drop drop = make_drop(keep_bits, keep_batch_stride, seed, p, keep_words);
+    const int n_tiles = (int)(grid.x * grid.y);
+    if (by_target->n_edges > 0)
+        k_value_dz<<<kDzCtas, kThreads, 0, s>>>(*by_target, in, drop, msg, gm, partials + (size_t)n_tiles * kGrads);
+    else if (cudaMemsetAsync(partials + (size_t)n_tiles * kGrads, 0, sizeof(float) * kGrads * kDzCtas, s) != cudaSuccess)
+        return TARL_E_LAUNCH;
+    k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, kDropSmemBytes, s>>>(*by_target, in, Bp, drop, msg, partials);
+    k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, n_tiles + kDzCtas, grads);
     return launch_status();
 }
 

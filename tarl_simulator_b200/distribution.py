@@ -99,6 +99,13 @@ class ActionSink:
         self.row_offset = int(row_offset)      # global index of the first replica (ranks of a data-parallel job differ)
         self.seed_dev = None                   # int64 [1] device tensor holding the key, or None: a host seed per call
         self.draw_id = 0                       # advanced by every draw taken with the device key
+        # A rollout may alternate TWO pairs of SELECTED_ROAD buffers (retarget()): prev_* are then the pair the previous
+        # step's decisions live in, from which a group without a hit carries its value over.
+        self.prev_links = self.prev_sources = None
+
+    def retarget(self, sel_links, sel_sources, prev_links=None, prev_sources=None):
+        self.sel_links, self.sel_sources = sel_links, sel_sources
+        self.prev_links, self.prev_sources = prev_links, prev_sources
 
     def matches(self, dist, rows: int) -> bool:
         return (dist._groups is self.groups and self.sel_links.size(0) == rows and self.sel_links.is_contiguous()
@@ -233,7 +240,9 @@ class GraphDistribution(Distribution):
                     self._groups.ref(), lg.data_ptr(), self.temperature, rows, _cabi.rows(u) if u is not None else None,
                     out.data_ptr(), lp.data_ptr() if fused else None, partials.data_ptr() if fused else None,
                     sink.group_node.data_ptr(), sink.edge_dst.data_ptr(), sink.sel_links.data_ptr(),
-                    sink.sel_sources.data_ptr() if sink.sel_sources is not None else None, sink.n_links, sink.n_nodes,
+                    sink.sel_sources.data_ptr() if sink.sel_sources is not None else None,
+                    sink.prev_links.data_ptr() if sink.prev_links is not None else None,
+                    sink.prev_sources.data_ptr() if sink.prev_sources is not None else None, sink.n_links, sink.n_nodes,
                     seed, seed_dev, draw, sink.row_offset, _stream(dev))
             _cabi.check(rc, "tarl_graphdist_sample_apply")
             sink.applied = True

@@ -210,14 +210,21 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
         pw, pb, nw, nb = (t.detach().reshape(-1).contiguous() for t in (msg_w, msg_b, node_w, node_b))
         ef_bs = ef.stride(0) if B > 1 else 0
         kb_ptr, kb_bs = (keep_bits.data_ptr(), keep_bits.stride(0)) if keep_bits is not None else (None, 0)
-        # words drawn in the kernel are kept (edge-major) for the backward pass instead of being drawn again
+        # words drawn in the kernel are kept (by-target order, like msg) for the backward pass instead of being drawn again
         words = torch.empty(max(E, 1), B, dtype=torch.int32, device=dev) if keep_bits is None else None
+        # position of every by-source entry's edge in the by-target order (static per graph, cached on the CSR object)
+        src_pos = getattr(by_source, "_pos_in_target", None)
+        if src_pos is None or src_pos[0] is not by_target:
+            inv = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+            inv[by_target.eid.long()] = torch.arange(E, dtype=torch.int32, device=dev)
+            src_pos = by_source._pos_in_target = (by_target, inv[by_source.eid.long()].contiguous())
+        src_pos = src_pos[1]
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_value_mp_forward_dropout(
                 by_source.ref(), by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs,
                 ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
-                kb_ptr, kb_bs, seed, p, words.data_ptr() if words is not None else None, msg.data_ptr(), mean.data_ptr(),
-                v.data_ptr(), flags.data_ptr(), _stream(dev))
+                kb_ptr, kb_bs, seed, p, src_pos.data_ptr(), words.data_ptr() if words is not None else None, msg.data_ptr(),
+                mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_forward_dropout")
         ctx.words = words
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs

@@ -250,6 +250,23 @@ class BatchedSimulatorEnv:
             sink.seed_dev = self.seed_words[1:2]
             sink.draw_id = 0
 
+    def sel_pair(self, which: int):
+        """Rollouts alternate two pairs of SELECTED_ROAD buffers (links [R*N], other nodes [R, N_tot - N]) so that the
+        action of step t+1 can be drawn while step t still reads its own: makes pair `which` (0 / 1) the one the
+        environment reads and returns (this pair, the other pair)."""
+        if getattr(self, "_sel_pairs", None) is None:
+            self._sel_pairs = [(self.store.sel, self.src_sel), (self.store.sel.clone(), self.src_sel.clone())]
+            self._sel_cur = 0
+        self._sel_cur = int(which)
+        cur, other = self._sel_pairs[self._sel_cur], self._sel_pairs[self._sel_cur ^ 1]
+        self.store.sel, self.src_sel = cur
+        return cur, other
+
+    def sync_sel_pairs(self):
+        """The pair not in use becomes a copy of the current one (entries no draw ever writes must agree in both)."""
+        cur, other = self.sel_pair(getattr(self, "_sel_cur", 0))
+        other[0].copy_(cur[0]); other[1].copy_(cur[1])
+
     def reset(self):
         """_reset (:186-219): empty queues, ON_WAY = DONE = 0, t = 06:00 − 60 s."""
         self.store.clear_queues()
