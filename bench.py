@@ -88,6 +88,11 @@ class ClockSampler:
 
     def _loop(self):
         while not self._stop.is_set():
+            self.sample_now()
+            self._stop.wait(self.period)
+
+    def sample_now(self):
+        if True:
             try:
                 if self._nvml is not None:
                     self.sm.append(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM))
@@ -105,12 +110,15 @@ class ClockSampler:
                             self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(self.period)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._loop, daemon=True)
         self._thread.start()
         return self
+
+    def mark(self):
+        """The timed region starts here: samples taken before it (warm-up) are dropped."""
+        self.sm, self.reasons = [], set()
 
     def __exit__(self, *exc):
         self._stop.set()
@@ -221,13 +229,17 @@ def run_native(args):
         state["t"] += float(n)
         state["i"] += n
 
-    run(warm)
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local, period=0.005) as clk:
+    # The sampler (NVML initialisation: tens of ms) is set up BEFORE the warm-up: the timed region is ~1 ms long, and a
+    # device left idle between warm-up and the timed region spends a good part of it getting back to its clocks.
+    with ClockSampler(local, period=0.002) as clk:
+        run(warm)
+        barrier()
+        clk.mark()
         ev0.record(stream)
         run(args.steps)
         ev1.record(stream)
+        clk.sample_now()          # the device is still inside the timed region (the enqueue runs ahead of it)
         torch.cuda.synchronize(dev)
     barrier()
     ms = ev0.elapsed_time(ev1)

@@ -30,7 +30,7 @@ for _ in range(reps):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    store.run(t, steps, sel_bank=bank[warm % 8:] + bank[:warm % 8], pop_bits=True)
+    store.run(t, steps, sel_bank=bank[warm % 8:] + bank[:warm % 8], pop_bits=True, delta_tt_link=True)
     e1.record()
     torch.cuda.synchronize()
     out.append(e0.elapsed_time(e1) / steps * 1e3)
@@ -38,6 +38,6 @@ try:
     store.check_errors()
 except RuntimeError as exc:
     print("faults:", str(exc)[:80])
-print(os.environ.get("TARL_TUNE", ""), "PDL off" if os.environ.get("TARL_NO_PDL") else "PDL on", workload, "R", R,
+print(os.environ.get("TARL_TUNE", ""), "ahead", os.environ.get("TARL_AHEAD_SELECT", "-"), os.environ.get("TARL_AHEAD_RESPOND", "-"), "PDL off" if os.environ.get("TARL_NO_PDL") else "PDL on", workload, "R", R,
       f"{steps} steps after {warm}: us/step:", " ".join(f"{v:.2f}" for v in out), "| min", f"{min(out):.2f}",
       "| pops last step", int(store.pop[: N * R].sum()) / (N * R))

@@ -189,6 +189,7 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
 // response phase gathers, delta_travel_time of the link's head (:94-96, from the PRE-step state: ONE value per upstream
 // link — every out-edge of the link carries the same number, tarl_expand_delta_tt materialises the [E] form), and the
 // pop hint for the upstream link whose head was admitted here.
+template <bool kWide>
 __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4 hA, float4 hB, const float4 st,
                                                    const Pick pk, float t, float* __restrict__ dtt_link,
                                                    int32_t* __restrict__ flags) {
@@ -226,9 +227,10 @@ __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4
         if (chosen != 0.0f && pk.src >= 0) s.hint[pk.src] = 1;     // that link's head just moved here: it will pop
     }
     hB.w = __int_as_float(meta);
-    s.hot_next[2 * (size_t)L] = hA;
-    s.hot_next[2 * (size_t)L + 1] = hB;
-    s.post[L] = make_float2(num_post, tail_post);
+    const uint64_t keep = l2_policy(s.pol_state);
+    if (kWide) st_record(&s.hot_next[2 * (size_t)L], hA, hB, s.pol_state == kPolKeep);
+    else st_record_narrow(&s.hot_next[2 * (size_t)L], hA, hB, keep);     // inside a __noinline__ function
+    st_hint(&s.post[L], make_float2(num_post, tail_post), keep);
 }
 
 // The general form of the direction phase for one link: in-edge scan out of the CSR (any degree, any edge weight, any
@@ -241,7 +243,7 @@ __device__ __noinline__ void select_append_general(const tarl_dual_csr& g, const
     const float4 hA = s.hot_cur[2 * (size_t)L], hB = s.hot_cur[2 * (size_t)L + 1];
     const float4 st = s.stat_a[d];
     const Pick pk = scan_in_edges_csr<kExtNoise>(g, s, attr_in, nz, r, d, L, t, hA.z < (hA.w - 3.0f), hA.w - hA.z, st.z);
-    append_and_publish(s, L, hA, hB, st, pk, t, dtt_link, flags);
+    append_and_publish<false>(s, L, hA, hB, st, pk, t, dtt_link, flags);
 }
 
 template <bool kExtNoise>
@@ -272,6 +274,19 @@ __global__ void __launch_bounds__(kThreads) k_csr_select_append(const __grid_con
 // warps — for a second, dense kernel. The streaming kernel loses a third of its instructions and 16 registers but not a
 // microsecond — it is bound by its two dependent load levels, not by issue slots or occupancy — and the second kernel
 // adds a third dependent launch to the step: 61 -> 68 us per step.)
+// The tile that is launched `ahead` CTAs after this one (x fastest, then the replica) and how many links it holds.
+struct Ahead { int r, d0, count; };
+__device__ __forceinline__ Ahead tile_ahead(int ahead, int N) {
+    const long long tile = (long long)blockIdx.y * gridDim.x + blockIdx.x + ahead;
+    Ahead a = {0, 0, 0};
+    if (tile < (long long)gridDim.x * gridDim.y) {
+        a.r = (int)(tile / gridDim.x);
+        a.d0 = (int)(tile - (long long)a.r * gridDim.x) * kThreads;
+        a.count = min(kThreads, N - a.d0);
+    }
+    return a;
+}
+
 #ifndef TARL_SELECT_MINBLOCKS
 #define TARL_SELECT_MINBLOCKS 9      // resident CTAs per SM the W = 4 kernel is compiled for (56 registers, no spills)
 #endif
@@ -281,28 +296,46 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
                                                                 const float* __restrict__ attr_in,
                                                                 const __grid_constant__ Noise nz, float t,
                                                                 float* __restrict__ dtt_link,
-                                                                int32_t* __restrict__ flags) {
+                                                                int32_t* __restrict__ flags, int ahead) {
     const int d = blockIdx.x * kThreads + threadIdx.x;
     if (d >= s.N) return;
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + d;
+    const uint64_t keep = l2_policy(s.pol_state), strm = l2_policy(s.pol_static);
+    // level 0: what the tile `ahead` launches further on will load at its level 1, requested from the L2 now
+    if (ahead > 0 && threadIdx.x < 3 + 2 * W) {
+        const Ahead tl = tile_ahead(ahead, s.N);
+        if (tl.count > 0) {
+            const int i = (int)threadIdx.x - 3;
+            if (i == -3) l2_prefetch_span(s.hot_cur, ((size_t)tl.r * s.N + tl.d0) * 32, tl.count * 32);
+            else if (i == -2) l2_prefetch_span(s.stat_a, (size_t)tl.d0 * 16, tl.count * 16);
+            else if (i == -1) l2_prefetch_span(s.sel, ((size_t)tl.r * s.N + tl.d0) * 4, tl.count * 4);
+            else l2_prefetch_span(i < W ? (const void*)ell.in_src : (const void*)ell.in_attr,
+                                  ((size_t)(i < W ? i : i - W) * ell.pitch + tl.d0) * 4, tl.count * 4);
+        }
+    }
     // level 1: everything addressed by the link id alone — the static part before the dependency wait
     pdl_trigger();
-    const float4 st = s.stat_a[d];
+    const float4 st = ld_static(&s.stat_a[d], strm);
     int u[W];
     float a[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-        u[j] = ell.in_src[(size_t)j * ell.pitch + d];
-        a[j] = ell.in_attr[(size_t)j * ell.pitch + d];
+        u[j] = ld_static(&ell.in_src[(size_t)j * ell.pitch + d], strm);
+#ifdef TARL_ABLATE_ATTR         // tuning only (wrong results): what does the edge weight column cost?
+        a[j] = 0.25f;
+#else
+        a[j] = ld_static(&ell.in_attr[(size_t)j * ell.pitch + d], strm);
+#endif
     }
     pdl_wait();
     if (u[W - 1] == -2) {     // more than W in-edges or an unsafe weight: this link walks its CSR segment instead
         select_append_general<kExtNoise>(g, s, attr_in, nz, t, dtt_link, flags, r, d, L);
         return;
     }
-    const float4 hA = s.hot_cur[2 * (size_t)L], hB = s.hot_cur[2 * (size_t)L + 1];
+    float4 hA, hB;
+    ld_record(&s.hot_cur[2 * (size_t)L], hA, hB, s.pol_state == kPolKeep);
     const bool free_d = hA.z < (hA.w - 3.0f);
     const float room_d = hA.w - hA.z, ridx_d = st.z;
     Pick pk = {0.0f, 0.0f, -1, false};
@@ -315,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
 #ifdef TARL_ABLATE_GATHER       // tuning only (wrong results): what would the kernel cost without its second load level?
             U[j] = hA; S[j] = st.z + (float)j;
 #else
-            U[j] = s.hot_cur[2 * (size_t)(base + u[j])];
+            U[j] = ld_hint(&s.hot_cur[2 * (size_t)(base + u[j])], keep);
             S[j] = s.sel[base + u[j]];
 #endif
         }
@@ -345,7 +378,11 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
                 }
             }
         }
+#ifdef TARL_ABLATE_CONTEST      // tuning only (wrong results): what does the contested path cost?
+        if (true) {
+#else
         if (safe && n_elig == 1) {
+#endif
             pk.have = true;       // a lone eligible edge wins without noise
         } else {
             float best = -FLT_MAX;
@@ -355,8 +392,12 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
             if (!kExtNoise) philox_key(nz, klo, khi);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
+#ifdef TARL_ABLATE_PHILOX       // tuning only (wrong results): what does the Philox draw cost?
+                if (!kExtNoise && (j & 3) == 0) { un[0] = 0.3f + 1e-9f * (float)L; un[1] = 0.5f; un[2] = 0.7f; un[3] = 0.9f; }
+#else
                 if (!kExtNoise && (j & 3) == 0)
                     philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), klo, khi, un);
+#endif
                 if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
                     const float sc = gumbel_score(p[j], kExtNoise ? uu[j] : un[j & 3]);
                     if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
@@ -364,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
             }
         }
     }
-    append_and_publish(s, L, hA, hB, st, pk, t, dtt_link, flags);
+    append_and_publish<true>(s, L, hA, hB, st, pk, t, dtt_link, flags);
 }
 
 // ------------------------------------------------------------------------------------------------ response phase
@@ -393,8 +434,8 @@ __device__ __forceinline__ float pop_head(const Store& s, int L, float4 hA, floa
     int nrh = rh + 1; if (nrh >= M) nrh = 0;
     meta = (meta & ~kMetaRingMask) | nrh;
     if (gv && q == 1) meta &= ~kMetaGarbage;                    // the garbage became the head slot
-    s.hot_next[2 * (size_t)L] = make_float4(new_head.x, new_head.z, hA.z - 1.0f, hA.w);
-    s.hot_next[2 * (size_t)L + 1] = make_float4(new_head.y, hB.y, hB.z, __int_as_float(meta));
+    st_record(&s.hot_next[2 * (size_t)L], make_float4(new_head.x, new_head.z, hA.z - 1.0f, hA.w),
+              make_float4(new_head.y, hB.y, hB.z, __int_as_float(meta)), s.pol_state == kPolKeep);
     return new_head.z;                                          // exit time of the new head
 }
 
@@ -439,24 +480,39 @@ __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, S
     if (accept) pop_head(s, L, A, B, t, false, A, A);
 }
 
+#ifndef TARL_RESPOND_MINBLOCKS
+#define TARL_RESPOND_MINBLOCKS 12     // 40 registers: at 16 CTAs (32 registers) the policy descriptors spill
+#endif
 template <int W>
-__global__ void __launch_bounds__(kThreads, W == 4 ? 16 : 1) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
+__global__ void __launch_bounds__(kThreads, W == 4 ? TARL_RESPOND_MINBLOCKS : 1) k_ell_respond_pop(tarl_dual_csr g, tarl_dual_ell ell, Store s, float t,
                                                               uint8_t* __restrict__ pop, uint32_t* __restrict__ pop_bits,
-                                                              int32_t* __restrict__ flags) {
+                                                              int32_t* __restrict__ flags, int ahead) {
     const int u = blockIdx.x * kThreads + threadIdx.x;
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + u;
     bool accept = false, hinted = false, fetched = false;
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
+    const uint64_t keep = l2_policy(s.pol_state), strm = l2_policy(s.pol_static);
+    if (ahead > 0 && threadIdx.x < 3 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
+        const Ahead tl = tile_ahead(ahead, s.N);
+        if (tl.count > 0) {
+            const int i = (int)threadIdx.x - 3;
+            const size_t L0 = (size_t)tl.r * s.N + tl.d0;
+            if (i == -3) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
+            else if (i == -2) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
+            else if (i == -1) l2_prefetch_span(s.hint, L0, tl.count);
+            else l2_prefetch_span(ell.out_dst, ((size_t)i * ell.pitch + tl.d0) * 4, tl.count * 4);
+        }
+    }
     pdl_trigger();
     int dn[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ell.out_dst[(size_t)j * ell.pitch + u] : -1;   // static: before the wait
+    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ld_static(&ell.out_dst[(size_t)j * ell.pitch + u], strm) : -1;   // static: before the wait
     pdl_wait();
     if (u < s.N) {
         // level 1: own post-append record and whether a downstream link admitted this link's head
-        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
+        ld_record(&s.hot_next[2 * (size_t)L], A, B, s.pol_state == kPolKeep);
         hinted = s.hint[L] != 0;
         // level 2: the neighbours' summaries and, for hinted links, the two ring slots a pop needs
         if (dn[W - 1] == -2) {
@@ -465,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? 16 : 1) k_ell_respond_pop(t
             float2 D[W];
 #pragma unroll
             for (int j = 0; j < W; ++j)
-                if (dn[j] >= 0) D[j] = s.post[base + dn[j]];
+                if (dn[j] >= 0) D[j] = ld_hint(&s.post[base + dn[j]], keep);
             if (hinted) {
                 const int rh = __float_as_int(B.w) & kMetaRingMask;
                 const float4* Q = s.queue + (size_t)L * s.M;
@@ -517,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
                                                                        uint8_t* __restrict__ pop,
                                                                        uint32_t* __restrict__ pop_bits,
                                                                        int32_t* __restrict__ flags,
-                                                                       const __grid_constant__ WithdrawArgs wa) {
+                                                                       const __grid_constant__ WithdrawArgs wa, int ahead) {
     // (__grid_constant__: the rare path takes `s` and `wa` by reference; without it every thread would first copy both
     // structs from the parameter space into local memory — 200 bytes per thread, measured 1.2 ms instead of 0.4 ms)
     const int u = blockIdx.x * kThreads + threadIdx.x;
@@ -526,13 +582,25 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
     const int L = base + u;
     bool accept = false, hinted = false, fetched = false;
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
+    const uint64_t keep = l2_policy(s.pol_state), strm = l2_policy(s.pol_static);
+    if (ahead > 0 && threadIdx.x < 3 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
+        const Ahead tl = tile_ahead(ahead, s.N);
+        if (tl.count > 0) {
+            const int i = (int)threadIdx.x - 3;
+            const size_t L0 = (size_t)tl.r * s.N + tl.d0;
+            if (i == -3) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
+            else if (i == -2) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
+            else if (i == -1) l2_prefetch_span(s.hint, L0, tl.count);
+            else l2_prefetch_span(ell.out_dst, ((size_t)i * ell.pitch + tl.d0) * 4, tl.count * 4);
+        }
+    }
     pdl_trigger();
     int dn[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ell.out_dst[(size_t)j * ell.pitch + u] : -1;   // static: before the wait
+    for (int j = 0; j < W; ++j) dn[j] = (u < s.N) ? ld_static(&ell.out_dst[(size_t)j * ell.pitch + u], strm) : -1;   // static: before the wait
     pdl_wait();
     if (u < s.N) {
-        A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
+        ld_record(&s.hot_next[2 * (size_t)L], A, B, s.pol_state == kPolKeep);
         hinted = s.hint[L] != 0;
         if (dn[W - 1] == -2) {
             accept = scan_out_edges_csr(g, s, base, u, A);
@@ -540,7 +608,7 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
             float2 D[W];
 #pragma unroll
             for (int j = 0; j < W; ++j)
-                if (dn[j] >= 0) D[j] = s.post[base + dn[j]];
+                if (dn[j] >= 0) D[j] = ld_hint(&s.post[base + dn[j]], keep);
             if (hinted) {
                 const int rh = __float_as_int(B.w) & kMetaRingMask;
                 const float4* Q = s.queue + (size_t)L * s.M;
@@ -588,6 +656,16 @@ void launch_pdl(void (*kernel)(KArgs...), dim3 grid, cudaStream_t cs, Args... ar
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// How many CTA launches ahead a tile's level-1 data is requested from the L2 (0 = off). CTAs are handed out in launch
+// order, so the distance is counted in resident CTAs: a little more than one full wave of the kernel (148 SMs x 9 CTAs
+// for the direction phase, x 16 for the response phase). TARL_AHEAD_SELECT / TARL_AHEAD_RESPOND override (tuning).
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v != nullptr ? atoi(v) : dflt;
+}
+inline int ahead_select() { static const int v = env_int("TARL_AHEAD_SELECT", 700); return v; }
+inline int ahead_respond() { static const int v = env_int("TARL_AHEAD_RESPOND", 1200); return v; }
+
 inline int blocks_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
 
@@ -613,6 +691,16 @@ int make_store(const tarl_link_store* p, Store* s) {
     s->slot_link = p->slot_link;
     s->link_slot = p->link_slot;
     if ((p->slot_link == nullptr) != (p->link_slot == nullptr)) return TARL_E_BADARG;
+    // records move as one 256-bit access
+    if (((reinterpret_cast<uintptr_t>(p->hot_cur) | reinterpret_cast<uintptr_t>(p->hot_next)) & 31) != 0) return TARL_E_BADARG;
+    // L2 residency (engine_common.cuh): does the state two consecutive kernels share fit the 126 MB L2?
+    const bool fits = (int64_t)p->n_links * p->n_replicas * 80 <= (int64_t)96 << 20;
+    s->pol_state = fits ? kPolKeep : kPolDefault;
+    s->pol_static = fits ? (p->n_replicas == 1 ? kPolStream : kPolDefault) : kPolKeep;
+    static const char* const tune = getenv("TARL_L2_POLICY");        // tuning only: "sk" = state, statics as digits 0/1/2
+    if (tune != nullptr && tune[0] >= '0' && tune[0] <= '2' && tune[1] >= '0' && tune[1] <= '2') {
+        s->pol_state = tune[0] - '0'; s->pol_static = tune[1] - '0';
+    }
     return TARL_OK;
 }
 
@@ -670,22 +758,23 @@ void launch_step(const tarl_dual_csr* g, const tarl_dual_ell* ell, const Store& 
     const float t = io.t;
     float* dtt = io.delta_tt_link;
     int32_t* flags = io.flags;
+    const int pf = s.pol_state == kPolKeep ? 1 : 0;       // prefetch ahead only where the state lives in the L2
     if (phase_mask & TARL_PHASE_SELECT_APPEND) {
         if (ell == nullptr) {
             if (ext) launch_pdl(k_csr_select_append<true>, grid, cs, *g, s, attr_in, nz, t, dtt, flags);
             else launch_pdl(k_csr_select_append<false>, grid, cs, *g, s, attr_in, nz, t, dtt, flags);
         } else if (ell->width == 4) {
-            if (ext) launch_pdl(k_ell_select_append<4, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
-            else launch_pdl(k_ell_select_append<4, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
+            if (ext) launch_pdl(k_ell_select_append<4, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags, pf * ahead_select());
+            else launch_pdl(k_ell_select_append<4, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags, pf * ahead_select());
         } else {
-            if (ext) launch_pdl(k_ell_select_append<8, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
-            else launch_pdl(k_ell_select_append<8, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags);
+            if (ext) launch_pdl(k_ell_select_append<8, true>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags, pf * ahead_select());
+            else launch_pdl(k_ell_select_append<8, false>, grid, cs, *g, *ell, s, attr_in, nz, t, dtt, flags, pf * ahead_select());
         }
     }
     if (phase_mask & TARL_PHASE_RESPOND_SHIFT) {
         if (ell == nullptr) launch_pdl(k_csr_respond_pop, grid, cs, *g, s, t, io.pop, io.pop_bits, flags);
-        else if (ell->width == 4) launch_pdl(k_ell_respond_pop<4>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags);
-        else launch_pdl(k_ell_respond_pop<8>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags);
+        else if (ell->width == 4) launch_pdl(k_ell_respond_pop<4>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags, pf * ahead_respond());
+        else launch_pdl(k_ell_respond_pop<8>, grid, cs, *g, *ell, s, t, io.pop, io.pop_bits, flags, pf * ahead_respond());
     }
 }
 
@@ -767,9 +856,11 @@ int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, c
                              *adjacency, withdrawn, counters, num_out, occupancy, nullptr, n_nodes};
     const dim3 grid(blocks_for(s.N), s.R);
     if (ell->width == 4)
-        launch_pdl(k_ell_respond_pop_withdraw<4>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa);
+        launch_pdl(k_ell_respond_pop_withdraw<4>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa,
+                   (s.pol_state == kPolKeep ? 1 : 0) * ahead_respond());
     else
-        launch_pdl(k_ell_respond_pop_withdraw<8>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa);
+        launch_pdl(k_ell_respond_pop_withdraw<8>, grid, cs, *g, *ell, s, io->t, io->pop, io->pop_bits, io->flags, wa,
+                   (s.pol_state == kPolKeep ? 1 : 0) * ahead_respond());
     return launch_status();
 }
 

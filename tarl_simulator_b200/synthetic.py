@@ -155,6 +155,9 @@ WORKLOADS = {
     "grid100": ("grid", (100,), 100_000),
     "ring_radial_1m": ("ring_radial", (500, 500), 2_000_000),
     "grid16": ("grid", (16,), 2_000),
+    # size sweep of the bench network (tuning: the state of the 250k form lives in the L2, that of the 4m form cannot)
+    "ring_radial_250k": ("ring_radial", (250, 250), 500_000),
+    "ring_radial_4m": ("ring_radial", (1000, 1000), 8_000_000),
 }
 
 
