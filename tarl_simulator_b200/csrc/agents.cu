@@ -151,23 +151,15 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
     if (listed) work[(size_t)r * ai.n_origins + base + __popc(m & ((1u << lane) - 1u))] = i;
 }
 
+// What the origin i0 of replica r does in the admit phase: if it ended up at the HEAD of its road's list it serves the
+// road. (A thread per road would launch N threads per replica to find the few roads with a list.)
 template <class Acc>
-__global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_index ai, AgentTable at, float t,
-                                                           int32_t* __restrict__ head, const int32_t* __restrict__ next,
-                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
-                                                           int32_t* __restrict__ inserted, const int32_t* __restrict__ work,
-                                                           const int32_t* __restrict__ work_count,
-                                                           float* __restrict__ num_out, int32_t* __restrict__ occupancy,
-                                                           int n_nodes) {
-    // One thread per (replica, origin) — or, with a worklist, per LISTED origin: the origin that ended up at the HEAD of
-    // its road's list serves the road. (A thread per road would launch N threads per replica to find the few roads
-    // with a list.)
-    int i0 = blockIdx.x * kThreads + threadIdx.x;
-    const int r = blockIdx.y;
-    if (work != nullptr) {
-        if (i0 >= work_count[r]) return;
-        i0 = work[(size_t)r * ai.n_origins + i0];
-    }
+__device__ __forceinline__ void insert_admit_one(const Acc& acc, const tarl_agent_index& ai, const AgentTable& at, float t,
+                                                 int32_t* __restrict__ head, const int32_t* __restrict__ next,
+                                                 int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
+                                                 int32_t* __restrict__ inserted, const int32_t* __restrict__ departed,
+                                                 float* __restrict__ num_out, int32_t* __restrict__ occupancy,
+                                                 int n_nodes, int r, int i0) {
     if (i0 >= ai.n_origins) return;
     if (next[(size_t)r * ai.n_origins + i0] == -2) return;                        // not listed this step
     const long long road = (long long)acc.sel_of(r, ai.origins[i0]);
@@ -191,6 +183,13 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
     while (admitted < cap && q0 + admitted < acc.Nmax) {
         int best_a = INT32_MAX, best_i = -1;
         for (int i = h; i >= 0; i = nx[i]) {
+            // Nobody (left) waiting at this origin — departed by now = inserted so far, see insert_offer_one: the scan
+            // below would walk the rest of the origin's agents, two dependent loads per four of them, to find nothing
+            // (after the one agent an origin typically inserts in a step that walk was half of the thread's chain)
+            if (inserted != nullptr && ai.dep_sorted != nullptr) {
+                const int n_dep = departed != nullptr ? departed[i] : departed_by(ai, ai.origins[i], t);
+                if (n_dep <= inserted[(size_t)r * ai.n_origins + i]) continue;
+            }
             const int end = ai.org_ptr[ai.origins[i] + 1];
             int k = cur[i];
             // first ready agent at or after k. Four candidates per round: their ids and then their rows are loaded
@@ -228,6 +227,29 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
             atomicAdd(&occupancy[r], admitted);
         }
     }
+}
+
+// One thread per (replica, origin) — or, with a worklist, a few CTAs per replica striding over its LISTED origins (a
+// grid sized for every origin spends its time retiring thousands of CTAs that find their index beyond the count).
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_index ai, AgentTable at, float t,
+                                                           int32_t* __restrict__ head, const int32_t* __restrict__ next,
+                                                           int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
+                                                           int32_t* __restrict__ inserted, const int32_t* __restrict__ work,
+                                                           const int32_t* __restrict__ work_count,
+                                                           const int32_t* __restrict__ departed,
+                                                           float* __restrict__ num_out, int32_t* __restrict__ occupancy,
+                                                           int n_nodes) {
+    const int r = blockIdx.y;
+    if (work == nullptr) {
+        insert_admit_one(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy, n_nodes, r,
+                         (int)(blockIdx.x * kThreads + threadIdx.x));
+        return;
+    }
+    const int count = work_count[r];
+    for (int w = blockIdx.x * kThreads + threadIdx.x; w < count; w += gridDim.x * kThreads)
+        insert_admit_one(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy, n_nodes, r,
+                         work[(size_t)r * ai.n_origins + w]);
 }
 
 
@@ -438,7 +460,8 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if (index->n_origins == 0 || N == 0) return TARL_OK;
     if (!index->org_ptr || !index->org_agent || !index->origins || !head || !next || !cursor) return TARL_E_BADARG;
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
-    const dim3 g1(blocks_for(index->n_origins), R), g2 = g1;
+    const dim3 g1(blocks_for(index->n_origins), R);
+    const dim3 g2(worklist != nullptr ? (g1.x < 4 ? g1.x : 4) : g1.x, R);      // worklist: CTAs stride over the listed origins
     if ((worklist != nullptr) != (work_count != nullptr)) return TARL_E_BADARG;
     if ((num_out != nullptr) != (occupancy != nullptr) || (num_out != nullptr && !is_store)) return TARL_E_BADARG;
     if (worklist != nullptr && cudaMemsetAsync(work_count, 0, sizeof(int32_t) * R, cs) != cudaSuccess) return TARL_E_LAUNCH;
@@ -452,11 +475,11 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if (is_store) {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count, dep_scratch);
         k_insert_admit<<<g2, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
-                                                num_out, occupancy, sto.n_nodes);
+                                                dep_scratch, num_out, occupancy, sto.n_nodes);
     } else {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count, dep_scratch);
         k_insert_admit<<<g2, kThreads, 0, cs>>>(row, *index, at, t, head, next, cursor, counters, inserted, worklist, work_count,
-                                                nullptr, nullptr, 0);
+                                                dep_scratch, nullptr, nullptr, 0);
     }
     return launch_status();
 }

@@ -391,11 +391,12 @@ class BatchedSimulatorEnv:
         return nf, (ai if agent_index else None)
 
     def step(self, action: torch.Tensor | None, noise: torch.Tensor | None = None, observe: bool = False,
-             compact_out=None, lean: bool = False):
+             compact_out=None, lean: bool = False, after_core=None):
         """One _step for every replica. action None = keep the current SELECTED_ROAD values. compact_out: see
         observe() — the post-step compact observation comes out of the same pass that computes the reward.
         lean=True returns nothing: reward = -self.occupancy (which may be pointed at a row of a caller-owned [T, R] int32
-        buffer beforehand), done = self.time > EPISODE_END."""
+        buffer beforehand), done = self.time > EPISODE_END. after_core: called once the core step (+ fused withdrawal)
+        is enqueued, before the insertion (rollouts record an event there for work they overlap with the insertion)."""
         if action is not None:
             self.apply_action(action)
         # occupancy-only observation (compact_out = (NUM frame, None, None)): withdraw holds every record anyway and
@@ -412,6 +413,8 @@ class BatchedSimulatorEnv:
         else:
             self.store.step(self.time, noise=noise, delta_tt=self.delta_tt)
             self.withdraw(num_out=compact_out[0] if fused else None)
+        if after_core is not None:
+            after_core()
         self.insert(num_out=compact_out[0] if fused else None)
         if self.metrics is not None:
             self.metrics.record(self.time, pop=self.store.pop[: self.R * self.N], withdrawn=self.withdrawn,
