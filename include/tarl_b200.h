@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 21
+#define TARL_ABI_VERSION 22
 
 /* return codes */
 #define TARL_OK 0
@@ -363,6 +363,8 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
  * BY-TARGET order: element (b, e) at pos(e)*B + b, pos(e) = position of edge e in by_target (a target node's in-edges are
  * contiguous: the backward pass finds them without loading an edge id first). source_pos: [E] int32, entry j = pos of
  * the j-th edge of by_source (static, built once per graph). mean, v as in tarl_value_mp_forward.
+ * agent_pack: NULL, or 16-byte aligned scratch of agent_rows * 12 floats: both passes re-lay agent_features there as
+ * 48-byte rows (three 128-bit loads per (node, row) pair instead of nine scalar gathers).
  * In-kernel stream for p <= 1/16: ONE Philox block per (row, edge) — 17 top nibbles decide 15 of 16 inputs, the rare
  * zero nibbles take a low byte from the block's 7 spare bytes; larger p: two blocks, 17 twelve-bit fields. */
 int tarl_value_mp_dropout_bits(uint64_t seed, float p, int32_t batch, int32_t n_edges, uint32_t* keep_bits, void* stream);
@@ -372,8 +374,8 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                                   int32_t agent_rows, const float* msg_weight, const float* msg_bias,
                                   const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                  const int32_t* source_pos, uint32_t* keep_words, float* msg, float* mean, float* v,
-                                  int32_t* flags, void* stream);
+                                  const int32_t* source_pos, uint32_t* keep_words, float* agent_pack, float* msg,
+                                  float* mean, float* v, int32_t* flags, void* stream);
 /* grads / gm / partials as in tarl_value_mp_backward; keep_bits / seed / p must be the forward call's. msg is
  * OVERWRITTEN (it becomes d z, the gradient at the tanh's argument). */
 int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by_target, const float* node_features,
@@ -381,8 +383,8 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                                    int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                   const uint32_t* keep_words, float* msg, const float* mean, const float* v,
-                                   const float* grad_v,
+                                   const uint32_t* keep_words, float* agent_pack, float* msg, const float* mean,
+                                   const float* v, const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream);
 

@@ -373,9 +373,8 @@ __device__ __forceinline__ void philox_raw(uint32_t c0, uint32_t c1, uint32_t c2
                                            uint32_t out[4]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;   // one IMAD.WIDE each
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
@@ -403,14 +402,26 @@ __device__ __forceinline__ uint32_t philox_keep_word(const Drop& d, int b, int e
         // top nibbles: inputs 0-7 in r[0], 8-15 in r[1], 16 in the low nibble of r[2]
         uint32_t zero = zero_nibbles(r[0]) | (zero_nibbles(r[1]) << 8) | (((r[2] & 0xfu) == 0u) ? (1u << 16) : 0u);
         uint32_t word = 0x1ffffu;
-        int used = 0;                                                             // spare bytes: r[3] (4), then r[2] >> 4 (3)
-        while (zero != 0u) {                                                      // 1.06 iterations on average
+        // spare bytes: r[3] (4), then r[2] >> 4 (3), as one shift register. 1.06 zero nibbles per word on average, but a
+        // warp walks as many rounds as its unluckiest lane (3 - 4): the round is kept to a handful of instructions.
+        uint64_t spare = (uint64_t)r[3] | ((uint64_t)(r[2] >> 4) << 32);
+        if (__popc(zero) <= 7) {
+            while (zero != 0u) {
+                const uint32_t lowest = zero & (0u - zero);
+                zero ^= lowest;
+                if ((uint32_t)(spare & 0xffu) < d.thresh) word ^= lowest;
+                spare >>= 8;
+            }
+            return word;
+        }
+        int used = 0;                                                             // more than 7 zero nibbles: 6e-6 of the words
+        while (zero != 0u) {
             const int k = __ffs((int)zero) - 1;
             zero &= zero - 1u;
             uint32_t byte;
             if (used < 4) byte = (r[3] >> (8 * used)) & 0xffu;
             else if (used < 7) byte = (r[2] >> (4 + 8 * (used - 4))) & 0xffu;
-            else {                                                                // more than 7 zero nibbles: 6e-6 of the words
+            else {
                 uint32_t q[4];
                 philox_raw((uint32_t)e, (uint32_t)b, (uint32_t)(1 + ((used - 7) >> 4)), 0x44524f50u, d.seed_lo, d.seed_hi, q);
                 const int i = (used - 7) & 15;
@@ -454,53 +465,155 @@ __global__ void __launch_bounds__(kThreads) k_value_dropout_bits(Drop d, int B, 
     out[(int64_t)b * E + e] = philox_keep_word(d, b, e);
 }
 
-// (target node, row) tiles (tile_map.cuh). Walk 1, nodes innermost: the 16 message inputs of every pair are read the way
-// the observation is laid out and parked in shared memory as products (x_k * scale) * w_k — 16 planes of the tile.
-// Walk 2, rows innermost: msg[e,b] = tanh(sum_k keep_k * product_k + keep_16 * (f * scale) * w_16 + w0) for every
-// in-edge e of the node (x * (mask / (1 - p)) as ATen's dropout computes it, then the 17-term dot product), written
-// with the row innermost at the edge's by-target position k (see keep_word). (A thread per pair that loads its inputs itself, rows innermost, reads one sector
-// per lane and input: measured 2.8 ms instead of ~1 ms at 32 rows x 6.0 M edges.)
-constexpr int kDropSmemBytes = kIn * tarl::kTileSmem * (int)sizeof(float);
-__global__ void __launch_bounds__(tarl::kTileThreads) k_value_message_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
-                                                                              const float* __restrict__ w,
-                                                                              const float* __restrict__ w0,
-                                                                              float* __restrict__ msg,
-                                                                              uint32_t* __restrict__ words_out,
-                                                                              int32_t* __restrict__ flags) {
-    extern __shared__ float xs[];                                 // [kIn][kTileSmem]
-    const tarl::Tile t = tarl::tile_here(in.B, Bp);
-    tarl::tile_walk_nodes(t, [&](int r, int j) {
-        const int n = t.n0 + j;
-        if (n >= in.N || r >= t.nrows) return;
-        float x[kIn];
-        load_x(in, t.b0 + r, n, x, flags);
-        const int slot = tarl::tile_slot(t, r, j);
+// The words of a training forward pass, by-target position major (element (b, k) at k*B + b): a streaming pass of its
+// own — one thread per (position, row), 28 registers, full occupancy — instead of a Philox chain inside the message
+// kernel's edge walk, where 24 warps per SM (66 KB of staged planes per CTA) could not hide it (message kernel 3.4 ms
+// with the draw, of which the draw was two thirds of the instructions).
+__global__ void __launch_bounds__(kThreads) k_value_keep_words(const int32_t* __restrict__ eid, int64_t total, int B,
+                                                               Drop d, uint32_t* __restrict__ words) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= total) return;
+    int k, b;
+    if ((B & (B - 1)) == 0) { k = (int)(i >> (31 - __clz(B))); b = (int)i & (B - 1); }      // no 64-bit division
+    else { k = (int)(i / B); b = (int)(i - (int64_t)k * B); }
+    words[i] = philox_keep_word(d, b, eid[k]);
+}
+
+constexpr int kDropSmemBytes = (kIn * tarl::kTileSmem + (tarl::kTileThreads / 32) * 32 * kNodeDim) * (int)sizeof(float);
+constexpr int kPairsPerThread = tarl::kTilePairs / tarl::kTileThreads;      // 4
+
+// Walk 1 of both train-mode kernels, nodes innermost, TWO of a thread's pairs at a time (a pair is two dependent load
+// levels — agent index -> agent row — and 66 KB of planes leave 24 warps per SM to hide them): store(c, slot, x_c).
+// The gather of a pair's 9 agent features is what the L1 spends its time on in this walk: 9 scalar loads per warp, each
+// on 32 different 36-byte rows = 9 x 32 tag look-ups, against 7 + 2 for everything else a warp loads here. pack =
+// the agent table re-laid as 48-byte rows (k_value_pack_agents, once per call): three 128-bit loads per pair.
+constexpr int kPackDim = 12;
+__global__ void __launch_bounds__(256) k_value_pack_agents(const float* __restrict__ af, int af_rows, float4* __restrict__ pack) {
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a >= af_rows) return;
+    const float* q = af + (int64_t)a * kAgentDim;
+    pack[3 * (int64_t)a] = make_float4(q[0], q[1], q[2], q[3]);
+    pack[3 * (int64_t)a + 1] = make_float4(q[4], q[5], q[6], q[7]);
+    pack[3 * (int64_t)a + 2] = make_float4(q[8], 0.0f, 0.0f, 0.0f);
+}
+
+template <typename Keep, typename Store>
+__device__ __forceinline__ void stage_inputs(const tarl::Tile& t, const Inputs& in, const float4* __restrict__ pack,
+                                             float* __restrict__ warp_buf, int32_t* flags, Keep keep, Store store) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int segs = t.TN >> 5;
+    const int total = t.Bp * segs;
+    constexpr int kWarps = tarl::kTileThreads / 32;
+    const bool dense = in.nf_rs == kNodeDim;
+    for (int u0 = warp; u0 < total; u0 += 2 * kWarps) {
+        float x[2][kIn];
+        int slot[2];
+        bool live[2];
 #pragma unroll
-        for (int c = 0; c < kIn; ++c) xs[c * tarl::kTileSmem + slot] = (x[c] * d.scale) * w[c];
-    });
+        for (int h = 0; h < 2; ++h) {
+            const int u = u0 + h * kWarps;                        // warp-uniform
+            const int r = u / segs, j = (u - r * segs) * 32 + lane;
+            const int n = t.n0 + j;
+            const bool row_live = u < total && r < t.nrows;       // warp-uniform
+            live[h] = row_live && n < in.N && keep(n);
+            slot[h] = tarl::tile_slot(t, r, j);
+            if (pack == nullptr) {
+                if (live[h]) load_x(in, t.b0 + r, n, x[h], flags);
+                continue;
+            }
+            long long a = 0;
+            if (live[h]) a = agent_row(in, t.b0 + r, n, flags);
+            if (row_live) load_nf_staged(in, dense, t.b0 + r, n - lane, lane, live[h], warp_buf, x[h]);
+            if (live[h]) {
+                const float4 p0 = pack[3 * a], p1 = pack[3 * a + 1], p2 = pack[3 * a + 2];
+                x[h][7] = p0.x; x[h][8] = p0.y; x[h][9] = p0.z; x[h][10] = p0.w;
+                x[h][11] = p1.x; x[h][12] = p1.y; x[h][13] = p1.z; x[h][14] = p1.w;
+                x[h][15] = p2.x;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!live[h]) continue;
+#pragma unroll
+            for (int c = 0; c < kIn; ++c) store(c, slot[h], x[h][c]);
+        }
+    }
+}
+
+// (target node, row) tiles (tile_map.cuh). Walk 1: the 16 message inputs of every pair are read the way the
+// observation is laid out and parked in shared memory as products (x_k * scale) * w_k — 16 planes of the tile.
+// Walk 2, rows innermost: msg = tanh(sum_k keep_k * product_k + keep_16 * (f * scale) * w_16 + w0) for every in-edge of
+// the node (x * (mask / (1 - p)) as ATen's dropout computes it, then the 17-term dot product), written with the row
+// innermost at the edge's by-target position k (see keep_word). A thread owns four pairs and walks them TOGETHER, two
+// in-edges of each per round: 8 edge ids, 8 keep words, then 8 edge features are in flight at once, and the products
+// are read from shared memory where they are used instead of being held in 16 registers per pair (which is what kept
+// the walk to one pair, i.e. one dependent load chain, at a time: 2.4 ms for 32 rows x 6.0 M edges without the draw).
+__global__ void __launch_bounds__(tarl::kTileThreads, 3) k_value_message_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
+                                                                                 const float* __restrict__ w,
+                                                                                 const float* __restrict__ w0,
+                                                                                 float* __restrict__ msg,
+                                                                                 uint32_t* __restrict__ words_out,
+                                                                                 int32_t* __restrict__ flags,
+                                                                                 const float4* __restrict__ pack) {
+    extern __shared__ float xs[];                                 // [kIn][kTileSmem], then a 224-float buffer per warp
+    const tarl::Tile t = tarl::tile_here(in.B, Bp);
+    stage_inputs(t, in, pack, xs + kIn * tarl::kTileSmem + (threadIdx.x >> 5) * 32 * kNodeDim, flags, [&](int) { return true; },
+                 [&](int c, int slot, float v) { xs[c * tarl::kTileSmem + slot] = (v * d.scale) * w[c]; });
     __syncthreads();
     const float we = w[kIn], bias = w0[0];
-    tarl::tile_walk_rows(t, [&](int r, int j) {
-        const int n = t.n0 + j, b = t.b0 + r;
-        if (n >= in.N || r >= t.nrows) return;
-        const int k0 = by_dst.ptr[n], k1 = by_dst.ptr[n + 1];
-        if (k0 == k1) return;
-        const int slot = tarl::tile_slot(t, r, j);
-        float x[kIn];
+    int k0[kPairsPerThread], k1[kPairsPerThread];
 #pragma unroll
-        for (int c = 0; c < kIn; ++c) x[c] = xs[c * tarl::kTileSmem + slot];
-        const float* ef = in.ef + b * in.ef_bs;
-        for (int k = k0; k < k1; ++k) {
-            const int e = by_dst.eid[k];
-            const uint32_t word = keep_word(d, in.B, b, e, k);
-            if (words_out != nullptr) words_out[(int64_t)k * in.B + b] = word;   // backward reads them instead of redrawing
-            float z = 0.0f;
+    for (int q = 0; q < kPairsPerThread; ++q) {
+        const int p = threadIdx.x + q * tarl::kTileThreads;
+        const int r = p & (t.Bp - 1), n = t.n0 + (p >> t.sh);
+        const bool live = n < in.N && r < t.nrows;
+        k0[q] = live ? by_dst.ptr[n] : 0;
+        k1[q] = live ? by_dst.ptr[n + 1] : 0;
+    }
+    for (;;) {
+        bool any = false;
 #pragma unroll
-            for (int c = 0; c < kIn; ++c) z += ((word >> c) & 1u) ? x[c] : 0.0f;
-            z += ((word >> kIn) & 1u) ? (ef[e] * d.scale) * we : 0.0f;
-            msg[(int64_t)k * in.B + b] = tanhf(z + bias);
+        for (int q = 0; q < kPairsPerThread; ++q) any = any || k0[q] < k1[q];
+        if (!any) break;
+        int e[kPairsPerThread][2];
+        uint32_t word[kPairsPerThread][2];
+        float f[kPairsPerThread][2];
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) e[q][i] = k0[q] + i < k1[q] ? by_dst.eid[k0[q] + i] : -1;
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q) {
+            const int b = t.b0 + ((threadIdx.x + q * tarl::kTileThreads) & (t.Bp - 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) word[q][i] = e[q][i] >= 0 ? keep_word(d, in.B, b, e[q][i], k0[q] + i) : 0u;
         }
-    });
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q) {
+            const int b = t.b0 + ((threadIdx.x + q * tarl::kTileThreads) & (t.Bp - 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) f[q][i] = e[q][i] >= 0 ? in.ef[(int64_t)b * in.ef_bs + e[q][i]] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q) {
+            const int p = threadIdx.x + q * tarl::kTileThreads;
+            const int r = p & (t.Bp - 1);
+            const int slot = tarl::tile_slot(t, r, p >> t.sh);
+            const int b = t.b0 + r;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (e[q][i] < 0) continue;
+                const int64_t o = (int64_t)(k0[q] + i) * in.B + b;
+                if (words_out != nullptr) words_out[o] = word[q][i];             // backward reads them back
+                float z = 0.0f;
+#pragma unroll
+                for (int c = 0; c < kIn; ++c) z += ((word[q][i] >> c) & 1u) ? xs[c * tarl::kTileSmem + slot] : 0.0f;
+                z += ((word[q][i] >> kIn) & 1u) ? (f[q][i] * d.scale) * we : 0.0f;
+                msg[o] = tanhf(z + bias);
+            }
+            k0[q] = min(k0[q] + 2, k1[q]);
+        }
+    }
 }
 
 // one thread per (source node, batch row): mean of the stored messages in ascending edge id, then the node update
@@ -536,6 +649,8 @@ __global__ void __launch_bounds__(kThreads) k_value_dz(tarl_csr by_dst, Inputs i
         const int64_t quads = total >> 2;
         const int qpe = B >> 2;                                   // quads per edge
         const int qsh = (qpe & (qpe - 1)) == 0 ? 31 - __clz(qpe) : -1;
+        // (two quads per round, with both edges' first-level loads requested before either's second level, was measured:
+        // 59 -> 72 registers, 0.71 -> 0.89 ms)
         for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < quads; q += step) {
             const int k = qsh >= 0 ? (int)(q >> qsh) : (int)(q / qpe);
             const int b = (int)(q - (int64_t)k * qpe) << 2;
@@ -547,10 +662,17 @@ __global__ void __launch_bounds__(kThreads) k_value_dz(tarl_csr by_dst, Inputs i
             z.z = g.z * (1.0f - m.z * m.z); z.w = g.w * (1.0f - m.w * m.w);
             *reinterpret_cast<float4*>(msg + (int64_t)k * B + b) = z;
             const float zz[4] = {z.x, z.y, z.z, z.w};
+            uint32_t wv[4];
+            if (d.bits == nullptr && d.words != nullptr) {        // the four rows' stored words are one 128-bit vector
+                const uint4 w4 = *reinterpret_cast<const uint4*>(d.words + (int64_t)k * B + b);
+                wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) wv[r] = keep_word(d, B, b + r, e, k);
+            }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const uint32_t word = keep_word(d, B, b + r, e, k);
-                if ((word >> kIn) & 1u) vals[0] += zz[r] * (in.ef[(int64_t)(b + r) * in.ef_bs + e] * d.scale);
+                if ((wv[r] >> kIn) & 1u) vals[0] += zz[r] * (in.ef[(int64_t)(b + r) * in.ef_bs + e] * d.scale);
                 vals[1] += zz[r];
             }
         }
@@ -573,55 +695,69 @@ __global__ void __launch_bounds__(kThreads) k_value_dz(tarl_csr by_dst, Inputs i
     block_store<kGrads>(all, partials + (size_t)blockIdx.x * kGrads);
 }
 
-// Pass 2, (target node, row) tiles as in the forward pass: d w_k += (sum over in-edges of keep_k * d z) * scale * x_k.
-// The in-edges' d z and keep words sit at k*B + b: nothing has to be loaded to find them, and the next edge's pair is
-// requested before the current one is consumed (the round-1 form walked edge id -> message, word, source -> gm one
-// dependent load after the other: 4.7 ms at 7 % of the DRAM bandwidth for 32 rows x 6.0 M edges).
-__global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
+// Pass 2, (target node, row) tiles as in the forward pass: d w_k += sum over in-edges of keep_k * d z * (scale * x_k).
+// The in-edges' d z and keep words sit at k*B + b: nothing has to be loaded to find them. Like the forward walk, a
+// thread takes its four pairs together, two in-edges of each per round (16 loads in flight), and multiplies by the
+// staged input where the edge is consumed — one predicated FFMA per (edge, input) into the thread's 16 running sums,
+// no per-pair accumulators. (History: the round-1 form walked edge id -> message, word, source -> gm one dependent load
+// after the other, 4.7 ms at 7 % of the DRAM bandwidth for 32 rows x 6.0 M edges; one pair at a time with per-pair
+// sums, however its loads were chunked, stayed at 2.0 - 2.3 ms.)
+__global__ void __launch_bounds__(tarl::kTileThreads, 3) k_value_edge_grad_dropout(tarl_csr by_dst, Inputs in, int Bp, Drop d,
                                                                                 const float* __restrict__ dz,
-                                                                                float* __restrict__ partials) {
-    extern __shared__ float xs[];                                 // [kIn][kTileSmem]
+                                                                                float* __restrict__ partials,
+                                                                                const float4* __restrict__ pack) {
+    extern __shared__ float xs[];                                 // [kIn][kTileSmem], then a 224-float buffer per warp
     const tarl::Tile t = tarl::tile_here(in.B, Bp);
-    tarl::tile_walk_nodes(t, [&](int r, int j) {
-        const int n = t.n0 + j;
-        if (n >= in.N || r >= t.nrows) return;
-        if (by_dst.ptr[n] == by_dst.ptr[n + 1]) return;           // nobody points at this node: its inputs are not needed
-        float x[kIn];
-        load_x(in, t.b0 + r, n, x, nullptr);
-        const int slot = tarl::tile_slot(t, r, j);
-#pragma unroll
-        for (int c = 0; c < kIn; ++c) xs[c * tarl::kTileSmem + slot] = x[c] * d.scale;
-    });
+    // (a node nobody points at needs no inputs)
+    stage_inputs(t, in, pack, xs + kIn * tarl::kTileSmem + (threadIdx.x >> 5) * 32 * kNodeDim, nullptr,
+                 [&](int n) { return by_dst.ptr[n] != by_dst.ptr[n + 1]; },
+                 [&](int c, int slot, float v) { xs[c * tarl::kTileSmem + slot] = v * d.scale; });
     __syncthreads();
     float vals[kIn];
 #pragma unroll
     for (int j = 0; j < kIn; ++j) vals[j] = 0.0f;
-    const bool stored = d.bits == nullptr && d.words != nullptr;  // words at k*B + b: prefetchable
-    tarl::tile_walk_rows(t, [&](int r, int j) {
-        const int n = t.n0 + j, b = t.b0 + r;
-        if (n >= in.N || r >= t.nrows) return;
-        const int k0 = by_dst.ptr[n], k1 = by_dst.ptr[n + 1];
-        if (k0 == k1) return;
-        float gx[kIn];
+    const bool stored = d.bits == nullptr && d.words != nullptr;  // words at k*B + b
+    int k0[kPairsPerThread], k1[kPairsPerThread];
 #pragma unroll
-        for (int c = 0; c < kIn; ++c) gx[c] = 0.0f;
-        float gz_nxt = dz[(int64_t)k0 * in.B + b];
-        uint32_t w_nxt = stored ? d.words[(int64_t)k0 * in.B + b] : 0u;
-        for (int k = k0; k < k1; ++k) {
-            const float gz = gz_nxt;
-            uint32_t word = w_nxt;
-            if (k + 1 < k1) {
-                gz_nxt = dz[(int64_t)(k + 1) * in.B + b];
-                if (stored) w_nxt = d.words[(int64_t)(k + 1) * in.B + b];
+    for (int q = 0; q < kPairsPerThread; ++q) {
+        const int p = threadIdx.x + q * tarl::kTileThreads;
+        const int r = p & (t.Bp - 1), n = t.n0 + (p >> t.sh);
+        const bool live = n < in.N && r < t.nrows;
+        k0[q] = live ? by_dst.ptr[n] : 0;
+        k1[q] = live ? by_dst.ptr[n + 1] : 0;
+    }
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q) any = any || k0[q] < k1[q];
+        if (!any) break;
+        float gz[kPairsPerThread][2];
+        uint32_t word[kPairsPerThread][2];
+#pragma unroll
+        for (int q = 0; q < kPairsPerThread; ++q) {
+            const int b = t.b0 + ((threadIdx.x + q * tarl::kTileThreads) & (t.Bp - 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool live = k0[q] + i < k1[q];
+                const int64_t o = (int64_t)(k0[q] + i) * in.B + b;
+                gz[q][i] = live ? dz[o] : 0.0f;
+                word[q][i] = 0u;
+                if (live) word[q][i] = stored ? d.words[o] : keep_word(d, in.B, b, by_dst.eid[k0[q] + i], k0[q] + i);
             }
-            if (!stored) word = keep_word(d, in.B, b, by_dst.eid[k], k);
-#pragma unroll
-            for (int c = 0; c < kIn; ++c) gx[c] += ((word >> c) & 1u) ? gz : 0.0f;
         }
-        const int slot = tarl::tile_slot(t, r, j);
 #pragma unroll
-        for (int c = 0; c < kIn; ++c) vals[c] += gx[c] * xs[c * tarl::kTileSmem + slot];
-    });
+        for (int q = 0; q < kPairsPerThread; ++q) {
+            const int p = threadIdx.x + q * tarl::kTileThreads;
+            const int slot = tarl::tile_slot(t, p & (t.Bp - 1), p >> t.sh);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+                for (int c = 0; c < kIn; ++c)
+                    if ((word[q][i] >> c) & 1u) vals[c] += gz[q][i] * xs[c * tarl::kTileSmem + slot];
+            }
+            k0[q] = min(k0[q] + 2, k1[q]);
+        }
+    }
     float all[18];
 #pragma unroll
     for (int j = 0; j < kIn; ++j) all[j] = vals[j];
@@ -749,8 +885,8 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                                   int32_t agent_rows, const float* msg_weight, const float* msg_bias,
                                   const float* node_weight, const float* node_bias, int32_t batch, int32_t n_nodes,
                                   const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                  const int32_t* source_pos, uint32_t* keep_words, float* msg, float* mean, float* v,
-                                  int32_t* flags, void* stream) {
+                                  const int32_t* source_pos, uint32_t* keep_words, float* agent_pack, float* msg,
+                                  float* mean, float* v, int32_t* flags, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc == TARL_OK) rc = check(by_target, n_nodes);
@@ -766,9 +902,21 @@ int tarl_value_mp_forward_dropout(const tarl_csr* by_source, const tarl_csr* by_
                        by_source->n_edges};
     const int nb = blocks_for((int64_t)batch * n_nodes);
     if ((rc = drop_smem_ready()) != TARL_OK) return rc;
+    if (agent_pack != nullptr) {
+        if ((reinterpret_cast<uintptr_t>(agent_pack) & 15) != 0) return TARL_E_BADARG;
+        k_value_pack_agents<<<(agent_rows + 255) / 256, 256, 0, s>>>(agent_features, agent_rows, reinterpret_cast<float4*>(agent_pack));
+    }
+    // words drawn here: a streaming pass writes them first and the message kernel reads them like the backward pass does
+    const bool draw_first = keep_bits == nullptr && keep_words != nullptr && by_target->n_edges > 0;
+    if (draw_first) {
+        const int64_t total = (int64_t)by_target->n_edges * batch;
+        k_value_keep_words<<<blocks_for(total), kThreads, 0, s>>>(by_target->eid, total, batch,
+                                                                  make_drop(nullptr, 0, seed, p), keep_words);
+    }
     k_value_message_dropout<<<tarl::tile_grid(n_nodes, batch), tarl::kTileThreads, kDropSmemBytes, s>>>(
-        *by_target, in, tarl::tile_rows_pow2(batch), make_drop(keep_bits, keep_batch_stride, seed, p), msg_weight, msg_bias,
-        msg, keep_bits == nullptr ? keep_words : nullptr, flags);
+        *by_target, in, tarl::tile_rows_pow2(batch),
+        make_drop(keep_bits, keep_batch_stride, seed, p, draw_first ? keep_words : nullptr), msg_weight, msg_bias, msg,
+        nullptr, flags, reinterpret_cast<const float4*>(agent_pack));
     k_value_aggregate_msg<<<nb, kThreads, 0, s>>>(*by_source, source_pos, batch, n_nodes, node_weight, node_bias, msg, mean, v);
     return launch_status();
 }
@@ -778,8 +926,8 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                                    int32_t agent_rows, const float* node_weight, int32_t batch, int32_t n_nodes,
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
-                                   const uint32_t* keep_words, float* msg, const float* mean, const float* v,
-                                   const float* grad_v,
+                                   const uint32_t* keep_words, float* agent_pack, float* msg, const float* mean,
+                                   const float* v, const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
@@ -807,7 +955,12 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
         k_value_dz<<<kDzCtas, kThreads, 0, s>>>(*by_target, in, drop, msg, gm, partials + (size_t)n_tiles * kGrads);
     else if (cudaMemsetAsync(partials + (size_t)n_tiles * kGrads, 0, sizeof(float) * kGrads * kDzCtas, s) != cudaSuccess)
         return TARL_E_LAUNCH;
-    k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, kDropSmemBytes, s>>>(*by_target, in, Bp, drop, msg, partials);
+    if (agent_pack != nullptr) {
+        if ((reinterpret_cast<uintptr_t>(agent_pack) & 15) != 0) return TARL_E_BADARG;
+        k_value_pack_agents<<<(agent_rows + 255) / 256, 256, 0, s>>>(agent_features, agent_rows, reinterpret_cast<float4*>(agent_pack));
+    }
+    k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, kDropSmemBytes, s>>>(*by_target, in, Bp, drop, msg, partials,
+                                                                               reinterpret_cast<const float4*>(agent_pack));
     k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, n_tiles + kDzCtas, grads);
     return launch_status();
 }

@@ -219,12 +219,14 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
             inv[by_target.eid.long()] = torch.arange(E, dtype=torch.int32, device=dev)
             src_pos = by_source._pos_in_target = (by_target, inv[by_source.eid.long()].contiguous())
         src_pos = src_pos[1]
+        pack = torch.empty(af.size(0), 12, dtype=torch.float32, device=dev)       # agent rows re-laid as 48-byte rows
+        ctx.pack = pack
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_value_mp_forward_dropout(
                 by_source.ref(), by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(), ef_bs,
                 ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), nb.data_ptr(), B, N,
-                kb_ptr, kb_bs, seed, p, src_pos.data_ptr(), words.data_ptr() if words is not None else None, msg.data_ptr(),
-                mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
+                kb_ptr, kb_bs, seed, p, src_pos.data_ptr(), words.data_ptr() if words is not None else None,
+                pack.data_ptr(), msg.data_ptr(), mean.data_ptr(), v.data_ptr(), flags.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_forward_dropout")
         ctx.words = words
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
@@ -248,7 +250,8 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
             rc = lib.tarl_value_mp_backward_dropout(
                 ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
                 ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), nw.data_ptr(), B, N, kb_ptr, kb_bs, seed, p,
-                ctx.words.data_ptr() if ctx.words is not None else None, msg.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
+                ctx.words.data_ptr() if ctx.words is not None else None, ctx.pack.data_ptr(), msg.data_ptr(),
+                mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
                 grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_backward_dropout")
         s = ctx.shapes
