@@ -339,63 +339,40 @@ def run_native(args):
     model.pack_pop = True
     words = (N + 31) // 32
     sel_hosts = [b[:N].cpu().pin_memory() for b in sel_bank]
-    sel_devs = [torch.empty(N, dtype=torch.float32, device=dev) for _ in range(2)]
     dtt_hosts = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(2)]
     pop_hosts = [torch.empty(words, dtype=torch.int32).pin_memory() for _ in range(2)]
+    host_outs = [{"delta_tt_link": dtt_hosts[j], "pop_bits": pop_hosts[j]} for j in range(2)]
     e2e_steps = min(args.steps, 100)
-    copy_stream = torch.cuda.Stream(dev)        # device -> host
-    in_stream = torch.cuda.Stream(dev)          # host -> device (its own copy engine)
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
     pending = {"k": 0}
 
-    def stage_inputs(k):            # H2D of step k's routing decisions, on the copy stream
-        with torch.cuda.stream(in_stream):
-            sel_devs[k % 2].copy_(sel_hosts[(state["i"] + k - pending["k"]) % len(sel_hosts)], non_blocking=True)
-            ev_in[k % 2].record(in_stream)
-
     def e2e_step():
-        # Double-buffered pipeline around the public call: while step k computes on the main stream, the copy stream
-        # returns step k-1's outputs to the host and brings in step k+2's inputs. Every byte is still moved inside the
-        # timed region; the copies just overlap the kernels of the neighbouring steps.
+        # ONE public call per step, host buffers on both sides: this step's routing decisions (pinned host memory) in,
+        # delta_travel_time per link + pop bits out into pinned host buffers. The library enqueues upload, kernels and
+        # downloads on its own copy streams (tarl_store_step_host), alternating two slots, so the copies of neighbouring
+        # steps overlap this step's kernels; every byte is moved inside the timed region.
         k = pending["k"]
-        stream.wait_event(ev_in[k % 2])
         model.set_time(state["t"])
-        model(g, selected_road=sel_devs[k % 2])
-        dtt = model.direction_mpnn.road_optimality_data["delta_travel_time_per_link"]
-        pop = model.last_pop_bits
-        done = torch.cuda.Event()
-        done.record(stream)
-        in_stream.wait_event(done)
-        stage_inputs(k + 2)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
-            dtt_hosts[k % 2].copy_(dtt, non_blocking=True)
-            pop_hosts[k % 2].copy_(pop, non_blocking=True)
-            dtt.record_stream(copy_stream); pop.record_stream(copy_stream)
-            ev_out[k % 2].record(copy_stream)
+        model(g, selected_road=sel_hosts[state["i"] % len(sel_hosts)], host_out=host_outs[k % 2])
         pending["k"] = k + 1
         state["t"] += 1.0
         state["i"] += 1
 
     # Warm-up long enough for the caching allocator to reach its steady state, then several windows of e2e_steps; the
     # MEDIAN window is reported and every window is listed (a single window is at the mercy of one host hiccup).
-    stage_inputs(0)
-    stage_inputs(1)
     for _ in range(20):
         e2e_step()
-    copy_stream.synchronize()
+    model.host_sync(g)
     model.response_mpnn.update_history.resolve()
     assert model.last_path == "resident"
-    windows = []
+    windows, enqueue = [], []
     for _ in range(5):
         barrier()
         w0 = time.perf_counter()
         ev0.record(stream)
         for _ in range(e2e_steps):
             e2e_step()
-        stream.wait_stream(copy_stream)
-        stream.wait_stream(in_stream)
+        enqueue.append((time.perf_counter() - w0) * 1e3)      # host time to enqueue the window (no synchronisation in it)
+        model.host_join(g)                                    # the window ends when its last download has landed
         ev1.record(stream)
         torch.cuda.synchronize(dev)
         windows.append(max(ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3))
@@ -405,7 +382,7 @@ def run_native(args):
         print(f"[rank {rank}] e2e windows (ms for {e2e_steps} steps): {[round(w, 2) for w in windows]}", file=sys.stderr)
     # the [E] contract of road_optimality_data["delta_travel_time"] on the host side: expanding the per-link vector
     # that crossed the bus with edge_index_routes[0] gives exactly what the device would have materialised
-    copy_stream.synchronize()
+    model.host_sync(g)
     k_last = (pending["k"] - 1) % 2
     full = model.direction_mpnn.road_optimality_data["delta_travel_time"]
     contract_ok = bool(torch.equal(dtt_hosts[k_last][g.edge_index_routes[0].cpu()], full.cpu()))
@@ -416,13 +393,15 @@ def run_native(args):
     e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
            "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4 + words * 4),
            "steps": e2e_steps, "windows_ms": [round(w, 3) for w in windows], "window": "median of 5",
+           "host_enqueue_ms": [round(w, 3) for w in enqueue],
            "kernel_path": model.last_path, "delta_tt_edge_form_reproduced_on_host": contract_ok,
-           "api": "SimulationCoreModel.forward(graph, selected_road=...): state resident on the device (link store "
-                  "behind graph.x, exported when graph.x is read); per step H2D = SELECTED_ROAD decisions [N] fp32 from "
-                  "pinned memory, D2H = delta_travel_time per upstream link [N] fp32 (the [E] vector of "
-                  "road_optimality_data is that value repeated on each out-edge: expanded on whichever side reads it) + "
-                  "pop mask as bits [N/8 bytes] into pinned memory, double-buffered on copy streams so that the copies "
-                  "of steps k-1 / k+2 overlap the kernels of step k; noise drawn on the device"}
+           "api": "SimulationCoreModel.forward(graph, selected_road=<pinned host tensor>, host_out={pinned host "
+                  "buffers}): ONE public call per step; state resident on the device (link store behind graph.x, exported "
+                  "when graph.x is read); per step H2D = SELECTED_ROAD decisions [N] fp32, D2H = delta_travel_time per "
+                  "upstream link [N] fp32 (the [E] vector of road_optimality_data is that value repeated on each "
+                  "out-edge: expanded on whichever side reads it) + pop mask as bits [N/8 bytes]; the library enqueues "
+                  "upload, kernels and downloads itself (tarl_store_step_host: two copy streams, two slots), so the "
+                  "copies of neighbouring steps overlap this step's kernels; noise drawn on the device"}
 
     out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": round(step_ms, 5), "higher_is_better": True,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 22
+#define TARL_ABI_VERSION 23
 
 /* return codes */
 #define TARL_OK 0
@@ -225,6 +225,26 @@ int tarl_cluster_links(int32_t n_links, const int32_t* adj_ptr, const int32_t* a
 int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
                    const float* attr_in, const tarl_step_io* io, float dt, int32_t n_steps,
                    const float* const* sel_bank, int32_t n_bank, void* stream);
+
+/* One step whose inputs and outputs live in HOST memory (what SimulationCoreModel.forward(graph, selected_road=<CPU
+ * tensor>, host_out=...) runs): the routing decisions come from sel_host (pinned, [R*N] fp32; NULL = keep the store's),
+ * delta_travel_time per upstream link and the pop bits go to dtt_host / pop_bits_host (pinned; NULL = not copied) —
+ * the copies of src/transportation_simulator.py:351 (.cpu() of the per-step outputs) and of the routing decisions an
+ * external controller hands in. The copies run on two streams of the pipe's own, ordered against the kernels by
+ * events, so that with two slots used alternately (slot = step & 1) the upload of step k+1 and the download of step
+ * k-1 overlap the kernels of step k while the host merely enqueues: ONE library call per step.
+ * Per slot the caller owns: sel_stage (device [R*N] fp32, receives sel_host and becomes this step's SELECTED_ROAD —
+ * pass it as store->sel), io->delta_tt_link and io->pop_bits (device outputs of this step; the next use of the slot
+ * waits for their download). tarl_host_pipe_join makes `stream` wait for every copy issued so far (timing, or
+ * before the host reads the buffers after synchronising `stream`). */
+typedef struct tarl_host_pipe tarl_host_pipe;
+int tarl_host_pipe_create(tarl_host_pipe** pipe);
+int tarl_host_pipe_destroy(tarl_host_pipe* pipe);
+int tarl_host_pipe_join(tarl_host_pipe* pipe, void* stream);
+int tarl_store_step_host(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                         const float* attr_in, const tarl_step_io* io, tarl_host_pipe* pipe, int32_t slot,
+                         const float* sel_host, float* sel_stage, float* dtt_host, uint32_t* pop_bits_host,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Learned-MPNN path (fp32, tolerance 1e-5 relative against the reference).

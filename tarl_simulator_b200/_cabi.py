@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 22       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 23       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -118,6 +118,10 @@ SIGNATURES = {
     "tarl_store_step_withdraw": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _ATB, _CSR1, _I32, _P, _P, _P, _P, _P]),
     "tarl_cluster_links": (C.c_int, [_I32, _P, _P, _I32, _P]),
     "tarl_store_run": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _F, _I32, _P, _I32, _P]),
+    "tarl_host_pipe_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "tarl_host_pipe_destroy": (C.c_int, [_P]),
+    "tarl_host_pipe_join": (C.c_int, [_P, _P]),
+    "tarl_store_step_host": (C.c_int, [_CSR, _ELL, _STORE, _P, _SIO, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_forward": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "tarl_policy_embed_backward": (C.c_int, [_CSR1, _ROWS, _P, _I32, _P, _P, _I32, _P]),
     "tarl_graphdist_partial_count": (_I32, [_I32, _I32]),

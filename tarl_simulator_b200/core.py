@@ -339,13 +339,24 @@ class SimulationCoreModel(nn.Module):
         self.direction_mpnn.set_time(time)
         self.response_mpnn.set_time(time)
 
-    def forward(self, graph, noise: Optional[torch.Tensor] = None, selected_road: Optional[torch.Tensor] = None):
-        """`selected_road` (optional, fp32 [N] on the device): this step's SELECTED_ROAD column, applied inside the
-        first kernel instead of by a separate strided write into graph.x beforehand."""
+    def forward(self, graph, noise: Optional[torch.Tensor] = None, selected_road: Optional[torch.Tensor] = None,
+                host_out: Optional[dict] = None):
+        """`selected_road` (optional, fp32 [N]): this step's SELECTED_ROAD column, applied inside the first kernel
+        instead of by a separate strided write into graph.x beforehand. On the device, or — resident steps only — a
+        PINNED host tensor: the upload then rides on the library's own copy stream (tarl_store_step_host).
+        `host_out` (optional, resident steps only): {"delta_tt_link": pinned fp32 [N], "pop_bits": pinned int32
+        [ceil(N/32)]} — host buffers that receive this step's delta_travel_time per upstream link and pop bits
+        (either key may be absent), copied asynchronously; complete after host_sync()."""
         N = int(graph.num_roads)
         rs = self._resident_for(graph, N)
+        host = host_out is not None or (selected_road is not None and not selected_road.is_cuda)
         if rs is not None:
+            if host:
+                return self._forward_resident_host(graph, rs, N, noise, selected_road, host_out or {})
             return self._forward_resident(graph, rs, N, noise, selected_road)
+        if host:
+            raise ValueError("host buffers (a CPU selected_road, host_out=) need the resident link store: "
+                             "construct the model with resident='always' (or 'auto' and leave graph.x alone between calls)")
         x_roads = graph.x[:N]                       # a view: every write lands in graph.x (reference :52,:81)
         _require_cuda_rows(x_roads, self.Nmax)
         ei = graph.edge_index_routes
@@ -436,6 +447,50 @@ class SimulationCoreModel(nn.Module):
         self.last_pop_bits = out.get("pop_bits")
         self.last_path = "resident"
         return graph
+
+    def _forward_resident_host(self, graph, rs, N, noise, selected_road, host_out):
+        """The resident step with host buffers on either side: one library call enqueues upload, kernels and downloads."""
+        store = rs.store
+        dev = store.device
+        ok = self.__dict__.setdefault("_host_ok", set())          # buffers already checked (pinned, shape, dtype)
+        dtt_h, bits_h = host_out.get("delta_tt_link"), host_out.get("pop_bits")
+        for t_, dt_, n_ in ((selected_road, torch.float32, N), (dtt_h, torch.float32, N), (bits_h, torch.int32, store.words)):
+            if t_ is None or (t_.data_ptr(), n_) in ok:
+                continue
+            if t_.is_cuda or t_.dtype != dt_ or t_.numel() != n_ or not t_.is_contiguous() or not t_.is_pinned():
+                raise ValueError("host buffers must be pinned, contiguous CPU tensors: selected_road / delta_tt_link fp32 [N], "
+                                 "pop_bits int32 [ceil(N/32)]")
+            if len(ok) > 64:
+                ok.clear()
+            ok.add((t_.data_ptr(), n_))
+        if noise is not None:
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+            if noise.numel() != store.E:
+                raise ValueError("noise must hold one uniform per dual edge")
+        pop, flags = self._arena.take(N, dev)
+        o = store.step_host(float(self.time), sel_host=selected_road, dtt_host=dtt_h, pop_bits_host=bits_h, noise=noise,
+                            out={"pop": pop, "flags": flags})
+        rs.dirty = True
+        rs.seen = rs.loaded
+        # (device copies of the outputs: per-slot buffers, valid until the next-but-one host step)
+        self.direction_mpnn.road_optimality_data = LazyOptimality(store, o["delta_tt_link"])
+        self.direction_mpnn._flags = flags
+        self.response_mpnn.update_history.push(self.time, pop, flags)
+        self.last_pop = pop
+        self.last_pop_bits = o["pop_bits"]
+        self.last_path = "resident"
+        return graph
+
+    def host_join(self, graph):
+        """torch's current stream waits for the host copies of every host step taken on `graph` so far."""
+        rs = graph.__dict__.get("_resident") if isinstance(graph, Data) else None
+        if rs is not None and rs.store is not None:
+            rs.store.host_join()
+
+    def host_sync(self, graph):
+        """Blocks until the host buffers of every host step taken on `graph` are complete."""
+        self.host_join(graph)
+        torch.cuda.current_stream(graph.x.device if not isinstance(graph, Data) else graph.__dict__["_x"].device).synchronize()
 
     def check_errors(self):
         """Synchronises; raises if any queued step reported a data-dependent fault."""

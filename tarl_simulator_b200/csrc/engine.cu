@@ -864,6 +864,93 @@ int tarl_store_step_withdraw(const tarl_dual_csr* g, const tarl_dual_ell* ell, c
     return launch_status();
 }
 
+struct tarl_host_pipe {
+    cudaStream_t h2d, d2h;
+    cudaEvent_t in[2], computed[2], out[2];
+    bool used[2];
+};
+
+int tarl_host_pipe_create(tarl_host_pipe** pipe) {
+    if (pipe == nullptr) return TARL_E_BADARG;
+    tarl_host_pipe* p = new tarl_host_pipe();
+    bool ok = cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaEventCreateWithFlags(&p->in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->computed[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->out[i], cudaEventDisableTiming) == cudaSuccess;
+        p->used[i] = false;
+    }
+    if (!ok) { delete p; return TARL_E_LAUNCH; }
+    *pipe = p;
+    return TARL_OK;
+}
+
+int tarl_host_pipe_destroy(tarl_host_pipe* p) {
+    if (p == nullptr) return TARL_OK;
+    cudaStreamSynchronize(p->h2d);
+    cudaStreamSynchronize(p->d2h);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(p->in[i]); cudaEventDestroy(p->computed[i]); cudaEventDestroy(p->out[i]); }
+    cudaStreamDestroy(p->h2d);
+    cudaStreamDestroy(p->d2h);
+    delete p;
+    return TARL_OK;
+}
+
+int tarl_host_pipe_join(tarl_host_pipe* p, void* stream) {
+    if (p == nullptr) return TARL_E_BADARG;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < 2; ++i) {
+        if (!p->used[i]) continue;
+        if (cudaStreamWaitEvent(cs, p->in[i], 0) != cudaSuccess || cudaStreamWaitEvent(cs, p->out[i], 0) != cudaSuccess)
+            return TARL_E_LAUNCH;
+    }
+    return TARL_OK;
+}
+
+int tarl_store_step_host(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
+                         const float* attr_in, const tarl_step_io* io, tarl_host_pipe* p, int32_t slot,
+                         const float* sel_host, float* sel_stage, float* dtt_host, uint32_t* pop_bits_host,
+                         void* stream) {
+    Store s;
+    int rc = make_store(store, &s);
+    if (rc != TARL_OK) return rc;
+    if ((rc = check_step(g, ell, s, attr_in, io)) != TARL_OK) return rc;
+    if (p == nullptr || slot < 0 || slot > 1) return TARL_E_BADARG;
+    if ((sel_host != nullptr) != (sel_stage != nullptr)) return TARL_E_BADARG;
+    if ((dtt_host != nullptr && io->delta_tt_link == nullptr) || (pop_bits_host != nullptr && io->pop_bits == nullptr))
+        return TARL_E_BADARG;
+    if (s.N == 0) return TARL_OK;
+    cudaStream_t cs = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)s.N * s.R;
+    bool ok = true;
+    if (sel_host != nullptr) {
+        // the staging buffer of this slot was last read by the step taken two calls ago
+        if (p->used[slot]) ok = ok && cudaStreamWaitEvent(p->h2d, p->computed[slot], 0) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(sel_stage, sel_host, n * sizeof(float), cudaMemcpyHostToDevice, p->h2d) == cudaSuccess;
+        ok = ok && cudaEventRecord(p->in[slot], p->h2d) == cudaSuccess;
+        ok = ok && cudaStreamWaitEvent(cs, p->in[slot], 0) == cudaSuccess;
+        s.sel = sel_stage;
+    }
+    // ... and its device outputs are still being downloaded until out[slot] fires
+    if (p->used[slot] && (dtt_host != nullptr || pop_bits_host != nullptr))
+        ok = ok && cudaStreamWaitEvent(cs, p->out[slot], 0) == cudaSuccess;
+    if (!ok) return TARL_E_LAUNCH;
+    launch_step(g, ell, s, attr_in, *io, cs, TARL_PHASE_SELECT_APPEND | TARL_PHASE_RESPOND_SHIFT);
+    ok = cudaEventRecord(p->computed[slot], cs) == cudaSuccess;
+    if (dtt_host != nullptr || pop_bits_host != nullptr) {
+        ok = ok && cudaStreamWaitEvent(p->d2h, p->computed[slot], 0) == cudaSuccess;
+        if (dtt_host != nullptr)
+            ok = ok && cudaMemcpyAsync(dtt_host, io->delta_tt_link, n * sizeof(float), cudaMemcpyDeviceToHost, p->d2h) == cudaSuccess;
+        if (pop_bits_host != nullptr)
+            ok = ok && cudaMemcpyAsync(pop_bits_host, io->pop_bits, (size_t)s.R * ((s.N + 31) >> 5) * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToHost, p->d2h) == cudaSuccess;
+    }
+    ok = ok && cudaEventRecord(p->out[slot], p->d2h) == cudaSuccess;
+    p->used[slot] = true;
+    return ok ? launch_status() : TARL_E_LAUNCH;
+}
+
 int tarl_store_run(const tarl_dual_csr* g, const tarl_dual_ell* ell, const tarl_link_store* store,
                    const float* attr_in, const tarl_step_io* io, float dt, int32_t n_steps,
                    const float* const* sel_bank, int32_t n_bank, void* stream) {

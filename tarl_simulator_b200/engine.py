@@ -252,6 +252,73 @@ class LinkStore:
             self.t_last = float(t)
         return self._to_links(self.pop[: self.N * self.R].view(self.R, self.N))
 
+    # ------------------------------------------------------------------------------------------------------------
+    def _host_pipe(self):
+        """The pipe of tarl_store_step_host (two copy streams + events, owned by the library) and the per-slot device
+        buffers a host step uses: SELECTED_ROAD staging, delta_travel_time per link, pop bits."""
+        if getattr(self, "_pipe", None) is None:
+            if self.slot_link is not None:
+                raise NotImplementedError("host steps need the store in link-id order (cluster=False)")
+            h = C.c_void_p()
+            _cabi.check(_cabi.lib().tarl_host_pipe_create(C.byref(h)), "tarl_host_pipe_create")
+            self._pipe = h
+            L = max(self.N * self.R, 1)
+            f32 = dict(dtype=torch.float32, device=self.device)
+            self._host_stage = [torch.empty(L, **f32) for _ in range(2)]
+            self._host_dtt = [torch.empty(L, **f32) for _ in range(2)]
+            self._host_bits = [torch.empty(max(self.R * self.words, 1), dtype=torch.int32, device=self.device) for _ in range(2)]
+            self._host_slot = 0
+        return self._pipe
+
+    def step_host(self, t: float, sel_host: torch.Tensor | None = None, dtt_host: torch.Tensor | None = None,
+                  pop_bits_host: torch.Tensor | None = None, noise: torch.Tensor | None = None, out=None,
+                  variant: int = VARIANT_ELL):
+        """One core step with HOST inputs / outputs (tarl_store_step_host): sel_host (pinned fp32 [R*N], this step's
+        SELECTED_ROAD in link-id order), dtt_host (pinned fp32 [R*N]) and pop_bits_host (pinned int32 [R*words]) are
+        copied on the pipe's own streams around the kernels; successive calls alternate two slots, so the upload of the
+        next step and the download of the previous one overlap this step's kernels. Returns the dict of this step's
+        DEVICE outputs ("delta_tt_link", "pop_bits" — per-slot buffers, overwritten by the next-but-one host step —
+        plus whatever `out` held). The host buffers are complete once host_join() + a synchronisation of the current
+        stream (or of the device) has passed."""
+        pipe = self._host_pipe()
+        slot = self._host_slot
+        self._host_slot ^= 1
+        o = dict(out) if out else {}
+        o.setdefault("delta_tt_link", self._host_dtt[slot])
+        o.setdefault("pop_bits", self._host_bits[slot])
+        stage = None
+        if sel_host is not None:
+            stage = self._host_stage[slot]
+            self.sel = stage                                  # this step's SELECTED_ROAD array (a pointer swap)
+        self._fill_struct()
+        io = self._step_io(t, noise, self.step_id, True, True, o)
+        with torch.cuda.device(self.device):
+            rc = _cabi.lib().tarl_store_step_host(
+                self.topo.ref(), C.byref(self._ell[0]) if variant == VARIANT_ELL else None, C.byref(self._struct),
+                self.attr_in.data_ptr(), io, pipe, slot, sel_host.data_ptr() if sel_host is not None else None,
+                stage.data_ptr() if stage is not None else None, dtt_host.data_ptr() if dtt_host is not None else None,
+                pop_bits_host.data_ptr() if pop_bits_host is not None else None, self._stream())
+        _cabi.check(rc, "tarl_store_step_host")
+        self.cur ^= 1
+        self.step_id += 1
+        self.t_last = float(t)
+        return o
+
+    def host_join(self):
+        """torch's current stream waits for every host copy the host steps have issued."""
+        if getattr(self, "_pipe", None) is not None:
+            with torch.cuda.device(self.device):
+                _cabi.check(_cabi.lib().tarl_host_pipe_join(self._pipe, self._stream()), "tarl_host_pipe_join")
+
+    def __del__(self):
+        pipe = getattr(self, "_pipe", None)
+        if pipe is not None:
+            try:
+                _cabi.lib().tarl_host_pipe_destroy(pipe)
+            except Exception:
+                pass
+            self._pipe = None
+
     def can_fuse_withdraw(self, variant: int = VARIANT_ELL, phase_mask: int = PHASE_SELECT_APPEND | PHASE_RESPOND_POP) -> bool:
         return (variant == VARIANT_ELL and self.slot_link is None and self.N > 0
                 and phase_mask == (PHASE_SELECT_APPEND | PHASE_RESPOND_POP))

@@ -104,6 +104,48 @@ def test_dropin_forward_with_injected_noise_at_benchmark_sizes(name, steps):
     assert len(model.response_mpnn.update_history) == steps
 
 
+@pytest.mark.parametrize("name,steps", [("grid100", 9), ("ring_radial_1m", 6)])
+def test_dropin_forward_with_host_buffers_matches_the_oracle(name, steps):
+    """SimulationCoreModel.forward(graph, selected_road=<pinned host tensor>, host_out=...) — the call bench.py times
+    end to end (tarl_store_step_host: upload, kernels and downloads enqueued by one library call on its own copy
+    streams, two alternating slots) — against the oracle, step by step: graph.x, and the HOST copies of
+    delta_travel_time per link (expanded to the reference's [E] form) and of the pop bits."""
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.core import SimulationCoreModel
+    g, Nmax, _ = _workload(name)
+    N, E = int(g.num_roads), g.edge_index_routes.size(1)
+    x, ei, w, cc, c = _oracle_inputs(g, Nmax)
+    model = SimulationCoreModel(Nmax=Nmax, device="cuda", time=T0, resident="always")
+    words = (N + 31) // 32
+    sels = [torch.empty(N, dtype=torch.float32).pin_memory() for _ in range(3)]
+    outs = [{"delta_tt_link": torch.empty(N, dtype=torch.float32).pin_memory(),
+             "pop_bits": torch.empty(words, dtype=torch.int32).pin_memory()} for _ in range(steps)]
+    gen = torch.Generator().manual_seed(11)
+    us, sel_log = [], []
+    for s in range(steps):                       # every step is enqueued before anything is read back
+        sel = synthetic.random_out_neighbour(g, 3000 + s).cpu()
+        if s >= 3:
+            model.host_sync(g)                   # the pinned input buffer about to be reused has been uploaded
+        sels[s % 3].copy_(sel)
+        u = torch.rand(E, generator=gen).clamp_(min=1e-7)
+        us.append(u); sel_log.append(sel)
+        model.set_time(T0 + s)
+        model(g, noise=u.cuda(), selected_road=sels[s % 3], host_out=outs[s])
+        assert model.last_path == "resident"
+    model.host_sync(g)
+    src = ei[0]
+    for s in range(steps):
+        x[:, c.SEL] = sel_log[s]
+        ref = core_port.core_step(x, ei, w, T0 + s, Nmax, us[s], cc)
+        assert torch.equal(outs[s]["delta_tt_link"][src], ref["delta_tt"]), f"{name}: host delta_tt differs at step {s}"
+        rp = ref["pop"] if ref["pop"] is not None else torch.zeros(N, dtype=torch.bool)
+        assert torch.equal(_unpack_bits(outs[s]["pop_bits"], N), rp), f"{name}: host pop bits differ at step {s}"
+    assert torch.equal(g.x[:N].cpu(), x), f"{name}: graph.x differs from the oracle after {steps} host steps"
+    model.check_errors()
+    with pytest.raises(ValueError):              # host buffers must be pinned
+        model(g, selected_road=torch.zeros(N), host_out=outs[0])
+
+
 def _fan_in_case(weights, copies, Nmax=15):
     """`copies` independent motifs: k upstream links (each holding one due agent that selects d) -> one empty link d.
     Link ids: motif m owns [m*(k+1), (m+1)*(k+1)), d last. Returns x0, edge_index, edge_attr."""
