@@ -135,9 +135,8 @@ typedef struct tarl_link_store {
     void* stat_b;       /* [N] 16-byte {LENGTH, MAX_FLOW, 0, 0} (export only)                            */
     void* queue;        /* [R*N*(nmax-1)] 16-byte ring slots {agent id, arrival, exit, pad}              */
     void* post;         /* [R*N] 8-byte scratch {NUM, tail id} handed from the direction to the response phase */
-    void* pop_hint;     /* [R*N] bytes, zeroed ONCE by the caller: set by the direction phase on the upstream link
-                           whose head was admitted, consumed (and cleared) by the response phase to fetch the ring
-                           slots of a pop one dependent load earlier                                            */
+    void* pop_hint;     /* unused since ABI 23 (may be NULL): the "pop hint" bytes of earlier versions cost the direction
+                           phase more than they returned to the response phase                             */
     const int32_t* slot_link; /* [N] link id held by store slot s, or NULL = identity. The store may keep the links
                                  in a locality order of its own (tarl_cluster_links): everything indexed [R*N] above
                                  and the topology handed to tarl_store_step are then in SLOT order; import / export

@@ -119,7 +119,6 @@ __device__ __forceinline__ float gumbel_score(float p, float u) {     // src/dir
 
 struct Pick {
     float psum, id;
-    int src;          // store index (replica*N + link) of the upstream link whose head was picked
     bool have;
 };
 
@@ -150,7 +149,7 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
                                                float ridx_d) {
     const int base = L - d;
     const int k0 = g.in_ptr[d], k1 = g.in_ptr[d + 1];
-    Pick out = {0.0f, 0.0f, -1, false};
+    Pick out = {0.0f, 0.0f, false};
     int n_elig = 0, lone = -1;
     bool safe = true;
     for (int k = k0; k < k1; ++k) {
@@ -167,7 +166,7 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
     if (!(out.psum > 0.0f)) return out;
     if (safe && n_elig == 1) {
         const int Lu = base + g.in_src[lone];
-        out.id = s.hot_cur[2 * Lu].x; out.src = Lu; out.have = true;
+        out.id = s.hot_cur[2 * Lu].x; out.have = true;
         return out;
     }
     float best = -FLT_MAX;
@@ -180,7 +179,7 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
         if (safe && !(p > 0.0f)) continue;
         const float uu = kExtNoise ? nz.ext[(int64_t)r * g.n_edges + g.in_eid[k]] : philox_uniform(nz, L, k - k0, un, grp);
         const float sc = gumbel_score(p, uu);
-        if (sc > best) { best = sc; out.id = U.x; out.src = Lu; out.have = true; }
+        if (sc > best) { best = sc; out.id = U.x; out.have = true; }
     }
     return out;
 }
@@ -188,7 +187,9 @@ __device__ __noinline__ Pick scan_in_edges_csr(const tarl_dual_csr& g, const Sto
 // Tail append on the link's own record (src/direction_mpnn.py:171-195, on EVERY link), the {NUM, tail id} summary the
 // response phase gathers, delta_travel_time of the link's head (:94-96, from the PRE-step state: ONE value per upstream
 // link — every out-edge of the link carries the same number, tarl_expand_delta_tt materialises the [E] form), and the
-// pop hint for the upstream link whose head was admitted here.
+// (Until ABI 22 the link also set a "pop hint" byte on the upstream link whose head it admitted, so that the response
+// phase could request that link's ring slots one load level earlier: the scattered byte store cost the direction
+// kernel 1.9 us per step of one million links and returned 0.3 us to the response kernel — removed.)
 template <bool kWide>
 __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4 hA, float4 hB, const float4 st,
                                                    const Pick pk, float t, float* __restrict__ dtt_link,
@@ -224,13 +225,14 @@ __device__ __forceinline__ void append_and_publish(const Store& s, int L, float4
             hB.z = dep_new;
         }
         hA.z = num_post;
-        if (chosen != 0.0f && pk.src >= 0) s.hint[pk.src] = 1;     // that link's head just moved here: it will pop
     }
     hB.w = __int_as_float(meta);
     const uint64_t keep = l2_policy(s.pol_state);
     if (kWide) st_record(&s.hot_next[2 * (size_t)L], hA, hB, s.pol_state == kPolKeep);
     else st_record_narrow(&s.hot_next[2 * (size_t)L], hA, hB, keep);     // inside a __noinline__ function
+#ifndef TARL_ABLATE_POST        // tuning only (wrong results)
     st_hint(&s.post[L], make_float2(num_post, tail_post), keep);
+#endif
 }
 
 // The general form of the direction phase for one link: in-edge scan out of the CSR (any degree, any edge weight, any
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
     ld_record(&s.hot_cur[2 * (size_t)L], hA, hB, s.pol_state == kPolKeep);
     const bool free_d = hA.z < (hA.w - 3.0f);
     const float room_d = hA.w - hA.z, ridx_d = st.z;
-    Pick pk = {0.0f, 0.0f, -1, false};
+    Pick pk = {0.0f, 0.0f, false};
     // level 2: the neighbours' records, all gathers in flight together
     float4 U[W];
     float S[W];
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
         if (u[j] >= 0) {
             p[j] = edge_prob(U[j], S[j], t, free_d, room_d, ridx_d, a[j]);
             pk.psum += p[j];
-            if (p[j] > 0.0f) { ++n_elig; pk.id = U[j].x; pk.src = base + u[j]; }
+            if (p[j] > 0.0f) { ++n_elig; pk.id = U[j].x; }
         }
     }
     if (pk.psum > 0.0f) {
@@ -387,7 +389,6 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
         } else {
             float best = -FLT_MAX;
             float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
-            pk.src = -1;
             uint32_t klo = 0u, khi = 0u;
             if (!kExtNoise) philox_key(nz, klo, khi);
 #pragma unroll
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
 #endif
                 if (u[j] >= 0 && !(safe && !(p[j] > 0.0f))) {
                     const float sc = gumbel_score(p[j], kExtNoise ? uu[j] : un[j & 3]);
-                    if (sc > best) { best = sc; pk.id = U[j].x; pk.src = base + u[j]; pk.have = true; }
+                    if (sc > best) { best = sc; pk.id = U[j].x; pk.have = true; }
                 }
             }
         }
@@ -411,9 +412,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
 // ------------------------------------------------------------------------------------------------ response phase
 // The pop itself (src/response_mpnn.py:119-122) as a ring-head increment: new head <- logical slot 1, and the slot that
 // becomes logical Nmax-1 <- old logical Nmax-1 (the reference's shift leaves the last slot in place, i.e. duplicates it).
-// `have` says q_head / q_last were fetched ahead of time (hinted links).
-__device__ __forceinline__ float pop_head(const Store& s, int L, float4 hA, float4 hB, float t, bool have, float4 q_head,
-                                          float4 q_last) {
+__device__ __forceinline__ float pop_head(const Store& s, int L, float4 hA, float4 hB, float t) {
     int meta = __float_as_int(hB.w);
     const int rh = meta & kMetaRingMask;
     const int M = s.M;
@@ -421,10 +420,9 @@ __device__ __forceinline__ float pop_head(const Store& s, int L, float4 hA, floa
     const bool gv = meta & kMetaGarbage;
     const float4 garbage = make_float4(0.0f, t, hB.z, 0.0f);    // pending garbage was (re)written this very step
     float4* Q = s.queue + (size_t)L * M;
-    if (!have) {
-        q_head = Q[rh];
-        if (M > 1) q_last = Q[ring_pos(rh, M, M)];
-    }
+    const float4 q_head = Q[rh];
+    float4 q_last = q_head;
+    if (M > 1) q_last = Q[ring_pos(rh, M, M)];
     const float4 new_head = (gv && q == 1) ? garbage : q_head;
     if (M > 1) {
         Q[rh] = (gv && q == M) ? garbage : q_last;              // becomes logical slot M after the increment
@@ -471,13 +469,12 @@ __global__ void __launch_bounds__(kThreads) k_csr_respond_pop(tarl_dual_csr g, S
     float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     if (u < s.N) {
         A = s.hot_next[2 * (size_t)L]; B = s.hot_next[2 * (size_t)L + 1];
-        if (s.hint[L]) s.hint[L] = 0;
         accept = scan_out_edges_csr(g, s, base, u, A);
         pop[L] = accept ? 1 : 0;
     }
     publish_pop_bits(pop_bits, accept, r, u, s.N);
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
-    if (accept) pop_head(s, L, A, B, t, false, A, A);
+    if (accept) pop_head(s, L, A, B, t);
 }
 
 #ifndef TARL_RESPOND_MINBLOCKS
@@ -491,17 +488,16 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_RESPOND_MINBLOCKS : 1)
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + u;
-    bool accept = false, hinted = false, fetched = false;
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
+    bool accept = false;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     const uint64_t keep = l2_policy(s.pol_state), strm = l2_policy(s.pol_static);
-    if (ahead > 0 && threadIdx.x < 3 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
+    if (ahead > 0 && threadIdx.x < 2 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
         const Ahead tl = tile_ahead(ahead, s.N);
         if (tl.count > 0) {
-            const int i = (int)threadIdx.x - 3;
+            const int i = (int)threadIdx.x - 2;
             const size_t L0 = (size_t)tl.r * s.N + tl.d0;
-            if (i == -3) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
-            else if (i == -2) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
-            else if (i == -1) l2_prefetch_span(s.hint, L0, tl.count);
+            if (i == -2) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
+            else if (i == -1) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
             else l2_prefetch_span(ell.out_dst, ((size_t)i * ell.pitch + tl.d0) * 4, tl.count * 4);
         }
     }
@@ -513,8 +509,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_RESPOND_MINBLOCKS : 1)
     if (u < s.N) {
         // level 1: own post-append record and whether a downstream link admitted this link's head
         ld_record(&s.hot_next[2 * (size_t)L], A, B, s.pol_state == kPolKeep);
-        hinted = s.hint[L] != 0;
-        // level 2: the neighbours' summaries and, for hinted links, the two ring slots a pop needs
+        // level 2: the neighbours' summaries (the ring slots of a pop are a third level, on the ~25 % of links that pop)
         if (dn[W - 1] == -2) {
             accept = scan_out_edges_csr(g, s, base, u, A);
         } else {
@@ -522,22 +517,14 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_RESPOND_MINBLOCKS : 1)
 #pragma unroll
             for (int j = 0; j < W; ++j)
                 if (dn[j] >= 0) D[j] = ld_hint(&s.post[base + dn[j]], keep);
-            if (hinted) {
-                const int rh = __float_as_int(B.w) & kMetaRingMask;
-                const float4* Q = s.queue + (size_t)L * s.M;
-                q_head = Q[rh];
-                if (s.M > 1) q_last = Q[ring_pos(rh, s.M, s.M)];
-                fetched = true;
-            }
 #pragma unroll
             for (int j = 0; j < W; ++j)
                 if (dn[j] >= 0) accept = accept || accepts(A, D[j]);
         }
-        if (hinted) s.hint[L] = 0;
         pop[L] = accept ? 1 : 0;
     }
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
-    if (accept) pop_head(s, L, A, B, t, fetched, q_head, q_last);
+    if (accept) pop_head(s, L, A, B, t);
     publish_pop_bits(pop_bits, accept, r, u, s.N);      // last: nothing else is live any more
 }
 
@@ -580,17 +567,16 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
     const int r = blockIdx.y;
     const int base = r * s.N;
     const int L = base + u;
-    bool accept = false, hinted = false, fetched = false;
-    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A, q_head = A, q_last = A;
+    bool accept = false;
+    float4 A = make_float4(0.f, 0.f, 0.f, 0.f), B = A;
     const uint64_t keep = l2_policy(s.pol_state), strm = l2_policy(s.pol_static);
-    if (ahead > 0 && threadIdx.x < 3 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
+    if (ahead > 0 && threadIdx.x < 2 + W) {     // level 0: the level-1 data of the tile `ahead` launches further on
         const Ahead tl = tile_ahead(ahead, s.N);
         if (tl.count > 0) {
-            const int i = (int)threadIdx.x - 3;
+            const int i = (int)threadIdx.x - 2;
             const size_t L0 = (size_t)tl.r * s.N + tl.d0;
-            if (i == -3) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
-            else if (i == -2) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
-            else if (i == -1) l2_prefetch_span(s.hint, L0, tl.count);
+            if (i == -2) l2_prefetch_span(s.hot_next, L0 * 32, tl.count * 32);
+            else if (i == -1) l2_prefetch_span(s.post, L0 * 8, tl.count * 8);
             else l2_prefetch_span(ell.out_dst, ((size_t)i * ell.pitch + tl.d0) * 4, tl.count * 4);
         }
     }
@@ -601,7 +587,6 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
     pdl_wait();
     if (u < s.N) {
         ld_record(&s.hot_next[2 * (size_t)L], A, B, s.pol_state == kPolKeep);
-        hinted = s.hint[L] != 0;
         if (dn[W - 1] == -2) {
             accept = scan_out_edges_csr(g, s, base, u, A);
         } else {
@@ -609,24 +594,16 @@ __global__ void __launch_bounds__(kThreads) k_ell_respond_pop_withdraw(tarl_dual
 #pragma unroll
             for (int j = 0; j < W; ++j)
                 if (dn[j] >= 0) D[j] = ld_hint(&s.post[base + dn[j]], keep);
-            if (hinted) {
-                const int rh = __float_as_int(B.w) & kMetaRingMask;
-                const float4* Q = s.queue + (size_t)L * s.M;
-                q_head = Q[rh];
-                if (s.M > 1) q_last = Q[ring_pos(rh, s.M, s.M)];
-                fetched = true;
-            }
 #pragma unroll
             for (int j = 0; j < W; ++j)
                 if (dn[j] >= 0) accept = accept || accepts(A, D[j]);
         }
-        if (hinted) s.hint[L] = 0;
         pop[L] = accept ? 1 : 0;
     }
     publish_pop_bits(pop_bits, accept, r, u, s.N);
     if (__syncthreads_or(accept) && threadIdx.x == 0) flags[TARL_FLAG_ANY_POP] = 1;
     float head_exit = A.y, num = A.z;
-    if (accept) { head_exit = pop_head(s, L, A, B, t, fetched, q_head, q_last); num = A.z - 1.0f; }
+    if (accept) { head_exit = pop_head(s, L, A, B, t); num = A.z - 1.0f; }
     if (u < s.N) {
         if (0.0f < num && head_exit <= t) num = withdraw_due_link(s, wa, t, flags, r, u);     // slot 0 is due: :362-366
         else wa.mask[L] = 0;
@@ -676,8 +653,7 @@ namespace tarl {
 int make_store(const tarl_link_store* p, Store* s) {
     if (p == nullptr || p->n_links < 0 || p->n_replicas < 1 || p->nmax < 2 || p->nmax - 1 > kMetaRingMask) return TARL_E_BADARG;
     if (p->n_replicas > 65535 || (int64_t)p->n_links * p->n_replicas * 2 >= INT32_MAX) return TARL_E_BADARG;
-    if (p->n_links > 0 && (!p->hot_cur || !p->hot_next || !p->sel || !p->stat_a || !p->stat_b || !p->queue || !p->post ||
-                           !p->pop_hint))
+    if (p->n_links > 0 && (!p->hot_cur || !p->hot_next || !p->sel || !p->stat_a || !p->stat_b || !p->queue || !p->post))
         return TARL_E_BADARG;
     s->N = p->n_links; s->R = p->n_replicas; s->Nmax = p->nmax; s->M = p->nmax - 1;
     s->hot_cur = static_cast<const float4*>(p->hot_cur);
@@ -687,7 +663,6 @@ int make_store(const tarl_link_store* p, Store* s) {
     s->stat_b = static_cast<const float4*>(p->stat_b);
     s->queue = static_cast<float4*>(p->queue);
     s->post = static_cast<float2*>(p->post);
-    s->hint = static_cast<uint8_t*>(p->pop_hint);
     s->slot_link = p->slot_link;
     s->link_slot = p->link_slot;
     if ((p->slot_link == nullptr) != (p->link_slot == nullptr)) return TARL_E_BADARG;

@@ -25,9 +25,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
                                               uint32_t k1, float out[4]) {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;   // one IMAD.WIDE each
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     const uint32_t c[4] = {c0, c1, c2, c3};
@@ -48,7 +47,6 @@ struct Store {
     const float4* stat_b;    // [N] {LENGTH, MAX_FLOW, 0, 0}
     float4* queue;           // [R*N*M]
     float2* post;            // [R*N] {NUM, tail id} after the direction phase
-    uint8_t* hint;           // [R*N] 1 = a downstream link admitted this link's head in the direction phase
     const int32_t* slot_link;   // [N] slot -> link id (nullptr = identity): the store's own locality order
     const int32_t* link_slot;   // [N] link id -> slot
     int pol_state, pol_static;  // L2 eviction policy (kPol*) of the records / summaries and of topology + statics
