@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 23
+#define TARL_ABI_VERSION 24
 
 /* return codes */
 #define TARL_OK 0
@@ -406,6 +406,38 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    const float* v, const float* grad_v,
                                    int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
                                    float* grads, void* stream);
+
+/* MPNNPolicyNet's per-edge MLPs (src/agents/mpnn_agent.py:30-50; their only use in the reference are the two
+ * commented-out bodies of update_edges, :220-231): with x[b,n] = [node_features[b,n,0:7] ‖ agent_features[agent_index
+ * [b,n], 0:9]] (:163-167),
+ *   TARL_EDGE_MLP       logit[b,e] = L3(relu(L2(relu(L1([x[b,src e] ‖ x[b,dst e] ‖ edge_attr[b,e]])))))   33 -> 64 -> 32 -> 1
+ *   TARL_EDGE_MLP_TEST  logit[b,e] = L2(relu(L1([x[b,src e] ‖ x[b,dst e]])))                              32 -> 16 -> 1
+ * tarl_edge_mlp_inputs assembles x ([B, N, 16] fp32, contiguous, 16-byte aligned) from the observation. weights: the
+ * module's parameters in Sequential order, row-major as nn.Linear stores them — {W1, b1, W2, b2, W3, b3} (6 pointers)
+ * or {W1, b1, W2, b2} (4). out / grad_out: element (b, e) at b*batch_stride + e*edge_stride. edge_attr: [B, E] with
+ * the given batch stride (0 = one row shared by all b); unused by TARL_EDGE_MLP_TEST.
+ * Forward: with tarl_edge_mlp_tc_available() != 0 and variant TARL_EDGE_MLP both hidden layers run on the tensor cores
+ * (tcgen05.mma kind::tf32, 3xTF32, activations in TMEM; csrc/edge_mlp_tc.cu; needs tc_scratch) unless
+ * use_tensor_cores == 0; otherwise on the fp32 pipe. Backward: parameter gradients only (the observation is a leaf), flat in Sequential.parameters()
+ * order — tarl_edge_mlp_param_count(variant) floats; partials: scratch of tarl_edge_mlp_partial_count() x that many
+ * floats; fixed summation order (deterministic). */
+#define TARL_EDGE_MLP 0
+#define TARL_EDGE_MLP_TEST 1
+int32_t tarl_edge_mlp_param_count(int32_t variant);
+int32_t tarl_edge_mlp_partial_count(void);
+int32_t tarl_edge_mlp_tc_available(void);
+int32_t tarl_edge_mlp_tc_scratch_floats(void);   /* tc_scratch of the forward call: that many floats, 16-byte aligned */
+int tarl_edge_mlp_inputs(const float* node_features, int64_t nf_batch_stride, int64_t nf_row_stride,
+                         const int64_t* agent_index, const float* agent_features, int32_t agent_rows, int32_t batch,
+                         int32_t n_nodes, float* x, int32_t* flags, void* stream);
+int tarl_edge_mlp_forward(int32_t variant, const int32_t* edge_src, const int32_t* edge_dst, int32_t n_edges,
+                          const float* x, int32_t batch, int32_t n_nodes, const float* edge_attr, int64_t ea_batch_stride,
+                          const float* const* weights, int32_t use_tensor_cores, float* tc_scratch, float* out,
+                          int64_t out_batch_stride, int64_t out_edge_stride, void* stream);
+int tarl_edge_mlp_backward(int32_t variant, const int32_t* edge_src, const int32_t* edge_dst, int32_t n_edges,
+                           const float* x, int32_t batch, int32_t n_nodes, const float* edge_attr, int64_t ea_batch_stride,
+                           const float* const* weights, const float* grad_out, int64_t go_batch_stride,
+                           int64_t go_edge_stride, float* partials, float* grads, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Population operations either side of the core step (csrc/agents.cu). Each works on either state layout.

@@ -188,8 +188,51 @@ def gen_value_train(out):
     np.savez_compressed(os.path.join(out, "mpnn_value_train.npz"), **blob)
 
 
+def gen_edge_mlp(out):
+    """MPNNPolicyNet.edge_mlp / edge_mlp_test evaluated by the UNMODIFIED reference modules on the formula of the two
+    commented-out bodies of update_edges (src/agents/mpnn_agent.py:220-231), with the x forward() assembles (:163-167):
+    outputs and parameter gradients, unbatched and batched (the reference batches by offsetting node ids: row b of the
+    batched result is the unbatched result of sample b)."""
+    mp = ref_loader.load("src.agents.mpnn_agent")
+    g = torch.Generator().manual_seed(44)
+    blob = {}
+    for tag, B in (("u", None), ("b", 3)):
+        N, E, A = 19, 301, 25                                  # E spans three 128-pair tiles with a ragged tail
+        ei, nf, ef, ai, tm, af = _small_net_inputs(g, N, E, A, B)
+        torch.manual_seed(9)
+        net = mp.MPNNPolicyNet(ei, N, torch.rand(E, generator=g) + 0.5, "cpu")
+        net.agent_features = af
+        with torch.no_grad():                                   # the reference's init is +-0.1 with zero biases: widen it
+            for p in list(net.edge_mlp.parameters()) + list(net.edge_mlp_test.parameters()):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() == 2 else 0.2))
+        rows = [None] if B is None else list(range(B))
+        outs = {"edge_mlp": [], "edge_mlp_test": []}
+        for b in rows:
+            sl = (lambda t: t) if b is None else (lambda t: t[b])
+            x = torch.cat((sl(nf), af[sl(ai)]), dim=-1)                                    # :181-184
+            x_i, x_j = x[ei[0]], x[ei[1]]                                                  # :228-229
+            outs["edge_mlp"].append(net.edge_mlp(torch.cat([x_i, x_j, sl(ef)], dim=1)).squeeze(-1))   # :230-231
+            outs["edge_mlp_test"].append(net.edge_mlp_test(torch.cat([x_i, x_j], dim=1)).squeeze(-1))  # :224-225 on x
+        for which, seq in (("edge_mlp", net.edge_mlp), ("edge_mlp_test", net.edge_mlp_test)):
+            o = outs[which][0] if B is None else torch.stack(outs[which])
+            w = torch.randn(o.shape, generator=g)
+            for p in seq.parameters():
+                p.grad = None
+            (o * w).sum().backward()
+            blob[f"{tag}.{which}.out"] = o.detach().numpy()
+            blob[f"{tag}.{which}.w_out"] = w.numpy()
+            for k, p in seq.named_parameters():
+                blob[f"{tag}.param.{which}.{k}"] = p.detach().numpy()
+                blob[f"{tag}.grad.{which}.{k}"] = p.grad.numpy()
+        blob.update({f"{tag}.{k}": t.numpy() for k, t in dict(edge_index=ei, node_features=nf, edge_features=ef,
+                                                             agent_index=ai, agent_features=af).items()})
+        print(f"edge mlp {tag}: logits[:3]={blob[f'{tag}.edge_mlp.out'].reshape(-1)[:3].tolist()}")
+    np.savez_compressed(os.path.join(out, "mpnn_edge_mlp.npz"), **blob)
+
+
 def main(out, only_new=False):
     if not only_new:
         gen_graph_distribution(out)
         gen_nets(out)
     gen_value_train(out)
+    gen_edge_mlp(out)

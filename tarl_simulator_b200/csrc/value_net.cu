@@ -487,7 +487,7 @@ constexpr int kPairsPerThread = tarl::kTilePairs / tarl::kTileThreads;      // 4
 // The gather of a pair's 9 agent features is what the L1 spends its time on in this walk: 9 scalar loads per warp, each
 // on 32 different 36-byte rows = 9 x 32 tag look-ups, against 7 + 2 for everything else a warp loads here. pack =
 // the agent table re-laid as 48-byte rows (k_value_pack_agents, once per call): three 128-bit loads per pair.
-constexpr int kPackDim = 12;
+constexpr int kPackDim = 12;   // floats per packed agent row (48 bytes)
 __global__ void __launch_bounds__(256) k_value_pack_agents(const float* __restrict__ af, int af_rows, float4* __restrict__ pack) {
     const int a = blockIdx.x * 256 + threadIdx.x;
     if (a >= af_rows) return;

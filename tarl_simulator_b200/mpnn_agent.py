@@ -65,11 +65,66 @@ class _PolicyEmbed(torch.autograd.Function):
         return gw.reshape(ctx.wshape), None, None, None, None
 
 
+class _EdgeMLP(torch.autograd.Function):
+    """logits [B, E] of MPNNPolicyNet.edge_mlp / edge_mlp_test on every edge (csrc/edge_mlp.cu, csrc/edge_mlp_tc.cu);
+    gradients with respect to the module's parameters (the observation is a leaf). x: [B, N, 16] assembled inputs."""
+
+    @staticmethod
+    def forward(ctx, variant, use_tc, x, ef, src32, dst32, *params):
+        B, N, _ = x.shape
+        E = src32.numel()
+        dev = x.device
+        ws = [p.detach().contiguous() for p in params]
+        ptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        out = torch.empty(B, E, dtype=torch.float32, device=dev)
+        ef_bs = 0 if (ef is None or B == 1) else ef.stride(0)
+        lib = _cabi.lib()
+        scratch = None
+        if use_tc and variant == 0 and lib.tarl_edge_mlp_tc_available():
+            scratch = torch.empty(lib.tarl_edge_mlp_tc_scratch_floats(), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_edge_mlp_forward(
+                variant, src32.data_ptr(), dst32.data_ptr(), E, x.data_ptr(), B, N,
+                ef.data_ptr() if ef is not None else None, ef_bs, ptrs, 1 if scratch is not None else 0,
+                scratch.data_ptr() if scratch is not None else None, out.data_ptr(), E, 1, _stream(dev))
+        _cabi.check(rc, "tarl_edge_mlp_forward")
+        ctx.variant, ctx.ef_bs, ctx.shapes = variant, ef_bs, [p.shape for p in params]
+        ctx.has_ef = ef is not None
+        ctx.save_for_backward(x, ef if ef is not None else x.new_empty(0), src32, dst32, *ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, ef, src32, dst32, *ws = ctx.saved_tensors
+        B, N, _ = x.shape
+        E = src32.numel()
+        dev = x.device
+        lib = _cabi.lib()
+        n = lib.tarl_edge_mlp_param_count(ctx.variant)
+        grads = torch.empty(n, dtype=torch.float32, device=dev)
+        partials = torch.empty(max(n * lib.tarl_edge_mlp_partial_count(), 1), dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * len(ws))(*[w.data_ptr() for w in ws])
+        g = grad_out.to(torch.float32)
+        with torch.cuda.device(dev):
+            rc = lib.tarl_edge_mlp_backward(
+                ctx.variant, src32.data_ptr(), dst32.data_ptr(), E, x.data_ptr(), B, N,
+                ef.data_ptr() if ctx.has_ef else None, ctx.ef_bs, ptrs, g.data_ptr(), g.stride(0) if B > 1 else 0,
+                g.stride(1) if E > 1 else 1, partials.data_ptr(), grads.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_edge_mlp_backward")
+        out, o = [], 0
+        for shp in ctx.shapes:
+            k = int(np.prod(shp))
+            out.append(grads[o:o + k].reshape(shp))
+            o += k
+        return (None, None, None, None, None, None, *out)
+
+
 class MPNNPolicyNet(MessagePassing, Agents):
     """Per-edge routing logits (src/agents/mpnn_agent.py:16-262). Active path: logits[e] =
-    nodes_embedding(ROAD_INDEX)[edge_index[1][e]] (:215-217); `edge_mlp` (33→64→32→1) and `edge_mlp_test`
-    (32→16→1) exist with the reference's initialisation so that state_dicts are interchangeable, but — as in the
-    reference at this commit — no forward path uses them."""
+    nodes_embedding(ROAD_INDEX)[edge_index[1][e]] (:215-217). `edge_mlp` (33→64→32→1) and `edge_mlp_test`
+    (32→16→1) carry the reference's names, shapes and initialisation (state_dicts are interchangeable); the reference's
+    only use of them are the two commented-out bodies of update_edges (:220-231) — `edge_logits()` evaluates those
+    bodies on the kernels of csrc/edge_mlp*.cu (forward of edge_mlp on the tensor cores), with autograd."""
 
     h = ObservationFeatureHelpers()
     reads_dynamic_features = False      # the active path only reads the (static) ROAD_INDEX column of node_features
@@ -138,6 +193,50 @@ class MPNNPolicyNet(MessagePassing, Agents):
         logits = _PolicyEmbed.apply(self.nodes_embedding.weight, nf, self._dst32, by_target, self._flags)
         if logits.size(0) != B_out:
             logits = logits.contiguous().expand(B_out, -1)
+        return logits if batched else logits.reshape(self.num_edges)
+
+    def edge_logits(self, node_features: torch.Tensor, edge_features: torch.Tensor, agent_index: torch.Tensor,
+                    which: str = "edge_mlp", tensor_cores: bool = True) -> torch.Tensor:
+        """The commented-out bodies of the reference's update_edges (src/agents/mpnn_agent.py:220-231) on x = [node_features
+        ‖ agent_features[agent_index]] (:163-167): which="edge_mlp": edge_mlp([x_i ‖ x_j ‖ edge_attr]) with x_i =
+        x[edge_index[0]], x_j = x[edge_index[1]]; which="edge_mlp_test": edge_mlp_test([x_i ‖ x_j]). Returns logits [E]
+        or [B, E] like forward(). tensor_cores=False keeps edge_mlp on the fp32 pipe (same results within 1e-5)."""
+        if which not in ("edge_mlp", "edge_mlp_test"):
+            raise ValueError("which must be 'edge_mlp' or 'edge_mlp_test'")
+        if not node_features.is_cuda:
+            raise RuntimeError("MPNNPolicyNet computes on CUDA devices only (no CPU fallback)")
+        batched = node_features.dim() == 3
+        nf = (node_features if batched else node_features.unsqueeze(0)).to(torch.float32)
+        if nf.stride(2) != 1:
+            nf = nf.contiguous()
+        B, N = nf.size(0), nf.size(1)
+        dev = nf.device
+        ai = (agent_index if batched else agent_index.unsqueeze(0)).to(torch.int64).contiguous()
+        af = self.agent_features.to(device=dev, dtype=torch.float32).contiguous()
+        ei = self.edge_index
+        if getattr(self, "_src32", None) is None or self._src32.device != dev or self._src32.numel() != ei.size(1):
+            self._src32 = ei[0].to(device=dev, dtype=torch.int32).contiguous()
+            self._dst32e = ei[1].to(device=dev, dtype=torch.int32).contiguous()
+        self._flags = torch.zeros(_cabi.FLAG_COUNT, dtype=torch.int32, device=dev)
+        x = torch.empty(B, N, 16, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_edge_mlp_inputs(nf.data_ptr(), nf.stride(0), nf.stride(1), ai.data_ptr(), af.data_ptr(),
+                                                  af.size(0), B, N, x.data_ptr(), self._flags.data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_edge_mlp_inputs")
+        ef = None
+        if which == "edge_mlp":
+            ef = (edge_features if batched else edge_features.unsqueeze(0)).to(torch.float32)
+            ef = ef.squeeze(-1) if ef.dim() == 3 else ef
+            if ef.stride(-1) != 1 or (B > 1 and ef.stride(0) not in (0, ef.size(1))):
+                ef = ef.contiguous()
+            seq, variant = self.edge_mlp, 0
+            params = (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias, seq[4].weight, seq[4].bias)
+        else:
+            seq, variant = self.edge_mlp_test, 1
+            params = (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
+        logits = _EdgeMLP.apply(variant, bool(tensor_cores), x, ef, self._src32, self._dst32e, *params)
+        self.last_edge_path = ("tcgen05" if (variant == 0 and tensor_cores and _cabi.lib().tarl_edge_mlp_tc_available())
+                               else "fp32")
         return logits if batched else logits.reshape(self.num_edges)
 
     def check_errors(self):

@@ -583,3 +583,84 @@ def test_sampling_kernel_own_uniform_stream():
     sigma = (p * (1 - p) / R).sqrt()
     assert bool(((freq - p).abs() <= 5 * sigma + 1e-3).all()), float(((freq - p).abs() / (sigma + 1e-6)).max())
     assert torch.allclose(lp1, d.log_prob(a1), rtol=1e-5, atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------- per-edge MLPs
+def _edge_mlp_net(d, tag, which):
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet
+    ei = torch.from_numpy(d[f"{tag}.edge_index"]).cuda()
+    nf = torch.from_numpy(d[f"{tag}.node_features"]).cuda()
+    net = MPNNPolicyNet(ei, nf.size(-2), None if nf.size(-2) > 4096 else torch.ones(ei.size(1), device="cuda"), "cuda")
+    net.agent_features = torch.from_numpy(d[f"{tag}.agent_features"]).cuda()
+    with torch.no_grad():
+        for k, p in getattr(net, which).named_parameters():
+            p.copy_(torch.from_numpy(d[f"{tag}.param.{which}.{k}"]))
+    return net, nf, torch.from_numpy(d[f"{tag}.edge_features"]).cuda(), torch.from_numpy(d[f"{tag}.agent_index"]).cuda()
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("tag", ["u", "b"])
+@pytest.mark.parametrize("which", ["edge_mlp", "edge_mlp_test"])
+def test_edge_mlp_matches_reference_modules(which, tag, tensor_cores, golden_dir):
+    """MPNNPolicyNet.edge_logits (csrc/edge_mlp.cu; edge_mlp's forward also on tcgen05, csrc/edge_mlp_tc.cu) against the
+    reference's own modules on the formula of the commented-out update_edges bodies: logits and every parameter
+    gradient within 1e-5 relative (atol stated)."""
+    d = np.load(os.path.join(golden_dir, "mpnn_edge_mlp.npz"))
+    net, nf, ef, ai = _edge_mlp_net(d, tag, which)
+    out = net.edge_logits(nf, ef, ai, which=which, tensor_cores=tensor_cores)
+    ref = torch.from_numpy(d[f"{tag}.{which}.out"])
+    assert out.shape == ref.shape
+    close(out, ref, rtol=1e-5, atol=2e-5)
+    (out * torch.from_numpy(d[f"{tag}.{which}.w_out"]).cuda()).sum().backward()
+    for k, p in getattr(net, which).named_parameters():
+        gref = torch.from_numpy(d[f"{tag}.grad.{which}.{k}"])
+        close(p.grad, gref, rtol=1e-5, atol=1e-5 * float(gref.abs().max()) + 1e-6)
+    if which == "edge_mlp" and tensor_cores:
+        from tarl_simulator_b200 import _cabi
+        assert net.last_edge_path == ("tcgen05" if _cabi.lib().tarl_edge_mlp_tc_available() else "fp32")
+    net.check_errors()
+
+
+@pytest.mark.parametrize("grid", [False, True])
+@pytest.mark.parametrize("B,N,E", [(1, 50, 1), (2, 300, 1000), (32, 2000, 9000), (3, 40, 127)])
+def test_edge_mlp_matches_port_on_seeded_inputs(B, N, E, grid):
+    """Both MLPs on random graphs / batches against oracle/mpnn_port.edge_mlp_logits evaluated in float64: tile tails, a
+    single edge, an edge_attr row shared by the batch (stride 0), fp32 pipe and tensor cores.
+    grid=False: random floats, LOGITS within 1e-5 relative. A ReLU net's parameter gradients are discontinuous where a
+    pre-activation crosses zero, and among 10^7 units some sit within fp32 rounding of it — no two summation orders agree
+    on those masks — so the GRADIENTS are checked on grid=True inputs: everything a multiple of 1/8 in a small range,
+    which makes every pre-activation exact in fp32 whatever the order (and exact under the 3xTF32 split), the masks
+    identical, and leaves only the rounding of the final sums over the pairs."""
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet
+    g = torch.Generator().manual_seed(B * 1000 + E + int(grid))
+    q = (lambda t, lo, hi: torch.randint(lo, hi + 1, t.shape, generator=g).float() / 8.0) if grid else None
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)])
+    nf = torch.rand(B, N, 7, generator=g) * 4
+    ai = torch.randint(0, 30, (B, N), generator=g)
+    af = torch.rand(30, 9, generator=g) * 2
+    ef = torch.rand(1, E, 1, generator=g)
+    if grid:
+        nf, af, ef = q(nf, 0, 16), q(af, 0, 8), q(ef, 0, 8)
+    ef = ef.expand(B, -1, -1)
+    net = MPNNPolicyNet(ei.cuda(), N, torch.ones(E, device="cuda"), "cuda")
+    net.agent_features = af.cuda()
+    with torch.no_grad():
+        for p in list(net.edge_mlp.parameters()) + list(net.edge_mlp_test.parameters()):
+            p.copy_((q(p, -4, 4) if grid else torch.randn(p.shape, generator=g) * 0.25).cuda())
+    sd = {k: v.detach().cpu().double() for k, v in net.state_dict().items() if k.startswith("edge_mlp")}
+    w = q(torch.empty(B, E), -8, 8) if grid else torch.randn(B, E, generator=g)
+    for which in ("edge_mlp", "edge_mlp_test"):
+        pd = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith(which + ".")}
+        ref = mpnn_port.edge_mlp_logits(pd, nf.double(), ef.double(), af.double(), ai, ei, which)
+        (ref * w.double()).sum().backward()
+        for tc in ((False, True) if which == "edge_mlp" else (False,)):
+            for p in getattr(net, which).parameters():
+                p.grad = None
+            out = net.edge_logits(nf.cuda(), ef.cuda(), ai.cuda(), which=which, tensor_cores=tc)
+            _within(out.detach().cpu(), ref.detach().float(), f"{which} tc={tc} logits")
+            if not grid:
+                continue
+            (out * w.cuda()).sum().backward()
+            for k, p in getattr(net, which).named_parameters():
+                _within(p.grad.cpu(), pd[f"{which}.{k}"].grad.float(), f"{which} tc={tc} grad {k}")
+    net.check_errors()

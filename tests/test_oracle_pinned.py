@@ -154,3 +154,21 @@ def test_nets_port(tag, golden_dir):
     assert torch.equal(lg.detach(), g(f"policy.{tag}.out"))
     (lg * g(f"policy.{tag}.w_out")).sum().backward()
     torch.testing.assert_close(emb.grad, g(f"policy.{tag}.grad_emb"), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["u", "b"])
+@pytest.mark.parametrize("which", ["edge_mlp", "edge_mlp_test"])
+def test_edge_mlp_port_matches_reference_modules(tag, which, golden_dir):
+    """oracle/mpnn_port.edge_mlp_logits against what the reference's own edge_mlp / edge_mlp_test modules return for
+    the formula of the commented-out update_edges bodies (tests/golden/mpnn_edge_mlp.npz), outputs and gradients."""
+    d = np.load(os.path.join(golden_dir, "mpnn_edge_mlp.npz"))
+    g = lambda k: torch.from_numpy(d[f"{tag}.{k}"])
+    p = {k[len(f"{tag}.param."):]: torch.from_numpy(d[k]).clone().requires_grad_(True)
+         for k in d.files if k.startswith(f"{tag}.param.{which}.")}
+    out = mpnn_port.edge_mlp_logits(p, g("node_features"), g("edge_features"), g("agent_features"), g("agent_index"),
+                                    g("edge_index"), which)
+    torch.testing.assert_close(out, g(f"{which}.out"), rtol=1e-6, atol=1e-6)
+    (out * g(f"{which}.w_out")).sum().backward()
+    for k, v in p.items():
+        gref = torch.from_numpy(d[f"{tag}.grad.{k}"])            # sums over ~1e3 pairs with cancellation: atol scales with the tensor
+        torch.testing.assert_close(v.grad, gref, rtol=1e-5, atol=1e-5 * max(1.0, float(gref.abs().max())))
