@@ -541,13 +541,15 @@ def mpnn_bench(args, g, dev, world, rank, peak):
     value.eval()
     del policy, value, nf, ai, action
     torch.cuda.empty_cache()
+    emlp = edge_mlp_bench(g, dev, timed, world)
+    torch.cuda.empty_cache()
     vmlp = value_mlp_bench(dev, timed, world, peak)
     # algorithmic bytes per edge: policy 28 B + GraphDistribution 24 B = 52 B/edge (+4 B/node)
     pol_bytes = B * (52 * E_full + 4 * N_tot)
     val_bytes = B * (2 * (12 * E_full) + 2 * 68 * N_tot)          # fwd + bwd: 12 B/edge + 68 B/node each
     train_bytes = B * (36 * E_full + 92 * N_tot)                  # train mode: a keep word and a message per (row, edge)
     return {"metric": "MPNN fwd+bwd edges/s", "unit": "edges/s", "batch_rows": B, "edges_full_graph": E_full,
-            "nodes_full_graph": N_tot, "iters": iters,
+            "nodes_full_graph": N_tot, "iters": iters, "edge_mlp": emlp,
             "policy_distribution": {"value": round(world * B * E_full / (pol_ms / 1e3), 1), "ms_per_iter": round(pol_ms, 4),
                                     "what": "MPNNPolicyNet.forward -> GraphDistribution.log_prob + entropy -> backward (7 kernels)",
                                     "roofline": {"bound": "hbm", "algorithmic_bytes": int(pol_bytes),
@@ -572,6 +574,61 @@ def mpnn_bench(args, g, dev, world, rank, peak):
                                              "edge_grad_dropout, finish): the per-node projection does not factor "
                                              "through a per-edge mask, every (row, edge) gathers its 16 inputs' products"},
             "value_mlp": vmlp}
+
+
+def edge_mlp_bench(g, dev, timed, world):
+    """MPNNPolicyNet.edge_mlp (33 -> 64 -> 32 -> 1 per edge; dormant in the reference, src/agents/mpnn_agent.py:38-44,
+    227-231) on the full graph of the workload at 8 rows: forward on tcgen05 (csrc/edge_mlp_tc.cu) beside the fp32-pipe
+    forward, and forward + backward (parameter gradients, fp32 pipe). Tensor-bound: 8.5 kflop per pair on 132 gathered
+    bytes; `tensor` relates the TF32 flop the MMAs issue (3xTF32, K padded to 40) to half the measured dense bf16 peak."""
+    import torch
+    from tarl_simulator_b200.mpnn_agent import MPNNPolicyNet
+    B = 8
+    ei = g.edge_index
+    E, N_tot = ei.size(1), g.x.size(0)
+    Nmax = (g.x.size(1) - 7) // 3
+    gen = torch.Generator(device=dev).manual_seed(17)
+    nf = g.x[:, 3 * Nmax:].unsqueeze(0).repeat(B, 1, 1).contiguous()
+    net = MPNNPolicyNet(ei, N_tot, None, str(dev)) if N_tot > 4096 else MPNNPolicyNet(ei, N_tot, torch.ones(E, device=dev), str(dev))
+    net.agent_features = torch.rand(1024, 9, device=dev, generator=gen)
+    ai = torch.randint(0, 1024, (B, N_tot), device=dev, generator=gen)
+    ef = g.edge_attr.reshape(1, E, 1).expand(B, -1, -1)
+    w = torch.randn(B, E, device=dev, generator=gen)
+    with torch.no_grad():
+        a = net.edge_logits(nf, ef, ai, tensor_cores=True)
+        path = net.last_edge_path
+        b = net.edge_logits(nf, ef, ai, tensor_cores=False)
+        rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+        tc_ms = timed(lambda: net.edge_logits(nf, ef, ai, tensor_cores=True), 5)
+        fp_ms = timed(lambda: net.edge_logits(nf, ef, ai, tensor_cores=False), 3)
+
+    def train():
+        for p_ in net.edge_mlp.parameters():
+            p_.grad = None
+        (net.edge_logits(nf, ef, ai, tensor_cores=True) * w).sum().backward()
+
+    tr_ms = timed(train, 3)
+    pairs = B * E
+    useful = 2 * (64 * 34 + 32 * 64 + 32) * pairs
+    issued = 2 * 3 * (64 * 40 + 32 * 64) * pairs
+    tf32_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf32_peak = float(json.load(f)["bf16_tflops"]) / 2
+    except Exception:
+        pass
+    return {"metric": "edge MLP (row, edge) pairs/s", "rows": B, "edges": E, "forward_path": path,
+            "tcgen05": {"value": round(world * pairs / (tc_ms / 1e3), 1), "ms": round(tc_ms, 4),
+                        "what": "x assembly + tarl_edge_mlp_forward: gather -> TMEM -> tcgen05.mma kind::tf32 (3xTF32) for both "
+                                "hidden layers, 32 -> 1 in registers"},
+            "fp32_pipe": {"value": round(world * pairs / (fp_ms / 1e3), 1), "ms": round(fp_ms, 4)},
+            "forward_backward": {"ms": round(tr_ms, 4), "what": "tcgen05 forward + k_edge_mlp_bwd (recompute, per-tile outer-"
+                                 "product sums on the fp32 pipe, deterministic finish)"},
+            "max_rel_diff_tc_vs_fp32": rel,
+            "tensor": {"bound": "tensor", "useful_tflops": round(useful / (tc_ms / 1e3) / 1e12, 2),
+                       "issued_tf32_tflops": round(issued / (tc_ms / 1e3) / 1e12, 2), "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": round(issued / (tc_ms / 1e3) / 1e12 / tf32_peak, 4) if tf32_peak else None,
+                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"}}
 
 
 def value_mlp_bench(dev, timed, world, peak):

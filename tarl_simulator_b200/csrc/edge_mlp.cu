@@ -190,18 +190,31 @@ struct BwdSmem {
 template <int ROWS, int COLS4, int kItems>
 __device__ __forceinline__ void outer_sum(const float* __restrict__ L, int pL, const float* __restrict__ R, int pR,
                                           int live, float4 (&acc)[kItems]) {
+    // the pair loop is the OUTER one: a thread's kItems accumulators are independent chains, and the shared-memory reads of
+    // one pair are in flight together (item-outer order left one dependent FMA chain per warp: 44 us per tile)
+    int offL[kItems], offR[kItems];
+    bool on[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
         const int item = threadIdx.x + k * kTile;
-        if (item >= ROWS * COLS4) continue;
-        const int r = item / COLS4, c4 = item - r * COLS4;
-        float4 s = acc[k];
-        for (int p = 0; p < live; ++p) {
-            const float l = L[p * pL + r];
-            const float4 v = *reinterpret_cast<const float4*>(R + p * pR + 4 * c4);
-            s.x += l * v.x; s.y += l * v.y; s.z += l * v.z; s.w += l * v.w;
+        on[k] = item < ROWS * COLS4;
+        const int r = on[k] ? item / COLS4 : 0, c4 = on[k] ? item - r * COLS4 : 0;
+        offL[k] = r; offR[k] = 4 * c4;
+    }
+#pragma unroll 2
+    for (int p = 0; p < live; ++p) {
+        float l[kItems];
+        float4 v[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            l[k] = L[p * pL + offL[k]];
+            v[k] = *reinterpret_cast<const float4*>(R + p * pR + offR[k]);
         }
-        acc[k] = s;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            if (!on[k]) continue;
+            acc[k].x += l[k] * v[k].x; acc[k].y += l[k] * v[k].y; acc[k].z += l[k] * v[k].z; acc[k].w += l[k] * v[k].w;
+        }
     }
 }
 
@@ -245,6 +258,8 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
             sG[p] = g;
 #pragma unroll
             for (int c = 0; c < S::kInP; ++c) sA[p * M::pA + c] = a[c];
+            // a spare padding column holds the constant 1: column IN of the W1 sums is then the bias gradient
+            if (S::kInP > IN) sA[p * M::pA + IN] = 1.0f;
             if (H2 > 0) {
                 float z2[H2 > 0 ? H2 : 1], g2[H2 > 0 ? H2 : 1];
 #pragma unroll
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
         outer_sum<H1, S::kInP / 4, kW1Items>(sG1, M::pH1, sA, M::pA, live, accW1);
         if (H2 > 0) outer_sum<H2, H1 / 4, kW2Items>(sG2, M::pH2, sH1, M::pH1, live, accW2);
         const int t = threadIdx.x;
-        if (t < H1) {
+        if (S::kInP == IN && t < H1) {                            // (otherwise the spare column of A carries it)
             float s = 0.0f;
             for (int q = 0; q < live; ++q) s += sG1[q * M::pH1 + t];
             accB1 += s;
@@ -317,8 +332,10 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
         const int r = item / (S::kInP / 4), c = 4 * (item - r * (S::kInP / 4));
         const float v[4] = {accW1[k].x, accW1[k].y, accW1[k].z, accW1[k].w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
             if (c + q < IN) out[S::oW1 + r * IN + c + q] = v[q];
+            else if (c + q == IN) out[S::oB1 + r] = v[q];
+        }
     }
     if (H2 > 0) {
 #pragma unroll
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
         }
     }
     const int t = threadIdx.x;
-    if (t < H1) out[S::oB1 + t] = accB1;
+    if (S::kInP == IN && t < H1) out[S::oB1 + t] = accB1;
     if (H2 > 0 && t < H2) out[S::oB2 + t] = accB2;
     if (t < S::kLast) out[S::oWo + t] = accWo;
     if (t == 0) out[S::oBo] = accBo;
