@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 24
+#define TARL_ABI_VERSION 25
 
 /* return codes */
 #define TARL_OK 0
@@ -498,11 +498,16 @@ typedef struct tarl_agent_index {
  * compacted per replica and the admission runs over that list only (identical results; the listed origins are a few
  * per cent of all (replica, origin) pairs and each carries a chain of dependent gathers).
  * num_out / occupancy: both NULL, or (link store only) the occupancy observation tarl_agents_withdraw left behind in
- * this very step — num_out [R, n_nodes], occupancy [R] — which the roads that admit agents patch in place. */
+ * this very step — num_out [R, n_nodes], occupancy [R] — which the roads that admit agents patch in place.
+ * road_origin: NULL, or [n_links] int32 for networks in which every road can be selected by ONE origin only
+ * (road_origin[n] = index into index->origins of that origin, -1 = none; config_network's graphs: a road leaves one
+ * intersection, whose SRC node alone has an edge into it). With it (and inserted + index->dep_sorted) the two phases
+ * run as ONE kernel without the per-road lists — identical results; an origin whose SELECTED_ROAD names another
+ * origin's road while it has a ready agent raises TARL_ERR_INSERT_TARGET instead of being served. */
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
                        int32_t* flags, int32_t* worklist, int32_t* work_count, float* num_out, int32_t* occupancy,
-                       void* stream);
+                       const int32_t* road_origin, void* stream);
 
 /* Replaces Agents.withdraw_agent_from_network (src/agents/base.py:334-403): per link the maximal prefix of queue
  * slots k < NUM whose exit time <= t and whose agent's DESTINATION node is adjacent to the link — adjacency = CSR of

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 24       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 25       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -147,7 +147,7 @@ SIGNATURES = {
     "tarl_edge_mlp_inputs": (C.c_int, [_P, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "tarl_edge_mlp_forward": (C.c_int, [_I32, _P, _P, _I32, _P, _I32, _I32, _P, _I64, _P, _I32, _P, _P, _I64, _I64, _P]),
     "tarl_edge_mlp_backward": (C.c_int, [_I32, _P, _P, _I32, _P, _I32, _I32, _P, _I64, _P, _P, _I64, _I64, _P, _P, _P]),
-    "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "tarl_agents_insert": (C.c_int, [_AST, _ATB, _AIX, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_withdraw": (C.c_int, [_AST, _ATB, _CSR1, _F, _P, _P, _P, _P, _P, _P]),
     "tarl_agents_choice": (C.c_int, [_AST, _CSR1, _P, _I32, _P, C.c_uint64, C.c_uint32, _P]),
     "tarl_agents_apply_action": (C.c_int, [_AST, _P, _P, _I32, _ROWS, _I32, _P]),

@@ -212,7 +212,7 @@ class Agents(AgentFeatureHelpers):
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_agents_insert(C.byref(st), C.byref(tab), idx.ref(), float(self.time),
                                                 head.data_ptr(), nxt.data_ptr(), cur.data_ptr(), None, None,
-                                                flags.data_ptr(), None, None, None, None, _stream(dev))
+                                                flags.data_ptr(), None, None, None, None, None, _stream(dev))
         _cabi.check(rc, "tarl_agents_insert")
         return graph.x
 

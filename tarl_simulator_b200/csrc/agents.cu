@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(kThreads) k_insert_offer(Acc acc, tarl_agent_i
 
 // What the origin i0 of replica r does in the admit phase: if it ended up at the HEAD of its road's list it serves the
 // road. (A thread per road would launch N threads per replica to find the few roads with a list.)
-template <class Acc>
+// kDirect: the origin serves its road on its own — no list was built (k_insert_direct: networks in which a road can be
+// selected by one origin only), the "list" is the origin itself.
+template <bool kDirect, class Acc>
 __device__ __forceinline__ void insert_admit_one(const Acc& acc, const tarl_agent_index& ai, const AgentTable& at, float t,
                                                  int32_t* __restrict__ head, const int32_t* __restrict__ next,
                                                  int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
@@ -161,14 +163,14 @@ __device__ __forceinline__ void insert_admit_one(const Acc& acc, const tarl_agen
                                                  float* __restrict__ num_out, int32_t* __restrict__ occupancy,
                                                  int n_nodes, int r, int i0) {
     if (i0 >= ai.n_origins) return;
-    if (next[(size_t)r * ai.n_origins + i0] == -2) return;                        // not listed this step
+    if (!kDirect && next[(size_t)r * ai.n_origins + i0] == -2) return;            // not listed this step
     const long long road = (long long)acc.sel_of(r, ai.origins[i0]);
     if (road < 0 || road >= acc.N) return;
     const int n = (int)road;
     const size_t L = (size_t)r * acc.N + n;
-    const int h = head[L];
+    const int h = kDirect ? i0 : head[L];
     if (h != i0) return;
-    head[L] = -1;                                                                // ready for the next call
+    if (!kDirect) head[L] = -1;                                                  // ready for the next call
     typename Acc::Link l = acc.open(r, n);
     const long long cap = (long long)((l.maxn - 3.0f) - l.num);                  // base.py:262-267
     if (cap <= 0) return;
@@ -182,7 +184,7 @@ __device__ __forceinline__ void insert_admit_one(const Acc& acc, const tarl_agen
     int admitted = 0;
     while (admitted < cap && q0 + admitted < acc.Nmax) {
         int best_a = INT32_MAX, best_i = -1;
-        for (int i = h; i >= 0; i = nx[i]) {
+        for (int i = h; i >= 0; i = kDirect ? -1 : nx[i]) {
             // Nobody (left) waiting at this origin — departed by now = inserted so far, see insert_offer_one: the scan
             // below would walk the rest of the origin's agents, two dependent loads per four of them, to find nothing
             // (after the one agent an origin typically inserts in a step that walk was half of the thread's chain)
@@ -242,14 +244,48 @@ __global__ void __launch_bounds__(kThreads) k_insert_admit(Acc acc, tarl_agent_i
                                                            int n_nodes) {
     const int r = blockIdx.y;
     if (work == nullptr) {
-        insert_admit_one(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy, n_nodes, r,
-                         (int)(blockIdx.x * kThreads + threadIdx.x));
+        insert_admit_one<false>(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy,
+                                n_nodes, r, (int)(blockIdx.x * kThreads + threadIdx.x));
         return;
     }
     const int count = work_count[r];
     for (int w = blockIdx.x * kThreads + threadIdx.x; w < count; w += gridDim.x * kThreads)
-        insert_admit_one(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy, n_nodes, r,
-                         work[(size_t)r * ai.n_origins + w]);
+        insert_admit_one<false>(acc, ai, at, t, head, next, cursor, counters, inserted, departed, num_out, occupancy,
+                                n_nodes, r, work[(size_t)r * ai.n_origins + w]);
+}
+
+// Offer and admit phase in ONE pass, for networks in which every road can be selected by a single origin only
+// (road_origin[n] = that origin's index, -1 = none: config_network's graphs, where a road leaves one intersection and
+// that intersection's SRC node is the only node with an edge into it). No list, no second kernel, no grid-wide
+// dependency between the two: one thread per (replica, origin); origins nobody waits at return after two loads, the
+// others insert straight away. A SELECTED_ROAD that names a road of another origin is reported (sticky error flag)
+// instead of being served: two threads could otherwise append to one queue.
+template <class Acc>
+__global__ void __launch_bounds__(kThreads) k_insert_direct(Acc acc, tarl_agent_index ai, AgentTable at, float t,
+                                                            const int32_t* __restrict__ road_origin,
+                                                            int32_t* __restrict__ cursor, int32_t* __restrict__ counters,
+                                                            int32_t* __restrict__ inserted,
+                                                            const int32_t* __restrict__ departed, int32_t* __restrict__ flags,
+                                                            float* __restrict__ num_out, int32_t* __restrict__ occupancy,
+                                                            int n_nodes) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= ai.n_origins) return;
+    const int o = ai.origins[i];
+    const size_t ri = (size_t)r * ai.n_origins + i;
+    const int n_dep = departed != nullptr ? departed[i] : departed_by(ai, o, t);
+    if (n_dep <= inserted[ri]) return;                                            // nobody is waiting here
+    const long long road = (long long)acc.sel_of(r, o);                          // base.py:259
+    cursor[ri] = ai.org_ptr[o];
+    if (road < 0 || road >= acc.N || road_origin[road] != i) {
+        // not a road, or not this origin's road: harmless unless one of this origin's agents is ready (see insert_offer_one)
+        bool any = false;
+        for (int k = ai.org_ptr[o]; k < ai.org_ptr[o + 1] && !any; ++k) any = agent_ready(at, r, ai.org_agent[k], t);
+        if (any) atomicOr(&flags[TARL_FLAG_ERROR], TARL_ERR_INSERT_TARGET);
+        return;
+    }
+    insert_admit_one<true>(acc, ai, at, t, nullptr, nullptr, cursor, counters, inserted, departed, num_out, occupancy,
+                           n_nodes, r, i);
 }
 
 
@@ -450,7 +486,7 @@ extern "C" {
 int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* agents, const tarl_agent_index* index,
                        float t, int32_t* head, int32_t* next, int32_t* cursor, int32_t* counters, int32_t* inserted,
                        int32_t* flags, int32_t* worklist, int32_t* work_count, float* num_out, int32_t* occupancy,
-                       void* stream) {
+                       const int32_t* road_origin, void* stream) {
     RowAcc row; StoreAcc sto; bool is_store; int R; AgentTable at;
     int rc = check_state(state, &row, &sto, &is_store, &R);
     if (rc != TARL_OK) return rc;
@@ -471,6 +507,15 @@ int tarl_agents_insert(const tarl_agent_state* state, const tarl_agent_table* ag
     if (work_count != nullptr && inserted != nullptr && index->dep_sorted != nullptr && R > 1) {
         dep_scratch = work_count + R;
         k_insert_departed<<<blocks_for(index->n_origins), kThreads, 0, cs>>>(*index, t, dep_scratch);
+    }
+    if (road_origin != nullptr && inserted != nullptr && index->dep_sorted != nullptr) {
+        if (is_store)
+            k_insert_direct<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, road_origin, cursor, counters, inserted, dep_scratch,
+                                                     flags, num_out, occupancy, sto.n_nodes);
+        else
+            k_insert_direct<<<g1, kThreads, 0, cs>>>(row, *index, at, t, road_origin, cursor, counters, inserted, dep_scratch,
+                                                     flags, nullptr, nullptr, 0);
+        return launch_status();
     }
     if (is_store) {
         k_insert_offer<<<g1, kThreads, 0, cs>>>(sto, *index, at, t, head, next, cursor, flags, inserted, worklist, work_count, dep_scratch);

@@ -519,7 +519,8 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                     draw(t)
                     applied = sink is not None and sink.applied
                     env.occupancy = occ[t]
-                    env.step(None if applied else action[t], compact_out=frame(t + 1), lean=True)
+                    env.step(None if applied else action[t], compact_out=frame(t + 1), lean=True,
+                             direct_insert=applied and R <= 256)
                     if env.time > EPISODE_END and t + 1 < n:  # auto-reset (see collect): not part of a captured rollout
                         adapter.reset()
                         adapter.dynamic(out=frame(t + 1))
@@ -553,7 +554,7 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                     raise RuntimeError("the overlapped rollout needs the sampling kernel to write SELECTED_ROAD itself")
                 main.wait_event(drawn)
                 env.occupancy = occ[t]
-                env.step(None, compact_out=frame(t + 1), lean=True, after_core=mark_core(t))
+                env.step(None, compact_out=frame(t + 1), lean=True, after_core=mark_core(t), direct_insert=R <= 256)
                 if env.time > EPISODE_END and t + 1 < n:
                     adapter.reset()
                     adapter.dynamic(out=frame(t + 1))

@@ -104,7 +104,8 @@ def test_batched_env_matches_reference(name, tmp_path, cluster):
     for s in range(len(d["t"])):
         u = torch.from_numpy(d["u_core"][s]).cuda().repeat(R, 1)
         a = torch.from_numpy(d["action"][s]).cuda().repeat(R, 1)
-        out = env.step(a, noise=u, observe=True)
+        # (cluster=False also takes the one-kernel insertion: every SRC node's SELECTED_ROAD comes from the action)
+        out = env.step(a, noise=u, observe=True, direct_insert=not cluster)
         x = env.export_x().cpu()
         for r in range(R):
             assert torch.equal(x[r], torch.from_numpy(d["x"][s])), f"replica {r}: x differs after step {s}"
@@ -459,3 +460,39 @@ def test_fused_step_withdraw_observe_equals_the_separate_passes(inject_noise):
         assert torch.equal(frame, out["node_features"][..., 1]), s
     assert int(a.counters[:, 1].min()) > 10                        # withdrawals did happen in every replica
     a.check_errors(); b.check_errors()
+
+
+def test_direct_insertion_equals_the_list_insertion(monkeypatch):
+    """tarl_agents_insert with road_origin (offer + admit as ONE kernel, for networks in which a road can be selected by
+    one origin only) against the two-kernel form with per-road lists on a twin environment: whole state, agent table,
+    counters and occupancy after every one of 200 steps of short trips on a 6 x 6 grid (origins that insert several
+    agents in one step, full roads that admit only some of them). A SELECTED_ROAD naming another origin's road raises."""
+    from tarl_simulator_b200 import synthetic
+    from tarl_simulator_b200.reinforcement_learning import BatchedSimulatorEnv
+    dev = torch.device("cuda")
+    frm, to, n_nodes = synthetic.grid_links(6, device=dev)
+    g, Nmax = synthetic.build_graph(frm, to, n_nodes)
+    af = synthetic.population(g, 900, 21540, 60, seed=5)          # 15 agents per second over 36 origins
+    R = 2
+    a = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=3)
+    monkeypatch.setenv("TARL_NO_DIRECT_INSERT", "1")
+    b = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=3)
+    monkeypatch.delenv("TARL_NO_DIRECT_INSERT")
+    assert a._road_origin is not None and b._road_origin is None
+    a.reset(); b.reset()
+    for s in range(200):
+        a.choice(seed=50 + s); b.choice(seed=50 + s)
+        oa = a.step(None, observe=False, direct_insert=True); ob = b.step(None, observe=False, direct_insert=True)
+        assert torch.equal(a.export_x(), b.export_x()), s
+        assert torch.equal(a.agent_features, b.agent_features), s
+        assert torch.equal(a.counters, b.counters) and torch.equal(oa["reward"], ob["reward"]), s
+    assert int(a.counters[:, 0].min()) > 500                      # insertions did happen
+    a.check_errors(); b.check_errors()
+    # every SRC node selects road 0: all but one origin name somebody else's road while they have ready agents
+    c = BatchedSimulatorEnv(g, Nmax, synthetic.population(g, 900, 21540, 1, seed=6), replicas=1, seed=3)
+    c.reset()
+    c.src_sel.zero_()
+    c.set_time(21541.0)
+    c.insert(direct=True)
+    with pytest.raises(RuntimeError):
+        c.check_errors()
