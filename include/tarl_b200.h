@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 25
+#define TARL_ABI_VERSION 26
 
 /* return codes */
 #define TARL_OK 0
@@ -368,8 +368,20 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
                            int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                            int32_t agent_rows, const float* msg_weight, const float* msg_bias, const float* node_weight,
                            int32_t batch, int32_t n_nodes, const float* proj, const float* mean, const float* v,
-                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, float* gm,
+                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, const float* head_g,
+                           const float* head_w, float* gm,
                            float* partials, float* grads, void* stream);
+
+/* The node part of MPNNValueNet's head (src/agents/mpnn_agent.py:359-361: final_mlp over [v ‖ time_net(t)]):
+ * out[b] = sum_n v[n, b] * head_weight[n] on the node-major v the propagate returns, fixed summation order; partials:
+ * tarl_value_head_partial_count(n_nodes) * batch floats. Its backward never materialises grad_v: both backward entry
+ * points take head_g [B] (= d loss / d out) and head_w [N] in place of grad_v (which may then be NULL) and use
+ * grad_v[b, n] = head_g[b] * head_w[n]; tarl_value_head_weight_grad gives d head_weight[n] = sum_b head_g[b] * v[n, b]. */
+int32_t tarl_value_head_partial_count(int32_t n_nodes);
+int tarl_value_head_forward(const float* v, int32_t batch, int32_t n_nodes, const float* head_weight, float* partials,
+                            float* out, void* stream);
+int tarl_value_head_weight_grad(const float* v, int32_t batch, int32_t n_nodes, const float* grad_out, float* grad_weight,
+                                void* stream);
 
 /* The same propagate in TRAIN mode: nn.Dropout(p) on the [B*E, 17] message input (src/agents/mpnn_agent.py:278,
  * 385-386; ATen computes x * (mask / (1 - p))). Every (row, edge) pair has a 17-bit keep word (bit k = input k
@@ -404,7 +416,8 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
                                    const uint32_t* keep_words, float* agent_pack, float* msg, const float* mean,
                                    const float* v, const float* grad_v,
-                                   int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
+                                   int64_t gv_batch_stride, int64_t gv_node_stride, const float* head_g,
+                                   const float* head_w, float* gm, float* partials,
                                    float* grads, void* stream);
 
 /* MPNNPolicyNet's per-edge MLPs (src/agents/mpnn_agent.py:30-50; their only use in the reference are the two

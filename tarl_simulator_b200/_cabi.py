@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 25       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 26       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -134,12 +134,15 @@ SIGNATURES = {
     "tarl_value_mp_forward": (C.c_int, [_CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P,
                                         _P, _P, _P, _P]),
     "tarl_value_mp_backward": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _I32, _I32, _P,
-                                         _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
+                                         _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "tarl_value_head_partial_count": (_I32, [_I32]),
+    "tarl_value_head_forward": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P]),
+    "tarl_value_head_weight_grad": (C.c_int, [_P, _I32, _I32, _P, _P, _P]),
     "tarl_value_mp_dropout_bits": (C.c_int, [C.c_uint64, _F, _I32, _I32, _P, _P]),
     "tarl_value_mp_forward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _P, _P, _P, _I32,
                                                 _I32, _P, _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tarl_value_mp_backward_dropout": (C.c_int, [_CSR1, _CSR1, _P, _I64, _I64, _P, _I64, _P, _P, _I32, _P, _I32, _I32, _P,
-                                                 _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P]),
+                                                 _I64, C.c_uint64, _F, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "tarl_edge_mlp_param_count": (_I32, [_I32]),
     "tarl_edge_mlp_partial_count": (_I32, []),
     "tarl_edge_mlp_tc_available": (_I32, []),

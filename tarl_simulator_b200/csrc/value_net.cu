@@ -229,17 +229,20 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_node_grad(tarl_csr
                                                                         const float* __restrict__ mean,
                                                                         const float* __restrict__ v,
                                                                         const float* __restrict__ gv, int64_t gv_sb,
-                                                                        int64_t gv_sn, float* __restrict__ gm,
+                                                                        int64_t gv_sn, const float* __restrict__ head_g,
+                                                                        const float* __restrict__ head_w,
+                                                                        float* __restrict__ gm,
                                                                         float* __restrict__ partials) {
     __shared__ float sm[tarl::kTileSmem];
     const tarl::Tile t = tarl::tile_here(B, Bp);
     float vals[2] = {0.0f, 0.0f};
     const float a0 = a[0];
-    // grad_v normally arrives row-major [B, N] (autograd of the dense head): staged with the node innermost
+    // grad_v normally arrives row-major [B, N] (autograd of a dense head): staged with the node innermost. With the
+    // value head applied by tarl_value_head_forward it is the rank-1 product head_g[b] * head_w[n] and never exists.
     tarl::tile_walk_nodes(t, [&](int r, int j) {
         const int n = t.n0 + j;
         if (n >= N || r >= t.nrows) return;
-        sm[tarl::tile_slot(t, r, j)] = gv[(t.b0 + r) * gv_sb + n * gv_sn];
+        sm[tarl::tile_slot(t, r, j)] = head_g != nullptr ? head_g[t.b0 + r] * head_w[n] : gv[(t.b0 + r) * gv_sb + n * gv_sn];
     });
     __syncthreads();
     tarl::tile_walk_rows(t, [&](int r, int j) {
@@ -343,6 +346,55 @@ __global__ void __launch_bounds__(tarl::kTileThreads) k_value_edge_grad(tarl_csr
         }
     });
     block_store<18>(vals, partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kGrads);
+}
+
+// ---- the value head: out[b] = sum_n v[n, b] * w[n] (the node part of final_mlp, src/agents/mpnn_agent.py:359-361) -------
+// v is node-major (element (b, n) at n*B + b). A CTA sums a block of kHeadNodes nodes: thread = (row b, node group), the
+// rows of one node on consecutive lanes (coalesced); per-CTA partial rows, then a fixed-order sum over the CTAs.
+constexpr int kHeadNodes = 2048;
+__global__ void __launch_bounds__(kThreads) k_value_head(const float* __restrict__ v, int B, int N,
+                                                         const float* __restrict__ w, float* __restrict__ partials) {
+    __shared__ float sm[kThreads];
+    const int n0 = blockIdx.x * kHeadNodes, n1 = min(n0 + kHeadNodes, N);
+    for (int b0 = 0; b0 < B; b0 += kThreads) {                    // (one pass for B <= 256)
+        const int rows = min(B - b0, kThreads);
+        int Bq = 1;
+        while (Bq < rows) Bq <<= 1;                               // rows of this pass rounded up to a power of two
+        const int groups = kThreads / Bq;                         // node groups working side by side
+        const int r = threadIdx.x & (Bq - 1), grp = threadIdx.x / Bq;
+        float acc = 0.0f;
+        if (r < rows) {
+            for (int n = n0 + grp; n < n1; n += groups) acc += v[(int64_t)n * B + b0 + r] * w[n];
+        }
+        sm[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < rows) {
+            float s = 0.0f;
+            for (int gI = 0; gI < groups; ++gI) s += sm[gI * Bq + threadIdx.x];
+            partials[(size_t)blockIdx.x * B + b0 + threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_value_head_finish(const float* __restrict__ partials, int n_parts, int B,
+                                                                float* __restrict__ out) {
+    const int b = blockIdx.x * kThreads + threadIdx.x;
+    if (b >= B) return;
+    float s = 0.0f;
+    for (int i = 0; i < n_parts; ++i) s += partials[(size_t)i * B + b];
+    out[b] = s;
+}
+// d w[n] = sum_b g[b] * v[n, b]: a warp per node at a time, rows on the lanes, shuffle tree (fixed order)
+__global__ void __launch_bounds__(kThreads) k_value_head_wgrad(const float* __restrict__ v, int B, int N,
+                                                               const float* __restrict__ g, float* __restrict__ gw) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (kThreads / 32);
+    for (int n = warp; n < N; n += n_warps) {
+        float acc = 0.0f;
+        for (int b = lane; b < B; b += 32) acc += g[b] * v[(int64_t)n * B + b];
+        acc = warp_sum(acc);
+        if (lane == 0) gw[n] = acc;
+    }
 }
 
 // grads[j] = sum over all blocks of partials[.., j]: one CTA per j, strided accumulation then a fixed tree
@@ -487,7 +539,6 @@ constexpr int kPairsPerThread = tarl::kTilePairs / tarl::kTileThreads;      // 4
 // The gather of a pair's 9 agent features is what the L1 spends its time on in this walk: 9 scalar loads per warp, each
 // on 32 different 36-byte rows = 9 x 32 tag look-ups, against 7 + 2 for everything else a warp loads here. pack =
 // the agent table re-laid as 48-byte rows (k_value_pack_agents, once per call): three 128-bit loads per pair.
-constexpr int kPackDim = 12;   // floats per packed agent row (48 bytes)
 __global__ void __launch_bounds__(256) k_value_pack_agents(const float* __restrict__ af, int af_rows, float4* __restrict__ pack) {
     const int a = blockIdx.x * 256 + threadIdx.x;
     if (a >= af_rows) return;
@@ -842,8 +893,8 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
                            int64_t ef_batch_stride, const int64_t* agent_index, const float* agent_features,
                            int32_t agent_rows, const float* msg_weight, const float* msg_bias, const float* node_weight,
                            int32_t batch, int32_t n_nodes, const float* proj, const float* mean, const float* v,
-                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, float* gm,
-                           float* partials, float* grads, void* stream) {
+                           const float* grad_v, int64_t gv_batch_stride, int64_t gv_node_stride, const float* head_g,
+                           const float* head_w, float* gm, float* partials, float* grads, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc == TARL_OK) rc = check(by_target, n_nodes);
@@ -853,15 +904,16 @@ int tarl_value_mp_backward(const tarl_csr* by_source, const tarl_csr* by_target,
         return cudaMemsetAsync(grads, 0, sizeof(float) * kGrads, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
     }
     if (!node_features || !agent_index || !agent_features || !msg_weight || !msg_bias || !node_weight || !proj ||
-        !mean || !v || !grad_v || !gm || !partials || (by_source->n_edges > 0 && !edge_features))
+        !mean || !v || !gm || !partials || (by_source->n_edges > 0 && !edge_features))
         return TARL_E_BADARG;
+    if ((head_g != nullptr) != (head_w != nullptr) || (grad_v == nullptr && head_g == nullptr)) return TARL_E_BADARG;
     const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
     const dim3 grid = tarl::tile_grid(n_nodes, batch);
     const int Bp = tarl::tile_rows_pow2(batch);
     k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
-                                                          gv_batch_stride, gv_node_stride, gm, partials);
+                                                          gv_batch_stride, gv_node_stride, head_g, head_w, gm, partials);
     // 4 rows per thread when every row chunk of the tile is a whole multiple of 4 rows and the B-vectors are 16-byte aligned
     const bool vec4 = (batch & 3) == 0 && Bp >= 4 &&
                       ((reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(gm)) & 15) == 0;
@@ -928,8 +980,8 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
                                    const uint32_t* keep_bits, int64_t keep_batch_stride, uint64_t seed, float p,
                                    const uint32_t* keep_words, float* agent_pack, float* msg, const float* mean,
                                    const float* v, const float* grad_v,
-                                   int64_t gv_batch_stride, int64_t gv_node_stride, float* gm, float* partials,
-                                   float* grads, void* stream) {
+                                   int64_t gv_batch_stride, int64_t gv_node_stride, const float* head_g,
+                                   const float* head_w, float* gm, float* partials, float* grads, void* stream) {
     if (batch < 0 || n_nodes < 0 || agent_rows < 1 || grads == nullptr || !(p >= 0.0f && p <= 1.0f)) return TARL_E_BADARG;
     int rc = check(by_source, n_nodes);
     if (rc == TARL_OK) rc = check(by_target, n_nodes);
@@ -938,16 +990,17 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
     if (batch == 0 || n_nodes == 0) {
         return cudaMemsetAsync(grads, 0, sizeof(float) * kGrads, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
     }
-    if (!node_features || !agent_index || !agent_features || !node_weight || !mean || !v || !grad_v || !gm ||
+    if (!node_features || !agent_index || !agent_features || !node_weight || !mean || !v || !gm ||
         !partials || (by_source->n_edges > 0 && (!edge_features || !msg)))
         return TARL_E_BADARG;
+    if ((head_g != nullptr) != (head_w != nullptr) || (grad_v == nullptr && head_g == nullptr)) return TARL_E_BADARG;
     const Inputs in = {node_features, nf_batch_stride, nf_row_stride, edge_features, ef_batch_stride,
                        reinterpret_cast<const long long*>(agent_index), agent_features, agent_rows, batch, n_nodes,
                        by_source->n_edges};
     const dim3 grid = tarl::tile_grid(n_nodes, batch);
     const int Bp = tarl::tile_rows_pow2(batch);
     k_value_node_grad<<<grid, tarl::kTileThreads, 0, s>>>(*by_source, batch, Bp, n_nodes, node_weight, mean, v, grad_v,
-                                                          gv_batch_stride, gv_node_stride, gm, partials);
+                                                          gv_batch_stride, gv_node_stride, head_g, head_w, gm, partials);
     if ((rc = drop_smem_ready()) != TARL_OK) return rc;
     const Drop drop = make_drop(keep_bits, keep_batch_stride, seed, p, keep_words);
     const int n_tiles = (int)(grid.x * grid.y);
@@ -962,6 +1015,36 @@ int tarl_value_mp_backward_dropout(const tarl_csr* by_source, const tarl_csr* by
     k_value_edge_grad_dropout<<<grid, tarl::kTileThreads, kDropSmemBytes, s>>>(*by_target, in, Bp, drop, msg, partials,
                                                                                reinterpret_cast<const float4*>(agent_pack));
     k_value_finish<<<kGrads, kThreads, 0, s>>>(partials, n_tiles + kDzCtas, grads);
+    return launch_status();
+}
+
+int32_t tarl_value_head_partial_count(int32_t n_nodes) { return n_nodes > 0 ? (n_nodes + kHeadNodes - 1) / kHeadNodes : 0; }
+
+int tarl_value_head_forward(const float* v, int32_t batch, int32_t n_nodes, const float* head_weight, float* partials,
+                            float* out, void* stream) {
+    if (batch < 0 || n_nodes < 0) return TARL_E_BADARG;
+    if (batch == 0) return TARL_OK;
+    if (out == nullptr) return TARL_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n_nodes == 0) return cudaMemsetAsync(out, 0, sizeof(float) * batch, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+    if (!v || !head_weight || !partials) return TARL_E_BADARG;
+    const int nb = tarl_value_head_partial_count(n_nodes);
+    k_value_head<<<nb, kThreads, 0, s>>>(v, batch, n_nodes, head_weight, partials);
+    k_value_head_finish<<<blocks_for(batch), kThreads, 0, s>>>(partials, nb, batch, out);
+    return launch_status();
+}
+
+int tarl_value_head_weight_grad(const float* v, int32_t batch, int32_t n_nodes, const float* grad_out, float* grad_weight,
+                                void* stream) {
+    if (batch < 0 || n_nodes < 0) return TARL_E_BADARG;
+    if (n_nodes == 0) return TARL_OK;
+    if (grad_weight == nullptr) return TARL_E_BADARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (batch == 0) return cudaMemsetAsync(grad_weight, 0, sizeof(float) * n_nodes, s) == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
+    if (!v || !grad_out) return TARL_E_BADARG;
+    const int64_t warps = n_nodes;
+    const int blocks = (int)((warps + kThreads / 32 - 1) / (kThreads / 32));
+    k_value_head_wgrad<<<blocks < 148 * 16 ? blocks : 148 * 16, kThreads, 0, s>>>(v, batch, n_nodes, grad_out, grad_weight);
     return launch_status();
 }
 

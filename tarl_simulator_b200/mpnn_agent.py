@@ -2,8 +2,8 @@
 
 Drop-in for the reference's src/agents/mpnn_agent.py: same constructors, parameter names and shapes (state_dict
 compatible), same forward signatures. The gather/scatter parts run in csrc/mpnn.cu (policy embedding fwd/bwd) and
-csrc/value_net.cu (MPNNValueNet message passing fwd/bwd); the dense per-node MLP of MPNNValueNetSimple is a plain
-library GEMM (nn.Linear → cuBLAS), see DESIGN.md.
+csrc/value_net.cu (MPNNValueNet message passing + head fwd/bwd), csrc/value_mlp.cu (MPNNValueNetSimple on tcgen05 and
+its backward), csrc/edge_mlp*.cu (the policy's per-edge MLPs); see DESIGN.md.
 """
 from __future__ import annotations
 
@@ -246,13 +246,39 @@ class MPNNPolicyNet(MessagePassing, Agents):
                 raise IndexError(_cabi.decode_error_bits(bits))
 
 
+def _head_dot(v_nm: torch.Tensor, head_w: torch.Tensor) -> torch.Tensor:
+    """out[b] = sum_n v[n, b] * head_w[n] on the node-major v [N, B] (tarl_value_head_forward: the node part of
+    final_mlp, src/agents/mpnn_agent.py:359-361, without the [B, N+1] concatenation and without a library GEMV)."""
+    N, B = v_nm.shape
+    dev = v_nm.device
+    lib = _cabi.lib()
+    out = torch.empty(B, dtype=torch.float32, device=dev)
+    partials = torch.empty(max(lib.tarl_value_head_partial_count(N) * B, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tarl_value_head_forward(v_nm.data_ptr(), B, N, head_w.data_ptr(), partials.data_ptr(), out.data_ptr(),
+                                         _stream(dev))
+    _cabi.check(rc, "tarl_value_head_forward")
+    return out
+
+
+def _head_weight_grad(v_nm: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    N, B = v_nm.shape
+    gw = torch.empty(N, dtype=torch.float32, device=v_nm.device)
+    with torch.cuda.device(v_nm.device):
+        rc = _cabi.lib().tarl_value_head_weight_grad(v_nm.data_ptr(), B, N, g.data_ptr(), gw.data_ptr(), _stream(v_nm.device))
+    _cabi.check(rc, "tarl_value_head_weight_grad")
+    return gw
+
+
 class _ValueMessagePassing(torch.autograd.Function):
     """v [B,N] = update(mean-aggregate(message)) of MPNNValueNet; gradients w.r.t. the four parameter tensors.
     ef: [B,E] (a batch stride of 0 — an expanded edge_attr — is passed through, not materialised). The result has
-    shape [B,N] over node-major memory (strides (1, B))."""
+    shape [B,N] over node-major memory (strides (1, B)) — or, with head_w [N] given, [B]: the node part of the value
+    head applied on the device (v . head_w per row; its gradient head_g[b] * head_w[n] is formed inside the backward
+    kernels and never materialised)."""
 
     @staticmethod
-    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags):
+    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags, head_w=None):
         B, N, _ = nf.shape
         dev = nf.device
         proj = torch.empty(N, B, dtype=torch.float32, device=dev)
@@ -269,28 +295,36 @@ class _ValueMessagePassing(torch.autograd.Function):
         _cabi.check(rc, "tarl_value_mp_forward")
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
         ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
-        ctx.save_for_backward(pw, pb, nw, nf, ef, ai, af, proj, mean, v)
-        return v.t()
+        hw = head_w.detach().reshape(-1).to(torch.float32).contiguous() if head_w is not None else None
+        ctx.has_head = hw is not None
+        ctx.save_for_backward(pw, pb, nw, nf, ef, ai, af, proj, mean, v, hw if hw is not None else v.new_empty(0))
+        return _head_dot(v, hw) if hw is not None else v.t()
 
     @staticmethod
-    def backward(ctx, grad_v):
-        pw, pb, nw, nf, ef, ai, af, proj, mean, v = ctx.saved_tensors
+    def backward(ctx, grad_out):
+        pw, pb, nw, nf, ef, ai, af, proj, mean, v, hw = ctx.saved_tensors
         B, N, _ = nf.shape
         dev = nf.device
         lib = _cabi.lib()
         gm = torch.empty(N, B, dtype=torch.float32, device=dev)
         partials = torch.empty(max(20 * lib.tarl_value_mp_partial_count(N, B), 1), dtype=torch.float32, device=dev)
         grads = torch.empty(20, dtype=torch.float32, device=dev)
+        if ctx.has_head:
+            g = grad_out.reshape(-1).to(torch.float32).contiguous()
+            gv_args = (None, 0, 0, g.data_ptr(), hw.data_ptr())
+        else:
+            gv_args = (grad_out.data_ptr(), grad_out.stride(0) if B > 1 else 0, grad_out.stride(1) if N > 1 else 1, None, None)
         with torch.cuda.device(dev):
             rc = lib.tarl_value_mp_backward(
                 ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
                 ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), pw.data_ptr(), pb.data_ptr(), nw.data_ptr(), B, N,
-                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
-                grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
+                proj.data_ptr(), mean.data_ptr(), v.data_ptr(), *gv_args, gm.data_ptr(), partials.data_ptr(),
+                grads.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_backward")
         s = ctx.shapes
         return (grads[:17].reshape(s[0]), grads[17:18].reshape(s[1]), grads[18:19].reshape(s[2]),
-                grads[19:20].reshape(s[3]), None, None, None, None, None, None, None)
+                grads[19:20].reshape(s[3]), None, None, None, None, None, None, None,
+                _head_weight_grad(v, g) if ctx.has_head else None)
 
 
 class _ValueMessagePassingDropout(torch.autograd.Function):
@@ -299,7 +333,8 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
     Philox stream of `seed` (kept edge-major for the backward pass)."""
 
     @staticmethod
-    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags, keep_bits, seed, p):
+    def forward(ctx, msg_w, msg_b, node_w, node_b, nf, ef, ai, af, by_source, by_target, flags, keep_bits, seed, p,
+                head_w=None):
         B, N, _ = nf.shape
         dev = nf.device
         E = by_source.n_edges
@@ -331,12 +366,14 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
         ctx.by_source, ctx.by_target, ctx.ef_bs = by_source, by_target, ef_bs
         ctx.drop = (keep_bits, seed, p)
         ctx.shapes = (msg_w.shape, msg_b.shape, node_w.shape, node_b.shape)
-        ctx.save_for_backward(nw, nf, ef, ai, af, msg, mean, v)
-        return v.t()
+        hw = head_w.detach().reshape(-1).to(torch.float32).contiguous() if head_w is not None else None
+        ctx.has_head = hw is not None
+        ctx.save_for_backward(nw, nf, ef, ai, af, msg, mean, v, hw if hw is not None else v.new_empty(0))
+        return _head_dot(v, hw) if hw is not None else v.t()
 
     @staticmethod
-    def backward(ctx, grad_v):
-        nw, nf, ef, ai, af, msg, mean, v = ctx.saved_tensors
+    def backward(ctx, grad_out):
+        nw, nf, ef, ai, af, msg, mean, v, hw = ctx.saved_tensors
         B, N, _ = nf.shape
         dev = nf.device
         lib = _cabi.lib()
@@ -345,17 +382,21 @@ class _ValueMessagePassingDropout(torch.autograd.Function):
         gm = torch.empty(N, B, dtype=torch.float32, device=dev)
         partials = torch.empty(max(20 * lib.tarl_value_mp_partial_count(N, B), 1), dtype=torch.float32, device=dev)
         grads = torch.empty(20, dtype=torch.float32, device=dev)
+        if ctx.has_head:
+            g = grad_out.reshape(-1).to(torch.float32).contiguous()
+            gv_args = (None, 0, 0, g.data_ptr(), hw.data_ptr())
+        else:
+            gv_args = (grad_out.data_ptr(), grad_out.stride(0) if B > 1 else 0, grad_out.stride(1) if N > 1 else 1, None, None)
         with torch.cuda.device(dev):
             rc = lib.tarl_value_mp_backward_dropout(
                 ctx.by_source.ref(), ctx.by_target.ref(), nf.data_ptr(), nf.stride(0), nf.stride(1), ef.data_ptr(),
                 ctx.ef_bs, ai.data_ptr(), af.data_ptr(), af.size(0), nw.data_ptr(), B, N, kb_ptr, kb_bs, seed, p,
                 ctx.words.data_ptr() if ctx.words is not None else None, ctx.pack.data_ptr(), msg.data_ptr(),
-                mean.data_ptr(), v.data_ptr(), grad_v.data_ptr(), grad_v.stride(0) if B > 1 else 0,
-                grad_v.stride(1) if N > 1 else 1, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
+                mean.data_ptr(), v.data_ptr(), *gv_args, gm.data_ptr(), partials.data_ptr(), grads.data_ptr(), _stream(dev))
         _cabi.check(rc, "tarl_value_mp_backward_dropout")
         s = ctx.shapes
         return (grads[:17].reshape(s[0]), grads[17:18].reshape(s[1]), grads[18:19].reshape(s[2]),
-                grads[19:20].reshape(s[3])) + (None,) * 10
+                grads[19:20].reshape(s[3])) + (None,) * 10 + (_head_weight_grad(v, g) if ctx.has_head else None,)
 
 
 class MPNNValueNet(MessagePassing, Agents):
@@ -363,7 +404,8 @@ class MPNNValueNet(MessagePassing, Agents):
     per edge tanh(Linear(17→1)([x_target(16) ‖ edge_attr])), mean over each source node's out-edges,
     tanh(Linear(1→1)), then Linear(N+1→1) over [v_nodes ‖ time_net(time)]. Parameter names / shapes are the
     reference's (`message_mlp.1.*`, `node_mlp.0.*`, `final_mlp.0.*`, `time_net.{0,3,6}.*`). The gather / aggregate /
-    update and their backward are csrc/value_net.cu; the two dense heads (time_net, final_mlp) are library GEMVs.
+    update, the node part of the head (v . W[:N]) and their backward are csrc/value_net.cu; what is left to torch is
+    time_net, a 1 -> 32 -> 32 -> 1 MLP on the [B, 1] time input.
 
     Train mode: the reference applies Dropout(0.05) to every [B*E, 17] message input (:278). The mask cannot factor
     through the per-node projection, so a second kernel set (`tarl_value_mp_*_dropout`) computes the messages per
@@ -437,18 +479,21 @@ class MPNNValueNet(MessagePassing, Agents):
                 # ranks seeded alike (identical initial parameters) must still drop different message inputs
                 seed = (seed + torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & ((1 << 62) - 1)
             self._last_drop = (keep_bits, seed, p_drop, B)
-            v = _ValueMessagePassingDropout.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
-                                                  by_target, self._flags, keep_bits, seed, p_drop)
-        else:
-            v = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
-                                           by_target, self._flags)
-        if not batched:
-            v = v.reshape(self.num_nodes)
-        # final_mlp([v_nodes ‖ time_net(t)]) with the weight split instead of the concatenation (src/agents/mpnn_agent.py:359-361 of the
-        # reference): the [B, N+1] copy of v would cost more than the whole message passing
+        # final_mlp([v_nodes ‖ time_net(t)]) with the weight split instead of the concatenation (src/agents/mpnn_agent.py:
+        # 359-361 of the reference): the node part v . W[:N] is applied on the device by the same autograd node (no
+        # [B, N+1] copy of v, no library GEMV, and its gradient g[b] * W[n] is never materialised)
         head = self.final_mlp[0]
         N = self.num_nodes
-        return (v @ head.weight[0, :N]).unsqueeze(-1) + self.time_net(time) * head.weight[0, N] + head.bias
+        head_w = head.weight[0, :N]
+        if self.training and p_drop > 0:
+            dot = _ValueMessagePassingDropout.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
+                                                    by_target, self._flags, keep_bits, seed, p_drop, head_w)
+        else:
+            dot = _ValueMessagePassing.apply(lin.weight, lin.bias, upd.weight, upd.bias, nf, ef, ai, af, by_source,
+                                             by_target, self._flags, head_w)
+        tt = time if batched else time.reshape(1, -1)
+        out = dot.unsqueeze(-1) + self.time_net(tt) * head.weight[0, N] + head.bias
+        return out if batched else out.reshape(-1)
 
     def check_errors(self):
         if self._flags is not None:
