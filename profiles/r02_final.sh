@@ -17,5 +17,9 @@ ncu --set full --clock-control none --import-source on -k regex:"k_gd_|k_policy_
 ncu -i /tmp/mpnn_$T.ncu-rep --page raw --csv > /tmp/mpnn_raw.csv 2>/dev/null && python profiles/summarise_ncu.py /tmp/mpnn_raw.csv gpurun_out/${T}_mpnn_ncu_full_summary.csv
 ncu --set full --clock-control none -k regex:"k_value_" -s 7 -c 7 -o /tmp/train_$T -f python profiles/value_train_once.py > gpurun_out/ncu_train_$T.log 2>&1
 ncu -i /tmp/train_$T.ncu-rep --page raw --csv > /tmp/train_raw.csv 2>/dev/null && python profiles/summarise_ncu.py /tmp/train_raw.csv gpurun_out/${T}_value_train_ncu_full_summary.csv
+ncu --set full --clock-control none -k regex:"k_edge_mlp" -c 6 -o /tmp/emlp_$T -f python profiles/edge_mlp_once.py > gpurun_out/ncu_emlp_$T.log 2>&1
+ncu -i /tmp/emlp_$T.ncu-rep --page raw --csv > /tmp/emlp_raw.csv 2>/dev/null && python profiles/summarise_ncu.py /tmp/emlp_raw.csv gpurun_out/${T}_edge_mlp_ncu_full_summary.csv
+python profiles/rollout_timeline.py 128 2>&1 | grep -v Warn | tail -20 > gpurun_out/rollout_timeline_${T}_128.txt
+python profiles/rollout_timeline.py 1024 2>&1 | grep -v Warn | tail -20 > gpurun_out/rollout_timeline_${T}_1024.txt
 python profiles/pcie_diag.py
 ls -la gpurun_out/*$T* | tail -30

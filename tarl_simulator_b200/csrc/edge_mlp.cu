@@ -63,13 +63,14 @@ __global__ void __launch_bounds__(256) k_edge_mlp_x(const float* __restrict__ nf
 template <int IN, int H1, int H2>
 struct Shape {
     static constexpr int kInP = (IN + 3) / 4 * 4;                 // padded row of W1 in shared memory
+    static constexpr int kW2P = H2 + 4;                           // row pitch of the transposed W2 copy (see k_edge_mlp_bwd)
     static constexpr int kLast = H2 > 0 ? H2 : H1;                // inputs of the output layer
     static constexpr int kParams = H1 * IN + H1 + (H2 > 0 ? H2 * H1 + H2 : 0) + kLast + 1;
     // offsets into the flat gradient vector: W1, b1, [W2, b2,] w_out, b_out — the order of Sequential.parameters()
     static constexpr int oW1 = 0, oB1 = H1 * IN, oW2 = oB1 + H1, oB2 = oW2 + (H2 > 0 ? H2 * H1 : 0),
                          oWo = oB2 + (H2 > 0 ? H2 : 0), oBo = oWo + kLast;
     // shared-memory copy of the weights (floats)
-    static constexpr int sW1 = 0, sB1 = H1 * kInP, sW2 = sB1 + H1, sB2 = sW2 + (H2 > 0 ? H2 * H1 : 0),
+    static constexpr int sW1 = 0, sB1 = H1 * kInP, sW2 = sB1 + H1, sB2 = sW2 + (H2 > 0 ? kW2P * H1 : 0),
                          sWo = sB2 + (H2 > 0 ? H2 : 0), sBo = sWo + kLast, kWeightFloats = (sBo + 1 + 3) / 4 * 4;
 };
 
@@ -88,7 +89,7 @@ __device__ __forceinline__ void stage_weights(const Weights& w, float* sm) {
     if (H2 > 0) {
         for (int i = threadIdx.x; i < H2 * H1; i += blockDim.x) {         // transposed: W2t[i][j], the j of one i contiguous
             const int j = i / H1, c = i - j * H1;
-            sm[S::sW2 + c * H2 + j] = w.w2[i];
+            sm[S::sW2 + c * S::kW2P + j] = w.w2[i];
         }
         for (int i = threadIdx.x; i < H2; i += blockDim.x) sm[S::sB2 + i] = w.b2[i];
     }
@@ -132,7 +133,7 @@ __device__ __forceinline__ float hidden1(const float* sm, const float (&a)[Shape
 template <int IN, int H1, int H2>
 __device__ __forceinline__ void feed2(const float* sm, int i, float h, float (&z2)[H2 > 0 ? H2 : 1]) {
     using S = Shape<IN, H1, H2>;
-    const float4* col = reinterpret_cast<const float4*>(sm + S::sW2 + i * H2);
+    const float4* col = reinterpret_cast<const float4*>(sm + S::sW2 + i * S::kW2P);
 #pragma unroll
     for (int q = 0; q < H2 / 4; ++q) {
         const float4 v = col[q];
@@ -187,7 +188,7 @@ struct BwdSmem {
 
 // acc[r][c..c+3] += sum over the tile's pairs of L[p][r] * R[p][c..c+3]: work items (r, c/4) dealt round-robin to the
 // CTA's threads, `kItems` per thread, accumulators in registers across tiles.
-template <int ROWS, int COLS4, int kItems>
+template <int ROWS, int COLS4, int kItems, int kThreadsB>
 __device__ __forceinline__ void outer_sum(const float* __restrict__ L, int pL, const float* __restrict__ R, int pR,
                                           int live, float4 (&acc)[kItems]) {
     // the pair loop is the OUTER one: a thread's kItems accumulators are independent chains, and the shared-memory reads of
@@ -196,7 +197,7 @@ __device__ __forceinline__ void outer_sum(const float* __restrict__ L, int pL, c
     bool on[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; ++k) {
-        const int item = threadIdx.x + k * kTile;
+        const int item = threadIdx.x + k * kThreadsB;
         on[k] = item < ROWS * COLS4;
         const int r = on[k] ? item / COLS4 : 0, c4 = on[k] ? item - r * COLS4 : 0;
         offL[k] = r; offR[k] = 4 * c4;
@@ -218,12 +219,17 @@ __device__ __forceinline__ void outer_sum(const float* __restrict__ L, int pL, c
     }
 }
 
+// FOUR threads per pair in the recompute phase (sub-thread s owns the hidden units i = 4 ii + s; the second layer's
+// sums are completed across the four by shuffles): 512 threads = 16 warps per SM on the one CTA the 145 KB of parked
+// activations allow. (One thread per pair: 4 warps per SM, the recompute a bare latency chain — 110 ms at 8 rows x
+// 6.0 M edges against 15 ms for the same arithmetic in the forward kernel's 12 CTAs per SM.)
+constexpr int kBwdThreads = 4 * kTile;
 template <int IN, int H1, int H2>
-__global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                                                        int E, int B, const float* __restrict__ x, int64_t x_bs,
-                                                        const float* __restrict__ ea, int64_t ea_bs, Weights w,
-                                                        const float* __restrict__ gout, int64_t g_bs, int64_t g_es,
-                                                        float* __restrict__ partials) {
+__global__ void __launch_bounds__(kBwdThreads) k_edge_mlp_bwd(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                                              int E, int B, const float* __restrict__ x, int64_t x_bs,
+                                                              const float* __restrict__ ea, int64_t ea_bs, Weights w,
+                                                              const float* __restrict__ gout, int64_t g_bs, int64_t g_es,
+                                                              float* __restrict__ partials) {
     using S = Shape<IN, H1, H2>;
     using M = BwdSmem<IN, H1, H2>;
     extern __shared__ float sm[];
@@ -234,8 +240,9 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
     float* sH2 = sm + M::oH2;
     float* sG2 = sm + M::oG2;
     float* sG = sm + M::oG;
-    constexpr int kW1Items = (H1 * (S::kInP / 4) + kTile - 1) / kTile;
-    constexpr int kW2Items = H2 > 0 ? (H2 * (H1 / 4) + kTile - 1) / kTile : 1;
+    constexpr int kW1Items = (H1 * (S::kInP / 4) + kBwdThreads - 1) / kBwdThreads;
+    constexpr int kW2Items = H2 > 0 ? (H2 * (H1 / 4) + kBwdThreads - 1) / kBwdThreads : 1;
+    constexpr int kOwn = H1 / 4;                                  // hidden units per sub-thread
     float4 accW1[kW1Items], accW2[kW2Items];
 #pragma unroll
     for (int k = 0; k < kW1Items; ++k) accW1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,52 +251,59 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
     float accB1 = 0.0f, accB2 = 0.0f, accWo = 0.0f, accBo = 0.0f;    // thread t: b1[t], b2[t], w_out[t]; thread 0: b_out
     const int tiles_per_row = (E + kTile - 1) / kTile;
     const long long n_tiles = (long long)tiles_per_row * B;
+    const int p = threadIdx.x >> 2, sub = threadIdx.x & 3;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = (int)(tile / tiles_per_row);
         const int e0 = (int)(tile - (long long)b * tiles_per_row) * kTile;
         const int live = min(kTile, E - e0);
         __syncthreads();                                          // weights staged / previous tile's reductions done
-        const int p = threadIdx.x;
+        const unsigned quad = __ballot_sync(0xffffffffu, p < live);   // the four sub-threads of a pair branch together
         if (p < live) {
             const int e = e0 + p;
             float a[S::kInP];
             load_inputs<IN>(x, x_bs, ea, ea_bs, b, e, src[e], dst[e], a);
             const float g = gout[b * g_bs + e * g_es];
-            sG[p] = g;
+            if (sub == 0) sG[p] = g;
 #pragma unroll
-            for (int c = 0; c < S::kInP; ++c) sA[p * M::pA + c] = a[c];
-            // a spare padding column holds the constant 1: column IN of the W1 sums is then the bias gradient
-            if (S::kInP > IN) sA[p * M::pA + IN] = 1.0f;
+            for (int c = 0; c < S::kInP; ++c)
+                if ((c & 3) == sub) sA[p * M::pA + c] = (S::kInP > IN && c == IN) ? 1.0f : a[c];   // spare column: carries d b1
             if (H2 > 0) {
-                float z2[H2 > 0 ? H2 : 1], g2[H2 > 0 ? H2 : 1];
+                float z2[H2 > 0 ? H2 : 1];
 #pragma unroll
-                for (int j = 0; j < H2; ++j) z2[j] = sm[S::sB2 + j];
+                for (int j = 0; j < H2; ++j) z2[j] = 0.0f;
 #pragma unroll 2
-                for (int i = 0; i < H1; ++i) {
+                for (int ii = 0; ii < kOwn; ++ii) {
+                    const int i = 4 * ii + sub;
                     const float h = hidden1<IN, H1, H2>(sm, a, i);
                     sH1[p * M::pH1 + i] = h;
                     feed2<IN, H1, H2>(sm, i, h, z2);
                 }
 #pragma unroll
                 for (int j = 0; j < H2; ++j) {
-                    g2[j] = z2[j] > 0.0f ? g * sm[S::sWo + j] : 0.0f;
-                    sH2[p * M::pH2 + j] = fmaxf(z2[j], 0.0f);
-                    sG2[p * M::pH2 + j] = g2[j];
+                    float z = z2[j];
+                    z += __shfl_xor_sync(quad, z, 1);
+                    z += __shfl_xor_sync(quad, z, 2);
+                    z += sm[S::sB2 + j];
+                    const float g2 = z > 0.0f ? g * sm[S::sWo + j] : 0.0f;
+                    if ((j & 3) == sub) { sH2[p * M::pH2 + j] = fmaxf(z, 0.0f); sG2[p * M::pH2 + j] = g2; }
+                    z2[j] = g2;
                 }
 #pragma unroll 2
-                for (int i = 0; i < H1; ++i) {
-                    const float4* col = reinterpret_cast<const float4*>(sm + S::sW2 + i * H2);
+                for (int ii = 0; ii < kOwn; ++ii) {
+                    const int i = 4 * ii + sub;
+                    const float4* col = reinterpret_cast<const float4*>(sm + S::sW2 + i * S::kW2P);
                     float acc = 0.0f;
 #pragma unroll
                     for (int q = 0; q < H2 / 4; ++q) {
                         const float4 v = col[q];
-                        acc += v.x * g2[4 * q] + v.y * g2[4 * q + 1] + v.z * g2[4 * q + 2] + v.w * g2[4 * q + 3];
+                        acc += v.x * z2[4 * q] + v.y * z2[4 * q + 1] + v.z * z2[4 * q + 2] + v.w * z2[4 * q + 3];
                     }
-                    sG1[p * M::pH1 + i] = sH1[p * M::pH1 + i] > 0.0f ? acc : 0.0f;
+                    sG1[p * M::pH1 + i] = sH1[p * M::pH1 + i] > 0.0f ? acc : 0.0f;     // (its own store: same thread)
                 }
             } else {
-#pragma unroll 2
-                for (int i = 0; i < H1; ++i) {
+#pragma unroll
+                for (int ii = 0; ii < kOwn; ++ii) {
+                    const int i = 4 * ii + sub;
                     const float h = hidden1<IN, H1, H2>(sm, a, i);
                     sH1[p * M::pH1 + i] = h;
                     sG1[p * M::pH1 + i] = h > 0.0f ? g * sm[S::sWo + i] : 0.0f;
@@ -298,8 +312,8 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
         }
         __syncthreads();
         // reductions over the tile's pairs (ascending pair order: fixed)
-        outer_sum<H1, S::kInP / 4, kW1Items>(sG1, M::pH1, sA, M::pA, live, accW1);
-        if (H2 > 0) outer_sum<H2, H1 / 4, kW2Items>(sG2, M::pH2, sH1, M::pH1, live, accW2);
+        outer_sum<H1, S::kInP / 4, kW1Items, kBwdThreads>(sG1, M::pH1, sA, M::pA, live, accW1);
+        if (H2 > 0) outer_sum<H2, H1 / 4, kW2Items, kBwdThreads>(sG2, M::pH2, sH1, M::pH1, live, accW2);
         const int t = threadIdx.x;
         if (S::kInP == IN && t < H1) {                            // (otherwise the spare column of A carries it)
             float s = 0.0f;
@@ -327,7 +341,7 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
     float* out = partials + (size_t)blockIdx.x * S::kParams;
 #pragma unroll
     for (int k = 0; k < kW1Items; ++k) {
-        const int item = threadIdx.x + k * kTile;
+        const int item = threadIdx.x + k * kBwdThreads;
         if (item >= H1 * (S::kInP / 4)) continue;
         const int r = item / (S::kInP / 4), c = 4 * (item - r * (S::kInP / 4));
         const float v[4] = {accW1[k].x, accW1[k].y, accW1[k].z, accW1[k].w};
@@ -340,7 +354,7 @@ __global__ void __launch_bounds__(kTile) k_edge_mlp_bwd(const int32_t* __restric
     if (H2 > 0) {
 #pragma unroll
         for (int k = 0; k < kW2Items; ++k) {
-            const int item = threadIdx.x + k * kTile;
+            const int item = threadIdx.x + k * kBwdThreads;
             if (item >= H2 * (H1 / 4)) continue;
             const int r = item / (H1 / 4), c = 4 * (item - r * (H1 / 4));
             out[S::oW2 + r * H1 + c] = accW2[k].x; out[S::oW2 + r * H1 + c + 1] = accW2[k].y;
@@ -387,7 +401,7 @@ int run_backward(const int32_t* src, const int32_t* dst, int E, int B, const flo
     static const bool ok =
         cudaFuncSetAttribute(k_edge_mlp_bwd<IN, H1, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
     if (!ok) return TARL_E_LAUNCH;
-    k_edge_mlp_bwd<IN, H1, H2><<<kBwdCtas, kTile, bytes, s>>>(src, dst, E, B, x, x_bs, ea, ea_bs, w, gout, g_bs, g_es, partials);
+    k_edge_mlp_bwd<IN, H1, H2><<<kBwdCtas, kBwdThreads, bytes, s>>>(src, dst, E, B, x, x_bs, ea, ea_bs, w, gout, g_bs, g_es, partials);
     k_edge_mlp_finish<<<(S::kParams + 255) / 256, 256, 0, s>>>(partials, kBwdCtas, S::kParams, grads);
     return launch_status();
 }

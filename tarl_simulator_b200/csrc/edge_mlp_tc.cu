@@ -39,7 +39,11 @@ constexpr uint32_t kColA = 0, kColD = 128;         // A1_hi [0,40) A1_lo [40,80)
 constexpr uint32_t kB1Tile = 128 * 128, kB2Tile = 64 * 128;
 constexpr uint32_t kOffB2 = 2 * kB1Tile, kOffVec = kOffB2 + 2 * kB2Tile, kOffBar = kOffVec + 68 * 4;
 constexpr uint32_t kPrepFloats = kOffVec / 4 + 68;         // what the preparation kernel writes (floats)
-constexpr size_t kSmemBytes = kOffBar + 64 + 1024;         // + alignment slack
+// Requested shared memory: the image + barriers + alignment slack, padded to 100 KB so that at most TWO CTAs fit an SM —
+// a third would sit in tcgen05.alloc (512 TMEM columns per SM, 256 per CTA) holding its share of the tiles until another
+// CTA exits: measured 8.4 ms instead of 4.6 ms for 8 rows x 6.0 M edges.
+constexpr size_t kSmemBytes = 100 * 1024;
+static_assert(kOffBar + 64 + 1024 <= kSmemBytes, "weight image does not fit");
 
 inline int launch_status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
 
