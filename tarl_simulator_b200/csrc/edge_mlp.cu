@@ -219,6 +219,23 @@ __device__ __forceinline__ void outer_sum(const float* __restrict__ L, int pL, c
     }
 }
 
+// acc[i][j] += sum over the tile's pairs of L[p][4 rb + i] * R[p][4 cb + j]: one 4 x 4 block per thread, two 128-bit
+// shared-memory reads per 16 multiply-adds (the 1 x 4 form above reads two words per 4: the reductions of a tile then
+// sit on the shared-memory pipe for ~18 us).
+__device__ __forceinline__ void outer_block4(const float* __restrict__ L, int pL, const float* __restrict__ R, int pR,
+                                             int rb, int cb, int live, float (&acc)[4][4]) {
+#pragma unroll 2
+    for (int p = 0; p < live; ++p) {
+        const float4 l = *reinterpret_cast<const float4*>(L + p * pL + 4 * rb);
+        const float4 v = *reinterpret_cast<const float4*>(R + p * pR + 4 * cb);
+        const float lv[4] = {l.x, l.y, l.z, l.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += lv[i] * vv[j];
+    }
+}
+
 // FOUR threads per pair in the recompute phase (sub-thread s owns the hidden units i = 4 ii + s; the second layer's
 // sums are completed across the four by shuffles): 512 threads = 16 warps per SM on the one CTA the 145 KB of parked
 // activations allow. (One thread per pair: 4 warps per SM, the recompute a bare latency chain — 110 ms at 8 rows x
@@ -240,14 +257,20 @@ __global__ void __launch_bounds__(kBwdThreads) k_edge_mlp_bwd(const int32_t* __r
     float* sH2 = sm + M::oH2;
     float* sG2 = sm + M::oG2;
     float* sG = sm + M::oG;
-    constexpr int kW1Items = (H1 * (S::kInP / 4) + kBwdThreads - 1) / kBwdThreads;
-    constexpr int kW2Items = H2 > 0 ? (H2 * (H1 / 4) + kBwdThreads - 1) / kBwdThreads : 1;
     constexpr int kOwn = H1 / 4;                                  // hidden units per sub-thread
-    float4 accW1[kW1Items], accW2[kW2Items];
+    // weight-gradient blocks: thread t < kW1Blocks owns the 4 x 4 block (t / C1, t % C1) of dW1 (padded to kInP columns);
+    // threads [kW2First, kW2First + kW2Blocks) own the blocks of dW2 — different warps, so both sets run side by side
+    constexpr int C1 = S::kInP / 4, kW1Blocks = (H1 / 4) * C1;
+    constexpr int C2 = H1 / 4, kW2Blocks = H2 > 0 ? (H2 / 4) * C2 : 0;
+    constexpr int kW2First = (kW1Blocks + 31) / 32 * 32;
+    static_assert(kW2First + kW2Blocks <= kBwdThreads, "not enough threads for the weight-gradient blocks");
+    float accW[4][4];
 #pragma unroll
-    for (int k = 0; k < kW1Items; ++k) accW1[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int k = 0; k < kW2Items; ++k) accW2[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) accW[i][j] = 0.0f;
+    const int tid = threadIdx.x;
+    const bool ownW1 = tid < kW1Blocks, ownW2 = H2 > 0 && tid >= kW2First && tid < kW2First + kW2Blocks;
     float accB1 = 0.0f, accB2 = 0.0f, accWo = 0.0f, accBo = 0.0f;    // thread t: b1[t], b2[t], w_out[t]; thread 0: b_out
     const int tiles_per_row = (E + kTile - 1) / kTile;
     const long long n_tiles = (long long)tiles_per_row * B;
@@ -312,8 +335,8 @@ __global__ void __launch_bounds__(kBwdThreads) k_edge_mlp_bwd(const int32_t* __r
         }
         __syncthreads();
         // reductions over the tile's pairs (ascending pair order: fixed)
-        outer_sum<H1, S::kInP / 4, kW1Items, kBwdThreads>(sG1, M::pH1, sA, M::pA, live, accW1);
-        if (H2 > 0) outer_sum<H2, H1 / 4, kW2Items, kBwdThreads>(sG2, M::pH2, sH1, M::pH1, live, accW2);
+        if (ownW1) outer_block4(sG1, M::pH1, sA, M::pA, tid / C1, tid % C1, live, accW);
+        else if (ownW2) outer_block4(sG2, M::pH2, sH1, M::pH1, (tid - kW2First) / C2, (tid - kW2First) % C2, live, accW);
         const int t = threadIdx.x;
         if (S::kInP == IN && t < H1) {                            // (otherwise the spare column of A carries it)
             float s = 0.0f;
@@ -339,27 +362,22 @@ __global__ void __launch_bounds__(kBwdThreads) k_edge_mlp_bwd(const int32_t* __r
     }
     // this CTA's partial gradient vector
     float* out = partials + (size_t)blockIdx.x * S::kParams;
+    if (ownW1) {
+        const int rb = tid / C1, cb = tid % C1;
 #pragma unroll
-    for (int k = 0; k < kW1Items; ++k) {
-        const int item = threadIdx.x + k * kBwdThreads;
-        if (item >= H1 * (S::kInP / 4)) continue;
-        const int r = item / (S::kInP / 4), c = 4 * (item - r * (S::kInP / 4));
-        const float v[4] = {accW1[k].x, accW1[k].y, accW1[k].z, accW1[k].w};
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (c + q < IN) out[S::oW1 + r * IN + c + q] = v[q];
-            else if (c + q == IN) out[S::oB1 + r] = v[q];
-        }
-    }
-    if (H2 > 0) {
+            for (int j = 0; j < 4; ++j) {
+                const int r = 4 * rb + i, c = 4 * cb + j;
+                if (c < IN) out[S::oW1 + r * IN + c] = accW[i][j];
+                else if (c == IN) out[S::oB1 + r] = accW[i][j];                  // the spare column of A carried d b1
+            }
+    } else if (ownW2) {
+        const int rb = (tid - kW2First) / C2, cb = (tid - kW2First) % C2;
 #pragma unroll
-        for (int k = 0; k < kW2Items; ++k) {
-            const int item = threadIdx.x + k * kBwdThreads;
-            if (item >= H2 * (H1 / 4)) continue;
-            const int r = item / (H1 / 4), c = 4 * (item - r * (H1 / 4));
-            out[S::oW2 + r * H1 + c] = accW2[k].x; out[S::oW2 + r * H1 + c + 1] = accW2[k].y;
-            out[S::oW2 + r * H1 + c + 2] = accW2[k].z; out[S::oW2 + r * H1 + c + 3] = accW2[k].w;
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[S::oW2 + (4 * rb + i) * H1 + 4 * cb + j] = accW[i][j];
     }
     const int t = threadIdx.x;
     if (S::kInP == IN && t < H1) out[S::oB1 + t] = accB1;
