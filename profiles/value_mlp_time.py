@@ -4,7 +4,9 @@ sys.path.insert(0, "/root/repo")
 from tarl_simulator_b200.mpnn_agent import MPNNValueNetSimple
 M, N = int(sys.argv[1]), int(sys.argv[2])
 net = MPNNValueNetSimple(torch.zeros(2, 1, dtype=torch.long, device="cuda"), N, "cuda")
-num = torch.rand(M, N, device="cuda"); time = torch.rand(M, 1, device="cuda")
+num = torch.rand(M, N, device="cuda")
+if len(sys.argv) > 3 and sys.argv[3] == "int": num = torch.randint(0, 16, (M, N), device="cuda").float()   # occupancies
+time = torch.rand(M, 1, device="cuda")
 with torch.no_grad():
     for _ in range(3): net.forward_occupancy(num, time)
     torch.cuda.synchronize()

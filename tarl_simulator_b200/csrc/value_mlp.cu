@@ -33,6 +33,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tarl_b200.h"
@@ -41,12 +42,15 @@ namespace {
 
 constexpr int BM = 128, BN = 64, BK = 32;
 constexpr int kGroup = 2;                              // A tiles requested together (NA must be a multiple)
-// ring depths: A tiles (smem), W tiles (smem) and A hi/lo (TMEM). The last two are released by the same event (the
-// MMAs of a k-block completing), so they share one depth and ONE "free" barrier: a tcgen05.commit costs the issuing
-// thread ~150 cycles (measured), more than a third of the 384-cycle MMA floor of a k-block.
-constexpr int NA = 8, NT = 4, NW = NT;
+// ring depths in k-blocks: A tiles (smem), A hi/lo (TMEM: 2 pairs), W tiles (smem: 3 pairs). The last two are released
+// by the same event (the MMAs of a pair completing) through ONE barrier per pair, pair p on barrier p % kPairBars: a
+// tcgen05.commit costs the issuing thread ~150 cycles (measured), more than a third of the 384-cycle MMA floor of a
+// k-block, so there is exactly one per pair.
+constexpr int NA = 8, NT = 4, NW = 6;
+constexpr int kPairBars = 6;                           // a multiple of NT / 2 and NW / 2, at least their maximum + 1
 constexpr int kHidden = 64;
-constexpr int kThreadsGemm = 224;
+constexpr int kSplitSets = 2;                          // splitter warp quartets, k-block kb goes to set kb % kSplitSets
+constexpr int kThreadsGemm = 32 * (2 + 4 * kSplitSets + 1);
 constexpr uint32_t kABytes = BM * BK * 4, kBBytes = BN * BK * 4;
 constexpr uint32_t kTmemCols = 512;                    // 2 x 128 accumulator + 4 x (32 hi + 32 lo)
 constexpr uint32_t kColAcc = 0, kAccCols = 2 * BN, kColA = 2 * kAccCols;
@@ -160,9 +164,27 @@ __global__ void __launch_bounds__(256) k_value_mlp_split_w(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ first layer
+#ifdef TARL_VM_PROFILE                                 // per-role cycle accounting of one CTA (profiles/value_mlp_roles.py)
+#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc_ = clock64(), pstart_ = pc_
+#define PROF(i) do { const long long n_ = clock64(); pt_[i] += n_ - pc_; pc_ = n_; } while (0)
+#define PROF_OUT(name) do { if (blockIdx.x == 1 && blockIdx.y == 3) printf("%s nkb %d total %lld | %lld %lld %lld %lld %lld %lld %lld %lld\n", name, nkb, clock64() - pstart_, pt_[0], pt_[1], pt_[2], pt_[3], pt_[4], pt_[5], pt_[6], pt_[7]); } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_OUT(name)
+#endif
 // Three rings decouple the three latencies: A tiles in shared memory (TMA -> splitters; a slot is free again as soon
 // as its rows sit in registers, so its cycle is HBM latency + split, not + MMA), A hi/lo in TMEM (splitters -> MMA),
 // W tiles in shared memory (TMA from L2 -> MMA).
+//
+// Everything downstream of the A ring works on PAIRS of k-blocks (2 x 32 columns). Measured with the per-role counters
+// above: the issuing thread is the pacemaker — an mbarrier test costs it ~200 cycles even when the barrier completed
+// long ago (its shared-memory round trip queues behind the splitter warps' LDS bursts), a tcgen05.commit ~150, and a
+// tcgen05.mma blocks until the previous one is about to finish (64 cycles at N = 128, 45 at N = 64:
+// profiles/micro/mma_rate.cu), so that per k-block two waits + eight MMAs + one commit came to ~1300 cycles against
+// the MMAs' own 384. Per pair there is ONE wait — `ready[p % 6]` collects the 256 splitter arrivals AND the W tiles'
+// bytes (the W producer's arrive.expect_tx) — sixteen MMAs and ONE commit: `pair_done[p % 6]`, which frees the TMEM
+// columns two pairs later (2 pair slots) and the W tiles three pairs later (3 pair slots) through the same barrier.
 __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid_constant__ CUtensorMap map_a,
                                                                     const __grid_constant__ CUtensorMap map_wh,
                                                                     const __grid_constant__ CUtensorMap map_wl, int M,
@@ -177,22 +199,23 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     auto sm_wl = [&](int s) { return w_base + s * 2 * kBBytes + kBBytes; };
     auto a_full = [&](int s) { return bars + 8u * s; };
     auto a_empty = [&](int s) { return bars + 8u * (NA + s); };
-    auto w_full = [&](int s) { return bars + 8u * (2 * NA + s); };
-    auto slot_free = [&](int s) { return bars + 8u * (2 * NA + NW + s); };    // W slot s and TMEM A slot s
-    auto t_ready = [&](int s) { return bars + 8u * (2 * NA + 2 * NW + s); };
-    auto accfull = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + b); };
-    auto accfree = [&](int b) { return bars + 8u * (2 * NA + 2 * NW + 2 * NT + 2 + b); };
-    const uint32_t tmem_slot = bars + 8u * (2 * NA + 2 * NW + 2 * NT + 4);
+    auto ready = [&](int s) { return bars + 8u * (2 * NA + s); };             // pair p -> ready(p % kPairBars)
+    auto pair_done = [&](int s) { return bars + 8u * (2 * NA + kPairBars + s); };
+    auto accfull = [&](int b) { return bars + 8u * (2 * NA + 2 * kPairBars + b); };
+    auto accfree = [&](int b) { return bars + 8u * (2 * NA + 2 * kPairBars + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * NA + 2 * kPairBars + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
     const int kb0 = blockIdx.y * kb_per_slice;
     const int nkb = min(kb_per_slice, kb_total - kb0);
     const int n_chunks = (nkb + kChunk - 1) / kChunk;
+    const int n_pairs = (nkb + 1) / 2;
+    // the pair whose MMAs must be complete before pair p may reuse its TMEM columns / its W slots
+    auto wait_pair_done = [&](int p) { if (p >= 0) mbar_wait(pair_done(p % kPairBars), (p / kPairBars) & 1); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 128); }
-        for (int s = 0; s < NW; ++s) { mbar_init(w_full(s), 1); mbar_init(slot_free(s), 1); }
-        for (int s = 0; s < NT; ++s) mbar_init(t_ready(s), 128);
+        for (int s = 0; s < kPairBars; ++s) { mbar_init(ready(s), 128 * kSplitSets + 1); mbar_init(pair_done(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(accfull(b), 1); mbar_init(accfree(b), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -210,53 +233,75 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
         if (lane == 0) {                                                 // ===== TMA producer, A tiles (HBM)
             // kGroup consecutive k-blocks are requested back to back: per row of A that is kGroup x 128 contiguous
             // bytes arriving at the memory controller together instead of 128-byte pieces one k-block period apart
+            PROF_DECL;
             for (int kg = 0; kg < nkb; kg += kGroup) {
                 const int n = min(kGroup, nkb - kg);
+                PROF(0);
                 for (int i = 0; i < n; ++i) mbar_wait(a_empty((kg + i) % NA), (((kg + i) / NA) & 1) ^ 1);
+                PROF(1);
                 for (int i = 0; i < n; ++i) {
                     const int kb = kg + i, s = kb % NA;
                     mbar_expect_tx(a_full(s), kABytes);
                     tma_load_2d(sm_a(s), &map_a, a_full(s), (kb0 + kb) * BK, m0);
                 }
             }
+            PROF_OUT("tmaA [other, wait a_empty]");
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + 4 * kSplitSets) {
         if (lane == 0) {                                                 // ===== TMA producer, W tiles (L2)
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NW, ph = (kb / NW) & 1;
-                mbar_wait(slot_free(s), ph ^ 1);
-                mbar_expect_tx(w_full(s), 2 * kBBytes);
-                tma_load_2d(sm_wh(s), &map_wh, w_full(s), (kb0 + kb) * BK, 0);
-                tma_load_2d(sm_wl(s), &map_wl, w_full(s), (kb0 + kb) * BK, 0);
+            for (int p = 0; p < n_pairs; ++p) {
+                const int n = min(2, nkb - 2 * p);
+                wait_pair_done(p - NW / 2);                              // the pair that read these W slots
+                mbar_expect_tx(ready(p % kPairBars), (uint32_t)n * 2 * kBBytes);
+                for (int j = 0; j < n; ++j) {
+                    const int kb = 2 * p + j, s = kb % NW;
+                    tma_load_2d(sm_wh(s), &map_wh, ready(p % kPairBars), (kb0 + kb) * BK, 0);
+                    tma_load_2d(sm_wl(s), &map_wl, ready(p % kPairBars), (kb0 + kb) * BK, 0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                                 // ===== MMA issuer
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int sw = kb % NW, pw = (kb / NW) & 1, st = kb % NT, pt = (kb / NT) & 1;
+            PROF_DECL;
+            const uint64_t dw0 = kmajor_sw128_desc(sm_wh(0));
+            for (int p = 0; p < n_pairs; ++p) {
+                const int kb = 2 * p;
                 const int chunk = kb / kChunk, b = chunk & 1, first = (kb % kChunk) == 0;
+                PROF(0);
                 if (first) mbar_wait(accfree(b), ((chunk >> 1) & 1) ^ 1);    // accumulator b drained (free at start)
-                mbar_wait(w_full(sw), pw);                               // W tiles landed (async proxy -> this thread)
-                mbar_wait(t_ready(st), pt);                              // A hi/lo of this k-block are in TMEM
+                PROF(1);
+                mbar_wait(ready(p % kPairBars), (p / kPairBars) & 1);    // A hi/lo in TMEM, W tiles in shared memory
+                PROF(2);
                 tc_fence_after();
                 // The W slot holds W_hi (rows 0-63) directly followed by W_lo (rows 64-127): ONE N = 128 MMA gives
                 // a_hi.w_hi (accumulator columns 0-63) and a_hi.w_lo (columns 64-127); a second, N = 64, adds
-                // a_lo.w_hi onto columns 0-63. (Measured: a 128 x 64 x 8 MMA costs ~75 cycles to dispatch, more than
-                // twice its 32-cycle floor, so three N = 64 MMAs per k-step made the issuing thread the bottleneck.)
-                const uint64_t dw = kmajor_sw128_desc(sm_wh(sw));
-                const uint32_t a_hi = tmem_base + kColA + st * 64, a_lo = a_hi + 32;
+                // a_lo.w_hi onto columns 0-63.
                 const uint32_t acc = tmem_base + kColAcc + b * kAccCols;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    tc_mma_tf32_ts(acc, a_hi + 8 * k, dw + 2 * k, kIdesc128, (first && k == 0) ? 0u : 1u);
-                    tc_mma_tf32_ts(acc, a_lo + 8 * k, dw + 2 * k, kIdesc64, 1u);
+                for (int j = 0; j < 2; ++j) {
+                    if (kb + j < nkb) {
+                        const uint64_t dw = dw0 + (uint64_t)((((kb + j) % NW) * 2 * kBBytes) >> 4);
+                        const uint32_t a_hi = tmem_base + kColA + ((kb + j) % NT) * 64, a_lo = a_hi + 32;
+#pragma unroll
+                        for (int k = 0; k < BK / 8; ++k) {
+                            tc_mma_tf32_ts(acc, a_hi + 8 * k, dw + 2 * k, kIdesc128, (first && j == 0 && k == 0) ? 0u : 1u);
+                            tc_mma_tf32_ts(acc, a_lo + 8 * k, dw + 2 * k, kIdesc64, 1u);
+                        }
+                    }
                 }
-                tc_commit(slot_free(st));                                // W slot and TMEM A columns reusable
-                if ((kb % kChunk) == kChunk - 1 || kb == nkb - 1) tc_commit(accfull(b));
+                PROF(3);
+                tc_commit(pair_done(p % kPairBars));                     // TMEM A columns and W slots reusable
+                if ((kb % kChunk) == kChunk - 2 || p == n_pairs - 1) tc_commit(accfull(b));
+                PROF(4);
             }
+            PROF_OUT("mma [other, wait accfree, wait ready, mma issue, commit]");
         }
-    } else {                                                             // ===== splitters + promotion (warps 2-5)
+    } else {                                                             // ===== splitters + promotion (warps 2-9)
+        // Two quartets of splitter warps: quartet s takes k-block 2p + s of pair p. Quartet s also promotes the
+        // chunks with (chunk & 1) == s, i.e. always accumulator s, into its own fp32 sums; the two sums are added
+        // through shared memory at the end (fixed order: deterministic).
         const int q = warp & 3;                                          // the TMEM lane quarter this warp may touch
+        const int set = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         float sum[BN];
@@ -277,9 +322,18 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
             tc_fence_before();
             mbar_arrive(accfree(b));
         };
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int sa = kb % NA, pa = (kb / NA) & 1, st = kb % NT, pt = (kb / NT) & 1;
+        int next_chunk = set;                                            // the next chunk this quartet promotes
+        PROF_DECL;
+        for (int p = 0; p < n_pairs; ++p) {
+            const int kb = 2 * p + set;
+            if (kb >= nkb) {                                             // odd tail: the pair's barrier still counts us
+                mbar_arrive(ready(p % kPairBars));
+                break;
+            }
+            const int sa = kb % NA, pa = (kb / NA) & 1, st = kb % NT;
+            PROF(0);
             mbar_wait(a_full(sa), pa);
+            PROF(1);
             const uint32_t row_addr = sm_a(sa) + row * 128;
             uint32_t hi[32], lo[32];
 #pragma unroll
@@ -298,7 +352,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                 }
             }
             mbar_arrive(a_empty(sa));                                    // the row is in registers: slot back to the TMA
-            mbar_wait(slot_free(st), pt ^ 1);                            // MMAs that read these TMEM columns are done
+            PROF(2);
+            wait_pair_done(p - NT / 2);                                  // MMAs that read these TMEM columns are done
+            PROF(3);
             tc_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -310,17 +366,38 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            mbar_arrive(t_ready(st));
-            // one chunk behind the splitting, so that the wait for the MMA never stalls the A pipeline
-            if ((kb % kChunk) == kChunk - 1 && kb / kChunk >= 1) promote(kb / kChunk - 1);
+            mbar_arrive(ready(p % kPairBars));
+            PROF(4);
+            // Half a chunk behind the MMAs: pair 2 of chunk c+1 got its TMEM columns, so the MMAs of chunk c are
+            // complete and committed — the wait inside promote() returns at once and the issuing thread finds the
+            // accumulator free long before it needs it again (chunk c+2).
+            if ((kb % kChunk) / 2 == kChunk / 4 && next_chunk <= kb / kChunk - 1) {
+                promote(next_chunk);
+                next_chunk += kSplitSets;
+                PROF(5);
+            }
         }
-        const int done = nkb / kChunk >= 1 ? nkb / kChunk - 1 : 0;       // chunks already promoted inside the loop
-        for (int c = done; c < n_chunks; ++c) promote(c);
-        const int m = m0 + row;
-        if (m < M) {
-            float4* out = reinterpret_cast<float4*>(partials + ((size_t)blockIdx.y * M + m) * kHidden);
+        for (; next_chunk < n_chunks; next_chunk += kSplitSets) promote(next_chunk);
+        if (lane == 0 && q == 0) PROF_OUT(set ? "split1 [other, wait a_full, lds+split, wait pair_done, st, promote]" : "split0 [other, wait a_full, lds+split, wait pair_done, st, promote]");
+        // quartet 1 parks its sums in the (drained) A ring, [j][row]; quartet 0 adds them
+        float* xch = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * kSplitSets) : "memory");     // every quartet has read its last tile
+        if (set > 0) {
 #pragma unroll
-            for (int c = 0; c < BN / 4; ++c) out[c] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+            for (int j = 0; j < BN; ++j) xch[((set - 1) * BN + j) * BM + row] = sum[j];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * kSplitSets) : "memory");
+        if (set == 0) {
+#pragma unroll
+            for (int s2 = 1; s2 < kSplitSets; ++s2)
+#pragma unroll
+                for (int j = 0; j < BN; ++j) sum[j] += xch[((s2 - 1) * BN + j) * BM + row];
+            const int m = m0 + row;
+            if (m < M) {
+                float4* out = reinterpret_cast<float4*>(partials + ((size_t)blockIdx.y * M + m) * kHidden);
+#pragma unroll
+                for (int c = 0; c < BN / 4; ++c) out[c] = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
+            }
         }
     }
     tc_fence_before();
