@@ -15,3 +15,15 @@ with torch.no_grad():
         torch.cuda.synchronize()
 for e in prof.key_averages():
     if "k_value" in e.key: print("%-24s %8.1f us" % (e.key.split("::")[-1][:22], e.device_time_total / e.count))
+with torch.no_grad():
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50): net.forward_occupancy(num, time)
+    e1.record(); torch.cuda.synchronize()
+    print("forward, 50 calls back to back: %.1f us per call" % (e0.elapsed_time(e1) * 1000 / 50))
+import time as _t
+with torch.no_grad():
+    torch.cuda.synchronize(); t0 = _t.perf_counter()
+    for _ in range(50): net.forward_occupancy(num, time)
+    t1 = _t.perf_counter(); torch.cuda.synchronize()
+    print("host time to enqueue one forward: %.1f us" % ((t1 - t0) * 1e6 / 50))

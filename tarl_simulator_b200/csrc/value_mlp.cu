@@ -41,12 +41,21 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 32;
-constexpr int kGroup = 2;                              // A tiles requested together (NA must be a multiple)
+#ifndef TARL_VM_GROUP
+#define TARL_VM_GROUP 2
+#endif
+constexpr int kGroup = TARL_VM_GROUP;                              // A tiles requested together (NA must be a multiple)
 // ring depths in k-blocks: A tiles (smem), A hi/lo (TMEM: 2 pairs), W tiles (smem: 3 pairs). The last two are released
 // by the same event (the MMAs of a pair completing) through ONE barrier per pair, pair p on barrier p % kPairBars: a
 // tcgen05.commit costs the issuing thread ~150 cycles (measured), more than a third of the 384-cycle MMA floor of a
 // k-block, so there is exactly one per pair.
-constexpr int NA = 8, NT = 4, NW = 6;
+#ifndef TARL_VM_NA
+#define TARL_VM_NA 8
+#endif
+#ifndef TARL_VM_NW
+#define TARL_VM_NW 6
+#endif
+constexpr int NA = TARL_VM_NA, NT = 4, NW = TARL_VM_NW;
 constexpr int kPairBars = 6;                           // a multiple of NT / 2 and NW / 2, at least their maximum + 1
 constexpr int kHidden = 64;
 constexpr int kSplitSets = 2;                          // splitter warp quartets, k-block kb goes to set kb % kSplitSets
@@ -214,6 +223,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     auto wait_pair_done = [&](int p) { if (p >= 0) mbar_wait(pair_done(p % kPairBars), (p / kPairBars) & 1); };
 
     if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");      // descriptors: kernel parameters
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wl) : "memory");
         for (int s = 0; s < NA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 128); }
         for (int s = 0; s < kPairBars; ++s) { mbar_init(ready(s), 128 * kSplitSets + 1); mbar_init(pair_done(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(accfull(b), 1); mbar_init(accfree(b), 128); }
@@ -228,6 +240,11 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // launched with programmatic stream serialization: barrier init and the TMEM allocation above overlap the drain
+    // of whatever kernel precedes (the previous call's tail kernel in a rollout); its results — the observation, the
+    // split weights, the partial-sum buffer the previous tail still reads — are touched only after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the tail kernel may stage its weights now
 
     if (warp == 0) {
         if (lane == 0) {                                                 // ===== TMA producer, A tiles (HBM)
@@ -283,7 +300,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) k_value_mlp_gemm(const __grid
                         const uint64_t dw = dw0 + (uint64_t)((((kb + j) % NW) * 2 * kBBytes) >> 4);
                         const uint32_t a_hi = tmem_base + kColA + ((kb + j) % NT) * 64, a_lo = a_hi + 32;
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
+                        for (int k = 0; k < BK / 8; ++k) {     // interleaved: 48 cycles per MMA against 64 / 45 back to back
                             tc_mma_tf32_ts(acc, a_hi + 8 * k, dw + 2 * k, kIdesc128, (first && j == 0 && k == 0) ? 0u : 1u);
                             tc_mma_tf32_ts(acc, a_lo + 8 * k, dw + 2 * k, kIdesc64, 1u);
                         }
@@ -425,19 +442,25 @@ __global__ void __launch_bounds__(kTailWarps * 32) k_value_mlp_tail(const float*
                                                                     float* __restrict__ save_z2) {
     __shared__ float s_w2t[kHidden][kHidden + 1];        // [i][j] = W2[j][i]
     __shared__ float s_h1[kTailWarps][kHidden];
+    // launched with programmatic stream serialization behind the GEMM: the weights (which no kernel of the call
+    // writes) are staged while the GEMM's last CTAs drain, the partial sums are touched only after the wait
     for (int i = threadIdx.x; i < kHidden * kHidden; i += blockDim.x) s_w2t[i % kHidden][i / kHidden] = w2[i];
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.x * kTailWarps + warp;
+    const float wt0 = w_time[lane], wt1 = w_time[lane + 32], b1a = b1[lane], b1b = b1[lane + 32];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next call's GEMM may set itself up
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
     if (m >= M) return;
     float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 9
     for (int s = 0; s < n_slices; ++s) {
         const float* p = partials + ((size_t)s * M + m) * kHidden;
         a0 += p[lane];
         a1 += p[lane + 32];
     }
     const float t = time[m * time_stride];
-    const float z1a = a0 + t * w_time[lane] + b1[lane], z1b = a1 + t * w_time[lane + 32] + b1[lane + 32];
+    const float z1a = a0 + t * wt0 + b1a, z1b = a1 + t * wt1 + b1b;
     if (save_z1 != nullptr) { save_z1[(size_t)m * kHidden + lane] = z1a; save_z1[(size_t)m * kHidden + lane + 32] = z1b; }
     s_h1[warp][lane] = fmaxf(z1a, 0.0f);
     s_h1[warp][lane + 32] = fmaxf(z1b, 0.0f);
@@ -640,15 +663,31 @@ int tarl_value_mlp_forward(const float* occupancy, int64_t occ_row_stride, const
     if (!make_map(&map_a, occupancy, n_rows, n_nodes, occ_row_stride, BM) ||
         !make_map(&map_wh, w_hi, kHidden, p.Kp, p.Kp, BN) || !make_map(&map_wl, w_lo, kHidden, p.Kp, p.Kp, BN))
         return TARL_E_LAUNCH;
-    if (cudaFuncSetAttribute(k_value_mlp_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess)
-        return TARL_E_LAUNCH;
+    static const bool smem_ok =                                          // once per process (thread-safe static)
+        cudaFuncSetAttribute(k_value_mlp_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) == cudaSuccess;
+    if (!smem_ok) return TARL_E_LAUNCH;
     const int64_t n_w = (int64_t)kHidden * p.Kp;
     if (weights_changed)
         k_value_mlp_split_w<<<(unsigned)((n_w + 255) / 256), 256, 0, s>>>(w1, n_nodes, p.Kp, w_hi, w_lo, w_time);
-    k_value_mlp_gemm<<<dim3(p.tiles, p.slices), kThreadsGemm, kSmemBytes, s>>>(map_a, map_wh, map_wl, n_rows, p.kb_total,
-                                                                              p.kb_per_slice, partials);
-    k_value_mlp_tail<<<(n_rows + kTailWarps - 1) / kTailWarps, kTailWarps * 32, 0, s>>>(partials, p.slices, n_rows, time, time_stride, w_time, b1, w2, b2,
-                                                          w3, b3, out, save_z1, save_z2);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.tiles, p.slices); cfg.blockDim = dim3(kThreadsGemm);
+        cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_value_mlp_gemm, map_a, map_wh, map_wl, (int)n_rows, (int)p.kb_total, (int)p.kb_per_slice,
+                           partials);
+    }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((n_rows + kTailWarps - 1) / kTailWarps); cfg.blockDim = dim3(kTailWarps * 32);
+        cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_value_mlp_tail, (const float*)partials, (int)p.slices, (int)n_rows, time, time_stride,
+                           (const float*)w_time, b1, w2, b2, w3, b3, out, save_z1, save_z2);
+    }
     return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH;
 }
 

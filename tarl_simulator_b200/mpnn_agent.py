@@ -7,6 +7,7 @@ its backward), csrc/edge_mlp*.cu (the policy's per-edge MLPs); see DESIGN.md.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -24,6 +25,14 @@ _DIJKSTRA_MAX_NODES = 4096      # dense [N,N] distances: impossible (and unused)
 
 def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on_device(device):
+    """torch.cuda.device(device), or nothing at all when it already is the current device (the context manager costs
+    ~10 us of host time per call: more than a sixth of one value-MLP forward)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
 
 
 class _PolicyEmbed(torch.autograd.Function):
@@ -559,6 +568,7 @@ class MPNNValueNetSimple(MessagePassing, Agents):
 
         self._ws = None
         self._ws_key = None
+        self._ws_need = {}                     # rows -> workspace bytes
         self.last_path = None            # "tcgen05" / "tcgen05+pad": how the latest call reached the kernel (tests)
 
     def forward(self, node_features, edge_features, agent_index, time):
@@ -588,13 +598,19 @@ class MPNNValueNetSimple(MessagePassing, Agents):
             num = padded[:, : self.num_nodes]
             self.last_path = "tcgen05+pad"
         l1, l2, l3 = self.final_mlp[0], self.final_mlp[2], self.final_mlp[4]
-        out = _ValueMLP.apply(self, num, tm, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
+        params = (l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias)
+        if not torch.is_grad_enabled() or not any(p.requires_grad for p in params):
+            out = self._launch_forward(num, tm, params)           # rollouts / evaluation: no autograd node (host time)
+        else:
+            out = _ValueMLP.apply(self, num, tm, *params)
         return out.reshape(*lead, 1)
 
     def _launch_forward(self, num, tm, params, z1=None, z2=None):
         M, dev = num.size(0), num.device
         lib = _cabi.lib()
-        need = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
+        need = self._ws_need.get(M)
+        if need is None:
+            need = self._ws_need[M] = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
         w1 = params[0]
         # the workspace keeps the TF32 hi/lo split of W1: redone only when the weight (or the problem shape) changes
         key = (M, w1.data_ptr(), w1._version)
@@ -604,9 +620,9 @@ class MPNNValueNetSimple(MessagePassing, Agents):
         changed = self._ws_key != key
         self._ws_key = key
         ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
-        params = [t.detach().contiguous() for t in params]
+        params = [t if t.is_contiguous() else t.detach().contiguous() for t in params]
         out = torch.empty(M, 1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = lib.tarl_value_mlp_forward(num.data_ptr(), num.stride(0) if M > 1 else (self.num_nodes + 3) // 4 * 4,
                                             tm.data_ptr(), tm.stride(0) if M > 1 else 1,
                                             M, self.num_nodes, *[t.data_ptr() for t in params], int(changed), ws_ptr,
