@@ -658,6 +658,12 @@ def value_mlp_bench(dev, timed, world, peak):
 
         tc_ms = timed(tc, 20)
         lib_ms = timed(lib, 20)
+        # the PPO update evaluates the net on all (T + 1) R frames of a rollout in ONE call: 8192 rows here (1.95 GB)
+        M8 = 8192
+        num8 = torch.randint(0, 12, (M8, N_tot), device=dev, generator=g).float()
+        tm8 = torch.full((M8, 1), 21600.0, device=dev)
+        big_ms = timed(lambda: net.forward_occupancy(num8, tm8), 10)
+        del num8, tm8
     # the PPO update's use of the same net: forward + backward on a 32-frame minibatch (src/rl/ppo_trainer.py:132-145)
     B = 32
     numb, tmb = num[:B].contiguous(), tm[:B].contiguous()
@@ -680,8 +686,8 @@ def value_mlp_bench(dev, timed, world, peak):
     flops = 2 * M * (N_tot + 1) * 64
     return {"metric": "value MLP observation rows/s", "rows": M, "nodes": N_tot,
             "tcgen05": {"value": round(world * M / (tc_ms / 1e3), 1), "ms": round(tc_ms, 4),
-                        "what": "tarl_value_mlp_forward: TMA -> TMEM split -> tcgen05.mma kind::tf32 (3xTF32), split-K, "
-                                "fused 64x64 + 64x1 tail; W1 hi/lo split cached"},
+                        "what": "tarl_value_mlp_forward, calls back to back: TMA -> TMEM split -> tcgen05.mma kind::tf32 "
+                                "(3xTF32), split-K, fused 64x64 + 64x1 tail; W1 hi/lo split cached"},
             "library": {"value": round(world * M / (lib_ms / 1e3), 1), "ms": round(lib_ms, 4),
                         "what": "torch.cat + nn.Linear x3 (cuBLAS fp32 SIMT)"},
             "max_rel_diff_vs_library": rel,
@@ -692,6 +698,10 @@ def value_mlp_bench(dev, timed, world, peak):
                                 "roofline": {"bound": "hbm", "algorithmic_bytes": tr_bytes,
                                              "achieved": round(tr_bytes / (tr_ms / 1e3) / 1e9, 1), "peak": peak,
                                              "unit": "GB/s", "frac": round(tr_bytes / (tr_ms / 1e3) / 1e9 / peak, 4)}},
+            "rows_8192": {"ms": round(big_ms, 4),
+                          "roofline": {"bound": "hbm", "algorithmic_bytes": M8 * N_tot * 4,
+                                       "achieved": round(M8 * N_tot * 4 / (big_ms / 1e3) / 1e9, 1), "peak": peak,
+                                       "unit": "GB/s", "frac": round(M8 * N_tot * 4 / (big_ms / 1e3) / 1e9 / peak, 4)}},
             "roofline": {"bound": "hbm", "algorithmic_bytes": a_bytes, "achieved": round(a_bytes / (tc_ms / 1e3) / 1e9, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(a_bytes / (tc_ms / 1e3) / 1e9 / peak, 4),
                          "useful_tflops": round(flops / (tc_ms / 1e3) / 1e12, 2),

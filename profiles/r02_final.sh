@@ -22,4 +22,7 @@ ncu -i /tmp/emlp_$T.ncu-rep --page raw --csv > /tmp/emlp_raw.csv 2>/dev/null && 
 python profiles/rollout_timeline.py 128 2>&1 | grep -v Warn | tail -20 > gpurun_out/rollout_timeline_${T}_128.txt
 python profiles/rollout_timeline.py 1024 2>&1 | grep -v Warn | tail -20 > gpurun_out/rollout_timeline_${T}_1024.txt
 python profiles/pcie_diag.py
+python profiles/value_mlp_time.py 1024 59600 int 2>&1 | grep 'k_value_mlp\|forward\|host' > gpurun_out/value_mlp_time_$T.txt
+python profiles/value_mlp_time.py 8192 59600 int 2>&1 | grep 'k_value_mlp\|forward\|host' >> gpurun_out/value_mlp_time_$T.txt
+./profiles/micro/mma_rate > gpurun_out/mma_rate_$T.txt 2>&1
 ls -la gpurun_out/*$T* | tail -30
