@@ -95,5 +95,5 @@ int main() {
     long long* out; cudaMallocManaged(&out, 16);
     return run<0>("ts tf32 N=128", out) || run<1>("ts tf32 N=64", out) || run<2>("ts tf32 N=256", out) || run<3>("ss tf32 N=128", out) ||
            run<4>("ts tf32 N=128 / N=64 alternating", out) || run<6>("ts bf16 N=128 K=16", out) || run<7>("ss tf32 N=256", out) ||
-           run<8>("ts tf32 N=128 two accumulators", out) || run<9>("ts tf32 N=128 / N=64, commit per 8 (unwaited)", out);
+           run<8>("ts tf32 N=128 two accumulators", out);
 }
