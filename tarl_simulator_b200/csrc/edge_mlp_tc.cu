@@ -190,6 +190,44 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_mlp_tc(const int32_t* __re
 
     const int tiles_per_row = (E + kTile - 1) / kTile;
     const long long n_tiles = (long long)tiles_per_row * B;
+    // Worker threads run their gathers ahead of the tile they feed to the tensor core: the edge's two node ids two tiles
+    // ahead, the 34 inputs (two dependent load levels behind the ids) one tile ahead — requested right after this tile's
+    // A1 went to TMEM, in flight while the thread waits for the MMAs and folds D1 / D2. Without it every tile began
+    // with ~1.5 us of exposed gather latency and an SM had two tiles (one per CTA) to hide it with.
+    struct Ids { int b, e, s, d; bool live; };
+    auto load_ids = [&](long long tile) {
+        Ids r = {0, 0, 0, 0, false};
+        if (tile < n_tiles) {
+            r.b = (int)(tile / tiles_per_row);
+            r.e = (int)(tile - (long long)r.b * tiles_per_row) * kTile + (int)threadIdx.x;
+            r.live = r.e < E;
+            if (r.live) { r.s = src[r.e]; r.d = dst[r.e]; }
+        }
+        return r;
+    };
+    auto gather = [&](const Ids& id, float (&a)[kK1]) {      // A1 = [x_i | x_j | attr | 1 | 0 ...]
+#pragma unroll
+        for (int c = 0; c < kK1; ++c) a[c] = 0.0f;
+        if (id.live) {
+            const float4* xi = reinterpret_cast<const float4*>(x + id.b * x_bs + (int64_t)id.s * kX);
+            const float4* xj = reinterpret_cast<const float4*>(x + id.b * x_bs + (int64_t)id.d * kX);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 u = xi[q], v = xj[q];
+                a[4 * q] = u.x; a[4 * q + 1] = u.y; a[4 * q + 2] = u.z; a[4 * q + 3] = u.w;
+                a[kX + 4 * q] = v.x; a[kX + 4 * q + 1] = v.y; a[kX + 4 * q + 2] = v.z; a[kX + 4 * q + 3] = v.w;
+            }
+            a[32] = ea[id.b * ea_bs + id.e];
+            a[33] = 1.0f;
+        }
+    };
+    Ids id_cur = {0, 0, 0, 0, false}, id_next = id_cur;
+    float a[kK1];
+    if (warp < 4) {
+        id_cur = load_ids(blockIdx.x);
+        id_next = load_ids((long long)blockIdx.x + gridDim.x);
+        gather(id_cur, a);
+    }
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
@@ -217,26 +255,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_mlp_tc(const int32_t* __re
             continue;
         }
         // ===== worker warps: thread r <-> pair r of the tile <-> TMEM lane r
-        const int b = (int)(tile / tiles_per_row);
-        const int e = (int)(tile - (long long)b * tiles_per_row) * kTile + (int)threadIdx.x;
-        const bool live = e < E;
+        const int b = id_cur.b, e = id_cur.e;
+        const bool live = id_cur.live;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        {   // A1 = [x_i | x_j | attr | 1 | 0 ...] split hi / lo, 40 + 40 columns
-            float a[kK1];
-#pragma unroll
-            for (int c = 0; c < kK1; ++c) a[c] = 0.0f;
-            if (live) {
-                const float4* xi = reinterpret_cast<const float4*>(x + b * x_bs + (int64_t)src[e] * kX);
-                const float4* xj = reinterpret_cast<const float4*>(x + b * x_bs + (int64_t)dst[e] * kX);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 u = xi[q], v = xj[q];
-                    a[4 * q] = u.x; a[4 * q + 1] = u.y; a[4 * q + 2] = u.z; a[4 * q + 3] = u.w;
-                    a[kX + 4 * q] = v.x; a[kX + 4 * q + 1] = v.y; a[kX + 4 * q + 2] = v.z; a[kX + 4 * q + 3] = v.w;
-                }
-                a[32] = ea[b * ea_bs + e];
-                a[33] = 1.0f;
-            }
+        {   // A1 split hi / lo, 40 + 40 columns
 #pragma unroll
             for (int c8 = 0; c8 < kK1 / 8; ++c8) {
                 uint32_t hi[8], lo[8];
@@ -253,6 +275,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_edge_mlp_tc(const int32_t* __re
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         mbar_arrive(a1_ready);
+        id_cur = id_next;                                                // the next tile's inputs: requested now
+        id_next = load_ids(tile + 2 * (long long)gridDim.x);
+        gather(id_cur, a);
         // h1 = relu(D1[:, 0:64] + D1[:, 64:128]) -> A2 hi / lo (64 + 64 columns, over the A1 columns: layer 1 is through)
         mbar_wait(d1_full, ph);
         tc_fence_after();
