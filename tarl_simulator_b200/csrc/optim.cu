@@ -95,11 +95,21 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(float* __restrict__ p, co
     if (threadIdx.x == 0 && norm_partials != nullptr) norm_partials[blockIdx.x] = sm[0];
 }
 
-__global__ void k_norm_finish(const double* __restrict__ partials, int n, float* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// One CTA: thread i sums partials i, i + 256, ... in that order, then a fixed tree over the 256 sums — the same result
+// on every rank and every run. (A single thread walking the ~3 800 partials of the grid100 nets one dependent load after
+// the other took 100 us, three times the Adam pass itself.)
+__global__ void __launch_bounds__(kAdamThreads) k_norm_finish(const double* __restrict__ partials, int n,
+                                                              float* __restrict__ out) {
+    __shared__ double sm[kAdamThreads];
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s += partials[i];
-    *out = (float)sqrt(s);
+    for (int i = threadIdx.x; i < n; i += kAdamThreads) s += partials[i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = kAdamThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = (float)sqrt(sm[0]);
 }
 
 inline int status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
@@ -148,7 +158,7 @@ int tarl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
     cudaStream_t cs = static_cast<cudaStream_t>(stream);
     k_adam<<<ctas, kAdamThreads, 0, cs>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1),
                                           (float)sqrt(bc2), grad_scale, norm_partials);
-    if (grad_norm != nullptr) k_norm_finish<<<1, 32, 0, cs>>>(norm_partials, ctas, grad_norm);
+    if (grad_norm != nullptr) k_norm_finish<<<1, kAdamThreads, 0, cs>>>(norm_partials, ctas, grad_norm);
     return status();
 }
 

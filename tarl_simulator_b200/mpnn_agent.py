@@ -613,7 +613,7 @@ class MPNNValueNetSimple(MessagePassing, Agents):
             need = self._ws_need[M] = lib.tarl_value_mlp_workspace_bytes(M, self.num_nodes)
         w1 = params[0]
         # the workspace keeps the TF32 hi/lo split of W1: redone only when the weight (or the problem shape) changes
-        key = (M, w1.data_ptr(), w1._version)
+        key = (w1.data_ptr(), w1._version)     # (the split sits at the head of the workspace, wherever M puts the rest)
         if self._ws is None or self._ws.numel() < need + 1024 or self._ws.device != dev:
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
             self._ws_key = None
