@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 26
+#define TARL_ABI_VERSION 27
 
 /* return codes */
 #define TARL_OK 0
@@ -609,6 +609,22 @@ int tarl_gae(const float* value, const float* next_value, int64_t value_step_str
 /* advantage <- (advantage - mean) / max(std, 1e-4) with the unbiased std, from stats = {count, sum, sum of squares}
  * (device doubles: no host round trip between the reduction and its use). */
 int tarl_standardise(float* advantage, int64_t n, const double* stats, void* stream);
+
+/* ClipPPOLoss as the reference wires it (src/rl/ppo_trainer.py:36: torchrl 0.5.0 ClipPPOLoss, clip_epsilon 0.2,
+ * entropy_coef 0.01, critic_coef 1.0, loss_critic_type "smooth_l1", normalize_advantage False) for the n frames of one
+ * minibatch, forward and backward in one launch — what the update loop evaluates at :135-139 (loss.backward() included):
+ *   ratio = exp(log_prob - sample_log_prob)
+ *   loss_objective = -mean(min(ratio A, clamp(ratio, 1 - clip, 1 + clip) A))
+ *   loss_entropy = -entropy_coef mean(entropy);   loss_critic = critic_coef mean(smooth_l1(value - value_target))
+ * out[6] = {loss_objective, loss_entropy, loss_critic, approx_kl = mean(sample_log_prob - log_prob),
+ *           clip_fraction = mean(|ratio - 1| > clip), entropy = mean(entropy)}.
+ * grad_log_prob / grad_entropy / grad_value [n]: gradient of loss_objective + loss_critic + loss_entropy with respect
+ * to the three differentiable inputs (torch's subgradient conventions: minimum splits ties, clamp passes the gradient
+ * on its closed interval). All arrays contiguous fp32 on the device; n >= 1. */
+int tarl_ppo_clip_loss(const float* log_prob, const float* sample_log_prob, const float* advantage, const float* entropy,
+                       const float* value, const float* value_target, int32_t n, double clip_epsilon, float entropy_coef,
+                       float critic_coef, float* out, float* grad_log_prob, float* grad_entropy, float* grad_value,
+                       void* stream);
 
 /* One torch.optim.Adam step (src/rl/ppo_trainer.py:39,142: lr 1e-3, betas 0.9 / 0.999, eps 1e-8, no weight decay) over
  * a flat fp32 bucket of n parameters — the bucket the gradient all-reduce works on. step: 1 for the first update.

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 26       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 27       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
@@ -160,6 +160,7 @@ SIGNATURES = {
     "tarl_gae_partial_count": (_I32, [_I32]),
     "tarl_gae": (C.c_int, [_P, _P, _I64, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P]),
     "tarl_standardise": (C.c_int, [_P, _I64, _P, _P]),
+    "tarl_ppo_clip_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, C.c_double, _F, _F, _P, _P, _P, _P, _P]),
     "tarl_adam_partial_count": (_I32, [_I64]),
     "tarl_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P, _P, _P]),
     "tarl_value_mlp_workspace_bytes": (_SZ, [_I32, _I32]),

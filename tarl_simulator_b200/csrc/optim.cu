@@ -112,6 +112,68 @@ __global__ void __launch_bounds__(kAdamThreads) k_norm_finish(const double* __re
     if (threadIdx.x == 0) *out = (float)sqrt(sm[0]);
 }
 
+// torchrl 0.5.0 ClipPPOLoss with the reference's settings (/root/reference/src/rl/ppo_trainer.py:36,135-139: clip 0.2,
+// entropy bonus 0.01, critic coefficient 1.0 with smooth-L1, advantages as given), forward AND the gradient of
+// loss_objective + loss_critic + loss_entropy with respect to log_prob, entropy and value, for the n frames of one
+// minibatch: one CTA, one launch, where the torch formula is ~40 launches of n-element kernels.
+//   ratio = exp(lp - lp_old); objective = -mean(min(ratio A, clamp(ratio, 1 - c, 1 + c) A))
+//   d objective / d lp = -(1/n) ratio A where the unclipped term is the smaller one (or both are the same term), else 0
+//   critic = coef mean(smooth_l1(v - target)), d/dv = coef (|d| < 1 ? d : sign d) / n;  entropy loss = -c_e mean(H)
+// out = {loss_objective, loss_entropy, loss_critic, approx_kl, clip_fraction, entropy}. Sums in fp64 over a fixed
+// thread-strided order and a fixed tree: deterministic.
+constexpr int kLossThreads = 256;
+__global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __restrict__ lp, const float* __restrict__ lp_old,
+                                                                const float* __restrict__ adv, const float* __restrict__ ent,
+                                                                const float* __restrict__ val, const float* __restrict__ tgt,
+                                                                int n, float lo, float hi, float clip, float ent_coef,
+                                                                float critic_coef, float* __restrict__ out,
+                                                                float* __restrict__ g_lp, float* __restrict__ g_ent,
+                                                                float* __restrict__ g_val) {
+    __shared__ double sm[5][kLossThreads];
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const float inv_n = 1.0f / (float)n;
+    for (int i = threadIdx.x; i < n; i += kLossThreads) {
+        const float lw = lp[i] - lp_old[i];
+        const float ratio = expf(lw);
+        const float a = adv[i];
+        const float clamped = fminf(fmaxf(ratio, lo), hi);
+        const float g1 = ratio * a, g2 = clamped * a;
+        const bool inside = (ratio >= lo) && (ratio <= hi);         // clamp passes the gradient on its closed interval
+        // torch.minimum splits the gradient evenly on ties; g2's own derivative is ratio A inside the interval, 0 outside
+        float w = 0.0f;
+        if (g1 < g2) w = 1.0f;
+        else if (g1 == g2) w = inside ? 1.0f : 0.5f;
+        else w = 0.0f;                                              // g2 < g1 happens only outside the interval
+        g_lp[i] = -inv_n * (w * g1);
+        g_ent[i] = -ent_coef * inv_n;
+        const float d = val[i] - tgt[i], ad = fabsf(d);
+        g_val[i] = critic_coef * inv_n * (ad < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f));
+        acc[0] += (double)fminf(g1, g2);
+        acc[1] += (double)ent[i];
+        acc[2] += (double)(ad < 1.0f ? 0.5f * d * d : ad - 0.5f);
+        acc[3] += (double)(-lw);
+        acc[4] += (fabsf(ratio - 1.0f) > clip) ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int off = kLossThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double m = 1.0 / (double)n;
+        out[0] = (float)(-sm[0][0] * m);
+        out[1] = (float)(-(double)ent_coef * sm[1][0] * m);
+        out[2] = (float)((double)critic_coef * sm[2][0] * m);
+        out[3] = (float)(sm[3][0] * m);
+        out[4] = (float)(sm[4][0] * m);
+        out[5] = (float)(sm[1][0] * m);
+    }
+}
+
 inline int status() { return cudaGetLastError() == cudaSuccess ? TARL_OK : TARL_E_LAUNCH; }
 
 }  // namespace
@@ -159,6 +221,23 @@ int tarl_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
     k_adam<<<ctas, kAdamThreads, 0, cs>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, (float)((double)lr / bc1),
                                           (float)sqrt(bc2), grad_scale, norm_partials);
     if (grad_norm != nullptr) k_norm_finish<<<1, kAdamThreads, 0, cs>>>(norm_partials, ctas, grad_norm);
+    return status();
+}
+
+int tarl_ppo_clip_loss(const float* log_prob, const float* sample_log_prob, const float* advantage, const float* entropy,
+                       const float* value, const float* value_target, int32_t n, double clip_epsilon, float entropy_coef,
+                       float critic_coef, float* out, float* grad_log_prob, float* grad_entropy, float* grad_value,
+                       void* stream) {
+    if (n < 1) return TARL_E_BADARG;             // the mean over an empty minibatch is not a number
+    if (!log_prob || !sample_log_prob || !advantage || !entropy || !value || !value_target || !out || !grad_log_prob ||
+        !grad_entropy || !grad_value)
+        return TARL_E_BADARG;
+    // the interval bounds as torch forms them: Python doubles, rounded to fp32 when they meet the tensor
+    const float lo = (float)(1.0 - clip_epsilon), hi = (float)(1.0 + clip_epsilon);
+    k_ppo_clip_loss<<<1, kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        log_prob, sample_log_prob, advantage, entropy, value, value_target, n, lo, hi, (float)clip_epsilon, entropy_coef,
+        critic_coef,
+        out, grad_log_prob, grad_entropy, grad_value);
     return status();
 }
 

@@ -152,7 +152,8 @@ def gae_device(v_frames, reward, done, terminated=None, gamma=0.99, lmbda=0.95, 
 
 def clip_ppo_loss(log_prob, sample_log_prob, advantage, entropy, value, value_target, clip_epsilon=0.2,
                   entropy_coef=0.01, critic_coef=1.0):
-    """torchrl 0.5.0 ClipPPOLoss.forward with the reference's settings."""
+    """torchrl 0.5.0 ClipPPOLoss.forward with the reference's settings, in plain torch: the specification of
+    tarl_ppo_clip_loss (tests) — ppo_train uses clip_ppo_loss_device."""
     log_weight = log_prob - sample_log_prob
     ratio = log_weight.exp()
     gain1 = ratio * advantage
@@ -167,6 +168,56 @@ def clip_ppo_loss(log_prob, sample_log_prob, advantage, entropy, value, value_ta
         out["clip_fraction"] = ((ratio - 1.0).abs() > clip_epsilon).float().mean()
         out["entropy"] = entropy.mean()
     return out
+
+
+class _ClipLoss(torch.autograd.Function):
+    """tarl_ppo_clip_loss behind autograd: forward leaves the six scalars and the three gradient vectors of
+    loss_objective + loss_critic + loss_entropy; backward scales them by the incoming gradient of the total."""
+
+    @staticmethod
+    def forward(ctx, log_prob, entropy, value, sample_log_prob, advantage, value_target, clip, ent_coef, critic_coef):
+        dev, n = log_prob.device, log_prob.numel()
+        f32 = lambda x: x.detach().reshape(-1).to(torch.float32).contiguous()
+        lp, ent, val = f32(log_prob), f32(entropy), f32(value)
+        slp, adv, tgt = f32(sample_log_prob), f32(advantage), f32(value_target)
+        if not (ent.numel() == val.numel() == slp.numel() == adv.numel() == tgt.numel() == n):
+            raise ValueError("clip_ppo_loss_device: the six inputs must hold one element per frame")
+        out = torch.empty(6, dtype=torch.float32, device=dev)
+        grads = torch.empty(3, n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _cabi.lib().tarl_ppo_clip_loss(lp.data_ptr(), slp.data_ptr(), adv.data_ptr(), ent.data_ptr(), val.data_ptr(),
+                                                tgt.data_ptr(), n, float(clip), float(ent_coef), float(critic_coef),
+                                                out.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(),
+                                                grads[2].data_ptr(), _stream(dev))
+        _cabi.check(rc, "tarl_ppo_clip_loss")
+        ctx.save_for_backward(grads)
+        ctx.shapes = (log_prob.shape, entropy.shape, value.shape)
+        total = out[0] + out[2] + out[1]          # objective + critic + entropy, the order of src/rl/ppo_trainer.py:136-138
+        ctx.mark_non_differentiable(out)
+        return total, out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_out):
+        (grads,) = ctx.saved_tensors
+        s0, s1, s2 = ctx.shapes
+        g = grads * g_total
+        return g[0].reshape(s0), g[1].reshape(s1), g[2].reshape(s2), None, None, None, None, None, None
+
+
+def clip_ppo_loss_device(log_prob, sample_log_prob, advantage, entropy, value, value_target, clip_epsilon=0.2,
+                         entropy_coef=0.01, critic_coef=1.0):
+    """clip_ppo_loss on the device in ONE launch (tarl_ppo_clip_loss, csrc/optim.cu) — forward and the gradient with
+    respect to log_prob, entropy and value. Returns the same dict plus "loss" = loss_objective + loss_critic +
+    loss_entropy, the only entry that carries a gradient (the reference differentiates exactly that sum,
+    src/rl/ppo_trainer.py:136-139)."""
+    if not log_prob.is_cuda:
+        raise RuntimeError("clip_ppo_loss_device computes on CUDA devices only (clip_ppo_loss is the plain-torch formula)")
+    total, out = _ClipLoss.apply(log_prob, entropy, value, sample_log_prob, advantage, value_target, clip_epsilon,
+                                 entropy_coef, critic_coef)
+    names = ("loss_objective", "loss_entropy", "loss_critic", "approx_kl", "clip_fraction", "entropy")
+    res = {k: out[i] for i, k in enumerate(names)}
+    res["loss"] = total
+    return res
 
 
 def reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
@@ -693,14 +744,22 @@ def ppo_train(env, policy_module, value_module, *, total_frames=128, frames_per_
             n = min(sub_batch_size, T * R)
             pick = torch.randperm(T * R, generator=gen, device=dev)[:n]
             ti, ri = pick // R, pick % R
-            flat = lambda x: None if x is None else x[ti, ri]     # gathers n frames whatever the strides of the trajectory
+
+            def flat(x):          # n frames of a [T, R, ...] trajectory array, whatever its strides
+                if x is None:
+                    return None
+                if x.is_contiguous():     # rows of the [T R, ...] view: one vectorised row gather
+                    return x.reshape(T * R, *x.shape[2:]).index_select(0, pick)
+                return x[ti, ri]
+
             obs = adapter.observation(flat(batch["num"]), flat(batch["sel"]), flat(batch["agent_index"]), flat(batch["time"]))
             d = policy_module.dist(obs)
             log_prob = d.log_prob(flat(batch["action"]))
             entropy = d.entropy()
             v = value_module(obs).reshape(n)
-            losses = clip_ppo_loss(log_prob, flat(batch["sample_log_prob"]), flat(adv), entropy, v, flat(target))
-            loss = losses["loss_objective"] + losses["loss_critic"] + losses["loss_entropy"]
+            # ClipPPOLoss forward + backward as one launch
+            losses = clip_ppo_loss_device(log_prob, flat(batch["sample_log_prob"]), flat(adv), entropy, v, flat(target))
+            loss = losses.pop("loss")
             loss.backward()
             optim.check_views()
             grad_norm = optim.step().clone()          # all-reduce + averaged-gradient norm + Adam: one launch

@@ -1,6 +1,6 @@
 """The device side of the PPO iteration (csrc/optim.cu, the captured rollout, the per-rank noise streams) against its
-plain-torch specification: tarl_gae / tarl_standardise vs gae_host / standardise_host, tarl_adam_step vs
-torch.optim.Adam on the same gradients, a rollout replayed from its CUDA graph vs the same rollout launched eagerly,
+plain-torch specification: tarl_gae / tarl_standardise vs gae_host / standardise_host, tarl_ppo_clip_loss vs
+clip_ppo_loss under torch autograd, tarl_adam_step vs torch.optim.Adam on the same gradients, a rollout replayed from its CUDA graph vs the same rollout launched eagerly,
 and two shards of one job drawing different actions from one seed (every rank sampled the same actions)."""
 import os
 
@@ -48,6 +48,41 @@ def test_gae_kernel_matches_the_torch_formula(T, R):
     scale = float(target_ref.abs().max())
     assert torch.allclose(target.cpu(), target_ref, rtol=1e-5, atol=1e-5 * scale)
     assert torch.allclose(adv.cpu(), std_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n", [1, 32, 1000])
+def test_clip_loss_kernel_matches_the_torch_formula_and_its_autograd(n):
+    """Forward scalars and the gradient of loss_objective + loss_critic + loss_entropy w.r.t. log_prob, entropy and
+    value: ratios on both sides of the clip interval with advantages of both signs (the four min / clamp regimes),
+    value errors on both sides of smooth-L1's |d| = 1, and a non-unit upstream gradient. Tolerance: 1e-5 relative,
+    1e-7 absolute (both sum n products of the same fp32 terms, in different orders)."""
+    from tarl_simulator_b200.rl import ppo_trainer as P
+    g = torch.Generator().manual_seed(n)
+    slp = -torch.rand(n, generator=g) * 3
+    lp0 = slp + torch.randn(n, generator=g) * 0.3              # ratios from ~0.4 to ~2.5: inside and outside [0.8, 1.2]
+    adv = torch.randn(n, generator=g)
+    ent0 = torch.rand(n, generator=g) * 2
+    tgt = torch.randn(n, generator=g) * 3
+    v0 = tgt + torch.randn(n, generator=g) * 1.5               # |v - target| below and above 1
+    if n >= 4:
+        lp0[0] = slp[0]; adv[1] = 0.0; v0[2] = tgt[2]; lp0[3] = slp[3] + 5.0     # ratio == 1, A == 0, d == 0, ratio >> 1
+    outs = []
+    for fn in (P.clip_ppo_loss, P.clip_ppo_loss_device):
+        lp, ent, v = (x.clone().cuda().requires_grad_(True) for x in (lp0, ent0, v0))
+        res = fn(lp, slp.cuda(), adv.cuda(), ent, v, tgt.cuda())
+        total = res["loss"] if "loss" in res else res["loss_objective"] + res["loss_critic"] + res["loss_entropy"]
+        (total * 1.7).backward()
+        outs.append(({k: res[k].detach().cpu() for k in ("loss_objective", "loss_entropy", "loss_critic", "approx_kl",
+                                                          "clip_fraction", "entropy")},
+                     total.detach().cpu(), [x.grad.cpu() for x in (lp, ent, v)]))
+    (ref, ref_total, ref_g), (our, our_total, our_g) = outs
+    for k in ref:
+        assert torch.allclose(our[k], ref[k], rtol=1e-5, atol=1e-7), k
+    assert torch.allclose(our_total, ref_total, rtol=1e-5, atol=1e-7)
+    for a, b, name in zip(our_g, ref_g, ("log_prob", "entropy", "value")):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-9), name
+    with pytest.raises(RuntimeError):
+        P.clip_ppo_loss_device(lp0, slp, adv, ent0, v0, tgt)                     # CPU tensors: no fallback
 
 
 def test_flat_adam_matches_torch_adam():
