@@ -616,8 +616,14 @@ int tarl_standardise(float* advantage, int64_t n, const double* stats, void* str
  *   ratio = exp(log_prob - sample_log_prob)
  *   loss_objective = -mean(min(ratio A, clamp(ratio, 1 - clip, 1 + clip) A))
  *   loss_entropy = -entropy_coef mean(entropy);   loss_critic = critic_coef mean(smooth_l1(value - value_target))
- * out[6] = {loss_objective, loss_entropy, loss_critic, approx_kl = mean(sample_log_prob - log_prob),
- *           clip_fraction = mean(|ratio - 1| > clip), entropy = mean(entropy)}.
+ * out[7] = {loss_objective, loss_entropy, loss_critic, approx_kl = mean(sample_log_prob - log_prob),
+ *           clip_fraction = mean(|ratio - 1| > clip), entropy = mean(entropy), number of impossible frames}.
+ * An "impossible" frame is one whose log_prob AND sample_log_prob are both -inf — GraphDistribution.log_prob's marker
+ * for an action that selects no edge in some group (src/reinforcement_learning.py:82-93), which sample() (:57-80)
+ * produces about once in 10^7 draws. Its ratio exp(-inf - -inf) is NaN in the torch formula and poisons every
+ * parameter at the next optimiser step; here it contributes nothing to the objective, approx_kl and clip_fraction
+ * (zero gradient w.r.t. its log_prob), still counts in the critic and entropy terms and in every denominator (declared
+ * divergence D8). Any other non-finite input propagates as in torch.
  * grad_log_prob / grad_entropy / grad_value [n]: gradient of loss_objective + loss_critic + loss_entropy with respect
  * to the three differentiable inputs (torch's subgradient conventions: minimum splits ties, clamp passes the gradient
  * on its closed interval). All arrays contiguous fp32 on the device; n >= 1. */

@@ -16,6 +16,7 @@ env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=100)
 policy = MPNNPolicyNet(g.edge_index, g.x.size(0), None, "cuda")
 pm = PolicyModule(policy, g.edge_index)
 ad = _EnvAdapter.of(env)
+torch.manual_seed(0)         # the rollouts' noise keys come from torch's CPU generator: same draws in every run
 for _ in range(4):
     collect(ad, pm, 32, occupancy_only=True)
 torch.cuda.synchronize()
@@ -36,3 +37,9 @@ print(f"kernel time in one collect: {total / 1e3:.3f} ms")
 for e in rows[:16]:
     m = re.search(r"(k_\w+|Memcpy\w*|Memset\w*|\w+Functor\w*|\w+_kernel\w*)", e.key)
     print(f"  {(m.group(1) if m else e.key[:40]):36s} {e.self_device_time_total / max(e.count, 1):8.1f} us x{e.count:3d} = {e.self_device_time_total / 1e3:7.3f} ms")
+b = collect(ad, pm, 32, occupancy_only=True)
+torch.cuda.synchronize()
+env.check_errors()
+# same numbers whatever the schedule (TARL_ROLLOUT_DRAW_AT, TARL_ROLLOUT_SIDE_PRIORITY, TARL_NO_ROLLOUT_OVERLAP)
+print("checksum: num %.1f action %d log_prob %.6f reward %.1f" % (float(b["num"].double().sum()), int(b["action"].sum()),
+      float(b["sample_log_prob"].double().sum()), float(b["reward"].double().sum())))

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kAdamThreads) k_norm_finish(const double* __re
 //   ratio = exp(lp - lp_old); objective = -mean(min(ratio A, clamp(ratio, 1 - c, 1 + c) A))
 //   d objective / d lp = -(1/n) ratio A where the unclipped term is the smaller one (or both are the same term), else 0
 //   critic = coef mean(smooth_l1(v - target)), d/dv = coef (|d| < 1 ? d : sign d) / n;  entropy loss = -c_e mean(H)
-// out = {loss_objective, loss_entropy, loss_critic, approx_kl, clip_fraction, entropy}. Sums in fp64 over a fixed
+// out = {loss_objective, loss_entropy, loss_critic, approx_kl, clip_fraction, entropy, #impossible frames}. Sums in fp64 over a fixed
 // thread-strided order and a fixed tree: deterministic.
 constexpr int kLossThreads = 256;
 __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __restrict__ lp, const float* __restrict__ lp_old,
@@ -129,13 +129,21 @@ __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __r
                                                                 float critic_coef, float* __restrict__ out,
                                                                 float* __restrict__ g_lp, float* __restrict__ g_ent,
                                                                 float* __restrict__ g_val) {
-    __shared__ double sm[5][kLossThreads];
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    __shared__ double sm[6][kLossThreads];
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const float inv_n = 1.0f / (float)n;
     for (int i = threadIdx.x; i < n; i += kLossThreads) {
-        const float lw = lp[i] - lp_old[i];
+        // GraphDistribution.log_prob marks an action that selects no edge in some group as impossible: -inf
+        // (/root/reference/src/reinforcement_learning.py:82-93), and its sample() produces such an action whenever a
+        // group's uniform is not below the group's last cumulative probability (:57-80) — about one draw in 10^7. On the
+        // reference's test networks that never happens; over the 2.4 10^8 draws of one 128-replica grid100 rollout it
+        // happens about ten times, the frame's ratio exp(-inf - -inf) is NaN and one optimiser step later so is every
+        // parameter. Such a frame (BOTH log-probabilities -inf, nothing else) takes no part in the objective; it still
+        // counts in the critic and entropy terms and in every mean's denominator; out[6] counts them.
+        const bool impossible = (lp[i] == -INFINITY) && (lp_old[i] == -INFINITY);
+        const float lw = impossible ? 0.0f : lp[i] - lp_old[i];
         const float ratio = expf(lw);
-        const float a = adv[i];
+        const float a = impossible ? 0.0f : adv[i];
         const float clamped = fminf(fmaxf(ratio, lo), hi);
         const float g1 = ratio * a, g2 = clamped * a;
         const bool inside = (ratio >= lo) && (ratio <= hi);         // clamp passes the gradient on its closed interval
@@ -153,14 +161,15 @@ __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __r
         acc[2] += (double)(ad < 1.0f ? 0.5f * d * d : ad - 0.5f);
         acc[3] += (double)(-lw);
         acc[4] += (fabsf(ratio - 1.0f) > clip) ? 1.0 : 0.0;
+        acc[5] += impossible ? 1.0 : 0.0;
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] = acc[k];
+    for (int k = 0; k < 6; ++k) sm[k][threadIdx.x] = acc[k];
     __syncthreads();
     for (int off = kLossThreads / 2; off > 0; off >>= 1) {
         if (threadIdx.x < off)
 #pragma unroll
-            for (int k = 0; k < 5; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
+            for (int k = 0; k < 6; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + off];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -171,6 +180,7 @@ __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __r
         out[3] = (float)(sm[3][0] * m);
         out[4] = (float)(sm[4][0] * m);
         out[5] = (float)(sm[1][0] * m);
+        out[6] = (float)sm[5][0];
     }
 }
 

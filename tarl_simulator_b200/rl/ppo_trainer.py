@@ -182,7 +182,7 @@ class _ClipLoss(torch.autograd.Function):
         slp, adv, tgt = f32(sample_log_prob), f32(advantage), f32(value_target)
         if not (ent.numel() == val.numel() == slp.numel() == adv.numel() == tgt.numel() == n):
             raise ValueError("clip_ppo_loss_device: the six inputs must hold one element per frame")
-        out = torch.empty(6, dtype=torch.float32, device=dev)
+        out = torch.empty(7, dtype=torch.float32, device=dev)
         grads = torch.empty(3, n, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             rc = _cabi.lib().tarl_ppo_clip_loss(lp.data_ptr(), slp.data_ptr(), adv.data_ptr(), ent.data_ptr(), val.data_ptr(),
@@ -209,12 +209,15 @@ def clip_ppo_loss_device(log_prob, sample_log_prob, advantage, entropy, value, v
     """clip_ppo_loss on the device in ONE launch (tarl_ppo_clip_loss, csrc/optim.cu) — forward and the gradient with
     respect to log_prob, entropy and value. Returns the same dict plus "loss" = loss_objective + loss_critic +
     loss_entropy, the only entry that carries a gradient (the reference differentiates exactly that sum,
-    src/rl/ppo_trainer.py:136-139)."""
+    src/rl/ppo_trainer.py:136-139) — and "impossible_frames": how many frames of the minibatch carry GraphDistribution's
+    -inf marker in both log-probabilities (an action without an edge in some group, about one draw in 10^7). The torch
+    formula turns such a frame into a NaN loss and, one Adam step later, NaN parameters; the kernel leaves it out of
+    the objective (declared divergence D8, include/tarl_b200.h)."""
     if not log_prob.is_cuda:
         raise RuntimeError("clip_ppo_loss_device computes on CUDA devices only (clip_ppo_loss is the plain-torch formula)")
     total, out = _ClipLoss.apply(log_prob, entropy, value, sample_log_prob, advantage, value_target, clip_epsilon,
                                  entropy_coef, critic_coef)
-    names = ("loss_objective", "loss_entropy", "loss_critic", "approx_kl", "clip_fraction", "entropy")
+    names = ("loss_objective", "loss_entropy", "loss_critic", "approx_kl", "clip_fraction", "entropy", "impossible_frames")
     res = {k: out[i] for i, k in enumerate(names)}
     res["loss"] = total
     return res
@@ -367,7 +370,9 @@ class _EnvAdapter:
 
     def side_stream(self):
         if self._side is None:
-            self._side = torch.cuda.Stream(self.device)
+            # TARL_ROLLOUT_SIDE_PRIORITY=1 (tuning): the draws' CTAs are dispatched ahead of the main stream's
+            prio = -1 if os.environ.get("TARL_ROLLOUT_SIDE_PRIORITY") else 0
+            self._side = torch.cuda.Stream(self.device, priority=prio)
         return self._side
 
     def trajectory_buffers(self, T: int, slim: bool):
@@ -582,6 +587,10 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
             env.sync_sel_pairs()
             side.wait_stream(main)
             core_done = [None] * n
+            step_done = [None] * n
+            # TARL_ROLLOUT_DRAW_AT=step (tuning): release draw t when step t-2 — the last reader of its pair — is
+            # through, i.e. next to the whole of step t-1 instead of next to its insertion only
+            early = os.environ.get("TARL_ROLLOUT_DRAW_AT") == "step"
 
             def mark_core(t):
                 def mark():
@@ -594,7 +603,9 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                 with torch.cuda.stream(side):
                     # not before the core step of step t-1 is through: that is when the device starts to idle (and
                     # step t-2, the last reader of this pair, finished long before)
-                    if t >= 1:
+                    if early and t >= 2:
+                        side.wait_event(step_done[t - 2])
+                    elif not early and t >= 1:
                         side.wait_event(core_done[t - 1])
                     sink.retarget(cur[0][: R * N_links].view(R, N_links), cur[1] if M > N_links else None,
                                   other[0][: R * N_links].view(R, N_links), other[1] if M > N_links else None)
@@ -606,6 +617,9 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                 main.wait_event(drawn)
                 env.occupancy = occ[t]
                 env.step(None, compact_out=frame(t + 1), lean=True, after_core=mark_core(t), direct_insert=R <= 256)
+                if early:
+                    step_done[t] = torch.cuda.Event()
+                    step_done[t].record(main)
                 if env.time > EPISODE_END and t + 1 < n:
                     adapter.reset()
                     adapter.dynamic(out=frame(t + 1))

@@ -72,6 +72,8 @@ def test_clip_loss_kernel_matches_the_torch_formula_and_its_autograd(n):
         res = fn(lp, slp.cuda(), adv.cuda(), ent, v, tgt.cuda())
         total = res["loss"] if "loss" in res else res["loss_objective"] + res["loss_critic"] + res["loss_entropy"]
         (total * 1.7).backward()
+        if "impossible_frames" in res:
+            assert float(res["impossible_frames"]) == 0.0
         outs.append(({k: res[k].detach().cpu() for k in ("loss_objective", "loss_entropy", "loss_critic", "approx_kl",
                                                           "clip_fraction", "entropy")},
                      total.detach().cpu(), [x.grad.cpu() for x in (lp, ent, v)]))
@@ -83,6 +85,44 @@ def test_clip_loss_kernel_matches_the_torch_formula_and_its_autograd(n):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-9), name
     with pytest.raises(RuntimeError):
         P.clip_ppo_loss_device(lp0, slp, adv, ent0, v0, tgt)                     # CPU tensors: no fallback
+
+
+def test_clip_loss_kernel_leaves_impossible_frames_out_of_the_objective():
+    """A frame whose action selects no edge in some group carries -inf in BOTH log-probabilities (GraphDistribution's
+    marker, src/reinforcement_learning.py:82-93; about one draw in 10^7 — ten frames of a 128-replica grid100 rollout).
+    The torch formula makes its ratio NaN (and the next Adam step every parameter); the kernel treats it as a frame
+    with ratio 1 and advantage 0 — same scalars and gradients as the torch formula on such a frame — and counts it
+    (declared divergence D8). A -inf or NaN on ONE side only still propagates."""
+    from tarl_simulator_b200.rl import ppo_trainer as P
+    n, bad = 32, [5, 17]
+    g = torch.Generator().manual_seed(7)
+    slp = -torch.rand(n, generator=g) * 3
+    lp0 = slp + torch.randn(n, generator=g) * 0.3
+    adv, ent0 = torch.randn(n, generator=g), torch.rand(n, generator=g) * 2
+    tgt = torch.randn(n, generator=g) * 3
+    v0 = tgt + torch.randn(n, generator=g) * 1.5
+    lp_ref, slp_ref, adv_ref = lp0.clone(), slp.clone(), adv.clone()
+    lp_ref[bad] = 0.0; slp_ref[bad] = 0.0; adv_ref[bad] = 0.0
+    lp_dev, slp_dev = lp0.clone(), slp.clone()
+    lp_dev[bad] = float("-inf"); slp_dev[bad] = float("-inf")
+    assert not torch.isfinite(P.clip_ppo_loss(lp_dev, slp_dev, adv, ent0, v0, tgt)["loss_objective"])     # the formula: NaN
+    lp, ent, v = (x.clone().cuda().requires_grad_(True) for x in (lp_ref, ent0, v0))
+    ref = P.clip_ppo_loss(lp, slp_ref.cuda(), adv_ref.cuda(), ent, v, tgt.cuda())
+    (ref["loss_objective"] + ref["loss_critic"] + ref["loss_entropy"]).backward()
+    lp2, ent2, v2 = (x.clone().cuda().requires_grad_(True) for x in (lp_dev, ent0, v0))
+    our = P.clip_ppo_loss_device(lp2, slp_dev.cuda(), adv.cuda(), ent2, v2, tgt.cuda())
+    our["loss"].backward()
+    assert float(our["impossible_frames"]) == len(bad)
+    for k in ("loss_objective", "loss_entropy", "loss_critic", "approx_kl", "clip_fraction", "entropy"):
+        assert torch.allclose(our[k], ref[k].detach(), rtol=1e-5, atol=1e-7), k
+    for a, b in ((lp2, lp), (ent2, ent), (v2, v)):
+        assert torch.isfinite(a.grad).all() and torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-9)
+    assert float(lp2.grad[bad].abs().max()) == 0.0
+    one_sided = lp0.clone().cuda(); one_sided[3] = float("-inf")
+    res = P.clip_ppo_loss_device(one_sided, slp.cuda(), adv.cuda(), ent0.cuda(), v0.cuda(), tgt.cuda())
+    assert float(res["impossible_frames"]) == 0 and torch.isfinite(res["loss_objective"])   # exp(-inf) = 0: a legal ratio
+    nan_in = lp0.clone().cuda(); nan_in[3] = float("nan")
+    assert torch.isnan(P.clip_ppo_loss_device(nan_in, slp.cuda(), adv.cuda(), ent0.cuda(), v0.cuda(), tgt.cuda())["loss_objective"])
 
 
 def test_flat_adam_matches_torch_adam():
