@@ -757,10 +757,13 @@ def ppo_bench(args, dev, world, rank):
     # eagerly once, captured in a CUDA graph on its second run and replayed from then on)
     ppo_train(env, pm, vm, total_frames=3 * T, frames_per_batch=T, num_epochs=1, sub_batch_size=32)
     slim = occupancy_only(pm, vm)                         # what ppo_train itself passes for this pair of nets
-    roll_ms = timed(lambda: collect(adapter, pm, T, occupancy_only=slim))
+    # median of three each: an iteration starts with a few hundred microseconds of host work (optimiser state reset,
+    # generator) during which the device waits — on a single call that jitter is as large as the update itself
     hist = []
-    train_ms = timed(lambda: ppo_train(env, pm, vm, total_frames=T, frames_per_batch=T, num_epochs=1, sub_batch_size=32,
-                                       history=hist))
+    roll_all = sorted(timed(lambda: collect(adapter, pm, T, occupancy_only=slim)) for _ in range(3))
+    train_all = sorted(timed(lambda: ppo_train(env, pm, vm, total_frames=T, frames_per_batch=T, num_epochs=1,
+                                               sub_batch_size=32, history=hist)) for _ in range(3))
+    roll_ms, train_ms = roll_all[1], train_all[1]
     env.check_errors()
     n_params = sum(p.numel() for p in list(policy.parameters()) + list(value.parameters()) if p.requires_grad)
     in_sync = None
@@ -775,6 +778,8 @@ def ppo_bench(args, dev, world, rank):
             "rollout_ms": round(roll_ms, 2), "env_steps_per_s": round(total * T / (roll_ms / 1e3), 1),
             "link_steps_per_s": round(total * T * N / (roll_ms / 1e3), 1),
             "iteration_ms": round(train_ms, 2), "update_ms": round(max(train_ms - roll_ms, 0.0), 2),
+            "rollout_ms_all": [round(x, 2) for x in roll_all], "iteration_ms_all": [round(x, 2) for x in train_all],
+            "impossible_frames_in_minibatches": float(sum(h.get("impossible_frames", 0.0) for h in hist)),
             "allreduce_bytes_per_update": 4 * n_params if world > 1 else 0, "parameters_identical_across_ranks": in_sync,
             "inserted_agents_per_replica": float(env.counters[:, 0].float().mean()),
             "rollout_from_cuda_graph": any(e.get("graph") is not None for e in adapter._graphs.values()),

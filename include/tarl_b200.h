@@ -620,7 +620,7 @@ int tarl_standardise(float* advantage, int64_t n, const double* stats, void* str
  *           clip_fraction = mean(|ratio - 1| > clip), entropy = mean(entropy), number of impossible frames}.
  * An "impossible" frame is one whose log_prob AND sample_log_prob are both -inf — GraphDistribution.log_prob's marker
  * for an action that selects no edge in some group (src/reinforcement_learning.py:82-93), which sample() (:57-80)
- * produces about once in 10^7 draws. Its ratio exp(-inf - -inf) is NaN in the torch formula and poisons every
+ * produces about once in 10^8 draws. Its ratio exp(-inf - -inf) is NaN in the torch formula and poisons every
  * parameter at the next optimiser step; here it contributes nothing to the objective, approx_kl and clip_fraction
  * (zero gradient w.r.t. its log_prob), still counts in the critic and entropy terms and in every denominator (declared
  * divergence D8). Any other non-finite input propagates as in torch.

@@ -13,10 +13,10 @@ frm, to = synthetic.reorder_links(frm, to, "node")
 g, Nmax = synthetic.build_graph(frm, to, n_nodes)
 af = synthetic.population(g, 100_000, 21540, 600, seed=7)
 env = BatchedSimulatorEnv(g, Nmax, af, replicas=R, seed=100)
+torch.manual_seed(0)         # same initial policy and (below) the same noise keys in every run
 policy = MPNNPolicyNet(g.edge_index, g.x.size(0), None, "cuda")
 pm = PolicyModule(policy, g.edge_index)
 ad = _EnvAdapter.of(env)
-torch.manual_seed(0)         # the rollouts' noise keys come from torch's CPU generator: same draws in every run
 for _ in range(4):
     collect(ad, pm, 32, occupancy_only=True)
 torch.cuda.synchronize()
@@ -41,5 +41,7 @@ b = collect(ad, pm, 32, occupancy_only=True)
 torch.cuda.synchronize()
 env.check_errors()
 # same numbers whatever the schedule (TARL_ROLLOUT_DRAW_AT, TARL_ROLLOUT_SIDE_PRIORITY, TARL_NO_ROLLOUT_OVERLAP)
-print("checksum: num %.1f action %d log_prob %.6f reward %.1f" % (float(b["num"].double().sum()), int(b["action"].sum()),
-      float(b["sample_log_prob"].double().sum()), float(b["reward"].double().sum())))
+lp = b["sample_log_prob"]
+print("checksum: num %.1f action %d log_prob %.6f (+ %d impossible frames of %d) reward %.1f" % (
+      float(b["num"].double().sum()), int(b["action"].sum()), float(lp[torch.isfinite(lp)].double().sum()),
+      int((~torch.isfinite(lp)).sum()), lp.numel(), float(b["reward"].double().sum())))

@@ -135,17 +135,18 @@ __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __r
     for (int i = threadIdx.x; i < n; i += kLossThreads) {
         // GraphDistribution.log_prob marks an action that selects no edge in some group as impossible: -inf
         // (/root/reference/src/reinforcement_learning.py:82-93), and its sample() produces such an action whenever a
-        // group's uniform is not below the group's last cumulative probability (:57-80) — about one draw in 10^7. On the
+        // group's uniform is not below the group's last cumulative probability (:57-80) — about one draw in 10^8. On the
         // reference's test networks that never happens; over the 2.4 10^8 draws of one 128-replica grid100 rollout it
-        // happens about ten times, the frame's ratio exp(-inf - -inf) is NaN and one optimiser step later so is every
+        // happens a few times, the frame's ratio exp(-inf - -inf) is NaN and one optimiser step later so is every
         // parameter. Such a frame (BOTH log-probabilities -inf, nothing else) takes no part in the objective; it still
         // counts in the critic and entropy terms and in every mean's denominator; out[6] counts them.
         const bool impossible = (lp[i] == -INFINITY) && (lp_old[i] == -INFINITY);
         const float lw = impossible ? 0.0f : lp[i] - lp_old[i];
         const float ratio = expf(lw);
         const float a = impossible ? 0.0f : adv[i];
-        const float clamped = fminf(fmaxf(ratio, lo), hi);
+        const float clamped = ratio < lo ? lo : (ratio > hi ? hi : ratio);      // a NaN ratio stays NaN, as in torch.clamp
         const float g1 = ratio * a, g2 = clamped * a;
+        const float gmin = (g1 != g1 || g2 != g2) ? g1 + g2 : fminf(g1, g2);    // torch.minimum propagates NaN, fminf drops it
         const bool inside = (ratio >= lo) && (ratio <= hi);         // clamp passes the gradient on its closed interval
         // torch.minimum splits the gradient evenly on ties; g2's own derivative is ratio A inside the interval, 0 outside
         float w = 0.0f;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kLossThreads) k_ppo_clip_loss(const float* __r
         g_ent[i] = -ent_coef * inv_n;
         const float d = val[i] - tgt[i], ad = fabsf(d);
         g_val[i] = critic_coef * inv_n * (ad < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f));
-        acc[0] += (double)fminf(g1, g2);
+        acc[0] += (double)gmin;
         acc[1] += (double)ent[i];
         acc[2] += (double)(ad < 1.0f ? 0.5f * d * d : ad - 0.5f);
         acc[3] += (double)(-lw);

@@ -210,7 +210,7 @@ def clip_ppo_loss_device(log_prob, sample_log_prob, advantage, entropy, value, v
     respect to log_prob, entropy and value. Returns the same dict plus "loss" = loss_objective + loss_critic +
     loss_entropy, the only entry that carries a gradient (the reference differentiates exactly that sum,
     src/rl/ppo_trainer.py:136-139) — and "impossible_frames": how many frames of the minibatch carry GraphDistribution's
-    -inf marker in both log-probabilities (an action without an edge in some group, about one draw in 10^7). The torch
+    -inf marker in both log-probabilities (an action without an edge in some group, about one draw in 10^8). The torch
     formula turns such a frame into a NaN loss and, one Adam step later, NaN parameters; the kernel leaves it out of
     the objective (declared divergence D8, include/tarl_b200.h)."""
     if not log_prob.is_cuda:
@@ -370,9 +370,7 @@ class _EnvAdapter:
 
     def side_stream(self):
         if self._side is None:
-            # TARL_ROLLOUT_SIDE_PRIORITY=1 (tuning): the draws' CTAs are dispatched ahead of the main stream's
-            prio = -1 if os.environ.get("TARL_ROLLOUT_SIDE_PRIORITY") else 0
-            self._side = torch.cuda.Stream(self.device, priority=prio)
+            self._side = torch.cuda.Stream(self.device)
         return self._side
 
     def trajectory_buffers(self, T: int, slim: bool):
@@ -554,6 +552,9 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
     # step t-1, not next to its bandwidth-bound core step. At 128 replicas per GPU the
     # insertion kernels are chains of dependent loads that leave most of the device idle (43 + 20 us per step against
     # 42 + 4 us of sampling): measured 10.7 -> 9.6 ms per 32-step rollout. Captured as a fork / join inside the graph.
+    # (Releasing draw t one whole step earlier — when step t-2, the last reader of its pair, is through — and / or a
+    # high-priority side stream: 9.41 -> 9.43 ms, measured and dropped: the kernels' summed time, not the join, is
+    # what the rollout costs.)
     overlap = sink is not None and not os.environ.get("TARL_NO_ROLLOUT_OVERLAP") and n >= 2
 
     def draw(t):
@@ -587,10 +588,6 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
             env.sync_sel_pairs()
             side.wait_stream(main)
             core_done = [None] * n
-            step_done = [None] * n
-            # TARL_ROLLOUT_DRAW_AT=step (tuning): release draw t when step t-2 — the last reader of its pair — is
-            # through, i.e. next to the whole of step t-1 instead of next to its insertion only
-            early = os.environ.get("TARL_ROLLOUT_DRAW_AT") == "step"
 
             def mark_core(t):
                 def mark():
@@ -603,9 +600,7 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                 with torch.cuda.stream(side):
                     # not before the core step of step t-1 is through: that is when the device starts to idle (and
                     # step t-2, the last reader of this pair, finished long before)
-                    if early and t >= 2:
-                        side.wait_event(step_done[t - 2])
-                    elif not early and t >= 1:
+                    if t >= 1:
                         side.wait_event(core_done[t - 1])
                     sink.retarget(cur[0][: R * N_links].view(R, N_links), cur[1] if M > N_links else None,
                                   other[0][: R * N_links].view(R, N_links), other[1] if M > N_links else None)
@@ -617,9 +612,6 @@ def _collect_static_policy(adapter, policy_module, T, frame, buf, sink, break_wh
                 main.wait_event(drawn)
                 env.occupancy = occ[t]
                 env.step(None, compact_out=frame(t + 1), lean=True, after_core=mark_core(t), direct_insert=R <= 256)
-                if early:
-                    step_done[t] = torch.cuda.Event()
-                    step_done[t].record(main)
                 if env.time > EPISODE_END and t + 1 < n:
                     adapter.reset()
                     adapter.dynamic(out=frame(t + 1))

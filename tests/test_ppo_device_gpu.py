@@ -89,7 +89,7 @@ def test_clip_loss_kernel_matches_the_torch_formula_and_its_autograd(n):
 
 def test_clip_loss_kernel_leaves_impossible_frames_out_of_the_objective():
     """A frame whose action selects no edge in some group carries -inf in BOTH log-probabilities (GraphDistribution's
-    marker, src/reinforcement_learning.py:82-93; about one draw in 10^7 — ten frames of a 128-replica grid100 rollout).
+    marker, src/reinforcement_learning.py:82-93; about one draw in 10^8 — a few frames of a 128-replica grid100 rollout).
     The torch formula makes its ratio NaN (and the next Adam step every parameter); the kernel treats it as a frame
     with ratio 1 and advantage 0 — same scalars and gradients as the torch formula on such a frame — and counts it
     (declared divergence D8). A -inf or NaN on ONE side only still propagates."""
