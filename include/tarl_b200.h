@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TARL_ABI_VERSION 27
+#define TARL_ABI_VERSION 28
 
 /* return codes */
 #define TARL_OK 0
@@ -122,16 +122,22 @@ int tarl_core_step_phases(const tarl_dual_csr* g, float* x, int64_t x_row_stride
  * reference's row layout exactly (every cell of x, including what the reference leaves past the queue tails).
  * All buffers are caller-owned device memory; R replicas of the same network are stepped by one launch.
  * ------------------------------------------------------------------------------------------------------------- */
+#define TARL_STORE_UNIFORM_WEIGHTS 1
 typedef struct tarl_link_store {
     int32_t n_links;    /* N                                                                             */
     int32_t n_replicas; /* R >= 1: independent copies of the network state (PPO rollout environments)    */
     int32_t nmax;       /* Nmax (FIFO slots per link)                                                    */
-    int32_t reserved;
+    int32_t hints;      /* 0, or TARL_STORE_UNIFORM_WEIGHTS: the caller filled stat_a[.].w (see there)    */
     void* hot_cur;      /* [R*N] 32-byte records holding the CURRENT state: {head id, head exit, NUM, MAXN |
                            head arrival, tail id, pending tail-garbage exit time, meta}                   */
     void* hot_next;     /* [R*N] 32-byte records written by the step; the caller swaps the two afterwards */
     void* sel;          /* [R*N] fp32 SELECTED_ROAD                                                      */
-    void* stat_a;       /* [N] 16-byte {FFTT, congestion_constant, ROAD_INDEX, MAXN}                     */
+    void* stat_a;       /* [N] 16-byte {FFTT, congestion_constant, ROAD_INDEX, w}. w belongs to the caller:
+                           tarl_store_import leaves NaN there. With hints = TARL_STORE_UNIFORM_WEIGHTS it holds, per link
+                           (store slot), the edge_attr value shared by ALL in-edges of the link in the topology the
+                           step calls are given, or NaN where they differ: the ELL direction kernel then takes the
+                           weight from the 16 bytes it loads anyway and reads its edge-weight columns (16 of ~100
+                           bytes per link) only for the NaN links                                         */
     void* stat_b;       /* [N] 16-byte {LENGTH, MAX_FLOW, 0, 0} (export only)                            */
     void* queue;        /* [R*N*(nmax-1)] 16-byte ring slots {agent id, arrival, exit, pad}              */
     void* post;         /* [R*N] 8-byte scratch {NUM, tail id} handed from the direction to the response phase */

@@ -8,8 +8,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TARL_B200_LIB") or os.path.join(_HERE, "libtarl_b200.so")   # override: tuning builds only
 
 OK = 0
-ABI_VERSION = 27       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
+ABI_VERSION = 28       # TARL_ABI_VERSION of include/tarl_b200.h this binding was written against
 FLAG_ANY_POP, FLAG_ERROR, FLAG_COUNT = 0, 1, 4
+STORE_UNIFORM_WEIGHTS = 1      # TARL_STORE_UNIFORM_WEIGHTS
 ERR_QUEUE_RANGE, ERR_NO_WINNER, ERR_EMBED_RANGE, ERR_INSERT_TARGET, ERR_AGENT_RANGE = 1, 2, 4, 8, 16
 ACTION_U8, ACTION_I64, ACTION_F32 = 0, 1, 2
 ERR_TEXT = {
@@ -57,7 +58,7 @@ def rows(t):
 
 class LinkStore(C.Structure):
     """struct tarl_link_store"""
-    _fields_ = [("n_links", C.c_int32), ("n_replicas", C.c_int32), ("nmax", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_links", C.c_int32), ("n_replicas", C.c_int32), ("nmax", C.c_int32), ("hints", C.c_int32),
                 ("hot_cur", C.c_void_p), ("hot_next", C.c_void_p), ("sel", C.c_void_p), ("stat_a", C.c_void_p),
                 ("stat_b", C.c_void_p), ("queue", C.c_void_p), ("post", C.c_void_p), ("pop_hint", C.c_void_p),
                 ("slot_link", C.c_void_p), ("link_slot", C.c_void_p)]

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads) k_store_import(Store s, const float*
         float ccn;
         if (cc != nullptr) ccn = cc[link];
         else ccn = fftt * ((maxn + 10.0f) - (row[c0 + 4] * fftt) / 3600.0f);   // src/simulation_core_model.py:60-67
-        stat_a[n] = make_float4(fftt, ccn, row[c0 + 6], maxn);
+        stat_a[n] = make_float4(fftt, ccn, row[c0 + 6], __int_as_float(0x7fc00000));    // .w: the caller's hint, NaN = none
         stat_b[n] = make_float4(row[c0 + 3], row[c0 + 4], 0.0f, 0.0f);
     }
 }
@@ -313,8 +313,9 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
             if (i == -3) l2_prefetch_span(s.hot_cur, ((size_t)tl.r * s.N + tl.d0) * 32, tl.count * 32);
             else if (i == -2) l2_prefetch_span(s.stat_a, (size_t)tl.d0 * 16, tl.count * 16);
             else if (i == -1) l2_prefetch_span(s.sel, ((size_t)tl.r * s.N + tl.d0) * 4, tl.count * 4);
-            else l2_prefetch_span(i < W ? (const void*)ell.in_src : (const void*)ell.in_attr,
-                                  ((size_t)(i < W ? i : i - W) * ell.pitch + tl.d0) * 4, tl.count * 4);
+            else if (i < W || !s.uni_hint)       // (the edge-weight columns are read by a few links only under the hint)
+                l2_prefetch_span(i < W ? (const void*)ell.in_src : (const void*)ell.in_attr,
+                                 ((size_t)(i < W ? i : i - W) * ell.pitch + tl.d0) * 4, tl.count * 4);
         }
     }
     // level 1: everything addressed by the link id alone — the static part before the dependency wait
@@ -322,19 +323,24 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
     const float4 st = ld_static(&s.stat_a[d], strm);
     int u[W];
     float a[W];
+    // Edge weights. On the networks this path is measured on (edge_attr = 1 / out-degree on grids and ring-radials) the
+    // in-edges of nearly every link carry ONE weight: with the store's hint (stat_a.w, NaN where they differ) that is the
+    // float already loaded above, and the W-column read (16 of the kernel's ~100 bytes per link) is left to the few
+    // links whose weights differ — for them one load level later. Without the hint the columns are level-1 loads.
 #pragma unroll
     for (int j = 0; j < W; ++j) {
         u[j] = ld_static(&ell.in_src[(size_t)j * ell.pitch + d], strm);
-#ifdef TARL_ABLATE_ATTR         // tuning only (wrong results): what does the edge weight column cost?
-        a[j] = 0.25f;
-#else
-        a[j] = ld_static(&ell.in_attr[(size_t)j * ell.pitch + d], strm);
-#endif
+        a[j] = st.w;
+        if (!s.uni_hint) a[j] = ld_static(&ell.in_attr[(size_t)j * ell.pitch + d], strm);
     }
     pdl_wait();
     if (u[W - 1] == -2) {     // more than W in-edges or an unsafe weight: this link walks its CSR segment instead
         select_append_general<kExtNoise>(g, s, attr_in, nz, t, dtt_link, flags, r, d, L);
         return;
+    }
+    if (s.uni_hint && st.w != st.w) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) a[j] = ld_static(&ell.in_attr[(size_t)j * ell.pitch + d], strm);
     }
     float4 hA, hB;
     ld_record(&s.hot_cur[2 * (size_t)L], hA, hB, s.pol_state == kPolKeep);
@@ -663,6 +669,7 @@ int make_store(const tarl_link_store* p, Store* s) {
     s->stat_b = static_cast<const float4*>(p->stat_b);
     s->queue = static_cast<float4*>(p->queue);
     s->post = static_cast<float2*>(p->post);
+    s->uni_hint = (p->hints & TARL_STORE_UNIFORM_WEIGHTS) != 0;
     s->slot_link = p->slot_link;
     s->link_slot = p->link_slot;
     if ((p->slot_link == nullptr) != (p->link_slot == nullptr)) return TARL_E_BADARG;

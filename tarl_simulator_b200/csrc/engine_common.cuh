@@ -43,10 +43,12 @@ struct Store {
     const float4* hot_cur;   // [R*N*2]
     float4* hot_next;        // [R*N*2]
     float* sel;              // [R*N]
-    const float4* stat_a;    // [N] {FFTT, cc, ROAD_INDEX, MAXN}
+    const float4* stat_a;    // [N] {FFTT, cc, ROAD_INDEX, weight shared by all in-edges of the link or NaN (uni_hint)}
     const float4* stat_b;    // [N] {LENGTH, MAX_FLOW, 0, 0}
     float4* queue;           // [R*N*M]
     float2* post;            // [R*N] {NUM, tail id} after the direction phase
+    bool uni_hint;           // stat_a.w is filled in (TARL_STORE_UNIFORM_WEIGHTS): the ELL direction kernel reads it
+                             // instead of the link's edge-weight column
     const int32_t* slot_link;   // [N] slot -> link id (nullptr = identity): the store's own locality order
     const int32_t* link_slot;   // [N] link id -> slot
     int pol_state, pol_static;  // L2 eviction policy (kPol*) of the records / summaries and of topology + statics

@@ -8,6 +8,7 @@ state on the device between steps use (benchmarks, batched PPO rollouts); the pe
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,10 @@ class LinkStore:
         attr = edge_attr_routes.reshape(-1).to(torch.float32)
         self.attr_in = attr[self.topo.in_eid.long()].contiguous()        # edge_attr in CSR-by-target order
         self._ell = self.topo.ell(edge_attr_routes)                      # ELLPACK copy of the first W edges per link
+        # stat_a.w = the weight all in-edges of a link share (NaN where they differ), re-applied after every import:
+        # the direction kernel then skips the edge-weight column of those links. TARL_NO_UNIFORM_WEIGHTS=1 (tests,
+        # A/B measurements) leaves the hint off: same results, every link reads its column.
+        self.uniform_weights = not os.environ.get("TARL_NO_UNIFORM_WEIGHTS")
         L = self.N * self.R
         f32 = dict(dtype=torch.float32, device=dev)
         self.hot = [torch.zeros(max(L, 1), 8, **f32), torch.zeros(max(L, 1), 8, **f32)]
@@ -88,7 +93,8 @@ class LinkStore:
 
     def _fill_struct(self):
         s = self._struct
-        s.n_links, s.n_replicas, s.nmax, s.reserved = self.N, self.R, self.Nmax, 0
+        s.n_links, s.n_replicas, s.nmax = self.N, self.R, self.Nmax
+        s.hints = _cabi.STORE_UNIFORM_WEIGHTS if self.uniform_weights else 0
         s.hot_cur, s.hot_next = self.hot[self.cur].data_ptr(), self.hot[self.cur ^ 1].data_ptr()
         s.sel, s.stat_a, s.stat_b = self.sel.data_ptr(), self.stat_a.data_ptr(), self.stat_b.data_ptr()
         s.queue, s.post, s.pop_hint = self.queue.data_ptr(), self.post.data_ptr(), self.hint.data_ptr()
@@ -130,6 +136,8 @@ class LinkStore:
             rc = _cabi.lib().tarl_store_import(C.byref(self._struct), x.data_ptr(), row_stride, rep_stride, ccp,
                                                self.flags.data_ptr(), self._stream())
         _cabi.check(rc, "tarl_store_import")
+        if self.uniform_weights and self.N > 0:
+            self.stat_a[: self.N, 3] = self._ell[4][: self.N]
 
     def export_x(self, out: torch.Tensor | None = None) -> torch.Tensor:
         """The road rows exactly as the reference would hold them: [R, N, F] (or into `out`, [N,F] allowed if R==1)."""

@@ -87,10 +87,30 @@ class DualTopology:
                     0, self.dst32.long(), unsafe.long()) > 0)
             in_src[W - 1, :N][general] = -2
             out_dst[W - 1, :N][out_deg > W] = -2
+        # the weight shared by ALL in-edges of a link (bitwise equal), NaN where they differ: LinkStore parks it in
+        # stat_a.w (TARL_STORE_UNIFORM_WEIGHTS) and the direction kernel skips the link's edge-weight column. Links
+        # that walk their CSR segment never look at it; a link without in-edges never uses a weight (0).
+        uniform = torch.zeros(max(N, 1), dtype=torch.float32, device=dev)
+        if N and E:
+            uniform[:N] = uniform_in_weights(in_attr[:, :N], in_deg, general)
         struct = _cabi.DualELL(W, pitch, in_src.data_ptr(), in_attr.data_ptr(), out_dst.data_ptr())
-        pack = (struct, in_src, in_attr, out_dst)
+        pack = (struct, in_src, in_attr, out_dst, uniform)
         self._ell = (key, pack)
         return pack
+
+
+def uniform_in_weights(in_attr: torch.Tensor, in_deg: torch.Tensor, general: torch.Tensor) -> torch.Tensor:
+    """in_attr [W, N]: the ELL edge-weight columns (column j = weight of the link's j-th in-edge in ascending edge id),
+    in_deg [N], general [N] bool (links that walk their CSR segment). Returns fp32 [N]: the weight when every in-edge of
+    the link carries bitwise the same one, NaN when they differ or the link is general, 0 for a link without in-edges
+    (which never uses a weight). Plain torch: runs wherever the tensors live."""
+    W, N = in_attr.shape
+    first = in_attr[0].contiguous()
+    same = torch.ones(N, dtype=torch.bool, device=in_attr.device)
+    for j in range(1, W):
+        same &= (in_deg <= j) | (in_attr[j].contiguous().view(torch.int32) == first.view(torch.int32))
+    nan = torch.full_like(first, float("nan"))
+    return torch.where(in_deg == 0, torch.zeros_like(first), torch.where(same & ~general, first, nan))
 
 
 _CACHE: dict = {}

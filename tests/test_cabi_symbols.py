@@ -70,3 +70,23 @@ def test_compute_classes_refuse_cpu_tensors():
     g = Data(x=x, edge_index_routes=ei, edge_attr_routes=torch.ones(2, 1), num_roads=3)
     with pytest.raises(RuntimeError, match="CUDA"):
         SimulationCoreModel(Nmax=5, device="cpu", time=0)(g)
+
+
+def test_uniform_in_edge_weight_hint():
+    """topology.uniform_in_weights (what LinkStore parks in stat_a.w under TARL_STORE_UNIFORM_WEIGHTS): the weight when
+    all in-edges of a link carry bitwise the same one, NaN when they differ or the link walks its CSR segment, 0 for a
+    link without in-edges; -1 pads the unused ELL cells and must not take part in the comparison."""
+    import torch
+    from tarl_simulator_b200.topology import uniform_in_weights
+    cols = torch.tensor([[0.25, 0.5, -1.0, 0.25, 0.3, 1.0 / 3.0],
+                         [0.25, 0.25, -1.0, -1.0, 0.3, float(torch.tensor(1.0) / torch.tensor(3.0))],
+                         [0.25, -1.0, -1.0, -1.0, 0.3, 0.33333334],
+                         [0.25, -1.0, -1.0, -1.0, -2.0, -1.0]])
+    deg = torch.tensor([4, 2, 0, 1, 7, 3])
+    general = torch.tensor([False, False, False, False, True, False])
+    out = uniform_in_weights(cols, deg, general)
+    assert out[0] == 0.25 and torch.isnan(out[1]) and out[2] == 0.0 and out[3] == 0.25 and torch.isnan(out[4])
+    assert out[5] == cols[0, 5]                               # the same float written three ways
+    assert _cabi.STORE_UNIFORM_WEIGHTS == 1
+    text = open(os.path.join(ROOT, "include", "tarl_b200.h")).read()
+    assert re.search(r"#define\s+TARL_STORE_UNIFORM_WEIGHTS\s+1\b", text)

@@ -190,3 +190,34 @@ def test_store_run_equals_repeated_steps(variant):
     a.step(107.0, variant=variant); pa = a.step(108.0, variant=variant)
     assert torch.equal(a.export_x(), b.export_x()) and torch.equal(pa, more)
     a.check_errors(); b.check_errors()
+
+
+def test_uniform_weight_hint_changes_nothing_but_the_bytes_read(monkeypatch):
+    """stat_a.w = the weight shared by all in-edges of a link (TARL_STORE_UNIFORM_WEIGHTS): the ELL direction kernel
+    reads it instead of the link's edge-weight column. A store with the hint and one without (every link reads its
+    column, as before ABI 28) must stay bit-identical — in-kernel noise, so contested links draw Gumbel scores from the
+    weights — on a graph that has links of both kinds."""
+    g = torch.Generator().manual_seed(77)
+    N, Nmax, R = 6000, 15, 2
+    ei, w = cases.random_dual_graph(g, N, 4)
+    x0, _ = cases.random_road_state(g, N, Nmax, 100.0, ei)
+    bank = [torch.stack([cases.random_selection(g, N, ei) for _ in range(R)]).reshape(-1).cuda() for _ in range(3)]
+    a, _ = make_store(x0, ei, w, Nmax, True, replicas=R, seed=5)
+    monkeypatch.setenv("TARL_NO_UNIFORM_WEIGHTS", "1")
+    b, _ = make_store(x0, ei, w, Nmax, True, replicas=R, seed=5)
+    assert a.uniform_weights and not b.uniform_weights
+    hint = a.stat_a[:N, 3]
+    assert int(torch.isnan(hint).sum()) > N // 10 and int((hint > 0).sum()) > N // 10      # both kinds of links
+    assert bool(torch.isnan(b.stat_a[:N, 3]).all())                                       # import leaves NaN
+    E = ei.size(1)
+    da, db = torch.empty(R, E, device="cuda"), torch.empty(R, E, device="cuda")
+    for s in range(8):
+        for st in (a, b):
+            st.set_selected_road(bank[s % 3].view(R, N))
+        pa = a.step(100.0 + s, delta_tt=da).clone()
+        pb = b.step(100.0 + s, delta_tt=db)
+        assert torch.equal(pa, pb) and torch.equal(da, db), f"step {s}"
+    assert torch.equal(a.export_x(), b.export_x())
+    a.import_x(a.export_x())                                    # a re-import must not lose the hint
+    assert torch.equal(torch.nan_to_num(a.stat_a[:N, 3], nan=-1.0), torch.nan_to_num(hint, nan=-1.0))
+    a.check_errors(); b.check_errors()
