@@ -309,8 +309,15 @@ def run_native(args):
     sb = R * step_bytes(N, E, Nmax, p)
     # what this formulation has to move at the least: delta_tt is emitted per upstream LINK (4 N
     # instead of 4 E; the [E] form is materialised by whoever reads it)
-    moved = {"direction": N * 56 + 8 * E, "response": ph["response"]}
+    # (and with the uniform-weight hint in stat_a.w the direction kernel does not read its 4 B/edge weight column)
+    moved = {"direction": N * 56 + (4 if getattr(store, "uniform_weights", False) else 8) * E, "response": ph["response"]}
     traffic = measured_traffic(args.workload, R, dom)
+    per_kernel = {}
+    for k in names[:2]:
+        tr = measured_traffic(args.workload, R, k)
+        per_kernel[k] = {"ms": round(per[k], 4), "algorithmic_bytes": int(pb[k]),
+                         "achieved": round(pb[k] / (per[k] / 1e3) / 1e9, 1), "frac": round(pb[k] / (per[k] / 1e3) / 1e9 / peak, 4),
+                         "traffic": tr}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per launch)",
@@ -320,6 +327,7 @@ def run_native(args):
                                          "not counted), response 17 N + 4 E + p N (24 (Nmax-1) + 4)",
                 "kernel_ms": round(per[dom], 4),
                 "kernels_ms": {k: round(v, 4) for k, v in per.items()},
+                "per_kernel": per_kernel,
                 "kernels_ms_how": f"{names[0]}: {reps} launches captured in one CUDA graph, replayed between one CUDA-event "
                                   f"pair; {names[1]}: pipelined step time minus that",
                 "kernels_ms_event_pair_per_launch": {k: round(v, 4) for k, v in pairs.items()},
