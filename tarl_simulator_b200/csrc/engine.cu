@@ -129,6 +129,7 @@ struct Pick {
 // lone eligible edge needs no noise at all. Outside these bounds the literal scan over every in-edge runs.
 // The in-kernel Philox stream only produces uniforms inside the interval.
 constexpr float kSafeULo = 5.9604645e-08f, kSafeUHi = 0.99999994f, kSafeAttr = 1e-3f;
+constexpr float kClearGap = 1e-4f;     // see the uniform-weight race in k_ell_select_append
 
 __device__ __forceinline__ float philox_uniform(const Noise& nz, int L, int j, float (&un)[4], int& have_group) {
     if (have_group != (j >> 2)) {
@@ -397,6 +398,31 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
             float un[4] = {0.5f, 0.5f, 0.5f, 0.5f};
             uint32_t klo = 0u, khi = 0u;
             if (!kExtNoise) philox_key(nz, klo, khi);
+            // One weight w on every in-edge (the store's hint) and only eligible edges in the race: the scores are
+            // log(w + 1e-12) + g(u_j) with g(u) = -log(-log u) increasing, so the winner is the edge with the LARGEST
+            // UNIFORM — no logarithm needed, where the literal form spends three per edge and nearly every warp has a
+            // contested lane (the kernel had become issue-bound: 70 % issue utilisation, ~700 instructions per warp,
+            // of which ~300 were these logarithms). fp32 rounding can reorder scores only when they are closer than
+            // their evaluation error, < 5e-6 (1 ulp of each logf and of the sum, |score| < 32); g'(u) = 1 / (u (-ln u))
+            // >= e everywhere, so uniforms kClearGap = 1e-4 apart give scores >= 2.7e-4 apart: the order of the
+            // uniforms IS the order of the reference's fp32 scores. Closer than that (~1e-3 of the contested links, exact
+            // ties of the uniforms included) the literal scores below decide, strict '>' in ascending edge id.
+            bool decided = false;
+            if (safe && s.uni_hint && st.w == st.w) {
+                float m1 = -1.0f, m2 = -1.0f, id1 = 0.0f;
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    if (!kExtNoise && (j & 3) == 0)
+                        philox4x32_10((uint32_t)L, 0u, nz.step_id, (uint32_t)(j >> 2), klo, khi, un);
+                    if (u[j] >= 0 && p[j] > 0.0f) {
+                        const float uj = kExtNoise ? uu[j] : un[j & 3];
+                        if (uj > m1) { m2 = m1; m1 = uj; id1 = U[j].x; }
+                        else if (uj > m2) m2 = uj;
+                    }
+                }
+                if (m1 - m2 >= kClearGap) { pk.id = id1; pk.have = true; decided = true; }
+            }
+            if (!decided) {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
 #ifdef TARL_ABLATE_PHILOX       // tuning only (wrong results): what does the Philox draw cost?
@@ -409,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, W == 4 ? TARL_SELECT_MINBLOCKS : 1) 
                     const float sc = gumbel_score(p[j], kExtNoise ? uu[j] : un[j & 3]);
                     if (sc > best) { best = sc; pk.id = U[j].x; pk.have = true; }
                 }
+            }
             }
         }
     }
