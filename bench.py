@@ -373,7 +373,7 @@ def run_native(args):
     model.response_mpnn.update_history.resolve()
     assert model.last_path == "resident"
     windows, enqueue = [], []
-    for _ in range(5):
+    for _ in range(9):
         barrier()
         w0 = time.perf_counter()
         ev0.record(stream)
@@ -423,7 +423,7 @@ def run_native(args):
         e2e_ms, floor_ms = float(tms[0].item()), float(tms[1].item())
     e2e = {"value": round(N * world * e2e_steps / (e2e_ms / 1e3), 1), "unit": UNIT,
            "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 4 + words * 4),
-           "steps": e2e_steps, "windows_ms": [round(w, 3) for w in windows], "window": "median of 5",
+           "steps": e2e_steps, "windows_ms": [round(w, 3) for w in windows], "window": "median of 9",
            "host_enqueue_ms": [round(w, 3) for w in enqueue],
            "copies_alone": {"value": round(N * world * e2e_steps / (floor_ms / 1e3), 1), "unit": UNIT,
                             "ms": round(floor_ms, 3),
