@@ -172,3 +172,25 @@ def test_edge_mlp_port_matches_reference_modules(tag, which, golden_dir):
     for k, v in p.items():
         gref = torch.from_numpy(d[f"{tag}.grad.{k}"])            # sums over ~1e3 pairs with cancellation: atol scales with the tensor
         torch.testing.assert_close(v.grad, gref, rtol=1e-5, atol=1e-5 * max(1.0, float(gref.abs().max())))
+
+
+def test_largest_uniform_wins_the_gumbel_race_when_the_gap_is_clear():
+    """The premise of the direction kernel's logarithm-free pick (csrc/engine.cu, kClearGap): among edges that carry ONE
+    weight w, the oracle's fp32 score log(w + 1e-12) + (-log(-log u)) (oracle/core_port.py:79-80, src/direction_mpnn.py:
+    137-138) orders two edges exactly as their uniforms do whenever those are at least 1e-4 apart — checked on the
+    worst case, the nearest pair of the kernel's 2^-23 uniform grid that is still 1e-4 apart, for 4 M random positions
+    per weight. The smallest score gap must stay far above the evaluation error of a score (< 5e-6)."""
+    g = torch.Generator().manual_seed(3)
+    worst = 1.0
+    for w in (0.25, 1.0 / 3.0, 0.5, 1.0, 1e-3):
+        lpa = torch.log(torch.tensor(w, dtype=torch.float32) + 1e-12)
+        k = torch.randint(0, 2 ** 23, (4_000_000,), generator=g)
+        u1 = ((k.double() + 0.5) / 2 ** 23).float()
+        k2 = torch.floor((u1.double() - 1e-4) * 2 ** 23 - 0.5).long()
+        u2 = ((k2.clamp_min(0).double() + 0.5) / 2 ** 23).float()
+        ok = (k2 >= 0) & ((u1 - u2) >= 1e-4)                      # the kernel's own test, in fp32
+        s1 = lpa + (-torch.log(-torch.log(u1[ok])))
+        s2 = lpa + (-torch.log(-torch.log(u2[ok])))
+        assert int(ok.sum()) > 3_900_000 and bool((s1 > s2).all())
+        worst = min(worst, float((s1 - s2).min()))
+    assert worst > 2.5e-4                                        # e * 1e-4 = 2.7e-4 in exact arithmetic
