@@ -194,3 +194,41 @@ def test_largest_uniform_wins_the_gumbel_race_when_the_gap_is_clear():
         assert int(ok.sum()) > 3_900_000 and bool((s1 > s2).all())
         worst = min(worst, float((s1 - s2).min()))
     assert worst > 2.5e-4                                        # e * 1e-4 = 2.7e-4 in exact arithmetic
+
+
+def test_logarithm_free_pick_rule_equals_the_literal_arg_max():
+    """The decision rule of k_ell_select_append on links whose in-edges share one weight (csrc/engine.cu), restated in
+    torch: winner = eligible edge with the largest uniform when the two largest are >= 1e-4 apart, else the literal
+    fp32 scores with strict '>' in ascending edge id — against the oracle's literal arg-max over the eligible edges
+    (oracle/core_port.py:79-84) on 2 M random fan-ins of 2..4 eligible edges, with near-ties and exact ties of the
+    uniforms planted (the kernel's 2^-23 grid makes exact ties a one-in-10^7 event per pair)."""
+    g = torch.Generator().manual_seed(11)
+    n, W = 2_000_000, 4
+    k = torch.randint(0, 2 ** 23, (n, W), generator=g)
+    k[: n // 20, 1] = k[: n // 20, 0]                                         # exact ties: lowest edge id must win
+    k[n // 20: n // 10, 2] = (k[n // 20: n // 10, 0] + torch.randint(-400, 401, (n // 10 - n // 20,), generator=g)).clamp(0, 2 ** 23 - 1)
+    u = ((k.double() + 0.5) / 2 ** 23).float()                                # near ties: inside the 1e-4 gap
+    elig = torch.rand(n, W, generator=g) < 0.7
+    elig[:, 0] = True; elig[:, 1] |= ~elig[:, 1:].any(1)                       # at least two eligible edges
+    w = torch.tensor([0.25, 1.0 / 3.0, 0.5, 1.0])[torch.randint(0, 4, (n,), generator=g)].unsqueeze(1)
+    score = torch.log(w + 1e-12) + (-torch.log(-torch.log(u)))                # the oracle's fp32 scores
+    literal = torch.where(elig, score, torch.full_like(score, float("-inf"))).argmax(1)   # first maximum = lowest id
+    assert bool((torch.where(elig, score, torch.full_like(score, float("-inf"))).max(1).values > float("-inf")).all())
+    # torch.argmax returns the first of equal maxima on CPU; make that explicit
+    best = torch.full((n,), float("-inf")); lit = torch.zeros(n, dtype=torch.long)
+    for j in range(W):
+        better = elig[:, j] & (score[:, j] > best)
+        best = torch.where(better, score[:, j], best); lit = torch.where(better, torch.full_like(lit, j), lit)
+    assert torch.equal(lit, literal)
+    m1 = torch.full((n,), -1.0); m2 = torch.full((n,), -1.0); j1 = torch.zeros(n, dtype=torch.long)
+    for j in range(W):                                                        # the kernel's running two largest
+        uj = u[:, j]
+        top = elig[:, j] & (uj > m1)
+        second = elig[:, j] & ~top & (uj > m2)
+        m2 = torch.where(top, m1, torch.where(second, uj, m2))
+        j1 = torch.where(top, torch.full_like(j1, j), j1)
+        m1 = torch.where(top, uj, m1)
+    clear = (m1 - m2) >= 1e-4
+    rule = torch.where(clear, j1, lit)
+    assert torch.equal(rule, lit)
+    assert 0.02 < float((~clear).float().mean()) < 0.2                        # the planted ties took the literal path
